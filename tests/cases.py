@@ -1,0 +1,130 @@
+"""Shared, seeded input builders for the parity tests, the golden generator and bench.py.
+
+Every catalogue is a dict in the reference's own format (nwaylib/__init__.py:38-48):
+name, ra, dec (deg), error (arcsec), area (deg^2), mags, magnames, maghists.
+"""
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _cat(name, ra, dec, error, area, mags=(), magnames=(), maghists=()):
+	return dict(name=name, ra=ra, dec=dec, error=error, area=float(area),
+		mags=list(mags), magnames=list(magnames), maghists=list(maghists))
+
+
+def cosmos_subset(ncat=2, mags=False):
+	"""the reference's demo field (doc/COSMOS_{XMM,OPTICAL,IRAC}.fits) cut to what a 20 arcsec match can
+	reach; see oracle/make_golden.py.  mags=True attaches MAG / mag_ch1 with maghists=None ('auto')."""
+	z = np.load(os.path.join(GOLDEN_DIR, 'cosmos_subset.npz'))
+	out = []
+	for name, magname in (('XMM', None), ('OPT', 'MAG'), ('IRAC', 'mag_ch1'))[:ncat]:
+		t = _cat(name, z[name + '_ra'].copy(), z[name + '_dec'].copy(), z[name + '_error'].copy(), 2.0)
+		if mags and magname is not None:
+			t['mags'] = [z[name + '_mag'].copy()]
+			t['magnames'] = [magname]
+			t['maghists'] = [None]
+		out.append(t)
+	return out
+
+
+def uniform_patch(seed, counts, sigmas, side_deg, ra0=150.0, dec0=0.0, names='ABCDEFGH'):
+	"""uniform catalogues on a small square centred on (ra0+side/2, dec0): the flat-sky regime in which the
+	reference's own hash is complete, so its row set is comparable 1:1."""
+	rng = np.random.default_rng(seed)
+	out = []
+	for c, (n, s) in enumerate(zip(counts, sigmas)):
+		ra = ra0 + side_deg * rng.uniform(size=n)
+		dec = dec0 - side_deg / 2 + side_deg * rng.uniform(size=n)
+		out.append(_cat(names[c], ra, dec, s * np.ones(n), side_deg * side_deg))
+	return out
+
+
+def allsky(seed, counts, sigmas, names='ABCDEFGH'):
+	"""uniform on the sphere."""
+	rng = np.random.default_rng(seed)
+	out = []
+	for c, (n, s) in enumerate(zip(counts, sigmas)):
+		ra = 360 * rng.uniform(size=n)
+		dec = np.degrees(np.arcsin(2 * rng.uniform(size=n) - 1))
+		out.append(_cat(names[c], ra, dec, s * np.ones(n), 41252.96124941928))
+	return out
+
+
+def config_c3(scale=1.0, seed=20260301):
+	"""BASELINE.json configs[2]: 1e5 x 1e7 uniform on 1 deg^2, sigma 1.0 / 0.2 arcsec, r = 5 arcsec,
+	completeness 0.9 (generator of SURVEY.md 8d).  scale < 1 shrinks the AREA at fixed surface density, so a
+	sample has the same rows per primary as the full workload."""
+	rng = np.random.default_rng(seed)
+	side = np.sqrt(scale)
+	n0, n1 = int(round(1e5 * scale)), int(round(1e7 * scale))
+	prim = _cat('A', 150 + side * rng.uniform(size=n0), -side / 2 + side * rng.uniform(size=n0), 1.0 * np.ones(n0), scale)
+	sec = _cat('B', 150 + side * rng.uniform(size=n1), -side / 2 + side * rng.uniform(size=n1), 0.2 * np.ones(n1), scale)
+	return [prim, sec]
+
+
+def fixed_hist(seed, lo=16.0, hi=28.0, nbins=16):
+	"""a deterministic user-supplied magnitude prior (bins_lo, bins_hi, hist_sel, hist_all), with one empty
+	hist_all bin (-> ratio 100, magnitudeweights.py:23) and one empty hist_sel bin (-> weight -inf)."""
+	rng = np.random.default_rng(seed)
+	edges = np.linspace(lo, hi, nbins + 1)
+	hs = rng.uniform(0.01, 0.2, nbins)
+	ha = rng.uniform(0.01, 0.2, nbins)
+	ha[3] = 0.0
+	hs[nbins - 2] = 0.0
+	return edges[:-1], edges[1:], hs, ha
+
+
+def with_mags(tables, seed, cats=(1,), ncols=1, hist=True):
+	"""attach ~N(22,2) magnitudes with 1% -99 to the given catalogues."""
+	rng = np.random.default_rng(seed)
+	for c in cats:
+		t = tables[c]
+		n = len(t['ra'])
+		for k in range(ncols):
+			m = rng.normal(22, 2, n)
+			m[rng.uniform(size=n) < 0.01] = -99
+			t['mags'].append(m)
+			t['magnames'].append('m%d' % k)
+			t['maghists'].append(fixed_hist(seed + 17 * c + k) if hist else None)
+	return tables
+
+
+GOLDEN_CASES = {
+	# name: how to build + how to call.  Outputs of the REAL reference are stored in golden/ref_<name>.npz
+	'cosmos2': dict(radius=20, completeness=0.9),
+	'cosmos2_magradius': dict(radius=20, completeness=0.9, kwargs=dict(mag_include_radius=4.0)),
+	'cosmos3': dict(radius=20, completeness=0.9, stride=211),
+	'cosmos3_magauto': dict(radius=20, completeness=0.9, stride=211),
+	'syn2': dict(radius=5, completeness=0.9, stride=97),
+	'syn2_sparse': dict(radius=5, completeness=0.7, stride=3),
+	'syn2_maghist': dict(radius=5, completeness=0.9, stride=97),
+	'syn3': dict(radius=8, completeness=0.9, stride=151),
+	'syn3_pcvec': dict(radius=8, completeness=np.array([1.0, 0.8, 0.6]), stride=151, kwargs=dict(prob_ratio_secondary=0.1)),
+	'syn4': dict(radius=6, completeness=0.95, stride=199),
+	'syn4_minprob': dict(radius=6, completeness=0.95, stride=23, kwargs=dict(min_prob=0.01)),
+}
+
+
+def build_case(name):
+	if name == 'cosmos2':
+		return cosmos_subset(2)
+	if name == 'cosmos2_magradius':
+		return cosmos_subset(2, mags=True)
+	if name == 'cosmos3':
+		return cosmos_subset(3)
+	if name == 'cosmos3_magauto':
+		return cosmos_subset(3, mags=True)
+	if name == 'syn2':
+		return config_c3(scale=0.02)
+	if name == 'syn2_sparse':
+		return uniform_patch(11, (1000, 700), (2.0, 1.0), 1.0)
+	if name == 'syn2_maghist':
+		return with_mags(config_c3(scale=0.01, seed=7), 99, cats=(1,), ncols=2)
+	if name in ('syn3', 'syn3_pcvec'):
+		return uniform_patch(5, (500, 20000, 15000), (1.0, 0.3, 0.5), 0.1)
+	if name in ('syn4', 'syn4_minprob'):
+		return with_mags(uniform_patch(6, (200, 3000, 3000, 2500), (1.0, 0.4, 0.5, 0.8), 0.05), 3, cats=(2,), ncols=1)
+	raise KeyError(name)

@@ -1,0 +1,64 @@
+"""Column-wise parity metric, shared by the oracle and the CUDA tests.
+
+integer / index columns : exact
+prob_has_match (p_any)  : |d| <= 1e-10*|ref| + 4*2^-53    (absolute floor: p_any = 1 - 10^x cancels, fact 4)
+prob_this_match (p_i)   : |d| <= 1e-10*|ref| for ref >= 1e-30, |d| <= 1e-40 below
+dist_bayesfactor*       : |d| <= 1e-9 + 1e-12*|ref|
+separations             : |d| <= 1e-9 arcsec relative 1e-10
+dist_post, p_single, bias_* : relative 1e-10 above 1e-30
+"""
+import numpy as np
+
+RTOL = 1e-10
+
+
+def column_error(name, ref, got):
+	"""returns (ok, worst absolute error, worst relative error, index of worst)"""
+	ref = np.asarray(ref)
+	got = np.asarray(got)
+	assert ref.shape == got.shape, (name, ref.shape, got.shape)
+	if ref.size == 0:
+		return True, 0.0, 0.0, -1
+	if ref.dtype.kind in 'iub':
+		bad = ref != got
+		return (not bad.any()), float(bad.sum()), 0.0, int(np.argmax(bad))
+	nan_r, nan_g = np.isnan(ref), np.isnan(got)
+	if (nan_r != nan_g).any():
+		return False, np.inf, np.inf, int(np.argmax(nan_r != nan_g))
+	r = np.where(nan_r, 0.0, ref)
+	g = np.where(nan_g, 0.0, got)
+	same_inf = np.isinf(r) & (r == g)
+	r = np.where(same_inf, 0.0, r)
+	g = np.where(same_inf, 0.0, g)
+	with np.errstate(invalid='ignore'):
+		d = np.abs(r - g)
+		d = np.where(np.isnan(d), np.inf, d)
+	if name == 'prob_has_match':
+		tol = RTOL * np.abs(r) + 4 * 2.0 ** -53
+	elif name.startswith('dist_bayesfactor'):
+		tol = 1e-9 + 1e-12 * np.abs(r)
+	elif name.startswith('Separation'):
+		tol = 1e-9 + RTOL * np.abs(r)
+	else:
+		tol = np.where(np.abs(r) >= 1e-30, RTOL * np.abs(r), 1e-40)
+	worst = int(np.argmax(d - tol))
+	with np.errstate(divide='ignore', invalid='ignore'):
+		rel = np.where(r != 0, d / np.abs(r), 0.0)
+	return bool((d <= tol).all()), float(d.max()), float(rel[np.abs(r) >= 1e-30].max() if (np.abs(r) >= 1e-30).any() else 0.0), worst
+
+
+def assert_tables_match(ref, got, columns=None, context=''):
+	"""ref / got: mappings column -> array.  Row set and order must be identical; see module docstring."""
+	columns = columns or [c for c in ref.keys() if not c.startswith('_')]
+	report = []
+	failed = []
+	for c in columns:
+		assert c in got, '%s: column %s missing (have %s)' % (context, c, list(got.keys()))
+		a, b = np.asarray(ref[c]), np.asarray(got[c])
+		assert len(a) == len(b), '%s: column %s has %d rows, expected %d' % (context, c, len(b), len(a))
+		ok, dabs, drel, worst = column_error(c, a, b)
+		report.append('%-30s %s  max|d| %.3e  max rel %.3e' % (c, 'ok  ' if ok else 'FAIL', dabs, drel))
+		if not ok:
+			failed.append('%s: %s row %d ref %r got %r' % (context, c, worst, a[worst], b[worst]))
+	assert not failed, '\n'.join(failed + report)
+	return report
