@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- candidate associations / second of the nway match-probability path on B200.
+
+  python bench.py --gpus N --steps K --warmup W                 this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K --warmup W   the reference's CPU algorithm (oracle port)
+
+A "step" is one full pass of the hot path (grid -> stream secondaries -> lists -> rows + group normalisation)
+over the workload.  N = 1 workload: BASELINE.json configs[2] ("C3": 1e5 x 1e7 uniform on 1 deg^2, r = 5 arcsec,
+circular errors, fp64) -- the configuration BASELINE.md quotes the 1e9 associations/s target on; configs[1]
+(COSMOS 3-catalogue) needs the reference's FITS files, has 1797 primaries and is launch-latency bound, so it is
+a parity-test case (tests/golden), not a bench line.  N > 1: weak scaling -- every rank matches its own block
+of 1e5 primaries against the (replicated) 1e7 secondaries; the only exchange is an all-gather of the per-rank
+row counts (what is needed to place each shard in the global table).
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RADIUS = 5.0
+COMPLETENESS = 0.9
+N_PRIMARY = 100000
+N_SECONDARY = 10000000
+
+
+def make_workload(world, scale=1.0, seed=20260301):
+	"""C3 generator of SURVEY.md 8d; `world` blocks of primaries (weak scaling), secondaries shared."""
+	rng = np.random.default_rng(seed)
+	side = np.sqrt(scale)
+	n0, n1 = int(round(N_PRIMARY * scale)), int(round(N_SECONDARY * scale))
+	pra = 150 + side * rng.uniform(size=n0)
+	pdec = -side / 2 + side * rng.uniform(size=n0)
+	sra = 150 + side * rng.uniform(size=n1)
+	sdec = -side / 2 + side * rng.uniform(size=n1)
+	for r in range(1, world):   # further primary blocks, one per extra rank
+		rr = np.random.default_rng(seed + 1000 * r)
+		pra = np.concatenate((pra, 150 + side * rr.uniform(size=n0)))
+		pdec = np.concatenate((pdec, -side / 2 + side * rr.uniform(size=n0)))
+	prim = dict(name='A', ra=pra, dec=pdec, error=1.0 * np.ones(len(pra)), area=scale, mags=[], magnames=[], maghists=[])
+	sec = dict(name='B', ra=sra, dec=sdec, error=0.2 * np.ones(n1), area=scale, mags=[], magnames=[], maghists=[])
+	return [prim, sec], n0
+
+
+class ClockSampler(threading.Thread):
+	"""nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+	FIELDS = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+	def __init__(self, device):
+		threading.Thread.__init__(self, daemon=True)
+		self.device = device
+		self.samples = []
+		self.stop_flag = threading.Event()
+
+	def run(self):
+		while not self.stop_flag.is_set():
+			try:
+				out = subprocess.run(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.FIELDS,
+					'--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout.strip()
+				if out:
+					self.samples.append([x.strip() for x in out.split(',')])
+			except Exception:
+				pass
+			self.stop_flag.wait(0.1)
+
+	def summary(self):
+		if not self.samples:
+			return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+		sm = sorted(float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit())
+		reasons = set()
+		for s in self.samples:
+			for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[3:7]):
+				if v.lower().startswith('active'):
+					reasons.add(name)
+		return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.samples[0][1]) if self.samples[0][1].replace('.', '').isdigit() else None,
+			'power_w_max': max(float(s[2]) for s in self.samples if s[2].replace('.', '').isdigit()) if self.samples else None,
+			'reasons': sorted(reasons), 'samples': len(self.samples)}
+
+
+def hbm_peak():
+	path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+	if os.path.exists(path):
+		try:
+			return float(json.load(open(path))['hbm_gbs']), 'measured'
+		except Exception:
+			pass
+	return 6650.0, 'fallback'
+
+
+def cpu_port(scale, steps=1, warmup=0):
+	"""the reference's algorithm (oracle port, flat-sky hash + cartesian product + numpy scoring) on a bounded
+	sample of the workload: same surface densities, `scale` of the area.  Single-threaded, as the reference is."""
+	from oracle import nway_oracle as O
+	tables, _ = make_workload(1, scale=scale)
+	times, rows = [], 0
+	for k in range(warmup + steps):
+		t0 = time.perf_counter()
+		out = O.nway_match(tables, RADIUS, COMPLETENESS, enumerator='refhash')
+		dt = time.perf_counter() - t0
+		rows = len(out['A'])
+		if k >= warmup:
+			times.append(dt)
+	return rows, times
+
+
+def run_reference(args):
+	rank = int(os.environ.get('RANK', '0'))
+	if rank != 0:
+		return
+	scale = args.ref_scale
+	rows, times = cpu_port(scale, steps=args.steps, warmup=min(args.warmup, 1))
+	sec = sum(times) / len(times)
+	value = rows / sec
+	sample = 'C3 at %.4g of the area (%d x %d sources, same densities): %d rows per step in %.2f s' % (
+		scale, round(N_PRIMARY * scale), round(N_SECONDARY * scale), rows, sec)
+	line = {
+		'impl': 'reference', 'metric': 'candidate associations/sec', 'value': value, 'unit': 'associations/s',
+		'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+		'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+		'config': {'workload': 'C3 synthetic 2-cat 1e5 x 1e7 on 1 deg^2, r=5 arcsec (bounded sample)', 'sample_scale': scale,
+			'radius_arcsec': RADIUS, 'prior_completeness': COMPLETENESS},
+		'cpu_baseline': {'value': value, 'unit': 'associations/s', 'cores': 1, 'kind': 'port', 'sample': sample},
+		'e2e': {'value': value, 'unit': 'associations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+		'gpu_launches': 0,
+	}
+	print(json.dumps(line))
+
+
+def run_b200(args):
+	import torch
+	import torch.distributed as dist
+	import nway_b200
+	from nway_b200 import _lib
+
+	rank = int(os.environ.get('RANK', '0'))
+	world = int(os.environ.get('WORLD_SIZE', '1'))
+	local = int(os.environ.get('LOCAL_RANK', '0'))
+	if not torch.cuda.is_available():
+		raise SystemExit('bench.py: no CUDA device -- there is no CPU fallback for the product path')
+	torch.cuda.set_device(local)
+	dev = torch.device('cuda', local)
+	if world > 1:
+		dist.init_process_group('nccl', device_id=dev)
+
+	tables, n0 = make_workload(world, scale=args.scale)
+	ctx = _lib.Context(local)
+	stream = torch.cuda.current_stream()
+	ctx.set_stream(stream.cuda_stream)
+
+	# ---- inputs resident in HBM ------------------------------------------------------------------------
+	dev_arrays = []
+	for c, t in enumerate(tables):
+		ra = torch.from_numpy(np.ascontiguousarray(t['ra'])).to(dev)
+		dec = torch.from_numpy(np.ascontiguousarray(t['dec'])).to(dev)
+		err = torch.from_numpy(np.ascontiguousarray(t['error'], dtype=np.float64)).to(dev)
+		dev_arrays.append((ra, dec, err))
+		ctx.set_catalogue_device(c, len(tables), len(t['ra']), ra.data_ptr(), dec.data_ptr(), err.data_ptr(), t['area'])
+	tab = nway_b200._scalar_tables(tables, COMPLETENESS, nway_b200.NullOutputLogger())
+	ctx.set_params(RADIUS, tab['pc'], 0.5, _lib.UNRELATED_API)
+	ctx.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
+	ctx.set_primary_range(rank * n0, n0)
+	counts = torch.zeros(world, dtype=torch.int64, device=dev)
+	mine = torch.zeros(1, dtype=torch.int64, device=dev)
+
+	def step():
+		rows = ctx.match(fuse_final=True)
+		if world > 1:
+			mine[0] = rows
+			dist.all_gather_into_tensor(counts, mine)
+		return rows
+
+	def barrier():
+		if world > 1:
+			dist.barrier()
+		torch.cuda.synchronize()
+
+	for _ in range(max(args.warmup, 3)):
+		rows = step()
+	barrier()
+	sampler = ClockSampler(local)
+	if rank == 0:
+		sampler.start()
+	acc = {k: 0.0 for k in _lib.STAGE_NAMES}
+	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	barrier()
+	e0.record(stream)
+	for _ in range(args.steps):
+		rows = step()
+		for k, v in ctx.timings().items():
+			acc[k] += v
+	e1.record(stream)
+	barrier()
+	ms_step = e0.elapsed_time(e1) / args.steps
+	sampler.stop_flag.set()
+	launches = ctx.launch_count() * args.steps
+	stats = ctx.stats()
+
+	t = torch.tensor([ms_step], dtype=torch.float64, device=dev)
+	r = torch.tensor([rows], dtype=torch.int64, device=dev)
+	if world > 1:
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		dist.all_reduce(r, op=dist.ReduceOp.SUM)
+	ms_step_max = float(t.item())
+	total_rows = int(r.item())
+	value = total_rows / (ms_step_max * 1e-3)
+
+	# ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ------------------------------
+	names = [tables[0]['name'], tables[1]['name']]
+	host_in = []
+	for c, tb in enumerate(tables):
+		if c == 0:
+			sl = slice(rank * n0, (rank + 1) * n0)
+		else:
+			sl = slice(None)
+		arrs = [torch.from_numpy(np.ascontiguousarray(np.asarray(tb[k], dtype=np.float64)[sl])).pin_memory() for k in ('ra', 'dec', 'error')]
+		host_in.append(arrs)
+	colsel = [_lib.COL_IDX, _lib.COL_IDX + 1, _lib.COL_SEP, _lib.COL_SEPMAX, _lib.COL_NCAT, _lib.COL_LOGBF_UNCORR, _lib.COL_LOGBF,
+		_lib.COL_DIST_POST, _lib.COL_P_SINGLE, _lib.COL_MATCH_FLAG, _lib.COL_P_ANY, _lib.COL_P_I]
+	host_out = [torch.empty(rows + 1024, dtype=torch.float64).pin_memory() for _ in colsel]
+	ctx2 = ctx
+	ctx2.set_primary_range(0, n0)
+	h2d = sum(a.numel() * 8 for arrs in host_in for a in arrs)
+	d2h = rows * 8 * len(colsel)
+
+	def e2e_step():
+		for c, arrs in enumerate(host_in):
+			n = arrs[0].numel()
+			ctx2.check(ctx2.lib.nwb_set_catalogue(ctx2.h, c, 2, n, arrs[0].data_ptr(), arrs[1].data_ptr(), arrs[2].data_ptr(),
+				_lib.ERR_CIRCULAR, None, 0, float(tables[c]['area']), 0))
+		ctx2.set_params(RADIUS, tab['pc'], 0.5, _lib.UNRELATED_API)
+		# the densities belong to the whole catalogue (world blocks of primaries): keep the tables of the resident run
+		ctx2.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
+		nr = ctx2.match(fuse_final=True)
+		for sel, buf in zip(colsel, host_out):
+			ctx2.check(ctx2.lib.nwb_fetch(ctx2.h, sel, buf.data_ptr()))
+		ctx2.sync()
+		return nr
+
+	e2e_steps = max(3, min(args.steps, 10))
+	e2e_step()
+	e2e_step()
+	barrier()
+	t0 = time.perf_counter()
+	for _ in range(e2e_steps):
+		nr = e2e_step()
+	barrier()
+	e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+	assert nr == rows
+	t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+	if world > 1:
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+	e2e_value = total_rows / (float(t.item()) * 1e-3)
+	# a cheap sanity check of what came back (the parity tests do the real checking)
+	p_any = host_out[10][:rows].numpy()
+	assert np.isfinite(p_any).all() and (p_any >= -1e-12).all() and (p_any <= 1 + 1e-12).all()
+
+	if rank != 0:
+		if world > 1:
+			dist.destroy_process_group()
+		return
+
+	# ---- roofline of the dominant kernel ---------------------------------------------------------------
+	peak, peak_kind = hbm_peak()
+	k_pairs_ms = acc['k_pairs'] / args.steps
+	k_rows_ms = acc['k_rows'] / args.steps
+	n1 = len(tables[1]['ra'])
+	pairs = stats['pairs_kept']
+	ncols = 12
+	bytes_pairs = n1 * 16 + pairs * 16                 # (ra, dec) of every secondary read once + pair records written
+	bytes_rows = rows * 8 * ncols + pairs * 12 + n0 * 24  # output columns + sorted lists read + primary (err, offsets)
+	if k_rows_ms >= k_pairs_ms:
+		kname, kms, kbytes = 'k_rows<2,fused>', k_rows_ms, bytes_rows
+	else:
+		kname, kms, kbytes = 'k_pairs', k_pairs_ms, bytes_pairs
+	achieved = kbytes / (kms * 1e-3) / 1e9
+	b_alg = sum(len(tb['ra']) for tb in tables[1:]) * 24 + n0 * 24 + rows * 8 * ncols   # B_in + R * B_row
+	roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+		'peak_kind': peak_kind, 'traffic': None, 'kernel_ms': kms, 'algorithmic_bytes': kbytes,
+		'other_kernel': {'k_pairs_ms': k_pairs_ms, 'k_pairs_GBs': bytes_pairs / (k_pairs_ms * 1e-3) / 1e9,
+			'k_rows_ms': k_rows_ms, 'k_rows_GBs': bytes_rows / (k_rows_ms * 1e-3) / 1e9},
+		'pipeline': {'B_alg_bytes': b_alg, 'GBs': b_alg / (ms_step_max * 1e-3) / 1e9, 'frac': b_alg / (ms_step_max * 1e-3) / 1e9 / peak}}
+	ncu_traffic = os.path.join(ROOT, 'profiles', 'traffic.json')
+	if os.path.exists(ncu_traffic):
+		try:
+			roofline['traffic'] = json.load(open(ncu_traffic)).get(kname.split('<')[0])
+		except Exception:
+			pass
+
+	cpu = None
+	if world == 1 and not args.no_cpu:
+		crow, ctimes = cpu_port(args.cpu_scale)
+		cpu = {'value': crow / ctimes[0], 'unit': 'associations/s', 'cores': 1, 'kind': 'port',
+			'sample': 'C3 at %.4g of the area (%d x %d sources, same densities), %d rows in %.1f s; oracle port of the reference algorithm (flat-sky hash + product + numpy scoring), single-threaded like the reference' % (
+				args.cpu_scale, round(N_PRIMARY * args.cpu_scale), round(N_SECONDARY * args.cpu_scale), crow, ctimes[0])}
+
+	line = {
+		'metric': 'candidate associations/sec', 'value': value, 'unit': 'associations/s', 'n_gpus': world,
+		'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step_max, 'higher_is_better': True,
+		'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+		'config': {'workload': 'C3 (BASELINE.json configs[2]): synthetic 2-cat, %d primaries per GPU x %d secondaries uniform on %.3g deg^2, r=5 arcsec, circular errors' % (n0, n1, args.scale),
+			'rows_per_gpu': rows, 'pairs_per_gpu': pairs, 'radius_arcsec': RADIUS, 'prior_completeness': COMPLETENESS,
+			'parallelism': 'primary rows sharded, %d rank(s); secondaries replicated; exchange = all-gather of row counts' % world,
+			'l2': 'inputs (%.0f MB) and outputs (%.0f MB) per step exceed the 126 MB L2; no explicit flush' % (h2d / 1e6, d2h / 1e6),
+			'stage_ms': {k: acc[k] / args.steps for k in acc}, 'grid': stats},
+		'roofline': roofline,
+		'cpu_baseline': cpu,
+		'e2e': {'value': e2e_value, 'unit': 'associations/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': float(t.item())},
+		'gpu_launches': launches,
+		'clocks': sampler.summary(),
+	}
+	print(json.dumps(line))
+	if world > 1:
+		dist.destroy_process_group()
+
+
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument('--gpus', type=int, default=1)
+	ap.add_argument('--steps', type=int, default=20)
+	ap.add_argument('--warmup', type=int, default=3)
+	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+	ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C3 area (same densities); 1.0 = the named workload')
+	ap.add_argument('--cpu-scale', type=float, default=0.2, help='sample of the workload the CPU baseline is timed on')
+	ap.add_argument('--ref-scale', type=float, default=0.05, help='sample per step of --impl reference')
+	ap.add_argument('--no-cpu', action='store_true')
+	args = ap.parse_args()
+	if args.impl == 'reference':
+		run_reference(args)
+	else:
+		run_b200(args)
+
+
+if __name__ == '__main__':
+	main()

@@ -1,0 +1,152 @@
+/*
+ * nwayb200.h -- C ABI of the B200-native nway match-probability path.
+ *
+ * The reference (JohannesBuchner/nway 4.7.1) is pure Python and has no FFI of its own; the boundary it
+ * offers is the Python function nwaylib.nway_match() (nwaylib/__init__.py:31-120).  This library is what a
+ * ctypes binding of that function's numeric stages binds to: every entry point below names the reference
+ * stage it replaces.  Plain pointers and sizes only; the caller owns every buffer it passes in; nothing is
+ * retained past a call except device copies held inside the opaque context.  No exceptions, no exit():
+ * every function returns 0 on success or a negative nwb_status; nwb_last_error() gives the text.
+ *
+ * Threading: one context per (process, device); calls on one context must be serialised by the caller;
+ * different contexts are independent.  All work of a context runs on one private CUDA stream.
+ *
+ * Units follow the reference: ra/dec in degrees, positional errors and radii in arcsec, areas in deg^2.
+ */
+#ifndef NWAYB200_H
+#define NWAYB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nwb_ctx nwb_ctx;
+
+enum nwb_status {
+	NWB_OK = 0,
+	NWB_ERR_CUDA = -1,        /* a CUDA runtime call failed (text has the CUDA error string) */
+	NWB_ERR_ARG = -2,         /* invalid argument / call order */
+	NWB_ERR_EMPTY = -3,       /* no rows: maps to nwaylib.EmptyResultException (__init__.py:92-93) */
+	NWB_ERR_NOMEM = -4,
+	NWB_ERR_STATE = -5        /* results requested before nwb_match / nwb_finalize ran */
+};
+
+enum { NWB_MAX_CATS = 8, NWB_MAX_MAGS = 8, NWB_MAX_BINS = 64 };
+
+/* error kinds for nwb_set_catalogue */
+enum { NWB_ERR_CIRCULAR = 1,   /* err = n sigma values (arcsec)                 -> bayesdistance.log_bf           */
+       NWB_ERR_ELLIPSE = 3 };  /* err = 3 columns of n: sigma_x, sigma_y, rho   -> bayesdistance.log_bf_elliptical */
+
+/* unrelated-association correction */
+enum { NWB_UNRELATED_API = 0,  /* nwaylib/__init__.py:262-301: inert in the reference -> no change */
+       NWB_UNRELATED_CLI = 1 };/* nway.py:366-421: the live algorithm                                              */
+
+/* stages for nwb_timing (device milliseconds of the last run, CUDA events on the context's stream) */
+enum { NWB_T_GRID = 0,      /* primary prep + cell lists                       fastskymatch.py:119-133            */
+       NWB_T_PAIRS = 1,     /* stream secondaries, exact separations, append   fastskymatch.py:134-160, 26-47     */
+       NWB_T_LISTS = 2,     /* scan + scatter + per-primary sort               fastskymatch.py:178-181,217        */
+       NWB_T_ROWS = 3,      /* enumerate + score (+ fused finalize)            __init__.py:123-259                */
+       NWB_T_FINAL = 4,     /* bias lookup, p_single, group log-sum-exp        __init__.py:376-461                */
+       NWB_T_TOTAL = 5,
+       NWB_T_KPAIRS = 6,    /* k_pairs launches alone (summed over the secondary catalogues)                      */
+       NWB_T_KROWS = 7,     /* the k_rows launch alone                                                            */
+       NWB_T_COUNT = 8 };
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+
+int nwb_create(int device, nwb_ctx **out);
+void nwb_destroy(nwb_ctx *ctx);
+const char *nwb_last_error(nwb_ctx *ctx);   /* ctx may be NULL: error of the last failed nwb_create */
+int nwb_version(void);
+/* run all work of this context on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)
+ * instead of the private one; stream == NULL restores the private stream. */
+int nwb_set_stream(nwb_ctx *ctx, void *cuda_stream);
+
+/* ---- inputs -------------------------------------------------------------------------------------------- */
+
+/* Catalogue c of ncat (c = 0 is the primary).  Replaces the match_tables[c] dict of nway_match
+ * (__init__.py:38-48).  mags: m columns of n values, column after column; NaN or -99 = undefined
+ * (__init__.py:319,384).  on_device != 0: the pointers are device pointers on the context's device and are
+ * used in place (they must stay valid until the next nwb_set_catalogue for c or nwb_destroy); otherwise
+ * they are host pointers and are copied (pinned host memory makes the copy asynchronous DMA). */
+int nwb_set_catalogue(nwb_ctx *ctx, int c, int ncat, int64_t n, const double *ra, const double *dec,
+	const double *err, int err_kind, const double *mags, int m, double area, int on_device);
+
+/* Scalars of nway_match (__init__.py:31-36).  completeness: ncat values, [0] == 1 (__init__.py:224-229,
+ * already expanded by the caller if scalar). */
+int nwb_set_params(nwb_ctx *ctx, double match_radius_arcsec, const double *completeness,
+	double prob_ratio_secondary, int unrelated_mode);
+
+/* Optional: the scalar tables the kernels consume, computed by the caller with the reference's own numpy
+ * expressions (so they are bit-identical to what nwaylib computes on that host).  If not called, the library
+ * derives the same tables itself in C double arithmetic.  norm: ncat+1 values indexed by the number of present
+ * catalogues (bayesdistance.py:76); prior / log10prior: 2^(ncat-1) values indexed by the presence mask of the
+ * secondaries, bit c-1 (__init__.py:254, bayesdistance.py:32,39); sub_log10prior: log10(nu[A0]/prod nu_plus[A])
+ * for the CLI correction (nway.py:395). */
+int nwb_set_tables(nwb_ctx *ctx, const double *norm, double log10e, const double *prior,
+	const double *log10prior, const double *sub_log10prior);
+
+/* Magnitude prior k of catalogue c as a step function (magnitudeweights.py:74-87): nbins+1 ascending edges,
+ * and per bin the weight log10(ratio) (__init__.py:386) and the bias column value 10**weight (__init__.py:392).
+ * The host computes both with the reference's own expressions so the table is bit-identical. */
+int nwb_set_maghist(nwb_ctx *ctx, int c, int k, int nbins, const double *edges, const double *weight,
+	const double *bias);
+
+/* Shard: only primaries [first, first+count) are matched by this context.  Row indices in the
+ * output stay global.  Default: all. */
+int nwb_set_primary_range(nwb_ctx *ctx, int64_t first, int64_t count);
+
+/* ---- the path ------------------------------------------------------------------------------------------ */
+
+/* H1+H2+H3: bin, enumerate, separations, radius filter, log Bayes factor, prior, dist_post
+ * (fastskymatch.crossproduct + __init__._create_match_table + _compute_single_log_bf + posterior).
+ * fuse_final != 0 also runs nwb_finalize's work inside the row kernel (allowed when every magnitude prior is
+ * already set, i.e. no 'auto' histogram has to be built from dist_post on the host in between).
+ * nrows receives R.  Rows stay in device memory. */
+int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows);
+
+/* H3b+H4: magnitude bias lookup, p_single, per-primary log-sum-exp -> prob_has_match, prob_this_match,
+ * match_flag (__init__._apply_magnitude_biasing lookup half + _compute_final_probabilities). */
+int nwb_finalize(nwb_ctx *ctx);
+
+/* a13 _truncate_table (__init__.py:464-471): keep rows with !(p_i < min_prob); compacts the device table in
+ * place and returns the new row count. */
+int nwb_truncate(nwb_ctx *ctx, double min_prob, int64_t *nrows);
+
+/* ---- outputs ------------------------------------------------------------------------------------------- */
+
+/* Column selectors for nwb_fetch / nwb_column_ptr.  Index columns: NWB_COL_IDX + c.  Separation of catalogues
+ * a < b: NWB_COL_SEP + pair(a,b), pairs numbered (0,1),(0,2),...,(1,2),... as _create_match_table emits them.
+ * Bias columns: NWB_COL_BIAS + j, j numbering the (catalogue, mag) pairs in catalogue order. */
+enum { NWB_COL_IDX = 0, NWB_COL_SEP = 100, NWB_COL_BIAS = 200,
+       NWB_COL_SEPMAX = 300, NWB_COL_NCAT = 301, NWB_COL_LOGBF_UNCORR = 302, NWB_COL_LOGBF = 303,
+       NWB_COL_DIST_POST = 304, NWB_COL_P_SINGLE = 305, NWB_COL_MATCH_FLAG = 306, NWB_COL_P_ANY = 307,
+       NWB_COL_P_I = 308 };
+
+/* copy one column of the last result (R values of 8 bytes: int64 for IDX/NCAT/MATCH_FLAG, double otherwise)
+ * to host memory; asynchronous on the context's stream when dst is pinned -- call nwb_sync() before reading. */
+int nwb_fetch(nwb_ctx *ctx, int column, void *dst_host);
+/* device address of a column (valid until the next nwb_match on this context) */
+int nwb_column_ptr(nwb_ctx *ctx, int column, void **dev_ptr);
+int nwb_sync(nwb_ctx *ctx);
+
+/* per-stage device time of the last nwb_match (+ nwb_finalize), and how many kernels it launched */
+int nwb_timing(nwb_ctx *ctx, int stage, float *ms);
+int nwb_launch_count(nwb_ctx *ctx, int64_t *launches);
+/* counters of the last run: [0] pairs tested exactly, [1] pairs kept, [2] grid cells, [3] cell entries */
+int nwb_stats(nwb_ctx *ctx, int64_t *out4);
+
+/* ---- element-wise surface (fastskymatch.dist, bayesdistance.log_bf / posterior) --------------------------
+ * host pointers, n elements; used by the thin Python mirrors of those functions. */
+int nwb_dist(nwb_ctx *ctx, int64_t n, const double *ra1, const double *dec1, const double *ra2,
+	const double *dec2, double *out_deg);                        /* fastskymatch.py:26-47 */
+int nwb_log_bf(nwb_ctx *ctx, int64_t n, int ncat, const double *sep /* ncat*ncat blocks of n, only i<j read */,
+	const double *err /* ncat blocks of n */, double *out);     /* bayesdistance.py:64-86 */
+int nwb_posterior(nwb_ctx *ctx, int64_t n, const double *prior, const double *log_bf, double *out); /* :26-32 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,212 @@
+"""nway_b200 -- B200-native implementation of nway's match-probability path.
+
+Drop-in for nwaylib.nway_match() (reference nwaylib/__init__.py:31-120): same arguments, same output columns,
+computed by hand-written sm_100a CUDA kernels behind the C ABI of include/nwayb200.h.  There is no CPU path:
+without the built library and a CUDA device, calls raise.
+"""
+from collections import OrderedDict
+
+import numpy
+from numpy import log10, pi
+
+from . import _lib
+from . import magnitudeweights
+from .logger import NormalLogger, NullOutputLogger
+
+__version__ = '0.1.0'
+
+
+class UndersampledException(Exception):
+	pass
+
+
+class EmptyResultException(Exception):
+	pass
+
+
+default_logger = NormalLogger()
+
+
+def _scalar_tables(match_tables, prior_completeness, logger):
+	"""host scalars feeding the kernels, with the reference's expressions: source densities
+	(__init__.py:199-217), completeness vector (:224-229), prior per presence pattern (:254), the Bayes-factor
+	normalisation (bayesdistance.py:15,76) and the CLI sub-association prior (nway.py:395)."""
+	ncats = len(match_tables)
+	source_densities = []
+	source_densities_plus = []
+	area_total = (4 * pi * (180 / pi)**2)
+	for i, t in enumerate(match_tables):
+		n = len(t['ra'])
+		area = t['area'] * 1.0
+		density = n / area * area_total
+		logger.log('%s "%s" (%d), density gives %.2e objects on entire sky' % ('Primary catalogue' if i == 0 else 'Catalogue', t['name'], n, density))
+		source_densities.append(density)
+		source_densities_plus.append((n + 1) / area * area_total)
+	source_densities_plus[0] = source_densities[0]
+	source_densities = numpy.array(source_densities)
+	source_densities_plus = numpy.array(source_densities_plus)
+
+	if numpy.shape(prior_completeness) == ():
+		prior_completeness = numpy.array([1.0] + [float(prior_completeness)**(1. / (ncats - 1)) for i in range(1, ncats)])
+	prior_completeness = numpy.asarray(prior_completeness, dtype=float)
+	if len(prior_completeness) != ncats:
+		raise Exception('Prior completeness needs one value per catalog. Received "%s".' % prior_completeness)
+	assert prior_completeness[0] == 1.0
+
+	nmask = 2**(ncats - 1)
+	prior = numpy.empty(nmask)
+	sub = numpy.ones(nmask)
+	for mask in range(nmask):
+		table_mask = numpy.array([True] + [(mask >> (c - 1)) & 1 == 1 for c in range(1, ncats)])
+		prior[mask] = source_densities[0] * numpy.prod(prior_completeness[table_mask]) / numpy.prod(source_densities_plus[table_mask])
+		aug = [c for c in range(1, ncats) if (mask >> (c - 1)) & 1]
+		if aug:
+			sub[mask] = source_densities[aug[0]] / numpy.prod(source_densities_plus[aug])
+	assert numpy.isfinite(prior).all(), (source_densities, prior_completeness, source_densities_plus)
+	log_arcsec2rad = numpy.log(3600 * 180 / pi)
+	norm = numpy.array([(n - 1) * numpy.log(2) + 2 * (n - 1) * log_arcsec2rad for n in range(ncats + 1)])
+	return dict(pc=prior_completeness, norm=norm, log10e=float(log10(numpy.e)), prior=prior, log10prior=log10(prior),
+		sub_log10prior=log10(sub))
+
+
+def _column_names(match_tables):
+	names = [t['name'] for t in match_tables]
+	n = len(names)
+	seps = ['Separation_%s_%s' % (names[a], names[b]) for a in range(n) for b in range(a + 1, n)]
+	biases = ['bias_%s_%s' % (t['name'], magname) for t in match_tables for magname in t.get('magnames', [])]
+	return names, seps, biases
+
+
+def _fetch_table(ctx, match_tables, nrows):
+	"""device columns -> OrderedDict of numpy arrays in the reference's column order (__init__.py:131-196,
+	100-103,111,392,405,415-419)"""
+	L = _lib
+	names, seps, biases = _column_names(match_tables)
+	cols = OrderedDict()
+	for c, name in enumerate(names):
+		cols[name] = ctx.fetch(L.COL_IDX + c, nrows, numpy.int64)
+	for k, name in enumerate(seps):
+		cols[name] = ctx.fetch(L.COL_SEP + k, nrows)
+	cols['Separation_max'] = ctx.fetch(L.COL_SEPMAX, nrows)
+	cols['ncat'] = ctx.fetch(L.COL_NCAT, nrows, numpy.int64)
+	cols['dist_bayesfactor_uncorrected'] = ctx.fetch(L.COL_LOGBF_UNCORR, nrows)
+	cols['dist_bayesfactor'] = ctx.fetch(L.COL_LOGBF, nrows)
+	cols['dist_post'] = ctx.fetch(L.COL_DIST_POST, nrows)
+	for k, name in enumerate(biases):
+		cols[name] = ctx.fetch(L.COL_BIAS + k, nrows)
+	cols['p_single'] = ctx.fetch(L.COL_P_SINGLE, nrows)
+	cols['match_flag'] = ctx.fetch(L.COL_MATCH_FLAG, nrows, numpy.int64)
+	cols['prob_has_match'] = ctx.fetch(L.COL_P_ANY, nrows)
+	cols['prob_this_match'] = ctx.fetch(L.COL_P_I, nrows)
+	ctx.sync()
+	return cols
+
+
+def nway_match(match_tables, match_radius, prior_completeness,
+	mag_include_radius=None, mag_exclude_radius=None, magauto_post_single_minvalue=0.9,
+	prob_ratio_secondary=0.5,
+	min_prob=0., consider_unrelated_associations=True,
+	store_mag_hists=True,
+	logger=default_logger,
+	unrelated_mode='api', device=None, primary_range=None, as_frame=True):
+	"""Same contract as nwaylib.nway_match (nwaylib/__init__.py:31-83); see there for the arguments.
+
+	match_tables: list of dicts with name, ra, dec (deg), error (arcsec), area (deg^2), mags, magnames, maghists
+	(None = build the histogram automatically; else (bins_lo, bins_hi, hist_sel, hist_all)).
+
+	Extra keyword arguments (not in the reference):
+	  unrelated_mode  'api' (default): the behaviour of the reference API, whose correction for unrelated
+	                  associations is inert; 'cli': the live algorithm of nway.py:366-421.
+	                  consider_unrelated_associations=False disables both.
+	  device          CUDA device index (default: $NWB_DEVICE, $LOCAL_RANK or 0)
+	  primary_range   (first, count): match only these primary rows (multi-GPU sharding)
+	  as_frame        False returns an OrderedDict of numpy columns instead of a pandas.DataFrame
+
+	Returns one row per association, ordered by primary index, then by the secondary indices with -1 first.
+	The primary index is an ordinary column (pandas < 2.2 shape of the reference's frame)."""
+	if mag_exclude_radius is None:
+		mag_exclude_radius = mag_include_radius
+	if mag_include_radius is not None:
+		if mag_include_radius >= match_radius:
+			logger.warn('WARNING: magnitude radius is very large (>= matching radius). Consider using a smaller value.')
+	if unrelated_mode not in ('api', 'cli'):
+		raise ValueError("unrelated_mode must be 'api' or 'cli'")
+
+	ncats = len(match_tables)
+	ctx = _lib.get_context(device)
+	mag_columns = []   # (catalogue, k, values in the caller's dtype with -99 -> NaN, maghist, name)
+	for c, t in enumerate(match_tables):
+		mags = []
+		for k, (magvals, maghist, magname) in enumerate(zip(t.get('mags', []), t.get('maghists', []), t.get('magnames', []))):
+			magvals = numpy.array(magvals)
+			if magvals.dtype.kind != 'f':
+				magvals = magvals.astype(float)
+			magvals[magvals == -99] = numpy.nan
+			mags.append(magvals)
+			mag_columns.append((c, k, magvals, maghist, magname))
+		ctx.set_catalogue(c, ncats, t['ra'], t['dec'], t['error'], t['area'], mags=mags)
+	if primary_range is not None:
+		ctx.set_primary_range(*primary_range)
+	else:
+		ctx.set_primary_range(0, -1)
+
+	tab = _scalar_tables(match_tables, prior_completeness, logger)
+	mode = _lib.UNRELATED_CLI if (unrelated_mode == 'cli' and consider_unrelated_associations) else _lib.UNRELATED_API
+	ctx.set_params(match_radius, tab['pc'], prob_ratio_secondary, mode)
+	ctx.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
+
+	def install_hist(c, k, bins, hist_sel, hist_all):
+		ctx.set_maghist(c, k, *magnitudeweights.step_tables(bins, hist_sel, hist_all))
+
+	auto = [mc for mc in mag_columns if mc[3] is None]
+	for c, k, magvals, maghist, magname in mag_columns:
+		if maghist is not None:
+			logger.log('magnitude histogramming: using user-supplied histogram for "%s_%s"' % (match_tables[c]['name'], magname))
+			bins_lo, bins_hi, hist_sel, hist_all = maghist
+			install_hist(c, k, numpy.array(list(bins_lo) + [bins_hi[-1]]), hist_sel, hist_all)
+
+	logger.log('Computing distance-based probabilities ...')
+	nrows = ctx.match(fuse_final=not auto)
+	logger.log('matching: %6d matches after filtering by search radius' % nrows)
+	if not nrows > 0:
+		raise EmptyResultException('No matches.')
+
+	if auto:
+		# first pass done; build the histograms on the host from dist_post / Separation_max (__init__.py:324-375)
+		sepmax = ctx.fetch(_lib.COL_SEPMAX, nrows)
+		dist_post = ctx.fetch(_lib.COL_DIST_POST, nrows)
+		ctx.sync()
+		for c, k, magvals, maghist, magname in auto:
+			table_name = match_tables[c]['name']
+			col = '%s_%s' % (table_name, magname)
+			mag = '%s:%s' % (table_name, magname)
+			logger.log('Incorporating bias "%s" ...' % mag)
+			res = ctx.fetch(_lib.COL_IDX + c, nrows, numpy.int64)
+			ctx.sync()
+			bins, hist_sel, hist_all, nsel, npossible, nothers = magnitudeweights.auto_histogram(res, magvals, sepmax, dist_post,
+				mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue)
+			logger.log('magnitude histogram of column "%s": %d secure matches, %d insecure matches and %d secure non-matches of %d total entries (%d valid)' % (
+				col, nsel, npossible, nothers, len(magvals), numpy.isfinite(magvals).sum()))
+			if store_mag_hists:
+				fname = mag.replace(':', '_') + '_fit.txt'
+				logger.log('magnitude histogram stored to "%s".' % fname)
+				with open(fname, 'wb') as f:
+					f.write(b'# lo hi selected others\n')
+					numpy.savetxt(f, numpy.transpose([bins[:-1], bins[1:], hist_sel, hist_all]), fmt=["%10.5f"] * 4)
+			if nsel < 100:
+				raise UndersampledException('ERROR: too few secure matches (%d) to make a good histogram. If you are sure you want to use this poorly sampled histogram, replace "auto" with the filename. You can also decrease the mag-auto-minprob parameter.' % nsel)
+			install_hist(c, k, bins, hist_sel, hist_all)
+		logger.log('')
+		logger.log('Computing final probabilities ...')
+		ctx.finalize()
+
+	if min_prob > 0:
+		kept = ctx.truncate(min_prob)
+		logger.log('    cutting away %d (below p_i minimum)' % (nrows - kept))
+		nrows = kept
+
+	cols = _fetch_table(ctx, match_tables, nrows)
+	if not as_frame:
+		return cols
+	import pandas
+	return pandas.DataFrame(cols)

@@ -1,0 +1,206 @@
+"""ctypes binding of libnwayb200.so (include/nwayb200.h).  There is no CPU fallback: if the library is
+missing or no CUDA device is visible, every entry point raises."""
+import ctypes
+import os
+
+import numpy
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnwayb200.so')
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int64_p = ctypes.POINTER(ctypes.c_int64)
+
+# column selectors (nwayb200.h)
+COL_IDX, COL_SEP, COL_BIAS = 0, 100, 200
+COL_SEPMAX, COL_NCAT, COL_LOGBF_UNCORR, COL_LOGBF, COL_DIST_POST, COL_P_SINGLE, COL_MATCH_FLAG, COL_P_ANY, COL_P_I = range(300, 309)
+ERR_CIRCULAR, ERR_ELLIPSE = 1, 3
+UNRELATED_API, UNRELATED_CLI = 0, 1
+T_GRID, T_PAIRS, T_LISTS, T_ROWS, T_FINAL, T_TOTAL, T_KPAIRS, T_KROWS = range(8)
+STAGE_NAMES = ['grid', 'pairs', 'lists', 'rows', 'final', 'total', 'k_pairs', 'k_rows']
+NWB_ERR_EMPTY = -3
+
+EXPORTS = {
+	# name: (restype, argtypes)
+	'nwb_version': (ctypes.c_int, []),
+	'nwb_create': (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+	'nwb_destroy': (None, [ctypes.c_void_p]),
+	'nwb_last_error': (ctypes.c_char_p, [ctypes.c_void_p]),
+	'nwb_set_stream': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+	'nwb_set_catalogue': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+		ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int]),
+	'nwb_set_params': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_double_p, ctypes.c_double, ctypes.c_int]),
+	'nwb_set_tables': (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_double, c_double_p, c_double_p, c_double_p]),
+	'nwb_set_maghist': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
+	'nwb_set_primary_range': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]),
+	'nwb_match': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_int64_p]),
+	'nwb_finalize': (ctypes.c_int, [ctypes.c_void_p]),
+	'nwb_truncate': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_int64_p]),
+	'nwb_fetch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+	'nwb_column_ptr': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+	'nwb_sync': (ctypes.c_int, [ctypes.c_void_p]),
+	'nwb_timing': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
+	'nwb_launch_count': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
+	'nwb_stats': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
+	'nwb_dist': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+	'nwb_log_bf': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
+	'nwb_posterior': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p]),
+}
+
+_lib = None
+
+
+class NwbError(RuntimeError):
+	def __init__(self, code, msg):
+		RuntimeError.__init__(self, 'libnwayb200 error %d: %s' % (code, msg))
+		self.code = code
+
+
+def load():
+	"""dlopen the in-tree library and declare every prototype.  Raises if it has not been built."""
+	global _lib
+	if _lib is not None:
+		return _lib
+	if not os.path.exists(LIB_PATH):
+		raise ImportError('%s not found: build it with `python -m nway_b200.build` (needs nvcc). '
+			'There is no CPU fallback.' % LIB_PATH)
+	lib = ctypes.CDLL(LIB_PATH)
+	for name, (restype, argtypes) in EXPORTS.items():
+		fn = getattr(lib, name)
+		fn.restype = restype
+		fn.argtypes = argtypes
+	_lib = lib
+	return lib
+
+
+def dptr(a):
+	return a.ctypes.data_as(c_double_p)
+
+
+def f64(a):
+	return numpy.ascontiguousarray(a, dtype=numpy.float64)
+
+
+class Context(object):
+	"""one libnwayb200 context == one CUDA device + stream + scratch"""
+
+	def __init__(self, device=0):
+		self.lib = load()
+		h = ctypes.c_void_p()
+		rc = self.lib.nwb_create(int(device), ctypes.byref(h))
+		if rc != 0:
+			raise NwbError(rc, (self.lib.nwb_last_error(None) or b'').decode())
+		self.h = h
+		self.device = int(device)
+		self._keep = []
+
+	def close(self):
+		if getattr(self, 'h', None):
+			self.lib.nwb_destroy(self.h)
+			self.h = None
+
+	def __del__(self):
+		try:
+			self.close()
+		except Exception:
+			pass
+
+	def check(self, rc):
+		if rc != 0:
+			raise NwbError(rc, (self.lib.nwb_last_error(self.h) or b'').decode())
+
+	def set_catalogue(self, c, ncat, ra, dec, err, area, mags=(), err_kind=ERR_CIRCULAR):
+		"""host numpy arrays (copied to the device)"""
+		ra, dec, err = f64(ra), f64(dec), f64(err)
+		n = len(ra)
+		assert len(dec) == n and err.size == n * err_kind
+		m = len(mags)
+		magbuf = numpy.ascontiguousarray(numpy.stack([f64(x) for x in mags])) if m else None
+		self.check(self.lib.nwb_set_catalogue(self.h, c, ncat, n, ra.ctypes.data, dec.ctypes.data, err.ctypes.data,
+			err_kind, magbuf.ctypes.data if m else None, m, float(area), 0))
+		self.sync()   # the host arrays may be temporaries
+
+	def set_catalogue_device(self, c, ncat, n, ra_ptr, dec_ptr, err_ptr, area, mags_ptr=None, m=0, err_kind=ERR_CIRCULAR):
+		"""device pointers (e.g. torch tensors' data_ptr()); used in place"""
+		self.check(self.lib.nwb_set_catalogue(self.h, c, ncat, int(n), ra_ptr, dec_ptr, err_ptr, err_kind,
+			mags_ptr, m, float(area), 1))
+
+	def set_stream(self, cuda_stream):
+		self.check(self.lib.nwb_set_stream(self.h, cuda_stream))
+
+	def set_params(self, radius, completeness, ratio_secondary=0.5, unrelated_mode=UNRELATED_API):
+		pc = f64(completeness)
+		self.check(self.lib.nwb_set_params(self.h, float(radius), dptr(pc), float(ratio_secondary), int(unrelated_mode)))
+
+	def set_tables(self, norm, log10e, prior, log10prior, sub_log10prior):
+		a, b, c, d = f64(norm), f64(prior), f64(log10prior), f64(sub_log10prior)
+		self.check(self.lib.nwb_set_tables(self.h, dptr(a), float(log10e), dptr(b), dptr(c), dptr(d)))
+
+	def set_maghist(self, c, k, edges, weight, bias):
+		e, w, b = f64(edges), f64(weight), f64(bias)
+		assert len(e) == len(w) + 1 == len(b) + 1
+		self.check(self.lib.nwb_set_maghist(self.h, c, k, len(w), dptr(e), dptr(w), dptr(b)))
+
+	def set_primary_range(self, first, count):
+		self.check(self.lib.nwb_set_primary_range(self.h, int(first), int(count)))
+
+	def match(self, fuse_final=True):
+		n = ctypes.c_int64(0)
+		rc = self.lib.nwb_match(self.h, 1 if fuse_final else 0, ctypes.byref(n))
+		if rc == NWB_ERR_EMPTY:
+			return 0
+		self.check(rc)
+		return n.value
+
+	def finalize(self):
+		self.check(self.lib.nwb_finalize(self.h))
+
+	def truncate(self, min_prob):
+		n = ctypes.c_int64(0)
+		self.check(self.lib.nwb_truncate(self.h, float(min_prob), ctypes.byref(n)))
+		return n.value
+
+	def fetch(self, column, nrows, dtype=numpy.float64, out=None):
+		if out is None:
+			out = numpy.empty(nrows, dtype=dtype)
+		assert out.dtype.itemsize == 8 and out.flags.c_contiguous and len(out) >= nrows
+		self.check(self.lib.nwb_fetch(self.h, int(column), out.ctypes.data))
+		return out
+
+	def column_ptr(self, column):
+		p = ctypes.c_void_p()
+		self.check(self.lib.nwb_column_ptr(self.h, int(column), ctypes.byref(p)))
+		return p.value
+
+	def sync(self):
+		self.check(self.lib.nwb_sync(self.h))
+
+	def timings(self):
+		out = {}
+		v = ctypes.c_float()
+		for k, name in enumerate(STAGE_NAMES):
+			self.check(self.lib.nwb_timing(self.h, k, ctypes.byref(v)))
+			out[name] = v.value
+		return out
+
+	def launch_count(self):
+		n = ctypes.c_int64(0)
+		self.check(self.lib.nwb_launch_count(self.h, ctypes.byref(n)))
+		return n.value
+
+	def stats(self):
+		a = (ctypes.c_int64 * 4)()
+		self.check(self.lib.nwb_stats(self.h, a))
+		return dict(pairs_kept=a[1], grid_cells=a[2], cell_entries=a[3])
+
+
+_contexts = {}
+
+
+def get_context(device=None):
+	"""process-wide context per device (scratch buffers are reused between calls)"""
+	if device is None:
+		device = int(os.environ.get('NWB_DEVICE', os.environ.get('LOCAL_RANK', '0')))
+	if device not in _contexts:
+		_contexts[device] = Context(device)
+	return _contexts[device]

@@ -1,0 +1,914 @@
+// C ABI of the B200-native nway match path: context, buffers, stage orchestration.  See include/nwayb200.h.
+#include "../../include/nwayb200.h"
+#include "nwb_kernels.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace nwb;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+struct CatSlot {
+	bool set = false;
+	int64_t n = 0;
+	const double *ra = nullptr, *dec = nullptr, *err = nullptr, *mags = nullptr;
+	int err_kind = NWB_ERR_CIRCULAR, m = 0;
+	double area = 0;
+	DevBuf own;   // one allocation holding ra|dec|err|mags when copied from the host
+};
+
+struct HostMagHist {
+	bool set = false;
+	int nbins = 0;
+	double edges[MAXB + 1], weight[MAXB], bias[MAXB];
+};
+
+}  // namespace
+
+struct nwb_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr, own_stream = nullptr;
+	std::string err;
+	int ncat = 0;
+	CatSlot cat[MAXC];
+	HostMagHist hist[MAXC][MAXM];
+	bool params_set = false, tables_set = false;
+	double radius = 0, ratio_secondary = 0.5;
+	double pc[MAXC];
+	int unrelated_mode = NWB_UNRELATED_API;
+	ConstTables tables;   // host copy
+	int64_t first = 0, count = -1;
+
+	// device scratch (grow-only)
+	DevBuf d_tables, d_prim, d_red, d_bands, d_cellcnt, d_cstart, d_entries, d_cub, d_pairs, d_paircount;
+	DevBuf d_cnt[MAXC], d_segoff[MAXC], d_seg_s[MAXC], d_seg_sep[MAXC], d_Ls[MAXC], d_Lsep[MAXC], d_Ltrig[MAXC];
+	DevBuf d_rows, d_rowoff, d_matsz, d_matoff, d_mat, d_cols, d_cols2, d_keep, d_keeppos, d_misc;
+
+	// result
+	bool matched = false, finalized = false;
+	int64_t nrows = 0, np = 0;
+	int ncols = 0;
+	int res_ncat = 0, res_nmag = 0;
+	Columns cols;
+	RowParams rp;
+
+	cudaEvent_t ev[8];
+	cudaEvent_t kev[2 * MAXC + 2];   // around each k_pairs launch, and around k_rows
+	float ms[NWB_T_COUNT];
+	int64_t launches = 0;
+	int64_t stats[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(nwb_ctx *c, int code, const std::string &msg)
+{
+	if (c) c->err = msg; else g_create_error = msg;
+	return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return fail(ctx, NWB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+#define LAUNCH(ctx, kernel, grid, block, ...) do { \
+	kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__); \
+	(ctx)->launches++; \
+	cudaError_t e_ = cudaGetLastError(); \
+	if (e_ != cudaSuccess) return fail(ctx, NWB_ERR_CUDA, std::string(#kernel) + ": " + cudaGetErrorString(e_)); } while (0)
+
+int ensure(nwb_ctx *ctx, DevBuf &b, size_t bytes)
+{
+	if (bytes <= b.cap && b.p) return NWB_OK;
+	if (b.p) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+	size_t want = std::max<size_t>(bytes + bytes / 8, 256);
+	cudaError_t e = cudaMalloc(&b.p, want);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		e = cudaMalloc(&b.p, std::max<size_t>(bytes, 256));
+		want = std::max<size_t>(bytes, 256);
+		if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return fail(ctx, NWB_ERR_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed"); }
+	}
+	b.cap = want;
+	return NWB_OK;
+}
+
+#define ENSURE(buf, bytes) do { int r_ = ensure(ctx, buf, bytes); if (r_) return r_; } while (0)
+
+void release(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+struct CastLL {
+	__host__ __device__ long long operator()(const int &x) const { return (long long) x; }
+};
+
+// exclusive prefix sum of n ints into n long longs (n includes a trailing 0 so out[n-1] is the total)
+int scan_int_to_ll(nwb_ctx *ctx, const int *in, long long *out, int64_t n)
+{
+	cub::TransformInputIterator<long long, CastLL, const int *> it(in, CastLL());
+	size_t bytes = 0;
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, (int) n, ctx->stream));
+	ENSURE(ctx->d_cub, bytes);
+	CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, bytes, it, out, (int) n, ctx->stream));
+	return NWB_OK;
+}
+
+int scan_ll(nwb_ctx *ctx, const long long *in, long long *out, int64_t n)
+{
+	size_t bytes = 0;
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int) n, ctx->stream));
+	ENSURE(ctx->d_cub, bytes);
+	CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, bytes, in, out, (int) n, ctx->stream));
+	return NWB_OK;
+}
+
+int scan_int(nwb_ctx *ctx, const int *in, int *out, int64_t n)
+{
+	size_t bytes = 0;
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int) n, ctx->stream));
+	ENSURE(ctx->d_cub, bytes);
+	CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, bytes, in, out, (int) n, ctx->stream));
+	return NWB_OK;
+}
+
+// the scalar tables, with the reference's expressions (used when the caller did not supply its own)
+void default_tables(nwb_ctx *ctx)
+{
+	ConstTables &T = ctx->tables;
+	const int nc = ctx->ncat;
+	const double log_arcsec2rad = std::log(3600 * 180 / M_PI);          // bayesdistance.py:15
+	for (int n = 0; n <= MAXC; n++)
+		T.norm[n] = (n - 1) * std::log(2.0) + 2 * (n - 1) * log_arcsec2rad;   // bayesdistance.py:76
+	T.log10e = std::log10(M_E);
+	const double area_total = 4 * M_PI * ((180 / M_PI) * (180 / M_PI));  // __init__.py:205
+	double nu[MAXC], nup[MAXC];
+	for (int c = 0; c < nc; c++) {
+		double n = (double) ctx->cat[c].n, area = ctx->cat[c].area * 1.0;
+		nu[c] = n / area * area_total;
+		nup[c] = (n + 1) / area * area_total;
+	}
+	nup[0] = nu[0];
+	for (unsigned mask = 0; mask < (1u << (nc - 1)); mask++) {
+		double pcprod = ctx->pc[0], nuprod = nup[0];     // numpy.prod: left to right, index 0 included
+		for (int c = 1; c < nc; c++)
+			if (mask >> (c - 1) & 1u) { pcprod *= ctx->pc[c]; nuprod *= nup[c]; }
+		T.prior[mask] = nu[0] * pcprod / nuprod;         // __init__.py:254
+		T.log10prior[mask] = std::log10(T.prior[mask]);
+		// sub-association prior of the CLI correction: nu[A0] / prod(nu_plus[A])   (nway.py:395)
+		double sub = 1.0;
+		int a0 = -1;
+		bool firstp = true;
+		double prod = 1.0;
+		for (int c = 1; c < nc; c++)
+			if (mask >> (c - 1) & 1u) {
+				if (a0 < 0) a0 = c;
+				if (firstp) { prod = nup[c]; firstp = false; } else prod *= nup[c];
+			}
+		if (a0 >= 0) sub = nu[a0] / prod;
+		T.sub_log10prior[mask] = std::log10(sub);
+	}
+}
+
+int upload_tables(nwb_ctx *ctx)
+{
+	ConstTables &T = ctx->tables;
+	int nmag = 0;
+	for (int c = 0; c < ctx->ncat; c++) {
+		for (int k = 0; k < ctx->cat[c].m; k++) {
+			if (nmag >= MAXM) return fail(ctx, NWB_ERR_ARG, "too many magnitude columns");
+			MagTable &M = T.mag[nmag];
+			const HostMagHist &H = ctx->hist[c][k];
+			M.cat = c;
+			M.mag = ctx->cat[c].mags + (int64_t) k * ctx->cat[c].n;
+			if (H.set) {
+				M.nbins = H.nbins;
+				memcpy(M.edges, H.edges, sizeof(double) * (H.nbins + 1));
+				memcpy(M.weight, H.weight, sizeof(double) * H.nbins);
+				memcpy(M.bias, H.bias, sizeof(double) * H.nbins);
+			} else {
+				// no prior yet: weight 0 / bias 1 everywhere (pass 1 of an 'auto' run)
+				M.nbins = 1;
+				M.edges[0] = 1.0; M.edges[1] = 0.0;   // empty range: every lookup is "outside"
+				M.weight[0] = 0.0; M.bias[0] = 1.0;
+			}
+			nmag++;
+		}
+	}
+	ctx->res_nmag = nmag;
+	ENSURE(ctx->d_tables, sizeof(ConstTables));
+	CU(cudaMemcpyAsync(ctx->d_tables.p, &T, sizeof(ConstTables), cudaMemcpyHostToDevice, ctx->stream));
+	return NWB_OK;
+}
+
+// choose the band grid from the primaries' bounding box (host side, tiny)
+struct HostGrid {
+	Grid g;
+	std::vector<int> nra, base;
+	std::vector<double> inv_w;
+};
+
+void build_grid(const double red[6], double rb_ins, double cell_min_deg, long long max_cells, HostGrid &H)
+{
+	const double margin = 1e-6;
+	double dec_lo = red[0] - rb_ins - margin, dec_hi = red[1] + rb_ins + margin;
+	dec_lo = std::max(dec_lo, -90.0 - margin);
+	dec_hi = std::min(dec_hi, 90.0 + margin);
+	double spanA = red[3] - red[2], spanB = red[5] - red[4];
+	Grid &g = H.g;
+	if (std::min(spanA, spanB) + 2 * margin >= 359.0) {
+		g.full_circle = 1; g.ra_org = 0.0; g.ra_span = 360.0;
+	} else if (spanA <= spanB) {
+		g.full_circle = 0; g.ra_org = red[2] - margin; g.ra_span = spanA + 2 * margin;
+	} else {
+		g.full_circle = 0; g.ra_org = red[4] - 180.0 - margin; g.ra_span = spanB + 2 * margin;
+	}
+	double dspan = dec_hi - dec_lo;
+	double s = std::max(cell_min_deg, std::sqrt(dspan * g.ra_span / (double) max_cells));
+	s = std::max(s, dspan / 1048576.0);
+	int nb = (int) std::ceil(dspan / s);
+	if (nb < 1) nb = 1;
+	g.dec_lo = dec_lo;
+	g.inv_h = 1.0 / s;
+	g.nbands = nb;
+	H.nra.resize(nb); H.base.resize(nb); H.inv_w.resize(nb);
+	long long tot = 0;
+	for (int b = 0; b < nb; b++) {
+		double mid = dec_lo + (b + 0.5) * s;
+		double c = std::cos(std::min(std::fabs(mid), 90.0) * M_PI / 180);
+		double w = s / std::max(c, 1e-6);
+		long long n = (long long) std::floor(g.ra_span / w);
+		n = std::max<long long>(1, std::min<long long>(n, 1 << 24));
+		H.nra[b] = (int) n;
+		H.base[b] = (int) tot;
+		H.inv_w[b] = (double) n / g.ra_span;
+		tot += n;
+	}
+	g.ncells = tot;
+}
+
+inline int grid_for(long long n, int block) { return (int) std::min<long long>((n + block - 1) / block, 1 << 30); }
+
+int column_lookup(nwb_ctx *ctx, int column, void **out)
+{
+	const Columns &C = ctx->cols;
+	int nc = ctx->res_ncat, npairs = nc * (nc - 1) / 2;
+	void *p = nullptr;
+	if (column >= NWB_COL_IDX && column < NWB_COL_IDX + nc) p = C.idx[column - NWB_COL_IDX];
+	else if (column >= NWB_COL_SEP && column < NWB_COL_SEP + npairs) p = C.sep[column - NWB_COL_SEP];
+	else if (column >= NWB_COL_BIAS && column < NWB_COL_BIAS + ctx->res_nmag) p = C.bias[column - NWB_COL_BIAS];
+	else switch (column) {
+		case NWB_COL_SEPMAX: p = C.sepmax; break;
+		case NWB_COL_NCAT: p = C.ncat; break;
+		case NWB_COL_LOGBF_UNCORR: p = C.lbf_u; break;
+		case NWB_COL_LOGBF: p = C.lbf; break;
+		case NWB_COL_DIST_POST: p = C.dist_post; break;
+		case NWB_COL_P_SINGLE: p = C.p_single; break;
+		case NWB_COL_MATCH_FLAG: p = C.flag; break;
+		case NWB_COL_P_ANY: p = C.p_any; break;
+		case NWB_COL_P_I: p = C.p_i; break;
+		default: break;
+	}
+	if (!p) return fail(ctx, NWB_ERR_ARG, "unknown column selector " + std::to_string(column));
+	*out = p;
+	return NWB_OK;
+}
+
+// lay the SoA columns out in one allocation
+int layout_columns(nwb_ctx *ctx, DevBuf &buf, int64_t R, int nc, int nmag, Columns &C, int &ncols)
+{
+	int npairs = nc * (nc - 1) / 2;
+	ncols = nc + npairs + 9 + nmag;
+	size_t stride = ((size_t) std::max<int64_t>(R, 1) * 8 + 255) / 256 * 256;
+	ENSURE(buf, stride * ncols);
+	char *base = (char *) buf.p;
+	int k = 0;
+	auto next = [&]() { return (void *) (base + stride * (k++)); };
+	for (int c = 0; c < nc; c++) C.idx[c] = (long long *) next();
+	for (int i = 0; i < npairs; i++) C.sep[i] = (double *) next();
+	C.sepmax = (double *) next();
+	C.ncat = (long long *) next();
+	C.lbf_u = (double *) next();
+	C.lbf = (double *) next();
+	C.dist_post = (double *) next();
+	for (int j = 0; j < nmag; j++) C.bias[j] = (double *) next();
+	C.p_single = (double *) next();
+	C.flag = (long long *) next();
+	C.p_any = (double *) next();
+	C.p_i = (double *) next();
+	return NWB_OK;
+}
+
+template <int NC>
+int launch_rows(nwb_ctx *ctx, const RowParams &rp, bool fuse, int grid)
+{
+	if (fuse) LAUNCH(ctx, (k_rows<NC, true>), grid, 256, rp);
+	else LAUNCH(ctx, (k_rows<NC, false>), grid, 256, rp);
+	return NWB_OK;
+}
+
+template <int NC>
+int launch_count(nwb_ctx *ctx, const RowParams &rp, long long *rows, int grid)
+{
+	LAUNCH(ctx, (k_count_rows<NC>), grid, 256, rp, rows);
+	return NWB_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int nwb_version(void) { return 100; }
+
+int nwb_create(int device, nwb_ctx **out)
+{
+	nwb_ctx *ctx = nullptr;
+	if (!out) return fail(nullptr, NWB_ERR_ARG, "out is NULL");
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return fail(nullptr, NWB_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+	if (device < 0 || device >= ndev) return fail(nullptr, NWB_ERR_ARG, "device index out of range");
+	e = cudaSetDevice(device);
+	if (e != cudaSuccess) return fail(nullptr, NWB_ERR_CUDA, cudaGetErrorString(e));
+	ctx = new nwb_ctx();
+	ctx->device = device;
+	e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+	ctx->stream = ctx->own_stream;
+	if (e != cudaSuccess) { delete ctx; return fail(nullptr, NWB_ERR_CUDA, cudaGetErrorString(e)); }
+	for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+	for (auto &ev : ctx->kev) cudaEventCreate(&ev);
+	for (auto &m : ctx->ms) m = 0;
+	for (int c = 0; c < MAXC; c++) ctx->pc[c] = 1.0;
+	memset(&ctx->tables, 0, sizeof(ctx->tables));
+	*out = ctx;
+	return NWB_OK;
+}
+
+void nwb_destroy(nwb_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	DevBuf *single[] = {&ctx->d_tables, &ctx->d_prim, &ctx->d_red, &ctx->d_bands, &ctx->d_cellcnt, &ctx->d_cstart,
+		&ctx->d_entries, &ctx->d_cub, &ctx->d_pairs, &ctx->d_paircount, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_matsz,
+		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc};
+	for (DevBuf *b : single) release(*b);
+	for (int c = 0; c < MAXC; c++) {
+		release(ctx->d_cnt[c]); release(ctx->d_segoff[c]); release(ctx->d_seg_s[c]); release(ctx->d_seg_sep[c]);
+		release(ctx->d_Ls[c]); release(ctx->d_Lsep[c]); release(ctx->d_Ltrig[c]); release(ctx->cat[c].own);
+	}
+	for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+	for (auto &ev : ctx->kev) cudaEventDestroy(ev);
+	cudaStreamDestroy(ctx->own_stream);
+	delete ctx;
+}
+
+int nwb_set_stream(nwb_ctx *ctx, void *cuda_stream)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+	return NWB_OK;
+}
+
+const char *nwb_last_error(nwb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int nwb_set_catalogue(nwb_ctx *ctx, int c, int ncat, int64_t n, const double *ra, const double *dec,
+	const double *err, int err_kind, const double *mags, int m, double area, int on_device)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (ncat < 2 || ncat > MAXC) return fail(ctx, NWB_ERR_ARG, "ncat must be 2.." + std::to_string(MAXC));
+	if (c < 0 || c >= ncat) return fail(ctx, NWB_ERR_ARG, "catalogue index out of range");
+	if (n < 0 || n >= (1ll << 31) - 64) return fail(ctx, NWB_ERR_ARG, "catalogue size must be < 2^31");
+	if (!ra || !dec || !err) if (n > 0) return fail(ctx, NWB_ERR_ARG, "ra/dec/err is NULL");
+	if (err_kind != NWB_ERR_CIRCULAR && err_kind != NWB_ERR_ELLIPSE) return fail(ctx, NWB_ERR_ARG, "bad err_kind");
+	if (m < 0 || m > MAXM || (m > 0 && !mags)) return fail(ctx, NWB_ERR_ARG, "bad magnitude columns");
+	if (!(area > 0)) return fail(ctx, NWB_ERR_ARG, "area must be > 0");
+	CU(cudaSetDevice(ctx->device));
+	if (ctx->ncat != ncat) {
+		for (int k = 0; k < MAXC; k++) { ctx->cat[k].set = false; for (auto &h : ctx->hist[k]) h.set = false; }
+		ctx->ncat = ncat;
+	}
+	CatSlot &S = ctx->cat[c];
+	S.n = n; S.err_kind = err_kind; S.m = m; S.area = area;
+	for (auto &h : ctx->hist[c]) h.set = false;
+	int ecols = err_kind;
+	if (on_device) {
+		S.ra = ra; S.dec = dec; S.err = err; S.mags = mags;
+	} else {
+		size_t cols = 2 + ecols + m;
+		ENSURE(S.own, std::max<size_t>(1, cols * n) * sizeof(double));
+		double *d = (double *) S.own.p;
+		CU(cudaMemcpyAsync(d, ra, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+		CU(cudaMemcpyAsync(d + n, dec, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+		CU(cudaMemcpyAsync(d + 2 * n, err, (size_t) ecols * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+		if (m) CU(cudaMemcpyAsync(d + (2 + ecols) * n, mags, (size_t) m * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+		S.ra = d; S.dec = d + n; S.err = d + 2 * n; S.mags = m ? d + (2 + ecols) * n : nullptr;
+	}
+	S.set = true;
+	ctx->matched = ctx->finalized = false;
+	return NWB_OK;
+}
+
+int nwb_set_params(nwb_ctx *ctx, double match_radius_arcsec, const double *completeness,
+	double prob_ratio_secondary, int unrelated_mode)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (!(match_radius_arcsec > 0) || !(match_radius_arcsec < 3600.0 * 30))
+		return fail(ctx, NWB_ERR_ARG, "match radius must be in (0, 30 deg)");
+	if (ctx->ncat < 2) return fail(ctx, NWB_ERR_ARG, "set the catalogues first");
+	if (!completeness) return fail(ctx, NWB_ERR_ARG, "completeness is NULL");
+	if (completeness[0] != 1.0) return fail(ctx, NWB_ERR_ARG, "completeness[0] must be 1");
+	if (unrelated_mode != NWB_UNRELATED_API && unrelated_mode != NWB_UNRELATED_CLI)
+		return fail(ctx, NWB_ERR_ARG, "bad unrelated_mode");
+	ctx->radius = match_radius_arcsec;
+	for (int c = 0; c < ctx->ncat; c++) ctx->pc[c] = completeness[c];
+	ctx->ratio_secondary = prob_ratio_secondary;
+	ctx->unrelated_mode = unrelated_mode;
+	ctx->params_set = true;
+	ctx->tables_set = false;
+	return NWB_OK;
+}
+
+// optional: scalar tables computed by the caller with the reference's own numpy expressions
+int nwb_set_tables(nwb_ctx *ctx, const double *norm /* ncat+1 */, double log10e, const double *prior,
+	const double *log10prior, const double *sub_log10prior /* each 2^(ncat-1) */)
+{
+	if (!ctx || !ctx->params_set) return fail(ctx, NWB_ERR_ARG, "nwb_set_params first");
+	int nm = 1 << (ctx->ncat - 1);
+	for (int n = 0; n <= ctx->ncat; n++) ctx->tables.norm[n] = norm[n];
+	ctx->tables.log10e = log10e;
+	for (int k = 0; k < nm; k++) {
+		ctx->tables.prior[k] = prior[k];
+		ctx->tables.log10prior[k] = log10prior[k];
+		ctx->tables.sub_log10prior[k] = sub_log10prior[k];
+	}
+	ctx->tables_set = true;
+	return NWB_OK;
+}
+
+int nwb_set_maghist(nwb_ctx *ctx, int c, int k, int nbins, const double *edges, const double *weight,
+	const double *bias)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (c < 0 || c >= ctx->ncat || !ctx->cat[c].set) return fail(ctx, NWB_ERR_ARG, "catalogue not set");
+	if (k < 0 || k >= ctx->cat[c].m) return fail(ctx, NWB_ERR_ARG, "magnitude column out of range");
+	if (nbins < 1 || nbins > MAXB) return fail(ctx, NWB_ERR_ARG, "nbins must be 1.." + std::to_string(MAXB));
+	HostMagHist &H = ctx->hist[c][k];
+	H.nbins = nbins;
+	for (int i = 0; i <= nbins; i++) H.edges[i] = edges[i];
+	for (int i = 0; i < nbins; i++) {
+		H.weight[i] = std::isnan(weight[i]) ? 0.0 : weight[i];
+		H.bias[i] = std::isnan(weight[i]) ? 1.0 : bias[i];
+	}
+	H.set = true;
+	return NWB_OK;
+}
+
+int nwb_set_primary_range(nwb_ctx *ctx, int64_t first, int64_t count)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (first < 0 || count < -1) return fail(ctx, NWB_ERR_ARG, "bad primary range");
+	ctx->first = first;
+	ctx->count = count;
+	return NWB_OK;
+}
+
+int nwb_sync(nwb_ctx *ctx)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return NWB_OK;
+}
+
+static int run_final(nwb_ctx *ctx)
+{
+	int grid = (int) std::min<int64_t>((ctx->np * 32 + 255) / 256, 148 * 64);
+	grid = std::max(grid, 1);
+	LAUNCH(ctx, k_final, grid, 256, ctx->rp);
+	return NWB_OK;
+}
+
+int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	const int nc = ctx->ncat;
+	if (nc < 2) return fail(ctx, NWB_ERR_ARG, "no catalogues");
+	for (int c = 0; c < nc; c++) {
+		if (!ctx->cat[c].set) return fail(ctx, NWB_ERR_ARG, "catalogue " + std::to_string(c) + " not set");
+		if (ctx->cat[c].err_kind != NWB_ERR_CIRCULAR)
+			return fail(ctx, NWB_ERR_ARG, "elliptical errors are not implemented in this build");
+	}
+	if (!ctx->params_set) return fail(ctx, NWB_ERR_ARG, "nwb_set_params not called");
+	CU(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	ctx->matched = ctx->finalized = false;
+	ctx->launches = 0;
+	int64_t first = ctx->first, np = ctx->count < 0 ? ctx->cat[0].n - ctx->first : ctx->count;
+	if (first + np > ctx->cat[0].n || np < 0) return fail(ctx, NWB_ERR_ARG, "primary range exceeds the catalogue");
+	ctx->np = np;
+	if (np == 0) { if (nrows) *nrows = 0; return fail(ctx, NWB_ERR_EMPTY, "No matches."); }
+	if (!ctx->tables_set) default_tables(ctx);
+	{ int r = upload_tables(ctx); if (r) return r; }
+	const bool cli = ctx->unrelated_mode == NWB_UNRELATED_CLI && nc >= 3;
+	const bool fuse = fuse_final && !cli;
+
+	CU(cudaEventRecord(ctx->ev[0], st));
+	// ---- K0: primaries -> grid ---------------------------------------------------------------------------
+	const double r_deg = ctx->radius / 3600.0;
+	const double rb = r_deg * (1 + 1e-9) + 1e-12;
+	const double rb_ins = rb + 1e-9, dra_eps = 1e-9;
+	ENSURE(ctx->d_prim, (size_t) np * 6 * sizeof(double));
+	PrimArrays P;
+	{
+		double *b = (double *) ctx->d_prim.p;
+		P.lon = b; P.slat = b + np; P.clat = b + 2 * np; P.ra_n = b + 3 * np; P.dec = b + 4 * np; P.dra = b + 5 * np;
+	}
+	int pblocks = grid_for(np, 256);
+	ENSURE(ctx->d_red, ((size_t) pblocks * 6 + 8) * sizeof(double));
+	double *d_red = (double *) ctx->d_red.p;
+	LAUNCH(ctx, k_prim_prep, pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red + 8);
+	LAUNCH(ctx, k_reduce6, 1, 32, pblocks, d_red + 8, d_red);
+	double red[6];
+	CU(cudaMemcpyAsync(red, d_red, sizeof(red), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	HostGrid HG;
+	long long max_cells = 4ll << 20;
+	build_grid(red, rb_ins, rb_ins, max_cells, HG);
+	Grid G = HG.g;
+	{
+		size_t nb = (size_t) G.nbands;
+		ENSURE(ctx->d_bands, nb * (sizeof(int) * 2 + sizeof(double)) + 64);
+		char *b = (char *) ctx->d_bands.p;
+		double *d_invw = (double *) b;
+		int *d_nra = (int *) (b + nb * sizeof(double));
+		int *d_base = d_nra + nb;
+		CU(cudaMemcpyAsync(d_invw, HG.inv_w.data(), nb * sizeof(double), cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(d_nra, HG.nra.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(d_base, HG.base.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+		G.inv_w = d_invw; G.nra = d_nra; G.base = d_base;
+	}
+	size_t ncell1 = (size_t) G.ncells + 1;
+	ENSURE(ctx->d_cellcnt, ncell1 * sizeof(int));
+	ENSURE(ctx->d_cstart, ncell1 * sizeof(int));
+	int *d_cellcnt = (int *) ctx->d_cellcnt.p, *d_cstart = (int *) ctx->d_cstart.p;
+	CU(cudaMemsetAsync(d_cellcnt, 0, ncell1 * sizeof(int), st));
+	LAUNCH(ctx, (k_prim_cells<false>), pblocks, 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) nullptr, (Entry *) nullptr);
+	{ int r = scan_int(ctx, d_cellcnt, d_cstart, (int64_t) ncell1); if (r) return r; }
+	int nentries = 0;
+	CU(cudaMemcpyAsync(&nentries, d_cstart + G.ncells, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CU(cudaMemsetAsync(d_cellcnt, 0, ncell1 * sizeof(int), st));
+	CU(cudaStreamSynchronize(st));
+	ENSURE(ctx->d_entries, std::max<size_t>(1, nentries) * sizeof(Entry));
+	Entry *d_entries = (Entry *) ctx->d_entries.p;
+	LAUNCH(ctx, (k_prim_cells<true>), pblocks, 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) d_cstart, d_entries);
+	ctx->stats[2] = G.ncells;
+	ctx->stats[3] = nentries;
+	CU(cudaEventRecord(ctx->ev[1], st));
+
+	// ---- K1: stream the secondaries ------------------------------------------------------------------------
+	// one append buffer per secondary catalogue, sized from the expected pair density and grown on overflow
+	ENSURE(ctx->d_paircount, MAXC * sizeof(unsigned long long));
+	unsigned long long *d_paircount = (unsigned long long *) ctx->d_paircount.p;
+	unsigned long long h_paircount[MAXC] = {0};
+	std::vector<size_t> pair_off(nc + 1, 0);
+	std::vector<unsigned long long> cap(nc, 0);
+	const double disc_deg2 = M_PI * r_deg * r_deg;
+	bool again = true;
+	for (int attempt = 0; again && attempt < 3; attempt++) {
+		size_t tot = 0;
+		for (int c = 1; c < nc; c++) {
+			if (attempt == 0) {
+				double expect = (double) np * (double) ctx->cat[c].n * disc_deg2 / ctx->cat[c].area;
+				unsigned long long want = (unsigned long long) (expect * 1.3) + 65536 + (unsigned long long) np;
+				// keep a previously grown capacity
+				cap[c] = std::max<unsigned long long>(want, 0);
+			} else if (h_paircount[c] > cap[c]) {
+				cap[c] = h_paircount[c] + 1024;
+			}
+			pair_off[c] = tot;
+			tot += cap[c];
+		}
+		pair_off[nc] = tot;
+		ENSURE(ctx->d_pairs, std::max<size_t>(1, tot) * sizeof(PairRec));
+		CU(cudaMemsetAsync(d_paircount, 0, MAXC * sizeof(unsigned long long), st));
+		for (int c = 1; c < nc; c++) {
+			ENSURE(ctx->d_cnt[c], (size_t) (np + 1) * sizeof(int));
+			CU(cudaMemsetAsync(ctx->d_cnt[c].p, 0, (size_t) (np + 1) * sizeof(int), st));
+			int64_t n = ctx->cat[c].n;
+			if (n == 0) continue;
+			int grid = (int) std::min<int64_t>((n + 255) / 256, 148 * 8 * 4);
+			CU(cudaEventRecord(ctx->kev[2 * c], st));
+			LAUNCH(ctx, k_pairs, grid, 256, (long long) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_cstart,
+				(const Entry *) d_entries, P, rb, ctx->radius, (PairRec *) ctx->d_pairs.p + pair_off[c], cap[c],
+				d_paircount + c, (int *) ctx->d_cnt[c].p);
+			CU(cudaEventRecord(ctx->kev[2 * c + 1], st));
+		}
+		CU(cudaMemcpyAsync(h_paircount, d_paircount, sizeof(h_paircount), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		again = false;
+		for (int c = 1; c < nc; c++) if (h_paircount[c] > cap[c]) again = true;
+	}
+	if (again) return fail(ctx, NWB_ERR_NOMEM, "pair buffer overflow persisted");
+	ctx->stats[1] = 0;
+	for (int c = 1; c < nc; c++) ctx->stats[1] += (int64_t) h_paircount[c];
+	CU(cudaEventRecord(ctx->ev[2], st));
+
+	// ---- lists: scan, scatter, sort ------------------------------------------------------------------------
+	Lists L;
+	memset(&L, 0, sizeof(L));
+	const bool trig = nc > 2;
+	int wgrid = std::max(1, (int) std::min<int64_t>((np * 32 + 255) / 256, 148 * 64));
+	for (int c = 1; c < nc; c++) {
+		size_t npair = (size_t) h_paircount[c];
+		ENSURE(ctx->d_segoff[c], (size_t) (np + 1) * sizeof(long long));
+		long long *off = (long long *) ctx->d_segoff[c].p;
+		{ int r = scan_int_to_ll(ctx, (const int *) ctx->d_cnt[c].p, off, np + 1); if (r) return r; }
+		ENSURE(ctx->d_seg_s[c], std::max<size_t>(1, npair) * sizeof(int));
+		ENSURE(ctx->d_seg_sep[c], std::max<size_t>(1, npair) * sizeof(double));
+		ENSURE(ctx->d_Ls[c], std::max<size_t>(1, npair) * sizeof(int));
+		ENSURE(ctx->d_Lsep[c], std::max<size_t>(1, npair) * sizeof(double));
+		if (trig) ENSURE(ctx->d_Ltrig[c], std::max<size_t>(1, npair) * 3 * sizeof(double));
+		CU(cudaMemsetAsync(ctx->d_cnt[c].p, 0, (size_t) (np + 1) * sizeof(int), st));
+		double *tr = trig ? (double *) ctx->d_Ltrig[c].p : nullptr;
+		if (npair) {
+			LAUNCH(ctx, k_scatter, grid_for((long long) npair, 256), 256, (long long) npair,
+				(const PairRec *) ctx->d_pairs.p + pair_off[c], (const long long *) off, (int *) ctx->d_cnt[c].p,
+				(int *) ctx->d_seg_s[c].p, (double *) ctx->d_seg_sep[c].p);
+			if (trig)
+				LAUNCH(ctx, (k_sort_lists<true>), wgrid, 256, (int) np, (const long long *) off, (const int *) ctx->d_seg_s[c].p,
+					(const double *) ctx->d_seg_sep[c].p, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
+					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair);
+			else
+				LAUNCH(ctx, (k_sort_lists<false>), wgrid, 256, (int) np, (const long long *) off, (const int *) ctx->d_seg_s[c].p,
+					(const double *) ctx->d_seg_sep[c].p, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
+					ctx->cat[c].ra, ctx->cat[c].dec, (double *) nullptr, (double *) nullptr, (double *) nullptr);
+		}
+		L.off[c] = off;
+		L.s[c] = (const int *) ctx->d_Ls[c].p;
+		L.sep[c] = (const double *) ctx->d_Lsep[c].p;
+		L.lon[c] = tr; L.slat[c] = tr ? tr + npair : nullptr; L.clat[c] = tr ? tr + 2 * npair : nullptr;
+	}
+	CU(cudaEventRecord(ctx->ev[3], st));
+
+	// ---- K2: rows ------------------------------------------------------------------------------------------
+	RowParams &rp = ctx->rp;
+	memset(&rp, 0, sizeof(rp));
+	rp.ncat = nc; rp.nmag = ctx->res_nmag; rp.np = (int) np; rp.first = first;
+	rp.radius = ctx->radius; rp.ratio_secondary = ctx->ratio_secondary;
+	for (int c = 0; c < nc; c++) rp.err[c] = ctx->cat[c].err;
+	rp.T = (const ConstTables *) ctx->d_tables.p;
+	rp.L = L;
+	ENSURE(ctx->d_rows, (size_t) (np + 1) * sizeof(long long));
+	ENSURE(ctx->d_rowoff, (size_t) (np + 1) * sizeof(long long));
+	long long *d_rows = (long long *) ctx->d_rows.p, *d_rowoff = (long long *) ctx->d_rowoff.p;
+	CU(cudaMemsetAsync(d_rows, 0, (size_t) (np + 1) * sizeof(long long), st));
+	if (nc == 2) {
+		LAUNCH(ctx, k_rows_per_primary_2, pblocks, 256, (int) np, L.off[1], d_rows);
+	} else {
+		ENSURE(ctx->d_matsz, (size_t) (np + 1) * sizeof(long long));
+		ENSURE(ctx->d_matoff, (size_t) (np + 1) * sizeof(long long));
+		long long *d_matsz = (long long *) ctx->d_matsz.p, *d_matoff = (long long *) ctx->d_matoff.p;
+		CU(cudaMemsetAsync(d_matsz, 0, (size_t) (np + 1) * sizeof(long long), st));
+		LAUNCH(ctx, k_mat_sizes, pblocks, 256, (int) np, nc, L, d_matsz);
+		{ int r = scan_ll(ctx, d_matsz, d_matoff, np + 1); if (r) return r; }
+		long long mat_total = 0;
+		CU(cudaMemcpyAsync(&mat_total, d_matoff + np, sizeof(long long), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		ENSURE(ctx->d_mat, std::max<size_t>(1, (size_t) mat_total) * sizeof(double));
+		rp.mat_off = d_matoff;
+		rp.mat = (double *) ctx->d_mat.p;
+		int r = 0;
+		switch (nc) {
+			case 3: r = launch_count<3>(ctx, rp, d_rows, wgrid); break;
+			case 4: r = launch_count<4>(ctx, rp, d_rows, wgrid); break;
+			case 5: r = launch_count<5>(ctx, rp, d_rows, wgrid); break;
+			case 6: r = launch_count<6>(ctx, rp, d_rows, wgrid); break;
+			case 7: r = launch_count<7>(ctx, rp, d_rows, wgrid); break;
+			default: r = launch_count<8>(ctx, rp, d_rows, wgrid); break;
+		}
+		if (r) return r;
+	}
+	{ int r = scan_ll(ctx, d_rows, d_rowoff, np + 1); if (r) return r; }
+	long long R = 0;
+	CU(cudaMemcpyAsync(&R, d_rowoff + np, sizeof(long long), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	rp.row_off = d_rowoff;
+	ctx->res_ncat = nc;
+	{ int r = layout_columns(ctx, ctx->d_cols, R, nc, ctx->res_nmag, ctx->cols, ctx->ncols); if (r) return r; }
+	rp.C = ctx->cols;
+	CU(cudaEventRecord(ctx->kev[0], st));
+	{
+		int r = 0;
+		switch (nc) {
+			case 2: r = launch_rows<2>(ctx, rp, fuse, wgrid); break;
+			case 3: r = launch_rows<3>(ctx, rp, fuse, wgrid); break;
+			case 4: r = launch_rows<4>(ctx, rp, fuse, wgrid); break;
+			case 5: r = launch_rows<5>(ctx, rp, fuse, wgrid); break;
+			case 6: r = launch_rows<6>(ctx, rp, fuse, wgrid); break;
+			case 7: r = launch_rows<7>(ctx, rp, fuse, wgrid); break;
+			default: r = launch_rows<8>(ctx, rp, fuse, wgrid); break;
+		}
+		if (r) return r;
+	}
+	CU(cudaEventRecord(ctx->kev[1], st));
+	if (cli) LAUNCH(ctx, k_correct_cli, wgrid, 256, rp);
+	CU(cudaEventRecord(ctx->ev[4], st));
+	if (fuse_final && !fuse) { int r = run_final(ctx); if (r) return r; }
+	CU(cudaEventRecord(ctx->ev[5], st));
+	CU(cudaStreamSynchronize(st));
+	for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&ctx->ms[k], ctx->ev[k], ctx->ev[k + 1]));
+	CU(cudaEventElapsedTime(&ctx->ms[NWB_T_TOTAL], ctx->ev[0], ctx->ev[5]));
+	ctx->ms[NWB_T_KPAIRS] = 0;
+	for (int c = 1; c < nc; c++) {
+		float t = 0;
+		if (ctx->cat[c].n > 0) CU(cudaEventElapsedTime(&t, ctx->kev[2 * c], ctx->kev[2 * c + 1]));
+		ctx->ms[NWB_T_KPAIRS] += t;
+	}
+	CU(cudaEventElapsedTime(&ctx->ms[NWB_T_KROWS], ctx->kev[0], ctx->kev[1]));
+	ctx->nrows = R;
+	ctx->matched = true;
+	ctx->finalized = fuse_final != 0;
+	if (nrows) *nrows = R;
+	return NWB_OK;
+}
+
+int nwb_finalize(nwb_ctx *ctx)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	CU(cudaSetDevice(ctx->device));
+	{ int r = upload_tables(ctx); if (r) return r; }   // magnitude priors may have been set since nwb_match
+	ctx->rp.nmag = ctx->res_nmag;
+	CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+	{ int r = run_final(ctx); if (r) return r; }
+	CU(cudaEventRecord(ctx->ev[7], ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaEventElapsedTime(&ctx->ms[NWB_T_FINAL], ctx->ev[6], ctx->ev[7]));
+	ctx->finalized = true;
+	return NWB_OK;
+}
+
+int nwb_truncate(nwb_ctx *ctx, double min_prob, int64_t *nrows)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (!ctx->finalized) return fail(ctx, NWB_ERR_STATE, "nwb_finalize has not run");
+	CU(cudaSetDevice(ctx->device));
+	int64_t R = ctx->nrows;
+	if (R == 0 || !(min_prob > 0)) { if (nrows) *nrows = R; return NWB_OK; }
+	cudaStream_t st = ctx->stream;
+	ENSURE(ctx->d_keep, (size_t) (R + 1) * sizeof(int));
+	ENSURE(ctx->d_keeppos, (size_t) (R + 1) * sizeof(long long));
+	int *keep = (int *) ctx->d_keep.p;
+	long long *pos = (long long *) ctx->d_keeppos.p;
+	CU(cudaMemsetAsync(keep + R, 0, sizeof(int), st));
+	LAUNCH(ctx, k_keep_flags, grid_for(R, 256), 256, (long long) R, (const double *) ctx->cols.p_i, min_prob, keep);
+	{ int r = scan_int_to_ll(ctx, keep, pos, R + 1); if (r) return r; }
+	long long R2 = 0;
+	CU(cudaMemcpyAsync(&R2, pos + R, sizeof(long long), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	Columns C2;
+	memset(&C2, 0, sizeof(C2));
+	int ncols2 = 0;
+	{ int r = layout_columns(ctx, ctx->d_cols2, R2, ctx->res_ncat, ctx->res_nmag, C2, ncols2); if (r) return r; }
+	size_t s1 = ((size_t) std::max<int64_t>(R, 1) * 8 + 255) / 256 * 256, s2 = ((size_t) std::max<int64_t>(R2, 1) * 8 + 255) / 256 * 256;
+	for (int k = 0; k < ctx->ncols; k++)
+		LAUNCH(ctx, k_compact8, grid_for(R, 256), 256, (long long) R, (const int *) keep, (const long long *) pos,
+			(const unsigned long long *) ((char *) ctx->d_cols.p + s1 * k), (unsigned long long *) ((char *) ctx->d_cols2.p + s2 * k));
+	CU(cudaStreamSynchronize(st));
+	std::swap(ctx->d_cols, ctx->d_cols2);
+	ctx->cols = C2;
+	ctx->rp.C = C2;
+	ctx->nrows = R2;
+	if (nrows) *nrows = R2;
+	return NWB_OK;
+}
+
+int nwb_column_ptr(nwb_ctx *ctx, int column, void **dev_ptr)
+{
+	if (!ctx || !dev_ptr) return NWB_ERR_ARG;
+	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	return column_lookup(ctx, column, dev_ptr);
+}
+
+int nwb_fetch(nwb_ctx *ctx, int column, void *dst_host)
+{
+	if (!ctx || !dst_host) return NWB_ERR_ARG;
+	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	void *p = nullptr;
+	int r = column_lookup(ctx, column, &p);
+	if (r) return r;
+	CU(cudaSetDevice(ctx->device));
+	if (ctx->nrows > 0)
+		CU(cudaMemcpyAsync(dst_host, p, (size_t) ctx->nrows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	return NWB_OK;
+}
+
+int nwb_timing(nwb_ctx *ctx, int stage, float *ms)
+{
+	if (!ctx || !ms || stage < 0 || stage >= NWB_T_COUNT) return NWB_ERR_ARG;
+	*ms = ctx->ms[stage];
+	return NWB_OK;
+}
+
+int nwb_launch_count(nwb_ctx *ctx, int64_t *launches)
+{
+	if (!ctx || !launches) return NWB_ERR_ARG;
+	*launches = ctx->launches;
+	return NWB_OK;
+}
+
+int nwb_stats(nwb_ctx *ctx, int64_t *out4)
+{
+	if (!ctx || !out4) return NWB_ERR_ARG;
+	for (int k = 0; k < 4; k++) out4[k] = ctx->stats[k];
+	return NWB_OK;
+}
+
+// ---- element-wise surface ------------------------------------------------------------------------------
+static int elementwise_io(nwb_ctx *ctx, int64_t n, int nin, const double *const *in, const int64_t *in_len, double **d_in, double **d_out)
+{
+	size_t tot = 0;
+	for (int k = 0; k < nin; k++) tot += (size_t) in_len[k];
+	ENSURE(ctx->d_misc, (tot + (size_t) n + 8) * sizeof(double));
+	double *b = (double *) ctx->d_misc.p;
+	for (int k = 0; k < nin; k++) {
+		d_in[k] = b;
+		CU(cudaMemcpyAsync(b, in[k], (size_t) in_len[k] * 8, cudaMemcpyHostToDevice, ctx->stream));
+		b += in_len[k];
+	}
+	*d_out = b;
+	return NWB_OK;
+}
+
+int nwb_dist(nwb_ctx *ctx, int64_t n, const double *ra1, const double *dec1, const double *ra2,
+	const double *dec2, double *out_deg)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (n <= 0) return NWB_OK;
+	CU(cudaSetDevice(ctx->device));
+	const double *in[4] = {ra1, dec1, ra2, dec2};
+	int64_t len[4] = {n, n, n, n};
+	double *d_in[4], *d_out;
+	{ int r = elementwise_io(ctx, n, 4, in, len, d_in, &d_out); if (r) return r; }
+	LAUNCH(ctx, k_dist, grid_for(n, 256), 256, (long long) n, d_in[0], d_in[1], d_in[2], d_in[3], d_out);
+	CU(cudaMemcpyAsync(out_deg, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return NWB_OK;
+}
+
+int nwb_log_bf(nwb_ctx *ctx, int64_t n, int ncat, const double *sep, const double *err, double *out)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (ncat < 1 || ncat > MAXC) return fail(ctx, NWB_ERR_ARG, "ncat out of range");
+	if (n <= 0) return NWB_OK;
+	CU(cudaSetDevice(ctx->device));
+	// norm / log10e only
+	ConstTables T;
+	memset(&T, 0, sizeof(T));
+	const double log_arcsec2rad = std::log(3600 * 180 / M_PI);
+	for (int k = 0; k <= MAXC; k++) T.norm[k] = (k - 1) * std::log(2.0) + 2 * (k - 1) * log_arcsec2rad;
+	T.log10e = std::log10(M_E);
+	const double *in[2] = {sep, err};
+	int64_t len[2] = {(int64_t) ncat * ncat * n, (int64_t) ncat * n};
+	double *d_in[2], *d_out;
+	{ int r = elementwise_io(ctx, n + (int64_t) (sizeof(ConstTables) / 8 + 1), 2, in, len, d_in, &d_out); if (r) return r; }
+	ConstTables *d_T = (ConstTables *) (d_out + n);
+	CU(cudaMemcpyAsync(d_T, &T, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	LAUNCH(ctx, k_log_bf, grid_for(n, 256), 256, (long long) n, ncat, d_in[0], d_in[1], (const ConstTables *) d_T, d_out);
+	CU(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return NWB_OK;
+}
+
+int nwb_posterior(nwb_ctx *ctx, int64_t n, const double *prior, const double *log_bf, double *out)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (n <= 0) return NWB_OK;
+	CU(cudaSetDevice(ctx->device));
+	const double *in[2] = {prior, log_bf};
+	int64_t len[2] = {n, n};
+	double *d_in[2], *d_out;
+	{ int r = elementwise_io(ctx, n, 2, in, len, d_in, &d_out); if (r) return r; }
+	LAUNCH(ctx, k_posterior, grid_for(n, 256), 256, (long long) n, d_in[0], d_in[1], d_out);
+	CU(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return NWB_OK;
+}
+
+}  // extern "C"

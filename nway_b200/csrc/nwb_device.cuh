@@ -1,0 +1,141 @@
+// Device-side arithmetic of the nway match path.  fp64 throughout, compiled with --fmad=false so that the
+// operation order below IS the rounding order (the reference is unfused numpy).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define NWB_FULL 0xffffffffu
+#define NWB_PI 3.141592653589793
+
+namespace nwb {
+
+constexpr int MAXC = 8;                       // catalogues
+constexpr int MAXP = MAXC * (MAXC - 1) / 2;   // catalogue pairs
+constexpr int MAXM = 8;                       // magnitude columns (all catalogues together)
+constexpr int MAXB = 64;                      // bins per magnitude prior
+
+// reference: nwaylib/fastskymatch.py:31-34 -- divide first, then multiply
+__device__ __forceinline__ double deg2rad_ref(double x) { return x / 180 * NWB_PI; }
+
+// Great-circle separation in ARCSEC between a (lower catalogue index) and b, from the precomputed
+// lon = ra/180*pi, sin/cos(dec/180*pi).  fastskymatch.py:36-47 then *60*60 (__init__.py:163).
+__device__ __forceinline__ double sep_arcsec_ref(double lon1, double slat1, double clat1,
+	double lon2, double slat2, double clat2)
+{
+	double sdlon, cdlon;
+	sincos(lon2 - lon1, &sdlon, &cdlon);
+	double num1 = clat2 * sdlon;
+	double num2 = clat1 * slat2 - slat1 * clat2 * cdlon;
+	double den = slat1 * slat2 + clat1 * clat2 * cdlon;
+	double deg = atan2(hypot(num1, num2), den) * 180 / NWB_PI;
+	return deg * 60 * 60;
+}
+
+// index of the catalogue pair (a < b) in the order _create_match_table emits the Separation columns
+// (__init__.py:143-168): (0,1),(0,2),...,(1,2),...
+__host__ __device__ __forceinline__ int pair_index(int a, int b, int ncat)
+{
+	return a * (2 * ncat - a - 1) / 2 + (b - a - 1);
+}
+
+// one magnitude prior as a step function (magnitudeweights.py:74-87)
+struct MagTable {
+	int cat;            // catalogue the column belongs to
+	int nbins;
+	const double *mag;  // device column, n[cat] values
+	double edges[MAXB + 1];
+	double weight[MAXB];  // log10(ratio), NaN already replaced by 0 (__init__.py:388)
+	double bias[MAXB];    // 10**weight     (__init__.py:392)
+};
+
+// host-computed scalar tables, all evaluated with the reference's own python/numpy expressions
+struct ConstTables {
+	double norm[MAXC + 1];             // (n-1)*log(2) + 2*(n-1)*log_arcsec2rad, by n   bayesdistance.py:76
+	double log10e;                     // numpy.log10(numpy.e)
+	double prior[1 << (MAXC - 1)];     // by presence mask of the secondaries (bit c-1)  __init__.py:254
+	double log10prior[1 << (MAXC - 1)];
+	double sub_log10prior[1 << (MAXC - 1)];  // log10(nu[A0]/prod(nu_plus[A]))           nway.py:395
+	MagTable mag[MAXM];
+};
+
+// log10 Bayes factor of the present catalogues (bayesdistance.py:64-86).
+// present: bit c set if catalogue c takes part (bit 0 = primary for a full row; sub-associations of the CLI
+// correction pass a mask without bit 0).  sig[c]: sigma in arcsec.  sep[pair_index(a,b)]: arcsec.
+template <int NC>
+__device__ __forceinline__ double log_bf_ref(const ConstTables *__restrict__ T, int ncat_rt, unsigned present,
+	const double *sig, const double *sep)
+{
+	const int ncat = NC > 0 ? NC : ncat_rt;
+	int n = __popc(present);
+	if (n <= 1)
+		return 0.0;   // norm = 0, slog = log(w) - log(w) = 0, q = 0  ->  exactly 0
+	double w[MAXC];
+	double wsum = 0.0, slog = 0.0;
+	bool first = true;
+#pragma unroll
+	for (int c = 0; c < (NC > 0 ? NC : MAXC); c++) {
+		if (c < ncat && (present >> c & 1u)) {
+			double s = sig[c];
+			w[c] = 1.0 / (s * s);
+			double lw = log(w[c]);
+			if (first) { wsum = w[c]; slog = lw; first = false; }
+			else { wsum = wsum + w[c]; slog = slog + lw; }
+		}
+	}
+	slog = slog - log(wsum);
+	double q = 0.0;
+	bool qfirst = true;
+#pragma unroll
+	for (int a = 0; a < (NC > 0 ? NC : MAXC); a++) {
+#pragma unroll
+		for (int b = a + 1; b < (NC > 0 ? NC : MAXC); b++) {
+			if (b < ncat && (present >> a & 1u) && (present >> b & 1u)) {
+				double p = sep[pair_index(a, b, ncat)];
+				double term = w[a] * w[b] * (p * p);
+				if (qfirst) { q = term; qfirst = false; } else q = q + term;   // 0 + term == term
+			}
+		}
+	}
+	double exponent = -q / 2 / wsum;
+	return (T->norm[n] + slog + exponent) * T->log10e;
+}
+
+// bayesdistance.py:26-32
+__device__ __forceinline__ double posterior_ref(double prior, double log10prior, double log_bf)
+{
+	return 1. / (1 + (1 - prior) * exp10(-log_bf - log10prior));
+}
+
+// zero-order-hold lookup; returns the weight and sets bias.  m is already -99 for undefined
+// (__init__.py:383-388).
+__device__ __forceinline__ double mag_weight(const MagTable &M, double m, double &bias)
+{
+	if (!(m >= M.edges[0] && m <= M.edges[M.nbins])) {   // also true for NaN
+		bias = 1.0;
+		return 0.0;
+	}
+	int k = 0;
+	for (int j = 1; j < M.nbins; j++)
+		if (M.edges[j] <= m) k = j;
+	bias = M.bias[k];
+	return M.weight[k];
+}
+
+__device__ __forceinline__ double warp_max(double v)
+{
+	for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(NWB_FULL, v, o));
+	return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NWB_FULL, v, o);
+	return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NWB_FULL, v, o);
+	return v;
+}
+
+}  // namespace nwb

@@ -7,7 +7,12 @@ dist_bayesfactor*       : |d| <= 1e-9 + 1e-12*|ref|
 separations             : |d| <= 1e-9 arcsec relative 1e-10
 dist_post, p_single, bias_* : relative 1e-10 above 1e-30
 """
+import hashlib
+import os
+
 import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 RTOL = 1e-10
 
@@ -62,3 +67,27 @@ def assert_tables_match(ref, got, columns=None, context=''):
 			failed.append('%s: %s row %d ref %r got %r' % (context, c, worst, a[worst], b[worst]))
 	assert not failed, '\n'.join(failed + report)
 	return report
+
+
+def load_golden(name):
+	return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def check_against_digest(name, got, names):
+	g = load_golden('ref_%s.npz' % name)
+	idx = np.stack([got[n] for n in names], axis=1).astype(np.int64)
+	assert len(idx) == int(g['nrows'])
+	sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(idx).tobytes()).digest(), dtype=np.uint8)
+	assert (sha == g['idx_sha256']).all(), 'row set / order differs from the reference'
+	starts = np.concatenate(([0], np.flatnonzero(np.diff(idx[:, 0]) != 0) + 1)) if len(idx) else np.zeros(0, dtype=np.int64)
+	ok, dabs, drel, worst = column_error('prob_has_match', g['p_any'], np.asarray(got['prob_has_match'])[starts])
+	assert ok, ('p_any', name, worst, dabs, drel)
+	sel = g['sample_rows']
+	ref = {str(c): g['col_' + str(c)] for c in g['columns']}
+	assert_tables_match(ref, {c: np.asarray(got[c])[sel] for c in ref}, context=name)
+	for c in ref:
+		v = np.asarray(got[c])
+		s = np.nansum(v[np.isfinite(v)]) if v.dtype.kind == 'f' else v.sum()
+		assert np.isclose(float(s), float(g['sum_' + c]), rtol=1e-9, atol=1e-9), (name, c, s, g['sum_' + c])
+
+

@@ -1,0 +1,136 @@
+"""GPU: the CUDA path (through the C ABI, via nway_b200.nway_match) against the oracle run live on the same
+inputs, and against the committed outputs of the real reference."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import cases, parity
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cuda(tables, radius, completeness, **kw):
+	import nway_b200
+	return nway_b200.nway_match(tables, radius, completeness, logger=nway_b200.NullOutputLogger(),
+		store_mag_hists=False, as_frame=False, **kw)
+
+
+def report(name, lines):
+	out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+	if os.path.isdir(out):
+		with open(os.path.join(out, 'parity_report.txt'), 'a') as f:
+			f.write('== %s\n%s\n' % (name, '\n'.join(lines)))
+
+
+@pytest.mark.parametrize('name', list(cases.GOLDEN_CASES))
+def test_cuda_matches_oracle_and_reference(name):
+	from oracle import nway_oracle as O
+	spec = cases.GOLDEN_CASES[name]
+	kw = spec.get('kwargs', {})
+	got = run_cuda(cases.build_case(name), spec['radius'], spec['completeness'], **kw)
+	tables = cases.build_case(name)
+	ref = O.nway_match(tables, spec['radius'], spec['completeness'], **kw)
+	cols = [c for c in ref if not c.startswith('_')]
+	assert list(got.keys()) == cols, (list(got.keys()), cols)
+	lines = parity.assert_tables_match(ref, got, columns=cols, context=name)
+	report(name, lines)
+	parity.check_against_digest(name, got, [t['name'] for t in tables])
+
+
+@pytest.mark.parametrize('mode', ['cli'])
+def test_cli_unrelated_correction(mode):
+	from oracle import nway_oracle as O
+	for name, radius in (('syn3', 8), ('syn4', 6), ('cosmos3', 20)):
+		got = run_cuda(cases.build_case(name), radius, 0.9, unrelated_mode=mode)
+		ref = O.nway_match(cases.build_case(name), radius, 0.9, unrelated_mode=mode)
+		cols = [c for c in ref if not c.startswith('_')]
+		changed = (ref['dist_bayesfactor'] != ref['dist_bayesfactor_uncorrected']).sum()
+		assert changed > 0
+		report(name + '/cli', parity.assert_tables_match(ref, got, columns=cols, context=name + '/cli'))
+
+
+def test_allsky_poles_and_wraparound():
+	"""complete on the whole sphere: primaries at the poles, across ra = 0/360 and everywhere else; the oracle's
+	KD-tree enumerator is the all-sky stand-in for the reference's HEALPix branch (healpy is un-vendored)."""
+	from oracle import nway_oracle as O
+	rng = np.random.default_rng(77)
+	tables = cases.allsky(78, (3000, 200000, 150000), (5.0, 3.0, 4.0))
+	# force difficult primaries
+	p = tables[0]
+	p['ra'][:6] = [0.0, 359.99999, 0.00001, 123.0, 250.0, 180.0]
+	p['dec'][:6] = [0.0, 10.0, -45.0, 89.9999, -89.99995, 90.0]
+	# secondaries clustered around them
+	for t in tables[1:]:
+		n = 400
+		k = rng.integers(0, 6, n)
+		rad = np.radians(rng.uniform(0, 0.12, n))
+		ang = rng.uniform(0, 2 * np.pi, n)
+		dec = p['dec'][k] + np.degrees(rad * np.cos(ang))
+		over = dec > 90
+		dec[over] = 180 - dec[over]
+		under = dec < -90
+		dec[under] = -180 - dec[under]
+		cosd = np.maximum(np.cos(np.radians(p['dec'][k])), 1e-6)
+		ra = (p['ra'][k] + np.degrees(rad * np.sin(ang)) / cosd + np.where(over | under, 180, 0)) % 360
+		t['ra'][:n] = ra
+		t['dec'][:n] = dec
+	radius = 300.0
+	got = run_cuda(tables, radius, 0.8)
+	ref = O.nway_match(tables, radius, 0.8)
+	cols = [c for c in ref if not c.startswith('_')]
+	report('allsky', parity.assert_tables_match(ref, got, columns=cols, context='allsky'))
+	assert (np.bincount(got['A'], minlength=6)[:6] > 1).all(), 'the pole / wrap primaries must have found counterparts'
+
+
+def test_ragged_and_degenerate_inputs():
+	from oracle import nway_oracle as O
+	import nway_b200
+	# a primary catalogue of one source; empty secondary lists for most; a secondary exactly on top of a primary
+	tables = cases.uniform_patch(3, (1, 50), (1.0, 0.5), 0.01)
+	tables[1]['ra'][0] = tables[0]['ra'][0]
+	tables[1]['dec'][0] = tables[0]['dec'][0]
+	got = run_cuda(tables, 10.0, 0.9)
+	ref = O.nway_match(tables, 10.0, 0.9)
+	parity.assert_tables_match(ref, got, columns=[c for c in ref if not c.startswith('_')], context='single primary')
+	# no secondary anywhere near: every group is the lone no-counterpart row (flag 1, p_any 0)
+	tables = cases.uniform_patch(4, (20, 30), (1.0, 0.5), 0.01)
+	tables[1]['dec'] = tables[1]['dec'] + 5.0
+	got = run_cuda(tables, 3.0, 0.9)
+	assert len(got['A']) == 20 and (got['B'] == -1).all() and (got['match_flag'] == 1).all() and (got['prob_has_match'] == 0).all()
+	# an empty secondary catalogue
+	tables = cases.uniform_patch(4, (20, 30, 0), (1.0, 0.5, 0.5), 0.01)
+	got = run_cuda(tables, 30.0, 0.9)
+	ref = O.nway_match(tables, 30.0, 0.9)
+	parity.assert_tables_match(ref, got, columns=[c for c in ref if not c.startswith('_')], context='empty third catalogue')
+	assert (got['C'] == -1).all()
+
+
+def test_sharded_primary_ranges_concatenate_to_the_full_table():
+	"""groups never span shards, so per-shard tables concatenate to the single-device table."""
+	tables = cases.build_case('syn3')
+	full = run_cuda(tables, 8, 0.9)
+	n0 = len(tables[0]['ra'])
+	parts = []
+	for first, count in ((0, 100), (100, 257), (357, n0 - 357)):
+		parts.append(run_cuda(cases.build_case('syn3'), 8, 0.9, primary_range=(first, count)))
+	for c in full:
+		cat = np.concatenate([p[c] for p in parts])
+		assert len(cat) == len(full[c])
+		assert ((cat == full[c]) | (np.isnan(cat.astype(float)) & np.isnan(full[c].astype(float)))).all(), c
+
+
+def test_elementwise_surface():
+	from nway_b200 import fastskymatch, bayesdistance
+	k = parity.load_golden('kat.npz')
+	d = fastskymatch.dist((k['dist_ra1'], k['dist_dec1']), (k['dist_ra2'], k['dist_dec2']))
+	ref = k['dist_out']
+	# separations far from 0 and 180 deg are well conditioned: a few ulp
+	ok = np.abs(d - ref) <= 1e-9 * np.abs(ref) + 1e-15
+	assert ok.all(), (d[~ok][:5], ref[~ok][:5])
+	for n in (1, 2, 3, 4):
+		s, p = k['logbf%d_s' % n], k['logbf%d_p' % n]
+		out = bayesdistance.log_bf([[p[i][j] for j in range(n)] for i in range(n)], list(s))
+		assert np.allclose(out, k['logbf%d_out' % n], rtol=1e-12, atol=1e-11)
+	out = bayesdistance.posterior(k['post_prior'], k['post_logbf'])
+	assert np.allclose(out, k['post_out'], rtol=1e-10, atol=0)

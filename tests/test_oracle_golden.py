@@ -11,26 +11,8 @@ from tests import cases, parity
 GOLDEN = cases.GOLDEN_DIR
 
 
-def load(name):
-	return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
-
-
-def check_against_digest(name, got, names):
-	g = load('ref_%s.npz' % name)
-	idx = np.stack([got[n] for n in names], axis=1).astype(np.int64)
-	assert len(idx) == int(g['nrows'])
-	sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(idx).tobytes()).digest(), dtype=np.uint8)
-	assert (sha == g['idx_sha256']).all(), 'row set / order differs from the reference'
-	starts = O.group_starts(idx[:, 0])
-	ok, dabs, drel, worst = parity.column_error('prob_has_match', g['p_any'], np.asarray(got['prob_has_match'])[starts])
-	assert ok, ('p_any', name, worst, dabs, drel)
-	sel = g['sample_rows']
-	ref = {str(c): g['col_' + str(c)] for c in g['columns']}
-	parity.assert_tables_match(ref, {c: np.asarray(got[c])[sel] for c in ref}, context=name)
-	for c in ref:
-		v = np.asarray(got[c])
-		s = np.nansum(v[np.isfinite(v)]) if v.dtype.kind == 'f' else v.sum()
-		assert np.isclose(float(s), float(g['sum_' + c]), rtol=1e-9, atol=1e-9), (name, c, s, g['sum_' + c])
+load = parity.load_golden
+check_against_digest = parity.check_against_digest
 
 
 @pytest.mark.parametrize('name', list(cases.GOLDEN_CASES))
