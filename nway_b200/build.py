@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
 	nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 	cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB, '-lcudart']
 	res = subprocess.run(cmd, capture_output=True, text=True)
-	if verbose or res.returncode != 0:
+	if res.returncode != 0 or (verbose and os.environ.get("NWB_BUILD_VERBOSE")):
 		sys.stderr.write(res.stdout + res.stderr)
 	if res.returncode != 0:
 		raise RuntimeError('nvcc failed building libnwayb200.so')

@@ -57,6 +57,10 @@ struct nwb_ctx {
 	DevBuf d_tables, d_prim, d_red, d_bands, d_cellcnt, d_cstart, d_entries, d_cub, d_pairs, d_paircount;
 	DevBuf d_cnt[MAXC], d_segoff[MAXC], d_seg_s[MAXC], d_seg_sep[MAXC], d_Ls[MAXC], d_Lsep[MAXC], d_Ltrig[MAXC];
 	DevBuf d_rows, d_rowoff, d_matsz, d_matoff, d_mat, d_cols, d_cols2, d_keep, d_keeppos, d_misc;
+	DevBuf d_spill, d_status, d_spilloff[MAXC], d_spillseg[MAXC];
+	size_t entries_cap = 0;
+	unsigned long long spill_cap = 0;
+	long long *h_status = nullptr;   // pinned
 
 	// result
 	bool matched = false, finalized = false;
@@ -215,8 +219,7 @@ int upload_tables(nwb_ctx *ctx)
 // choose the band grid from the primaries' bounding box (host side, tiny)
 struct HostGrid {
 	Grid g;
-	std::vector<int> nra, base;
-	std::vector<double> inv_w;
+	std::vector<BandRec> bands;
 };
 
 void build_grid(const double red[6], double rb_ins, double cell_min_deg, long long max_cells, HostGrid &H)
@@ -242,7 +245,7 @@ void build_grid(const double red[6], double rb_ins, double cell_min_deg, long lo
 	g.dec_lo = dec_lo;
 	g.inv_h = 1.0 / s;
 	g.nbands = nb;
-	H.nra.resize(nb); H.base.resize(nb); H.inv_w.resize(nb);
+	H.bands.resize(nb);
 	long long tot = 0;
 	for (int b = 0; b < nb; b++) {
 		double mid = dec_lo + (b + 0.5) * s;
@@ -250,12 +253,34 @@ void build_grid(const double red[6], double rb_ins, double cell_min_deg, long lo
 		double w = s / std::max(c, 1e-6);
 		long long n = (long long) std::floor(g.ra_span / w);
 		n = std::max<long long>(1, std::min<long long>(n, 1 << 24));
-		H.nra[b] = (int) n;
-		H.base[b] = (int) tot;
-		H.inv_w[b] = (double) n / g.ra_span;
+		H.bands[b].nra = (int) n;
+		H.bands[b].base = (int) tot;
+		H.bands[b].inv_w = (double) n / g.ra_span;
 		tot += n;
 	}
 	g.ncells = tot;
+}
+
+// constants of the fp32 flat pre-test (see struct Entry): rr2 and the pole cut-off tau_max
+void pretest_constants(Grid &g, double rb_deg)
+{
+	const double theta = rb_deg * M_PI / 180;
+	double tau_max = 0.02;
+	double kappa;
+	if (theta > 0.02) {
+		tau_max = -1.0;   // large radii: every primary is pre-tested on declination only
+		kappa = 0.0;
+	} else {
+		double f = (1 - theta * theta / 2 - tau_max) * (1 - (theta + tau_max) * (theta + tau_max) / 12);
+		kappa = 1 / std::sqrt(f) - 1 + 1e-6;
+	}
+	const double dspan = (double) g.nbands / g.inv_h;
+	const double slack = std::ldexp(std::max(g.ra_span, dspan), -21) + 1e-9;   // fp32 rounding of the relative coordinates
+	const double rr = rb_deg * (1 + kappa) + 1.5 * slack;
+	g.rr2 = std::nextafter((float) (rr * rr * (1 + 1e-6)), INFINITY);
+	g.ra_org_n = g.ra_org - 360.0 * std::floor(g.ra_org / 360.0);
+	if (g.ra_org_n >= 360.0 || g.ra_org_n < 0.0) g.ra_org_n = 0.0;
+	g.tau_max = tau_max;
 }
 
 inline int grid_for(long long n, int block) { return (int) std::min<long long>((n + block - 1) / block, 1 << 30); }
@@ -364,12 +389,14 @@ void nwb_destroy(nwb_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *single[] = {&ctx->d_tables, &ctx->d_prim, &ctx->d_red, &ctx->d_bands, &ctx->d_cellcnt, &ctx->d_cstart,
 		&ctx->d_entries, &ctx->d_cub, &ctx->d_pairs, &ctx->d_paircount, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_matsz,
-		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc};
+		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc, &ctx->d_spill, &ctx->d_status};
 	for (DevBuf *b : single) release(*b);
 	for (int c = 0; c < MAXC; c++) {
 		release(ctx->d_cnt[c]); release(ctx->d_segoff[c]); release(ctx->d_seg_s[c]); release(ctx->d_seg_sep[c]);
 		release(ctx->d_Ls[c]); release(ctx->d_Lsep[c]); release(ctx->d_Ltrig[c]); release(ctx->cat[c].own);
+		release(ctx->d_spilloff[c]); release(ctx->d_spillseg[c]);
 	}
+	if (ctx->h_status) cudaFreeHost(ctx->h_status);
 	for (auto &ev : ctx->ev) cudaEventDestroy(ev);
 	for (auto &ev : ctx->kev) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
@@ -527,9 +554,11 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	{ int r = upload_tables(ctx); if (r) return r; }
 	const bool cli = ctx->unrelated_mode == NWB_UNRELATED_CLI && nc >= 3;
 	const bool fuse = fuse_final && !cli;
+	if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocDefault));
+	long long *hs = ctx->h_status;
 
 	CU(cudaEventRecord(ctx->ev[0], st));
-	// ---- K0: primaries -> grid ---------------------------------------------------------------------------
+	// ---- K0: primaries -> bounding box (the one unavoidable early sync: the grid geometry is chosen on the host)
 	const double r_deg = ctx->radius / 3600.0;
 	const double rb = r_deg * (1 + 1e-9) + 1e-12;
 	const double rb_ins = rb + 1e-9, dra_eps = 1e-9;
@@ -544,155 +573,179 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	double *d_red = (double *) ctx->d_red.p;
 	LAUNCH(ctx, k_prim_prep, pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red + 8);
 	LAUNCH(ctx, k_reduce6, 1, 32, pblocks, d_red + 8, d_red);
-	double red[6];
-	CU(cudaMemcpyAsync(red, d_red, sizeof(red), cudaMemcpyDeviceToHost, st));
+	double *red = (double *) (hs + 32);
+	CU(cudaMemcpyAsync(red, d_red, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	HostGrid HG;
 	long long max_cells = 4ll << 20;
 	build_grid(red, rb_ins, rb_ins, max_cells, HG);
+	pretest_constants(HG.g, rb_ins);
 	Grid G = HG.g;
 	{
 		size_t nb = (size_t) G.nbands;
-		ENSURE(ctx->d_bands, nb * (sizeof(int) * 2 + sizeof(double)) + 64);
-		char *b = (char *) ctx->d_bands.p;
-		double *d_invw = (double *) b;
-		int *d_nra = (int *) (b + nb * sizeof(double));
-		int *d_base = d_nra + nb;
-		CU(cudaMemcpyAsync(d_invw, HG.inv_w.data(), nb * sizeof(double), cudaMemcpyHostToDevice, st));
-		CU(cudaMemcpyAsync(d_nra, HG.nra.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
-		CU(cudaMemcpyAsync(d_base, HG.base.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
-		G.inv_w = d_invw; G.nra = d_nra; G.base = d_base;
+		ENSURE(ctx->d_bands, nb * sizeof(BandRec) + 64);
+		CU(cudaMemcpyAsync(ctx->d_bands.p, HG.bands.data(), nb * sizeof(BandRec), cudaMemcpyHostToDevice, st));
+		G.bands = (const BandRec *) ctx->d_bands.p;
 	}
-	size_t ncell1 = (size_t) G.ncells + 1;
-	ENSURE(ctx->d_cellcnt, ncell1 * sizeof(int));
+	// one zero-initialised block: cell counters | per-catalogue match counters | scalar counters
+	const size_t ncell1 = (size_t) G.ncells + 1;
+	const size_t cnt_stride = ((size_t) np + 1 + 3) / 4 * 4;
+	const size_t zero_ints = (ncell1 + 3) / 4 * 4 + cnt_stride * (nc - 1) + 4 * MAXC;
+	ENSURE(ctx->d_cellcnt, zero_ints * sizeof(int));
 	ENSURE(ctx->d_cstart, ncell1 * sizeof(int));
 	int *d_cellcnt = (int *) ctx->d_cellcnt.p, *d_cstart = (int *) ctx->d_cstart.p;
-	CU(cudaMemsetAsync(d_cellcnt, 0, ncell1 * sizeof(int), st));
-	LAUNCH(ctx, (k_prim_cells<false>), pblocks, 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) nullptr, (Entry *) nullptr);
-	{ int r = scan_int(ctx, d_cellcnt, d_cstart, (int64_t) ncell1); if (r) return r; }
-	int nentries = 0;
-	CU(cudaMemcpyAsync(&nentries, d_cstart + G.ncells, sizeof(int), cudaMemcpyDeviceToHost, st));
-	CU(cudaMemsetAsync(d_cellcnt, 0, ncell1 * sizeof(int), st));
-	CU(cudaStreamSynchronize(st));
-	ENSURE(ctx->d_entries, std::max<size_t>(1, nentries) * sizeof(Entry));
-	Entry *d_entries = (Entry *) ctx->d_entries.p;
-	LAUNCH(ctx, (k_prim_cells<true>), pblocks, 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) d_cstart, d_entries);
-	ctx->stats[2] = G.ncells;
-	ctx->stats[3] = nentries;
-	CU(cudaEventRecord(ctx->ev[1], st));
+	int *d_cnt[MAXC] = {nullptr};
+	for (int c = 1; c < nc; c++) d_cnt[c] = d_cellcnt + (ncell1 + 3) / 4 * 4 + cnt_stride * (c - 1);
+	unsigned long long *d_spillcount = (unsigned long long *) (d_cellcnt + (ncell1 + 3) / 4 * 4 + cnt_stride * (nc - 1));
 
-	// ---- K1: stream the secondaries ------------------------------------------------------------------------
-	// one append buffer per secondary catalogue, sized from the expected pair density and grown on overflow
-	ENSURE(ctx->d_paircount, MAXC * sizeof(unsigned long long));
-	unsigned long long *d_paircount = (unsigned long long *) ctx->d_paircount.p;
-	unsigned long long h_paircount[MAXC] = {0};
-	std::vector<size_t> pair_off(nc + 1, 0);
-	std::vector<unsigned long long> cap(nc, 0);
+	// slots per primary and catalogue: expected matches + 6 sigma (a uniform field almost never spills)
+	int Cs[MAXC] = {0};
+	size_t base_off[MAXC + 1] = {0};
 	const double disc_deg2 = M_PI * r_deg * r_deg;
-	bool again = true;
-	for (int attempt = 0; again && attempt < 3; attempt++) {
-		size_t tot = 0;
+	for (int c = 1; c < nc; c++) {
+		double mu = (double) ctx->cat[c].n * disc_deg2 / ctx->cat[c].area;
+		double want = std::ceil(mu + 6 * std::sqrt(mu) + 2);
+		double cap_mem = std::floor(6e9 / 16.0 / (double) np / (nc - 1));
+		int C = (int) std::max(2.0, std::min(std::min(want, cap_mem), 1e6));
+		C = (C + 1) / 2 * 2;
+		if (ctx->cat[c].n == 0) C = 2;
+		Cs[c] = C;
+		base_off[c + 1] = base_off[c] + (size_t) np * C;
+	}
+	ENSURE(ctx->d_pairs, std::max<size_t>(1, base_off[nc]) * sizeof(Slot16));
+	Slot16 *d_base = (Slot16 *) ctx->d_pairs.p;
+	if (ctx->spill_cap < 65536) ctx->spill_cap = 65536;
+	if (ctx->entries_cap < (size_t) np * 12 + 4096) ctx->entries_cap = (size_t) np * 12 + 4096;
+	ENSURE(ctx->d_rows, (size_t) (np + 1) * sizeof(long long));
+	ENSURE(ctx->d_rowoff, (size_t) (np + 1) * sizeof(long long));
+	long long *d_rows = (long long *) ctx->d_rows.p, *d_rowoff = (long long *) ctx->d_rowoff.p;
+	ENSURE(ctx->d_status, 64 * sizeof(long long));
+	long long *d_status = (long long *) ctx->d_status.p;
+
+	PairStore stores[MAXC];
+	memset(stores, 0, sizeof(stores));
+	long long R = 0;
+	bool done = false;
+	for (int attempt = 0; !done && attempt < 4; attempt++) {
+		ENSURE(ctx->d_entries, ctx->entries_cap * sizeof(Entry));
+		ENSURE(ctx->d_spill, (size_t) ctx->spill_cap * (nc - 1) * sizeof(SpillRec));
+		Entry *d_entries = (Entry *) ctx->d_entries.p;
+		SpillRec *d_spill = (SpillRec *) ctx->d_spill.p;
+		CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
+		LAUNCH(ctx, (k_prim_cells<false>), pblocks, 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) nullptr,
+			(Entry *) nullptr, (long long) 0);
+		{ int r = scan_int(ctx, d_cellcnt, d_cstart, (int64_t) ncell1); if (r) return r; }
+		LAUNCH(ctx, (k_prim_cells<true>), pblocks, 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) d_cstart,
+			d_entries, (long long) ctx->entries_cap);
+		if (attempt == 0) CU(cudaEventRecord(ctx->ev[1], st));
+
+		// ---- K1: stream the secondaries ----------------------------------------------------------------
 		for (int c = 1; c < nc; c++) {
-			if (attempt == 0) {
-				double expect = (double) np * (double) ctx->cat[c].n * disc_deg2 / ctx->cat[c].area;
-				unsigned long long want = (unsigned long long) (expect * 1.3) + 65536 + (unsigned long long) np;
-				// keep a previously grown capacity
-				cap[c] = std::max<unsigned long long>(want, 0);
-			} else if (h_paircount[c] > cap[c]) {
-				cap[c] = h_paircount[c] + 1024;
-			}
-			pair_off[c] = tot;
-			tot += cap[c];
-		}
-		pair_off[nc] = tot;
-		ENSURE(ctx->d_pairs, std::max<size_t>(1, tot) * sizeof(PairRec));
-		CU(cudaMemsetAsync(d_paircount, 0, MAXC * sizeof(unsigned long long), st));
-		for (int c = 1; c < nc; c++) {
-			ENSURE(ctx->d_cnt[c], (size_t) (np + 1) * sizeof(int));
-			CU(cudaMemsetAsync(ctx->d_cnt[c].p, 0, (size_t) (np + 1) * sizeof(int), st));
 			int64_t n = ctx->cat[c].n;
+			stores[c].base = d_base + base_off[c];
+			stores[c].C = Cs[c];
+			stores[c].cnt = d_cnt[c];
+			stores[c].spill_off = nullptr;
+			stores[c].spill = nullptr;
 			if (n == 0) continue;
-			int grid = (int) std::min<int64_t>((n + 255) / 256, 148 * 8 * 4);
+			int grid = (int) std::min<int64_t>((n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), 148 * 5);
 			CU(cudaEventRecord(ctx->kev[2 * c], st));
-			LAUNCH(ctx, k_pairs, grid, 256, (long long) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_cstart,
-				(const Entry *) d_entries, P, rb, ctx->radius, (PairRec *) ctx->d_pairs.p + pair_off[c], cap[c],
-				d_paircount + c, (int *) ctx->d_cnt[c].p);
+			LAUNCH(ctx, k_pairs, grid, K1_WARPS * 32, (long long) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_cstart,
+				(const Entry *) d_entries, (long long) ctx->entries_cap, P, ctx->radius, d_base + base_off[c], Cs[c], d_cnt[c],
+				d_spill + (size_t) ctx->spill_cap * (c - 1), (unsigned long long) ctx->spill_cap, d_spillcount + c);
 			CU(cudaEventRecord(ctx->kev[2 * c + 1], st));
 		}
-		CU(cudaMemcpyAsync(h_paircount, d_paircount, sizeof(h_paircount), cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
-		again = false;
-		for (int c = 1; c < nc; c++) if (h_paircount[c] > cap[c]) again = true;
-	}
-	if (again) return fail(ctx, NWB_ERR_NOMEM, "pair buffer overflow persisted");
-	ctx->stats[1] = 0;
-	for (int c = 1; c < nc; c++) ctx->stats[1] += (int64_t) h_paircount[c];
-	CU(cudaEventRecord(ctx->ev[2], st));
-
-	// ---- lists: scan, scatter, sort ------------------------------------------------------------------------
-	Lists L;
-	memset(&L, 0, sizeof(L));
-	const bool trig = nc > 2;
-	int wgrid = std::max(1, (int) std::min<int64_t>((np * 32 + 255) / 256, 148 * 64));
-	for (int c = 1; c < nc; c++) {
-		size_t npair = (size_t) h_paircount[c];
-		ENSURE(ctx->d_segoff[c], (size_t) (np + 1) * sizeof(long long));
-		long long *off = (long long *) ctx->d_segoff[c].p;
-		{ int r = scan_int_to_ll(ctx, (const int *) ctx->d_cnt[c].p, off, np + 1); if (r) return r; }
-		ENSURE(ctx->d_seg_s[c], std::max<size_t>(1, npair) * sizeof(int));
-		ENSURE(ctx->d_seg_sep[c], std::max<size_t>(1, npair) * sizeof(double));
-		ENSURE(ctx->d_Ls[c], std::max<size_t>(1, npair) * sizeof(int));
-		ENSURE(ctx->d_Lsep[c], std::max<size_t>(1, npair) * sizeof(double));
-		if (trig) ENSURE(ctx->d_Ltrig[c], std::max<size_t>(1, npair) * 3 * sizeof(double));
-		CU(cudaMemsetAsync(ctx->d_cnt[c].p, 0, (size_t) (np + 1) * sizeof(int), st));
-		double *tr = trig ? (double *) ctx->d_Ltrig[c].p : nullptr;
-		if (npair) {
-			LAUNCH(ctx, k_scatter, grid_for((long long) npair, 256), 256, (long long) npair,
-				(const PairRec *) ctx->d_pairs.p + pair_off[c], (const long long *) off, (int *) ctx->d_cnt[c].p,
-				(int *) ctx->d_seg_s[c].p, (double *) ctx->d_seg_sep[c].p);
-			if (trig)
-				LAUNCH(ctx, (k_sort_lists<true>), wgrid, 256, (int) np, (const long long *) off, (const int *) ctx->d_seg_s[c].p,
-					(const double *) ctx->d_seg_sep[c].p, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
-					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair);
-			else
-				LAUNCH(ctx, (k_sort_lists<false>), wgrid, 256, (int) np, (const long long *) off, (const int *) ctx->d_seg_s[c].p,
-					(const double *) ctx->d_seg_sep[c].p, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
-					ctx->cat[c].ra, ctx->cat[c].dec, (double *) nullptr, (double *) nullptr, (double *) nullptr);
+		if (attempt == 0) CU(cudaEventRecord(ctx->ev[2], st));
+		if (nc == 2) {
+			CU(cudaMemsetAsync(d_rows + np, 0, sizeof(long long), st));
+			LAUNCH(ctx, k_rows_per_primary_2, pblocks, 256, (int) np, (const int *) d_cnt[1], d_rows);
+			{ int r = scan_ll(ctx, d_rows, d_rowoff, np + 1); if (r) return r; }
 		}
-		L.off[c] = off;
-		L.s[c] = (const int *) ctx->d_Ls[c].p;
-		L.sep[c] = (const double *) ctx->d_Lsep[c].p;
-		L.lon[c] = tr; L.slat[c] = tr ? tr + npair : nullptr; L.clat[c] = tr ? tr + 2 * npair : nullptr;
+		LAUNCH(ctx, k_collect_status, 1, 32, nc, (const int *) d_cstart + G.ncells, (const unsigned long long *) d_spillcount,
+			nc == 2 ? (const long long *) d_rowoff + np : (const long long *) nullptr, d_status);
+		CU(cudaMemcpyAsync(hs, d_status, 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		done = true;
+		if ((size_t) hs[0] > ctx->entries_cap) { ctx->entries_cap = (size_t) hs[0] + 1024; done = false; }
+		for (int c = 1; c < nc; c++)
+			if ((unsigned long long) hs[c] > ctx->spill_cap) { ctx->spill_cap = (unsigned long long) hs[c] + 1024; done = false; }
+		R = hs[8];
+		ctx->stats[3] = hs[0];
 	}
-	CU(cudaEventRecord(ctx->ev[3], st));
+	if (!done) return fail(ctx, NWB_ERR_NOMEM, "grid / spill buffers kept overflowing");
+	ctx->stats[2] = G.ncells;
+	const Entry *d_entries = (const Entry *) ctx->d_entries.p;
+	(void) d_entries;
 
-	// ---- K2: rows ------------------------------------------------------------------------------------------
+	// ---- overflowed primaries (rare): spill records -> per-primary spill segments ------------------------
+	for (int c = 1; c < nc; c++) {
+		long long nsp = hs[c];
+		if (nsp == 0) continue;
+		ENSURE(ctx->d_spilloff[c], (size_t) (np + 1) * sizeof(long long));
+		ENSURE(ctx->d_spillseg[c], (size_t) nsp * sizeof(Slot16));
+		ENSURE(ctx->d_matsz, (size_t) (np + 1) * sizeof(long long));
+		int *sizes = (int *) ctx->d_matsz.p;
+		CU(cudaMemsetAsync(sizes, 0, (size_t) (np + 1) * sizeof(int), st));
+		LAUNCH(ctx, k_spill_sizes, pblocks, 256, (int) np, (const int *) d_cnt[c], Cs[c], sizes);
+		{ int r = scan_int_to_ll(ctx, sizes, (long long *) ctx->d_spilloff[c].p, np + 1); if (r) return r; }
+		LAUNCH(ctx, k_spill_scatter, grid_for(nsp, 256), 256, nsp, (const SpillRec *) ctx->d_spill.p + (size_t) ctx->spill_cap * (c - 1),
+			Cs[c], (const long long *) ctx->d_spilloff[c].p, (Slot16 *) ctx->d_spillseg[c].p);
+		stores[c].spill_off = (const long long *) ctx->d_spilloff[c].p;
+		stores[c].spill = (const Slot16 *) ctx->d_spillseg[c].p;
+	}
+
 	RowParams &rp = ctx->rp;
 	memset(&rp, 0, sizeof(rp));
 	rp.ncat = nc; rp.nmag = ctx->res_nmag; rp.np = (int) np; rp.first = first;
 	rp.radius = ctx->radius; rp.ratio_secondary = ctx->ratio_secondary;
 	for (int c = 0; c < nc; c++) rp.err[c] = ctx->cat[c].err;
 	rp.T = (const ConstTables *) ctx->d_tables.p;
-	rp.L = L;
-	ENSURE(ctx->d_rows, (size_t) (np + 1) * sizeof(long long));
-	ENSURE(ctx->d_rowoff, (size_t) (np + 1) * sizeof(long long));
-	long long *d_rows = (long long *) ctx->d_rows.p, *d_rowoff = (long long *) ctx->d_rowoff.p;
-	CU(cudaMemsetAsync(d_rows, 0, (size_t) (np + 1) * sizeof(long long), st));
-	if (nc == 2) {
-		LAUNCH(ctx, k_rows_per_primary_2, pblocks, 256, (int) np, L.off[1], d_rows);
-	} else {
+	rp.S1 = stores[1];
+	int wgrid = std::max(1, (int) std::min<int64_t>((np * 32 + 255) / 256, 148 * 64));
+	ctx->stats[1] = 0;
+
+	if (nc > 2) {
+		// ---- lists: N >= 3 needs the matches sorted and compact -----------------------------------------
+		Lists L;
+		memset(&L, 0, sizeof(L));
+		for (int c = 1; c < nc; c++) {
+			ENSURE(ctx->d_segoff[c], (size_t) (np + 1) * sizeof(long long));
+			long long *off = (long long *) ctx->d_segoff[c].p;
+			{ int r = scan_int_to_ll(ctx, (const int *) d_cnt[c], off, np + 1); if (r) return r; }   // cnt[np] == 0
+			CU(cudaMemcpyAsync(hs + 16 + c, off + np, sizeof(long long), cudaMemcpyDeviceToHost, st));
+		}
+		CU(cudaStreamSynchronize(st));
+		for (int c = 1; c < nc; c++) {
+			size_t npair = (size_t) hs[16 + c];
+			ctx->stats[1] += (int64_t) npair;
+			ENSURE(ctx->d_Ls[c], std::max<size_t>(1, npair) * sizeof(int));
+			ENSURE(ctx->d_Lsep[c], std::max<size_t>(1, npair) * sizeof(double));
+			ENSURE(ctx->d_Ltrig[c], std::max<size_t>(1, npair) * 3 * sizeof(double));
+			double *tr = (double *) ctx->d_Ltrig[c].p;
+			const long long *off = (const long long *) ctx->d_segoff[c].p;
+			if (npair)
+				LAUNCH(ctx, k_sort_lists, wgrid, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
+					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair);
+			L.off[c] = off;
+			L.s[c] = (const int *) ctx->d_Ls[c].p;
+			L.sep[c] = (const double *) ctx->d_Lsep[c].p;
+			L.lon[c] = tr; L.slat[c] = tr + npair; L.clat[c] = tr + 2 * npair;
+		}
+		rp.L = L;
+		CU(cudaEventRecord(ctx->ev[3], st));
 		ENSURE(ctx->d_matsz, (size_t) (np + 1) * sizeof(long long));
 		ENSURE(ctx->d_matoff, (size_t) (np + 1) * sizeof(long long));
 		long long *d_matsz = (long long *) ctx->d_matsz.p, *d_matoff = (long long *) ctx->d_matoff.p;
 		CU(cudaMemsetAsync(d_matsz, 0, (size_t) (np + 1) * sizeof(long long), st));
 		LAUNCH(ctx, k_mat_sizes, pblocks, 256, (int) np, nc, L, d_matsz);
 		{ int r = scan_ll(ctx, d_matsz, d_matoff, np + 1); if (r) return r; }
-		long long mat_total = 0;
-		CU(cudaMemcpyAsync(&mat_total, d_matoff + np, sizeof(long long), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(hs + 24, d_matoff + np, sizeof(long long), cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
+		long long mat_total = hs[24];
 		ENSURE(ctx->d_mat, std::max<size_t>(1, (size_t) mat_total) * sizeof(double));
 		rp.mat_off = d_matoff;
 		rp.mat = (double *) ctx->d_mat.p;
+		CU(cudaMemsetAsync(d_rows, 0, (size_t) (np + 1) * sizeof(long long), st));
 		int r = 0;
 		switch (nc) {
 			case 3: r = launch_count<3>(ctx, rp, d_rows, wgrid); break;
@@ -703,11 +756,16 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 			default: r = launch_count<8>(ctx, rp, d_rows, wgrid); break;
 		}
 		if (r) return r;
+		{ int r2 = scan_ll(ctx, d_rows, d_rowoff, np + 1); if (r2) return r2; }
+		CU(cudaMemcpyAsync(hs + 25, d_rowoff + np, sizeof(long long), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		R = hs[25];
+	} else {
+		ctx->stats[1] = R - np;
+		CU(cudaEventRecord(ctx->ev[3], st));
 	}
-	{ int r = scan_ll(ctx, d_rows, d_rowoff, np + 1); if (r) return r; }
-	long long R = 0;
-	CU(cudaMemcpyAsync(&R, d_rowoff + np, sizeof(long long), cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
+
+	// ---- K2: rows ------------------------------------------------------------------------------------------
 	rp.row_off = d_rowoff;
 	ctx->res_ncat = nc;
 	{ int r = layout_columns(ctx, ctx->d_cols, R, nc, ctx->res_nmag, ctx->cols, ctx->ncols); if (r) return r; }
@@ -716,7 +774,12 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	{
 		int r = 0;
 		switch (nc) {
-			case 2: r = launch_rows<2>(ctx, rp, fuse, wgrid); break;
+			case 2: {
+				int grid2 = (int) std::min<int64_t>((np + R2_WARPS - 1) / R2_WARPS, 148 * 4);
+				if (fuse) LAUNCH(ctx, (k_rows2<true>), grid2, R2_WARPS * 32, rp);
+				else LAUNCH(ctx, (k_rows2<false>), grid2, R2_WARPS * 32, rp);
+				break;
+			}
 			case 3: r = launch_rows<3>(ctx, rp, fuse, wgrid); break;
 			case 4: r = launch_rows<4>(ctx, rp, fuse, wgrid); break;
 			case 5: r = launch_rows<5>(ctx, rp, fuse, wgrid); break;
@@ -745,6 +808,7 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	ctx->matched = true;
 	ctx->finalized = fuse_final != 0;
 	if (nrows) *nrows = R;
+	if (R == 0) return fail(ctx, NWB_ERR_EMPTY, "No matches.");
 	return NWB_OK;
 }
 

@@ -3,10 +3,10 @@
 // Pipeline (one shard of primaries per context):
 //   k_prim_prep     per primary: lon, sin/cos(lat), search box           -> P_* arrays           (K0)
 //   k_prim_cells    count / fill: primary -> every grid cell its box overlaps                    (K0)
-//   k_pairs         stream a secondary catalogue once: cell -> box test -> exact separation,
-//                   warp-aggregated append of (primary, secondary, sep)                          (K1)
-//   k_scatter       pair records -> per-primary segments                                         (K1)
-//   k_sort_lists    per primary: rank-sort the segment by secondary index                        (K1)
+//   k_pairs         stream a secondary catalogue once: cell -> box test -> per-warp candidate queue ->
+//                   dense exact separations -> (secondary, sep) straight into the primary's slot (K1)
+//   k_spill_*       the rare primaries with more matches than slots: overflow records -> segments (K1)
+//   k_sort_lists    N >= 3: per primary rank-sort by secondary index into compact lists          (K1)
 //   k_count_rows    N >= 3: secondary-secondary separations + number of valid tuples             (K2)
 //   k_rows          per primary: enumerate tuples in lexicographic order, score, write columns;
 //                   optionally fused with the group normalisation                                (K2[+K3])
@@ -20,46 +20,88 @@ namespace nwb {
 // ---------------------------------------------------------------------------------------------------------
 // grid over (ra, dec): declination bands of height h, each cut into nra[b] cells along ra
 // ---------------------------------------------------------------------------------------------------------
+struct BandRec {   // 16 bytes, one load
+	int base;       // first cell of the band
+	int nra;        // cells along ra
+	double inv_w;   // cells per degree of ra
+};
+
 struct Grid {
 	double dec_lo, inv_h;
 	double ra_org, ra_span;
+	double ra_org_n;        // ra_org brought into [0, 360)
 	int nbands;
 	int full_circle;
-	const int *nra;         // [nbands]
-	const int *base;        // [nbands] first cell of the band
-	const double *inv_w;    // [nbands] cells per degree of ra
+	const BandRec *bands;   // [nbands]
 	long long ncells;
+	float rr2;              // squared radius (deg^2) of the fp32 flat pre-test, all margins included
+	double tau_max;         // primaries with rb_rad * tan|dec| above this are tested on dec only
 };
 
-struct Entry {   // 32 bytes: one primary as seen from one cell
-	double ra_n, dec, dra;
-	int p, pad;
+// 16 bytes, one load: one primary as seen from one cell, for the fp32 flat PRE-test
+//     (dy)^2 + (clat * dx)^2 <= rr2,     dx, dy relative to the grid origin (small numbers: fp32 is accurate)
+// which is a superset of the exact disc (derivation in DESIGN.md: hav(theta) = hav(ddec) + cos d1 cos d2 hav(dra),
+// cos d2 >= cos d1 (1 - ddec^2/2 - |ddec| tan|d1|)); the exact fp64 separation decides.  Primaries too close to a
+// pole for the flat metric get clat = 0, i.e. they are pre-tested on declination only.
+struct Entry {
+	float x, y, clat;
+	int p;
 };
 
-struct PairRec {   // 16 bytes
-	int p, s;
+struct Slot16 {   // 16 bytes: one match of a primary
+	int s, pad;
 	double sep;
 };
 
+struct SpillRec {   // 24 bytes: a match that did not fit the primary's slots
+	int p, slot, s, pad;
+	double sep;
+};
+
+// where the matches of one secondary catalogue live: C slots per primary, in arrival order (cnt[p] of them are
+// valid), plus -- only if some primary overflowed -- per-primary spill segments.
+struct PairStore {
+	const Slot16 *base;
+	int C;
+	const int *cnt;
+	const long long *spill_off;   // nullptr when nothing spilled
+	const Slot16 *spill;
+};
+
+__device__ __forceinline__ Slot16 store_get(const PairStore &S, int p, int e)
+{
+	if (e < S.C) return S.base[(size_t) p * S.C + e];
+	return S.spill[S.spill_off[p] + (e - S.C)];
+}
+
 __device__ __forceinline__ double wrap360(double x)
 {
-	double y = x - 360.0 * floor(x / 360.0);
+	if (x >= 0.0 && x < 360.0) return x;
+	double y = x - 360.0 * floor(x * (1.0 / 360.0));
 	return (y >= 360.0 || y < 0.0) ? 0.0 : y;
 }
 
 __device__ __forceinline__ int band_of(const Grid &G, double dec)
 {
-	double t = floor((dec - G.dec_lo) * G.inv_h);
+	double t = (dec - G.dec_lo) * G.inv_h;
 	if (!(t >= 0.0)) return -1;
 	if (t >= (double) G.nbands) return G.nbands;
-	return (int) t;
+	return __double2int_rd(t);
 }
 
-__device__ __forceinline__ int racell_of(const Grid &G, int b, double x /* wrap360(ra - ra_org) */)
+__device__ __forceinline__ int racell_of(const BandRec &B, double x /* wrap360(ra - ra_org) */)
 {
-	int n = G.nra[b];
-	int i = (int) (x * G.inv_w[b]);
-	return i >= n ? n - 1 : (i < 0 ? 0 : i);
+	int i = __double2int_rd(x * B.inv_w);
+	return i >= B.nra ? B.nra - 1 : (i < 0 ? 0 : i);
+}
+
+__device__ __forceinline__ BandRec load_band(const Grid &G, int b)
+{
+	const int4 v = __ldg(reinterpret_cast<const int4 *>(G.bands + b));
+	BandRec B;
+	B.base = v.x; B.nra = v.y;
+	B.inv_w = __hiloint2double(v.w, v.z);
+	return B;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -146,44 +188,56 @@ __global__ void k_reduce6(int nblocks, const double *__restrict__ red, double *_
 }
 
 // FILL = false: cellcnt[cell] += 1 for every cell the primary's (slightly inflated) box overlaps.
-// FILL = true : write the entry at cstart[cell] + slot.
+// FILL = true : write the entry at cstart[cell] + slot, the slots being handed out by counting cellcnt back
+// down (no second memset).  If the entry buffer is too small nothing is written; the host sees the total
+// and retries.
 template <bool FILL>
 __global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double dra_eps,
-	int *__restrict__ cellcnt, const int *__restrict__ cstart, Entry *__restrict__ entries)
+	int *__restrict__ cellcnt, const int *__restrict__ cstart, Entry *__restrict__ entries, long long entries_cap)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= np) return;
+	if (FILL && (long long) cstart[G.ncells] > entries_cap) return;
 	double d = P.dec[i], rn = P.ra_n[i], dra = P.dra[i];
 	int b0 = band_of(G, d - rb_ins), b1 = band_of(G, d + rb_ins);
 	b0 = max(b0, 0);
 	b1 = min(b1, G.nbands - 1);
 	Entry en;
-	en.ra_n = rn; en.dec = d; en.dra = dra; en.p = i; en.pad = 0;
+	{
+		double x = rn - G.ra_org_n;
+		if (x < 0.0) x += 360.0;
+		en.x = (float) x;
+		en.y = (float) (d - G.dec_lo);
+		double tau = (rb_ins / 180 * NWB_PI) * tan(fmin(fabs(d), 89.9999) / 180 * NWB_PI);
+		en.clat = (tau > G.tau_max || dra >= 180.0) ? 0.f : __double2float_rd(P.clat[i]);
+		en.p = i;
+	}
 	double di = dra + dra_eps;
 	for (int b = b0; b <= b1; b++) {
-		int n = G.nra[b];
+		BandRec B = load_band(G, b);
+		int n = B.nra;
 		int i0, cnt;
 		double cellw = G.ra_span / n;
 		if (G.full_circle) {
 			if (2 * di + 2 * cellw >= 360.0) { i0 = 0; cnt = n; }
 			else {
-				i0 = racell_of(G, b, wrap360(rn - di - G.ra_org));
-				int i1 = racell_of(G, b, wrap360(rn + di - G.ra_org));
+				i0 = racell_of(B, wrap360(rn - di - G.ra_org));
+				int i1 = racell_of(B, wrap360(rn + di - G.ra_org));
 				cnt = (i1 - i0 + n) % n + 1;
 			}
 		} else {
 			// the grid's ra window was built from min(rn - dra) .. max(rn + dra) with a margin: no wrap inside
 			double x0 = wrap360(rn - G.ra_org) - di, x1 = wrap360(rn - G.ra_org) + di;
-			i0 = racell_of(G, b, fmax(x0, 0.0));
-			int i1 = racell_of(G, b, fmin(x1, G.ra_span));
+			i0 = racell_of(B, fmax(x0, 0.0));
+			int i1 = racell_of(B, fmin(x1, G.ra_span));
 			cnt = i1 - i0 + 1;
 		}
-		int cb = G.base[b];
+		int cb = B.base;
 		for (int k = 0; k < cnt; k++) {
 			int cell = cb + (i0 + k) % n;
 			if (FILL) {
-				int slot = atomicAdd(&cellcnt[cell], 1);
-				entries[cstart[cell] + slot] = en;
+				int slot = atomicSub(&cellcnt[cell], 1) - 1;
+				*reinterpret_cast<int4 *>(entries + cstart[cell] + slot) = *reinterpret_cast<const int4 *>(&en);
 			} else {
 				atomicAdd(&cellcnt[cell], 1);
 			}
@@ -194,118 +248,231 @@ __global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double
 // ---------------------------------------------------------------------------------------------------------
 // K1: stream one secondary catalogue
 // ---------------------------------------------------------------------------------------------------------
-// One thread per secondary source, coalesced streaming loads of (ra, dec) -- 16 algorithmic bytes per source,
-// read exactly once.  The cell lookup and the primary records come from L2-resident tables.  Matches are
-// appended with one atomicAdd per warp.
-__global__ void __launch_bounds__(256)
-k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G,
-	const int *__restrict__ cstart, const Entry *__restrict__ entries, PrimArrays P, double rb, double radius,
-	PairRec *__restrict__ out, unsigned long long cap, unsigned long long *__restrict__ out_count,
-	int *__restrict__ cnt)
+// One thread per secondary source, coalesced streaming loads of (ra, dec): 16 algorithmic bytes per source, read
+// exactly once.  Phase A (cheap, divergent): cell lookup in the L2-resident grid and the box test against the
+// primaries registered in that cell; survivors go into a per-warp shared-memory queue.  Phase B (expensive,
+// dense): whenever the queue holds 32 candidates every lane evaluates one exact separation, so the fp64 pipe
+// runs full warps instead of the 1-5 active lanes a per-thread loop would give.  A match takes the next slot of
+// its primary (atomicAdd on the per-primary counter) and is written there directly -- no append buffer, no
+// scatter pass.
+constexpr int K1_WARPS = 8;
+constexpr int K1_ROUND = 4;                      // cell entries taken per lane and round
+constexpr int K1_ICAP = 32 * (K1_ROUND + 1);     // work items: 31 left over + one full round
+constexpr int K1_QCAP = 64;                      // candidates: 31 left over + 32 new
+constexpr int K1_SBANDS = 1024;                  // bands cached in shared memory (16 KB)
+
+struct K1Smem {   // per warp
+	int4 items[K1_ICAP];   // (x, y) of a secondary as floats, entry index, secondary index
+	int2 cand[K1_QCAP];    // (secondary, primary) that passed the pre-test
+};
+
+// exact fp64 separation for `count` queued candidates, one per lane; a match takes the next slot of its primary
+__device__ __forceinline__ void k1_flush(const K1Smem &M, int lo, int count, int lane,
+	const double *__restrict__ ra, const double *__restrict__ dec, const PrimArrays &P, double radius,
+	Slot16 *__restrict__ base, int C, int *__restrict__ cnt, SpillRec *__restrict__ spill,
+	unsigned long long spill_cap, unsigned long long *__restrict__ spill_count)
 {
-	const int lane = threadIdx.x & 31;
-	long long stride = (long long) gridDim.x * blockDim.x;
-	long long nround = (n + 31) / 32 * 32;
-	for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-		int e0 = 0, e1 = 0;
-		double r = 0, d = 0, rn = 0;
-		if (i < n) {
-			r = __ldcs(ra + i);
-			d = __ldcs(dec + i);
-			int b = band_of(G, d);
-			if (b >= 0 && b < G.nbands) {
-				double x = wrap360(r - G.ra_org);
-				if (G.full_circle || x <= G.ra_span) {
-					int cell = G.base[b] + racell_of(G, b, x);
-					e0 = cstart[cell];
-					e1 = cstart[cell + 1];
-					rn = wrap360(r);
-				}
-			}
-		}
-		bool have_trig = false;
-		double lon2 = 0, slat2 = 0, clat2 = 0;
-		for (int e = e0; __any_sync(NWB_FULL, e < e1); e++) {
-			bool hit = false;
-			int p = 0;
-			double sep = 0;
-			if (e < e1) {
-				Entry en = entries[e];
-				if (fabs(d - en.dec) <= rb) {
-					double dr = rn - en.ra_n;
-					if (dr > 180.0) dr -= 360.0;
-					else if (dr < -180.0) dr += 360.0;
-					if (fabs(dr) <= en.dra) {
-						if (!have_trig) {
-							sincos(deg2rad_ref(d), &slat2, &clat2);
-							lon2 = deg2rad_ref(r);
-							have_trig = true;
-						}
-						p = en.p;
-						sep = sep_arcsec_ref(P.lon[p], P.slat[p], P.clat[p], lon2, slat2, clat2);
-						hit = sep < radius;
-					}
-				}
-			}
-			unsigned m = __ballot_sync(NWB_FULL, hit);
-			if (m) {
-				unsigned long long basepos = 0;
-				int leader = __ffs(m) - 1;
-				if (lane == leader) basepos = atomicAdd(out_count, (unsigned long long) __popc(m));
-				basepos = __shfl_sync(NWB_FULL, basepos, leader);
-				if (hit) {
-					unsigned long long pos = basepos + __popc(m & ((1u << lane) - 1));
-					if (pos < cap) {
-						PairRec rec;
-						rec.p = p; rec.s = (int) i; rec.sep = sep;
-						out[pos] = rec;
-						atomicAdd(&cnt[p], 1);
-					}
+	if (lane < count) {
+		const int2 c = M.cand[lo + lane];
+		const int s = c.x, p = c.y;
+		double r = ra[s], d = dec[s];   // streamed a moment ago: L2 hits
+		double lon1 = P.lon[p], slat1 = P.slat[p], clat1 = P.clat[p];
+		double slat2, clat2;
+		sincos(deg2rad_ref(d), &slat2, &clat2);
+		double lon2 = deg2rad_ref(r);
+		double sep = sep_arcsec_ref(lon1, slat1, clat1, lon2, slat2, clat2);
+		if (sep < radius) {
+			int slot = atomicAdd(&cnt[p], 1);
+			if (slot < C) {
+				int4 v;
+				v.x = s; v.y = 0; v.z = __double2loint(sep); v.w = __double2hiint(sep);
+				*reinterpret_cast<int4 *>(base + (size_t) p * C + slot) = v;
+			} else {
+				unsigned long long pos = atomicAdd(spill_count, 1ull);
+				if (pos < spill_cap) {
+					SpillRec rec;
+					rec.p = p; rec.slot = slot; rec.s = s; rec.pad = 0; rec.sep = sep;
+					spill[pos] = rec;
 				}
 			}
 		}
 	}
 }
 
-__global__ void k_scatter(long long npairs, const PairRec *__restrict__ recs, const long long *__restrict__ seg_off,
-	int *__restrict__ fill, int *__restrict__ seg_s, double *__restrict__ seg_sep)
+// fp32 pre-test of `count` work items, one per lane (dense); survivors are queued as candidates
+__device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane, int &qn, const Grid &G,
+	const Entry *__restrict__ entries, const double *__restrict__ ra, const double *__restrict__ dec,
+	const PrimArrays &P, double radius, Slot16 *__restrict__ base, int C, int *__restrict__ cnt,
+	SpillRec *__restrict__ spill, unsigned long long spill_cap, unsigned long long *__restrict__ spill_count)
 {
-	long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= npairs) return;
-	PairRec r = recs[i];
-	long long pos = seg_off[r.p] + atomicAdd(&fill[r.p], 1);
-	seg_s[pos] = r.s;
-	seg_sep[pos] = r.sep;
+	bool pass = false;
+	int s = 0, p = 0;
+	if (lane < count) {
+		const int4 it = M.items[lo + lane];
+		const int4 ev = __ldg(reinterpret_cast<const int4 *>(entries + it.z));
+		float dx = __int_as_float(it.x) - __int_as_float(ev.x);
+		if (dx > 180.f) dx -= 360.f;
+		else if (dx < -180.f) dx += 360.f;
+		float u = dx * __int_as_float(ev.z);
+		float dy = __int_as_float(it.y) - __int_as_float(ev.y);
+		pass = u * u + dy * dy <= G.rr2;
+		s = it.w;
+		p = ev.w;
+	}
+	unsigned m = __ballot_sync(NWB_FULL, pass);
+	if (m) {
+		if (pass) M.cand[qn + __popc(m & ((1u << lane) - 1))] = make_int2(s, p);
+		qn += __popc(m);
+		__syncwarp();
+		if (qn >= 32) {
+			qn -= 32;
+			k1_flush(M, qn, 32, lane, ra, dec, P, radius, base, C, cnt, spill, spill_cap, spill_count);
+			__syncwarp();
+		}
+	}
 }
 
-// One warp per primary: out-of-place rank sort of its segment by secondary index (the reference's sorted()
-// of every bucket list, fastskymatch.py:181).  WITH_TRIG additionally stores lon, sin/cos(lat) of the
-// secondary for the secondary-secondary separations of N >= 3.
-template <bool WITH_TRIG>
-__global__ void k_sort_lists(int np, const long long *__restrict__ seg_off, const int *__restrict__ seg_s,
-	const double *__restrict__ seg_sep, int *__restrict__ L_s, double *__restrict__ L_sep,
-	const double *__restrict__ ra, const double *__restrict__ dec, double *__restrict__ L_lon,
-	double *__restrict__ L_slat, double *__restrict__ L_clat)
+// One thread per secondary source, coalesced streaming loads of (ra, dec): 16 algorithmic bytes per source (the
+// next batch is prefetched while the current one is processed).  Three stages, each run with full warps:
+//   1. per source: grid cell -> (first entry, count); every (source, cell entry) pair becomes a work item in a
+//      per-warp shared-memory list;
+//   2. whenever 32 items are there: fp32 flat pre-test against the primary of the entry (L2-resident, 16 bytes);
+//      survivors become candidates;
+//   3. whenever 32 candidates are there: exact fp64 separation in the reference's arithmetic; a match takes the
+//      next slot of its primary (atomicAdd on the per-primary counter) and is written there directly -- no
+//      append buffer, no scatter pass.
+__global__ void __launch_bounds__(K1_WARPS * 32, 3)
+k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G,
+	const int *__restrict__ cstart, const Entry *__restrict__ entries, long long entries_cap, PrimArrays P,
+	double radius, Slot16 *__restrict__ base, int C, int *__restrict__ cnt, SpillRec *__restrict__ spill,
+	unsigned long long spill_cap, unsigned long long *__restrict__ spill_count)
+{
+	__shared__ K1Smem smem[K1_WARPS];
+	__shared__ int4 sbands[K1_SBANDS];   // the band table, when it is small enough (one L2 round trip less)
+	if ((long long) cstart[G.ncells] > entries_cap) return;   // the cell lists were not written: the host retries
+	const bool bands_in_smem = G.nbands <= K1_SBANDS;
+	if (bands_in_smem) {
+		for (int b = threadIdx.x; b < G.nbands; b += blockDim.x)
+			sbands[b] = __ldg(reinterpret_cast<const int4 *>(G.bands + b));
+		__syncthreads();
+	}
+	const int lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1;
+	K1Smem &M = smem[threadIdx.x >> 5];
+	int nit = 0, qn = 0;   // warp-uniform fill levels of the two lists
+	const long long stride = (long long) gridDim.x * blockDim.x;
+	const long long nround = (n + 31) / 32 * 32;
+	long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	double r_nxt = 0, d_nxt = 0;
+	if (i < n) { r_nxt = ra[i]; d_nxt = dec[i]; }
+	for (; i < nround; i += stride) {
+		const double r = r_nxt, d = d_nxt;
+		const bool valid = i < n;
+		{
+			long long j = i + stride;   // software prefetch of the next batch: hides the DRAM latency
+			if (j < n) { r_nxt = ra[j]; d_nxt = dec[j]; }   // default caching: the exact stage re-reads these from L2
+		}
+		int e0 = 0, ecnt = 0;
+		int xi = 0, yi = 0;
+		if (valid) {
+			double y = d - G.dec_lo;
+			double t = y * G.inv_h;
+			if (t >= 0.0 && t < (double) G.nbands) {
+				double x = wrap360(r) - G.ra_org_n;
+				if (x < 0.0) x += 360.0;
+				if (G.full_circle || x <= G.ra_span) {
+					const int b = __double2int_rd(t);
+					BandRec B;
+					if (bands_in_smem) {
+						const int4 v = sbands[b];
+						B.base = v.x; B.nra = v.y; B.inv_w = __hiloint2double(v.w, v.z);
+					} else {
+						B = load_band(G, b);
+					}
+					int cell = B.base + racell_of(B, x);
+					e0 = cstart[cell];
+					ecnt = cstart[cell + 1] - e0;
+					xi = __float_as_int((float) x);
+					yi = __float_as_int((float) y);
+				}
+			}
+		}
+		int maxc = __reduce_max_sync(NWB_FULL, ecnt);
+		for (int t0 = 0; t0 < maxc; t0 += K1_ROUND) {
+			int kmax = min(maxc - t0, K1_ROUND);
+			for (int k = 0; k < kmax; k++) {
+				bool has = t0 + k < ecnt;
+				unsigned m = __ballot_sync(NWB_FULL, has);
+				if (has) M.items[nit + __popc(m & lt)] = make_int4(xi, yi, e0 + t0 + k, (int) i);
+				nit += __popc(m);
+			}
+			__syncwarp();
+			while (nit >= 32) {
+				nit -= 32;
+				k1_items(M, nit, 32, lane, qn, G, entries, ra, dec, P, radius, base, C, cnt, spill, spill_cap, spill_count);
+			}
+			__syncwarp();
+		}
+	}
+	if (nit > 0) k1_items(M, 0, nit, lane, qn, G, entries, ra, dec, P, radius, base, C, cnt, spill, spill_cap, spill_count);
+	__syncwarp();
+	if (qn > 0) k1_flush(M, 0, qn, lane, ra, dec, P, radius, base, C, cnt, spill, spill_cap, spill_count);
+}
+
+// the scalars the host needs after K1, gathered for one small copy: [0] cell entries, [c] spill records of
+// catalogue c, [8] total rows (N == 2)
+__global__ void k_collect_status(int ncat, const int *__restrict__ entries_total,
+	const unsigned long long *__restrict__ spill_count, const long long *__restrict__ total_rows,
+	long long *__restrict__ out)
+{
+	int t = threadIdx.x;
+	if (t == 0) out[0] = *entries_total;
+	if (t >= 1 && t < ncat) out[t] = (long long) spill_count[t];
+	if (t == 8) out[8] = total_rows ? *total_rows : 0;
+}
+
+// overflow handling (only launched when some primary had more matches than slots)
+__global__ void k_spill_sizes(int np, const int *__restrict__ cnt, int C, int *__restrict__ sizes)
+{
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < np) sizes[p] = max(cnt[p] - C, 0);
+}
+
+__global__ void k_spill_scatter(long long n, const SpillRec *__restrict__ recs, int C,
+	const long long *__restrict__ spill_off, Slot16 *__restrict__ out)
+{
+	long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	SpillRec r = recs[i];
+	Slot16 v;
+	v.s = r.s; v.pad = 0; v.sep = r.sep;
+	out[spill_off[r.p] + (r.slot - C)] = v;
+}
+
+// N >= 3: one warp per primary rank-sorts its matches by secondary index (the reference's sorted() of every
+// bucket list, fastskymatch.py:181) into compact lists, and stores lon, sin/cos(lat) of each secondary for the
+// secondary-secondary separations.
+__global__ void k_sort_lists(int np, PairStore S, const long long *__restrict__ seg_off, int *__restrict__ L_s,
+	double *__restrict__ L_sep, const double *__restrict__ ra, const double *__restrict__ dec,
+	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat)
 {
 	int lane = threadIdx.x & 31;
 	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	int nwarps = (gridDim.x * blockDim.x) >> 5;
 	for (int p = warp; p < np; p += nwarps) {
 		long long lo = seg_off[p];
-		int n = (int) (seg_off[p + 1] - lo);
+		int n = S.cnt[p];
 		for (int e = lane; e < n; e += 32) {
-			int s = seg_s[lo + e];
+			Slot16 me = store_get(S, p, e);
 			int rank = 0;
-			for (int f = 0; f < n; f++) rank += seg_s[lo + f] < s;
-			L_s[lo + rank] = s;
-			L_sep[lo + rank] = seg_sep[lo + e];
-			if (WITH_TRIG) {
-				double sl, cl;
-				sincos(deg2rad_ref(dec[s]), &sl, &cl);
-				L_lon[lo + rank] = deg2rad_ref(ra[s]);
-				L_slat[lo + rank] = sl;
-				L_clat[lo + rank] = cl;
-			}
+			for (int f = 0; f < n; f++) rank += store_get(S, p, f).s < me.s;
+			L_s[lo + rank] = me.s;
+			L_sep[lo + rank] = me.sep;
+			double sl, cl;
+			sincos(deg2rad_ref(dec[me.s]), &sl, &cl);
+			L_lon[lo + rank] = deg2rad_ref(ra[me.s]);
+			L_slat[lo + rank] = sl;
+			L_clat[lo + rank] = cl;
 		}
 	}
 }
@@ -343,6 +510,7 @@ struct RowParams {
 	const long long *row_off;        // [np+1]
 	const long long *mat_off;        // [np+1] (N >= 3)
 	double *mat;                     // secondary-secondary separations
+	PairStore S1;                    // N == 2: the matches of catalogue 1, unsorted, straight from k_pairs
 };
 
 template <int NC>
@@ -436,10 +604,10 @@ __global__ void k_count_rows(RowParams R, long long *__restrict__ rows)
 }
 
 // N == 2: rows per primary = matches + 1
-__global__ void k_rows_per_primary_2(int np, const long long *__restrict__ off, long long *__restrict__ rows)
+__global__ void k_rows_per_primary_2(int np, const int *__restrict__ cnt, long long *__restrict__ rows)
 {
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p < np) rows[p] = off[p + 1] - off[p] + 1;
+	if (p < np) rows[p] = (long long) cnt[p] + 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -612,6 +780,191 @@ k_rows(RowParams R)
 			__syncwarp();
 			group_normalise(R, rbase, written, lane);
 		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2 for two catalogues (the streaming configuration): one warp per primary, everything of the group staged in
+// shared memory: the unsorted matches are rank-sorted by secondary index (fastskymatch.py:181,217), rows are
+// scored and written with coalesced stores, and -- FUSE -- the group's log-sum-exp runs on the shared copy of
+// the log-weights, so no column is ever read back from global memory.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int R2_WARPS = 8;
+constexpr int R2_CAP = 128;   // matches per primary handled in shared memory; larger groups take k_rows2_big
+
+struct __align__(16) R2Smem {
+	int s_in[R2_CAP];
+	int s[R2_CAP];
+	double sep[R2_CAP];
+	double v[R2_CAP + 1];
+};
+
+// per-lane memo of the error-dependent terms of the 2-catalogue Bayes factor: catalogues very often carry one
+// positional error for all sources (or a handful of values), and then w, log(w), log(w0 + w1) need not be
+// recomputed row after row.  Same expressions, same bits -- just not evaluated twice for equal inputs.
+struct R2Memo {
+	double s1 = -1.0, w1 = 0.0, lw1 = 0.0;      // key s1
+	double kw0 = -1.0, kw1 = -1.0, wsum = 0.0, lwsum = 0.0;   // key (w0, w1)
+};
+
+template <bool FUSE>
+__device__ __forceinline__ void rows2_write(const RowParams &R, const ConstTables *__restrict__ T, long long row,
+	long long gp, long long sidx1, double sep, double w0, double lw0, R2Memo &memo, double &v_out)
+{
+	const bool present = sidx1 >= 0;
+	R.C.idx[0][row] = gp;
+	R.C.idx[1][row] = sidx1;
+	R.C.sep[0][row] = present ? sep : nan("");
+	R.C.sepmax[row] = present ? sep : 0.0;
+	R.C.ncat[row] = present ? 2 : 1;
+	double lbf = 0.0;
+	if (present) {
+		// bayesdistance.py:64-86 for n = 2, same operation order as log_bf_ref<2>
+		double s1 = R.err[1][sidx1];
+		if (s1 != memo.s1) {
+			memo.s1 = s1;
+			memo.w1 = 1.0 / (s1 * s1);
+			memo.lw1 = log(memo.w1);
+		}
+		double w1 = memo.w1;
+		if (w0 != memo.kw0 || w1 != memo.kw1) {
+			memo.kw0 = w0; memo.kw1 = w1;
+			memo.wsum = w0 + w1;
+			memo.lwsum = log(memo.wsum);
+		}
+		double wsum = memo.wsum;
+		double slog = lw0 + memo.lw1 - memo.lwsum;
+		double q = w0 * w1 * (sep * sep);
+		double exponent = -q / 2 / wsum;
+		lbf = (T->norm[2] + slog + exponent) * T->log10e;
+	}
+	unsigned smask = present ? 1u : 0u;
+	double prior = T->prior[smask], l10p = T->log10prior[smask];
+	double post = posterior_ref(prior, l10p, lbf);
+	R.C.lbf_u[row] = lbf;
+	R.C.lbf[row] = lbf;
+	R.C.dist_post[row] = post;
+	if (FUSE) {
+		double total = lbf;
+		double ps = post;
+		if (R.nmag > 0) {
+			long long sidx[2] = {gp, sidx1};
+			total = lbf + row_bias(R, row, sidx);
+			ps = posterior_ref(prior, l10p, total);
+		}
+		R.C.p_single[row] = ps;
+		v_out = total + l10p;
+	}
+}
+
+template <bool FUSE>
+__global__ void __launch_bounds__(R2_WARPS * 32, 4)
+k_rows2(RowParams R)
+{
+	__shared__ R2Smem smem[R2_WARPS];
+	const int lane = threadIdx.x & 31;
+	R2Smem &M = smem[threadIdx.x >> 5];
+	const ConstTables *__restrict__ T = R.T;
+	R2Memo memo;
+	double m_sig0 = -1.0, w0 = 0.0, lw0 = 0.0;
+	const int nwarps = gridDim.x * R2_WARPS;
+	for (int p = blockIdx.x * R2_WARPS + (threadIdx.x >> 5); p < R.np; p += nwarps) {
+	const int n = R.S1.cnt[p];
+	const long long rbase = R.row_off[p];
+	const long long gp = R.first + p;
+	const double sig0 = R.err[0][gp];
+	if (sig0 != m_sig0) {
+		m_sig0 = sig0;
+		w0 = 1.0 / (sig0 * sig0);
+		lw0 = log(w0);
+	}
+	__syncwarp();
+	if (n <= R2_CAP) {
+		for (int e = lane; e < n; e += 32) {
+			Slot16 x = store_get(R.S1, p, e);
+			M.s_in[e] = x.s;
+			M.v[e] = x.sep;   // parked here until ranked
+		}
+		__syncwarp();
+		for (int e = lane; e < n; e += 32) {
+			int mine = M.s_in[e];
+			int rank = 0;
+			int f = 0;
+			for (; f + 4 <= n; f += 4) {
+				int4 o = *reinterpret_cast<const int4 *>(&M.s_in[f]);
+				rank += (o.x < mine) + (o.y < mine) + (o.z < mine) + (o.w < mine);
+			}
+			for (; f < n; f++) rank += M.s_in[f] < mine;
+			M.s[rank] = mine;
+			M.sep[rank] = M.v[e];
+		}
+		__syncwarp();
+		// rows in order: row 0 = no counterpart, row k = k-th smallest secondary index
+		const int rows = n + 1;
+		for (int k = lane; k < rows; k += 32) {
+			double v = 0.0;
+			rows2_write<FUSE>(R, T, rbase + k, gp, k == 0 ? -1 : (long long) M.s[k - 1], k == 0 ? 0.0 : M.sep[k - 1],
+				w0, lw0, memo, v);
+			if (FUSE) M.v[k] = v;
+		}
+		if (!FUSE) continue;
+		// group normalisation (__init__.py:423-457) on the shared copy of the log-weights; every lane only ever
+		// touches its own k = lane + 32 j, except for v[0]
+		__syncwarp();
+		const double v0 = M.v[0];
+		double m_all = v0, m_rest = -INFINITY;
+		for (int k = lane + (lane == 0 ? 32 : 0); k < rows; k += 32) m_rest = fmax(m_rest, M.v[k]);
+		m_rest = warp_max(m_rest);
+		m_all = fmax(m_all, m_rest);
+		const bool same = m_all == m_rest;
+		double s_all = 0.0, s_rest = 0.0;
+		for (int k = lane + (lane == 0 ? 32 : 0); k < rows; k += 32) {
+			double x = M.v[k];
+			double t = exp10(x - m_rest);
+			s_rest += t;
+			s_all += same ? t : exp10(x - m_all);
+		}
+		if (lane == 0) s_all += exp10(v0 - m_all);
+		s_all = warp_sum(s_all);
+		s_rest = warp_sum(s_rest);
+		const double bfsum = log10(s_all) + m_all;
+		const double bfsum1 = rows > 1 ? log10(s_rest) + m_rest : 0.0;
+		const double p_any = 1 - exp10(v0 - bfsum);
+		__syncwarp();
+		double best = 0.0;
+		for (int k = lane; k < rows; k += 32) {
+			double pi = k == 0 ? 0.0 : exp10(M.v[k] - bfsum1);
+			M.v[k] = pi;
+			best = fmax(best, pi);
+		}
+		best = warp_max(best);
+		for (int k = lane; k < rows; k += 32) {
+			long long row = rbase + k;
+			double pi = M.v[k];
+			R.C.p_i[row] = pi;
+			R.C.p_any[row] = p_any;
+			R.C.flag[row] = (pi == best) ? 1 : (pi > R.ratio_secondary * best ? 2 : 0);
+		}
+	} else {
+		// big group: rank against global memory, write rows, normalise through the p_i column
+		for (int e = lane; e < n; e += 32) {
+			Slot16 me = store_get(R.S1, p, e);
+			int rank = 0;
+			for (int f = 0; f < n; f++) rank += store_get(R.S1, p, f).s < me.s;
+			double v = 0.0;
+			rows2_write<FUSE>(R, T, rbase + 1 + rank, gp, me.s, me.sep, w0, lw0, memo, v);
+			if (FUSE) R.C.p_i[rbase + 1 + rank] = v;
+		}
+		if (lane == 0) {
+			double v = 0.0;
+			rows2_write<FUSE>(R, T, rbase, gp, -1, 0.0, w0, lw0, memo, v);
+			if (FUSE) R.C.p_i[rbase] = v;
+		}
+		if (FUSE) {
+			__syncwarp();
+			group_normalise(R, rbase, (long long) n + 1, lane);
+		}
+	}
 	}
 }
 
