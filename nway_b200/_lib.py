@@ -6,7 +6,7 @@ import os
 import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnwayb200.so')
+LIB_PATH = os.environ.get('NWB_LIB') or os.path.join(_HERE, 'libnwayb200.so')   # $NWB_LIB: experiment builds
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)

@@ -26,6 +26,17 @@ def needs_build():
 	return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(out, defines):
+	"""experiment builds: same sources with -D overrides into another .so (select it with $NWB_LIB)"""
+	nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+	cmd = [nvcc] + NVCC_FLAGS + ['-D' + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', out, '-lcudart']
+	res = subprocess.run(cmd, capture_output=True, text=True)
+	if res.returncode != 0:
+		sys.stderr.write(res.stdout + res.stderr)
+		raise RuntimeError('nvcc failed')
+	return res.stdout + res.stderr
+
+
 def build(force=False, verbose=False):
 	if not force and not needs_build():
 		return LIB

@@ -29,6 +29,8 @@ struct CatSlot {
 	int err_kind = NWB_ERR_CIRCULAR, m = 0;
 	double area = 0;
 	DevBuf own;   // one allocation holding ra|dec|err|mags when copied from the host
+	bool err_const = false;   // every source has the same (positive, circular) error
+	double err_value = 0;
 };
 
 struct HostMagHist {
@@ -57,10 +59,11 @@ struct nwb_ctx {
 	DevBuf d_tables, d_prim, d_red, d_bands, d_cellcnt, d_cstart, d_entries, d_cub, d_pairs, d_paircount;
 	DevBuf d_cnt[MAXC], d_segoff[MAXC], d_seg_s[MAXC], d_seg_sep[MAXC], d_Ls[MAXC], d_Lsep[MAXC], d_Ltrig[MAXC];
 	DevBuf d_rows, d_rowoff, d_matsz, d_matoff, d_mat, d_cols, d_cols2, d_keep, d_keeppos, d_misc;
-	DevBuf d_spill, d_status, d_spilloff[MAXC], d_spillseg[MAXC];
+	DevBuf d_spill, d_status, d_spilloff[MAXC], d_spillseg[MAXC], d_cells;
 	size_t entries_cap = 0;
 	unsigned long long spill_cap = 0;
 	long long *h_status = nullptr;   // pinned
+	int k1_blocks_per_sm = 0, num_sms = 0;
 
 	// result
 	bool matched = false, finalized = false;
@@ -389,7 +392,7 @@ void nwb_destroy(nwb_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *single[] = {&ctx->d_tables, &ctx->d_prim, &ctx->d_red, &ctx->d_bands, &ctx->d_cellcnt, &ctx->d_cstart,
 		&ctx->d_entries, &ctx->d_cub, &ctx->d_pairs, &ctx->d_paircount, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_matsz,
-		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc, &ctx->d_spill, &ctx->d_status};
+		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc, &ctx->d_spill, &ctx->d_status, &ctx->d_cells};
 	for (DevBuf *b : single) release(*b);
 	for (int c = 0; c < MAXC; c++) {
 		release(ctx->d_cnt[c]); release(ctx->d_segoff[c]); release(ctx->d_seg_s[c]); release(ctx->d_seg_sep[c]);
@@ -448,6 +451,23 @@ int nwb_set_catalogue(nwb_ctx *ctx, int c, int ncat, int64_t n, const double *ra
 	}
 	S.set = true;
 	ctx->matched = ctx->finalized = false;
+	// one positional error for the whole catalogue?  (lets the row kernels skip a random gather per row)
+	S.err_const = false;
+	if (n > 0 && err_kind == NWB_ERR_CIRCULAR) {
+		ENSURE(ctx->d_status, 64 * sizeof(long long));
+		if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocDefault));
+		unsigned long long init[2] = {0x7ff0000000000000ull, 0ull};
+		unsigned long long *d_mm = (unsigned long long *) ctx->d_status.p + 32;
+		CU(cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+		LAUNCH(ctx, k_minmax, (int) std::min<int64_t>((n + 255) / 256, 148 * 8), 256, (long long) n, S.err, (double *) d_mm);
+		CU(cudaMemcpyAsync(ctx->h_status + 40, d_mm, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		double lo, hi;
+		memcpy(&lo, ctx->h_status + 40, 8);
+		memcpy(&hi, ctx->h_status + 41, 8);
+		S.err_const = lo == hi && lo > 0 && std::isfinite(lo);
+		S.err_value = lo;
+	}
 	return NWB_OK;
 }
 
@@ -562,11 +582,11 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	const double r_deg = ctx->radius / 3600.0;
 	const double rb = r_deg * (1 + 1e-9) + 1e-12;
 	const double rb_ins = rb + 1e-9, dra_eps = 1e-9;
-	ENSURE(ctx->d_prim, (size_t) np * 6 * sizeof(double));
+	ENSURE(ctx->d_prim, (size_t) np * 8 * sizeof(double));
 	PrimArrays P;
 	{
 		double *b = (double *) ctx->d_prim.p;
-		P.lon = b; P.slat = b + np; P.clat = b + 2 * np; P.ra_n = b + 3 * np; P.dec = b + 4 * np; P.dra = b + 5 * np;
+		P.rec = (PrimRec *) b; P.clat = b + 4 * np; P.ra_n = b + 5 * np; P.dec = b + 6 * np; P.dra = b + 7 * np;
 	}
 	int pblocks = grid_for(np, 256);
 	ENSURE(ctx->d_red, ((size_t) pblocks * 6 + 8) * sizeof(double));
@@ -637,6 +657,9 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 		{ int r = scan_int(ctx, d_cellcnt, d_cstart, (int64_t) ncell1); if (r) return r; }
 		LAUNCH(ctx, (k_prim_cells<true>), pblocks, 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) d_cstart,
 			d_entries, (long long) ctx->entries_cap);
+		ENSURE(ctx->d_cells, (size_t) G.ncells * sizeof(CellRec));
+		LAUNCH(ctx, k_cell_records, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cstart,
+			(const Entry *) d_entries, (long long) ctx->entries_cap, (CellRec *) ctx->d_cells.p);
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[1], st));
 
 		// ---- K1: stream the secondaries ----------------------------------------------------------------
@@ -648,11 +671,22 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 			stores[c].spill_off = nullptr;
 			stores[c].spill = nullptr;
 			if (n == 0) continue;
-			int grid = (int) std::min<int64_t>((n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), 148 * 5);
+			if (ctx->k1_blocks_per_sm <= 0) {
+				int nb = 0, nsm = 0;
+				CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pairs, K1_WARPS * 32, 0));
+				CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+				ctx->k1_blocks_per_sm = std::max(nb, 1);
+				ctx->num_sms = std::max(nsm, 1);
+			}
+			// persistent: exactly one wave of resident blocks, each striding over the catalogue
+			int grid = (int) std::min<int64_t>((n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), (int64_t) ctx->num_sms * ctx->k1_blocks_per_sm);
 			CU(cudaEventRecord(ctx->kev[2 * c], st));
+			K1Args ka;
+			ka.P = P; ka.radius = ctx->radius; ka.base = d_base + base_off[c]; ka.C = Cs[c]; ka.cnt = d_cnt[c];
+			ka.spill = d_spill + (size_t) ctx->spill_cap * (c - 1); ka.spill_cap = (unsigned long long) ctx->spill_cap;
+			ka.spill_count = d_spillcount + c;
 			LAUNCH(ctx, k_pairs, grid, K1_WARPS * 32, (long long) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_cstart,
-				(const Entry *) d_entries, (long long) ctx->entries_cap, P, ctx->radius, d_base + base_off[c], Cs[c], d_cnt[c],
-				d_spill + (size_t) ctx->spill_cap * (c - 1), (unsigned long long) ctx->spill_cap, d_spillcount + c);
+				(const CellRec *) ctx->d_cells.p, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
 			CU(cudaEventRecord(ctx->kev[2 * c + 1], st));
 		}
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[2], st));
@@ -701,6 +735,8 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	for (int c = 0; c < nc; c++) rp.err[c] = ctx->cat[c].err;
 	rp.T = (const ConstTables *) ctx->d_tables.p;
 	rp.S1 = stores[1];
+	rp.err1_const = ctx->cat[1].err_const ? 1 : 0;
+	rp.err1_value = ctx->cat[1].err_value;
 	int wgrid = std::max(1, (int) std::min<int64_t>((np * 32 + 255) / 256, 148 * 64));
 	ctx->stats[1] = 0;
 

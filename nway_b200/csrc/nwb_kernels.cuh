@@ -107,9 +107,23 @@ __device__ __forceinline__ BandRec load_band(const Grid &G, int b)
 // ---------------------------------------------------------------------------------------------------------
 // K0: primaries
 // ---------------------------------------------------------------------------------------------------------
+struct PrimRec {   // 32 bytes = one L2 sector: what the exact formula needs of a primary
+	double lon, slat, clat, spare;
+};
+
 struct PrimArrays {
-	double *lon, *slat, *clat;   // for the exact formula
+	PrimRec *rec;                // for the exact formula
+	double *clat;                // (also kept as a plain column for the cell entries)
 	double *ra_n, *dec, *dra;    // search box (degrees); dra >= 180 means "all ra"
+};
+
+// 32 bytes = one L2 sector per cell: how many primaries are registered here, where the list is, and the first
+// of them inline -- a source in a cell with a single primary (the common case) needs no second lookup.
+struct CellRec {
+	int cnt, start;
+	float x, y, clat;
+	int p;
+	int pad0, pad1;
 };
 
 // box margins: rb (deg) is the search radius inflated by 1e-9 relative + 1e-12, so that rounding in the
@@ -124,8 +138,9 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 		double lat = deg2rad_ref(d);
 		double sl, cl;
 		sincos(lat, &sl, &cl);
-		P.lon[i] = deg2rad_ref(r);
-		P.slat[i] = sl;
+		PrimRec pr;
+		pr.lon = deg2rad_ref(r); pr.slat = sl; pr.clat = cl; pr.spare = 0.0;
+		P.rec[i] = pr;
 		P.clat[i] = cl;
 		double rn = wrap360(r);
 		double dra;
@@ -256,96 +271,131 @@ __global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double
 // its primary (atomicAdd on the per-primary counter) and is written there directly -- no append buffer, no
 // scatter pass.
 constexpr int K1_WARPS = 8;
-constexpr int K1_ROUND = 4;                      // cell entries taken per lane and round
+constexpr int K1_ROUND = 2;                      // further cell entries taken per lane and round
 constexpr int K1_ICAP = 32 * (K1_ROUND + 1);     // work items: 31 left over + one full round
-constexpr int K1_QCAP = 64;                      // candidates: 31 left over + 32 new
+constexpr int K1_QCAP = 64;                      // candidates: 31 left over + 32 new (flushed before the next 32)
 constexpr int K1_SBANDS = 1024;                  // bands cached in shared memory (16 KB)
 
+#ifndef NWB_K1_MINBLOCKS
+#define NWB_K1_MINBLOCKS 3
+#endif
+
 struct K1Smem {   // per warp
-	int4 items[K1_ICAP];   // (x, y) of a secondary as floats, entry index, secondary index
-	int2 cand[K1_QCAP];    // (secondary, primary) that passed the pre-test
+	int2 item_es[K1_ICAP];      // (entry index, secondary index)
+	double2 item_rd[K1_ICAP];   // (ra, dec) of the secondary
+	int2 cand_sp[K1_QCAP];      // (secondary, primary) that passed the pre-test
+	double2 cand_rd[K1_QCAP];   // (ra, dec) of the secondary
 };
 
-// exact fp64 separation for `count` queued candidates, one per lane; a match takes the next slot of its primary
-__device__ __forceinline__ void k1_flush(const K1Smem &M, int lo, int count, int lane,
-	const double *__restrict__ ra, const double *__restrict__ dec, const PrimArrays &P, double radius,
-	Slot16 *__restrict__ base, int C, int *__restrict__ cnt, SpillRec *__restrict__ spill,
-	unsigned long long spill_cap, unsigned long long *__restrict__ spill_count)
+struct K1Args {
+	PrimArrays P;
+	double radius;
+	Slot16 *base;
+	int C;
+	int *cnt;
+	SpillRec *spill;
+	unsigned long long spill_cap;
+	unsigned long long *spill_count;
+};
+
+// exact fp64 separation for `count` (<= 32) queued candidates, one per lane; a match takes the next slot of its
+// primary
+__device__ __forceinline__ void k1_flush(const K1Smem &M, int lo, int count, int lane, const K1Args &A)
 {
 	if (lane < count) {
-		const int2 c = M.cand[lo + lane];
+		const int2 c = M.cand_sp[lo + lane];
+		const double2 rd = M.cand_rd[lo + lane];
 		const int s = c.x, p = c.y;
-		double r = ra[s], d = dec[s];   // streamed a moment ago: L2 hits
-		double lon1 = P.lon[p], slat1 = P.slat[p], clat1 = P.clat[p];
+		const double4 pr = *reinterpret_cast<const double4 *>(A.P.rec + p);   // one sector
 		double slat2, clat2;
-		sincos(deg2rad_ref(d), &slat2, &clat2);
-		double lon2 = deg2rad_ref(r);
-		double sep = sep_arcsec_ref(lon1, slat1, clat1, lon2, slat2, clat2);
-		if (sep < radius) {
-			int slot = atomicAdd(&cnt[p], 1);
-			if (slot < C) {
+		sincos(deg2rad_ref(rd.y), &slat2, &clat2);
+		double lon2 = deg2rad_ref(rd.x);
+		double sep = sep_arcsec_ref(pr.x, pr.y, pr.z, lon2, slat2, clat2);
+		if (sep < A.radius) {
+			int slot = atomicAdd(&A.cnt[p], 1);
+			if (slot < A.C) {
 				int4 v;
 				v.x = s; v.y = 0; v.z = __double2loint(sep); v.w = __double2hiint(sep);
-				*reinterpret_cast<int4 *>(base + (size_t) p * C + slot) = v;
+				*reinterpret_cast<int4 *>(A.base + (size_t) p * A.C + slot) = v;
 			} else {
-				unsigned long long pos = atomicAdd(spill_count, 1ull);
-				if (pos < spill_cap) {
+				unsigned long long pos = atomicAdd(A.spill_count, 1ull);
+				if (pos < A.spill_cap) {
 					SpillRec rec;
 					rec.p = p; rec.slot = slot; rec.s = s; rec.pad = 0; rec.sep = sep;
-					spill[pos] = rec;
+					A.spill[pos] = rec;
 				}
 			}
 		}
 	}
 }
 
-// fp32 pre-test of `count` work items, one per lane (dense); survivors are queued as candidates
-__device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane, int &qn, const Grid &G,
-	const Entry *__restrict__ entries, const double *__restrict__ ra, const double *__restrict__ dec,
-	const PrimArrays &P, double radius, Slot16 *__restrict__ base, int C, int *__restrict__ cnt,
-	SpillRec *__restrict__ spill, unsigned long long spill_cap, unsigned long long *__restrict__ spill_count)
+// the fp32 flat pre-test (see struct Entry); (x, y) = the secondary relative to the grid origin
+__device__ __forceinline__ bool k1_pretest(const Grid &G, float x, float y, float ex, float ey, float eclat)
 {
-	bool pass = false;
-	int s = 0, p = 0;
-	if (lane < count) {
-		const int4 it = M.items[lo + lane];
-		const int4 ev = __ldg(reinterpret_cast<const int4 *>(entries + it.z));
-		float dx = __int_as_float(it.x) - __int_as_float(ev.x);
-		if (dx > 180.f) dx -= 360.f;
-		else if (dx < -180.f) dx += 360.f;
-		float u = dx * __int_as_float(ev.z);
-		float dy = __int_as_float(it.y) - __int_as_float(ev.y);
-		pass = u * u + dy * dy <= G.rr2;
-		s = it.w;
-		p = ev.w;
-	}
+	float dx = x - ex;
+	if (dx > 180.f) dx -= 360.f;
+	else if (dx < -180.f) dx += 360.f;
+	float u = dx * eclat;
+	float dy = y - ey;
+	return u * u + dy * dy <= G.rr2;
+}
+
+// queue the lanes with pass == true as candidates; run the exact stage when 32 are there
+__device__ __forceinline__ void k1_enqueue(K1Smem &M, bool pass, int s, int p, double r, double d, int lane, int &qn,
+	const K1Args &A)
+{
 	unsigned m = __ballot_sync(NWB_FULL, pass);
 	if (m) {
-		if (pass) M.cand[qn + __popc(m & ((1u << lane) - 1))] = make_int2(s, p);
+		if (pass) {
+			int q = qn + __popc(m & ((1u << lane) - 1));
+			M.cand_sp[q] = make_int2(s, p);
+			M.cand_rd[q] = make_double2(r, d);
+		}
 		qn += __popc(m);
 		__syncwarp();
 		if (qn >= 32) {
 			qn -= 32;
-			k1_flush(M, qn, 32, lane, ra, dec, P, radius, base, C, cnt, spill, spill_cap, spill_count);
+			k1_flush(M, qn, 32, lane, A);
 			__syncwarp();
 		}
 	}
 }
 
-// One thread per secondary source, coalesced streaming loads of (ra, dec): 16 algorithmic bytes per source (the
-// next batch is prefetched while the current one is processed).  Three stages, each run with full warps:
-//   1. per source: grid cell -> (first entry, count); every (source, cell entry) pair becomes a work item in a
-//      per-warp shared-memory list;
-//   2. whenever 32 items are there: fp32 flat pre-test against the primary of the entry (L2-resident, 16 bytes);
-//      survivors become candidates;
-//   3. whenever 32 candidates are there: exact fp64 separation in the reference's arithmetic; a match takes the
-//      next slot of its primary (atomicAdd on the per-primary counter) and is written there directly -- no
-//      append buffer, no scatter pass.
-__global__ void __launch_bounds__(K1_WARPS * 32, 3)
+// fp32 pre-test of `count` work items (entries beyond the first of a cell), one per lane
+__device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane, int &qn, const Grid &G,
+	const Entry *__restrict__ entries, const K1Args &A)
+{
+	bool pass = false;
+	int s = 0, p = 0;
+	double r = 0, d = 0;
+	if (lane < count) {
+		const int2 es = M.item_es[lo + lane];
+		const double2 rd = M.item_rd[lo + lane];
+		const int4 ev = __ldg(reinterpret_cast<const int4 *>(entries + es.x));
+		r = rd.x; d = rd.y;
+		double x = wrap360(r) - G.ra_org_n;
+		if (x < 0.0) x += 360.0;
+		pass = k1_pretest(G, (float) x, (float) (d - G.dec_lo), __int_as_float(ev.x), __int_as_float(ev.y), __int_as_float(ev.z));
+		s = es.y;
+		p = ev.w;
+	}
+	k1_enqueue(M, pass, s, p, r, d, lane, qn, A);
+}
+
+// One thread per secondary source, coalesced loads of (ra, dec): 16 algorithmic bytes per source, the next batch
+// prefetched while the current one is processed.  The kernel is bound by L2 -> SM sector traffic (every lookup
+// is a random 32-byte sector), so the data is laid out to need few of them:
+//   1. per source ONE sector: the cell record = number of primaries registered in the cell, and the first of
+//      them inline; it is pre-tested (fp32, flat metric) on the spot.  Further primaries of the cell become work
+//      items in a per-warp shared-memory list and are pre-tested 32 at a time (one 16-byte entry each).
+//   2. survivors (candidates) carry the source's (ra, dec) with them; whenever 32 are queued every lane
+//      evaluates one exact fp64 separation in the reference's arithmetic against ONE sector of primary data.
+//   3. a match takes the next slot of its primary (atomicAdd on the per-primary counter) and is written there
+//      directly -- no append buffer, no scatter pass.
+__global__ void __launch_bounds__(K1_WARPS * 32, NWB_K1_MINBLOCKS)
 k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G,
-	const int *__restrict__ cstart, const Entry *__restrict__ entries, long long entries_cap, PrimArrays P,
-	double radius, Slot16 *__restrict__ base, int C, int *__restrict__ cnt, SpillRec *__restrict__ spill,
-	unsigned long long spill_cap, unsigned long long *__restrict__ spill_count)
+	const int *__restrict__ cstart, const CellRec *__restrict__ cells, const Entry *__restrict__ entries,
+	long long entries_cap, K1Args A)
 {
 	__shared__ K1Smem smem[K1_WARPS];
 	__shared__ int4 sbands[K1_SBANDS];   // the band table, when it is small enough (one L2 round trip less)
@@ -367,14 +417,13 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 	if (i < n) { r_nxt = ra[i]; d_nxt = dec[i]; }
 	for (; i < nround; i += stride) {
 		const double r = r_nxt, d = d_nxt;
-		const bool valid = i < n;
 		{
 			long long j = i + stride;   // software prefetch of the next batch: hides the DRAM latency
-			if (j < n) { r_nxt = ra[j]; d_nxt = dec[j]; }   // default caching: the exact stage re-reads these from L2
+			if (j < n) { r_nxt = ra[j]; d_nxt = dec[j]; }
 		}
-		int e0 = 0, ecnt = 0;
-		int xi = 0, yi = 0;
-		if (valid) {
+		int ecnt = 0, estart = 0, p0 = 0;
+		bool pass0 = false;
+		if (i < n) {
 			double y = d - G.dec_lo;
 			double t = y * G.inv_h;
 			if (t >= 0.0 && t < (double) G.nbands) {
@@ -389,34 +438,66 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 					} else {
 						B = load_band(G, b);
 					}
-					int cell = B.base + racell_of(B, x);
-					e0 = cstart[cell];
-					ecnt = cstart[cell + 1] - e0;
-					xi = __float_as_int((float) x);
-					yi = __float_as_int((float) y);
+					const int cell = B.base + racell_of(B, x);
+					const int4 c0 = __ldg(reinterpret_cast<const int4 *>(cells + cell));       // cnt, start, x, y
+					const int2 c1 = __ldg(reinterpret_cast<const int2 *>(cells + cell) + 2);   // clat, p (same sector)
+					ecnt = c0.x; estart = c0.y;
+					if (ecnt > 0) {
+						pass0 = k1_pretest(G, (float) x, (float) y, __int_as_float(c0.z), __int_as_float(c0.w), __int_as_float(c1.x));
+						p0 = c1.y;
+					}
 				}
 			}
 		}
+		k1_enqueue(M, pass0, (int) i, p0, r, d, lane, qn, A);
+		// entries beyond the inline one
 		int maxc = __reduce_max_sync(NWB_FULL, ecnt);
-		for (int t0 = 0; t0 < maxc; t0 += K1_ROUND) {
+		for (int t0 = 1; t0 < maxc; t0 += K1_ROUND) {
 			int kmax = min(maxc - t0, K1_ROUND);
 			for (int k = 0; k < kmax; k++) {
 				bool has = t0 + k < ecnt;
 				unsigned m = __ballot_sync(NWB_FULL, has);
-				if (has) M.items[nit + __popc(m & lt)] = make_int4(xi, yi, e0 + t0 + k, (int) i);
+				if (has) {
+					int q = nit + __popc(m & lt);
+					M.item_es[q] = make_int2(estart + t0 + k, (int) i);
+					M.item_rd[q] = make_double2(r, d);
+				}
 				nit += __popc(m);
 			}
 			__syncwarp();
 			while (nit >= 32) {
 				nit -= 32;
-				k1_items(M, nit, 32, lane, qn, G, entries, ra, dec, P, radius, base, C, cnt, spill, spill_cap, spill_count);
+				k1_items(M, nit, 32, lane, qn, G, entries, A);
 			}
 			__syncwarp();
 		}
 	}
-	if (nit > 0) k1_items(M, 0, nit, lane, qn, G, entries, ra, dec, P, radius, base, C, cnt, spill, spill_cap, spill_count);
+	if (nit > 0) k1_items(M, 0, nit, lane, qn, G, entries, A);
 	__syncwarp();
-	if (qn > 0) k1_flush(M, 0, qn, lane, ra, dec, P, radius, base, C, cnt, spill, spill_cap, spill_count);
+	while (qn > 0) {
+		int take = min(qn, 32);
+		qn -= take;
+		k1_flush(M, qn, take, lane, A);
+	}
+}
+
+// cell records from the cell lists: count, start and the first entry inline
+__global__ void k_cell_records(long long ncells, const int *__restrict__ cstart, const Entry *__restrict__ entries,
+	long long entries_cap, CellRec *__restrict__ cells)
+{
+	long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= ncells) return;
+	if ((long long) cstart[ncells] > entries_cap) return;
+	int s = cstart[c], cnt = cstart[c + 1] - s;
+	int4 a = make_int4(cnt, s, 0, 0);
+	int4 b = make_int4(0, 0, 0, 0);
+	if (cnt > 0) {
+		const int4 e = __ldg(reinterpret_cast<const int4 *>(entries + s));
+		a.z = e.x; a.w = e.y; b.x = e.z; b.y = e.w;
+	}
+	int4 *out = reinterpret_cast<int4 *>(cells + c);
+	out[0] = a;
+	out[1] = b;
 }
 
 // the scalars the host needs after K1, gathered for one small copy: [0] cell entries, [c] spill records of
@@ -511,6 +592,8 @@ struct RowParams {
 	const long long *mat_off;        // [np+1] (N >= 3)
 	double *mat;                     // secondary-secondary separations
 	PairStore S1;                    // N == 2: the matches of catalogue 1, unsorted, straight from k_pairs
+	int err1_const;                  // catalogue 1 carries one positional error for all sources:
+	double err1_value;               //   no per-row gather (one random 32-byte sector per row saved)
 };
 
 template <int NC>
@@ -820,7 +903,7 @@ __device__ __forceinline__ void rows2_write(const RowParams &R, const ConstTable
 	double lbf = 0.0;
 	if (present) {
 		// bayesdistance.py:64-86 for n = 2, same operation order as log_bf_ref<2>
-		double s1 = R.err[1][sidx1];
+		double s1 = R.err1_const ? R.err1_value : R.err[1][sidx1];
 		if (s1 != memo.s1) {
 			memo.s1 = s1;
 			memo.w1 = 1.0 / (s1 * s1);
@@ -1056,6 +1139,28 @@ __global__ void k_correct_cli(RowParams R)
 			}
 			__syncwarp();
 		}
+	}
+}
+
+// min / max of a column (is a catalogue's positional error one constant?)
+__global__ void k_minmax(long long n, const double *__restrict__ x, double *__restrict__ out /* [2], pre-set */)
+{
+	double lo = 1e300, hi = -1e300;
+	for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+		double v = x[i];
+		if (!(v == v)) { lo = -1e300; hi = 1e300; }   // NaN: never "constant"
+		lo = fmin(lo, v); hi = fmax(hi, v);
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		lo = fmin(lo, __shfl_xor_sync(NWB_FULL, lo, o));
+		hi = fmax(hi, __shfl_xor_sync(NWB_FULL, hi, o));
+	}
+	if ((threadIdx.x & 31) == 0) {
+		// doubles of one sign order like their bit patterns; errors are positive, anything else disables the shortcut
+		if (lo > 0) atomicMin(reinterpret_cast<unsigned long long *>(out), (unsigned long long) __double_as_longlong(lo));
+		else atomicMin(reinterpret_cast<unsigned long long *>(out), 0ull);
+		if (hi > 0) atomicMax(reinterpret_cast<unsigned long long *>(out + 1), (unsigned long long) __double_as_longlong(hi));
+		else atomicMax(reinterpret_cast<unsigned long long *>(out + 1), 0x7ff0000000000000ull);
 	}
 }
 
