@@ -128,6 +128,9 @@ enum { NWB_COL_IDX = 0, NWB_COL_SEP = 100, NWB_COL_BIAS = 200,
 /* copy one column of the last result (R values of 8 bytes: int64 for IDX/NCAT/MATCH_FLAG, double otherwise)
  * to host memory; asynchronous on the context's stream when dst is pinned -- call nwb_sync() before reading. */
 int nwb_fetch(nwb_ctx *ctx, int column, void *dst_host);
+/* same, into a DEVICE buffer of the caller on the context's device (e.g. a torch tensor that is then handed to
+ * NCCL); asynchronous on the context's stream */
+int nwb_fetch_device(nwb_ctx *ctx, int column, void *dst_device);
 /* device address of a column (valid until the next nwb_match on this context) */
 int nwb_column_ptr(nwb_ctx *ctx, int column, void **dev_ptr);
 int nwb_sync(nwb_ctx *ctx);

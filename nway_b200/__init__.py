@@ -77,27 +77,36 @@ def _column_names(match_tables):
 	return names, seps, biases
 
 
-def _fetch_table(ctx, match_tables, nrows):
-	"""device columns -> OrderedDict of numpy arrays in the reference's column order (__init__.py:131-196,
+def _column_selectors(match_tables):
+	"""output column name -> libnwayb200 column selector, in the reference's column order (__init__.py:131-196,
 	100-103,111,392,405,415-419)"""
 	L = _lib
 	names, seps, biases = _column_names(match_tables)
-	cols = OrderedDict()
+	sel = OrderedDict()
 	for c, name in enumerate(names):
-		cols[name] = ctx.fetch(L.COL_IDX + c, nrows, numpy.int64)
+		sel[name] = L.COL_IDX + c
 	for k, name in enumerate(seps):
-		cols[name] = ctx.fetch(L.COL_SEP + k, nrows)
-	cols['Separation_max'] = ctx.fetch(L.COL_SEPMAX, nrows)
-	cols['ncat'] = ctx.fetch(L.COL_NCAT, nrows, numpy.int64)
-	cols['dist_bayesfactor_uncorrected'] = ctx.fetch(L.COL_LOGBF_UNCORR, nrows)
-	cols['dist_bayesfactor'] = ctx.fetch(L.COL_LOGBF, nrows)
-	cols['dist_post'] = ctx.fetch(L.COL_DIST_POST, nrows)
+		sel[name] = L.COL_SEP + k
+	sel['Separation_max'] = L.COL_SEPMAX
+	sel['ncat'] = L.COL_NCAT
+	sel['dist_bayesfactor_uncorrected'] = L.COL_LOGBF_UNCORR
+	sel['dist_bayesfactor'] = L.COL_LOGBF
+	sel['dist_post'] = L.COL_DIST_POST
 	for k, name in enumerate(biases):
-		cols[name] = ctx.fetch(L.COL_BIAS + k, nrows)
-	cols['p_single'] = ctx.fetch(L.COL_P_SINGLE, nrows)
-	cols['match_flag'] = ctx.fetch(L.COL_MATCH_FLAG, nrows, numpy.int64)
-	cols['prob_has_match'] = ctx.fetch(L.COL_P_ANY, nrows)
-	cols['prob_this_match'] = ctx.fetch(L.COL_P_I, nrows)
+		sel[name] = L.COL_BIAS + k
+	sel['p_single'] = L.COL_P_SINGLE
+	sel['match_flag'] = L.COL_MATCH_FLAG
+	sel['prob_has_match'] = L.COL_P_ANY
+	sel['prob_this_match'] = L.COL_P_I
+	return sel
+
+
+def _fetch_table(ctx, match_tables, nrows):
+	"""device columns -> OrderedDict of numpy arrays"""
+	names = set(t['name'] for t in match_tables) | {'ncat', 'match_flag'}
+	cols = OrderedDict()
+	for name, sel in _column_selectors(match_tables).items():
+		cols[name] = ctx.fetch(sel, nrows, numpy.int64 if name in names else numpy.float64)
 	ctx.sync()
 	return cols
 
@@ -108,7 +117,7 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	min_prob=0., consider_unrelated_associations=True,
 	store_mag_hists=True,
 	logger=default_logger,
-	unrelated_mode='api', device=None, primary_range=None, as_frame=True):
+	unrelated_mode='api', device=None, primary_range=None, as_frame=True, keep_on_device=False, allow_empty=False):
 	"""Same contract as nwaylib.nway_match (nwaylib/__init__.py:31-83); see there for the arguments.
 
 	match_tables: list of dicts with name, ra, dec (deg), error (arcsec), area (deg^2), mags, magnames, maghists
@@ -121,6 +130,8 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	  device          CUDA device index (default: $NWB_DEVICE, $LOCAL_RANK or 0)
 	  primary_range   (first, count): match only these primary rows (multi-GPU sharding)
 	  as_frame        False returns an OrderedDict of numpy columns instead of a pandas.DataFrame
+	  keep_on_device  leave the table in device memory and return {'nrows', 'selectors'} (used by nway_b200.parallel)
+	  allow_empty     do not raise EmptyResultException for an empty shard
 
 	Returns one row per association, ordered by primary index, then by the secondary indices with -1 first.
 	The primary index is an ordinary column (pandas < 2.2 shape of the reference's frame)."""
@@ -169,6 +180,9 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	nrows = ctx.match(fuse_final=not auto)
 	logger.log('matching: %6d matches after filtering by search radius' % nrows)
 	if not nrows > 0:
+		if allow_empty:
+			return dict(nrows=0, selectors=_column_selectors(match_tables)) if keep_on_device else OrderedDict(
+				(k, numpy.zeros(0)) for k in _column_selectors(match_tables))
 		raise EmptyResultException('No matches.')
 
 	if auto:
@@ -205,6 +219,8 @@ def nway_match(match_tables, match_radius, prior_completeness,
 		logger.log('    cutting away %d (below p_i minimum)' % (nrows - kept))
 		nrows = kept
 
+	if keep_on_device:
+		return dict(nrows=nrows, selectors=_column_selectors(match_tables))
 	cols = _fetch_table(ctx, match_tables, nrows)
 	if not as_frame:
 		return cols

@@ -37,6 +37,7 @@ EXPORTS = {
 	'nwb_finalize': (ctypes.c_int, [ctypes.c_void_p]),
 	'nwb_truncate': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_int64_p]),
 	'nwb_fetch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+	'nwb_fetch_device': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
 	'nwb_column_ptr': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
 	'nwb_sync': (ctypes.c_int, [ctypes.c_void_p]),
 	'nwb_timing': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
@@ -166,6 +167,9 @@ class Context(object):
 		assert out.dtype.itemsize == 8 and out.flags.c_contiguous and len(out) >= nrows
 		self.check(self.lib.nwb_fetch(self.h, int(column), out.ctypes.data))
 		return out
+
+	def fetch_device(self, column, dst_ptr):
+		self.check(self.lib.nwb_fetch_device(self.h, int(column), dst_ptr))
 
 	def column_ptr(self, column):
 		p = ctypes.c_void_p()

@@ -919,6 +919,19 @@ int nwb_fetch(nwb_ctx *ctx, int column, void *dst_host)
 	return NWB_OK;
 }
 
+int nwb_fetch_device(nwb_ctx *ctx, int column, void *dst_device)
+{
+	if (!ctx || !dst_device) return NWB_ERR_ARG;
+	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	void *p = nullptr;
+	int r = column_lookup(ctx, column, &p);
+	if (r) return r;
+	CU(cudaSetDevice(ctx->device));
+	if (ctx->nrows > 0)
+		CU(cudaMemcpyAsync(dst_device, p, (size_t) ctx->nrows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	return NWB_OK;
+}
+
 int nwb_timing(nwb_ctx *ctx, int stage, float *ms)
 {
 	if (!ctx || !ms || stage < 0 || stage >= NWB_T_COUNT) return NWB_ERR_ARG;

@@ -148,6 +148,19 @@ def test_sharded_primary_ranges_concatenate_to_the_full_table():
 		assert ((cat == full[c]) | (np.isnan(cat.astype(float)) & np.isnan(full[c].astype(float)))).all(), c
 
 
+def test_nccl_sharded_match_equals_single_device():
+	"""one process per GPU over NCCL (2 ranks when the box has 2 GPUs, else 1): gathered table == single-device table"""
+	import subprocess
+	import sys
+	import torch
+	world = min(2, torch.cuda.device_count())
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr', '127.0.0.1',
+		'--master-port', '29631', os.path.join(root, 'tests', 'run_sharded.py')]
+	res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+	assert res.returncode == 0 and 'SHARDED_OK' in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
 def test_elementwise_surface():
 	from nway_b200 import fastskymatch, bayesdistance
 	k = parity.load_golden('kat.npz')

@@ -1,0 +1,69 @@
+"""CPU, world_size 2, gloo: the host-side logic of the sharded path (shard bounds, count exchange, padded
+all-gather of ragged shards, re-assembly order).  The per-shard tables come from the oracle, so this runs without
+a GPU; the same code path runs over NCCL on device tensors in tests/test_gpu_parity.py / bench.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nway_b200 import parallel
+from tests import cases
+
+
+def free_port():
+	s = socket.socket()
+	s.bind(('127.0.0.1', 0))
+	port = s.getsockname()[1]
+	s.close()
+	return port
+
+
+def worker(rank, world, port, ret):
+	os.environ['MASTER_ADDR'] = '127.0.0.1'
+	os.environ['MASTER_PORT'] = str(port)
+	dist.init_process_group('gloo', rank=rank, world_size=world)
+	try:
+		from oracle import nway_oracle as O
+		tables = cases.uniform_patch(9, (301, 4000, 3000), (1.0, 0.4, 0.6), 0.05)
+		full = O.nway_match(tables, 6.0, 0.9)
+		n0 = len(tables[0]['ra'])
+		first, count = parallel.shard_range(n0, rank, world)
+		mine = (full['A'] >= first) & (full['A'] < first + count)
+		cols = {k: torch.from_numpy(np.ascontiguousarray(v[mine])) for k, v in full.items() if not k.startswith('_')}
+		counts = parallel.exchange_counts(int(mine.sum()), None, 'cpu')
+		assert sum(counts) == len(full['A'])
+		assert parallel.row_offsets(counts)[rank] == int((full['A'] < first).sum())
+		got = parallel.allgather_columns(cols, counts)
+		for k, v in got.items():
+			a, b = v.numpy(), full[k]
+			assert a.shape == b.shape, k
+			assert np.array_equal(a, b, equal_nan=True), k
+		ret[rank] = 'ok'
+	except Exception as e:   # surface the failure in the parent
+		ret[rank] = repr(e)
+	finally:
+		dist.destroy_process_group()
+
+
+def test_shard_ranges_cover_the_primaries():
+	for n in (0, 1, 7, 100000, 1000003):
+		for world in (1, 2, 3, 8):
+			spans = [parallel.shard_range(n, r, world) for r in range(world)]
+			assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+			for (f0, c0), (f1, _) in zip(spans, spans[1:]):
+				assert f0 + c0 == f1
+			assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_world2_gloo_allgather_reassembles_the_table():
+	world = 2
+	port = free_port()
+	with mp.Manager() as mgr:
+		ret = mgr.dict()
+		mp.spawn(worker, args=(world, port, ret), nprocs=world, join=True)
+		assert dict(ret) == {0: 'ok', 1: 'ok'}, dict(ret)
