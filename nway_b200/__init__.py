@@ -69,6 +69,43 @@ def _scalar_tables(match_tables, prior_completeness, logger):
 		sub_log10prior=log10(sub))
 
 
+def _is_triple(error):
+	return isinstance(error, (tuple, list)) and len(error) == 3 and numpy.ndim(error[0]) == 1
+
+
+def _error_triple(error, n):
+	"""(sigma_ra, sigma_dec, rho) columns stacked for nwb_set_catalogue(err_kind=ELLIPSE); a circular error
+	column becomes (sigma, sigma, 0) as in nway.py:79-88"""
+	if _is_triple(error):
+		cols = [numpy.asarray(x, dtype=float) for x in error]
+	else:
+		e = numpy.asarray(error, dtype=float)
+		cols = [e, e, numpy.zeros(n)]
+	assert all(len(x) == n for x in cols)
+	return numpy.ascontiguousarray(numpy.stack(cols))
+
+
+def convert_from_ellipse(a, b, phi):
+	"""covariance parameters (sigma_x, sigma_y, rho) from major axis a, minor axis b, angle phi in radians
+	(bayesdistance.py:190-204; host side: one pass over a catalogue column)"""
+	a2 = a**2
+	b2 = b**2
+	s = numpy.sin(phi)
+	c = numpy.cos(phi)
+	s2 = s**2
+	c2 = c**2
+	sigma_x = (a2 * s2 + b2 * c2)**0.5
+	sigma_y = (a2 * c2 + b2 * s2)**0.5
+	rho = c * s * (a2 - b2) / (sigma_x * sigma_y)
+	return sigma_x, sigma_y, rho
+
+
+def ellipse_error(major, minor, angle_deg):
+	"""the CLI's `:maj:min:angle` error specification as an `error` triple (nway.py:56-65)"""
+	return convert_from_ellipse(numpy.asarray(major, dtype=float), numpy.asarray(minor, dtype=float),
+		(numpy.asarray(angle_deg, dtype=float) - 90) / 180 * pi)
+
+
 def _column_names(match_tables):
 	names = [t['name'] for t in match_tables]
 	n = len(names)
@@ -122,6 +159,8 @@ def nway_match(match_tables, match_radius, prior_completeness,
 
 	match_tables: list of dicts with name, ra, dec (deg), error (arcsec), area (deg^2), mags, magnames, maghists
 	(None = build the histogram automatically; else (bins_lo, bins_hi, hist_sel, hist_all)).
+	error may also be a triple (sigma_ra, sigma_dec, rho) of columns (see ellipse_error()): this switches the match
+	to the elliptical Bayes factor of the reference's CLI (nway.py:346-354, bayesdistance.py:207-240).
 
 	Extra keyword arguments (not in the reference):
 	  unrelated_mode  'api' (default): the behaviour of the reference API, whose correction for unrelated
@@ -144,6 +183,7 @@ def nway_match(match_tables, match_radius, prior_completeness,
 		raise ValueError("unrelated_mode must be 'api' or 'cli'")
 
 	ncats = len(match_tables)
+	elliptical = any(_is_triple(t['error']) for t in match_tables)
 	ctx = _lib.get_context(device)
 	mag_columns = []   # (catalogue, k, values in the caller's dtype with -99 -> NaN, maghist, name)
 	for c, t in enumerate(match_tables):
@@ -155,7 +195,11 @@ def nway_match(match_tables, match_radius, prior_completeness,
 			magvals[magvals == -99] = numpy.nan
 			mags.append(magvals)
 			mag_columns.append((c, k, magvals, maghist, magname))
-		ctx.set_catalogue(c, ncats, t['ra'], t['dec'], t['error'], t['area'], mags=mags)
+		if elliptical:
+			err = _error_triple(t['error'], len(t['ra']))
+			ctx.set_catalogue(c, ncats, t['ra'], t['dec'], err, t['area'], mags=mags, err_kind=_lib.ERR_ELLIPSE)
+		else:
+			ctx.set_catalogue(c, ncats, t['ra'], t['dec'], t['error'], t['area'], mags=mags)
 	if primary_range is not None:
 		ctx.set_primary_range(*primary_range)
 	else:

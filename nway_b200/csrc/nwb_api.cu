@@ -558,9 +558,13 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	if (nc < 2) return fail(ctx, NWB_ERR_ARG, "no catalogues");
 	for (int c = 0; c < nc; c++) {
 		if (!ctx->cat[c].set) return fail(ctx, NWB_ERR_ARG, "catalogue " + std::to_string(c) + " not set");
-		if (ctx->cat[c].err_kind != NWB_ERR_CIRCULAR)
-			return fail(ctx, NWB_ERR_ARG, "elliptical errors are not implemented in this build");
 	}
+	bool ell = false;
+	for (int c = 0; c < nc; c++) ell = ell || ctx->cat[c].err_kind == NWB_ERR_ELLIPSE;
+	if (ell)
+		for (int c = 0; c < nc; c++)
+			if (ctx->cat[c].err_kind != NWB_ERR_ELLIPSE)
+				return fail(ctx, NWB_ERR_ARG, "elliptical mode: every catalogue must carry (sigma_x, sigma_y, rho); pass (s, s, 0) for circular ones (nway.py:79-88)");
 	if (!ctx->params_set) return fail(ctx, NWB_ERR_ARG, "nwb_set_params not called");
 	CU(cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
@@ -589,13 +593,20 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 		P.rec = (PrimRec *) b; P.clat = b + 4 * np; P.ra_n = b + 5 * np; P.dec = b + 6 * np; P.dra = b + 7 * np;
 	}
 	int pblocks = grid_for(np, 256);
-	ENSURE(ctx->d_red, ((size_t) pblocks * 6 + 8) * sizeof(double));
-	double *d_red = (double *) ctx->d_red.p;
-	LAUNCH(ctx, k_prim_prep, pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red + 8);
-	LAUNCH(ctx, k_reduce6, 1, 32, pblocks, d_red + 8, d_red);
+	ENSURE(ctx->d_red, 8 * sizeof(double));
+	unsigned long long *d_red = (unsigned long long *) ctx->d_red.p;
+	CU(cudaMemsetAsync(d_red, 0, 6 * sizeof(unsigned long long), st));
+	LAUNCH(ctx, k_prim_prep, pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red);
 	double *red = (double *) (hs + 32);
 	CU(cudaMemcpyAsync(red, d_red, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	for (int k = 0; k < 6; k++) {   // undo the order-preserving encoding; minima were stored negated
+		unsigned long long u;
+		memcpy(&u, &red[k], 8);
+		u ^= (u >> 63) ? 0x8000000000000000ull : ~0ull;
+		memcpy(&red[k], &u, 8);
+		if (!(k & 1)) red[k] = -red[k];
+	}
 	HostGrid HG;
 	long long max_cells = 4ll << 20;
 	build_grid(red, rb_ins, rb_ins, max_cells, HG);
@@ -642,6 +653,7 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	ENSURE(ctx->d_status, 64 * sizeof(long long));
 	long long *d_status = (long long *) ctx->d_status.p;
 
+	const bool generic = nc > 2 || ell;   // N == 2 with circular errors takes the specialised row kernel
 	PairStore stores[MAXC];
 	memset(stores, 0, sizeof(stores));
 	long long R = 0;
@@ -652,10 +664,10 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 		Entry *d_entries = (Entry *) ctx->d_entries.p;
 		SpillRec *d_spill = (SpillRec *) ctx->d_spill.p;
 		CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
-		LAUNCH(ctx, (k_prim_cells<false>), pblocks, 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) nullptr,
+		LAUNCH(ctx, (k_prim_cells<false>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) nullptr,
 			(Entry *) nullptr, (long long) 0);
 		{ int r = scan_int(ctx, d_cellcnt, d_cstart, (int64_t) ncell1); if (r) return r; }
-		LAUNCH(ctx, (k_prim_cells<true>), pblocks, 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) d_cstart,
+		LAUNCH(ctx, (k_prim_cells<true>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) d_cstart,
 			d_entries, (long long) ctx->entries_cap);
 		ENSURE(ctx->d_cells, (size_t) G.ncells * sizeof(CellRec));
 		LAUNCH(ctx, k_cell_records, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cstart,
@@ -690,13 +702,13 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 			CU(cudaEventRecord(ctx->kev[2 * c + 1], st));
 		}
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[2], st));
-		if (nc == 2) {
+		if (!generic) {
 			CU(cudaMemsetAsync(d_rows + np, 0, sizeof(long long), st));
 			LAUNCH(ctx, k_rows_per_primary_2, pblocks, 256, (int) np, (const int *) d_cnt[1], d_rows);
 			{ int r = scan_ll(ctx, d_rows, d_rowoff, np + 1); if (r) return r; }
 		}
 		LAUNCH(ctx, k_collect_status, 1, 32, nc, (const int *) d_cstart + G.ncells, (const unsigned long long *) d_spillcount,
-			nc == 2 ? (const long long *) d_rowoff + np : (const long long *) nullptr, d_status);
+			!generic ? (const long long *) d_rowoff + np : (const long long *) nullptr, d_status);
 		CU(cudaMemcpyAsync(hs, d_status, 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
 		done = true;
@@ -732,7 +744,10 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	memset(&rp, 0, sizeof(rp));
 	rp.ncat = nc; rp.nmag = ctx->res_nmag; rp.np = (int) np; rp.first = first;
 	rp.radius = ctx->radius; rp.ratio_secondary = ctx->ratio_secondary;
-	for (int c = 0; c < nc; c++) rp.err[c] = ctx->cat[c].err;
+	for (int c = 0; c < nc; c++) {
+		rp.err[c] = ctx->cat[c].err; rp.n[c] = ctx->cat[c].n; rp.ra[c] = ctx->cat[c].ra; rp.dec[c] = ctx->cat[c].dec;
+	}
+	rp.ell = ell ? 1 : 0;
 	rp.T = (const ConstTables *) ctx->d_tables.p;
 	rp.S1 = stores[1];
 	rp.err1_const = ctx->cat[1].err_const ? 1 : 0;
@@ -740,8 +755,8 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	int wgrid = std::max(1, (int) std::min<int64_t>((np * 32 + 255) / 256, 148 * 64));
 	ctx->stats[1] = 0;
 
-	if (nc > 2) {
-		// ---- lists: N >= 3 needs the matches sorted and compact -----------------------------------------
+	if (generic) {
+		// ---- lists: N >= 3 (and the elliptical mode) need the matches sorted and compact -----------------------------------------
 		Lists L;
 		memset(&L, 0, sizeof(L));
 		for (int c = 1; c < nc; c++) {
@@ -784,6 +799,7 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 		CU(cudaMemsetAsync(d_rows, 0, (size_t) (np + 1) * sizeof(long long), st));
 		int r = 0;
 		switch (nc) {
+			case 2: r = launch_count<2>(ctx, rp, d_rows, wgrid); break;
 			case 3: r = launch_count<3>(ctx, rp, d_rows, wgrid); break;
 			case 4: r = launch_count<4>(ctx, rp, d_rows, wgrid); break;
 			case 5: r = launch_count<5>(ctx, rp, d_rows, wgrid); break;
@@ -811,6 +827,7 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 		int r = 0;
 		switch (nc) {
 			case 2: {
+				if (generic) { r = launch_rows<2>(ctx, rp, fuse, wgrid); break; }
 				int grid2 = (int) std::min<int64_t>((np + R2_WARPS - 1) / R2_WARPS, 148 * 4);
 				if (fuse) LAUNCH(ctx, (k_rows2<true>), grid2, R2_WARPS * 32, rp);
 				else LAUNCH(ctx, (k_rows2<false>), grid2, R2_WARPS * 32, rp);

@@ -129,7 +129,7 @@ struct CellRec {
 // box margins: rb (deg) is the search radius inflated by 1e-9 relative + 1e-12, so that rounding in the
 // box test can never reject a pair the exact formula would accept.
 __global__ void k_prim_prep(int np, long long first, const double *__restrict__ ra, const double *__restrict__ dec,
-	double rb, PrimArrays P, double *__restrict__ red /* [gridDim.x][6] */)
+	double rb, PrimArrays P, unsigned long long *__restrict__ red /* [6], zeroed */)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	double v[6] = {1e300, -1e300, 1e300, -1e300, 1e300, -1e300};   // dec min/max, A lo/hi, B lo/hi
@@ -158,16 +158,14 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 		v[2] = rn - dra; v[3] = rn + dra;
 		v[4] = rn_b - dra; v[5] = rn_b + dra;
 	}
-	// block reduce
+	// block reduce, then one atomicMax per quantity on an order-preserving integer image of the double
+	// (minima are stored negated), so no second kernel is needed
 	__shared__ double sm[6][32];
 	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
 	for (int k = 0; k < 6; k++) {
-		double x = v[k];
-		for (int o = 16; o > 0; o >>= 1) {
-			double y = __shfl_xor_sync(NWB_FULL, x, o);
-			x = (k & 1) ? fmax(x, y) : fmin(x, y);
-		}
+		double x = (k & 1) ? v[k] : -v[k];
+		for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(NWB_FULL, x, o));
 		if (lane == 0) sm[k][w] = x;
 	}
 	__syncthreads();
@@ -175,30 +173,14 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 		int nw = blockDim.x >> 5;
 #pragma unroll
 		for (int k = 0; k < 6; k++) {
-			double x = lane < nw ? sm[k][lane] : ((k & 1) ? -1e300 : 1e300);
-			for (int o = 16; o > 0; o >>= 1) {
-				double y = __shfl_xor_sync(NWB_FULL, x, o);
-				x = (k & 1) ? fmax(x, y) : fmin(x, y);
+			double x = lane < nw ? sm[k][lane] : -1e300;
+			for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(NWB_FULL, x, o));
+			if (lane == 0) {
+				unsigned long long u = (unsigned long long) __double_as_longlong(x);
+				u ^= (u >> 63) ? ~0ull : 0x8000000000000000ull;
+				atomicMax(red + k, u);
 			}
-			if (lane == 0) red[blockIdx.x * 6 + k] = x;
 		}
-	}
-}
-
-__global__ void k_reduce6(int nblocks, const double *__restrict__ red, double *__restrict__ out)
-{
-	int lane = threadIdx.x;
-	for (int k = 0; k < 6; k++) {
-		double x = (k & 1) ? -1e300 : 1e300;
-		for (int i = lane; i < nblocks; i += 32) {
-			double y = red[i * 6 + k];
-			x = (k & 1) ? fmax(x, y) : fmin(x, y);
-		}
-		for (int o = 16; o > 0; o >>= 1) {
-			double y = __shfl_xor_sync(NWB_FULL, x, o);
-			x = (k & 1) ? fmax(x, y) : fmin(x, y);
-		}
-		if (lane == 0) out[k] = x;
 	}
 }
 
@@ -210,7 +192,8 @@ template <bool FILL>
 __global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double dra_eps,
 	int *__restrict__ cellcnt, const int *__restrict__ cstart, Entry *__restrict__ entries, long long entries_cap)
 {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int i = t >> 2, bslot = t & 3;   // four threads per primary, one declination band each
 	if (i >= np) return;
 	if (FILL && (long long) cstart[G.ncells] > entries_cap) return;
 	double d = P.dec[i], rn = P.ra_n[i], dra = P.dra[i];
@@ -228,7 +211,7 @@ __global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double
 		en.p = i;
 	}
 	double di = dra + dra_eps;
-	for (int b = b0; b <= b1; b++) {
+	for (int b = b0 + bslot; b <= b1; b += 4) {
 		BandRec B = load_band(G, b);
 		int n = B.nra;
 		int i0, cnt;
@@ -584,7 +567,10 @@ struct RowParams {
 	int ncat, nmag, np;
 	long long first;                 // global index of local primary 0
 	double radius, ratio_secondary;
-	const double *err[MAXC];         // sigma columns (circular)
+	const double *err[MAXC];         // sigma columns (circular); elliptical: sigma_x | sigma_y | rho, each n[c] long
+	int ell;                         // elliptical mode (nway.py:346-354): every catalogue carries a triple
+	long long n[MAXC];               // catalogue sizes (stride of the error triple)
+	const double *ra[MAXC], *dec[MAXC];
 	const ConstTables *T;
 	Lists L;
 	Columns C;
@@ -696,6 +682,65 @@ __global__ void k_rows_per_primary_2(int np, const int *__restrict__ cnt, long l
 // ---------------------------------------------------------------------------------------------------------
 // per-row finalisation pieces shared by k_rows<FUSE> and k_final
 // ---------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------
+// elliptical positional errors (CLI only in the reference): bayesdistance.py:164-240, fastskymatch.py:50-74
+// ---------------------------------------------------------------------------------------------------------
+// Offsets (arcsec) of the target t in the tangent frame centred on the origin o: what astropy's
+// SkyOffsetFrame(origin=o) gives for t, with the sign of fastskymatch.py:65-66.
+__device__ __forceinline__ void offsets_ref(double ra_o, double dec_o, double ra_t, double dec_t, double &dra, double &ddec)
+{
+	const double D2R = 0.017453292519943295, R2D = 57.29577951308232;   // numpy.radians / numpy.degrees constants
+	double so, co, st, ct, sd, cd;
+	sincos(dec_o * D2R, &so, &co);
+	sincos(dec_t * D2R, &st, &ct);
+	sincos(ra_t * D2R - ra_o * D2R, &sd, &cd);
+	double lon = atan2(ct * sd, co * ct * cd + so * st);
+	double z = co * st - so * ct * cd;
+	double lat = asin(fmin(fmax(z, -1.0), 1.0));
+	dra = -(lon * R2D) * 60 * 60;
+	ddec = -(lat * R2D) * 60 * 60;
+}
+
+// v^T Sigma^-1 v for the unit vector v (bayesdistance.py:150-161,183-187)
+__device__ __forceinline__ double dir_precision(double vx, double vy, double sx, double sy, double rho)
+{
+	double f = 1.0 / (sx * sx * (sy * sy) * (1 - rho * rho));
+	double m11 = f * (sy * sy), m12 = f * -rho * sx * sy, m22 = f * (sx * sx);
+	double l1 = vx * m11 + vy * m12;
+	double l2 = vx * m12 + vy * m22;
+	return l1 * vx + l2 * vy;
+}
+
+// For the catalogues in `present` (bit c) with sources sidx[c]: the circularised errors (-> sig) and, for every
+// present pair a < b, the separation rescaled by the ratio of circular to directional error (-> sep), ready for
+// log_bf_ref.  bayesdistance.py:207-240; offsets measured in the frame of the later catalogue's source as the CLI
+// does (fastskymatch.py:299-312 with nway.py's make_separation_table_matrix).
+__device__ __forceinline__ void ell_prepare(const RowParams &R, unsigned present, const long long *sidx, double *sig, double *sep)
+{
+	const int nc = R.ncat;
+	double sx[MAXC], sy[MAXC], rho[MAXC], ra[MAXC], de[MAXC];
+	for (int c = 0; c < nc; c++)
+		if (present >> c & 1u) {
+			long long i = sidx[c];
+			sx[c] = R.err[c][i]; sy[c] = R.err[c][R.n[c] + i]; rho[c] = R.err[c][2 * R.n[c] + i];
+			ra[c] = R.ra[c][i]; de[c] = R.dec[c][i];
+			sig[c] = sqrt((sx[c] * sx[c] + sy[c] * sy[c]) / 2);
+		}
+	for (int a = 0; a < nc; a++)
+		for (int b = a + 1; b < nc; b++)
+			if ((present >> a & 1u) && (present >> b & 1u)) {
+				double vx, vy;
+				offsets_ref(ra[b], de[b], ra[a], de[a], vx, vy);
+				double d = sqrt(vx * vx + vy * vy);
+				double ux = d == 0 ? 0.7071067811865476 : vx / (d + 1e-300);
+				double uy = d == 0 ? 0.7071067811865476 : vy / (d + 1e-300);
+				double wa = dir_precision(ux, uy, sx[a], sy[a], rho[a]);
+				double wb = dir_precision(ux, uy, sx[b], sy[b], rho[b]);
+				double ratio = (sig[a] * sig[a] + sig[b] * sig[b]) / (1 / wa + 1 / wb);
+				sep[pair_index(a, b, nc)] = d * (1.0 / sqrt(ratio));
+			}
+}
+
 // bias lookup for one row: returns sum of weights in the reference's order ((0 + w1) + w2 ...), writes bias cols
 __device__ __forceinline__ double row_bias(const RowParams &R, long long row, const long long *sidx /* [ncat] */)
 {
@@ -842,10 +887,17 @@ k_rows(RowParams R)
 				}
 				R.C.sepmax[row] = smax;
 				R.C.ncat[row] = __popc(present);
+				double lbf;
+				if (R.ell) {
+					double esig[MAXC], esep[MAXP];
+					ell_prepare(R, present, sidx, esig, esep);
+					lbf = log_bf_ref<0>(T, NC, present, esig, esep);
+				} else {
 #pragma unroll
-				for (int c = 1; c < NC; c++)
-					if (present >> c & 1u) sig[c] = R.err[c][sidx[c]];
-				double lbf = log_bf_ref<NC>(T, NC, present, sig, sep);
+					for (int c = 1; c < NC; c++)
+						if (present >> c & 1u) sig[c] = R.err[c][sidx[c]];
+					lbf = log_bf_ref<NC>(T, NC, present, sig, sep);
+				}
 				unsigned smask = present >> 1;
 				double prior = T->prior[smask], l10p = T->log10prior[smask];
 				R.C.lbf_u[row] = lbf;
@@ -875,11 +927,16 @@ k_rows(RowParams R)
 constexpr int R2_WARPS = 8;
 constexpr int R2_CAP = 128;   // matches per primary handled in shared memory; larger groups take k_rows2_big
 
+constexpr int R2_NB = 128;    // buckets of the in-group sort
+
 struct __align__(16) R2Smem {
 	int s_in[R2_CAP];
 	int s[R2_CAP];
 	double sep[R2_CAP];
-	double v[R2_CAP + 1];
+	double v[R2_CAP + 2];           // (+2 keeps hist 16-byte aligned)
+	int hist[R2_NB + 4];            // bucket counts, then exclusive bucket starts (R2_NB + 1 used)
+	unsigned char pos[R2_CAP];      // arrival position of an element inside its bucket
+	unsigned char ord[R2_CAP];      // element ids in bucket order
 };
 
 // per-lane memo of the error-dependent terms of the 2-catalogue Bayes factor: catalogues very often carry one
@@ -963,21 +1020,51 @@ k_rows2(RowParams R)
 	}
 	__syncwarp();
 	if (n <= R2_CAP) {
+		// Sort the group by secondary index: bucket the indices over [min, max] of the group (monotone map, so an
+		// element's rank = elements in lower buckets + smaller elements of its own bucket), ~1 element per bucket.
+		int smin = 0x7fffffff, smax = -1;
 		for (int e = lane; e < n; e += 32) {
 			Slot16 x = store_get(R.S1, p, e);
 			M.s_in[e] = x.s;
 			M.v[e] = x.sep;   // parked here until ranked
+			smin = min(smin, x.s);
+			smax = max(smax, x.s);
+		}
+		*reinterpret_cast<int4 *>(&M.hist[4 * lane]) = make_int4(0, 0, 0, 0);
+		smin = __reduce_min_sync(NWB_FULL, smin);
+		smax = __reduce_max_sync(NWB_FULL, smax);
+		const float bscale = (float) R2_NB / ((float) (smax - smin) + 1.0f);
+		__syncwarp();
+		for (int e = lane; e < n; e += 32) {
+			int b = min(R2_NB - 1, (int) ((float) (M.s_in[e] - smin) * bscale));
+			M.pos[e] = (unsigned char) atomicAdd(&M.hist[b], 1);
+		}
+		__syncwarp();
+		{
+			int4 c = *reinterpret_cast<const int4 *>(&M.hist[4 * lane]);
+			int tot = c.x + c.y + c.z + c.w;
+			int incl = tot;
+			for (int o = 1; o < 32; o <<= 1) {
+				int y = __shfl_up_sync(NWB_FULL, incl, o);
+				if (lane >= o) incl += y;
+			}
+			int base = incl - tot;
+			__syncwarp();
+			*reinterpret_cast<int4 *>(&M.hist[4 * lane]) = make_int4(base, base + c.x, base + c.x + c.y, base + c.x + c.y + c.z);
+			if (lane == 31) M.hist[R2_NB] = incl;
+		}
+		__syncwarp();
+		for (int e = lane; e < n; e += 32) {
+			int b = min(R2_NB - 1, (int) ((float) (M.s_in[e] - smin) * bscale));
+			M.ord[M.hist[b] + M.pos[e]] = (unsigned char) e;
 		}
 		__syncwarp();
 		for (int e = lane; e < n; e += 32) {
 			int mine = M.s_in[e];
-			int rank = 0;
-			int f = 0;
-			for (; f + 4 <= n; f += 4) {
-				int4 o = *reinterpret_cast<const int4 *>(&M.s_in[f]);
-				rank += (o.x < mine) + (o.y < mine) + (o.z < mine) + (o.w < mine);
-			}
-			for (; f < n; f++) rank += M.s_in[f] < mine;
+			int b = min(R2_NB - 1, (int) ((float) (mine - smin) * bscale));
+			int lo = M.hist[b], hi = M.hist[b + 1];
+			int rank = lo;
+			for (int j = lo; j < hi; j++) rank += M.s_in[M.ord[j]] < mine;
 			M.s[rank] = mine;
 			M.sep[rank] = M.v[e];
 		}
@@ -1114,12 +1201,18 @@ __global__ void k_correct_cli(RowParams R)
 				unsigned A = M & pres;
 				if (__popc(A) < 2) continue;
 				double sig[MAXC], sep[MAXP];
-				for (int c = 1; c < nc; c++)
-					if (A >> (c - 1) & 1u) sig[c] = R.err[c][R.C.idx[c][row]];
-				for (int a = 1; a < nc; a++)
-					for (int b = a + 1; b < nc; b++)
-						if ((A >> (a - 1) & 1u) && (A >> (b - 1) & 1u))
-							sep[pair_index(a, b, nc)] = R.C.sep[pair_index(a, b, nc)][row];
+				if (R.ell) {
+					long long sidx[MAXC];
+					for (int c = 1; c < nc; c++) sidx[c] = R.C.idx[c][row];
+					ell_prepare(R, A << 1, sidx, sig, sep);
+				} else {
+					for (int c = 1; c < nc; c++)
+						if (A >> (c - 1) & 1u) sig[c] = R.err[c][R.C.idx[c][row]];
+					for (int a = 1; a < nc; a++)
+						for (int b = a + 1; b < nc; b++)
+							if ((A >> (a - 1) & 1u) && (A >> (b - 1) & 1u))
+								sep[pair_index(a, b, nc)] = R.C.sep[pair_index(a, b, nc)][row];
+				}
 				double lp = log_bf_ref<0>(T, nc, A << 1, sig, sep) + T->sub_log10prior[A];
 				if (lp > best) best = lp;
 			}

@@ -155,9 +155,30 @@ def crossproduct_complete(radectables, radius_deg):
 	return np.concatenate(blocks, axis=0)
 
 
+def is_elliptical(tables):
+	"""a catalogue's 'error' may be a triple (sigma_ra, sigma_dec, rho) instead of one sigma column: the CLI's
+	elliptical mode (nway.py:25-98, 346-354).  One elliptical catalogue switches the whole match to that mode,
+	circular catalogues becoming (sigma, sigma, 0) (nway.py:79-88)."""
+	return any(isinstance(t['error'], (tuple, list)) and len(t['error']) == 3 for t in tables)
+
+
+def error_triples(tables):
+	out = []
+	for t in tables:
+		e = t['error']
+		if isinstance(e, (tuple, list)) and len(e) == 3:
+			out.append(tuple(np.asarray(x, dtype=float) for x in e))
+		else:
+			e = np.asarray(e, dtype=float)
+			out.append((e, e, np.zeros_like(e)))
+	return out
+
+
 def create_match_table(tables, match_radius, enumerator='complete'):
 	"""nwaylib/__init__.py:123-196.  Returns dict(idx (R,N) int64, sep {(a,b): (R,)}, sepmax, ncat,
-	errors [N x (R,)])."""
+	errors [N x (R,)]); in elliptical mode also off {(a,b): (dra, ddec)} in arcsec, measured like the CLI does
+	(fastskymatch.py:299-331: offset frame centred on the source of the LATER catalogue b, the earlier one is the
+	target) and errors as triples."""
 	radec = [(np.asarray(t['ra'], dtype=float), np.asarray(t['dec'], dtype=float)) for t in tables]
 	radius_deg = match_radius / 60. / 60
 	if enumerator == 'refhash':
@@ -180,7 +201,17 @@ def create_match_table(tables, match_radius, enumerator='complete'):
 	keep = sepmax < match_radius
 	idx = idx[keep]
 	out = dict(idx=idx, sep={k: v[keep] for k, v in sep.items()}, sepmax=sepmax[keep], ncat=(idx > -1).sum(axis=1))
-	out['errors'] = [np.asarray(t['error'], dtype=float)[idx[:, c]] for c, t in enumerate(tables)]
+	if is_elliptical(tables):
+		trip = error_triples(tables)
+		out['errors'] = [tuple(x[idx[:, c]] for x in trip[c]) for c in range(n)]
+		out['off'] = {}
+		for a in range(n):
+			for b in range(a + 1, n):
+				ia, ib = idx[:, a], idx[:, b]
+				_, dra, ddec = offsets((radec[b][0][ib], radec[b][1][ib]), (radec[a][0][ia], radec[a][1][ia]))
+				out['off'][(a, b)] = (dra * 60 * 60, ddec * 60 * 60)
+	else:
+		out['errors'] = [np.asarray(t['error'], dtype=float)[idx[:, c]] for c, t in enumerate(tables)]
 	return out
 
 
@@ -253,9 +284,15 @@ def single_log_bf(mt, nu, nu_plus, pc):
 	for cats, mask in presence_patterns(idx):
 		if not mask.any():
 			continue
-		p = [[mt['sep'][(a, b)][mask] if a < b else None for b in cats] for a in cats]
-		s = [mt['errors'][c][mask] for c in cats]
-		lbf[mask] = log_bf(p, s)
+		if 'off' in mt:   # nway.py:346-354
+			sra = [[mt['off'][(a, b)][0][mask] if a < b else None for b in cats] for a in cats]
+			sde = [[mt['off'][(a, b)][1][mask] if a < b else None for b in cats] for a in cats]
+			errs = [tuple(x[mask] for x in mt['errors'][c]) for c in cats]
+			lbf[mask] = log_bf_elliptical(sra, sde, errs) if len(cats) > 1 else 0.0
+		else:
+			p = [[mt['sep'][(a, b)][mask] if a < b else None for b in cats] for a in cats]
+			s = [mt['errors'][c][mask] for c in cats]
+			lbf[mask] = log_bf(p, s)
 		sel = np.zeros(idx.shape[1], dtype=bool)
 		sel[cats] = True
 		prior[mask] = nu[0] * np.prod(pc[sel]) / np.prod(nu_plus[sel])
@@ -339,10 +376,17 @@ def correct_unrelated_cli(mt, lbf, nu, nu_plus, group_start):
 					continue
 				key = (j, aug)
 				if key not in cache:
-					p = [[[mt['sep'][(a, b)][j]] if a < b else None for b in aug] for a in aug]
-					s = [[mt['errors'][k][j]] for k in aug]
 					pr = nu[aug[0]] / np.prod(nu_plus[list(aug)])
-					cache[key] = float(log_bf(p, s)[0] + np.log10(pr))
+					if 'off' in mt:   # nway.py:404-411
+						sra = [[np.array([mt['off'][(a, b)][0][j]]) if a < b else None for b in aug] for a in aug]
+						sde = [[np.array([mt['off'][(a, b)][1][j]]) if a < b else None for b in aug] for a in aug]
+						errs = [tuple(np.array([x[j]]) for x in mt['errors'][k]) for k in aug]
+						val = log_bf_elliptical(sra, sde, errs)[0]
+					else:
+						p = [[[mt['sep'][(a, b)][j]] if a < b else None for b in aug] for a in aug]
+						s = [[mt['errors'][k][j]] for k in aug]
+						val = log_bf(p, s)[0]
+					cache[key] = float(val + np.log10(pr))
 				best = max(best, cache[key])
 			if best > 0:
 				out[i] += best

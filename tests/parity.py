@@ -19,11 +19,12 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 RTOL = 1e-10
 
 
-def column_error(name, ref, got):
+def column_error(name, ref, got, rtol=None):
 	"""returns (ok, worst absolute error, worst relative error, index of worst)"""
 	ref = np.asarray(ref)
 	got = np.asarray(got)
 	assert ref.shape == got.shape, (name, ref.shape, got.shape)
+	RTOL = globals()['RTOL'] if rtol is None else rtol
 	if ref.size == 0:
 		return True, 0.0, 0.0, -1
 	if ref.dtype.kind in 'iub':
@@ -43,7 +44,7 @@ def column_error(name, ref, got):
 	if name == 'prob_has_match':
 		tol = RTOL * np.abs(r) + 2e-13
 	elif name.startswith('dist_bayesfactor'):
-		tol = 1e-9 + 1e-12 * np.abs(r)
+		tol = max(1e-9, 10 * RTOL) + 1e-12 * np.abs(r)
 	elif name.startswith('Separation'):
 		tol = 1e-9 + RTOL * np.abs(r)
 	else:
@@ -54,7 +55,7 @@ def column_error(name, ref, got):
 	return bool((d <= tol).all()), float(d.max()), float(rel[np.abs(r) >= 1e-30].max() if (np.abs(r) >= 1e-30).any() else 0.0), worst
 
 
-def assert_tables_match(ref, got, columns=None, context=''):
+def assert_tables_match(ref, got, columns=None, context='', rtol=None):
 	"""ref / got: mappings column -> array.  Row set and order must be identical; see module docstring."""
 	columns = columns or [c for c in ref.keys() if not c.startswith('_')]
 	report = []
@@ -63,7 +64,7 @@ def assert_tables_match(ref, got, columns=None, context=''):
 		assert c in got, '%s: column %s missing (have %s)' % (context, c, list(got.keys()))
 		a, b = np.asarray(ref[c]), np.asarray(got[c])
 		assert len(a) == len(b), '%s: column %s has %d rows, expected %d' % (context, c, len(b), len(a))
-		ok, dabs, drel, worst = column_error(c, a, b)
+		ok, dabs, drel, worst = column_error(c, a, b, rtol)
 		report.append('%-30s %s  max|d| %.3e  max rel %.3e' % (c, 'ok  ' if ok else 'FAIL', dabs, drel))
 		if not ok:
 			failed.append('%s: %s row %d ref %r got %r' % (context, c, worst, a[worst], b[worst]))

@@ -148,6 +148,40 @@ def test_sharded_primary_ranges_concatenate_to_the_full_table():
 		assert ((cat == full[c]) | (np.isnan(cat.astype(float)) & np.isnan(full[c].astype(float)))).all(), c
 
 
+@pytest.mark.parametrize('ncat,mode', [(2, 'api'), (3, 'api'), (3, 'cli'), (4, 'cli')])
+def test_elliptical_errors(ncat, mode):
+	"""the CLI's elliptical Bayes factor (nway.py:346-354 / bayesdistance.py:207-240); the oracle's restatement is
+	pinned to the real log_bf_elliptical / convert_from_ellipse (tests/golden/kat.npz); the tangent-plane offsets
+	(astropy in the reference) are the closed form of SURVEY.md A.6 on both sides"""
+	import nway_b200
+	from oracle import nway_oracle as O
+	def build():
+		rng = np.random.default_rng(17)
+		tables = cases.uniform_patch(19, (150, 4000, 3000, 2500)[:ncat], (1.0, 0.4, 0.6, 0.5)[:ncat], 0.05, dec0=35.0)
+		for k, t in enumerate(tables):
+			n = len(t['ra'])
+			if k == 2:
+				continue   # one catalogue keeps a circular error column
+			a = rng.uniform(0.5, 2.0, n)
+			t['error'] = nway_b200.ellipse_error(a, rng.uniform(0.3, 1.0, n) * a, rng.uniform(0, 180, n))
+		return tables
+	got = run_cuda(build(), 6.0, 0.9, unrelated_mode=mode)
+	ref = O.nway_match(build(), 6.0, 0.9, unrelated_mode=mode)
+	# tolerance 1e-8 here: the tangent-plane latitude asin(cos d1 sin d2 - sin d1 cos d2 cos dl) cancels ~4 digits at
+	# dec 35 deg (terms 0.47, result 3e-5), so 1-ulp differences of sin/cos give 1e-12 in the offsets and, through
+	# psi'^2 / sigma^2 (up to ~70 for rows with p_i >= 1e-30), a few 1e-10 in p_i; this piece is unpinned anyway
+	report('elliptical%d/%s' % (ncat, mode), parity.assert_tables_match(ref, got, columns=[c for c in ref if not c.startswith('_')],
+		context='elliptical', rtol=1e-8))
+	# and the reference's own consistency property (tests/bayesdistance_test.py:149-203): circular errors through
+	# the elliptical code give the circular answer to ~7 decimals
+	circ = cases.uniform_patch(19, (150, 4000, 3000)[:min(ncat, 3)], (1.0, 0.4, 0.6)[:min(ncat, 3)], 0.05)
+	a = run_cuda(circ, 6.0, 0.9)
+	for t in circ:
+		t['error'] = (t['error'], t['error'].copy(), np.zeros(len(t['ra'])))
+	b = run_cuda(circ, 6.0, 0.9)
+	assert np.array_equal(a['A'], b['A']) and np.abs(a['dist_bayesfactor'] - b['dist_bayesfactor']).max() < 1e-6
+
+
 def test_nccl_sharded_match_equals_single_device():
 	"""one process per GPU over NCCL (2 ranks when the box has 2 GPUs, else 1): gathered table == single-device table"""
 	import subprocess
