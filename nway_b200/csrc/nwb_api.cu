@@ -64,6 +64,14 @@ struct nwb_ctx {
 	unsigned long long spill_cap = 0;
 	long long *h_status = nullptr;   // pinned
 	int k1_blocks_per_sm = 0, num_sms = 0;
+	// grid geometry of the previous match, re-used when the primaries' bounding box and the radius are unchanged
+	bool geom_valid = false;
+	double geom_rb = 0;
+	int64_t geom_np = -1, geom_first = -1;
+	BoundsKey geom_key;
+	Grid geom_G;
+	int64_t cols_cap_rows = 0;
+	int cols_cap_ncols = 0;
 
 	// result
 	bool matched = false, finalized = false;
@@ -551,9 +559,28 @@ static int run_final(nwb_ctx *ctx)
 	return NWB_OK;
 }
 
-int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
+// the scalar part of the row-kernel parameter block
+static int fill_row_params(nwb_ctx *ctx, const PairStore *stores, int64_t first, int64_t np, bool ell)
 {
-	if (!ctx) return NWB_ERR_ARG;
+	const int nc = ctx->ncat;
+	RowParams &rp = ctx->rp;
+	memset(&rp, 0, sizeof(rp));
+	rp.ncat = nc; rp.nmag = ctx->res_nmag; rp.np = (int) np; rp.first = first;
+	rp.radius = ctx->radius; rp.ratio_secondary = ctx->ratio_secondary;
+	for (int c = 0; c < nc; c++) {
+		rp.err[c] = ctx->cat[c].err; rp.n[c] = ctx->cat[c].n; rp.ra[c] = ctx->cat[c].ra; rp.dec[c] = ctx->cat[c].dec;
+	}
+	rp.ell = ell ? 1 : 0;
+	rp.T = (const ConstTables *) ctx->d_tables.p;
+	rp.S1 = stores[1];
+	rp.err1_const = ctx->cat[1].err_const ? 1 : 0;
+	rp.err1_value = ctx->cat[1].err_value;
+	rp.guard = nullptr;
+	return NWB_OK;
+}
+
+static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_cached)
+{
 	const int nc = ctx->ncat;
 	if (nc < 2) return fail(ctx, NWB_ERR_ARG, "no catalogues");
 	for (int c = 0; c < nc; c++) {
@@ -597,27 +624,35 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	unsigned long long *d_red = (unsigned long long *) ctx->d_red.p;
 	CU(cudaMemsetAsync(d_red, 0, 6 * sizeof(unsigned long long), st));
 	LAUNCH(ctx, k_prim_prep, pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red);
-	double *red = (double *) (hs + 32);
-	CU(cudaMemcpyAsync(red, d_red, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
-	for (int k = 0; k < 6; k++) {   // undo the order-preserving encoding; minima were stored negated
-		unsigned long long u;
-		memcpy(&u, &red[k], 8);
-		u ^= (u >> 63) ? 0x8000000000000000ull : ~0ull;
-		memcpy(&red[k], &u, 8);
-		if (!(k & 1)) red[k] = -red[k];
-	}
-	HostGrid HG;
-	long long max_cells = 4ll << 20;
-	build_grid(red, rb_ins, rb_ins, max_cells, HG);
-	pretest_constants(HG.g, rb_ins);
-	Grid G = HG.g;
-	{
-		size_t nb = (size_t) G.nbands;
+	const bool use_cached = allow_cached && ctx->geom_valid && ctx->geom_rb == rb && ctx->geom_np == np && ctx->geom_first == first;
+	if (!use_cached) {
+		// the grid geometry is chosen on the host from the bounding box: one sync.  It is kept for the next match
+		// on this context, which only has to verify (on the device) that the box is still the same.
+		unsigned long long *raw = (unsigned long long *) (hs + 32);
+		CU(cudaMemcpyAsync(raw, d_red, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		double red[6];
+		for (int k = 0; k < 6; k++) {   // undo the order-preserving encoding; minima were stored negated
+			ctx->geom_key.k[k] = raw[k];
+			unsigned long long u = raw[k];
+			u ^= (u >> 63) ? 0x8000000000000000ull : ~0ull;
+			memcpy(&red[k], &u, 8);
+			if (!(k & 1)) red[k] = -red[k];
+		}
+		HostGrid HG;
+		long long max_cells = 4ll << 20;
+		build_grid(red, rb_ins, rb_ins, max_cells, HG);
+		pretest_constants(HG.g, rb_ins);
+		size_t nb = (size_t) HG.g.nbands;
 		ENSURE(ctx->d_bands, nb * sizeof(BandRec) + 64);
 		CU(cudaMemcpyAsync(ctx->d_bands.p, HG.bands.data(), nb * sizeof(BandRec), cudaMemcpyHostToDevice, st));
-		G.bands = (const BandRec *) ctx->d_bands.p;
+		CU(cudaStreamSynchronize(st));   // HG.bands is a temporary
+		HG.g.bands = (const BandRec *) ctx->d_bands.p;
+		ctx->geom_G = HG.g;
+		ctx->geom_rb = rb; ctx->geom_np = np; ctx->geom_first = first;
+		ctx->geom_valid = true;
 	}
+	const Grid G = ctx->geom_G;
 	// one zero-initialised block: cell counters | per-catalogue match counters | scalar counters
 	const size_t ncell1 = (size_t) G.ncells + 1;
 	const size_t cnt_stride = ((size_t) np + 1 + 3) / 4 * 4;
@@ -657,7 +692,7 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	PairStore stores[MAXC];
 	memset(stores, 0, sizeof(stores));
 	long long R = 0;
-	bool done = false;
+	bool done = false, speculated = false;
 	for (int attempt = 0; !done && attempt < 4; attempt++) {
 		ENSURE(ctx->d_entries, ctx->entries_cap * sizeof(Entry));
 		ENSURE(ctx->d_spill, (size_t) ctx->spill_cap * (nc - 1) * sizeof(SpillRec));
@@ -708,15 +743,41 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 			{ int r = scan_ll(ctx, d_rows, d_rowoff, np + 1); if (r) return r; }
 		}
 		LAUNCH(ctx, k_collect_status, 1, 32, nc, (const int *) d_cstart + G.ncells, (const unsigned long long *) d_spillcount,
-			!generic ? (const long long *) d_rowoff + np : (const long long *) nullptr, d_status);
+			!generic ? (const long long *) d_rowoff + np : (const long long *) nullptr, (const unsigned long long *) d_red,
+			ctx->geom_key, d_status);
+		// speculative K2: if the table of the previous match was big enough, launch the row kernel right away; it
+		// checks the status words on the device.  One host sync per match instead of three.
+		speculated = false;
+		if (!generic && ctx->cols_cap_rows > 0 && ctx->cols_cap_ncols == 2 + 1 + 9 + ctx->res_nmag) {
+			int r = fill_row_params(ctx, stores, first, np, ell);
+			if (r) return r;
+			ctx->rp.row_off = d_rowoff;
+			{ int r2 = layout_columns(ctx, ctx->d_cols, ctx->cols_cap_rows, nc, ctx->res_nmag, ctx->cols, ctx->ncols); if (r2) return r2; }
+			ctx->rp.C = ctx->cols;
+			ctx->rp.guard = d_status;
+			ctx->rp.max_rows = ctx->cols_cap_rows;
+			ctx->rp.entries_cap = (long long) ctx->entries_cap;
+			CU(cudaEventRecord(ctx->ev[3], st));
+			CU(cudaEventRecord(ctx->kev[0], st));
+			int grid2 = (int) std::min<int64_t>((np + R2_WARPS - 1) / R2_WARPS, 148 * 4);
+			if (fuse) LAUNCH(ctx, (k_rows2<true>), grid2, R2_WARPS * 32, ctx->rp);
+			else LAUNCH(ctx, (k_rows2<false>), grid2, R2_WARPS * 32, ctx->rp);
+			CU(cudaEventRecord(ctx->kev[1], st));
+			speculated = true;
+		}
 		CU(cudaMemcpyAsync(hs, d_status, 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
+		if (hs[9] != 0) {   // the primaries moved: the cached geometry is stale
+			ctx->geom_valid = false;
+			return 1;       // caller retries without the cache
+		}
 		done = true;
 		if ((size_t) hs[0] > ctx->entries_cap) { ctx->entries_cap = (size_t) hs[0] + 1024; done = false; }
 		for (int c = 1; c < nc; c++)
 			if ((unsigned long long) hs[c] > ctx->spill_cap) { ctx->spill_cap = (unsigned long long) hs[c] + 1024; done = false; }
 		R = hs[8];
 		ctx->stats[3] = hs[0];
+		if (speculated && !(done && hs[1] == 0 && R <= ctx->cols_cap_rows)) speculated = false;   // the kernel declined
 	}
 	if (!done) return fail(ctx, NWB_ERR_NOMEM, "grid / spill buffers kept overflowing");
 	ctx->stats[2] = G.ncells;
@@ -741,17 +802,7 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	}
 
 	RowParams &rp = ctx->rp;
-	memset(&rp, 0, sizeof(rp));
-	rp.ncat = nc; rp.nmag = ctx->res_nmag; rp.np = (int) np; rp.first = first;
-	rp.radius = ctx->radius; rp.ratio_secondary = ctx->ratio_secondary;
-	for (int c = 0; c < nc; c++) {
-		rp.err[c] = ctx->cat[c].err; rp.n[c] = ctx->cat[c].n; rp.ra[c] = ctx->cat[c].ra; rp.dec[c] = ctx->cat[c].dec;
-	}
-	rp.ell = ell ? 1 : 0;
-	rp.T = (const ConstTables *) ctx->d_tables.p;
-	rp.S1 = stores[1];
-	rp.err1_const = ctx->cat[1].err_const ? 1 : 0;
-	rp.err1_value = ctx->cat[1].err_value;
+	if (!speculated) { int r = fill_row_params(ctx, stores, first, np, ell); if (r) return r; }
 	int wgrid = std::max(1, (int) std::min<int64_t>((np * 32 + 255) / 256, 148 * 64));
 	ctx->stats[1] = 0;
 
@@ -814,16 +865,21 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 		R = hs[25];
 	} else {
 		ctx->stats[1] = R - np;
-		CU(cudaEventRecord(ctx->ev[3], st));
+		if (!speculated) CU(cudaEventRecord(ctx->ev[3], st));
 	}
 
 	// ---- K2: rows ------------------------------------------------------------------------------------------
-	rp.row_off = d_rowoff;
 	ctx->res_ncat = nc;
-	{ int r = layout_columns(ctx, ctx->d_cols, R, nc, ctx->res_nmag, ctx->cols, ctx->ncols); if (r) return r; }
-	rp.C = ctx->cols;
-	CU(cudaEventRecord(ctx->kev[0], st));
-	{
+	if (!speculated) {
+		rp.row_off = d_rowoff;
+		// keep the capacity of the previous table (grow-only) so that the next match can launch K2 speculatively
+		int64_t cap_rows = std::max<int64_t>(R + R / 16 + 1024, ctx->cols_cap_rows);
+		if (ctx->cols_cap_ncols != nc + nc * (nc - 1) / 2 + 9 + ctx->res_nmag) cap_rows = R + R / 16 + 1024;
+		{ int r = layout_columns(ctx, ctx->d_cols, cap_rows, nc, ctx->res_nmag, ctx->cols, ctx->ncols); if (r) return r; }
+		ctx->cols_cap_rows = cap_rows;
+		ctx->cols_cap_ncols = ctx->ncols;
+		rp.C = ctx->cols;
+		CU(cudaEventRecord(ctx->kev[0], st));
 		int r = 0;
 		switch (nc) {
 			case 2: {
@@ -841,8 +897,9 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 			default: r = launch_rows<8>(ctx, rp, fuse, wgrid); break;
 		}
 		if (r) return r;
+		CU(cudaEventRecord(ctx->kev[1], st));
 	}
-	CU(cudaEventRecord(ctx->kev[1], st));
+	rp.guard = nullptr;   // k_final / later calls are not speculative
 	if (cli) LAUNCH(ctx, k_correct_cli, wgrid, 256, rp);
 	CU(cudaEventRecord(ctx->ev[4], st));
 	if (fuse_final && !fuse) { int r = run_final(ctx); if (r) return r; }
@@ -863,6 +920,14 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	if (nrows) *nrows = R;
 	if (R == 0) return fail(ctx, NWB_ERR_EMPTY, "No matches.");
 	return NWB_OK;
+}
+
+int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	int r = match_impl(ctx, fuse_final, nrows, true);
+	if (r == 1) r = match_impl(ctx, fuse_final, nrows, false);   // the cached grid geometry did not fit: rebuild it
+	return r;
 }
 
 int nwb_finalize(nwb_ctx *ctx)
@@ -903,12 +968,13 @@ int nwb_truncate(nwb_ctx *ctx, double min_prob, int64_t *nrows)
 	memset(&C2, 0, sizeof(C2));
 	int ncols2 = 0;
 	{ int r = layout_columns(ctx, ctx->d_cols2, R2, ctx->res_ncat, ctx->res_nmag, C2, ncols2); if (r) return r; }
-	size_t s1 = ((size_t) std::max<int64_t>(R, 1) * 8 + 255) / 256 * 256, s2 = ((size_t) std::max<int64_t>(R2, 1) * 8 + 255) / 256 * 256;
+	size_t s1 = ((size_t) std::max<int64_t>(ctx->cols_cap_rows, 1) * 8 + 255) / 256 * 256, s2 = ((size_t) std::max<int64_t>(R2, 1) * 8 + 255) / 256 * 256;
 	for (int k = 0; k < ctx->ncols; k++)
 		LAUNCH(ctx, k_compact8, grid_for(R, 256), 256, (long long) R, (const int *) keep, (const long long *) pos,
 			(const unsigned long long *) ((char *) ctx->d_cols.p + s1 * k), (unsigned long long *) ((char *) ctx->d_cols2.p + s2 * k));
 	CU(cudaStreamSynchronize(st));
 	std::swap(ctx->d_cols, ctx->d_cols2);
+	ctx->cols_cap_rows = std::max<int64_t>(R2, 1);
 	ctx->cols = C2;
 	ctx->rp.C = C2;
 	ctx->nrows = R2;

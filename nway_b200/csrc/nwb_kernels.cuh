@@ -485,14 +485,21 @@ __global__ void k_cell_records(long long ncells, const int *__restrict__ cstart,
 
 // the scalars the host needs after K1, gathered for one small copy: [0] cell entries, [c] spill records of
 // catalogue c, [8] total rows (N == 2)
+struct BoundsKey { unsigned long long k[6]; };
+
 __global__ void k_collect_status(int ncat, const int *__restrict__ entries_total,
 	const unsigned long long *__restrict__ spill_count, const long long *__restrict__ total_rows,
-	long long *__restrict__ out)
+	const unsigned long long *__restrict__ bounds, BoundsKey expected, long long *__restrict__ out)
 {
 	int t = threadIdx.x;
 	if (t == 0) out[0] = *entries_total;
 	if (t >= 1 && t < ncat) out[t] = (long long) spill_count[t];
 	if (t == 8) out[8] = total_rows ? *total_rows : 0;
+	if (t == 9) {   // [9] != 0: the primaries' bounding box is not the one the (re-used) grid geometry was built for
+		long long bad = 0;
+		for (int k = 0; k < 6; k++) bad |= (long long) (bounds[k] != expected.k[k]);
+		out[9] = bad;
+	}
 }
 
 // overflow handling (only launched when some primary had more matches than slots)
@@ -580,7 +587,18 @@ struct RowParams {
 	PairStore S1;                    // N == 2: the matches of catalogue 1, unsorted, straight from k_pairs
 	int err1_const;                  // catalogue 1 carries one positional error for all sources:
 	double err1_value;               //   no per-row gather (one random 32-byte sector per row saved)
+	// speculative launch (no host sync between K1 and K2): the kernel runs only if the status words written by
+	// k_collect_status say that everything it depends on is valid and fits; the host checks the same words after
+	// its single sync and re-runs the non-speculative path otherwise
+	const long long *guard;
+	long long max_rows, entries_cap;
 };
+
+__device__ __forceinline__ bool guard_ok(const RowParams &R)
+{
+	if (!R.guard) return true;
+	return R.guard[9] == 0 && R.guard[1] == 0 && R.guard[8] <= R.max_rows && R.guard[0] <= R.entries_cap;
+}
 
 template <int NC>
 __device__ __forceinline__ long long mat_block_offset(const int *nl, int c, int d)
@@ -1005,6 +1023,7 @@ k_rows2(RowParams R)
 	const int lane = threadIdx.x & 31;
 	R2Smem &M = smem[threadIdx.x >> 5];
 	const ConstTables *__restrict__ T = R.T;
+	if (!guard_ok(R)) return;
 	R2Memo memo;
 	double m_sig0 = -1.0, w0 = 0.0, lw0 = 0.0;
 	const int nwarps = gridDim.x * R2_WARPS;

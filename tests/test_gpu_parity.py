@@ -134,6 +134,19 @@ def test_clustered_field_spills_and_big_groups(ncat):
 	assert np.bincount(got['A']).max() > 129
 
 
+def test_back_to_back_matches_reuse_and_invalidate_cached_state():
+	"""the context keeps the grid geometry and the output capacity of the previous match and launches the row kernel
+	speculatively; a second match with the same sizes but moved / denser catalogues must notice and redo"""
+	from oracle import nway_oracle as O
+	a = cases.uniform_patch(51, (300, 20000), (1.0, 0.3), 0.1)
+	b = cases.uniform_patch(52, (300, 20000), (1.0, 0.3), 0.1, ra0=150.3, dec0=0.2)     # same shapes, elsewhere
+	c = cases.uniform_patch(53, (300, 60000), (1.0, 0.3), 0.1, ra0=150.3, dec0=0.2)     # same primaries' box, 3x the rows
+	for tables in (a, a, b, c, a):
+		got = run_cuda(tables, 6.0, 0.9)
+		ref = O.nway_match(tables, 6.0, 0.9)
+		parity.assert_tables_match(ref, got, columns=[k for k in ref if not k.startswith('_')], context='back-to-back')
+
+
 def test_sharded_primary_ranges_concatenate_to_the_full_table():
 	"""groups never span shards, so per-shard tables concatenate to the single-device table."""
 	tables = cases.build_case('syn3')
