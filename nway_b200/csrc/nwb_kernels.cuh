@@ -254,8 +254,7 @@ __global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double
 // its primary (atomicAdd on the per-primary counter) and is written there directly -- no append buffer, no
 // scatter pass.
 constexpr int K1_WARPS = 8;
-constexpr int K1_ROUND = 2;                      // further cell entries taken per lane and round
-constexpr int K1_ICAP = 32 * (K1_ROUND + 1);     // work items: 31 left over + one full round
+constexpr int K1_ICAP = 64;                      // work items: 31 left over + 32 new (tested before the next 32)
 constexpr int K1_QCAP = 64;                      // candidates: 31 left over + 32 new (flushed before the next 32)
 constexpr int K1_SBANDS = 1024;                  // bands cached in shared memory (16 KB)
 
@@ -433,28 +432,26 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 			}
 		}
 		k1_enqueue(M, pass0, (int) i, p0, r, d, lane, qn, A);
-		// entries beyond the inline one
-		int maxc = __reduce_max_sync(NWB_FULL, ecnt);
-		for (int t0 = 1; t0 < maxc; t0 += K1_ROUND) {
-			int kmax = min(maxc - t0, K1_ROUND);
-			for (int k = 0; k < kmax; k++) {
-				bool has = t0 + k < ecnt;
-				unsigned m = __ballot_sync(NWB_FULL, has);
-				if (has) {
-					int q = nit + __popc(m & lt);
-					M.item_es[q] = make_int2(estart + t0 + k, (int) i);
-					M.item_rd[q] = make_double2(r, d);
-				}
-				nit += __popc(m);
+		// entries beyond the inline one: one work item each, pre-tested as soon as 32 are there
+		const int maxc = __reduce_max_sync(NWB_FULL, ecnt);
+		for (int k = 1; k < maxc; k++) {
+			const bool has = k < ecnt;
+			const unsigned m = __ballot_sync(NWB_FULL, has);
+			if (has) {
+				int q = nit + __popc(m & lt);
+				M.item_es[q] = make_int2(estart + k, (int) i);
+				M.item_rd[q] = make_double2(r, d);
 			}
-			__syncwarp();
-			while (nit >= 32) {
+			nit += __popc(m);
+			if (nit >= 32) {
+				__syncwarp();
 				nit -= 32;
 				k1_items(M, nit, 32, lane, qn, G, entries, A);
+				__syncwarp();
 			}
-			__syncwarp();
 		}
 	}
+	__syncwarp();
 	if (nit > 0) k1_items(M, 0, nit, lane, qn, G, entries, A);
 	__syncwarp();
 	while (qn > 0) {
@@ -1097,39 +1094,41 @@ k_rows2(RowParams R)
 			if (FUSE) M.v[k] = v;
 		}
 		if (!FUSE) continue;
-		// group normalisation (__init__.py:423-457) on the shared copy of the log-weights; every lane only ever
-		// touches its own k = lane + 32 j, except for v[0]
+		// Group normalisation (__init__.py:423-457) on the shared copy of the log-weights, with ONE exp10 per row:
+		//   t_k = 10^(v_k - m_rest) (k >= 1),  s_rest = sum t_k,  p_i = t_k / s_rest  [= 10^(v_k - bfsum1), since
+		//   bfsum1 = log10(s_rest) + m_rest],  s_all = s_rest * 10^(m_rest - m_all) + 10^(v_0 - m_all).
+		// Same numbers as the reference's formulas up to the rounding of the exponent arguments (~1e-14 relative,
+		// four orders below the parity tolerance).  Every lane only touches its own k = lane + 32 j, except v[0].
 		__syncwarp();
 		const double v0 = M.v[0];
-		double m_all = v0, m_rest = -INFINITY;
+		double m_rest = -INFINITY;
 		for (int k = lane + (lane == 0 ? 32 : 0); k < rows; k += 32) m_rest = fmax(m_rest, M.v[k]);
 		m_rest = warp_max(m_rest);
-		m_all = fmax(m_all, m_rest);
-		const bool same = m_all == m_rest;
-		double s_all = 0.0, s_rest = 0.0;
+		const double m_all = fmax(v0, m_rest);
+		double s_rest = 0.0;
 		for (int k = lane + (lane == 0 ? 32 : 0); k < rows; k += 32) {
-			double x = M.v[k];
-			double t = exp10(x - m_rest);
+			double t = exp10(M.v[k] - m_rest);
+			M.v[k] = t;
 			s_rest += t;
-			s_all += same ? t : exp10(x - m_all);
 		}
-		if (lane == 0) s_all += exp10(v0 - m_all);
-		s_all = warp_sum(s_all);
 		s_rest = warp_sum(s_rest);
-		const double bfsum = log10(s_all) + m_all;
-		const double bfsum1 = rows > 1 ? log10(s_rest) + m_rest : 0.0;
-		const double p_any = 1 - exp10(v0 - bfsum);
-		__syncwarp();
-		double best = 0.0;
-		for (int k = lane; k < rows; k += 32) {
-			double pi = k == 0 ? 0.0 : exp10(M.v[k] - bfsum1);
-			M.v[k] = pi;
-			best = fmax(best, pi);
+		double p_any = 0.0, inv_rest = 0.0;
+		if (rows > 1) {
+			// lane-uniform scalars: 10^(v0 - m_all) and 10^(m_rest - m_all); one of the two exponents is zero
+			const double e0 = exp10(fmin(v0, m_rest) - m_all);
+			const double s_all = v0 >= m_rest ? 1.0 + s_rest * e0 : s_rest + e0;
+			const double bfsum = log10(s_all) + m_all;
+			p_any = 1 - exp10(v0 - bfsum);
+			inv_rest = s_rest;
+		} else {
+			// lone no-counterpart row: bfsum = v0 exactly, p_any = 1 - 10^0 = 0
+			p_any = 1 - exp10(v0 - (log10(1.0) + v0));
 		}
-		best = warp_max(best);
+		__syncwarp();
+		const double best = rows > 1 ? 1.0 / inv_rest : 0.0;   // the largest t_k is exactly 1
 		for (int k = lane; k < rows; k += 32) {
 			long long row = rbase + k;
-			double pi = M.v[k];
+			double pi = k == 0 ? 0.0 : M.v[k] / inv_rest;
 			R.C.p_i[row] = pi;
 			R.C.p_any[row] = p_any;
 			R.C.flag[row] = (pi == best) ? 1 : (pi > R.ratio_secondary * best ? 2 : 0);
