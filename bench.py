@@ -51,39 +51,48 @@ def make_workload(world, scale=1.0, seed=20260301):
 	return [prim, sec], n0
 
 
-class ClockSampler(threading.Thread):
-	"""nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+class ClockSampler(object):
+	"""nvidia-smi clocks / throttle reasons while the measured loops run (B200_PROFILING.md): one background
+	`nvidia-smi -lms 20` process, started before the timed region and stopped after the e2e loop."""
 	FIELDS = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
 	def __init__(self, device):
-		threading.Thread.__init__(self, daemon=True)
 		self.device = device
-		self.samples = []
-		self.stop_flag = threading.Event()
+		self.proc = None
+		self.lines = []
 
-	def run(self):
-		while not self.stop_flag.is_set():
-			try:
-				out = subprocess.run(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.FIELDS,
-					'--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout.strip()
-				if out:
-					self.samples.append([x.strip() for x in out.split(',')])
-			except Exception:
-				pass
-			self.stop_flag.wait(0.1)
+	def start(self):
+		try:
+			self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.FIELDS,
+				'--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+		except Exception:
+			self.proc = None
+
+	def stop(self):
+		if self.proc is None:
+			return
+		try:
+			self.proc.terminate()
+			out, _ = self.proc.communicate(timeout=5)
+			self.lines = [l for l in out.splitlines() if l.strip()]
+		except Exception:
+			pass
 
 	def summary(self):
-		if not self.samples:
+		samples = [[x.strip() for x in l.split(',')] for l in self.lines]
+		samples = [s for s in samples if len(s) >= 7]
+		if not samples:
 			return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-		sm = sorted(float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit())
+		num = lambda v: float(v) if v.replace('.', '', 1).isdigit() else None
+		sm = sorted(x for x in (num(s[0]) for s in samples) if x is not None)
+		power = [x for x in (num(s[2]) for s in samples) if x is not None]
 		reasons = set()
-		for s in self.samples:
+		for s in samples:
 			for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[3:7]):
 				if v.lower().startswith('active'):
 					reasons.add(name)
-		return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.samples[0][1]) if self.samples[0][1].replace('.', '').isdigit() else None,
-			'power_w_max': max(float(s[2]) for s in self.samples if s[2].replace('.', '').isdigit()) if self.samples else None,
-			'reasons': sorted(reasons), 'samples': len(self.samples)}
+		return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': num(samples[0][1]), 'power_w_max': max(power) if power else None,
+			'reasons': sorted(reasons), 'samples': len(samples), 'window': 'timed loop + e2e loop, nvidia-smi -lms 20'}
 
 
 def hbm_peak():
@@ -193,14 +202,16 @@ def run_b200(args):
 	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 	barrier()
 	e0.record(stream)
-	for _ in range(args.steps):
+	nsampled = 0
+	for it in range(args.steps):
 		rows = step()
-		for k, v in ctx.timings().items():
-			acc[k] += v
+		if it % 8 == 7 or it == args.steps - 1:   # per-stage event times of that step (8 small API calls: not every step)
+			for k, v in ctx.timings().items():
+				acc[k] += v
+			nsampled += 1
 	e1.record(stream)
 	barrier()
 	ms_step = e0.elapsed_time(e1) / args.steps
-	sampler.stop_flag.set()
 	launches = ctx.launch_count() * args.steps
 	stats = ctx.stats()
 
@@ -255,6 +266,8 @@ def run_b200(args):
 	barrier()
 	e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
 	assert nr == rows
+	if rank == 0:
+		sampler.stop()
 	t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
 	if world > 1:
 		dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -263,6 +276,32 @@ def run_b200(args):
 	p_any = host_out[10][:rows].numpy()
 	assert np.isfinite(p_any).all() and (p_any >= -1e-12).all() and (p_any <= 1 + 1e-12).all()
 
+	# ---- (N > 1, informational) the padded NCCL all-gather of the whole table, outside the timed region -----------
+	allgather_ms = None
+	if world > 1:
+		from nway_b200 import parallel
+		ctx.set_primary_range(rank * n0, n0)
+		nr2 = ctx.match(fuse_final=True)
+		cols = {}
+		for k, sel in enumerate(colsel):
+			tns = torch.empty(nr2, dtype=torch.int64 if sel in (_lib.COL_IDX, _lib.COL_IDX + 1, _lib.COL_NCAT, _lib.COL_MATCH_FLAG) else torch.float64, device=dev)
+			ctx.fetch_device(sel, tns.data_ptr())
+			cols[k] = tns
+		ctx.sync()
+		cnts = parallel.exchange_counts(nr2, None, dev)
+		parallel.allgather_columns(cols, cnts)   # warm-up
+		barrier()
+		g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		g0.record()
+		full = parallel.allgather_columns(cols, cnts)
+		g1.record()
+		barrier()
+		tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+		dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+		allgather_ms = float(tg.item())
+		assert full[0].numel() == sum(cnts)
+		del full
+
 	if rank != 0:
 		if world > 1:
 			dist.destroy_process_group()
@@ -270,15 +309,15 @@ def run_b200(args):
 
 	# ---- roofline of the dominant kernel ---------------------------------------------------------------
 	peak, peak_kind = hbm_peak()
-	k_pairs_ms = acc['k_pairs'] / args.steps
-	k_rows_ms = acc['k_rows'] / args.steps
+	k_pairs_ms = acc['k_pairs'] / nsampled
+	k_rows_ms = acc['k_rows'] / nsampled
 	n1 = len(tables[1]['ra'])
 	pairs = stats['pairs_kept']
 	ncols = 12
 	bytes_pairs = n1 * 16 + pairs * 16                 # (ra, dec) of every secondary read once + pair records written
 	bytes_rows = rows * 8 * ncols + pairs * 12 + n0 * 24  # output columns + sorted lists read + primary (err, offsets)
 	if k_rows_ms >= k_pairs_ms:
-		kname, kms, kbytes = 'k_rows<2,fused>', k_rows_ms, bytes_rows
+		kname, kms, kbytes = 'k_rows2<fused>', k_rows_ms, bytes_rows
 	else:
 		kname, kms, kbytes = 'k_pairs', k_pairs_ms, bytes_pairs
 	achieved = kbytes / (kms * 1e-3) / 1e9
@@ -289,9 +328,9 @@ def run_b200(args):
 			'k_rows_ms': k_rows_ms, 'k_rows_GBs': bytes_rows / (k_rows_ms * 1e-3) / 1e9},
 		'pipeline': {'B_alg_bytes': b_alg, 'GBs': b_alg / (ms_step_max * 1e-3) / 1e9, 'frac': b_alg / (ms_step_max * 1e-3) / 1e9 / peak}}
 	ncu_traffic = os.path.join(ROOT, 'profiles', 'traffic.json')
-	if os.path.exists(ncu_traffic):
-		try:
-			roofline['traffic'] = json.load(open(ncu_traffic)).get(kname.split('<')[0])
+	if os.path.exists(ncu_traffic) and args.scale == 1.0:
+		try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel, from the committed ncu capture
+			roofline['traffic'] = json.load(open(ncu_traffic))['kernels'][kname.split('<')[0]]['dram_bytes_per_launch']
 		except Exception:
 			pass
 
@@ -310,7 +349,8 @@ def run_b200(args):
 			'rows_per_gpu': rows, 'pairs_per_gpu': pairs, 'radius_arcsec': RADIUS, 'prior_completeness': COMPLETENESS,
 			'parallelism': 'primary rows sharded, %d rank(s); secondaries replicated; exchange = all-gather of row counts' % world,
 			'l2': 'inputs (%.0f MB) and outputs (%.0f MB) per step exceed the 126 MB L2; no explicit flush' % (h2d / 1e6, d2h / 1e6),
-			'stage_ms': {k: acc[k] / args.steps for k in acc}, 'grid': stats},
+			'stage_ms': {k: acc[k] / nsampled for k in acc}, 'grid': stats,
+			'allgather_full_table_ms': allgather_ms},
 		'roofline': roofline,
 		'cpu_baseline': cpu,
 		'e2e': {'value': e2e_value, 'unit': 'associations/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': float(t.item())},
@@ -325,7 +365,7 @@ def run_b200(args):
 def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument('--gpus', type=int, default=1)
-	ap.add_argument('--steps', type=int, default=20)
+	ap.add_argument('--steps', type=int, default=200)
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C3 area (same densities); 1.0 = the named workload')

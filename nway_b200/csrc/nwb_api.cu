@@ -72,6 +72,8 @@ struct nwb_ctx {
 	Grid geom_G;
 	int64_t cols_cap_rows = 0;
 	int cols_cap_ncols = 0;
+	bool timing_dirty = false, tables_dirty = true;
+	int timing_ncat = 0;
 
 	// result
 	bool matched = false, finalized = false;
@@ -198,6 +200,7 @@ void default_tables(nwb_ctx *ctx)
 
 int upload_tables(nwb_ctx *ctx)
 {
+	if (!ctx->tables_dirty && ctx->d_tables.p) return NWB_OK;   // nothing changed since the last upload
 	ConstTables &T = ctx->tables;
 	int nmag = 0;
 	for (int c = 0; c < ctx->ncat; c++) {
@@ -224,6 +227,7 @@ int upload_tables(nwb_ctx *ctx)
 	ctx->res_nmag = nmag;
 	ENSURE(ctx->d_tables, sizeof(ConstTables));
 	CU(cudaMemcpyAsync(ctx->d_tables.p, &T, sizeof(ConstTables), cudaMemcpyHostToDevice, ctx->stream));
+	ctx->tables_dirty = false;
 	return NWB_OK;
 }
 
@@ -458,6 +462,7 @@ int nwb_set_catalogue(nwb_ctx *ctx, int c, int ncat, int64_t n, const double *ra
 		S.ra = d; S.dec = d + n; S.err = d + 2 * n; S.mags = m ? d + (2 + ecols) * n : nullptr;
 	}
 	S.set = true;
+	ctx->tables_dirty = true;
 	ctx->matched = ctx->finalized = false;
 	// one positional error for the whole catalogue?  (lets the row kernels skip a random gather per row)
 	S.err_const = false;
@@ -496,6 +501,7 @@ int nwb_set_params(nwb_ctx *ctx, double match_radius_arcsec, const double *compl
 	ctx->unrelated_mode = unrelated_mode;
 	ctx->params_set = true;
 	ctx->tables_set = false;
+	ctx->tables_dirty = true;
 	return NWB_OK;
 }
 
@@ -513,6 +519,7 @@ int nwb_set_tables(nwb_ctx *ctx, const double *norm /* ncat+1 */, double log10e,
 		ctx->tables.sub_log10prior[k] = sub_log10prior[k];
 	}
 	ctx->tables_set = true;
+	ctx->tables_dirty = true;
 	return NWB_OK;
 }
 
@@ -531,6 +538,7 @@ int nwb_set_maghist(nwb_ctx *ctx, int c, int k, int nbins, const double *edges, 
 		H.bias[i] = std::isnan(weight[i]) ? 1.0 : bias[i];
 	}
 	H.set = true;
+	ctx->tables_dirty = true;
 	return NWB_OK;
 }
 
@@ -601,7 +609,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	if (first + np > ctx->cat[0].n || np < 0) return fail(ctx, NWB_ERR_ARG, "primary range exceeds the catalogue");
 	ctx->np = np;
 	if (np == 0) { if (nrows) *nrows = 0; return fail(ctx, NWB_ERR_EMPTY, "No matches."); }
-	if (!ctx->tables_set) default_tables(ctx);
+	if (!ctx->tables_set && ctx->tables_dirty) default_tables(ctx);
 	{ int r = upload_tables(ctx); if (r) return r; }
 	const bool cli = ctx->unrelated_mode == NWB_UNRELATED_CLI && nc >= 3;
 	const bool fuse = fuse_final && !cli;
@@ -905,15 +913,8 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	if (fuse_final && !fuse) { int r = run_final(ctx); if (r) return r; }
 	CU(cudaEventRecord(ctx->ev[5], st));
 	CU(cudaStreamSynchronize(st));
-	for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&ctx->ms[k], ctx->ev[k], ctx->ev[k + 1]));
-	CU(cudaEventElapsedTime(&ctx->ms[NWB_T_TOTAL], ctx->ev[0], ctx->ev[5]));
-	ctx->ms[NWB_T_KPAIRS] = 0;
-	for (int c = 1; c < nc; c++) {
-		float t = 0;
-		if (ctx->cat[c].n > 0) CU(cudaEventElapsedTime(&t, ctx->kev[2 * c], ctx->kev[2 * c + 1]));
-		ctx->ms[NWB_T_KPAIRS] += t;
-	}
-	CU(cudaEventElapsedTime(&ctx->ms[NWB_T_KROWS], ctx->kev[0], ctx->kev[1]));
+	ctx->timing_dirty = true;   // elapsed times are read from the events on demand (nwb_timing)
+	ctx->timing_ncat = nc;
 	ctx->nrows = R;
 	ctx->matched = true;
 	ctx->finalized = fuse_final != 0;
@@ -930,6 +931,23 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 	return r;
 }
 
+static int refresh_timings(nwb_ctx *ctx)
+{
+	if (!ctx->timing_dirty) return NWB_OK;
+	CU(cudaSetDevice(ctx->device));
+	for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&ctx->ms[k], ctx->ev[k], ctx->ev[k + 1]));
+	CU(cudaEventElapsedTime(&ctx->ms[NWB_T_TOTAL], ctx->ev[0], ctx->ev[5]));
+	ctx->ms[NWB_T_KPAIRS] = 0;
+	for (int c = 1; c < ctx->timing_ncat; c++) {
+		float t = 0;
+		if (ctx->cat[c].n > 0) CU(cudaEventElapsedTime(&t, ctx->kev[2 * c], ctx->kev[2 * c + 1]));
+		ctx->ms[NWB_T_KPAIRS] += t;
+	}
+	CU(cudaEventElapsedTime(&ctx->ms[NWB_T_KROWS], ctx->kev[0], ctx->kev[1]));
+	ctx->timing_dirty = false;
+	return NWB_OK;
+}
+
 int nwb_finalize(nwb_ctx *ctx)
 {
 	if (!ctx) return NWB_ERR_ARG;
@@ -941,6 +959,7 @@ int nwb_finalize(nwb_ctx *ctx)
 	{ int r = run_final(ctx); if (r) return r; }
 	CU(cudaEventRecord(ctx->ev[7], ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	{ int r = refresh_timings(ctx); if (r) return r; }
 	CU(cudaEventElapsedTime(&ctx->ms[NWB_T_FINAL], ctx->ev[6], ctx->ev[7]));
 	ctx->finalized = true;
 	return NWB_OK;
@@ -1018,6 +1037,7 @@ int nwb_fetch_device(nwb_ctx *ctx, int column, void *dst_device)
 int nwb_timing(nwb_ctx *ctx, int stage, float *ms)
 {
 	if (!ctx || !ms || stage < 0 || stage >= NWB_T_COUNT) return NWB_ERR_ARG;
+	{ int r = refresh_timings(ctx); if (r) return r; }
 	*ms = ctx->ms[stage];
 	return NWB_OK;
 }
