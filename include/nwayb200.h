@@ -133,6 +133,9 @@ int nwb_fetch(nwb_ctx *ctx, int column, void *dst_host);
 int nwb_fetch_device(nwb_ctx *ctx, int column, void *dst_device);
 /* device address of a column (valid until the next nwb_match on this context) */
 int nwb_column_ptr(nwb_ctx *ctx, int column, void **dev_ptr);
+/* device address of the int64 row count of the last match (lets a multi-GPU caller all-gather the per-rank row
+ * counts with NCCL straight from device memory) */
+int nwb_nrows_device_ptr(nwb_ctx *ctx, void **dev_ptr);
 int nwb_sync(nwb_ctx *ctx);
 
 /* per-stage device time of the last nwb_match (+ nwb_finalize), and how many kernels it launched */

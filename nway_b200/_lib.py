@@ -37,6 +37,7 @@ EXPORTS = {
 	'nwb_finalize': (ctypes.c_int, [ctypes.c_void_p]),
 	'nwb_truncate': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_int64_p]),
 	'nwb_fetch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+	'nwb_nrows_device_ptr': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
 	'nwb_fetch_device': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
 	'nwb_column_ptr': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
 	'nwb_sync': (ctypes.c_int, [ctypes.c_void_p]),
@@ -171,6 +172,11 @@ class Context(object):
 	def fetch_device(self, column, dst_ptr):
 		self.check(self.lib.nwb_fetch_device(self.h, int(column), dst_ptr))
 
+	def nrows_device_ptr(self):
+		p = ctypes.c_void_p()
+		self.check(self.lib.nwb_nrows_device_ptr(self.h, ctypes.byref(p)))
+		return p.value
+
 	def column_ptr(self, column):
 		p = ctypes.c_void_p()
 		self.check(self.lib.nwb_column_ptr(self.h, int(column), ctypes.byref(p)))
@@ -196,6 +202,13 @@ class Context(object):
 		a = (ctypes.c_int64 * 4)()
 		self.check(self.lib.nwb_stats(self.h, a))
 		return dict(pairs_kept=a[1], grid_cells=a[2], cell_entries=a[3])
+
+
+class DeviceView(object):
+	"""wrap a raw device pointer for torch.as_tensor(..., device='cuda') via the CUDA array interface"""
+
+	def __init__(self, ptr, n, typestr='<i8'):
+		self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
 
 
 _contexts = {}

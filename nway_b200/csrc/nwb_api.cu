@@ -1021,6 +1021,14 @@ int nwb_fetch(nwb_ctx *ctx, int column, void *dst_host)
 	return NWB_OK;
 }
 
+int nwb_nrows_device_ptr(nwb_ctx *ctx, void **dev_ptr)
+{
+	if (!ctx || !dev_ptr) return NWB_ERR_ARG;
+	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	*dev_ptr = (void *) ((long long *) ctx->d_rowoff.p + ctx->np);   // row_off[np] == R
+	return NWB_OK;
+}
+
 int nwb_fetch_device(nwb_ctx *ctx, int column, void *dst_device)
 {
 	if (!ctx || !dst_device) return NWB_ERR_ARG;
