@@ -13,6 +13,10 @@
 
 using namespace nwb;
 
+#ifndef NWB_R2_SHARE
+#define NWB_R2_SHARE 1
+#endif
+
 namespace {
 
 std::string g_create_error;
@@ -768,8 +772,9 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			CU(cudaEventRecord(ctx->ev[3], st));
 			CU(cudaEventRecord(ctx->kev[0], st));
 			int grid2 = (int) std::min<int64_t>((np + R2_WARPS - 1) / R2_WARPS, 148 * 4);
-			if (fuse) LAUNCH(ctx, (k_rows2<true>), grid2, R2_WARPS * 32, ctx->rp);
-			else LAUNCH(ctx, (k_rows2<false>), grid2, R2_WARPS * 32, ctx->rp);
+			if (fuse && ctx->res_nmag == 0 && NWB_R2_SHARE) LAUNCH(ctx, (k_rows2<true, true>), grid2, R2_WARPS * 32, ctx->rp);
+			else if (fuse) LAUNCH(ctx, (k_rows2<true, false>), grid2, R2_WARPS * 32, ctx->rp);
+			else LAUNCH(ctx, (k_rows2<false, false>), grid2, R2_WARPS * 32, ctx->rp);
 			CU(cudaEventRecord(ctx->kev[1], st));
 			speculated = true;
 		}
@@ -893,8 +898,9 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			case 2: {
 				if (generic) { r = launch_rows<2>(ctx, rp, fuse, wgrid); break; }
 				int grid2 = (int) std::min<int64_t>((np + R2_WARPS - 1) / R2_WARPS, 148 * 4);
-				if (fuse) LAUNCH(ctx, (k_rows2<true>), grid2, R2_WARPS * 32, rp);
-				else LAUNCH(ctx, (k_rows2<false>), grid2, R2_WARPS * 32, rp);
+				if (fuse && ctx->res_nmag == 0 && NWB_R2_SHARE) LAUNCH(ctx, (k_rows2<true, true>), grid2, R2_WARPS * 32, rp);
+				else if (fuse) LAUNCH(ctx, (k_rows2<true, false>), grid2, R2_WARPS * 32, rp);
+				else LAUNCH(ctx, (k_rows2<false, false>), grid2, R2_WARPS * 32, rp);
 				break;
 			}
 			case 3: r = launch_rows<3>(ctx, rp, fuse, wgrid); break;

@@ -136,6 +136,39 @@ __device__ __forceinline__ double log_bf_ref(const ConstTables *__restrict__ T, 
 	return (T->norm[n] + slog + exponent) * T->log10e;
 }
 
+// 10^x for the row kernels.  Same scheme as the CUDA library routine (k = rint(x log2 10), r = x - k log10 2 in two
+// pieces, degree-13 polynomial of 10^r, scale by 2^k) but with the coefficients in constant memory, so a call is
+// ~30 instructions instead of ~70 (the library materialises every 64-bit coefficient with two moves).  Checked
+// against 80-bit powl on 4e7 arguments over [-320, 300]: max error 1.25 ulp (library: 1 ulp).
+__constant__ double c_exp10_poly[13] = {
+	2.3025850929940459, 2.6509490552391992, 2.034678592293476, 1.1712551489122669, 0.5393829291955814,
+	0.2069958486968681, 0.068089365074437067, 0.019597694626478524, 0.0050139288337754401,
+	0.0011544997789984348, 0.00024166672554424694, 4.6371516642572196e-05, 8.2134125354393867e-06};
+
+#ifndef NWB_OWN_EXP10
+#define NWB_OWN_EXP10 1
+#endif
+__device__ __forceinline__ double nwb_exp10(double x)
+{
+#if !NWB_OWN_EXP10
+	return exp10(x);
+#endif
+	if (!(x >= -323.4)) return x != x ? x : 0.0;
+	if (x > 308.3) return INFINITY;
+	const double kd = rint(x * 3.321928094887362348);
+	double r = fma(-kd, 0.3010299950838089, x);          // log10(2), 26 significant bits: k * hi is exact
+	r = fma(-kd, 5.8017229629986518e-10, r);
+	double p = c_exp10_poly[12];
+#pragma unroll
+	for (int n = 11; n >= 0; n--) p = fma(p, r, c_exp10_poly[n]);
+	p = fma(p, r, 1.0);
+	const int k = (int) kd;
+	if (k > -1000 && k < 1000)
+		return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+	const int k1 = k / 2, k2 = k - k1;   // subnormal / near-overflow results: scale in two steps
+	return p * __hiloint2double((1023 + k1) << 20, 0) * __hiloint2double((1023 + k2) << 20, 0);
+}
+
 // bayesdistance.py:26-32
 __device__ __forceinline__ double posterior_ref(double prior, double log10prior, double log_bf)
 {

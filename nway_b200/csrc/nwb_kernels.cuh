@@ -962,7 +962,9 @@ struct R2Memo {
 	double kw0 = -1.0, kw1 = -1.0, wsum = 0.0, lwsum = 0.0;   // key (w0, w1)
 };
 
-template <bool FUSE>
+// SHARE (fused, no magnitude priors): dist_post and p_single are not written here but by the normalisation, which
+// gets 10^(-v) from the exponential it evaluates anyway
+template <bool FUSE, bool SHARE>
 __device__ __forceinline__ void rows2_write(const RowParams &R, const ConstTables *__restrict__ T, long long row,
 	long long gp, long long sidx1, double sep, double w0, double lw0, R2Memo &memo, double &v_out)
 {
@@ -995,9 +997,13 @@ __device__ __forceinline__ void rows2_write(const RowParams &R, const ConstTable
 	}
 	unsigned smask = present ? 1u : 0u;
 	double prior = T->prior[smask], l10p = T->log10prior[smask];
-	double post = posterior_ref(prior, l10p, lbf);
 	R.C.lbf_u[row] = lbf;
 	R.C.lbf[row] = lbf;
+	if (SHARE) {
+		v_out = lbf + l10p;
+		return;
+	}
+	double post = 1. / (1 + (1 - prior) * nwb_exp10(-lbf - l10p));   // bayesdistance.py:32
 	R.C.dist_post[row] = post;
 	if (FUSE) {
 		double total = lbf;
@@ -1012,7 +1018,7 @@ __device__ __forceinline__ void rows2_write(const RowParams &R, const ConstTable
 	}
 }
 
-template <bool FUSE>
+template <bool FUSE, bool SHARE>
 __global__ void __launch_bounds__(R2_WARPS * 32, 4)
 k_rows2(RowParams R)
 {
@@ -1089,7 +1095,7 @@ k_rows2(RowParams R)
 		const int rows = n + 1;
 		for (int k = lane; k < rows; k += 32) {
 			double v = 0.0;
-			rows2_write<FUSE>(R, T, rbase + k, gp, k == 0 ? -1 : (long long) M.s[k - 1], k == 0 ? 0.0 : M.sep[k - 1],
+			rows2_write<FUSE, SHARE>(R, T, rbase + k, gp, k == 0 ? -1 : (long long) M.s[k - 1], k == 0 ? 0.0 : M.sep[k - 1],
 				w0, lw0, memo, v);
 			if (FUSE) M.v[k] = v;
 		}
@@ -1107,7 +1113,7 @@ k_rows2(RowParams R)
 		const double m_all = fmax(v0, m_rest);
 		double s_rest = 0.0;
 		for (int k = lane + (lane == 0 ? 32 : 0); k < rows; k += 32) {
-			double t = exp10(M.v[k] - m_rest);
+			double t = nwb_exp10(M.v[k] - m_rest);
 			M.v[k] = t;
 			s_rest += t;
 		}
@@ -1115,23 +1121,35 @@ k_rows2(RowParams R)
 		double p_any = 0.0, inv_rest = 0.0;
 		if (rows > 1) {
 			// lane-uniform scalars: 10^(v0 - m_all) and 10^(m_rest - m_all); one of the two exponents is zero
-			const double e0 = exp10(fmin(v0, m_rest) - m_all);
+			const double e0 = nwb_exp10(fmin(v0, m_rest) - m_all);
 			const double s_all = v0 >= m_rest ? 1.0 + s_rest * e0 : s_rest + e0;
 			const double bfsum = log10(s_all) + m_all;
-			p_any = 1 - exp10(v0 - bfsum);
+			p_any = 1 - nwb_exp10(v0 - bfsum);
 			inv_rest = s_rest;
 		} else {
 			// lone no-counterpart row: bfsum = v0 exactly, p_any = 1 - 10^0 = 0
-			p_any = 1 - exp10(v0 - (log10(1.0) + v0));
+			p_any = 1 - nwb_exp10(v0 - (log10(1.0) + v0));
 		}
 		__syncwarp();
 		const double best = rows > 1 ? 1.0 / inv_rest : 0.0;   // the largest t_k is exactly 1
+		// SHARE: dist_post = 1/(1 + (1 - prior) 10^(-v)) with 10^(-v_k) = 10^(-m_rest) / t_k: no second exponential
+		// per row.  Outside |m_rest| <= 250 (10^(-m_rest) near the ends of the double range) the direct form is used.
+		const bool direct = SHARE && !(fabs(m_rest) <= 250.0);
+		const double escale = (SHARE && rows > 1 && !direct) ? nwb_exp10(-m_rest) : 0.0;
+		const double omp = 1 - T->prior[1], l10p1 = T->log10prior[1];
 		for (int k = lane; k < rows; k += 32) {
 			long long row = rbase + k;
-			double pi = k == 0 ? 0.0 : M.v[k] / inv_rest;
+			double t = M.v[k];
+			double pi = k == 0 ? 0.0 : t / inv_rest;
 			R.C.p_i[row] = pi;
 			R.C.p_any[row] = p_any;
 			R.C.flag[row] = (pi == best) ? 1 : (pi > R.ratio_secondary * best ? 2 : 0);
+			if (SHARE) {
+				double post = 1.0;   // row 0: prior = 1, (1 - prior) * 10^0 = 0
+				if (k > 0) post = 1. / (1 + omp * (direct ? nwb_exp10(-R.C.lbf[row] - l10p1) : escale / t));
+				R.C.dist_post[row] = post;
+				R.C.p_single[row] = post;
+			}
 		}
 	} else {
 		// big group: rank against global memory, write rows, normalise through the p_i column
@@ -1140,12 +1158,12 @@ k_rows2(RowParams R)
 			int rank = 0;
 			for (int f = 0; f < n; f++) rank += store_get(R.S1, p, f).s < me.s;
 			double v = 0.0;
-			rows2_write<FUSE>(R, T, rbase + 1 + rank, gp, me.s, me.sep, w0, lw0, memo, v);
+			rows2_write<FUSE, false>(R, T, rbase + 1 + rank, gp, me.s, me.sep, w0, lw0, memo, v);
 			if (FUSE) R.C.p_i[rbase + 1 + rank] = v;
 		}
 		if (lane == 0) {
 			double v = 0.0;
-			rows2_write<FUSE>(R, T, rbase, gp, -1, 0.0, w0, lw0, memo, v);
+			rows2_write<FUSE, false>(R, T, rbase, gp, -1, 0.0, w0, lw0, memo, v);
 			if (FUSE) R.C.p_i[rbase] = v;
 		}
 		if (FUSE) {

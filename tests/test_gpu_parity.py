@@ -134,6 +134,17 @@ def test_clustered_field_spills_and_big_groups(ncat):
 	assert np.bincount(got['A']).max() > 129
 
 
+def test_extreme_bayes_factors():
+	"""positional errors far smaller than the separations: log BFs of -1e5, every exponential under/overflows; and
+	the opposite, errors far larger than the radius"""
+	from oracle import nway_oracle as O
+	for sig, seed in (((0.01, 0.005), 61), ((300.0, 200.0), 62), ((1e-4, 1.0), 63)):
+		tables = cases.uniform_patch(seed, (200, 20000), sig, 0.05)
+		got = run_cuda(tables, 8.0, 0.9)
+		ref = O.nway_match(tables, 8.0, 0.9)
+		report('extreme%s' % (sig,), parity.assert_tables_match(ref, got, columns=[k for k in ref if not k.startswith('_')], context='extreme %s' % (sig,)))
+
+
 def test_back_to_back_matches_reuse_and_invalidate_cached_state():
 	"""the context keeps the grid geometry and the output capacity of the previous match and launches the row kernel
 	speculatively; a second match with the same sizes but moved / denser catalogues must notice and redo"""
