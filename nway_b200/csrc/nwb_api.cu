@@ -771,7 +771,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			ctx->rp.entries_cap = (long long) ctx->entries_cap;
 			CU(cudaEventRecord(ctx->ev[3], st));
 			CU(cudaEventRecord(ctx->kev[0], st));
-			int grid2 = (int) std::min<int64_t>((np + R2_WARPS - 1) / R2_WARPS, 148 * 4);
+			int grid2 = (int) std::min<int64_t>((np + R2_WARPS - 1) / R2_WARPS, 148 * NWB_R2_GRID_PER_SM);
 			if (fuse && ctx->res_nmag == 0 && NWB_R2_SHARE) LAUNCH(ctx, (k_rows2<true, true>), grid2, R2_WARPS * 32, ctx->rp);
 			else if (fuse) LAUNCH(ctx, (k_rows2<true, false>), grid2, R2_WARPS * 32, ctx->rp);
 			else LAUNCH(ctx, (k_rows2<false, false>), grid2, R2_WARPS * 32, ctx->rp);
@@ -897,7 +897,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		switch (nc) {
 			case 2: {
 				if (generic) { r = launch_rows<2>(ctx, rp, fuse, wgrid); break; }
-				int grid2 = (int) std::min<int64_t>((np + R2_WARPS - 1) / R2_WARPS, 148 * 4);
+				int grid2 = (int) std::min<int64_t>((np + R2_WARPS - 1) / R2_WARPS, 148 * NWB_R2_GRID_PER_SM);
 				if (fuse && ctx->res_nmag == 0 && NWB_R2_SHARE) LAUNCH(ctx, (k_rows2<true, true>), grid2, R2_WARPS * 32, rp);
 				else if (fuse) LAUNCH(ctx, (k_rows2<true, false>), grid2, R2_WARPS * 32, rp);
 				else LAUNCH(ctx, (k_rows2<false, false>), grid2, R2_WARPS * 32, rp);

@@ -943,6 +943,12 @@ constexpr int R2_WARPS = 8;
 constexpr int R2_CAP = 128;   // matches per primary handled in shared memory; larger groups take k_rows2_big
 
 constexpr int R2_NB = 128;    // buckets of the in-group sort
+#ifndef NWB_R2_MINBLOCKS
+#define NWB_R2_MINBLOCKS 4
+#endif
+#ifndef NWB_R2_GRID_PER_SM
+#define NWB_R2_GRID_PER_SM 4
+#endif
 
 struct __align__(16) R2Smem {
 	int s_in[R2_CAP];
@@ -959,7 +965,7 @@ struct __align__(16) R2Smem {
 // recomputed row after row.  Same expressions, same bits -- just not evaluated twice for equal inputs.
 struct R2Memo {
 	double s1 = -1.0, w1 = 0.0, lw1 = 0.0;      // key s1
-	double kw0 = -1.0, kw1 = -1.0, wsum = 0.0, lwsum = 0.0;   // key (w0, w1)
+	double kw0 = -1.0, kw1 = -1.0, wsum = 0.0, lwsum = 0.0, rwsum = 0.0;   // key (w0, w1); rwsum = RN(1 / wsum)
 };
 
 // SHARE (fused, no magnitude priors): dist_post and p_single are not written here but by the normalisation, which
@@ -988,11 +994,23 @@ __device__ __forceinline__ void rows2_write(const RowParams &R, const ConstTable
 			memo.kw0 = w0; memo.kw1 = w1;
 			memo.wsum = w0 + w1;
 			memo.lwsum = log(memo.wsum);
+			memo.rwsum = 1.0 / memo.wsum;
 		}
 		double wsum = memo.wsum;
 		double slog = lw0 + memo.lw1 - memo.lwsum;
 		double q = w0 * w1 * (sep * sep);
-		double exponent = -q / 2 / wsum;
+		// -q / 2 / wsum: the halving is exact; the quotient is the correctly rounded one (Markstein: with y = RN(1/b),
+		// q0 = RN(a y), r = a - b q0 exactly by FMA, RN(q0 + r y) = RN(a / b)) as long as nothing under/overflows --
+		// anything else (q huge or wsum denormal-ish) takes the division
+		double hq = -q / 2;
+		double exponent;
+		if (fabs(hq) < 1e280 && fabs(hq) > 1e-280 && wsum > 1e-280 && wsum < 1e280) {
+			double q0 = hq * memo.rwsum;
+			double rr = fma(-q0, wsum, hq);
+			exponent = fma(rr, memo.rwsum, q0);
+		} else {
+			exponent = hq / wsum;
+		}
 		lbf = (T->norm[2] + slog + exponent) * T->log10e;
 	}
 	unsigned smask = present ? 1u : 0u;
@@ -1019,7 +1037,7 @@ __device__ __forceinline__ void rows2_write(const RowParams &R, const ConstTable
 }
 
 template <bool FUSE, bool SHARE>
-__global__ void __launch_bounds__(R2_WARPS * 32, 4)
+__global__ void __launch_bounds__(R2_WARPS * 32, NWB_R2_MINBLOCKS)
 k_rows2(RowParams R)
 {
 	__shared__ R2Smem smem[R2_WARPS];
@@ -1118,35 +1136,41 @@ k_rows2(RowParams R)
 			s_rest += t;
 		}
 		s_rest = warp_sum(s_rest);
-		double p_any = 0.0, inv_rest = 0.0;
+		double p_any = 0.0, rinv = 0.0;
 		if (rows > 1) {
-			// lane-uniform scalars: 10^(v0 - m_all) and 10^(m_rest - m_all); one of the two exponents is zero
+			// p_any = 1 - 10^(v0 - bfsum), bfsum = log10(s_all) + m_all, s_all = sum 10^(v_k - m_all)   (__init__.py:428-439)
+			//       = 1 - 10^(v0 - m_all) / s_all = [sum over k >= 1 of 10^(v_k - m_all)] / s_all
+			// -- the same number without the logarithm, the second exponential and the cancellation of "1 -"; it differs
+			// from the reference's rounding of that expression by the reference's own ~1e-14 (parity metric).
+			// One of the two exponents below is zero: e0 = 10^(-|v0 - m_rest|).
 			const double e0 = nwb_exp10(fmin(v0, m_rest) - m_all);
-			const double s_all = v0 >= m_rest ? 1.0 + s_rest * e0 : s_rest + e0;
-			const double bfsum = log10(s_all) + m_all;
-			p_any = 1 - nwb_exp10(v0 - bfsum);
-			inv_rest = s_rest;
-		} else {
-			// lone no-counterpart row: bfsum = v0 exactly, p_any = 1 - 10^0 = 0
-			p_any = 1 - nwb_exp10(v0 - (log10(1.0) + v0));
+			const double rest = v0 >= m_rest ? s_rest * e0 : s_rest;      // sum over k >= 1, scaled by 10^(-m_all)
+			const double s_all = v0 >= m_rest ? 1.0 + rest : rest + e0;
+			p_any = rest / s_all;
+			rinv = 1.0 / s_rest;
 		}
+		// lone no-counterpart row: bfsum = v0 exactly, p_any = 1 - 10^0 = 0
 		__syncwarp();
-		const double best = rows > 1 ? 1.0 / inv_rest : 0.0;   // the largest t_k is exactly 1
-		// SHARE: dist_post = 1/(1 + (1 - prior) 10^(-v)) with 10^(-v_k) = 10^(-m_rest) / t_k: no second exponential
-		// per row.  Outside |m_rest| <= 250 (10^(-m_rest) near the ends of the double range) the direct form is used.
+		const double best = rinv;   // the largest t_k is exactly 1, so max p_i = 1 * rinv (0 for a lone row)
+		// SHARE: dist_post = 1/(1 + (1 - prior) 10^(-v)) with 10^(-v_k) = 10^(-m_rest) / t_k, i.e.
+		// t_k / (t_k + (1 - prior) 10^(-m_rest)): no second exponential per row.  Outside |m_rest| <= 250 (10^(-m_rest)
+		// near the ends of the double range) and for t_k = 0 the direct form is used.
 		const bool direct = SHARE && !(fabs(m_rest) <= 250.0);
-		const double escale = (SHARE && rows > 1 && !direct) ? nwb_exp10(-m_rest) : 0.0;
+		const double oscale = (SHARE && rows > 1 && !direct) ? (1 - T->prior[1]) * nwb_exp10(-m_rest) : 0.0;
 		const double omp = 1 - T->prior[1], l10p1 = T->log10prior[1];
 		for (int k = lane; k < rows; k += 32) {
 			long long row = rbase + k;
 			double t = M.v[k];
-			double pi = k == 0 ? 0.0 : t / inv_rest;
+			double pi = k == 0 ? 0.0 : t * rinv;
 			R.C.p_i[row] = pi;
 			R.C.p_any[row] = p_any;
 			R.C.flag[row] = (pi == best) ? 1 : (pi > R.ratio_secondary * best ? 2 : 0);
 			if (SHARE) {
 				double post = 1.0;   // row 0: prior = 1, (1 - prior) * 10^0 = 0
-				if (k > 0) post = 1. / (1 + omp * (direct ? nwb_exp10(-R.C.lbf[row] - l10p1) : escale / t));
+				if (k > 0) {
+					if (direct || !(t > 1e-290)) post = 1. / (1 + omp * nwb_exp10(-R.C.lbf[row] - l10p1));
+					else post = t / (t + oscale);
+				}
 				R.C.dist_post[row] = post;
 				R.C.p_single[row] = post;
 			}
