@@ -79,6 +79,21 @@ int nwb_set_catalogue(nwb_ctx *ctx, int c, int ncat, int64_t n, const double *ra
 int nwb_set_params(nwb_ctx *ctx, double match_radius_arcsec, const double *completeness,
 	double prob_ratio_secondary, int unrelated_mode);
 
+/* --prefilter-pair of nway.py (fastskymatch.crossproduct's pairwise_errs, fastskymatch.py:184-208), as intended: an
+ * association that contains a source of catalogue cat_a[k] AND one of cat_b[k] is only formed if the two are closer
+ * than radius_arcsec[k]; associations lacking either are unaffected.  The reference's code as written drops every
+ * such association regardless of distance (its mask assignment writes to a temporary) -- that
+ * behaviour is radius 0 here.  npairs = 0 clears the list.  Call after the catalogues are set. */
+int nwb_set_prefilter(nwb_ctx *ctx, int npairs, const int *cat_a, const int *cat_b, const double *radius_arcsec);
+
+/* Compatibility switches of the reference's command-line program (nway.py); default 0 = the fp64 API behaviour.
+ * NWB_COMPAT_SEP_F32: nway.py stores every separation (and, for elliptical errors, every tangent-plane offset) in a
+ * float32 FITS column and scores what it reads back (fastskymatch.py:328-331 -> nway.py:269,302-305):
+ * round them to float32 after the (fp64) radius filter and before the Bayes factor.  The Separation columns then
+ * hold float32-representable values. */
+enum { NWB_COMPAT_SEP_F32 = 1 };
+int nwb_set_compat(nwb_ctx *ctx, int flags);
+
 /* Optional: the scalar tables the kernels consume, computed by the caller with the reference's own numpy
  * expressions (so they are bit-identical to what nwaylib computes on that host).  If not called, the library
  * derives the same tables itself in C double arithmetic.  norm: ncat+1 values indexed by the number of present
@@ -151,6 +166,13 @@ int nwb_dist(nwb_ctx *ctx, int64_t n, const double *ra1, const double *dec1, con
 int nwb_log_bf(nwb_ctx *ctx, int64_t n, int ncat, const double *sep /* ncat*ncat blocks of n, only i<j read */,
 	const double *err /* ncat blocks of n */, double *out);     /* bayesdistance.py:64-86 */
 int nwb_posterior(nwb_ctx *ctx, int64_t n, const double *prior, const double *log_bf, double *out); /* :26-32 */
+int nwb_log_bf_elliptical(nwb_ctx *ctx, int64_t n, int ncat, const double *sep_ra, const double *sep_dec /* like sep */,
+	const double *err /* ncat blocks of (sigma_x | sigma_y | rho), each n */, double *out);   /* bayesdistance.py:207-240 */
+
+/* Tangent-plane offsets (arcsec) between the members a < b of every row of the last result, R values each, NaN where
+ * either is absent: the Separation_<b>_<a>_ra / _dec columns match_multiple adds for non-circular errors
+ * (fastskymatch.py:299-331, dist3d :50-74). */
+int nwb_row_offsets(nwb_ctx *ctx, int a, int b, double *dra_host, double *ddec_host);
 
 #ifdef __cplusplus
 }

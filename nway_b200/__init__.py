@@ -154,7 +154,8 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	min_prob=0., consider_unrelated_associations=True,
 	store_mag_hists=True,
 	logger=default_logger,
-	unrelated_mode='api', device=None, primary_range=None, as_frame=True, keep_on_device=False, allow_empty=False):
+	unrelated_mode='api', device=None, primary_range=None, as_frame=True, keep_on_device=False, allow_empty=False,
+	cli_compat=False, pairwise_errs=()):
 	"""Same contract as nwaylib.nway_match (nwaylib/__init__.py:31-83); see there for the arguments.
 
 	match_tables: list of dicts with name, ra, dec (deg), error (arcsec), area (deg^2), mags, magnames, maghists
@@ -171,6 +172,13 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	  as_frame        False returns an OrderedDict of numpy columns instead of a pandas.DataFrame
 	  keep_on_device  leave the table in device memory and return {'nrows', 'selectors'} (used by nway_b200.parallel)
 	  allow_empty     do not raise EmptyResultException for an empty shard
+	  pairwise_errs   [(catalogue index a, catalogue index b, radius in arcsec), ...]: nway.py's --prefilter-pair as
+	                  intended -- associations containing sources of both a and b are formed only if those two are
+	                  closer than the radius (fastskymatch.py:184-208; the reference's code as written drops all of
+	                  them, SURVEY.md Q8, which is radius 0 here)
+	  cli_compat      the arithmetic quirks of the command-line program nway.py on top of unrelated_mode='cli':
+	                  separations (elliptical: offsets) pass through float32 before they are scored
+	                  and automatic histograms take the weights of the selected rows (nway.py:471)
 
 	Returns one row per association, ordered by primary index, then by the secondary indices with -1 first.
 	The primary index is an ordinary column (pandas < 2.2 shape of the reference's frame)."""
@@ -208,6 +216,8 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	tab = _scalar_tables(match_tables, prior_completeness, logger)
 	mode = _lib.UNRELATED_CLI if (unrelated_mode == 'cli' and consider_unrelated_associations) else _lib.UNRELATED_API
 	ctx.set_params(match_radius, tab['pc'], prob_ratio_secondary, mode)
+	ctx.set_compat(_lib.COMPAT_SEP_F32 if cli_compat else 0)
+	ctx.set_prefilter(list(pairwise_errs))
 	ctx.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
 
 	def install_hist(c, k, bins, hist_sel, hist_all):
@@ -242,7 +252,7 @@ def nway_match(match_tables, match_radius, prior_completeness,
 			res = ctx.fetch(_lib.COL_IDX + c, nrows, numpy.int64)
 			ctx.sync()
 			bins, hist_sel, hist_all, nsel, npossible, nothers = magnitudeweights.auto_histogram(res, magvals, sepmax, dist_post,
-				mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue)
+				mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue, cli=cli_compat)
 			logger.log('magnitude histogram of column "%s": %d secure matches, %d insecure matches and %d secure non-matches of %d total entries (%d valid)' % (
 				col, nsel, npossible, nothers, len(magvals), numpy.isfinite(magvals).sum()))
 			if store_mag_hists:

@@ -16,6 +16,7 @@ COL_IDX, COL_SEP, COL_BIAS = 0, 100, 200
 COL_SEPMAX, COL_NCAT, COL_LOGBF_UNCORR, COL_LOGBF, COL_DIST_POST, COL_P_SINGLE, COL_MATCH_FLAG, COL_P_ANY, COL_P_I = range(300, 309)
 ERR_CIRCULAR, ERR_ELLIPSE = 1, 3
 UNRELATED_API, UNRELATED_CLI = 0, 1
+COMPAT_SEP_F32 = 1
 T_GRID, T_PAIRS, T_LISTS, T_ROWS, T_FINAL, T_TOTAL, T_KPAIRS, T_KROWS = range(8)
 STAGE_NAMES = ['grid', 'pairs', 'lists', 'rows', 'final', 'total', 'k_pairs', 'k_rows']
 NWB_ERR_EMPTY = -3
@@ -30,6 +31,8 @@ EXPORTS = {
 	'nwb_set_catalogue': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
 		ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int]),
 	'nwb_set_params': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_double_p, ctypes.c_double, ctypes.c_int]),
+	'nwb_set_compat': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+	'nwb_set_prefilter': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), c_double_p]),
 	'nwb_set_tables': (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_double, c_double_p, c_double_p, c_double_p]),
 	'nwb_set_maghist': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
 	'nwb_set_primary_range': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]),
@@ -47,6 +50,8 @@ EXPORTS = {
 	'nwb_dist': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
 	'nwb_log_bf': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
 	'nwb_posterior': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p]),
+	'nwb_log_bf_elliptical': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
+	'nwb_row_offsets': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p]),
 }
 
 _lib = None
@@ -133,6 +138,24 @@ class Context(object):
 	def set_params(self, radius, completeness, ratio_secondary=0.5, unrelated_mode=UNRELATED_API):
 		pc = f64(completeness)
 		self.check(self.lib.nwb_set_params(self.h, float(radius), dptr(pc), float(ratio_secondary), int(unrelated_mode)))
+
+	def row_offsets(self, a, b, nrows):
+		"""(dra, ddec) in arcsec between the members a < b of every row of the last result (NaN where absent)"""
+		dra, ddec = numpy.empty(nrows), numpy.empty(nrows)
+		if nrows:
+			self.check(self.lib.nwb_row_offsets(self.h, int(a), int(b), dptr(dra), dptr(ddec)))
+		return dra, ddec
+
+	def set_prefilter(self, pairwise_errs):
+		"""[(catalogue a, catalogue b, radius in arcsec), ...]; empty clears"""
+		n = len(pairwise_errs)
+		a = (ctypes.c_int * max(n, 1))(*[int(x[0]) for x in pairwise_errs])
+		b = (ctypes.c_int * max(n, 1))(*[int(x[1]) for x in pairwise_errs])
+		r = (ctypes.c_double * max(n, 1))(*[float(x[2]) for x in pairwise_errs])
+		self.check(self.lib.nwb_set_prefilter(self.h, n, a, b, r))
+
+	def set_compat(self, flags):
+		self.check(self.lib.nwb_set_compat(self.h, int(flags)))
 
 	def set_tables(self, norm, log10e, prior, log10prior, sub_log10prior):
 		a, b, c, d = f64(norm), f64(prior), f64(log10prior), f64(sub_log10prior)

@@ -56,6 +56,9 @@ struct nwb_ctx {
 	double radius = 0, ratio_secondary = 0.5;
 	double pc[MAXC];
 	int unrelated_mode = NWB_UNRELATED_API;
+	int compat = 0;
+	double prefilter[MAXP];          // per catalogue pair, arcsec; +inf = none
+	bool prefilter_on = false;
 	ConstTables tables;   // host copy
 	int64_t first = 0, count = -1;
 
@@ -396,6 +399,7 @@ int nwb_create(int device, nwb_ctx **out)
 	for (auto &ev : ctx->kev) cudaEventCreate(&ev);
 	for (auto &m : ctx->ms) m = 0;
 	for (int c = 0; c < MAXC; c++) ctx->pc[c] = 1.0;
+	for (int k = 0; k < MAXP; k++) ctx->prefilter[k] = INFINITY;
 	memset(&ctx->tables, 0, sizeof(ctx->tables));
 	*out = ctx;
 	return NWB_OK;
@@ -509,6 +513,32 @@ int nwb_set_params(nwb_ctx *ctx, double match_radius_arcsec, const double *compl
 	return NWB_OK;
 }
 
+int nwb_set_prefilter(nwb_ctx *ctx, int npairs, const int *cat_a, const int *cat_b, const double *radius_arcsec)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	for (int k = 0; k < MAXP; k++) ctx->prefilter[k] = INFINITY;
+	ctx->prefilter_on = false;
+	if (npairs < 0 || (npairs > 0 && (!cat_a || !cat_b || !radius_arcsec))) return fail(ctx, NWB_ERR_ARG, "bad prefilter list");
+	if (npairs > 0 && ctx->ncat < 2) return fail(ctx, NWB_ERR_ARG, "set the catalogues before the prefilter");
+	for (int k = 0; k < npairs; k++) {
+		int a = std::min(cat_a[k], cat_b[k]), b = std::max(cat_a[k], cat_b[k]);
+		if (a < 0 || b >= ctx->ncat || a == b) return fail(ctx, NWB_ERR_ARG, "prefilter: bad catalogue pair");
+		if (!(radius_arcsec[k] >= 0)) return fail(ctx, NWB_ERR_ARG, "prefilter: radius must be >= 0");
+		double &slot = ctx->prefilter[pair_index(a, b, ctx->ncat)];
+		slot = std::min(slot, radius_arcsec[k]);
+		ctx->prefilter_on = true;
+	}
+	return NWB_OK;
+}
+
+int nwb_set_compat(nwb_ctx *ctx, int flags)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (flags & ~NWB_COMPAT_SEP_F32) return fail(ctx, NWB_ERR_ARG, "unknown compatibility flag");
+	ctx->compat = flags;
+	return NWB_OK;
+}
+
 // optional: scalar tables computed by the caller with the reference's own numpy expressions
 int nwb_set_tables(nwb_ctx *ctx, const double *norm /* ncat+1 */, double log10e, const double *prior,
 	const double *log10prior, const double *sub_log10prior /* each 2^(ncat-1) */)
@@ -583,6 +613,8 @@ static int fill_row_params(nwb_ctx *ctx, const PairStore *stores, int64_t first,
 		rp.err[c] = ctx->cat[c].err; rp.n[c] = ctx->cat[c].n; rp.ra[c] = ctx->cat[c].ra; rp.dec[c] = ctx->cat[c].dec;
 	}
 	rp.ell = ell ? 1 : 0;
+	rp.sep_f32 = (ctx->compat & NWB_COMPAT_SEP_F32) ? 1 : 0;
+	for (int k = 0; k < MAXP; k++) rp.pair_radius[k] = ctx->prefilter_on ? std::min(ctx->radius, ctx->prefilter[k]) : ctx->radius;
 	rp.T = (const ConstTables *) ctx->d_tables.p;
 	rp.S1 = stores[1];
 	rp.err1_const = ctx->cat[1].err_const ? 1 : 0;
@@ -741,7 +773,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			int grid = (int) std::min<int64_t>((n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), (int64_t) ctx->num_sms * ctx->k1_blocks_per_sm);
 			CU(cudaEventRecord(ctx->kev[2 * c], st));
 			K1Args ka;
-			ka.P = P; ka.radius = ctx->radius; ka.base = d_base + base_off[c]; ka.C = Cs[c]; ka.cnt = d_cnt[c];
+			ka.P = P; ka.radius = ctx->prefilter_on ? std::min(ctx->radius, ctx->prefilter[pair_index(0, c, nc)]) : ctx->radius; ka.base = d_base + base_off[c]; ka.C = Cs[c]; ka.cnt = d_cnt[c];
 			ka.spill = d_spill + (size_t) ctx->spill_cap * (c - 1); ka.spill_cap = (unsigned long long) ctx->spill_cap;
 			ka.spill_count = d_spillcount + c;
 			LAUNCH(ctx, k_pairs, grid, K1_WARPS * 32, (long long) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_cstart,
@@ -1122,6 +1154,48 @@ int nwb_log_bf(nwb_ctx *ctx, int64_t n, int ncat, const double *sep, const doubl
 	CU(cudaMemcpyAsync(d_T, &T, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
 	LAUNCH(ctx, k_log_bf, grid_for(n, 256), 256, (long long) n, ncat, d_in[0], d_in[1], (const ConstTables *) d_T, d_out);
 	CU(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return NWB_OK;
+}
+
+int nwb_log_bf_elliptical(nwb_ctx *ctx, int64_t n, int ncat, const double *sep_ra, const double *sep_dec,
+	const double *err, double *out)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (ncat < 1 || ncat > MAXC) return fail(ctx, NWB_ERR_ARG, "ncat out of range");
+	if (n <= 0) return NWB_OK;
+	CU(cudaSetDevice(ctx->device));
+	ConstTables T;
+	memset(&T, 0, sizeof(T));
+	const double log_arcsec2rad = std::log(3600 * 180 / M_PI);
+	for (int k = 0; k <= MAXC; k++) T.norm[k] = (k - 1) * std::log(2.0) + 2 * (k - 1) * log_arcsec2rad;
+	T.log10e = std::log10(M_E);
+	const double *in[3] = {sep_ra, sep_dec, err};
+	int64_t len[3] = {(int64_t) ncat * ncat * n, (int64_t) ncat * ncat * n, (int64_t) ncat * 3 * n};
+	double *d_in[3], *d_out;
+	{ int r = elementwise_io(ctx, n + (int64_t) (sizeof(ConstTables) / 8 + 1), 3, in, len, d_in, &d_out); if (r) return r; }
+	ConstTables *d_T = (ConstTables *) (d_out + n);
+	CU(cudaMemcpyAsync(d_T, &T, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	LAUNCH(ctx, k_log_bf_ell, grid_for(n, 256), 256, (long long) n, ncat, d_in[0], d_in[1], d_in[2], (const ConstTables *) d_T, d_out);
+	CU(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return NWB_OK;
+}
+
+int nwb_row_offsets(nwb_ctx *ctx, int a, int b, double *dra_host, double *ddec_host)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	if (a < 0 || b <= a || b >= ctx->res_ncat) return fail(ctx, NWB_ERR_ARG, "need catalogue indices a < b");
+	const int64_t R = ctx->nrows;
+	if (R <= 0) return NWB_OK;
+	CU(cudaSetDevice(ctx->device));
+	ENSURE(ctx->d_misc, (size_t) (2 * R + 8) * sizeof(double));
+	double *d = (double *) ctx->d_misc.p;
+	LAUNCH(ctx, k_row_offsets, grid_for(R, 256), 256, (long long) R, (const long long *) ctx->cols.idx[a],
+		(const long long *) ctx->cols.idx[b], ctx->cat[a].ra, ctx->cat[a].dec, ctx->cat[b].ra, ctx->cat[b].dec, d, d + R);
+	CU(cudaMemcpyAsync(dra_host, d, R * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(ddec_host, d + R, R * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	return NWB_OK;
 }

@@ -97,9 +97,11 @@ struct ConstTables {
 // log10 Bayes factor of the present catalogues (bayesdistance.py:64-86).
 // present: bit c set if catalogue c takes part (bit 0 = primary for a full row; sub-associations of the CLI
 // correction pass a mask without bit 0).  sig[c]: sigma in arcsec.  sep[pair_index(a,b)]: arcsec.
+// sq32: the separations are float32 values and are squared in float32, as numpy does for the command-line program's
+// 'E' columns (`p[i][j]**2`, bayesdistance.py:83, on what nway.py:302-305 reads back); the products stay fp64.
 template <int NC>
 __device__ __forceinline__ double log_bf_ref(const ConstTables *__restrict__ T, int ncat_rt, unsigned present,
-	const double *sig, const double *sep)
+	const double *sig, const double *sep, bool sq32 = false)
 {
 	const int ncat = NC > 0 ? NC : ncat_rt;
 	int n = __popc(present);
@@ -127,7 +129,8 @@ __device__ __forceinline__ double log_bf_ref(const ConstTables *__restrict__ T, 
 		for (int b = a + 1; b < (NC > 0 ? NC : MAXC); b++) {
 			if (b < ncat && (present >> a & 1u) && (present >> b & 1u)) {
 				double p = sep[pair_index(a, b, ncat)];
-				double term = w[a] * w[b] * (p * p);
+				double p2 = sq32 ? (double) __fmul_rn((float) p, (float) p) : p * p;
+				double term = w[a] * w[b] * p2;
 				if (qfirst) { q = term; qfirst = false; } else q = q + term;   // 0 + term == term
 			}
 		}

@@ -571,8 +571,10 @@ struct RowParams {
 	int ncat, nmag, np;
 	long long first;                 // global index of local primary 0
 	double radius, ratio_secondary;
+	double pair_radius[MAXP];        // per catalogue pair: min(radius, --prefilter-pair radius), arcsec (fastskymatch.py:184-208)
 	const double *err[MAXC];         // sigma columns (circular); elliptical: sigma_x | sigma_y | rho, each n[c] long
 	int ell;                         // elliptical mode (nway.py:346-354): every catalogue carries a triple
+	int sep_f32;                     // nway.py compatibility: separations / offsets pass through float32
 	long long n[MAXC];               // catalogue sizes (stride of the error triple)
 	const double *ra[MAXC], *dec[MAXC];
 	const ConstTables *T;
@@ -675,7 +677,7 @@ __global__ void k_count_rows(RowParams R, long long *__restrict__ rows)
 				for (int b = a + 1; b < NC; b++) {
 					if (dg[a] > 0 && dg[b] > 0) {
 						double s = mat[bo + (long long) (dg[a] - 1) * nl[b] + (dg[b] - 1)];
-						ok = ok && (s < R.radius);
+						ok = ok && (s < R.pair_radius[pair_index(a, b, NC)]);
 					}
 					bo += (long long) nl[a] * nl[b];
 				}
@@ -726,6 +728,19 @@ __device__ __forceinline__ double dir_precision(double vx, double vy, double sx,
 	return l1 * vx + l2 * vy;
 }
 
+// separation of one pair rescaled by the ratio of circular to directional error (bayesdistance.py:224-238)
+__device__ __forceinline__ double ell_rescaled_sep(double vx, double vy, double sxa, double sya, double rhoa,
+	double sxb, double syb, double rhob, double siga, double sigb)
+{
+	double d = sqrt(vx * vx + vy * vy);
+	double ux = d == 0 ? 0.7071067811865476 : vx / (d + 1e-300);
+	double uy = d == 0 ? 0.7071067811865476 : vy / (d + 1e-300);
+	double wa = dir_precision(ux, uy, sxa, sya, rhoa);
+	double wb = dir_precision(ux, uy, sxb, syb, rhob);
+	double ratio = (siga * siga + sigb * sigb) / (1 / wa + 1 / wb);
+	return d * (1.0 / sqrt(ratio));
+}
+
 // For the catalogues in `present` (bit c) with sources sidx[c]: the circularised errors (-> sig) and, for every
 // present pair a < b, the separation rescaled by the ratio of circular to directional error (-> sep), ready for
 // log_bf_ref.  bayesdistance.py:207-240; offsets measured in the frame of the later catalogue's source as the CLI
@@ -746,13 +761,8 @@ __device__ __forceinline__ void ell_prepare(const RowParams &R, unsigned present
 			if ((present >> a & 1u) && (present >> b & 1u)) {
 				double vx, vy;
 				offsets_ref(ra[b], de[b], ra[a], de[a], vx, vy);
-				double d = sqrt(vx * vx + vy * vy);
-				double ux = d == 0 ? 0.7071067811865476 : vx / (d + 1e-300);
-				double uy = d == 0 ? 0.7071067811865476 : vy / (d + 1e-300);
-				double wa = dir_precision(ux, uy, sx[a], sy[a], rho[a]);
-				double wb = dir_precision(ux, uy, sx[b], sy[b], rho[b]);
-				double ratio = (sig[a] * sig[a] + sig[b] * sig[b]) / (1 / wa + 1 / wb);
-				sep[pair_index(a, b, nc)] = d * (1.0 / sqrt(ratio));
+				if (R.sep_f32) { vx = (double) (float) vx; vy = (double) (float) vy; }   // the CLI's 'E' columns
+				sep[pair_index(a, b, nc)] = ell_rescaled_sep(vx, vy, sx[a], sy[a], rho[a], sx[b], sy[b], rho[b], sig[a], sig[b]);
 			}
 }
 
@@ -881,7 +891,7 @@ k_rows(RowParams R)
 							double s = nan("");
 							if (dg[a] > 0 && dg[b] > 0) {
 								s = mat[bo + (long long) (dg[a] - 1) * nl[b] + (dg[b] - 1)];
-								ok = ok && (s < R.radius);
+								ok = ok && (s < R.pair_radius[pair_index(a, b, NC)]);
 							}
 							sep[pair_index(a, b, NC)] = s;
 							bo += (long long) nl[a] * nl[b];
@@ -893,6 +903,10 @@ k_rows(RowParams R)
 			if (ok) {
 				long long row = rbase + written + __popc(m & ((1u << lane) - 1));
 				double smax = 0.0;
+				if (R.sep_f32) {
+#pragma unroll
+					for (int k = 0; k < NC * (NC - 1) / 2; k++) sep[k] = (double) (float) sep[k];   // NaN stays NaN
+				}
 #pragma unroll
 				for (int c = 0; c < NC; c++) R.C.idx[c][row] = sidx[c];
 #pragma unroll
@@ -911,7 +925,7 @@ k_rows(RowParams R)
 #pragma unroll
 					for (int c = 1; c < NC; c++)
 						if (present >> c & 1u) sig[c] = R.err[c][sidx[c]];
-					lbf = log_bf_ref<NC>(T, NC, present, sig, sep);
+					lbf = log_bf_ref<NC>(T, NC, present, sig, sep, R.sep_f32 != 0);
 				}
 				unsigned smask = present >> 1;
 				double prior = T->prior[smask], l10p = T->log10prior[smask];
@@ -975,6 +989,7 @@ __device__ __forceinline__ void rows2_write(const RowParams &R, const ConstTable
 	long long gp, long long sidx1, double sep, double w0, double lw0, R2Memo &memo, double &v_out)
 {
 	const bool present = sidx1 >= 0;
+	if (R.sep_f32) sep = (double) (float) sep;
 	R.C.idx[0][row] = gp;
 	R.C.idx[1][row] = sidx1;
 	R.C.sep[0][row] = present ? sep : nan("");
@@ -998,7 +1013,7 @@ __device__ __forceinline__ void rows2_write(const RowParams &R, const ConstTable
 		}
 		double wsum = memo.wsum;
 		double slog = lw0 + memo.lw1 - memo.lwsum;
-		double q = w0 * w1 * (sep * sep);
+		double q = w0 * w1 * (R.sep_f32 ? (double) __fmul_rn((float) sep, (float) sep) : sep * sep);
 		// -q / 2 / wsum: the halving is exact; the quotient is the correctly rounded one (Markstein: with y = RN(1/b),
 		// q0 = RN(a y), r = a - b q0 exactly by FMA, RN(q0 + r y) = RN(a / b)) as long as nothing under/overflows --
 		// anything else (q huge or wsum denormal-ish) takes the division
@@ -1359,6 +1374,44 @@ __global__ void k_log_bf(long long n, int ncat, const double *__restrict__ sep, 
 		for (int b = a + 1; b < ncat; b++)
 			sp[pair_index(a, b, ncat)] = sep[((long long) a * ncat + b) * n + i];
 	out[i] = log_bf_ref<0>(T, ncat, (1u << ncat) - 1, sig, sp);
+}
+
+// bayesdistance.log_bf_elliptical (:207-240) on caller-supplied offsets: sep_ra / sep_dec are ncat*ncat blocks of n
+// (only a < b read), err is ncat blocks of (sigma_x | sigma_y | rho), each n long
+__global__ void k_log_bf_ell(long long n, int ncat, const double *__restrict__ sra, const double *__restrict__ sde,
+	const double *__restrict__ err, const ConstTables *__restrict__ T, double *__restrict__ out)
+{
+	long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double sx[MAXC], sy[MAXC], rho[MAXC], sig[MAXC], sp[MAXP];
+	for (int c = 0; c < ncat; c++) {
+		sx[c] = err[((long long) c * 3 + 0) * n + i];
+		sy[c] = err[((long long) c * 3 + 1) * n + i];
+		rho[c] = err[((long long) c * 3 + 2) * n + i];
+		sig[c] = sqrt((sx[c] * sx[c] + sy[c] * sy[c]) / 2);
+	}
+	for (int a = 0; a < ncat; a++)
+		for (int b = a + 1; b < ncat; b++) {
+			long long k = ((long long) a * ncat + b) * n + i;
+			sp[pair_index(a, b, ncat)] = ell_rescaled_sep(sra[k], sde[k], sx[a], sy[a], rho[a], sx[b], sy[b], rho[b], sig[a], sig[b]);
+		}
+	out[i] = log_bf_ref<0>(T, ncat, (1u << ncat) - 1, sig, sp);
+}
+
+// tangent-plane offsets (arcsec) of the rows of the result table for the catalogue pair (a, b), a < b, measured like
+// fastskymatch.match_multiple does for circular=False (:299-331): frame centred on the source of the later catalogue
+// b, the earlier one is the target.  NaN where either source is absent.
+__global__ void k_row_offsets(long long nrows, const long long *__restrict__ ia, const long long *__restrict__ ib,
+	const double *__restrict__ ra_a, const double *__restrict__ dec_a, const double *__restrict__ ra_b,
+	const double *__restrict__ dec_b, double *__restrict__ dra, double *__restrict__ ddec)
+{
+	long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nrows) return;
+	long long sa = ia[i], sb = ib[i];
+	double x = nan(""), y = nan("");
+	if (sa >= 0 && sb >= 0) offsets_ref(ra_b[sb], dec_b[sb], ra_a[sa], dec_a[sa], x, y);
+	dra[i] = x;
+	ddec[i] = y;
 }
 
 __global__ void k_posterior(long long n, const double *__restrict__ prior, const double *__restrict__ lbf,

@@ -53,11 +53,13 @@ def adaptive_histograms(mag_all, mag_sel, weights=None):
 
 
 def auto_histogram(res, magvals, separation_max, dist_post, mag_include_radius, mag_exclude_radius,
-		magauto_post_single_minvalue):
+		magauto_post_single_minvalue, cli=False):
 	"""Select secure counterparts / secure field sources from the first pass and histogram their magnitudes
 	(__init__.py:324-366).  res: index column of the catalogue; magvals: its magnitude column with NaN for
 	undefined, in the caller's dtype.  Includes the reference's weight indexing so that results
-	are identical.  Returns bins, hist_sel, hist_all, n_secure, n_possible, n_others."""
+	are identical: the API takes the weights of the rows with a counterpart (__init__.py:337), the command-line
+	program those of the selected rows (nway.py:471) -- cli=True.
+	Returns bins, hist_sel, hist_all, n_secure, n_possible, n_others."""
 	res_defined = res != -1
 	mask_all = numpy.isfinite(magvals)
 	if mag_include_radius is not None:
@@ -69,7 +71,7 @@ def auto_histogram(res, magvals, separation_max, dist_post, mag_include_radius, 
 		selection_weights = dist_post
 		selection_possible = dist_post > 0.01
 	selection = numpy.logical_and(selection, res_defined)
-	selection_weights = selection_weights[res_defined]
+	selection_weights = selection_weights[selection] if cli else selection_weights[res_defined]
 	selection_possible = numpy.logical_and(selection_possible, res_defined)
 	rows, unique_indices = numpy.unique(res[selection], return_index=True)
 	rows_weights = selection_weights[unique_indices]

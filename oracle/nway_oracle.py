@@ -174,11 +174,13 @@ def error_triples(tables):
 	return out
 
 
-def create_match_table(tables, match_radius, enumerator='complete'):
+def create_match_table(tables, match_radius, enumerator='complete', sep_f32=False, pairwise_errs=()):
 	"""nwaylib/__init__.py:123-196.  Returns dict(idx (R,N) int64, sep {(a,b): (R,)}, sepmax, ncat,
 	errors [N x (R,)]); in elliptical mode also off {(a,b): (dra, ddec)} in arcsec, measured like the CLI does
 	(fastskymatch.py:299-331: offset frame centred on the source of the LATER catalogue b, the earlier one is the
-	target) and errors as triples."""
+	target) and errors as triples.  sep_f32: the command-line program keeps separations and offsets in float32
+	FITS columns ('E', fastskymatch.py:328-333) and scores what it reads back (nway.py:269,302-305); the radius
+	filter runs before that, on the fp64 values (fastskymatch.py:335)."""
 	radec = [(np.asarray(t['ra'], dtype=float), np.asarray(t['dec'], dtype=float)) for t in tables]
 	radius_deg = match_radius / 60. / 60
 	if enumerator == 'refhash':
@@ -199,8 +201,19 @@ def create_match_table(tables, match_radius, enumerator='complete'):
 			with np.errstate(invalid='ignore'):
 				sepmax = np.where(np.isnan(col), sepmax, np.maximum(col, sepmax))
 	keep = sepmax < match_radius
+	# --prefilter-pair as intended (fastskymatch.py:184-208): with both members present the pair must be closer than
+	# its own radius.  The reference as written drops every tuple holding both (the mask assignment at :203 writes to
+	# a temporary): that is radius 0 here -- pinned against the real nway.py in tests/golden/ref_cli_*.
+	for a, b, rad in pairwise_errs:
+		col = sep[(min(a, b), max(a, b))]
+		with np.errstate(invalid='ignore'):
+			keep &= np.isnan(col) | (col < rad)
 	idx = idx[keep]
-	out = dict(idx=idx, sep={k: v[keep] for k, v in sep.items()}, sepmax=sepmax[keep], ncat=(idx > -1).sum(axis=1))
+	# sep_f32: the separation arrays STAY float32, so that log_bf squares them in float32 exactly as numpy does for
+	# the reference (`p[i][j]**2` on an 'E' column, bayesdistance.py:83); offsets are rounded and widened again
+	# (the elliptical branch cannot run here, its float32 arithmetic is not pinned: DESIGN.md)
+	f32 = (lambda x: x.astype(np.float32)) if sep_f32 else (lambda x: x)
+	out = dict(idx=idx, sep={k: f32(v[keep]) for k, v in sep.items()}, sepmax=f32(sepmax[keep]).astype(float), ncat=(idx > -1).sum(axis=1))
 	if is_elliptical(tables):
 		trip = error_triples(tables)
 		out['errors'] = [tuple(x[idx[:, c]] for x in trip[c]) for c in range(n)]
@@ -209,7 +222,7 @@ def create_match_table(tables, match_radius, enumerator='complete'):
 			for b in range(a + 1, n):
 				ia, ib = idx[:, a], idx[:, b]
 				_, dra, ddec = offsets((radec[b][0][ib], radec[b][1][ib]), (radec[a][0][ia], radec[a][1][ia]))
-				out['off'][(a, b)] = (dra * 60 * 60, ddec * 60 * 60)
+				out['off'][(a, b)] = (f32(dra * 60 * 60).astype(float), f32(ddec * 60 * 60).astype(float))
 	else:
 		out['errors'] = [np.asarray(t['error'], dtype=float)[idx[:, c]] for c, t in enumerate(tables)]
 	return out
@@ -383,7 +396,8 @@ def correct_unrelated_cli(mt, lbf, nu, nu_plus, group_start):
 						errs = [tuple(np.array([x[j]]) for x in mt['errors'][k]) for k in aug]
 						val = log_bf_elliptical(sra, sde, errs)[0]
 					else:
-						p = [[[mt['sep'][(a, b)][j]] if a < b else None for b in aug] for a in aug]
+						# nway.py:389-392 builds one numpy.array from float32 separations and float64 NaNs: float64
+						p = [[[float(mt['sep'][(a, b)][j])] if a < b else None for b in aug] for a in aug]
 						s = [[mt['errors'][k][j]] for k in aug]
 						val = log_bf(p, s)[0]
 					cache[key] = float(val + np.log10(pr))
@@ -435,9 +449,9 @@ def adaptive_histograms(mag_all, mag_sel, weights=None):
 	return edges, hs, ha
 
 
-def auto_histogram(res, magvals, sepmax, dist_post, mag_include_radius, mag_exclude_radius, minprob):
+def auto_histogram(res, magvals, sepmax, dist_post, mag_include_radius, mag_exclude_radius, minprob, cli=False):
 	"""nwaylib/__init__.py:324-366, including quirk Q7 (weights compressed by res_defined but
-	indexed by positions inside res[selection])."""
+	indexed by positions inside res[selection]); cli=True: nway.py:455-503 (weights compressed by the selection)."""
 	res_defined = res != -1
 	mask_all = np.isfinite(magvals)
 	if mag_include_radius is not None:
@@ -449,7 +463,7 @@ def auto_histogram(res, magvals, sepmax, dist_post, mag_include_radius, mag_excl
 		sw = dist_post
 		possible = dist_post > 0.01
 	selection = selection & res_defined
-	sw = sw[res_defined]
+	sw = sw[selection] if cli else sw[res_defined]
 	possible = possible & res_defined
 	rows, first = np.unique(res[selection], return_index=True)
 	rw = sw[first]
@@ -508,14 +522,15 @@ def group_statistics(v, starts, ratio_secondary):
 
 def nway_match(tables, match_radius, prior_completeness, mag_include_radius=None, mag_exclude_radius=None,
 		magauto_post_single_minvalue=0.9, prob_ratio_secondary=0.5, min_prob=0.,
-		unrelated_mode='api', enumerator='complete'):
+		unrelated_mode='api', enumerator='complete', cli_compat=False, pairwise_errs=()):
 	"""nwaylib.nway_match (nwaylib/__init__.py:31-120) as a dict of numpy columns.
-	unrelated_mode 'api' reproduces the API (inert correction, Q1); 'cli' applies nway.py:366-421."""
+	unrelated_mode 'api' reproduces the API (inert correction, Q1); 'cli' applies nway.py:366-421.
+	cli_compat: float32 separations / offsets (Q2) and the CLI's histogram weights (Q7), as nway.py computes."""
 	if mag_exclude_radius is None:
 		mag_exclude_radius = mag_include_radius
 	n = len(tables)
 	names = [t['name'] for t in tables]
-	mt = create_match_table(tables, match_radius, enumerator=enumerator)
+	mt = create_match_table(tables, match_radius, enumerator=enumerator, sep_f32=cli_compat, pairwise_errs=pairwise_errs)
 	idx = mt['idx']
 	if len(idx) == 0:
 		raise ValueError('No matches.')
@@ -530,7 +545,7 @@ def nway_match(tables, match_radius, prior_completeness, mag_include_radius=None
 	for c in range(n):
 		out[names[c]] = idx[:, c]
 	for (a, b), col in mt['sep'].items():
-		out['Separation_%s_%s' % (names[a], names[b])] = col
+		out['Separation_%s_%s' % (names[a], names[b])] = col.astype(float)
 	out['Separation_max'] = mt['sepmax']
 	out['ncat'] = mt['ncat']
 	out['dist_bayesfactor_uncorrected'] = lbf
@@ -545,7 +560,7 @@ def nway_match(tables, match_radius, prior_completeness, mag_include_radius=None
 			res = idx[:, c]
 			if maghist is None:
 				edges, hs, ha, nsel = auto_histogram(res, magvals, mt['sepmax'], out['dist_post'],
-					mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue)
+					mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue, cli=cli_compat)
 			else:
 				lo, hi, hs, ha = maghist
 				edges = np.array(list(lo) + [hi[-1]])

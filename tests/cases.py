@@ -128,3 +128,39 @@ def build_case(name):
 	if name in ('syn4', 'syn4_minprob'):
 		return with_mags(uniform_patch(6, (200, 3000, 3000, 2500), (1.0, 0.4, 0.5, 0.8), 0.05), 3, cats=(2,), ncols=1)
 	raise KeyError(name)
+
+
+# ---- command-line cases: FITS files of the COSMOS subset + argument lists (oracle/make_golden_cli.py) ----------
+
+def write_cosmos_subset_fits(directory):
+	"""the COSMOS subset as three FITS catalogues with the columns of the reference's demo files
+	(doc/COSMOS_{XMM,OPTICAL,IRAC}.fits: ID, RA, DEC + pos_err / MAG / mag_ch1; SKYAREA = 2 deg^2).  Written with
+	the product's FITS writer; the reference run that produced the goldens read them with its own reader."""
+	from nway_b200 import fitsio
+	z = np.load(os.path.join(GOLDEN_DIR, 'cosmos_subset.npz'))
+	paths = {}
+	for name, extra, key in (('XMM', 'pos_err', 'error'), ('OPT', 'MAG', 'mag'), ('IRAC', 'mag_ch1', 'mag')):
+		n = len(z[name + '_ra'])
+		cols = [fitsio.Column('ID', 'J', np.arange(1, n + 1)), fitsio.Column('RA', 'D', z[name + '_ra']),
+			fitsio.Column('DEC', 'D', z[name + '_dec']), fitsio.Column(extra, 'E', z['%s_%s' % (name, key)])]
+		paths[name] = os.path.join(directory, 'SUB_%s.fits' % name)
+		fitsio.write_table(paths[name], cols, name, table_header=[('SKYAREA', 2.0)])
+	return paths
+
+
+CLI_CASES = {
+	# name: arguments after the catalogue list is substituted ({XMM}, {OPT}, {IRAC} = file paths)
+	'cli2': ['--radius', '20', '--prior-completeness', '0.9', '{XMM}', ':pos_err', '{OPT}', '0.1'],
+	'cli3': ['--radius', '20', '{XMM}', ':pos_err', '{OPT}', '0.1', '{IRAC}', '0.5'],
+	'cli3_magauto': ['--radius', '20', '{XMM}', ':pos_err', '{OPT}', '0.1', '{IRAC}', '0.5',
+		'--mag', 'OPT:MAG', 'auto', '--mag', 'IRAC:mag_ch1', 'auto', '--mag-radius', '4'],
+	'cli3_bayes': ['--radius', '15', '--prior-completeness', '0.9:0.8', '--acceptable-prob', '0.3', '{XMM}', ':pos_err', '{OPT}', '0.1',
+		'{IRAC}', '0.5', '--mag', 'OPT:MAG', 'auto', '--mag-auto-minprob', '0.8'],
+	'cli3_minprob': ['--radius', '12', '--prior-completeness', '0.95', '--min-prob', '0.01', '--ignore-unrelated-associations',
+		'{XMM}', ':pos_err', '{OPT}', '0.1', '{IRAC}', '0.5'],
+	'cli3_prefilter': ['--radius', '12', '{XMM}', ':pos_err', '{OPT}', '0.1', '{IRAC}', '0.5', '--prefilter-pair', 'OPT', 'IRAC', '0.5'],
+}
+
+
+def cli_args(name, paths, outfile):
+	return [a.format(**paths) for a in CLI_CASES[name]] + ['--out=' + outfile]

@@ -1,0 +1,58 @@
+"""CPU tests of the command-line layer: FITS table I/O, and the oracle in cli_compat mode against the golden
+outputs of the UNMODIFIED reference nway.py (tests/golden/ref_cli_*.npz, made by oracle/make_golden_cli.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import cases, cliparity
+
+
+def test_fits_roundtrip(tmp_path):
+	from nway_b200 import fitsio as F
+	rng = np.random.default_rng(5)
+	n = 1234
+	cols = [F.Column('A_ID', 'J', np.arange(n)), F.Column('x', 'E', rng.normal(size=n)), F.Column('n', 'I', rng.integers(-99, 99, n)),
+		F.Column('s', '7A', [('s%d' % i).encode() for i in range(n)]), F.Column('d', 'D', rng.normal(size=n) * 1e10),
+		F.Column('k', 'K', 2**40 + np.arange(n)), F.Column('b', 'L', rng.integers(0, 2, n) > 0), F.Column('u', 'B', rng.integers(0, 255, n))]
+	path = str(tmp_path / 't.fits')
+	long_cmd = 'nway.py ' + ' '.join("--arg%d 'value %d'" % (i, i) for i in range(20))
+	F.write_table(path, cols, 'NWAYMATCH', primary_header=[('METHOD', 'NWAY multi-way matching'), ('NWAYCMD', long_cmd), ('N', 3), ('X', 2.5)],
+		table_header=[('SKYAREA', 2.0)], comments=['argument radius: 20', 'x' * 200])
+	assert os.path.getsize(path) % 2880 == 0
+	t = F.read_table(path)
+	assert t.name == 'NWAYMATCH' and t.columns == [c.name for c in cols] and t.formats == [c.format for c in cols]
+	assert t.header['SKYAREA'] == 2.0
+	for c in cols:
+		assert t.data[c.name].dtype == c.array.dtype and (t.data[c.name] == c.array).all(), c.name
+	cards, _ = F._read_header(open(path, 'rb').read(), 0)
+	assert cards['NWAYCMD'] == long_cmd and cards['N'] == 3 and cards['X'] == 2.5
+	assert cards['COMMENT'][0].strip() == 'argument radius: 20'
+	with pytest.raises(ValueError):
+		F.read_table(path, ext=2)
+
+
+def test_fits_empty_and_bad_format(tmp_path):
+	from nway_b200 import fitsio as F
+	path = str(tmp_path / 'e.fits')
+	F.write_table(path, [F.Column('a', 'D', np.zeros(0))], 'EMPTY')
+	assert len(F.read_table(path)) == 0
+	with pytest.raises(ValueError):
+		F.Column('v', '3E', np.zeros(3))
+	with pytest.raises(ValueError):
+		F.write_table(path, [F.Column('a', 'D', np.zeros(2)), F.Column('b', 'D', np.zeros(3))], 'X')
+
+
+def test_subset_fits_files(tmp_path):
+	from nway_b200 import fitsio as F
+	paths = cases.write_cosmos_subset_fits(str(tmp_path))
+	t = F.read_table(paths['XMM'])
+	assert t.name == 'XMM' and len(t) == 1797 and t.columns == ['ID', 'RA', 'DEC', 'pos_err'] and t.formats == ['J', 'D', 'D', 'E']
+	assert t.header['SKYAREA'] == 2.0
+
+
+@pytest.mark.parametrize('name', ['cli2', 'cli3_minprob', 'cli3_prefilter'])
+def test_oracle_cli_mode_against_reference_cli(name, tmp_path):
+	"""the oracle port with cli_compat=True == the real nway.py, bit for bit in the output formats"""
+	got = cliparity.oracle_cli_table(name)
+	cliparity.check_against_cli_digest(name, got, exact=True)
