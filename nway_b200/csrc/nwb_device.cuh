@@ -15,6 +15,17 @@ constexpr int MAXP = MAXC * (MAXC - 1) / 2;   // catalogue pairs
 constexpr int MAXM = 8;                       // magnitude columns (all catalogues together)
 constexpr int MAXB = 64;                      // bins per magnitude prior
 
+// One 32-byte sector per lane in ONE request (sm_100 has 256-bit global loads: LDG.E.256).  A 128-bit + a 64-bit load
+// of the same record would walk the L1TEX tag / data stages twice, and k_pairs is bound by exactly those
+// (l1tex__data_pipe_lsu_wavefronts at 90 % of peak, profiles/r01_step3_*).  Read-only data only (.nc).
+struct Sector32 { unsigned long long q[4]; };
+__device__ __forceinline__ Sector32 ldg_sector(const void *p /* 32-byte aligned */)
+{
+	Sector32 s;
+	asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s.q[0]), "=l"(s.q[1]), "=l"(s.q[2]), "=l"(s.q[3]) : "l"(p));
+	return s;
+}
+
 // x / b for a compile-time constant b, correctly rounded like the IEEE division the reference performs, but
 // without the division subroutine: q = RN(x * RN(1/b)), one FMA residual, one FMA correction (Markstein).
 // Checked against x / b on 4e8 random arguments for b = 180 and b = pi (0 mismatches).

@@ -288,11 +288,12 @@ __device__ __forceinline__ void k1_flush(const K1Smem &M, int lo, int count, int
 		const int2 c = M.cand_sp[lo + lane];
 		const double2 rd = M.cand_rd[lo + lane];
 		const int s = c.x, p = c.y;
-		const double4 pr = *reinterpret_cast<const double4 *>(A.P.rec + p);   // one sector
+		const Sector32 pr = ldg_sector(A.P.rec + p);   // one sector, one request
 		double slat2, clat2;
 		sincos(deg2rad_ref(rd.y), &slat2, &clat2);
 		double lon2 = deg2rad_ref(rd.x);
-		double sep = sep_arcsec_ref(pr.x, pr.y, pr.z, lon2, slat2, clat2);
+		double sep = sep_arcsec_ref(__longlong_as_double(pr.q[0]), __longlong_as_double(pr.q[1]), __longlong_as_double(pr.q[2]),
+			lon2, slat2, clat2);
 		if (sep < A.radius) {
 			int slot = atomicAdd(&A.cnt[p], 1);
 			if (slot < A.C) {
@@ -421,12 +422,12 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 						B = load_band(G, b);
 					}
 					const int cell = B.base + racell_of(B, x);
-					const int4 c0 = __ldg(reinterpret_cast<const int4 *>(cells + cell));       // cnt, start, x, y
-					const int2 c1 = __ldg(reinterpret_cast<const int2 *>(cells + cell) + 2);   // clat, p (same sector)
-					ecnt = c0.x; estart = c0.y;
+					const Sector32 cr = ldg_sector(cells + cell);   // cnt, start | x, y | clat, p | pad: one sector, one request
+					ecnt = (int) (unsigned) cr.q[0]; estart = (int) (cr.q[0] >> 32);
 					if (ecnt > 0) {
-						pass0 = k1_pretest(G, (float) x, (float) y, __int_as_float(c0.z), __int_as_float(c0.w), __int_as_float(c1.x));
-						p0 = c1.y;
+						pass0 = k1_pretest(G, (float) x, (float) y, __uint_as_float((unsigned) cr.q[1]), __uint_as_float((unsigned) (cr.q[1] >> 32)),
+							__uint_as_float((unsigned) cr.q[2]));
+						p0 = (int) (cr.q[2] >> 32);
 					}
 				}
 			}
