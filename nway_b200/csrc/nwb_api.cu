@@ -242,6 +242,7 @@ int upload_tables(nwb_ctx *ctx)
 struct HostGrid {
 	Grid g;
 	std::vector<BandRec> bands;
+	std::vector<float> kx;   // per band, for the packed pre-test (struct PEntry)
 };
 
 void build_grid(const double red[6], double rb_ins, double cell_min_deg, long long max_cells, HostGrid &H)
@@ -284,8 +285,9 @@ void build_grid(const double red[6], double rb_ins, double cell_min_deg, long lo
 }
 
 // constants of the fp32 flat pre-test (see struct Entry): rr2 and the pole cut-off tau_max
-void pretest_constants(Grid &g, double rb_deg)
+void pretest_constants(HostGrid &H, double rb_deg)
 {
+	Grid &g = H.g;
 	const double theta = rb_deg * M_PI / 180;
 	double tau_max = 0.02;
 	double kappa;
@@ -303,6 +305,33 @@ void pretest_constants(Grid &g, double rb_deg)
 	g.ra_org_n = g.ra_org - 360.0 * std::floor(g.ra_org / 360.0);
 	if (g.ra_org_n >= 360.0 || g.ra_org_n < 0.0) g.ra_org_n = 0.0;
 	g.tau_max = tau_max;
+	// packed pre-test: per band kx = (smallest cos(dec) any primary registered in the band can have) x (cell width in
+	// degrees), rounded down -- a smaller kx only makes the test more permissive.  Primaries registered in band b lie
+	// within rb of it.  Bands that reach the zone where the flat metric is not a safe bound (tau > tau_max, or a search
+	// box spanning all of ra) are tested on declination only: kx = 0.
+	const double s = 1.0 / g.inv_h;
+	H.kx.resize(g.nbands);
+	double cell_true_max = s;
+	for (int b = 0; b < g.nbands; b++) {
+		double lo = g.dec_lo + b * s - (rb_deg + 1e-8), hi = g.dec_lo + (b + 1) * s + (rb_deg + 1e-8);
+		double amax = std::max(std::fabs(lo), std::fabs(hi));
+		bool polar = tau_max < 0 || amax + rb_deg >= 89.99 || theta * std::tan(std::min(amax, 89.9999) * M_PI / 180) > tau_max;
+		float k = 0.f;
+		if (!polar) {
+			double v = std::cos(amax * M_PI / 180) * (1 - 1e-7) / H.bands[b].inv_w;
+			k = (float) v;
+			if ((double) k > v) k = std::nextafter(k, 0.f);
+			const double amin = (lo < 0 && hi > 0) ? 0.0 : std::min(std::fabs(lo), std::fabs(hi));
+			cell_true_max = std::max(cell_true_max, std::cos(amin * M_PI / 180) / H.bands[b].inv_w);
+		}
+		H.kx[b] = k;
+	}
+	g.hdeg = std::nextafter((float) s, 0.f);   // rounded down: only more permissive
+	// quantisation of the packed entries: half a step of 4/32768 cell widths in x and of 4/65536 band heights in y, plus
+	// the fp32 rounding of a handful of O(1) quantities
+	const double quant = std::sqrt(6.2e-5 * 6.2e-5 + 3.1e-5 * 3.1e-5) * std::max(cell_true_max, s) + 4e-6 * std::max(cell_true_max, s);
+	const double rrp = rb_deg * (1 + kappa) + quant + 1e-9;
+	g.rr2p = std::nextafter((float) (rrp * rrp * (1 + 1e-6)), INFINITY);
 }
 
 inline int grid_for(long long n, int block) { return (int) std::min<long long>((n + block - 1) / block, 1 << 30); }
@@ -686,12 +715,14 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		HostGrid HG;
 		long long max_cells = 4ll << 20;
 		build_grid(red, rb_ins, rb_ins, max_cells, HG);
-		pretest_constants(HG.g, rb_ins);
+		pretest_constants(HG, rb_ins);
 		size_t nb = (size_t) HG.g.nbands;
-		ENSURE(ctx->d_bands, nb * sizeof(BandRec) + 64);
+		ENSURE(ctx->d_bands, nb * (sizeof(BandRec) + sizeof(float)) + 64);
 		CU(cudaMemcpyAsync(ctx->d_bands.p, HG.bands.data(), nb * sizeof(BandRec), cudaMemcpyHostToDevice, st));
-		CU(cudaStreamSynchronize(st));   // HG.bands is a temporary
+		CU(cudaMemcpyAsync((char *) ctx->d_bands.p + nb * sizeof(BandRec), HG.kx.data(), nb * sizeof(float), cudaMemcpyHostToDevice, st));
+		CU(cudaStreamSynchronize(st));   // HG.bands / HG.kx are temporaries
 		HG.g.bands = (const BandRec *) ctx->d_bands.p;
+		HG.g.kx = (const float *) ((const char *) ctx->d_bands.p + nb * sizeof(BandRec));
 		ctx->geom_G = HG.g;
 		ctx->geom_rb = rb; ctx->geom_np = np; ctx->geom_first = first;
 		ctx->geom_valid = true;
@@ -738,19 +769,20 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	long long R = 0;
 	bool done = false, speculated = false;
 	for (int attempt = 0; !done && attempt < 4; attempt++) {
-		ENSURE(ctx->d_entries, ctx->entries_cap * sizeof(Entry));
+		ENSURE(ctx->d_entries, ctx->entries_cap * (sizeof(Entry) + sizeof(PEntry)));
 		ENSURE(ctx->d_spill, (size_t) ctx->spill_cap * (nc - 1) * sizeof(SpillRec));
 		Entry *d_entries = (Entry *) ctx->d_entries.p;
+		PEntry *d_pentries = (PEntry *) (d_entries + ctx->entries_cap);
 		SpillRec *d_spill = (SpillRec *) ctx->d_spill.p;
 		CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
 		LAUNCH(ctx, (k_prim_cells<false>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) nullptr,
-			(Entry *) nullptr, (long long) 0);
+			(Entry *) nullptr, (PEntry *) nullptr, (long long) 0);
 		{ int r = scan_int(ctx, d_cellcnt, d_cstart, (int64_t) ncell1); if (r) return r; }
 		LAUNCH(ctx, (k_prim_cells<true>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) d_cstart,
-			d_entries, (long long) ctx->entries_cap);
+			d_entries, d_pentries, (long long) ctx->entries_cap);
 		ENSURE(ctx->d_cells, (size_t) G.ncells * sizeof(CellRec));
 		LAUNCH(ctx, k_cell_records, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cstart,
-			(const Entry *) d_entries, (long long) ctx->entries_cap, (CellRec *) ctx->d_cells.p);
+			(const PEntry *) d_pentries, (long long) ctx->entries_cap, (CellRec *) ctx->d_cells.p);
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[1], st));
 
 		// ---- K1: stream the secondaries ----------------------------------------------------------------

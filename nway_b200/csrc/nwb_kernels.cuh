@@ -36,6 +36,9 @@ struct Grid {
 	long long ncells;
 	float rr2;              // squared radius (deg^2) of the fp32 flat pre-test, all margins included
 	double tau_max;         // primaries with rb_rad * tan|dec| above this are tested on dec only
+	const float *kx;        // [nbands] packed pre-test: degrees of true angle per cell width, rounded down; 0 = dec only
+	float hdeg;             // band height in degrees
+	float rr2p;             // squared radius of the packed pre-test (rr2's margins + the quantisation of the entries)
 };
 
 // 16 bytes, one load: one primary as seen from one cell, for the fp32 flat PRE-test
@@ -47,6 +50,26 @@ struct Entry {
 	float x, y, clat;
 	int p;
 };
+
+// 8 bytes: the same primary in CELL units, for the entries that live inside the cell record.  x, y = position
+// relative to the cell's origin (x in cell widths, y in band heights), fixed point over [-1.5, 2.5): 15 bits for x
+// (bit 15 = "always pass": the encoding did not apply), 16 bits for y.  The pre-test then is
+//     ((xr - px) kx)^2 + ((yr - py) h)^2 <= rr2p,     (xr, yr) = the secondary inside its cell, in [0, 1)^2,
+// kx = cos(dec) x cell width for the band (rounded down, so the test only gets more permissive; 0 for bands near a
+// pole).  No RA wrap logic: px is measured from the unwrapped cell index.
+struct PEntry {
+	unsigned xy;
+	int p;
+};
+constexpr float PE_OFF = 1.5f;
+constexpr float PE_XSTEP = 4.0f / 32768.0f, PE_YSTEP = 4.0f / 65536.0f;
+
+__device__ __forceinline__ unsigned pe_encode(double px, double py, bool always)
+{
+	double fx = rint((px + 1.5) * 8192.0), fy = rint((py + 1.5) * 16384.0);
+	if (!(fx >= 0.0 && fx <= 32767.0 && fy >= 0.0 && fy <= 65535.0)) { always = true; fx = 0.0; fy = 0.0; }
+	return (unsigned) (int) fx | (always ? 0x8000u : 0u) | ((unsigned) (int) fy << 16);
+}
 
 struct Slot16 {   // 16 bytes: one match of a primary
 	int s, pad;
@@ -117,13 +140,12 @@ struct PrimArrays {
 	double *ra_n, *dec, *dra;    // search box (degrees); dra >= 180 means "all ra"
 };
 
-// 32 bytes = one L2 sector per cell: how many primaries are registered here, where the list is, and the first
-// of them inline -- a source in a cell with a single primary (the common case) needs no second lookup.
+// 32 bytes = one L2 sector per cell, fetched with one 256-bit load: how many primaries are registered here and the
+// first three of them inline, packed (PEntry); entries beyond the third become work items.  A secondary in a cell
+// with <= 3 primaries (90 % of the occupied cells at C3's densities) needs no second lookup.
+//     q[0] = cnt | list start << 32      q[1] = entry 0      q[2] = entry 1      q[3] = entry 2
 struct CellRec {
-	int cnt, start;
-	float x, y, clat;
-	int p;
-	int pad0, pad1;
+	unsigned long long q[4];
 };
 
 // box margins: rb (deg) is the search radius inflated by 1e-9 relative + 1e-12, so that rounding in the
@@ -190,7 +212,8 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 // and retries.
 template <bool FILL>
 __global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double dra_eps,
-	int *__restrict__ cellcnt, const int *__restrict__ cstart, Entry *__restrict__ entries, long long entries_cap)
+	int *__restrict__ cellcnt, const int *__restrict__ cstart, Entry *__restrict__ entries, PEntry *__restrict__ pentries,
+	long long entries_cap)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	const int i = t >> 2, bslot = t & 3;   // four threads per primary, one declination band each
@@ -211,11 +234,15 @@ __global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double
 		en.p = i;
 	}
 	double di = dra + dra_eps;
+	const double xp = wrap360(rn - G.ra_org);          // the primary along ra, from the grid origin
+	const double yp = (d - G.dec_lo) * G.inv_h;        // ... and in band heights
 	for (int b = b0 + bslot; b <= b1; b += 4) {
 		BandRec B = load_band(G, b);
 		int n = B.nra;
 		int i0, cnt;
 		double cellw = G.ra_span / n;
+		const int ip = racell_of(B, xp);               // the primary's own cell in this band
+		const double xc = xp * B.inv_w - (double) ip;  // its position inside that cell, in cell widths
 		if (G.full_circle) {
 			if (2 * di + 2 * cellw >= 360.0) { i0 = 0; cnt = n; }
 			else {
@@ -231,13 +258,38 @@ __global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double
 			cnt = i1 - i0 + 1;
 		}
 		int cb = B.base;
-		for (int k = 0; k < cnt; k++) {
-			int cell = cb + (i0 + k) % n;
-			if (FILL) {
-				int slot = atomicSub(&cellcnt[cell], 1) - 1;
-				*reinterpret_cast<int4 *>(entries + cstart[cell] + slot) = *reinterpret_cast<const int4 *>(&en);
-			} else {
-				atomicAdd(&cellcnt[cell], 1);
+		if (!FILL) {
+			for (int k = 0; k < cnt; k++) atomicAdd(&cellcnt[cb + (i0 + k) % n], 1);
+			continue;
+		}
+		// four cells at a time: the slot requests (atomics with return) and the list starts are independent loads, issued
+		// together so that their latencies overlap; then the stores
+		for (int k0 = 0; k0 < cnt; k0 += 4) {
+			int pos[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				pos[u] = -1;
+				if (k0 + u < cnt) {
+					int cell = cb + (i0 + k0 + u) % n;
+					pos[u] = cstart[cell] + atomicSub(&cellcnt[cell], 1) - 1;
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				if (pos[u] < 0) continue;
+				*reinterpret_cast<int4 *>(entries + pos[u]) = *reinterpret_cast<const int4 *>(&en);
+				// packed twin: offset of this cell from the primary's own, unwrapped
+				int m = i0 + k0 + u - ip;
+				bool always = false;
+				if (G.full_circle) {
+					if (m > n / 2) m -= n;
+					else if (m < -(n / 2)) m += n;
+					always = n < 4 || cnt >= n;   // too few cells to tell which way round is the near one
+				}
+				PEntry pe;
+				pe.xy = pe_encode(xc - (double) m, yp - (double) b, always);
+				pe.p = i;
+				*reinterpret_cast<int2 *>(pentries + pos[u]) = *reinterpret_cast<const int2 *>(&pe);
 			}
 		}
 	}
@@ -259,7 +311,7 @@ constexpr int K1_QCAP = 64;                      // candidates: 31 left over + 3
 constexpr int K1_SBANDS = 1024;                  // bands cached in shared memory (16 KB)
 
 #ifndef NWB_K1_MINBLOCKS
-#define NWB_K1_MINBLOCKS 3
+#define NWB_K1_MINBLOCKS 4
 #endif
 
 struct K1Smem {   // per warp
@@ -323,6 +375,16 @@ __device__ __forceinline__ bool k1_pretest(const Grid &G, float x, float y, floa
 	return u * u + dy * dy <= G.rr2;
 }
 
+// the packed pre-test (see struct PEntry); (xr, yr) = the secondary inside its cell
+__device__ __forceinline__ bool k1_pretest_packed(const Grid &G, float xr, float yr, float kx, unsigned xy)
+{
+	float px = (float) (xy & 0x7fffu) * PE_XSTEP - PE_OFF;
+	float py = (float) (xy >> 16) * PE_YSTEP - PE_OFF;
+	float fx = (xr - px) * kx;
+	float fy = (yr - py) * G.hdeg;
+	return (xy & 0x8000u) != 0u || fx * fx + fy * fy <= G.rr2p;
+}
+
 // queue the lanes with pass == true as candidates; run the exact stage when 32 are there
 __device__ __forceinline__ void k1_enqueue(K1Smem &M, bool pass, int s, int p, double r, double d, int lane, int &qn,
 	const K1Args &A)
@@ -382,11 +444,14 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 {
 	__shared__ K1Smem smem[K1_WARPS];
 	__shared__ int4 sbands[K1_SBANDS];   // the band table, when it is small enough (one L2 round trip less)
+	__shared__ float skx[K1_SBANDS];
 	if ((long long) cstart[G.ncells] > entries_cap) return;   // the cell lists were not written: the host retries
 	const bool bands_in_smem = G.nbands <= K1_SBANDS;
 	if (bands_in_smem) {
-		for (int b = threadIdx.x; b < G.nbands; b += blockDim.x)
+		for (int b = threadIdx.x; b < G.nbands; b += blockDim.x) {
 			sbands[b] = __ldg(reinterpret_cast<const int4 *>(G.bands + b));
+			skx[b] = __ldg(G.kx + b);
+		}
 		__syncthreads();
 	}
 	const int lane = threadIdx.x & 31;
@@ -404,8 +469,9 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 			long long j = i + stride;   // software prefetch of the next batch: hides the DRAM latency
 			if (j < n) { r_nxt = ra[j]; d_nxt = dec[j]; }
 		}
-		int ecnt = 0, estart = 0, p0 = 0;
-		bool pass0 = false;
+		int ecnt = 0, estart = 0;
+		unsigned long long e0 = 0, e1 = 0, e2 = 0;
+		float xr = 0.f, yr = 0.f, kx = 0.f;
 		if (i < n) {
 			double y = d - G.dec_lo;
 			double t = y * G.inv_h;
@@ -418,24 +484,33 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 					if (bands_in_smem) {
 						const int4 v = sbands[b];
 						B.base = v.x; B.nra = v.y; B.inv_w = __hiloint2double(v.w, v.z);
+						kx = skx[b];
 					} else {
 						B = load_band(G, b);
+						kx = __ldg(G.kx + b);
 					}
-					const int cell = B.base + racell_of(B, x);
-					const Sector32 cr = ldg_sector(cells + cell);   // cnt, start | x, y | clat, p | pad: one sector, one request
-					ecnt = (int) (unsigned) cr.q[0]; estart = (int) (cr.q[0] >> 32);
-					if (ecnt > 0) {
-						pass0 = k1_pretest(G, (float) x, (float) y, __uint_as_float((unsigned) cr.q[1]), __uint_as_float((unsigned) (cr.q[1] >> 32)),
-							__uint_as_float((unsigned) cr.q[2]));
-						p0 = (int) (cr.q[2] >> 32);
-					}
+					const double xcells = x * B.inv_w;
+					int ic = __double2int_rd(xcells);
+					ic = ic >= B.nra ? B.nra - 1 : (ic < 0 ? 0 : ic);
+					const Sector32 cr = ldg_sector(cells + B.base + ic);   // one sector, one request
+					ecnt = (int) (unsigned) cr.q[0];
+					estart = (int) (cr.q[0] >> 32);
+					e0 = cr.q[1]; e1 = cr.q[2]; e2 = cr.q[3];
+					xr = (float) (xcells - (double) ic);
+					yr = (float) (t - (double) b);
 				}
 			}
 		}
-		k1_enqueue(M, pass0, (int) i, p0, r, d, lane, qn, A);
-		// entries beyond the inline one: one work item each, pre-tested as soon as 32 are there
+		// the inline entries: up to three fp32 pre-tests on the spot
+		const int ninl = min(ecnt, 3);
+		k1_enqueue(M, ninl > 0 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e0), (int) i, (int) (e0 >> 32), r, d, lane, qn, A);
+		if (__any_sync(NWB_FULL, ninl > 1))
+			k1_enqueue(M, ninl > 1 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e1), (int) i, (int) (e1 >> 32), r, d, lane, qn, A);
+		if (__any_sync(NWB_FULL, ninl > 2))
+			k1_enqueue(M, ninl > 2 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e2), (int) i, (int) (e2 >> 32), r, d, lane, qn, A);
+		// crowded cells (> 3 primaries): the entries beyond the third become work items, pre-tested 32 at a time
 		const int maxc = __reduce_max_sync(NWB_FULL, ecnt);
-		for (int k = 1; k < maxc; k++) {
+		for (int k = 3; k < maxc; k++) {
 			const bool has = k < ecnt;
 			const unsigned m = __ballot_sync(NWB_FULL, has);
 			if (has) {
@@ -462,23 +537,24 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 	}
 }
 
-// cell records from the cell lists: count, start and the first entry inline
-__global__ void k_cell_records(long long ncells, const int *__restrict__ cstart, const Entry *__restrict__ entries,
+// cell records from the cell lists (see struct CellRec)
+__global__ void k_cell_records(long long ncells, const int *__restrict__ cstart, const PEntry *__restrict__ pentries,
 	long long entries_cap, CellRec *__restrict__ cells)
 {
 	long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= ncells) return;
 	if ((long long) cstart[ncells] > entries_cap) return;
 	int s = cstart[c], cnt = cstart[c + 1] - s;
-	int4 a = make_int4(cnt, s, 0, 0);
-	int4 b = make_int4(0, 0, 0, 0);
+	unsigned long long q[4] = {(unsigned long long) (unsigned) cnt | ((unsigned long long) (unsigned) s << 32), 0ull, 0ull, 0ull};
 	if (cnt > 0) {
-		const int4 e = __ldg(reinterpret_cast<const int4 *>(entries + s));
-		a.z = e.x; a.w = e.y; b.x = e.z; b.y = e.w;
+		const unsigned long long *pe = reinterpret_cast<const unsigned long long *>(pentries + s);
+		q[1] = __ldg(pe);
+		if (cnt > 1) q[2] = __ldg(pe + 1);
+		if (cnt > 2) q[3] = __ldg(pe + 2);
 	}
-	int4 *out = reinterpret_cast<int4 *>(cells + c);
-	out[0] = a;
-	out[1] = b;
+	ulonglong2 *out = reinterpret_cast<ulonglong2 *>(cells + c);
+	out[0] = make_ulonglong2(q[0], q[1]);
+	out[1] = make_ulonglong2(q[2], q[3]);
 }
 
 // the scalars the host needs after K1, gathered for one small copy: [0] cell entries, [c] spill records of
@@ -971,8 +1047,8 @@ struct __align__(16) R2Smem {
 	double sep[R2_CAP];
 	double v[R2_CAP + 2];           // (+2 keeps hist 16-byte aligned)
 	int hist[R2_NB + 4];            // bucket counts, then exclusive bucket starts (R2_NB + 1 used)
+	int key[R2_CAP];                // the indices again, in bucket order
 	unsigned char pos[R2_CAP];      // arrival position of an element inside its bucket
-	unsigned char ord[R2_CAP];      // element ids in bucket order
 };
 
 // per-lane memo of the error-dependent terms of the 2-catalogue Bayes factor: catalogues very often carry one
@@ -1112,7 +1188,7 @@ k_rows2(RowParams R)
 		__syncwarp();
 		for (int e = lane; e < n; e += 32) {
 			int b = min(R2_NB - 1, (int) ((float) (M.s_in[e] - smin) * bscale));
-			M.ord[M.hist[b] + M.pos[e]] = (unsigned char) e;
+			M.key[M.hist[b] + M.pos[e]] = M.s_in[e];
 		}
 		__syncwarp();
 		for (int e = lane; e < n; e += 32) {
@@ -1120,18 +1196,22 @@ k_rows2(RowParams R)
 			int b = min(R2_NB - 1, (int) ((float) (mine - smin) * bscale));
 			int lo = M.hist[b], hi = M.hist[b + 1];
 			int rank = lo;
-			for (int j = lo; j < hi; j++) rank += M.s_in[M.ord[j]] < mine;
+			for (int j = lo; j < hi; j++) rank += M.key[j] < mine;
 			M.s[rank] = mine;
 			M.sep[rank] = M.v[e];
 		}
 		__syncwarp();
 		// rows in order: row 0 = no counterpart, row k = k-th smallest secondary index
 		const int rows = n + 1;
+		double m_rest = -INFINITY;   // max of the log-weights of rows 1.. (this lane's share)
 		for (int k = lane; k < rows; k += 32) {
 			double v = 0.0;
 			rows2_write<FUSE, SHARE>(R, T, rbase + k, gp, k == 0 ? -1 : (long long) M.s[k - 1], k == 0 ? 0.0 : M.sep[k - 1],
 				w0, lw0, memo, v);
-			if (FUSE) M.v[k] = v;
+			if (FUSE) {
+				M.v[k] = v;
+				if (k > 0) m_rest = fmax(m_rest, v);
+			}
 		}
 		if (!FUSE) continue;
 		// Group normalisation (__init__.py:423-457) on the shared copy of the log-weights, with ONE exp10 per row:
@@ -1141,8 +1221,6 @@ k_rows2(RowParams R)
 		// four orders below the parity tolerance).  Every lane only touches its own k = lane + 32 j, except v[0].
 		__syncwarp();
 		const double v0 = M.v[0];
-		double m_rest = -INFINITY;
-		for (int k = lane + (lane == 0 ? 32 : 0); k < rows; k += 32) m_rest = fmax(m_rest, M.v[k]);
 		m_rest = warp_max(m_rest);
 		const double m_all = fmax(v0, m_rest);
 		double s_rest = 0.0;
