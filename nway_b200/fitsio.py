@@ -193,6 +193,20 @@ def _cards(key, value):
 	return [_card(key, value)]
 
 
+_STRUCTURAL = ('XTENSION', 'BITPIX', 'NAXIS', 'NAXIS1', 'NAXIS2', 'PCOUNT', 'GCOUNT', 'TFIELDS', 'EXTNAME', 'COMMENT', 'HISTORY')
+
+
+def extra_header(table):
+	"""the (keyword, value) pairs of a table's header that are not structural (SKYAREA and friends), to carry over
+	into a rewritten copy (nway-create-shifted-catalogue.py:88-90)"""
+	out = []
+	for k, v in table.header.items():
+		if k in _STRUCTURAL or k[:5] in ('TTYPE', 'TFORM', 'TUNIT', 'TDISP', 'TNULL', 'TSCAL', 'TZERO', 'TDIM'):
+			continue
+		out.append((k, v))
+	return out
+
+
 def _card(key, value, comment=''):
 	if isinstance(value, bool):
 		v = '%20s' % ('T' if value else 'F')
