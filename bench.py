@@ -376,7 +376,7 @@ def main():
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C3 area (same densities); 1.0 = the named workload')
-	ap.add_argument('--cpu-scale', type=float, default=0.2, help='sample of the workload the CPU baseline is timed on')
+	ap.add_argument('--cpu-scale', type=float, default=0.4, help='sample of the workload the CPU baseline is timed on')
 	ap.add_argument('--ref-scale', type=float, default=0.05, help='sample per step of --impl reference')
 	ap.add_argument('--no-cpu', action='store_true')
 	args = ap.parse_args()
