@@ -126,6 +126,25 @@ int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows);
  * match_flag (__init__._apply_magnitude_biasing lookup half + _compute_final_probabilities). */
 int nwb_finalize(nwb_ctx *ctx);
 
+/* Automatic magnitude histograms (nwaylib/__init__.py:324-366, nway.py:455-503) between nwb_match(fuse_final=0) and
+ * nwb_finalize: the selection runs on the device, only the compact sample of secure counterparts comes back.
+ *
+ * nwb_maghist_select: over the rows of the last match, for magnitude column k of catalogue c (c >= 1):
+ *   by_radius != 0: selected = Separation_max < thr_select, possible = Separation_max < thr_possible, weights 1;
+ *   by_radius == 0: selected = dist_post > thr_select, possible = dist_post > thr_possible, weights = dist_post
+ *   (both only where the catalogue has a counterpart).  The selected sources are made unique by first occurrence
+ *   (numpy.unique(..., return_index=True)); weights_cli chooses the reference's weight indexing of the command-line
+ *   program (nway.py:471) instead of the API's (__init__.py:337) -- SURVEY.md Q7.
+ *   Out: nselected = unique selected sources; counts3 = {sources with a "possible" row, field sources (finite
+ *   magnitude, not possible), sources with a finite magnitude}; minmax2 = min / max magnitude of the field sources.
+ * nwb_maghist_sample: the magnitudes (NaN if undefined) and weights of the nselected sources, ascending source index.
+ * nwb_maghist_count: numpy.histogram(magnitudes of the field sources, bins=edges) -- integer counts per bin, last bin
+ *   closed on the right; the caller turns them into a density exactly as numpy does. */
+int nwb_maghist_select(nwb_ctx *ctx, int c, int k, int by_radius, double thr_select, double thr_possible, int weights_cli,
+	int64_t *nselected, int64_t *counts3, double *minmax2);
+int nwb_maghist_sample(nwb_ctx *ctx, int64_t nselected, double *mag_host, double *weight_host);
+int nwb_maghist_count(nwb_ctx *ctx, int c, int k, int nbins, const double *edges, int64_t *counts);
+
 /* a13 _truncate_table (__init__.py:464-471): keep rows with !(p_i < min_prob); compacts the device table in
  * place and returns the new row count. */
 int nwb_truncate(nwb_ctx *ctx, double min_prob, int64_t *nrows);

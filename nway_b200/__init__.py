@@ -240,18 +240,14 @@ def nway_match(match_tables, match_radius, prior_completeness,
 		raise EmptyResultException('No matches.')
 
 	if auto:
-		# first pass done; build the histograms on the host from dist_post / Separation_max (__init__.py:324-375)
-		sepmax = ctx.fetch(_lib.COL_SEPMAX, nrows)
-		dist_post = ctx.fetch(_lib.COL_DIST_POST, nrows)
-		ctx.sync()
+		# first pass done; select the secure counterparts / field sources on the device and build the <= 17-bin tables
+		# from the compact sample (__init__.py:324-375)
 		for c, k, magvals, maghist, magname in auto:
 			table_name = match_tables[c]['name']
 			col = '%s_%s' % (table_name, magname)
 			mag = '%s:%s' % (table_name, magname)
 			logger.log('Incorporating bias "%s" ...' % mag)
-			res = ctx.fetch(_lib.COL_IDX + c, nrows, numpy.int64)
-			ctx.sync()
-			bins, hist_sel, hist_all, nsel, npossible, nothers = magnitudeweights.auto_histogram(res, magvals, sepmax, dist_post,
+			bins, hist_sel, hist_all, nsel, npossible, nothers = magnitudeweights.auto_histogram_device(ctx, c, k, magvals.dtype,
 				mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue, cli=cli_compat)
 			logger.log('magnitude histogram of column "%s": %d secure matches, %d insecure matches and %d secure non-matches of %d total entries (%d valid)' % (
 				col, nsel, npossible, nothers, len(magvals), numpy.isfinite(magvals).sum()))

@@ -32,6 +32,10 @@ EXPORTS = {
 		ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int]),
 	'nwb_set_params': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_double_p, ctypes.c_double, ctypes.c_int]),
 	'nwb_set_compat': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+	'nwb_maghist_select': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+		c_int64_p, c_int64_p, c_double_p]),
+	'nwb_maghist_sample': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p]),
+	'nwb_maghist_count': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_int64_p]),
 	'nwb_set_prefilter': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), c_double_p]),
 	'nwb_set_tables': (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_double, c_double_p, c_double_p, c_double_p]),
 	'nwb_set_maghist': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
@@ -153,6 +157,25 @@ class Context(object):
 		b = (ctypes.c_int * max(n, 1))(*[int(x[1]) for x in pairwise_errs])
 		r = (ctypes.c_double * max(n, 1))(*[float(x[2]) for x in pairwise_errs])
 		self.check(self.lib.nwb_set_prefilter(self.h, n, a, b, r))
+
+	def maghist_select(self, c, k, by_radius, thr_select, thr_possible, weights_cli):
+		"""device half of the automatic histogram: returns (magnitudes, weights) of the unique selected sources in
+		ascending source order, (n_possible, n_others, n_valid), (min, max) magnitude of the field sources"""
+		nsel = ctypes.c_int64()
+		counts = (ctypes.c_int64 * 3)()
+		mm = (ctypes.c_double * 2)()
+		self.check(self.lib.nwb_maghist_select(self.h, int(c), int(k), int(bool(by_radius)), float(thr_select), float(thr_possible),
+			int(bool(weights_cli)), ctypes.byref(nsel), counts, mm))
+		mag, w = numpy.empty(nsel.value), numpy.empty(nsel.value)
+		if nsel.value:
+			self.check(self.lib.nwb_maghist_sample(self.h, nsel.value, dptr(mag), dptr(w)))
+		return mag, w, tuple(int(x) for x in counts), (float(mm[0]), float(mm[1]))
+
+	def maghist_count(self, c, k, edges):
+		edges = f64(edges)
+		counts = numpy.zeros(len(edges) - 1, dtype=numpy.int64)
+		self.check(self.lib.nwb_maghist_count(self.h, int(c), int(k), len(edges) - 1, dptr(edges), counts.ctypes.data_as(c_int64_p)))
+		return counts
 
 	def set_compat(self, flags):
 		self.check(self.lib.nwb_set_compat(self.h, int(flags)))

@@ -67,6 +67,8 @@ struct nwb_ctx {
 	DevBuf d_cnt[MAXC], d_segoff[MAXC], d_seg_s[MAXC], d_seg_sep[MAXC], d_Ls[MAXC], d_Lsep[MAXC], d_Ltrig[MAXC];
 	DevBuf d_rows, d_rowoff, d_matsz, d_matoff, d_mat, d_cols, d_cols2, d_keep, d_keeppos, d_misc;
 	DevBuf d_spill, d_status, d_spilloff[MAXC], d_spillseg[MAXC], d_cells;
+	DevBuf d_hrow, d_hsrc, d_hout;   // automatic histograms: per-row / per-source scratch, compact sample
+	int hist_cat = -1, hist_k = -1;  // the (catalogue, magnitude) whose 'possible' marks d_hsrc holds
 	size_t entries_cap = 0;
 	unsigned long long spill_cap = 0;
 	long long *h_status = nullptr;   // pinned
@@ -441,7 +443,8 @@ void nwb_destroy(nwb_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *single[] = {&ctx->d_tables, &ctx->d_prim, &ctx->d_red, &ctx->d_bands, &ctx->d_cellcnt, &ctx->d_cstart,
 		&ctx->d_entries, &ctx->d_cub, &ctx->d_pairs, &ctx->d_paircount, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_matsz,
-		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc, &ctx->d_spill, &ctx->d_status, &ctx->d_cells};
+		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc, &ctx->d_spill, &ctx->d_status, &ctx->d_cells,
+		&ctx->d_hrow, &ctx->d_hsrc, &ctx->d_hout};
 	for (DevBuf *b : single) release(*b);
 	for (int c = 0; c < MAXC; c++) {
 		release(ctx->d_cnt[c]); release(ctx->d_segoff[c]); release(ctx->d_seg_s[c]); release(ctx->d_seg_sep[c]);
@@ -1131,6 +1134,113 @@ int nwb_stats(nwb_ctx *ctx, int64_t *out4)
 {
 	if (!ctx || !out4) return NWB_ERR_ARG;
 	for (int k = 0; k < 4; k++) out4[k] = ctx->stats[k];
+	return NWB_OK;
+}
+
+// ---- N1: automatic magnitude histograms ---------------------------------------------------------------------
+int nwb_maghist_select(nwb_ctx *ctx, int c, int k, int by_radius, double thr_select, double thr_possible, int weights_cli,
+	int64_t *nselected, int64_t *counts3, double *minmax2)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	if (c < 1 || c >= ctx->res_ncat) return fail(ctx, NWB_ERR_ARG, "catalogue index out of range");
+	if (k < 0 || k >= ctx->cat[c].m) return fail(ctx, NWB_ERR_ARG, "magnitude column out of range");
+	CU(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const int64_t R = ctx->nrows, n = ctx->cat[c].n;
+	if (R >= 0x7f7f7f7fll) return fail(ctx, NWB_ERR_ARG, "table too long for the histogram selection");
+	const double *mag = ctx->cat[c].mags + (size_t) k * n;
+	// per-row scratch: flag bytes | isel | idef | selpos | defpos | W
+	const size_t Rp = ((size_t) R + 63) / 64 * 64;
+	ENSURE(ctx->d_hrow, Rp + 4 * Rp * sizeof(int) + Rp * sizeof(double) + 256);
+	unsigned char *flag = (unsigned char *) ctx->d_hrow.p;
+	int *isel = (int *) (flag + Rp), *idef = isel + Rp, *selpos = idef + Rp, *defpos = selpos + Rp;
+	double *W = (double *) (defpos + Rp);
+	// per-source scratch: first | selflag | selrank | possible bytes | stats
+	const size_t np_ = ((size_t) n + 63) / 64 * 64;
+	ENSURE(ctx->d_hsrc, 3 * (np_ + 64) * sizeof(int) + np_ + 64 + 8 * sizeof(unsigned long long));
+	int *first = (int *) ctx->d_hsrc.p, *selflag = first + np_ + 64, *selrank = selflag + np_ + 64;
+	unsigned char *possible = (unsigned char *) (selrank + np_ + 64);
+	unsigned long long *stats = (unsigned long long *) (possible + np_ + 64);
+	CU(cudaMemsetAsync(first, 0x7f, (np_ + 64) * sizeof(int), st));      // 0x7f7f7f7f: any real position is smaller
+	CU(cudaMemsetAsync(possible, 0, np_ + 64, st));
+	CU(cudaMemsetAsync(selflag, 0, (np_ + 64) * sizeof(int), st));
+	unsigned long long init[5] = {0, 0, 0, ~0ull, 0};
+	CU(cudaMemcpyAsync(stats, init, sizeof(init), cudaMemcpyHostToDevice, st));
+	const double *sw = by_radius ? nullptr : (const double *) ctx->cols.dist_post;
+	if (R > 0) {
+		LAUNCH(ctx, k_hist_flags, grid_for(R, 256), 256, (long long) R, (const long long *) ctx->cols.idx[c],
+			(const double *) ctx->cols.sepmax, (const double *) ctx->cols.dist_post, by_radius, thr_select, thr_possible, flag, isel, idef);
+		{ int r = scan_int(ctx, isel, selpos, R); if (r) return r; }
+		{ int r = scan_int(ctx, idef, defpos, R); if (r) return r; }
+		LAUNCH(ctx, k_hist_mark, grid_for(R, 256), 256, (long long) R, (const long long *) ctx->cols.idx[c], (const unsigned char *) flag,
+			(const int *) selpos, (const int *) defpos, sw, weights_cli, first, possible, W);
+	}
+	if (n > 0) {
+		LAUNCH(ctx, k_hist_sources, grid_for(n, 256), 256, (long long) n, mag, (const int *) first, (const unsigned char *) possible, selflag, stats);
+		{ int r = scan_int(ctx, selflag, selrank, n + 1); if (r) return r; }   // selflag[n] == 0: selrank[n] is the total
+	}
+	if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocDefault));
+	long long *hs = ctx->h_status;
+	CU(cudaMemcpyAsync(hs + 48, stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	hs[47] = 0;
+	if (n > 0) CU(cudaMemcpyAsync(hs + 47, selrank + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	const int64_t nsel = (int64_t) (int) hs[47];
+	ENSURE(ctx->d_hout, (size_t) (2 * std::max<int64_t>(nsel, 1) + 2 * MAXB + 8) * sizeof(double));   // + edges / counts of nwb_maghist_count
+	double *out = (double *) ctx->d_hout.p;
+	if (nsel > 0)
+		LAUNCH(ctx, k_hist_gather, grid_for(n, 256), 256, (long long) n, mag, (const int *) first, (const int *) selflag,
+			(const int *) selrank, (const double *) (sw ? W : nullptr), out, out + nsel);
+	ctx->hist_cat = c; ctx->hist_k = k;
+	ctx->stats[0] = nsel;
+	if (nselected) *nselected = nsel;
+	if (counts3) { counts3[0] = hs[48]; counts3[1] = hs[49]; counts3[2] = hs[50]; }
+	if (minmax2) {
+		for (int j = 0; j < 2; j++) {
+			unsigned long long u = (unsigned long long) hs[51 + j];
+			u ^= (u >> 63) ? 0x8000000000000000ull : ~0ull;
+			memcpy(&minmax2[j], &u, 8);
+		}
+		if (hs[49] == 0) minmax2[0] = minmax2[1] = NAN;
+	}
+	return NWB_OK;
+}
+
+int nwb_maghist_sample(nwb_ctx *ctx, int64_t nselected, double *mag_host, double *weight_host)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (ctx->hist_cat < 0 || nselected != ctx->stats[0]) return fail(ctx, NWB_ERR_STATE, "nwb_maghist_select first");
+	if (nselected <= 0) return NWB_OK;
+	CU(cudaSetDevice(ctx->device));
+	const double *out = (const double *) ctx->d_hout.p;
+	CU(cudaMemcpyAsync(mag_host, out, nselected * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(weight_host, out + nselected, nselected * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return NWB_OK;
+}
+
+int nwb_maghist_count(nwb_ctx *ctx, int c, int k, int nbins, const double *edges, int64_t *counts)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (ctx->hist_cat != c || ctx->hist_k != k) return fail(ctx, NWB_ERR_STATE, "nwb_maghist_select for this column first");
+	if (nbins < 1 || nbins > MAXB) return fail(ctx, NWB_ERR_ARG, "1.." + std::to_string(MAXB) + " bins");
+	CU(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const int64_t n = ctx->cat[c].n;
+	const size_t np_ = ((size_t) n + 63) / 64 * 64;
+	const unsigned char *possible = (const unsigned char *) ((int *) ctx->d_hsrc.p + 3 * (np_ + 64));
+	ENSURE(ctx->d_hout, (size_t) (2 * std::max<int64_t>(ctx->stats[0], 1) + 2 * MAXB + 8) * sizeof(double));
+	// the compact sample may still be wanted: put the edges / counts behind it
+	double *d_edges = (double *) ctx->d_hout.p + 2 * std::max<int64_t>(ctx->stats[0], 1);
+	unsigned long long *d_counts = (unsigned long long *) (d_edges + MAXB + 1);
+	CU(cudaMemcpyAsync(d_edges, edges, (size_t) (nbins + 1) * 8, cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(d_counts, 0, (size_t) nbins * 8, st));
+	if (n > 0)
+		LAUNCH(ctx, k_hist_count, (int) std::min<int64_t>((n + 255) / 256, 148 * 8), 256, (long long) n, ctx->cat[c].mags + (size_t) k * n,
+			possible, nbins, (const double *) d_edges, d_counts);
+	CU(cudaMemcpyAsync(counts, d_counts, (size_t) nbins * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
 	return NWB_OK;
 }
 

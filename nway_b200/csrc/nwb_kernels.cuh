@@ -1412,6 +1412,119 @@ __global__ void k_minmax(long long n, const double *__restrict__ x, double *__re
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// N1: automatic magnitude histograms (nwaylib/__init__.py:324-366, nway.py:455-503) -- the selection half on the device
+// ---------------------------------------------------------------------------------------------------------
+// per row: bit 0 = the catalogue has a counterpart in this row, bit 1 = row selected as a secure match, bit 2 = row
+// "possible" (its source is removed from the field-source histogram); isel / idef feed the two prefix sums
+__global__ void k_hist_flags(long long nrows, const long long *__restrict__ res, const double *__restrict__ sepmax,
+	const double *__restrict__ dist_post, int by_radius, double thr_sel, double thr_possible,
+	unsigned char *__restrict__ flag, int *__restrict__ isel, int *__restrict__ idef)
+{
+	long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrows) return;
+	const bool def = res[r] != -1;
+	const double x = by_radius ? sepmax[r] : dist_post[r];
+	const bool sel = def && (by_radius ? x < thr_sel : x > thr_sel);
+	const bool pos = def && (by_radius ? x < thr_possible : x > thr_possible);
+	flag[r] = (unsigned char) ((def ? 1 : 0) | (sel ? 2 : 0) | (pos ? 4 : 0));
+	isel[r] = sel;
+	idef[r] = def;
+}
+
+// numpy.unique(res[selection], return_index=True): the first occurrence of a source inside the selected sub-array is
+// the smallest selected-position -> atomicMin.  Weights: the reference compresses them by res_defined (API,
+// __init__.py:337) or by the selection (command-line program, nway.py:471) and then indexes them with the
+// selected-positions -- W holds that compressed array.
+__global__ void k_hist_mark(long long nrows, const long long *__restrict__ res, const unsigned char *__restrict__ flag,
+	const int *__restrict__ selpos, const int *__restrict__ defpos, const double *__restrict__ sw, int weights_cli,
+	int *__restrict__ first, unsigned char *__restrict__ possible, double *__restrict__ W)
+{
+	long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrows) return;
+	const unsigned f = flag[r];
+	if (!(f & 1u)) return;
+	const long long s = res[r];
+	if (sw && !weights_cli) W[defpos[r]] = sw[r];
+	if (f & 2u) {
+		atomicMin(&first[s], selpos[r]);
+		if (sw && weights_cli) W[selpos[r]] = sw[r];
+	}
+	if (f & 4u) possible[s] = 1;
+}
+
+// per source of the catalogue: selected?  field source (finite magnitude, not "possible")?  min / max of the field
+// sources' magnitudes (order-preserving integer images, as in k_prim_prep) and the three counts the reference logs
+__global__ void k_hist_sources(long long n, const double *__restrict__ mag, const int *__restrict__ first,
+	const unsigned char *__restrict__ possible, int *__restrict__ selflag, unsigned long long *__restrict__ stats
+	/* [0] possible, [1] others, [2] valid, [3] min key, [4] max key; zeroed except [3] = ~0 */)
+{
+	long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long npos = 0, noth = 0, nval = 0, kmin = ~0ull, kmax = 0ull;
+	if (s < n) {
+		double m = mag[s];
+		bool valid = isfinite(m) && m != -99.0;
+		bool pos = possible[s] != 0;
+		selflag[s] = first[s] != 0x7f7f7f7f;   // the memset pattern = never selected
+		npos = pos; nval = valid;
+		if (valid && !pos) {
+			noth = 1;
+			unsigned long long u = (unsigned long long) __double_as_longlong(m);
+			u ^= (u >> 63) ? ~0ull : 0x8000000000000000ull;
+			kmin = kmax = u;
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		npos += __shfl_xor_sync(NWB_FULL, npos, o);
+		noth += __shfl_xor_sync(NWB_FULL, noth, o);
+		nval += __shfl_xor_sync(NWB_FULL, nval, o);
+		unsigned long long a = __shfl_xor_sync(NWB_FULL, kmin, o), b = __shfl_xor_sync(NWB_FULL, kmax, o);
+		kmin = a < kmin ? a : kmin;
+		kmax = b > kmax ? b : kmax;
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (npos) atomicAdd(stats + 0, npos);
+		if (noth) atomicAdd(stats + 1, noth);
+		if (nval) atomicAdd(stats + 2, nval);
+		if (noth) { atomicMin(stats + 3, kmin); atomicMax(stats + 4, kmax); }
+	}
+}
+
+// the selected sources in ascending index order (= numpy.unique's order): magnitude and weight
+__global__ void k_hist_gather(long long n, const double *__restrict__ mag, const int *__restrict__ first,
+	const int *__restrict__ selflag, const int *__restrict__ selrank, const double *__restrict__ W,
+	double *__restrict__ out_mag, double *__restrict__ out_w)
+{
+	long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n || !selflag[s]) return;
+	double m = mag[s];
+	out_mag[selrank[s]] = m == -99.0 ? nan("") : m;
+	out_w[selrank[s]] = W ? W[first[s]] : 1.0;
+}
+
+// numpy.histogram(mag[others], bins=edges): counts per bin, last bin closed on the right
+__global__ void k_hist_count(long long n, const double *__restrict__ mag, const unsigned char *__restrict__ possible,
+	int nbins, const double *__restrict__ edges, unsigned long long *__restrict__ counts)
+{
+	__shared__ unsigned int sc[MAXB];
+	__shared__ double se[MAXB + 1];
+	for (int k = threadIdx.x; k < nbins; k += blockDim.x) sc[k] = 0;
+	for (int k = threadIdx.x; k <= nbins; k += blockDim.x) se[k] = edges[k];
+	__syncthreads();
+	for (long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (long long) gridDim.x * blockDim.x) {
+		double m = mag[s];
+		if (!(isfinite(m) && m != -99.0) || possible[s]) continue;
+		if (!(m >= se[0] && m <= se[nbins])) continue;
+		int k = 0;
+		for (int j = 1; j < nbins; j++)
+			if (se[j] <= m) k = j;
+		atomicAdd(&sc[k], 1u);
+	}
+	__syncthreads();
+	for (int k = threadIdx.x; k < nbins; k += blockDim.x)
+		if (sc[k]) atomicAdd(counts + k, (unsigned long long) sc[k]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // a13 truncation + element-wise surface
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_keep_flags(long long n, const double *__restrict__ p_i, double min_prob, int *__restrict__ keep)

@@ -1,6 +1,10 @@
-"""Magnitude-prior histograms: host side of the path (they are <= 17-bin tables; the per-row lookup runs on
-the GPU, see nwb_set_maghist).  Mirrors nwaylib/magnitudeweights.py:18-23,74-118 and the selection logic of
-nwaylib/__init__.py:324-375.  Row N1 of SURVEY.md 8f (building these on the device) is future work."""
+"""Magnitude-prior histograms.  The per-row lookup runs on the GPU (nwb_set_maghist); so does the selection of the
+secure counterparts / field sources for the automatic histograms and the counting of the field sources
+(auto_histogram_device: nwb_maghist_select / _count) -- what stays on the host is the <= 17-bin
+table itself: the quantile bins of a sample of a few thousand magnitudes, with the reference's own numpy / scipy
+calls so that the bin edges are bit-identical.  Mirrors nwaylib/magnitudeweights.py:18-23,74-118 and the selection
+logic of nwaylib/__init__.py:324-375; auto_histogram is the all-host version of the same (kept for callers that hold
+the columns on the host; the product path uses the device version)."""
 import numpy
 import scipy.interpolate
 
@@ -83,3 +87,39 @@ def auto_histogram(res, magvals, separation_max, dist_post, mag_include_radius, 
 	mask_sel = ~numpy.logical_or(numpy.isnan(mag_sel), numpy.isinf(mag_sel))
 	bins, hist_sel, hist_all = adaptive_histograms(magvals[mask_others], mag_sel[mask_sel], weights=rows_weights[mask_sel])
 	return bins, hist_sel, hist_all, int(mask_sel.sum()), len(rows_possible), int(mask_others.sum())
+
+
+def auto_histogram_device(ctx, c, k, magdtype, mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue, cli=False):
+	"""auto_histogram() with the row / catalogue-sized work on the device: the selection, first-occurrence unique,
+	weight indexing and the field-source histogram run in nwb_maghist_select / nwb_maghist_count; the host only sees
+	the compact sample of selected sources.  magdtype: dtype of the caller's magnitude column (the reference bins in
+	that dtype: float32 quantile edges differ from float64 ones).  Same return value as auto_histogram."""
+	if mag_include_radius is not None:
+		mag_sel, w, (npossible, nothers, nvalid), (lo, hi) = ctx.maghist_select(c, k, True, mag_include_radius, mag_exclude_radius, cli)
+	else:
+		mag_sel, w, (npossible, nothers, nvalid), (lo, hi) = ctx.maghist_select(c, k, False, magauto_post_single_minvalue, 0.01, cli)
+	assert len(mag_sel) > 0, 'No magnitude values within radius.'
+	magdtype = numpy.dtype(magdtype)
+	if magdtype.kind != 'f':
+		magdtype = numpy.dtype(float)
+	mag_sel = mag_sel.astype(magdtype)   # lossless: the device column holds the caller's values widened to fp64
+	ok = ~numpy.logical_or(numpy.isnan(mag_sel), numpy.isinf(mag_sel))
+	mag_sel, weights = mag_sel[ok], w[ok]
+	# adaptive_histograms() with the histogram of the field sources counted on the device
+	order = numpy.argsort(mag_sel)
+	sorted_sel = mag_sel[order]
+	cum = numpy.cumsum(weights[order]) / numpy.sum(weights)
+	cum[0] = 0
+	cum[-1] = 1
+	quantile = scipy.interpolate.interp1d(cum, sorted_sel)
+	x = numpy.unique(quantile(numpy.linspace(0, 1, 15)))
+	lo, hi = magdtype.type(lo), magdtype.type(hi)
+	if x[-1] < hi:
+		x = numpy.asarray(list(x) + [hi + 1])
+	if x[0] > lo:
+		x = numpy.asarray([lo - 1] + list(x))
+	hist_sel, bins = numpy.histogram(mag_sel, bins=x, density=True, weights=weights)
+	n = ctx.maghist_count(c, k, bins)
+	db = numpy.array(numpy.diff(bins), float)
+	hist_all = n / db / n.sum()   # numpy.histogram(..., density=True)
+	return bins, hist_sel, hist_all, int(ok.sum()), npossible, nothers
