@@ -391,6 +391,11 @@ int layout_columns(nwb_ctx *ctx, DevBuf &buf, int64_t R, int nc, int nmag, Colum
 template <int NC>
 int launch_rows(nwb_ctx *ctx, const RowParams &rp, bool fuse, int grid)
 {
+	if (rp.small_t > 0) {   // sparse primaries: one thread each
+		int sgrid = (rp.np + 127) / 128;
+		if (fuse) LAUNCH(ctx, (k_rows_small<NC, true>), sgrid, 128, rp);
+		else LAUNCH(ctx, (k_rows_small<NC, false>), sgrid, 128, rp);
+	}
 	if (fuse) LAUNCH(ctx, (k_rows<NC, true>), grid, 256, rp);
 	else LAUNCH(ctx, (k_rows<NC, false>), grid, 256, rp);
 	return NWB_OK;
@@ -399,6 +404,7 @@ int launch_rows(nwb_ctx *ctx, const RowParams &rp, bool fuse, int grid)
 template <int NC>
 int launch_count(nwb_ctx *ctx, const RowParams &rp, long long *rows, int grid)
 {
+	if (rp.small_t > 0) LAUNCH(ctx, (k_count_rows_small<NC>), (rp.np + 127) / 128, 128, rp, rows);
 	LAUNCH(ctx, (k_count_rows<NC>), grid, 256, rp, rows);
 	return NWB_OK;
 }
@@ -646,6 +652,7 @@ static int fill_row_params(nwb_ctx *ctx, const PairStore *stores, int64_t first,
 	}
 	rp.ell = ell ? 1 : 0;
 	rp.sep_f32 = (ctx->compat & NWB_COMPAT_SEP_F32) ? 1 : 0;
+	rp.small_t = SMALL_T;
 	for (int k = 0; k < MAXP; k++) rp.pair_radius[k] = ctx->prefilter_on ? std::min(ctx->radius, ctx->prefilter[k]) : ctx->radius;
 	rp.T = (const ConstTables *) ctx->d_tables.p;
 	rp.S1 = stores[1];
@@ -716,7 +723,9 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			if (!(k & 1)) red[k] = -red[k];
 		}
 		HostGrid HG;
-		long long max_cells = 4ll << 20;
+		// cells: ~16 per primary is plenty (each primary occupies 1-9 of them), and the 32-byte records of at most 2 M
+		// cells (64 MB) stay in the 126 MB L2 next to the streamed catalogue
+		long long max_cells = std::min<long long>(2ll << 20, std::max<long long>(1ll << 16, 16 * (long long) np));
 		build_grid(red, rb_ins, rb_ins, max_cells, HG);
 		pretest_constants(HG, rb_ins);
 		size_t nb = (size_t) HG.g.nbands;
@@ -729,6 +738,17 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		ctx->geom_G = HG.g;
 		ctx->geom_rb = rb; ctx->geom_np = np; ctx->geom_first = first;
 		ctx->geom_valid = true;
+	}
+	{
+		// cell records, then (sparse primaries only) the occupancy bitmap behind them
+		Grid &g = ctx->geom_G;
+		const size_t rec_bytes = ((size_t) g.ncells * sizeof(CellRec) + 255) / 256 * 256;
+		const size_t bit_bytes = ((size_t) g.ncells / 32 + 2) * sizeof(unsigned);
+		ENSURE(ctx->d_cells, rec_bytes + bit_bytes);
+		const double s_deg = 1.0 / g.inv_h;
+		const double reach = 1.0 + 2.0 * rb_ins / s_deg;   // cells a primary's box spans along one axis, on average
+		const bool sparse = (double) np * reach * reach < 0.5 * (double) g.ncells;
+		g.bits = sparse ? (const unsigned *) ((const char *) ctx->d_cells.p + rec_bytes) : nullptr;
 	}
 	const Grid G = ctx->geom_G;
 	// one zero-initialised block: cell counters | per-catalogue match counters | scalar counters
@@ -783,9 +803,8 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		{ int r = scan_int(ctx, d_cellcnt, d_cstart, (int64_t) ncell1); if (r) return r; }
 		LAUNCH(ctx, (k_prim_cells<true>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) d_cstart,
 			d_entries, d_pentries, (long long) ctx->entries_cap);
-		ENSURE(ctx->d_cells, (size_t) G.ncells * sizeof(CellRec));
 		LAUNCH(ctx, k_cell_records, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cstart,
-			(const PEntry *) d_pentries, (long long) ctx->entries_cap, (CellRec *) ctx->d_cells.p);
+			(const PEntry *) d_pentries, (long long) ctx->entries_cap, (CellRec *) ctx->d_cells.p, (unsigned *) G.bits);
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[1], st));
 
 		// ---- K1: stream the secondaries ----------------------------------------------------------------
@@ -905,9 +924,12 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			ENSURE(ctx->d_Ltrig[c], std::max<size_t>(1, npair) * 3 * sizeof(double));
 			double *tr = (double *) ctx->d_Ltrig[c].p;
 			const long long *off = (const long long *) ctx->d_segoff[c].p;
-			if (npair)
-				LAUNCH(ctx, k_sort_lists, wgrid, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
+			if (npair) {
+				LAUNCH(ctx, k_sort_lists_small, pblocks, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
 					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair);
+				LAUNCH(ctx, k_sort_lists, wgrid, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
+					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair, SMALL_N);
+			}
 			L.off[c] = off;
 			L.s[c] = (const int *) ctx->d_Ls[c].p;
 			L.sep[c] = (const double *) ctx->d_Lsep[c].p;

@@ -39,6 +39,9 @@ struct Grid {
 	const float *kx;        // [nbands] packed pre-test: degrees of true angle per cell width, rounded down; 0 = dec only
 	float hdeg;             // band height in degrees
 	float rr2p;             // squared radius of the packed pre-test (rr2's margins + the quantisation of the entries)
+	const unsigned *bits;   // one bit per cell: any primary registered?  nullptr when most cells are occupied anyway.  A sparse
+	                        // primary catalogue leaves ~97 % of the cells empty; the bitmap (ncells / 8 bytes: L1 / L2 resident)
+	                        // answers those without touching the 32-byte cell records
 };
 
 // 16 bytes, one load: one primary as seen from one cell, for the fp32 flat PRE-test
@@ -492,10 +495,13 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 					const double xcells = x * B.inv_w;
 					int ic = __double2int_rd(xcells);
 					ic = ic >= B.nra ? B.nra - 1 : (ic < 0 ? 0 : ic);
-					const Sector32 cr = ldg_sector(cells + B.base + ic);   // one sector, one request
-					ecnt = (int) (unsigned) cr.q[0];
-					estart = (int) (cr.q[0] >> 32);
-					e0 = cr.q[1]; e1 = cr.q[2]; e2 = cr.q[3];
+					const int cell = B.base + ic;
+					if (!G.bits || (__ldg(G.bits + (cell >> 5)) >> (cell & 31) & 1u)) {
+						const Sector32 cr = ldg_sector(cells + cell);   // one sector, one request
+						ecnt = (int) (unsigned) cr.q[0];
+						estart = (int) (cr.q[0] >> 32);
+						e0 = cr.q[1]; e1 = cr.q[2]; e2 = cr.q[3];
+					}
 					xr = (float) (xcells - (double) ic);
 					yr = (float) (t - (double) b);
 				}
@@ -539,12 +545,17 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 
 // cell records from the cell lists (see struct CellRec)
 __global__ void k_cell_records(long long ncells, const int *__restrict__ cstart, const PEntry *__restrict__ pentries,
-	long long entries_cap, CellRec *__restrict__ cells)
+	long long entries_cap, CellRec *__restrict__ cells, unsigned *__restrict__ bits)
 {
 	long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= ncells) return;
 	if ((long long) cstart[ncells] > entries_cap) return;
-	int s = cstart[c], cnt = cstart[c + 1] - s;
+	int s = 0, cnt = 0;
+	if (c < ncells) { s = cstart[c]; cnt = cstart[c + 1] - s; }
+	if (bits) {   // a warp covers 32 consecutive cells = one word of the bitmap
+		unsigned w = __ballot_sync(NWB_FULL, cnt > 0);
+		if ((threadIdx.x & 31) == 0 && c < ncells) bits[c >> 5] = w;
+	}
+	if (c >= ncells) return;
 	unsigned long long q[4] = {(unsigned long long) (unsigned) cnt | ((unsigned long long) (unsigned) s << 32), 0ull, 0ull, 0ull};
 	if (cnt > 0) {
 		const unsigned long long *pe = reinterpret_cast<const unsigned long long *>(pentries + s);
@@ -599,7 +610,7 @@ __global__ void k_spill_scatter(long long n, const SpillRec *__restrict__ recs, 
 // secondary-secondary separations.
 __global__ void k_sort_lists(int np, PairStore S, const long long *__restrict__ seg_off, int *__restrict__ L_s,
 	double *__restrict__ L_sep, const double *__restrict__ ra, const double *__restrict__ dec,
-	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat)
+	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat, int small_n)
 {
 	int lane = threadIdx.x & 31;
 	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -607,6 +618,7 @@ __global__ void k_sort_lists(int np, PairStore S, const long long *__restrict__ 
 	for (int p = warp; p < np; p += nwarps) {
 		long long lo = seg_off[p];
 		int n = S.cnt[p];
+		if (n <= small_n) continue;   // k_sort_lists_small's
 		for (int e = lane; e < n; e += 32) {
 			Slot16 me = store_get(S, p, e);
 			int rank = 0;
@@ -619,6 +631,43 @@ __global__ void k_sort_lists(int np, PairStore S, const long long *__restrict__ 
 			L_slat[lo + rank] = sl;
 			L_clat[lo + rank] = cl;
 		}
+	}
+}
+
+// the same for primaries with at most SMALL_N matches, one THREAD per primary (sparse all-sky matches: most primaries
+// have 0 or 1): insertion sort in registers
+constexpr int SMALL_N = 4;
+
+__global__ void k_sort_lists_small(int np, PairStore S, const long long *__restrict__ seg_off, int *__restrict__ L_s,
+	double *__restrict__ L_sep, const double *__restrict__ ra, const double *__restrict__ dec,
+	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat)
+{
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= np) return;
+	int n = S.cnt[p];
+	if (n == 0 || n > SMALL_N) return;
+	long long lo = seg_off[p];
+	Slot16 x[SMALL_N];
+#pragma unroll
+	for (int e = 0; e < SMALL_N; e++)
+		if (e < n) x[e] = store_get(S, p, e);
+#pragma unroll
+	for (int a = 1; a < SMALL_N; a++) {
+#pragma unroll
+		for (int b = a; b >= 1; b--) {
+			if (b < n && a < n && x[b].s < x[b - 1].s) { Slot16 t = x[b]; x[b] = x[b - 1]; x[b - 1] = t; }
+		}
+	}
+#pragma unroll
+	for (int e = 0; e < SMALL_N; e++) {
+		if (e >= n) break;
+		L_s[lo + e] = x[e].s;
+		L_sep[lo + e] = x[e].sep;
+		double sl, cl;
+		sincos(deg2rad_ref(dec[x[e].s]), &sl, &cl);
+		L_lon[lo + e] = deg2rad_ref(ra[x[e].s]);
+		L_slat[lo + e] = sl;
+		L_clat[lo + e] = cl;
 	}
 }
 
@@ -652,6 +701,7 @@ struct RowParams {
 	const double *err[MAXC];         // sigma columns (circular); elliptical: sigma_x | sigma_y | rho, each n[c] long
 	int ell;                         // elliptical mode (nway.py:346-354): every catalogue carries a triple
 	int sep_f32;                     // nway.py compatibility: separations / offsets pass through float32
+	int small_t;                     // primaries with at most this many candidate tuples are handled by k_rows_small (0 = off)
 	long long n[MAXC];               // catalogue sizes (stride of the error triple)
 	const double *ra[MAXC], *dec[MAXC];
 	const ConstTables *T;
@@ -720,6 +770,7 @@ __global__ void k_count_rows(RowParams R, long long *__restrict__ rows)
 			nl[c] = (int) (R.L.off[c][p + 1] - lo[c]);
 			T *= nl[c] + 1;
 		}
+		if (T <= R.small_t) continue;   // k_count_rows_small's
 		double *mat = R.mat + R.mat_off[p];
 		long long boff = 0;
 #pragma unroll
@@ -764,6 +815,67 @@ __global__ void k_count_rows(RowParams R, long long *__restrict__ rows)
 		count = warp_sum_ll(count);
 		if (lane == 0) rows[p] = count;
 	}
+}
+
+// the same for primaries with at most R.small_t candidate tuples, one THREAD per primary
+template <int NC>
+__global__ void k_count_rows_small(RowParams R, long long *__restrict__ rows)
+{
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= R.np) return;
+	int nl[NC];
+	long long lo[NC];
+	int T = 1;
+	nl[0] = 0; lo[0] = 0;
+#pragma unroll
+	for (int c = 1; c < NC; c++) {
+		lo[c] = R.L.off[c][p];
+		nl[c] = (int) (R.L.off[c][p + 1] - lo[c]);
+		T = T <= 8 ? T * (nl[c] + 1) : T;
+	}
+	if (T > R.small_t) return;
+	if (T == 1) { rows[p] = 1; return; }
+	double *mat = R.mat + R.mat_off[p];
+	long long boff = 0;
+#pragma unroll
+	for (int a = 1; a < NC; a++) {
+#pragma unroll
+		for (int b = a + 1; b < NC; b++) {
+			int na = nl[a], nb = nl[b];
+			for (int e = 0; e < na * nb; e++) {
+				int j = e / nb, k = e - j * nb;
+				long long ja = lo[a] + j, kb = lo[b] + k;
+				mat[boff + e] = sep_arcsec_ref(R.L.lon[a][ja], R.L.slat[a][ja], R.L.clat[a][ja],
+					R.L.lon[b][kb], R.L.slat[b][kb], R.L.clat[b][kb]);
+			}
+			boff += (long long) na * nb;
+		}
+	}
+	int count = 0;
+	for (int t = 0; t < T; t++) {
+		int dg[NC];
+		int rem = t;
+#pragma unroll
+		for (int c = NC - 1; c >= 1; c--) {
+			dg[c] = rem % (nl[c] + 1);
+			rem /= (nl[c] + 1);
+		}
+		bool ok = true;
+		long long bo = 0;
+#pragma unroll
+		for (int a = 1; a < NC; a++) {
+#pragma unroll
+			for (int b = a + 1; b < NC; b++) {
+				if (dg[a] > 0 && dg[b] > 0) {
+					double s = mat[bo + (long long) (dg[a] - 1) * nl[b] + (dg[b] - 1)];
+					ok = ok && (s < R.pair_radius[pair_index(a, b, NC)]);
+				}
+				bo += (long long) nl[a] * nl[b];
+			}
+		}
+		count += ok;
+	}
+	rows[p] = count;
 }
 
 // N == 2: rows per primary = matches + 1
@@ -925,6 +1037,7 @@ k_rows(RowParams R)
 			nl[c] = (int) (R.L.off[c][p + 1] - lo[c]);
 			ntup *= nl[c] + 1;
 		}
+		if (ntup <= R.small_t) continue;   // k_rows_small's
 		const long long rbase = R.row_off[p];
 		const double *mat = NC > 2 ? R.mat + R.mat_off[p] : nullptr;
 		const long long gp = R.first + p;
@@ -1021,6 +1134,150 @@ k_rows(RowParams R)
 			__syncwarp();
 			group_normalise(R, rbase, written, lane);
 		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2 for sparse primaries: ONE THREAD per primary with at most R.small_t (<= SMALL_T) candidate tuples.  An all-sky
+// match leaves ~99 % of the primaries with nothing but their no-counterpart row; a warp per primary (k_rows) then runs
+// one lane in 32 behind a chain of dependent loads.  Here 32 primaries share a warp, the stores of consecutive
+// primaries coalesce, and the group normalisation is a scalar loop over <= SMALL_T rows with the reference's formulas
+// (__init__.py:423-457).  Same rows, same order, same arithmetic as k_rows.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SMALL_T = 8;
+
+template <int NC, bool FUSE>
+__global__ void __launch_bounds__(128)
+k_rows_small(RowParams R)
+{
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= R.np) return;
+	const ConstTables *__restrict__ T = R.T;
+	int nl[NC];
+	long long lo[NC];
+	int ntup = 1;
+	nl[0] = 0; lo[0] = 0;
+#pragma unroll
+	for (int c = 1; c < NC; c++) {
+		lo[c] = R.L.off[c][p];
+		nl[c] = (int) (R.L.off[c][p + 1] - lo[c]);
+		ntup = ntup <= SMALL_T ? ntup * (nl[c] + 1) : ntup;
+	}
+	if (ntup > R.small_t) return;
+	const long long rbase = R.row_off[p];
+	const double *mat = NC > 2 ? R.mat + R.mat_off[p] : nullptr;
+	const long long gp = R.first + p;
+	double v[SMALL_T];
+	int nrow = 0;
+	for (int t = 0; t < ntup; t++) {
+		int dg[NC];
+		long long sidx[NC];
+		double sep[NC * (NC - 1) / 2];
+		double sig[NC];
+		unsigned present = 1u;
+		bool ok = true;
+		sidx[0] = gp;
+		int rem = t;
+#pragma unroll
+		for (int c = NC - 1; c >= 1; c--) {
+			dg[c] = rem % (nl[c] + 1);
+			rem /= (nl[c] + 1);
+		}
+#pragma unroll
+		for (int c = 1; c < NC; c++) {
+			if (dg[c] > 0) {
+				long long e = lo[c] + dg[c] - 1;
+				sidx[c] = R.L.s[c][e];
+				sep[pair_index(0, c, NC)] = R.L.sep[c][e];
+				present |= 1u << c;
+			} else {
+				sidx[c] = -1;
+				sep[pair_index(0, c, NC)] = nan("");
+			}
+		}
+		if (NC > 2) {
+			long long bo = 0;
+#pragma unroll
+			for (int a = 1; a < NC; a++) {
+#pragma unroll
+				for (int b = a + 1; b < NC; b++) {
+					double s = nan("");
+					if (dg[a] > 0 && dg[b] > 0) {
+						s = mat[bo + (long long) (dg[a] - 1) * nl[b] + (dg[b] - 1)];
+						ok = ok && (s < R.pair_radius[pair_index(a, b, NC)]);
+					}
+					sep[pair_index(a, b, NC)] = s;
+					bo += (long long) nl[a] * nl[b];
+				}
+			}
+		}
+		if (!ok) continue;
+		const long long row = rbase + nrow;
+		double smax = 0.0;
+		if (R.sep_f32) {
+#pragma unroll
+			for (int k = 0; k < NC * (NC - 1) / 2; k++) sep[k] = (double) (float) sep[k];
+		}
+#pragma unroll
+		for (int c = 0; c < NC; c++) R.C.idx[c][row] = sidx[c];
+#pragma unroll
+		for (int k = 0; k < NC * (NC - 1) / 2; k++) {
+			R.C.sep[k][row] = sep[k];
+			if (sep[k] > smax) smax = sep[k];
+		}
+		R.C.sepmax[row] = smax;
+		R.C.ncat[row] = __popc(present);
+		double lbf = 0.0;
+		if (present != 1u) {
+			if (R.ell) {
+				double esig[MAXC], esep[MAXP];
+				ell_prepare(R, present, sidx, esig, esep);
+				lbf = log_bf_ref<0>(T, NC, present, esig, esep);
+			} else {
+				sig[0] = R.err[0][gp];
+#pragma unroll
+				for (int c = 1; c < NC; c++)
+					if (present >> c & 1u) sig[c] = R.err[c][sidx[c]];
+				lbf = log_bf_ref<NC>(T, NC, present, sig, sep, R.sep_f32 != 0);
+			}
+		}
+		const unsigned smask = present >> 1;
+		const double prior = T->prior[smask], l10p = T->log10prior[smask];
+		R.C.lbf_u[row] = lbf;
+		R.C.lbf[row] = lbf;
+		R.C.dist_post[row] = posterior_ref(prior, l10p, lbf);
+		if (FUSE) {
+			double total = lbf + row_bias(R, row, sidx);
+			R.C.p_single[row] = posterior_ref(prior, l10p, total);
+			v[nrow] = total + l10p;
+		}
+		nrow++;
+	}
+	if (!FUSE) return;
+	// group normalisation, scalar (__init__.py:423-457)
+	double m_all = -INFINITY, m_rest = -INFINITY;
+	for (int k = 0; k < nrow; k++) {
+		m_all = fmax(m_all, v[k]);
+		if (k > 0) m_rest = fmax(m_rest, v[k]);
+	}
+	double s_all = 0.0, s_rest = 0.0;
+	for (int k = 0; k < nrow; k++) {
+		s_all += exp10(v[k] - m_all);
+		if (k > 0) s_rest += exp10(v[k] - m_rest);
+	}
+	const double bfsum = log10(s_all) + m_all;
+	const double bfsum1 = nrow > 1 ? log10(s_rest) + m_rest : 0.0;
+	const double p_any = 1 - exp10(v[0] - bfsum);
+	double best = 0.0;
+	for (int k = 1; k < nrow; k++) {
+		v[k] = exp10(v[k] - bfsum1);
+		best = fmax(best, v[k]);
+	}
+	v[0] = 0.0;
+	for (int k = 0; k < nrow; k++) {
+		R.C.p_i[rbase + k] = v[k];
+		R.C.p_any[rbase + k] = p_any;
+		R.C.flag[rbase + k] = (v[k] == best) ? 1 : (v[k] > R.ratio_secondary * best ? 2 : 0);
 	}
 }
 
