@@ -57,6 +57,7 @@ struct nwb_ctx {
 	double pc[MAXC];
 	int unrelated_mode = NWB_UNRELATED_API;
 	int compat = 0;
+	bool any_big = true;             // some primary has more candidate tuples than k_rows_small handles
 	double prefilter[MAXP];          // per catalogue pair, arcsec; +inf = none
 	bool prefilter_on = false;
 	ConstTables tables;   // host copy
@@ -389,23 +390,24 @@ int layout_columns(nwb_ctx *ctx, DevBuf &buf, int64_t R, int nc, int nmag, Colum
 }
 
 template <int NC>
-int launch_rows(nwb_ctx *ctx, const RowParams &rp, bool fuse, int grid)
+int launch_rows(nwb_ctx *ctx, const RowParams &rp, bool fuse, int grid, bool any_big = true)
 {
 	if (rp.small_t > 0) {   // sparse primaries: one thread each
 		int sgrid = (rp.np + 127) / 128;
 		if (fuse) LAUNCH(ctx, (k_rows_small<NC, true>), sgrid, 128, rp);
 		else LAUNCH(ctx, (k_rows_small<NC, false>), sgrid, 128, rp);
 	}
+	if (!any_big) return NWB_OK;   // no primary is left for the warp-per-primary kernel
 	if (fuse) LAUNCH(ctx, (k_rows<NC, true>), grid, 256, rp);
 	else LAUNCH(ctx, (k_rows<NC, false>), grid, 256, rp);
 	return NWB_OK;
 }
 
 template <int NC>
-int launch_count(nwb_ctx *ctx, const RowParams &rp, long long *rows, int grid)
+int launch_count(nwb_ctx *ctx, const RowParams &rp, long long *rows, int grid, bool any_big = true)
 {
 	if (rp.small_t > 0) LAUNCH(ctx, (k_count_rows_small<NC>), (rp.np + 127) / 128, 128, rp, rows);
-	LAUNCH(ctx, (k_count_rows<NC>), grid, 256, rp, rows);
+	if (any_big) LAUNCH(ctx, (k_count_rows<NC>), grid, 256, rp, rows);
 	return NWB_OK;
 }
 
@@ -914,8 +916,14 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			long long *off = (long long *) ctx->d_segoff[c].p;
 			{ int r = scan_int_to_ll(ctx, (const int *) d_cnt[c], off, np + 1); if (r) return r; }   // cnt[np] == 0
 			CU(cudaMemcpyAsync(hs + 16 + c, off + np, sizeof(long long), cudaMemcpyDeviceToHost, st));
+			// largest match count of any primary: decides whether the warp-per-primary sort is needed at all
+			int *d_maxcnt = (int *) (d_status + 40) + c;
+			CU(cudaMemsetAsync(d_maxcnt, 0, sizeof(int), st));
+			LAUNCH(ctx, k_max_int, (int) std::min<int64_t>((np + 255) / 256, 148 * 8), 256, (long long) np, (const int *) d_cnt[c], d_maxcnt);
 		}
+		CU(cudaMemcpyAsync(hs + 40, d_status + 40, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
+		const int *h_maxcnt = (const int *) (hs + 40);
 		for (int c = 1; c < nc; c++) {
 			size_t npair = (size_t) hs[16 + c];
 			ctx->stats[1] += (int64_t) npair;
@@ -927,8 +935,9 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			if (npair) {
 				LAUNCH(ctx, k_sort_lists_small, pblocks, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
 					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair);
-				LAUNCH(ctx, k_sort_lists, wgrid, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
-					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair, SMALL_N);
+				if (h_maxcnt[c] > SMALL_N)
+					LAUNCH(ctx, k_sort_lists, wgrid, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
+						ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair, SMALL_N);
 			}
 			L.off[c] = off;
 			L.s[c] = (const int *) ctx->d_Ls[c].p;
@@ -941,24 +950,29 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		ENSURE(ctx->d_matoff, (size_t) (np + 1) * sizeof(long long));
 		long long *d_matsz = (long long *) ctx->d_matsz.p, *d_matoff = (long long *) ctx->d_matoff.p;
 		CU(cudaMemsetAsync(d_matsz, 0, (size_t) (np + 1) * sizeof(long long), st));
-		LAUNCH(ctx, k_mat_sizes, pblocks, 256, (int) np, nc, L, d_matsz);
+		unsigned long long *d_maxtup = (unsigned long long *) (d_status + 44);
+		CU(cudaMemsetAsync(d_maxtup, 0, sizeof(unsigned long long), st));
+		LAUNCH(ctx, k_mat_sizes, pblocks, 256, (int) np, nc, L, d_matsz, d_maxtup);
 		{ int r = scan_ll(ctx, d_matsz, d_matoff, np + 1); if (r) return r; }
 		CU(cudaMemcpyAsync(hs + 24, d_matoff + np, sizeof(long long), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(hs + 26, d_maxtup, sizeof(long long), cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
 		long long mat_total = hs[24];
+		const bool any_big = (unsigned long long) hs[26] > (unsigned long long) SMALL_T;   // else every primary is a "small" one
+		ctx->any_big = any_big;
 		ENSURE(ctx->d_mat, std::max<size_t>(1, (size_t) mat_total) * sizeof(double));
 		rp.mat_off = d_matoff;
 		rp.mat = (double *) ctx->d_mat.p;
 		CU(cudaMemsetAsync(d_rows, 0, (size_t) (np + 1) * sizeof(long long), st));
 		int r = 0;
 		switch (nc) {
-			case 2: r = launch_count<2>(ctx, rp, d_rows, wgrid); break;
-			case 3: r = launch_count<3>(ctx, rp, d_rows, wgrid); break;
-			case 4: r = launch_count<4>(ctx, rp, d_rows, wgrid); break;
-			case 5: r = launch_count<5>(ctx, rp, d_rows, wgrid); break;
-			case 6: r = launch_count<6>(ctx, rp, d_rows, wgrid); break;
-			case 7: r = launch_count<7>(ctx, rp, d_rows, wgrid); break;
-			default: r = launch_count<8>(ctx, rp, d_rows, wgrid); break;
+			case 2: r = launch_count<2>(ctx, rp, d_rows, wgrid, any_big); break;
+			case 3: r = launch_count<3>(ctx, rp, d_rows, wgrid, any_big); break;
+			case 4: r = launch_count<4>(ctx, rp, d_rows, wgrid, any_big); break;
+			case 5: r = launch_count<5>(ctx, rp, d_rows, wgrid, any_big); break;
+			case 6: r = launch_count<6>(ctx, rp, d_rows, wgrid, any_big); break;
+			case 7: r = launch_count<7>(ctx, rp, d_rows, wgrid, any_big); break;
+			default: r = launch_count<8>(ctx, rp, d_rows, wgrid, any_big); break;
 		}
 		if (r) return r;
 		{ int r2 = scan_ll(ctx, d_rows, d_rowoff, np + 1); if (r2) return r2; }
@@ -985,19 +999,19 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		int r = 0;
 		switch (nc) {
 			case 2: {
-				if (generic) { r = launch_rows<2>(ctx, rp, fuse, wgrid); break; }
+				if (generic) { r = launch_rows<2>(ctx, rp, fuse, wgrid, ctx->any_big); break; }
 				int grid2 = (int) std::min<int64_t>((np + R2_WARPS - 1) / R2_WARPS, 148 * NWB_R2_GRID_PER_SM);
 				if (fuse && ctx->res_nmag == 0 && NWB_R2_SHARE) LAUNCH(ctx, (k_rows2<true, true>), grid2, R2_WARPS * 32, rp);
 				else if (fuse) LAUNCH(ctx, (k_rows2<true, false>), grid2, R2_WARPS * 32, rp);
 				else LAUNCH(ctx, (k_rows2<false, false>), grid2, R2_WARPS * 32, rp);
 				break;
 			}
-			case 3: r = launch_rows<3>(ctx, rp, fuse, wgrid); break;
-			case 4: r = launch_rows<4>(ctx, rp, fuse, wgrid); break;
-			case 5: r = launch_rows<5>(ctx, rp, fuse, wgrid); break;
-			case 6: r = launch_rows<6>(ctx, rp, fuse, wgrid); break;
-			case 7: r = launch_rows<7>(ctx, rp, fuse, wgrid); break;
-			default: r = launch_rows<8>(ctx, rp, fuse, wgrid); break;
+			case 3: r = launch_rows<3>(ctx, rp, fuse, wgrid, ctx->any_big); break;
+			case 4: r = launch_rows<4>(ctx, rp, fuse, wgrid, ctx->any_big); break;
+			case 5: r = launch_rows<5>(ctx, rp, fuse, wgrid, ctx->any_big); break;
+			case 6: r = launch_rows<6>(ctx, rp, fuse, wgrid, ctx->any_big); break;
+			case 7: r = launch_rows<7>(ctx, rp, fuse, wgrid, ctx->any_big); break;
+			default: r = launch_rows<8>(ctx, rp, fuse, wgrid, ctx->any_big); break;
 		}
 		if (r) return r;
 		CU(cudaEventRecord(ctx->kev[1], st));

@@ -509,6 +509,7 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 		}
 		// the inline entries: up to three fp32 pre-tests on the spot
 		const int ninl = min(ecnt, 3);
+		if (!__any_sync(NWB_FULL, ninl > 0)) continue;   // sparse primaries: most batches end here
 		k1_enqueue(M, ninl > 0 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e0), (int) i, (int) (e0 >> 32), r, d, lane, qn, A);
 		if (__any_sync(NWB_FULL, ninl > 1))
 			k1_enqueue(M, ninl > 1 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e1), (int) i, (int) (e1 >> 32), r, d, lane, qn, A);
@@ -740,15 +741,37 @@ __device__ __forceinline__ long long mat_block_offset(const int *nl, int c, int 
 }
 
 // sizes of the secondary-secondary separation scratch per primary
-__global__ void k_mat_sizes(int np, int ncat, Lists L, long long *__restrict__ sizes)
+// (+ the largest number of candidate tuples of any primary, so that the host can skip the warp-per-primary kernels
+// when every primary is handled by the one-thread-per-primary ones)
+__global__ void k_mat_sizes(int np, int ncat, Lists L, long long *__restrict__ sizes, unsigned long long *__restrict__ max_tuples)
 {
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= np) return;
-	long long tot = 0;
-	for (int a = 1; a < ncat; a++)
-		for (int b = a + 1; b < ncat; b++)
-			tot += (L.off[a][p + 1] - L.off[a][p]) * (L.off[b][p + 1] - L.off[b][p]);
-	sizes[p] = tot;
+	unsigned long long ntup = 0;
+	if (p < np) {
+		long long tot = 0;
+		ntup = 1;
+		for (int a = 1; a < ncat; a++) {
+			unsigned long long na = (unsigned long long) (L.off[a][p + 1] - L.off[a][p]);
+			ntup = ntup > (1ull << 40) ? ntup : ntup * (na + 1);
+			for (int b = a + 1; b < ncat; b++)
+				tot += (long long) na * (L.off[b][p + 1] - L.off[b][p]);
+		}
+		sizes[p] = tot;
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		unsigned long long y = __shfl_xor_sync(NWB_FULL, ntup, o);
+		ntup = y > ntup ? y : ntup;
+	}
+	if ((threadIdx.x & 31) == 0 && ntup > 1) atomicMax(max_tuples, ntup);
+}
+
+// largest element of an int array (match counts per primary)
+__global__ void k_max_int(long long n, const int *__restrict__ x, int *__restrict__ out /* zeroed */)
+{
+	int m = 0;
+	for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) m = max(m, x[i]);
+	m = __reduce_max_sync(NWB_FULL, m);
+	if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
 }
 
 // N >= 3: one warp per primary computes every secondary-secondary separation once and counts the tuples
