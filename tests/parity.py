@@ -48,7 +48,7 @@ def column_error(name, ref, got, rtol=None):
 	elif name.startswith('Separation'):
 		tol = 1e-9 + RTOL * np.abs(r)
 	else:
-		tol = np.where(np.abs(r) >= 1e-30, RTOL * np.abs(r), 1e-40)
+		tol = np.maximum(RTOL * np.abs(r), 1e-40)
 	worst = int(np.argmax(d - tol))
 	with np.errstate(divide='ignore', invalid='ignore'):
 		rel = np.where(r != 0, d / np.abs(r), 0.0)
