@@ -95,6 +95,32 @@ class ClockSampler(object):
 			'reasons': sorted(reasons), 'samples': len(samples), 'window': 'timed loop + e2e loop, nvidia-smi -lms 20'}
 
 
+def bind_near_gpu(local):
+	"""run this rank's host threads (and, by first touch, its pinned buffers) on the CPUs NVML reports as local to the
+	GPU: with one rank per GPU the host <-> device copies of the e2e loop otherwise cross the socket interconnect for
+	half of the ranks.  Best effort: returns a description, or None when nothing was changed."""
+	try:
+		import pynvml
+		import torch
+		pynvml.nvmlInit()
+		try:
+			pr = torch.cuda.get_device_properties(local)
+			h = pynvml.nvmlDeviceGetHandleByPciBusId(('%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+		except Exception:
+			h = pynvml.nvmlDeviceGetHandleByIndex(local)
+		ncpu = os.cpu_count() or 1
+		mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+		near = set(64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1)
+		allowed = os.sched_getaffinity(0)
+		target = near & allowed
+		if not target or target == allowed:
+			return None
+		os.sched_setaffinity(0, target)
+		return '%d of %d host cpus (NVML affinity of the GPU)' % (len(target), len(allowed))
+	except Exception:
+		return None
+
+
 def hbm_peak():
 	path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
 	if os.path.exists(path):
@@ -157,6 +183,7 @@ def run_b200(args):
 		raise SystemExit('bench.py: no CUDA device -- there is no CPU fallback for the product path')
 	torch.cuda.set_device(local)
 	dev = torch.device('cuda', local)
+	affinity = bind_near_gpu(local)
 	if world > 1:
 		dist.init_process_group('nccl', device_id=dev)
 
@@ -177,28 +204,44 @@ def run_b200(args):
 	ctx.set_params(RADIUS, tab['pc'], 0.5, _lib.UNRELATED_API)
 	ctx.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
 	ctx.set_primary_range(rank * n0, n0)
-	counts = torch.zeros(world, dtype=torch.int64, device=dev)
-	mine = torch.zeros(1, dtype=torch.int64, device=dev)
+	# the one exchange of the sharded path: per-rank row counts (what is needed to place each shard in the global table),
+	# gathered by NCCL straight from device memory.  It runs on a side stream, double-buffered, so that the next
+	# match does not queue behind the collective's latency; torch.cuda.synchronize() at the end of the timed region
+	# waits for the last one.
+	counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
+	mine = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(2)]
+	side = torch.cuda.Stream(device=dev) if world > 1 else None
+	copied = [torch.cuda.Event() for _ in range(2)]
+	gathered = [torch.cuda.Event() for _ in range(2)]
 
-	state = {'view': None}
+	state = {'view': None, 'k': 0}
 
 	def step():
-		rows = ctx.match(fuse_final=True)
+		# nwb_match_async: the whole match is enqueued without a host round trip (the row count stays on the device), so
+		# consecutive steps run back to back; match_wait() below collects the last one and checks its status words
+		ctx.match_async(fuse_final=True)
 		if world > 1:
-			# the one exchange of the sharded path: per-rank row counts, gathered by NCCL straight from the device
-			# word the match left behind (no host round trip)
-			if state['view'] is None:
-				state['view'] = torch.as_tensor(_lib.DeviceView(ctx.nrows_device_ptr(), 1), device=dev)
-			dist.all_gather_into_tensor(counts, state['view'])
-		return rows
+			b = state['k'] & 1
+			state['k'] += 1
+			stream.wait_event(gathered[b])          # the collective that last used this buffer is done
+			mine[b].copy_(state['view'])            # 8 bytes, before the next match overwrites the device word
+			copied[b].record(stream)
+			side.wait_event(copied[b])
+			with torch.cuda.stream(side):
+				dist.all_gather_into_tensor(counts[b], mine[b])
+				gathered[b].record(side)
 
 	def barrier():
 		if world > 1:
 			dist.barrier()
 		torch.cuda.synchronize()
 
+	rows = ctx.match(fuse_final=True)   # the first match of a context chooses the grid geometry and sizes the buffers
+	if world > 1:
+		state['view'] = torch.as_tensor(_lib.DeviceView(ctx.nrows_device_ptr(), 1), device=dev)
 	for _ in range(max(args.warmup, 3)):
-		rows = step()
+		step()
+	rows = ctx.match_wait()
 	barrier()
 	sampler = ClockSampler(local)
 	if rank == 0:
@@ -209,8 +252,9 @@ def run_b200(args):
 	e0.record(stream)
 	nsampled = 0
 	for it in range(args.steps):
-		rows = step()
-		if it % 8 == 7 or it == args.steps - 1:   # per-stage event times of that step (8 small API calls: not every step)
+		step()
+		if it % 32 == 31 or it == args.steps - 1:   # per-stage event times of that step: needs the step collected (one host sync)
+			rows = ctx.match_wait()
 			for k, v in ctx.timings().items():
 				acc[k] += v
 			nsampled += 1
@@ -229,7 +273,7 @@ def run_b200(args):
 	total_rows = int(r.item())
 	value = total_rows / (ms_step_max * 1e-3)
 	if world > 1:
-		assert int(counts.sum().item()) == total_rows, 'the gathered row counts do not add up'
+		assert int(counts[(state['k'] - 1) & 1].sum().item()) == total_rows, 'the gathered row counts do not add up'
 
 	# ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ------------------------------
 	names = [tables[0]['name'], tables[1]['name']]
@@ -354,7 +398,8 @@ def run_b200(args):
 		'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
 		'config': {'workload': 'C3 (BASELINE.json configs[2]): synthetic 2-cat, %d primaries per GPU x %d secondaries uniform on %.3g deg^2, r=5 arcsec, circular errors' % (n0, n1, args.scale),
 			'rows_per_gpu': rows, 'pairs_per_gpu': pairs, 'radius_arcsec': RADIUS, 'prior_completeness': COMPLETENESS,
-			'parallelism': 'primary rows sharded, %d rank(s); secondaries replicated; exchange = all-gather of row counts' % world,
+			'parallelism': 'primary rows sharded, %d rank(s); secondaries replicated; exchange = NCCL all-gather of row counts (side stream, overlaps the next match)' % world,
+			'stepping': 'nwb_match_async back to back, nwb_match_wait every 32 steps and at the end', 'cpu_affinity': affinity,
 			'l2': 'inputs (%.0f MB) and outputs (%.0f MB) per step exceed the 126 MB L2; no explicit flush' % (h2d / 1e6, d2h / 1e6),
 			'stage_ms': {k: acc[k] / nsampled for k in acc}, 'grid': stats,
 			'allgather_full_table_ms': allgather_ms},

@@ -122,6 +122,16 @@ int nwb_set_primary_range(nwb_ctx *ctx, int64_t first, int64_t count);
  * nrows receives R.  Rows stay in device memory. */
 int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows);
 
+/* The same match without the host round trip at its end, for callers that run one match after another on resident
+ * catalogues (a shard loop, the calibration loop of nway-calibrate-cutoff.py): nwb_match_async enqueues the whole
+ * pipeline on the context's stream and returns; the row count stays on the device (nwb_nrows_device_ptr).
+ * nwb_match_wait synchronises, checks the status words the kernels left (grid geometry of the previous match still
+ * valid, buffers big enough) and, if they say no, redoes the match step by step -- the result is always that of
+ * nwb_match.  When the pipeline cannot be enqueued blindly (first match of a context, three or more catalogues,
+ * elliptical errors) nwb_match_async simply runs nwb_match.  Results may be read only after nwb_match_wait. */
+int nwb_match_async(nwb_ctx *ctx, int fuse_final);
+int nwb_match_wait(nwb_ctx *ctx, int64_t *nrows);
+
 /* H3b+H4: magnitude bias lookup, p_single, per-primary log-sum-exp -> prob_has_match, prob_this_match,
  * match_flag (__init__._apply_magnitude_biasing lookup half + _compute_final_probabilities). */
 int nwb_finalize(nwb_ctx *ctx);

@@ -41,6 +41,8 @@ EXPORTS = {
 	'nwb_set_maghist': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
 	'nwb_set_primary_range': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]),
 	'nwb_match': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_int64_p]),
+	'nwb_match_async': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+	'nwb_match_wait': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
 	'nwb_finalize': (ctypes.c_int, [ctypes.c_void_p]),
 	'nwb_truncate': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_int64_p]),
 	'nwb_fetch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
@@ -195,6 +197,20 @@ class Context(object):
 	def match(self, fuse_final=True):
 		n = ctypes.c_int64(0)
 		rc = self.lib.nwb_match(self.h, 1 if fuse_final else 0, ctypes.byref(n))
+		if rc == NWB_ERR_EMPTY:
+			return 0
+		self.check(rc)
+		return n.value
+
+	def match_async(self, fuse_final=True):
+		"""enqueue a match on the context's stream without waiting for it (nwb_match_async); collect it with match_wait()"""
+		rc = self.lib.nwb_match_async(self.h, 1 if fuse_final else 0)
+		if rc != NWB_ERR_EMPTY:
+			self.check(rc)
+
+	def match_wait(self):
+		n = ctypes.c_int64(0)
+		rc = self.lib.nwb_match_wait(self.h, ctypes.byref(n))
 		if rc == NWB_ERR_EMPTY:
 			return 0
 		self.check(rc)

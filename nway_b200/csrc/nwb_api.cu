@@ -16,6 +16,9 @@ using namespace nwb;
 #ifndef NWB_R2_SHARE
 #define NWB_R2_SHARE 1
 #endif
+#ifndef NWB_CELL_FACTOR
+#define NWB_CELL_FACTOR 1.0   // smallest cell edge in units of the search radius (experiment knob; >= 1)
+#endif
 
 namespace {
 
@@ -86,6 +89,8 @@ struct nwb_ctx {
 	int timing_ncat = 0;
 
 	// result
+	bool pending = false;            // nwb_match_async enqueued a match that nwb_match_wait has not collected yet
+	int pending_fuse = 0;
 	bool matched = false, finalized = false;
 	int64_t nrows = 0, np = 0;
 	int ncols = 0;
@@ -149,6 +154,25 @@ int scan_int_to_ll(nwb_ctx *ctx, const int *in, long long *out, int64_t n)
 	CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, (int) n, ctx->stream));
 	ENSURE(ctx->d_cub, bytes);
 	CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, bytes, it, out, (int) n, ctx->stream));
+	return NWB_OK;
+}
+
+// rows per primary of a two-catalogue match = matches + the no-counterpart row; element np is the trailing 0
+struct RowsOfPrimary {
+	const int *cnt;
+	int np;
+	__host__ __device__ long long operator()(const int &p) const { return p < np ? (long long) cnt[p] + 1 : 0ll; }
+};
+
+// row_off[0 .. np] (row_off[np] = R) straight from the match counters: no separate "rows per primary" pass
+int scan_rows2(nwb_ctx *ctx, const int *cnt, long long *out, int64_t np)
+{
+	cub::CountingInputIterator<int> idx(0);
+	cub::TransformInputIterator<long long, RowsOfPrimary, cub::CountingInputIterator<int>> it(idx, RowsOfPrimary{cnt, (int) np});
+	size_t bytes = 0;
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, (int) np + 1, ctx->stream));
+	ENSURE(ctx->d_cub, bytes);
+	CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, bytes, it, out, (int) np + 1, ctx->stream));
 	return NWB_OK;
 }
 
@@ -512,6 +536,7 @@ int nwb_set_catalogue(nwb_ctx *ctx, int c, int ncat, int64_t n, const double *ra
 	S.set = true;
 	ctx->tables_dirty = true;
 	ctx->matched = ctx->finalized = false;
+	ctx->pending = false;   // a match still in flight belongs to the old catalogue: abandoned
 	// one positional error for the whole catalogue?  (lets the row kernels skip a random gather per row)
 	S.err_const = false;
 	if (n > 0 && err_kind == NWB_ERR_CIRCULAR) {
@@ -664,7 +689,7 @@ static int fill_row_params(nwb_ctx *ctx, const PairStore *stores, int64_t first,
 	return NWB_OK;
 }
 
-static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_cached)
+static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_cached, bool defer)
 {
 	const int nc = ctx->ncat;
 	if (nc < 2) return fail(ctx, NWB_ERR_ARG, "no catalogues");
@@ -681,6 +706,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	CU(cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
 	ctx->matched = ctx->finalized = false;
+	ctx->pending = false;
 	ctx->launches = 0;
 	int64_t first = ctx->first, np = ctx->count < 0 ? ctx->cat[0].n - ctx->first : ctx->count;
 	if (first + np > ctx->cat[0].n || np < 0) return fail(ctx, NWB_ERR_ARG, "primary range exceeds the catalogue");
@@ -708,9 +734,10 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	ENSURE(ctx->d_red, 8 * sizeof(double));
 	unsigned long long *d_red = (unsigned long long *) ctx->d_red.p;
 	CU(cudaMemsetAsync(d_red, 0, 6 * sizeof(unsigned long long), st));
-	LAUNCH(ctx, k_prim_prep, pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red);
 	const bool use_cached = allow_cached && ctx->geom_valid && ctx->geom_rb == rb && ctx->geom_np == np && ctx->geom_first == first;
 	if (!use_cached) {
+		LAUNCH(ctx, (k_prim_prep<false>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
+			Grid(), rb_ins, dra_eps, (int *) nullptr);
 		// the grid geometry is chosen on the host from the bounding box: one sync.  It is kept for the next match
 		// on this context, which only has to verify (on the device) that the box is still the same.
 		unsigned long long *raw = (unsigned long long *) (hs + 32);
@@ -728,7 +755,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		// cells: ~16 per primary is plenty (each primary occupies 1-9 of them), and the 32-byte records of at most 2 M
 		// cells (64 MB) stay in the 126 MB L2 next to the streamed catalogue
 		long long max_cells = std::min<long long>(2ll << 20, std::max<long long>(1ll << 16, 16 * (long long) np));
-		build_grid(red, rb_ins, rb_ins, max_cells, HG);
+		build_grid(red, rb_ins, rb_ins * NWB_CELL_FACTOR, max_cells, HG);
 		pretest_constants(HG, rb_ins);
 		size_t nb = (size_t) HG.g.nbands;
 		ENSURE(ctx->d_bands, nb * (sizeof(BandRec) + sizeof(float)) + 64);
@@ -758,11 +785,11 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	const size_t cnt_stride = ((size_t) np + 1 + 3) / 4 * 4;
 	const size_t zero_ints = (ncell1 + 3) / 4 * 4 + cnt_stride * (nc - 1) + 4 * MAXC;
 	ENSURE(ctx->d_cellcnt, zero_ints * sizeof(int));
-	ENSURE(ctx->d_cstart, ncell1 * sizeof(int));
-	int *d_cellcnt = (int *) ctx->d_cellcnt.p, *d_cstart = (int *) ctx->d_cstart.p;
+	int *d_cellcnt = (int *) ctx->d_cellcnt.p;
 	int *d_cnt[MAXC] = {nullptr};
 	for (int c = 1; c < nc; c++) d_cnt[c] = d_cellcnt + (ncell1 + 3) / 4 * 4 + cnt_stride * (c - 1);
 	unsigned long long *d_spillcount = (unsigned long long *) (d_cellcnt + (ncell1 + 3) / 4 * 4 + cnt_stride * (nc - 1));
+	int *d_etotal = (int *) (d_spillcount + 12);   // [0] overflow entries of the cell lists, [1] registrations
 
 	// slots per primary and catalogue: expected matches + 6 sigma (a uniform field almost never spills)
 	int Cs[MAXC] = {0};
@@ -794,19 +821,24 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	long long R = 0;
 	bool done = false, speculated = false;
 	for (int attempt = 0; !done && attempt < 4; attempt++) {
-		ENSURE(ctx->d_entries, ctx->entries_cap * (sizeof(Entry) + sizeof(PEntry)));
+		ENSURE(ctx->d_entries, ctx->entries_cap * sizeof(Entry));
 		ENSURE(ctx->d_spill, (size_t) ctx->spill_cap * (nc - 1) * sizeof(SpillRec));
 		Entry *d_entries = (Entry *) ctx->d_entries.p;
-		PEntry *d_pentries = (PEntry *) (d_entries + ctx->entries_cap);
 		SpillRec *d_spill = (SpillRec *) ctx->d_spill.p;
-		CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
-		LAUNCH(ctx, (k_prim_cells<false>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) nullptr,
-			(Entry *) nullptr, (PEntry *) nullptr, (long long) 0);
-		{ int r = scan_int(ctx, d_cellcnt, d_cstart, (int64_t) ncell1); if (r) return r; }
-		LAUNCH(ctx, (k_prim_cells<true>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (const int *) d_cstart,
-			d_entries, d_pentries, (long long) ctx->entries_cap);
-		LAUNCH(ctx, k_cell_records, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cstart,
-			(const PEntry *) d_pentries, (long long) ctx->entries_cap, (CellRec *) ctx->d_cells.p, (unsigned *) G.bits);
+		CellRec *d_cells = (CellRec *) ctx->d_cells.p;
+		if (attempt == 0 && use_cached) {
+			// known geometry: the primaries are counted into their cells by the preparation kernel itself
+			CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
+			LAUNCH(ctx, (k_prim_prep<true>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
+				G, rb_ins, dra_eps, d_cellcnt);
+		} else {
+			CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
+			LAUNCH(ctx, (k_prim_cells<false>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (CellRec *) nullptr,
+				(Entry *) nullptr, (const int *) nullptr, (long long) 0);
+		}
+		LAUNCH(ctx, k_cell_headers, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cellcnt, d_cells, (unsigned *) G.bits, d_etotal);
+		LAUNCH(ctx, (k_prim_cells<true>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, d_cells,
+			d_entries, (const int *) d_etotal, (long long) ctx->entries_cap);
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[1], st));
 
 		// ---- K1: stream the secondaries ----------------------------------------------------------------
@@ -832,17 +864,13 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			ka.P = P; ka.radius = ctx->prefilter_on ? std::min(ctx->radius, ctx->prefilter[pair_index(0, c, nc)]) : ctx->radius; ka.base = d_base + base_off[c]; ka.C = Cs[c]; ka.cnt = d_cnt[c];
 			ka.spill = d_spill + (size_t) ctx->spill_cap * (c - 1); ka.spill_cap = (unsigned long long) ctx->spill_cap;
 			ka.spill_count = d_spillcount + c;
-			LAUNCH(ctx, k_pairs, grid, K1_WARPS * 32, (long long) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_cstart,
-				(const CellRec *) ctx->d_cells.p, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
+			LAUNCH(ctx, k_pairs, grid, K1_WARPS * 32, (long long) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_etotal,
+				(const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
 			CU(cudaEventRecord(ctx->kev[2 * c + 1], st));
 		}
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[2], st));
-		if (!generic) {
-			CU(cudaMemsetAsync(d_rows + np, 0, sizeof(long long), st));
-			LAUNCH(ctx, k_rows_per_primary_2, pblocks, 256, (int) np, (const int *) d_cnt[1], d_rows);
-			{ int r = scan_ll(ctx, d_rows, d_rowoff, np + 1); if (r) return r; }
-		}
-		LAUNCH(ctx, k_collect_status, 1, 32, nc, (const int *) d_cstart + G.ncells, (const unsigned long long *) d_spillcount,
+		if (!generic) { int r = scan_rows2(ctx, (const int *) d_cnt[1], d_rowoff, np); if (r) return r; }
+		LAUNCH(ctx, k_collect_status, 1, 32, nc, (const int *) d_etotal, (const unsigned long long *) d_spillcount,
 			!generic ? (const long long *) d_rowoff + np : (const long long *) nullptr, (const unsigned long long *) d_red,
 			ctx->geom_key, d_status);
 		// speculative K2: if the table of the previous match was big enough, launch the row kernel right away; it
@@ -867,6 +895,15 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			speculated = true;
 		}
 		CU(cudaMemcpyAsync(hs, d_status, 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+		if (defer && speculated && use_cached && attempt == 0) {
+			// nwb_match_async: everything of this match is in the stream (the row kernel checks the status words on the
+			// device); nwb_match_wait looks at the same words on the host and redoes the match if they say no
+			CU(cudaEventRecord(ctx->ev[4], st));
+			CU(cudaEventRecord(ctx->ev[5], st));
+			ctx->pending = true;
+			ctx->pending_fuse = fuse_final;
+			return NWB_OK;
+		}
 		CU(cudaStreamSynchronize(st));
 		if (hs[9] != 0) {   // the primaries moved: the cached geometry is stale
 			ctx->geom_valid = false;
@@ -877,13 +914,11 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		for (int c = 1; c < nc; c++)
 			if ((unsigned long long) hs[c] > ctx->spill_cap) { ctx->spill_cap = (unsigned long long) hs[c] + 1024; done = false; }
 		R = hs[8];
-		ctx->stats[3] = hs[0];
+		ctx->stats[3] = hs[10];
 		if (speculated && !(done && hs[1] == 0 && R <= ctx->cols_cap_rows)) speculated = false;   // the kernel declined
 	}
 	if (!done) return fail(ctx, NWB_ERR_NOMEM, "grid / spill buffers kept overflowing");
 	ctx->stats[2] = G.ncells;
-	const Entry *d_entries = (const Entry *) ctx->d_entries.p;
-	(void) d_entries;
 
 	// ---- overflowed primaries (rare): spill records -> per-primary spill segments ------------------------
 	for (int c = 1; c < nc; c++) {
@@ -1035,9 +1070,49 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
 {
 	if (!ctx) return NWB_ERR_ARG;
-	int r = match_impl(ctx, fuse_final, nrows, true);
-	if (r == 1) r = match_impl(ctx, fuse_final, nrows, false);   // the cached grid geometry did not fit: rebuild it
+	int r = match_impl(ctx, fuse_final, nrows, true, false);
+	if (r == 1) r = match_impl(ctx, fuse_final, nrows, false, false);   // the cached grid geometry did not fit: rebuild it
 	return r;
+}
+
+int nwb_match_async(nwb_ctx *ctx, int fuse_final)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	int r = match_impl(ctx, fuse_final, nullptr, true, true);
+	if (r == 1) r = match_impl(ctx, fuse_final, nullptr, false, false);
+	return r;
+}
+
+int nwb_match_wait(nwb_ctx *ctx, int64_t *nrows)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (!ctx->pending) {   // nwb_match_async ran the match synchronously (first match of a context, N >= 3, ...)
+		if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match_wait: no match in flight");
+		if (nrows) *nrows = ctx->nrows;
+		return ctx->nrows == 0 ? fail(ctx, NWB_ERR_EMPTY, "No matches.") : NWB_OK;
+	}
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->pending = false;
+	const long long *hs = ctx->h_status;
+	const long long R = hs[8];
+	// the conditions the row kernel checked on the device (guard_ok): geometry still valid, overflow entries fit,
+	// nothing spilled, the table of the previous match is big enough
+	const bool ok = hs[9] == 0 && (size_t) hs[0] <= ctx->entries_cap && hs[1] == 0 && R <= ctx->cols_cap_rows;
+	if (!ok) return nwb_match(ctx, ctx->pending_fuse, nrows);
+	ctx->stats[1] = R - ctx->np;
+	ctx->stats[2] = ctx->geom_G.ncells;
+	ctx->stats[3] = hs[10];
+	ctx->res_ncat = ctx->ncat;
+	ctx->rp.guard = nullptr;
+	ctx->timing_dirty = true;
+	ctx->timing_ncat = ctx->ncat;
+	ctx->nrows = R;
+	ctx->matched = true;
+	ctx->finalized = ctx->pending_fuse != 0;
+	if (nrows) *nrows = R;
+	if (R == 0) return fail(ctx, NWB_ERR_EMPTY, "No matches.");
+	return NWB_OK;
 }
 
 static int refresh_timings(nwb_ctx *ctx)

@@ -151,10 +151,105 @@ struct CellRec {
 	unsigned long long q[4];
 };
 
+// Register one primary in every grid cell its (slightly inflated) search box overlaps.
+// FILL = false: cellcnt[cell] += 1.
+// FILL = true : take a slot of the cell by counting cellcnt back down (no second memset).  Slots 0..2 live INSIDE the
+// cell record (packed, see PEntry) and are written there directly; later slots go to the cell's overflow segment of
+// `entries`, whose start k_cell_headers put into the record.  Both passes enumerate the same (band, cell) pairs from the
+// same doubles, whichever thread layout (bslot, bstride) they use.
+template <bool FILL>
+__device__ __forceinline__ void prim_register(const Grid &G, const int i, const double d, const double rn, const double dra,
+	const double clat_i, const double rb_ins, const double dra_eps, const int bslot, const int bstride,
+	int *__restrict__ cellcnt, CellRec *cells, Entry *__restrict__ entries)
+{
+	int b0 = band_of(G, d - rb_ins), b1 = band_of(G, d + rb_ins);
+	b0 = max(b0, 0);
+	b1 = min(b1, G.nbands - 1);
+	Entry en;
+	bool have_en = false;
+	const double di = dra + dra_eps;
+	const double xp = wrap360(rn - G.ra_org);          // the primary along ra, from the grid origin
+	const double yp = (d - G.dec_lo) * G.inv_h;        // ... and in band heights
+	for (int b = b0 + bslot; b <= b1; b += bstride) {
+		BandRec B = load_band(G, b);
+		int n = B.nra;
+		int i0, cnt;
+		double cellw = G.ra_span / n;
+		const int ip = racell_of(B, xp);               // the primary's own cell in this band
+		const double xc = xp * B.inv_w - (double) ip;  // its position inside that cell, in cell widths
+		if (G.full_circle) {
+			if (2 * di + 2 * cellw >= 360.0) { i0 = 0; cnt = n; }
+			else {
+				i0 = racell_of(B, wrap360(rn - di - G.ra_org));
+				int i1 = racell_of(B, wrap360(rn + di - G.ra_org));
+				cnt = (i1 - i0 + n) % n + 1;
+			}
+		} else {
+			// the grid's ra window was built from min(rn - dra) .. max(rn + dra) with a margin: no wrap inside
+			double x0 = wrap360(rn - G.ra_org) - di, x1 = wrap360(rn - G.ra_org) + di;
+			i0 = racell_of(B, fmax(x0, 0.0));
+			int i1 = racell_of(B, fmin(x1, G.ra_span));
+			cnt = i1 - i0 + 1;
+		}
+		int cb = B.base;
+		if (!FILL) {
+			for (int k = 0; k < cnt; k++) atomicAdd(&cellcnt[cb + (i0 + k) % n], 1);
+			continue;
+		}
+		// four cells at a time: the slot requests (atomics with return) are independent, issued together so that their
+		// latencies overlap; then the stores
+		for (int k0 = 0; k0 < cnt; k0 += 4) {
+			int sl[4], cell[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				sl[u] = -1;
+				cell[u] = 0;
+				if (k0 + u < cnt) {
+					cell[u] = cb + (i0 + k0 + u) % n;
+					sl[u] = atomicSub(&cellcnt[cell[u]], 1) - 1;
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				if (sl[u] < 0) continue;
+				if (sl[u] < 3) {
+					// packed: offset of this cell from the primary's own, unwrapped
+					int m = i0 + k0 + u - ip;
+					bool always = false;
+					if (G.full_circle) {
+						if (m > n / 2) m -= n;
+						else if (m < -(n / 2)) m += n;
+						always = n < 4 || cnt >= n;   // too few cells to tell which way round is the near one
+					}
+					const unsigned xy = pe_encode(xc - (double) m, yp - (double) b, always);
+					cells[cell[u]].q[1 + sl[u]] = (unsigned long long) xy | ((unsigned long long) (unsigned) i << 32);
+				} else {
+					if (!have_en) {   // the fp32 entry of the crowded cells' work items (rare: computed on demand)
+						double x = rn - G.ra_org_n;
+						if (x < 0.0) x += 360.0;
+						en.x = (float) x;
+						en.y = (float) (d - G.dec_lo);
+						double tau = (rb_ins / 180 * NWB_PI) * tan(fmin(fabs(d), 89.9999) / 180 * NWB_PI);
+						en.clat = (tau > G.tau_max || dra >= 180.0) ? 0.f : __double2float_rd(clat_i);
+						en.p = i;
+						have_en = true;
+					}
+					const int est = (int) (cells[cell[u]].q[0] >> 32);   // written by k_cell_headers (an earlier launch)
+					*reinterpret_cast<int4 *>(entries + est + sl[u]) = *reinterpret_cast<const int4 *>(&en);
+				}
+			}
+		}
+	}
+}
+
 // box margins: rb (deg) is the search radius inflated by 1e-9 relative + 1e-12, so that rounding in the
 // box test can never reject a pair the exact formula would accept.
+// COUNT: the grid geometry is already known (re-used from the previous match, verified afterwards on the device), so
+// the primary is counted into its cells right here -- one kernel and one pass over the primaries less.
+template <bool COUNT>
 __global__ void k_prim_prep(int np, long long first, const double *__restrict__ ra, const double *__restrict__ dec,
-	double rb, PrimArrays P, unsigned long long *__restrict__ red /* [6], zeroed */)
+	double rb, PrimArrays P, unsigned long long *__restrict__ red /* [6], zeroed */,
+	Grid G, double rb_ins, double dra_eps, int *__restrict__ cellcnt)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	double v[6] = {1e300, -1e300, 1e300, -1e300, 1e300, -1e300};   // dec min/max, A lo/hi, B lo/hi
@@ -182,6 +277,7 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 		v[0] = d; v[1] = d;
 		v[2] = rn - dra; v[3] = rn + dra;
 		v[4] = rn_b - dra; v[5] = rn_b + dra;
+		if (COUNT) prim_register<false>(G, i, d, rn, dra, cl, rb_ins, dra_eps, 0, 1, cellcnt, nullptr, nullptr);
 	}
 	// block reduce, then one atomicMax per quantity on an order-preserving integer image of the double
 	// (minima are stored negated), so no second kernel is needed
@@ -209,92 +305,56 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 	}
 }
 
-// FILL = false: cellcnt[cell] += 1 for every cell the primary's (slightly inflated) box overlaps.
-// FILL = true : write the entry at cstart[cell] + slot, the slots being handed out by counting cellcnt back
-// down (no second memset).  If the entry buffer is too small nothing is written; the host sees the total
-// and retries.
+// four threads per primary, one declination band each (see prim_register).  FILL returns without writing when the
+// overflow segments do not fit the entry buffer; the host sees the total and retries.
 template <bool FILL>
 __global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double dra_eps,
-	int *__restrict__ cellcnt, const int *__restrict__ cstart, Entry *__restrict__ entries, PEntry *__restrict__ pentries,
-	long long entries_cap)
+	int *__restrict__ cellcnt, CellRec *cells, Entry *__restrict__ entries, const int *__restrict__ etotal, long long entries_cap)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	const int i = t >> 2, bslot = t & 3;   // four threads per primary, one declination band each
+	const int i = t >> 2, bslot = t & 3;
 	if (i >= np) return;
-	if (FILL && (long long) cstart[G.ncells] > entries_cap) return;
-	double d = P.dec[i], rn = P.ra_n[i], dra = P.dra[i];
-	int b0 = band_of(G, d - rb_ins), b1 = band_of(G, d + rb_ins);
-	b0 = max(b0, 0);
-	b1 = min(b1, G.nbands - 1);
-	Entry en;
-	{
-		double x = rn - G.ra_org_n;
-		if (x < 0.0) x += 360.0;
-		en.x = (float) x;
-		en.y = (float) (d - G.dec_lo);
-		double tau = (rb_ins / 180 * NWB_PI) * tan(fmin(fabs(d), 89.9999) / 180 * NWB_PI);
-		en.clat = (tau > G.tau_max || dra >= 180.0) ? 0.f : __double2float_rd(P.clat[i]);
-		en.p = i;
+	if (FILL && (long long) etotal[0] > entries_cap) return;
+	prim_register<FILL>(G, i, P.dec[i], P.ra_n[i], P.dra[i], FILL ? P.clat[i] : 0.0, rb_ins, dra_eps, bslot, 4, cellcnt, cells, entries);
+}
+
+// One header per cell: q[0] = count | (start of the cell's overflow segment - 3) << 32, so that entry k >= 3 of the cell
+// is entries[start + k]; the segments are handed out block by block (block scan + one atomicAdd per block -- no
+// device-wide prefix sum).  Also the occupancy bitmap (sparse primaries) and the totals the host checks:
+// totals[0] = overflow entries (must fit the entry buffer), totals[1] = registrations.
+__global__ void __launch_bounds__(256)
+k_cell_headers(long long ncells, const int *__restrict__ cellcnt, CellRec *__restrict__ cells, unsigned *__restrict__ bits,
+	int *__restrict__ totals /* zeroed */)
+{
+	__shared__ int wneed[8], wcnt[8];
+	__shared__ int base;
+	const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int cnt = c < ncells ? cellcnt[c] : 0;
+	if (bits) {   // a warp covers 32 consecutive cells = one word of the bitmap
+		unsigned word = __ballot_sync(NWB_FULL, cnt > 0);
+		if (lane == 0 && c < ncells) bits[c >> 5] = word;
 	}
-	double di = dra + dra_eps;
-	const double xp = wrap360(rn - G.ra_org);          // the primary along ra, from the grid origin
-	const double yp = (d - G.dec_lo) * G.inv_h;        // ... and in band heights
-	for (int b = b0 + bslot; b <= b1; b += 4) {
-		BandRec B = load_band(G, b);
-		int n = B.nra;
-		int i0, cnt;
-		double cellw = G.ra_span / n;
-		const int ip = racell_of(B, xp);               // the primary's own cell in this band
-		const double xc = xp * B.inv_w - (double) ip;  // its position inside that cell, in cell widths
-		if (G.full_circle) {
-			if (2 * di + 2 * cellw >= 360.0) { i0 = 0; cnt = n; }
-			else {
-				i0 = racell_of(B, wrap360(rn - di - G.ra_org));
-				int i1 = racell_of(B, wrap360(rn + di - G.ra_org));
-				cnt = (i1 - i0 + n) % n + 1;
-			}
-		} else {
-			// the grid's ra window was built from min(rn - dra) .. max(rn + dra) with a margin: no wrap inside
-			double x0 = wrap360(rn - G.ra_org) - di, x1 = wrap360(rn - G.ra_org) + di;
-			i0 = racell_of(B, fmax(x0, 0.0));
-			int i1 = racell_of(B, fmin(x1, G.ra_span));
-			cnt = i1 - i0 + 1;
-		}
-		int cb = B.base;
-		if (!FILL) {
-			for (int k = 0; k < cnt; k++) atomicAdd(&cellcnt[cb + (i0 + k) % n], 1);
-			continue;
-		}
-		// four cells at a time: the slot requests (atomics with return) and the list starts are independent loads, issued
-		// together so that their latencies overlap; then the stores
-		for (int k0 = 0; k0 < cnt; k0 += 4) {
-			int pos[4];
-#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				pos[u] = -1;
-				if (k0 + u < cnt) {
-					int cell = cb + (i0 + k0 + u) % n;
-					pos[u] = cstart[cell] + atomicSub(&cellcnt[cell], 1) - 1;
-				}
-			}
-#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				if (pos[u] < 0) continue;
-				*reinterpret_cast<int4 *>(entries + pos[u]) = *reinterpret_cast<const int4 *>(&en);
-				// packed twin: offset of this cell from the primary's own, unwrapped
-				int m = i0 + k0 + u - ip;
-				bool always = false;
-				if (G.full_circle) {
-					if (m > n / 2) m -= n;
-					else if (m < -(n / 2)) m += n;
-					always = n < 4 || cnt >= n;   // too few cells to tell which way round is the near one
-				}
-				PEntry pe;
-				pe.xy = pe_encode(xc - (double) m, yp - (double) b, always);
-				pe.p = i;
-				*reinterpret_cast<int2 *>(pentries + pos[u]) = *reinterpret_cast<const int2 *>(&pe);
-			}
-		}
+	const int need = max(cnt - 3, 0);
+	int incl = need;
+	for (int o = 1; o < 32; o <<= 1) {
+		int y = __shfl_up_sync(NWB_FULL, incl, o);
+		if (lane >= o) incl += y;
+	}
+	const int csum = __reduce_add_sync(NWB_FULL, cnt);
+	if (lane == 31) wneed[w] = incl;
+	if (lane == 0) wcnt[w] = csum;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int s = 0, sc = 0;
+		for (int k = 0; k < 8; k++) { int t = wneed[k]; wneed[k] = s; s += t; sc += wcnt[k]; }
+		base = s ? atomicAdd(&totals[0], s) : 0;
+		if (sc) atomicAdd(&totals[1], sc);
+	}
+	__syncthreads();
+	if (c < ncells) {
+		const int start = base + wneed[w] + incl - need - 3;
+		cells[c].q[0] = (unsigned long long) (unsigned) cnt | ((unsigned long long) (unsigned) start << 32);
 	}
 }
 
@@ -315,6 +375,9 @@ constexpr int K1_SBANDS = 1024;                  // bands cached in shared memor
 
 #ifndef NWB_K1_MINBLOCKS
 #define NWB_K1_MINBLOCKS 4
+#endif
+#ifndef NWB_K1_COMBINE
+#define NWB_K1_COMBINE 1
 #endif
 
 struct K1Smem {   // per warp
@@ -442,13 +505,13 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 //      directly -- no append buffer, no scatter pass.
 __global__ void __launch_bounds__(K1_WARPS * 32, NWB_K1_MINBLOCKS)
 k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G,
-	const int *__restrict__ cstart, const CellRec *__restrict__ cells, const Entry *__restrict__ entries,
+	const int *__restrict__ etotal, const CellRec *__restrict__ cells, const Entry *__restrict__ entries,
 	long long entries_cap, K1Args A)
 {
 	__shared__ K1Smem smem[K1_WARPS];
 	__shared__ int4 sbands[K1_SBANDS];   // the band table, when it is small enough (one L2 round trip less)
 	__shared__ float skx[K1_SBANDS];
-	if ((long long) cstart[G.ncells] > entries_cap) return;   // the cell lists were not written: the host retries
+	if ((long long) etotal[0] > entries_cap) return;   // the cell lists were not written: the host retries
 	const bool bands_in_smem = G.nbands <= K1_SBANDS;
 	if (bands_in_smem) {
 		for (int b = threadIdx.x; b < G.nbands; b += blockDim.x) {
@@ -510,11 +573,40 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 		// the inline entries: up to three fp32 pre-tests on the spot
 		const int ninl = min(ecnt, 3);
 		if (!__any_sync(NWB_FULL, ninl > 0)) continue;   // sparse primaries: most batches end here
+#if NWB_K1_COMBINE
+		{
+			// the three pre-tests first (independent: they overlap), then ONE update of the candidate queue
+			const bool p0 = ninl > 0 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e0);
+			const bool p1 = ninl > 1 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e1);
+			const bool p2 = ninl > 2 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e2);
+			const unsigned m0 = __ballot_sync(NWB_FULL, p0), m1 = __ballot_sync(NWB_FULL, p1), m2 = __ballot_sync(NWB_FULL, p2);
+			const int n0 = __popc(m0), n01 = n0 + __popc(m1), n012 = n01 + __popc(m2);
+			if (qn + n012 <= K1_QCAP) {
+				if (n012) {
+					if (p0) { const int q = qn + __popc(m0 & lt); M.cand_sp[q] = make_int2((int) i, (int) (e0 >> 32)); M.cand_rd[q] = make_double2(r, d); }
+					if (p1) { const int q = qn + n0 + __popc(m1 & lt); M.cand_sp[q] = make_int2((int) i, (int) (e1 >> 32)); M.cand_rd[q] = make_double2(r, d); }
+					if (p2) { const int q = qn + n01 + __popc(m2 & lt); M.cand_sp[q] = make_int2((int) i, (int) (e2 >> 32)); M.cand_rd[q] = make_double2(r, d); }
+					qn += n012;
+					__syncwarp();
+					while (qn >= 32) {
+						qn -= 32;
+						k1_flush(M, qn, 32, lane, A);
+						__syncwarp();
+					}
+				}
+			} else {   // more than the queue holds at once (rare): one entry at a time
+				k1_enqueue(M, p0, (int) i, (int) (e0 >> 32), r, d, lane, qn, A);
+				k1_enqueue(M, p1, (int) i, (int) (e1 >> 32), r, d, lane, qn, A);
+				k1_enqueue(M, p2, (int) i, (int) (e2 >> 32), r, d, lane, qn, A);
+			}
+		}
+#else
 		k1_enqueue(M, ninl > 0 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e0), (int) i, (int) (e0 >> 32), r, d, lane, qn, A);
 		if (__any_sync(NWB_FULL, ninl > 1))
 			k1_enqueue(M, ninl > 1 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e1), (int) i, (int) (e1 >> 32), r, d, lane, qn, A);
 		if (__any_sync(NWB_FULL, ninl > 2))
 			k1_enqueue(M, ninl > 2 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e2), (int) i, (int) (e2 >> 32), r, d, lane, qn, A);
+#endif
 		// crowded cells (> 3 primaries): the entries beyond the third become work items, pre-tested 32 at a time
 		const int maxc = __reduce_max_sync(NWB_FULL, ecnt);
 		for (int k = 3; k < maxc; k++) {
@@ -544,31 +636,6 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 	}
 }
 
-// cell records from the cell lists (see struct CellRec)
-__global__ void k_cell_records(long long ncells, const int *__restrict__ cstart, const PEntry *__restrict__ pentries,
-	long long entries_cap, CellRec *__restrict__ cells, unsigned *__restrict__ bits)
-{
-	long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	if ((long long) cstart[ncells] > entries_cap) return;
-	int s = 0, cnt = 0;
-	if (c < ncells) { s = cstart[c]; cnt = cstart[c + 1] - s; }
-	if (bits) {   // a warp covers 32 consecutive cells = one word of the bitmap
-		unsigned w = __ballot_sync(NWB_FULL, cnt > 0);
-		if ((threadIdx.x & 31) == 0 && c < ncells) bits[c >> 5] = w;
-	}
-	if (c >= ncells) return;
-	unsigned long long q[4] = {(unsigned long long) (unsigned) cnt | ((unsigned long long) (unsigned) s << 32), 0ull, 0ull, 0ull};
-	if (cnt > 0) {
-		const unsigned long long *pe = reinterpret_cast<const unsigned long long *>(pentries + s);
-		q[1] = __ldg(pe);
-		if (cnt > 1) q[2] = __ldg(pe + 1);
-		if (cnt > 2) q[3] = __ldg(pe + 2);
-	}
-	ulonglong2 *out = reinterpret_cast<ulonglong2 *>(cells + c);
-	out[0] = make_ulonglong2(q[0], q[1]);
-	out[1] = make_ulonglong2(q[2], q[3]);
-}
-
 // the scalars the host needs after K1, gathered for one small copy: [0] cell entries, [c] spill records of
 // catalogue c, [8] total rows (N == 2)
 struct BoundsKey { unsigned long long k[6]; };
@@ -578,7 +645,8 @@ __global__ void k_collect_status(int ncat, const int *__restrict__ entries_total
 	const unsigned long long *__restrict__ bounds, BoundsKey expected, long long *__restrict__ out)
 {
 	int t = threadIdx.x;
-	if (t == 0) out[0] = *entries_total;
+	if (t == 0) out[0] = entries_total[0];    // overflow entries of the cell lists
+	if (t == 10) out[10] = entries_total[1];  // registrations (primary, cell)
 	if (t >= 1 && t < ncat) out[t] = (long long) spill_count[t];
 	if (t == 8) out[8] = total_rows ? *total_rows : 0;
 	if (t == 9) {   // [9] != 0: the primaries' bounding box is not the one the (re-used) grid geometry was built for
@@ -902,12 +970,6 @@ __global__ void k_count_rows_small(RowParams R, long long *__restrict__ rows)
 }
 
 // N == 2: rows per primary = matches + 1
-__global__ void k_rows_per_primary_2(int np, const int *__restrict__ cnt, long long *__restrict__ rows)
-{
-	int p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p < np) rows[p] = (long long) cnt[p] + 1;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // per-row finalisation pieces shared by k_rows<FUSE> and k_final
 // ---------------------------------------------------------------------------------------------------------

@@ -234,3 +234,65 @@ def test_elementwise_surface():
 		assert np.allclose(out, k['logbf%d_out' % n], rtol=1e-12, atol=1e-11)
 	out = bayesdistance.posterior(k['post_prior'], k['post_logbf'])
 	assert np.allclose(out, k['post_out'], rtol=1e-10, atol=0)
+
+
+def _low_level_context(tables, radius, completeness):
+	import nway_b200
+	from nway_b200 import _lib
+	ctx = _lib.Context(0)
+	_load_tables(ctx, tables, radius, completeness)
+	return ctx
+
+
+def _load_tables(ctx, tables, radius, completeness):
+	import nway_b200
+	from nway_b200 import _lib
+	for c, t in enumerate(tables):
+		ctx.set_catalogue(c, len(tables), t['ra'], t['dec'], t['error'], t['area'])
+	tab = nway_b200._scalar_tables(tables, completeness, nway_b200.NullOutputLogger())
+	ctx.set_params(radius, tab['pc'], 0.5, _lib.UNRELATED_API)
+	ctx.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
+
+
+def _all_columns(ctx, nrows):
+	from nway_b200 import _lib
+	sels = [_lib.COL_IDX, _lib.COL_IDX + 1, _lib.COL_SEP, _lib.COL_SEPMAX, _lib.COL_NCAT, _lib.COL_LOGBF_UNCORR, _lib.COL_LOGBF,
+		_lib.COL_DIST_POST, _lib.COL_P_SINGLE, _lib.COL_MATCH_FLAG, _lib.COL_P_ANY, _lib.COL_P_I]
+	out = [ctx.fetch(sel, nrows, dtype=np.int64) for sel in sels]   # bit patterns: NaNs compare equal too
+	ctx.sync()
+	return out
+
+
+def test_async_match_equals_sync_match_and_recovers_from_failed_speculation():
+	"""nwb_match_async / nwb_match_wait (no host round trip at the end of a match): same table bit for bit as nwb_match,
+	also when the blindly enqueued pipeline does not hold (catalogue replaced by a shifted / a three times denser one)"""
+	from nway_b200 import _lib
+	a = cases.uniform_patch(51, (300, 20000), (1.0, 0.3), 0.1)
+	b = cases.uniform_patch(52, (300, 20000), (1.0, 0.3), 0.1, ra0=150.3, dec0=0.2)
+	c = cases.uniform_patch(53, (300, 60000), (1.0, 0.3), 0.1, ra0=150.3, dec0=0.2)
+	ctx = _low_level_context(a, 6.0, 0.9)
+	with pytest.raises(_lib.NwbError):
+		ctx.match_wait()                      # nothing in flight, nothing matched
+	ctx.match_async()                         # first match of the context: runs synchronously inside
+	n0 = ctx.match_wait()
+	want = _all_columns(ctx, n0)
+	ref_ctx = _low_level_context(a, 6.0, 0.9)
+	assert ref_ctx.match() == n0
+	for x, y in zip(want, _all_columns(ref_ctx, n0)):
+		assert (x == y).all()
+	for _ in range(3):                        # now truly asynchronous, back to back
+		ctx.match_async()
+	with pytest.raises(_lib.NwbError):
+		ctx.fetch(_lib.COL_P_ANY, n0)         # results may be read only after match_wait
+	assert ctx.match_wait() == n0
+	assert ctx.match_wait() == n0             # idempotent
+	for x, y in zip(want, _all_columns(ctx, n0)):
+		assert (x == y).all()
+	for tables in (b, c, a):                  # moved primaries (stale grid geometry), then a table that outgrows the buffers
+		_load_tables(ctx, tables, 6.0, 0.9)
+		ctx.match_async()
+		n = ctx.match_wait()
+		ref_ctx = _low_level_context(tables, 6.0, 0.9)
+		assert ref_ctx.match() == n
+		for x, y in zip(_all_columns(ctx, n), _all_columns(ref_ctx, n)):
+			assert (x == y).all()
