@@ -541,12 +541,12 @@ int nwb_set_catalogue(nwb_ctx *ctx, int c, int ncat, int64_t n, const double *ra
 	S.err_const = false;
 	if (n > 0 && err_kind == NWB_ERR_CIRCULAR) {
 		ENSURE(ctx->d_status, 64 * sizeof(long long));
-		if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocDefault));
+		if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocMapped));
 		unsigned long long init[2] = {0x7ff0000000000000ull, 0ull};
 		unsigned long long *d_mm = (unsigned long long *) ctx->d_status.p + 32;
 		CU(cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
 		LAUNCH(ctx, k_minmax, (int) std::min<int64_t>((n + 255) / 256, 148 * 8), 256, (long long) n, S.err, (double *) d_mm);
-		CU(cudaMemcpyAsync(ctx->h_status + 40, d_mm, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		LAUNCH(ctx, k_words_to_host, 1, 32, (const long long *) d_mm, ctx->h_status + 40, 2);
 		CU(cudaStreamSynchronize(ctx->stream));
 		double lo, hi;
 		memcpy(&lo, ctx->h_status + 40, 8);
@@ -716,7 +716,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	{ int r = upload_tables(ctx); if (r) return r; }
 	const bool cli = ctx->unrelated_mode == NWB_UNRELATED_CLI && nc >= 3;
 	const bool fuse = fuse_final && !cli;
-	if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocDefault));
+	if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocMapped));
 	long long *hs = ctx->h_status;
 
 	CU(cudaEventRecord(ctx->ev[0], st));
@@ -733,9 +733,9 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	int pblocks = grid_for(np, 256);
 	ENSURE(ctx->d_red, 8 * sizeof(double));
 	unsigned long long *d_red = (unsigned long long *) ctx->d_red.p;
-	CU(cudaMemsetAsync(d_red, 0, 6 * sizeof(unsigned long long), st));
 	const bool use_cached = allow_cached && ctx->geom_valid && ctx->geom_rb == rb && ctx->geom_np == np && ctx->geom_first == first;
 	if (!use_cached) {
+		CU(cudaMemsetAsync(d_red, 0, 6 * sizeof(unsigned long long), st));
 		LAUNCH(ctx, (k_prim_prep<false>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
 			Grid(), rb_ins, dra_eps, (int *) nullptr);
 		// the grid geometry is chosen on the host from the bounding box: one sync.  It is kept for the next match
@@ -828,7 +828,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		CellRec *d_cells = (CellRec *) ctx->d_cells.p;
 		if (attempt == 0 && use_cached) {
 			// known geometry: the primaries are counted into their cells by the preparation kernel itself
-			CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
+			LAUNCH(ctx, k_zero, (int) std::min<size_t>((zero_ints / 4 + 255) / 256, 148 * 8), 256, (int4 *) d_cellcnt, (long long) (zero_ints / 4), d_red, 6);
 			LAUNCH(ctx, (k_prim_prep<true>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
 				G, rb_ins, dra_eps, d_cellcnt);
 		} else {
@@ -852,27 +852,33 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			if (n == 0) continue;
 			if (ctx->k1_blocks_per_sm <= 0) {
 				int nb = 0, nsm = 0;
-				CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pairs, K1_WARPS * 32, 0));
+				CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pairs<false>, K1_WARPS * 32, 0));
 				CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
 				ctx->k1_blocks_per_sm = std::max(nb, 1);
 				ctx->num_sms = std::max(nsm, 1);
 			}
 			// persistent: exactly one wave of resident blocks, each striding over the catalogue
 			int grid = (int) std::min<int64_t>((n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), (int64_t) ctx->num_sms * ctx->k1_blocks_per_sm);
+			if (n + (int64_t) grid * K1_WARPS * 32 + 64 > 0x7fffffffll)
+				return fail(ctx, NWB_ERR_ARG, "catalogue too large: secondary indices are 32-bit");
 			CU(cudaEventRecord(ctx->kev[2 * c], st));
 			K1Args ka;
 			ka.P = P; ka.radius = ctx->prefilter_on ? std::min(ctx->radius, ctx->prefilter[pair_index(0, c, nc)]) : ctx->radius; ka.base = d_base + base_off[c]; ka.C = Cs[c]; ka.cnt = d_cnt[c];
 			ka.spill = d_spill + (size_t) ctx->spill_cap * (c - 1); ka.spill_cap = (unsigned long long) ctx->spill_cap;
 			ka.spill_count = d_spillcount + c;
-			LAUNCH(ctx, k_pairs, grid, K1_WARPS * 32, (long long) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_etotal,
-				(const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
+			if (G.nbands <= K1_SBANDS && !G.bits)
+				LAUNCH(ctx, (k_pairs<true>), grid, K1_WARPS * 32, (int) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_etotal,
+					(const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
+			else
+				LAUNCH(ctx, (k_pairs<false>), grid, K1_WARPS * 32, (int) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_etotal,
+					(const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
 			CU(cudaEventRecord(ctx->kev[2 * c + 1], st));
 		}
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[2], st));
 		if (!generic) { int r = scan_rows2(ctx, (const int *) d_cnt[1], d_rowoff, np); if (r) return r; }
 		LAUNCH(ctx, k_collect_status, 1, 32, nc, (const int *) d_etotal, (const unsigned long long *) d_spillcount,
 			!generic ? (const long long *) d_rowoff + np : (const long long *) nullptr, (const unsigned long long *) d_red,
-			ctx->geom_key, d_status);
+			ctx->geom_key, d_status, hs);
 		// speculative K2: if the table of the previous match was big enough, launch the row kernel right away; it
 		// checks the status words on the device.  One host sync per match instead of three.
 		speculated = false;
@@ -894,7 +900,6 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			CU(cudaEventRecord(ctx->kev[1], st));
 			speculated = true;
 		}
-		CU(cudaMemcpyAsync(hs, d_status, 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
 		if (defer && speculated && use_cached && attempt == 0) {
 			// nwb_match_async: everything of this match is in the stream (the row kernel checks the status words on the
 			// device); nwb_match_wait looks at the same words on the host and redoes the match if they say no
@@ -1291,7 +1296,7 @@ int nwb_maghist_select(nwb_ctx *ctx, int c, int k, int by_radius, double thr_sel
 		LAUNCH(ctx, k_hist_sources, grid_for(n, 256), 256, (long long) n, mag, (const int *) first, (const unsigned char *) possible, selflag, stats);
 		{ int r = scan_int(ctx, selflag, selrank, n + 1); if (r) return r; }   // selflag[n] == 0: selrank[n] is the total
 	}
-	if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocDefault));
+	if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocMapped));
 	long long *hs = ctx->h_status;
 	CU(cudaMemcpyAsync(hs + 48, stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	hs[47] = 0;

@@ -307,8 +307,12 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 
 // four threads per primary, one declination band each (see prim_register).  FILL returns without writing when the
 // overflow segments do not fit the entry buffer; the host sees the total and retries.
+#ifndef NWB_FILL_MINBLOCKS
+#define NWB_FILL_MINBLOCKS 3
+#endif
 template <bool FILL>
-__global__ void k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double dra_eps,
+__global__ void __launch_bounds__(256, NWB_FILL_MINBLOCKS)
+k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double dra_eps,
 	int *__restrict__ cellcnt, CellRec *cells, Entry *__restrict__ entries, const int *__restrict__ etotal, long long entries_cap)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -376,9 +380,7 @@ constexpr int K1_SBANDS = 1024;                  // bands cached in shared memor
 #ifndef NWB_K1_MINBLOCKS
 #define NWB_K1_MINBLOCKS 4
 #endif
-#ifndef NWB_K1_COMBINE
-#define NWB_K1_COMBINE 1
-#endif
+
 
 struct K1Smem {   // per warp
 	int2 item_es[K1_ICAP];      // (entry index, secondary index)
@@ -503,8 +505,11 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 //      evaluates one exact fp64 separation in the reference's arithmetic against ONE sector of primary data.
 //   3. a match takes the next slot of its primary (atomicAdd on the per-primary counter) and is written there
 //      directly -- no append buffer, no scatter pass.
+// DENSE: the band table fits shared memory and there is no occupancy bitmap (the streaming configuration of the
+// benchmark) -- the same kernel with those two run-time branches resolved at compile time.
+template <bool DENSE>
 __global__ void __launch_bounds__(K1_WARPS * 32, NWB_K1_MINBLOCKS)
-k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G,
+k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G,
 	const int *__restrict__ etotal, const CellRec *__restrict__ cells, const Entry *__restrict__ entries,
 	long long entries_cap, K1Args A)
 {
@@ -512,7 +517,7 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 	__shared__ int4 sbands[K1_SBANDS];   // the band table, when it is small enough (one L2 round trip less)
 	__shared__ float skx[K1_SBANDS];
 	if ((long long) etotal[0] > entries_cap) return;   // the cell lists were not written: the host retries
-	const bool bands_in_smem = G.nbands <= K1_SBANDS;
+	const bool bands_in_smem = DENSE || G.nbands <= K1_SBANDS;
 	if (bands_in_smem) {
 		for (int b = threadIdx.x; b < G.nbands; b += blockDim.x) {
 			sbands[b] = __ldg(reinterpret_cast<const int4 *>(G.bands + b));
@@ -524,15 +529,17 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 	const unsigned lt = (1u << lane) - 1;
 	K1Smem &M = smem[threadIdx.x >> 5];
 	int nit = 0, qn = 0;   // warp-uniform fill levels of the two lists
-	const long long stride = (long long) gridDim.x * blockDim.x;
-	const long long nround = (n + 31) / 32 * 32;
-	long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	// 32-bit indices: the host guarantees n + (one wave of threads) < 2^31 (secondary indices are ints in the slots anyway)
+	const int stride = gridDim.x * blockDim.x;
+	const int nround = (n + 31) / 32 * 32;
+	const double nbands_d = (double) G.nbands;
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	double r_nxt = 0, d_nxt = 0;
 	if (i < n) { r_nxt = ra[i]; d_nxt = dec[i]; }
 	for (; i < nround; i += stride) {
 		const double r = r_nxt, d = d_nxt;
 		{
-			long long j = i + stride;   // software prefetch of the next batch: hides the DRAM latency
+			const int j = i + stride;   // software prefetch of the next batch: hides the DRAM latency
 			if (j < n) { r_nxt = ra[j]; d_nxt = dec[j]; }
 		}
 		int ecnt = 0, estart = 0;
@@ -541,7 +548,7 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 		if (i < n) {
 			double y = d - G.dec_lo;
 			double t = y * G.inv_h;
-			if (t >= 0.0 && t < (double) G.nbands) {
+			if (t >= 0.0 && t < nbands_d) {
 				double x = wrap360(r) - G.ra_org_n;
 				if (x < 0.0) x += 360.0;
 				if (G.full_circle || x <= G.ra_span) {
@@ -559,7 +566,7 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 					int ic = __double2int_rd(xcells);
 					ic = ic >= B.nra ? B.nra - 1 : (ic < 0 ? 0 : ic);
 					const int cell = B.base + ic;
-					if (!G.bits || (__ldg(G.bits + (cell >> 5)) >> (cell & 31) & 1u)) {
+					if (DENSE || !G.bits || (__ldg(G.bits + (cell >> 5)) >> (cell & 31) & 1u)) {
 						const Sector32 cr = ldg_sector(cells + cell);   // one sector, one request
 						ecnt = (int) (unsigned) cr.q[0];
 						estart = (int) (cr.q[0] >> 32);
@@ -573,7 +580,6 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 		// the inline entries: up to three fp32 pre-tests on the spot
 		const int ninl = min(ecnt, 3);
 		if (!__any_sync(NWB_FULL, ninl > 0)) continue;   // sparse primaries: most batches end here
-#if NWB_K1_COMBINE
 		{
 			// the three pre-tests first (independent: they overlap), then ONE update of the candidate queue
 			const bool p0 = ninl > 0 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e0);
@@ -583,9 +589,9 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 			const int n0 = __popc(m0), n01 = n0 + __popc(m1), n012 = n01 + __popc(m2);
 			if (qn + n012 <= K1_QCAP) {
 				if (n012) {
-					if (p0) { const int q = qn + __popc(m0 & lt); M.cand_sp[q] = make_int2((int) i, (int) (e0 >> 32)); M.cand_rd[q] = make_double2(r, d); }
-					if (p1) { const int q = qn + n0 + __popc(m1 & lt); M.cand_sp[q] = make_int2((int) i, (int) (e1 >> 32)); M.cand_rd[q] = make_double2(r, d); }
-					if (p2) { const int q = qn + n01 + __popc(m2 & lt); M.cand_sp[q] = make_int2((int) i, (int) (e2 >> 32)); M.cand_rd[q] = make_double2(r, d); }
+					if (p0) { const int q = qn + __popc(m0 & lt); M.cand_sp[q] = make_int2(i, (int) (e0 >> 32)); M.cand_rd[q] = make_double2(r, d); }
+					if (p1) { const int q = qn + n0 + __popc(m1 & lt); M.cand_sp[q] = make_int2(i, (int) (e1 >> 32)); M.cand_rd[q] = make_double2(r, d); }
+					if (p2) { const int q = qn + n01 + __popc(m2 & lt); M.cand_sp[q] = make_int2(i, (int) (e2 >> 32)); M.cand_rd[q] = make_double2(r, d); }
 					qn += n012;
 					__syncwarp();
 					while (qn >= 32) {
@@ -595,18 +601,11 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 					}
 				}
 			} else {   // more than the queue holds at once (rare): one entry at a time
-				k1_enqueue(M, p0, (int) i, (int) (e0 >> 32), r, d, lane, qn, A);
-				k1_enqueue(M, p1, (int) i, (int) (e1 >> 32), r, d, lane, qn, A);
-				k1_enqueue(M, p2, (int) i, (int) (e2 >> 32), r, d, lane, qn, A);
+				k1_enqueue(M, p0, i, (int) (e0 >> 32), r, d, lane, qn, A);
+				k1_enqueue(M, p1, i, (int) (e1 >> 32), r, d, lane, qn, A);
+				k1_enqueue(M, p2, i, (int) (e2 >> 32), r, d, lane, qn, A);
 			}
 		}
-#else
-		k1_enqueue(M, ninl > 0 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e0), (int) i, (int) (e0 >> 32), r, d, lane, qn, A);
-		if (__any_sync(NWB_FULL, ninl > 1))
-			k1_enqueue(M, ninl > 1 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e1), (int) i, (int) (e1 >> 32), r, d, lane, qn, A);
-		if (__any_sync(NWB_FULL, ninl > 2))
-			k1_enqueue(M, ninl > 2 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e2), (int) i, (int) (e2 >> 32), r, d, lane, qn, A);
-#endif
 		// crowded cells (> 3 primaries): the entries beyond the third become work items, pre-tested 32 at a time
 		const int maxc = __reduce_max_sync(NWB_FULL, ecnt);
 		for (int k = 3; k < maxc; k++) {
@@ -614,7 +613,7 @@ k_pairs(long long n, const double *__restrict__ ra, const double *__restrict__ d
 			const unsigned m = __ballot_sync(NWB_FULL, has);
 			if (has) {
 				int q = nit + __popc(m & lt);
-				M.item_es[q] = make_int2(estart + k, (int) i);
+				M.item_es[q] = make_int2(estart + k, i);
 				M.item_rd[q] = make_double2(r, d);
 			}
 			nit += __popc(m);
@@ -642,18 +641,37 @@ struct BoundsKey { unsigned long long k[6]; };
 
 __global__ void k_collect_status(int ncat, const int *__restrict__ entries_total,
 	const unsigned long long *__restrict__ spill_count, const long long *__restrict__ total_rows,
-	const unsigned long long *__restrict__ bounds, BoundsKey expected, long long *__restrict__ out)
+	const unsigned long long *__restrict__ bounds, BoundsKey expected, long long *__restrict__ out,
+	long long *__restrict__ host /* the same words in mapped pinned host memory: no copy-engine transfer to wait for */)
 {
 	int t = threadIdx.x;
-	if (t == 0) out[0] = entries_total[0];    // overflow entries of the cell lists
-	if (t == 10) out[10] = entries_total[1];  // registrations (primary, cell)
-	if (t >= 1 && t < ncat) out[t] = (long long) spill_count[t];
-	if (t == 8) out[8] = total_rows ? *total_rows : 0;
+	long long v = 0;
+	bool mine = false;
+	if (t == 0) { v = entries_total[0]; mine = true; }     // overflow entries of the cell lists
+	if (t == 10) { v = entries_total[1]; mine = true; }    // registrations (primary, cell)
+	if (t >= 1 && t < ncat) { v = (long long) spill_count[t]; mine = true; }
+	if (t == 8) { v = total_rows ? *total_rows : 0; mine = true; }
 	if (t == 9) {   // [9] != 0: the primaries' bounding box is not the one the (re-used) grid geometry was built for
-		long long bad = 0;
-		for (int k = 0; k < 6; k++) bad |= (long long) (bounds[k] != expected.k[k]);
-		out[9] = bad;
+		for (int k = 0; k < 6; k++) v |= (long long) (bounds[k] != expected.k[k]);
+		mine = true;
 	}
+	if (mine) { out[t] = v; host[t] = v; }
+}
+
+// a few 8-byte words from device memory into mapped pinned host memory.  Small read-backs go this way rather than through
+// cudaMemcpyAsync: a copy would queue on the device-to-host copy engine behind whatever bulk transfer another context
+// has in flight there (two contexts overlapping their H2D / D2H), a store from a kernel does not.
+__global__ void k_words_to_host(const long long *__restrict__ src, long long *__restrict__ dst, int n)
+{
+	if ((int) threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+// zero-fill (16-byte units) plus a few extra words elsewhere -- one launch instead of two memsets
+__global__ void k_zero(int4 *__restrict__ a, long long n16, unsigned long long *__restrict__ b, int nb)
+{
+	const long long stride = (long long) gridDim.x * blockDim.x;
+	for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) a[i] = make_int4(0, 0, 0, 0);
+	if (blockIdx.x == 0 && (int) threadIdx.x < nb) b[threadIdx.x] = 0ull;
 }
 
 // overflow handling (only launched when some primary had more matches than slots)
@@ -1382,6 +1400,7 @@ constexpr int R2_NB = 128;    // buckets of the in-group sort
 #ifndef NWB_R2_GRID_PER_SM
 #define NWB_R2_GRID_PER_SM 4
 #endif
+
 
 struct __align__(16) R2Smem {
 	int s_in[R2_CAP];
