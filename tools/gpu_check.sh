@@ -11,7 +11,7 @@ timeout 600 python bench.py --steps 200 --warmup 5 > $out/bench.json 2> $out/ben
 cat $out/bench.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref.json 2> $out/bench_ref.err
 cat $out/bench_ref.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $out/launches.csv \
 	python bench.py --steps 2 --warmup 3 --no-cpu > $out/launches_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_pairs|k_rows2' --launch-skip 6 -c 2 -f -o $out/hot \
 	python bench.py --steps 2 --warmup 3 --no-cpu > $out/ncu_full.log 2>&1
