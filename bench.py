@@ -421,7 +421,10 @@ def run_b200(args):
 	ncu_traffic = os.path.join(ROOT, 'profiles', 'traffic.json')
 	if os.path.exists(ncu_traffic) and args.scale == 1.0:
 		try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel, from the committed ncu capture
-			roofline['traffic'] = json.load(open(ncu_traffic))['kernels'][kname.split('<')[0]]['dram_bytes_per_launch']
+			prof = json.load(open(ncu_traffic))['kernels'][kname.split('<')[0]]
+			roofline['traffic'] = prof['dram_bytes_per_launch']
+			if 'limiter' in prof:   # what the ncu capture says actually bounds the kernel (it is not HBM): informational
+				roofline['limiter'] = prof['limiter']
 		except Exception:
 			pass
 

@@ -26,6 +26,10 @@ def main(path, label):
 		rd = to_bytes(r[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']])
 		wr = to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
 		out[key] = {'dram_bytes_read': rd, 'dram_bytes_write': wr, 'dram_bytes_per_launch': rd + wr}
+		g = lambda m: float(r[idx[m]]) if m in idx and r[idx[m]] not in ('', 'n/a') else None
+		out[key]['limiter'] = {'l1tex_data_pipe_lsu_wavefronts_pct': g('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed'),
+			'issue_active_pct': g('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+			'dram_throughput_pct': g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')}
 	json.dump({'source': label, 'kernels': out}, open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w'), indent=1)
 	print(json.dumps(out))
 

@@ -8,7 +8,10 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 	'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'smsp__thread_inst_executed_per_inst_executed.ratio', 'launch__grid_size',
 	'sm__cycles_elapsed.max', 'lts__t_sectors_op_read.sum', 'lts__t_sectors_op_write.sum', 'lts__t_sectors_op_atom.sum', 'lts__t_sectors_op_red.sum',
 	'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'smsp__inst_executed_pipe_fp64.sum',
-	'sm__inst_executed_pipe_fp64.sum', 'smsp__inst_executed_pipe_lsu.sum', 'smsp__inst_executed_pipe_xu.sum']
+	'sm__inst_executed_pipe_fp64.sum', 'smsp__inst_executed_pipe_lsu.sum', 'smsp__inst_executed_pipe_xu.sum',
+	'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+	'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+	'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
 
 
 def main(path):
