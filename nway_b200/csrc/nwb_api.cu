@@ -724,6 +724,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	const double r_deg = ctx->radius / 3600.0;
 	const double rb = r_deg * (1 + 1e-9) + 1e-12;
 	const double rb_ins = rb + 1e-9, dra_eps = 1e-9;
+	const double entry_tau_max = (rb_ins * M_PI / 180 > 0.02) ? -1.0 : 0.02;   // the pole rule of pretest_constants (Grid::tau_max)
 	ENSURE(ctx->d_prim, (size_t) np * 8 * sizeof(double));
 	PrimArrays P;
 	{
@@ -737,7 +738,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	if (!use_cached) {
 		CU(cudaMemsetAsync(d_red, 0, 6 * sizeof(unsigned long long), st));
 		LAUNCH(ctx, (k_prim_prep<false>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
-			Grid(), rb_ins, dra_eps, (int *) nullptr);
+			Grid(), rb_ins, dra_eps, (int *) nullptr, entry_tau_max);
 		// the grid geometry is chosen on the host from the bounding box: one sync.  It is kept for the next match
 		// on this context, which only has to verify (on the device) that the box is still the same.
 		unsigned long long *raw = (unsigned long long *) (hs + 32);
@@ -830,7 +831,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			// known geometry: the primaries are counted into their cells by the preparation kernel itself
 			LAUNCH(ctx, k_zero, (int) std::min<size_t>((zero_ints / 4 + 255) / 256, 148 * 8), 256, (int4 *) d_cellcnt, (long long) (zero_ints / 4), d_red, 6);
 			LAUNCH(ctx, (k_prim_prep<true>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
-				G, rb_ins, dra_eps, d_cellcnt);
+				G, rb_ins, dra_eps, d_cellcnt, entry_tau_max);
 		} else {
 			CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
 			LAUNCH(ctx, (k_prim_cells<false>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (CellRec *) nullptr,

@@ -139,7 +139,7 @@ struct PrimRec {   // 32 bytes = one L2 sector: what the exact formula needs of 
 
 struct PrimArrays {
 	PrimRec *rec;                // for the exact formula
-	double *clat;                // (also kept as a plain column for the cell entries)
+	double *clat;                // cos(dec) for the fp32 entries of crowded cells: float-valued, rounded down, 0 near a pole
 	double *ra_n, *dec, *dra;    // search box (degrees); dra >= 180 means "all ra"
 };
 
@@ -174,10 +174,10 @@ __device__ __forceinline__ void prim_register(const Grid &G, const int i, const 
 		BandRec B = load_band(G, b);
 		int n = B.nra;
 		int i0, cnt;
-		double cellw = G.ra_span / n;
 		const int ip = racell_of(B, xp);               // the primary's own cell in this band
 		const double xc = xp * B.inv_w - (double) ip;  // its position inside that cell, in cell widths
 		if (G.full_circle) {
+			const double cellw = G.ra_span / n;
 			if (2 * di + 2 * cellw >= 360.0) { i0 = 0; cnt = n; }
 			else {
 				i0 = racell_of(B, wrap360(rn - di - G.ra_org));
@@ -229,8 +229,7 @@ __device__ __forceinline__ void prim_register(const Grid &G, const int i, const 
 						if (x < 0.0) x += 360.0;
 						en.x = (float) x;
 						en.y = (float) (d - G.dec_lo);
-						double tau = (rb_ins / 180 * NWB_PI) * tan(fmin(fabs(d), 89.9999) / 180 * NWB_PI);
-						en.clat = (tau > G.tau_max || dra >= 180.0) ? 0.f : __double2float_rd(clat_i);
+						en.clat = (float) clat_i;   // k_prim_prep applied the pole rule and the rounding
 						en.p = i;
 						have_en = true;
 					}
@@ -249,7 +248,7 @@ __device__ __forceinline__ void prim_register(const Grid &G, const int i, const 
 template <bool COUNT>
 __global__ void k_prim_prep(int np, long long first, const double *__restrict__ ra, const double *__restrict__ dec,
 	double rb, PrimArrays P, unsigned long long *__restrict__ red /* [6], zeroed */,
-	Grid G, double rb_ins, double dra_eps, int *__restrict__ cellcnt)
+	Grid G, double rb_ins, double dra_eps, int *__restrict__ cellcnt, double tau_max)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	double v[6] = {1e300, -1e300, 1e300, -1e300, 1e300, -1e300};   // dec min/max, A lo/hi, B lo/hi
@@ -261,7 +260,6 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 		PrimRec pr;
 		pr.lon = deg2rad_ref(r); pr.slat = sl; pr.clat = cl; pr.spare = 0.0;
 		P.rec[i] = pr;
-		P.clat[i] = cl;
 		double rn = wrap360(r);
 		double dra;
 		if (fabs(d) + rb >= 89.999) {
@@ -273,6 +271,12 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 		P.ra_n[i] = rn;
 		P.dec[i] = d;
 		P.dra[i] = dra;
+		{
+			// cos(dec) as the fp32 flat pre-test of the overflow entries wants it (struct Entry): rounded down, 0 for primaries
+			// too close to a pole for the flat metric -- decided here, once per primary, not in the (divergent) fill pass
+			const double tau = (rb_ins / 180 * NWB_PI) * tan(fmin(fabs(d), 89.9999) / 180 * NWB_PI);
+			P.clat[i] = (tau > tau_max || dra >= 180.0) ? 0.0 : (double) __double2float_rd(cl);
+		}
 		double rn_b = wrap360(rn + 180.0);
 		v[0] = d; v[1] = d;
 		v[2] = rn - dra; v[3] = rn + dra;

@@ -16,6 +16,7 @@ d=json.loads(sys.stdin.read()); s=d['config']['stage_ms']
 print('%-16s %.4e/s step %.4f ms  k_pairs %.1f k_rows %.1f grid %.1f lists %.1f total %.1f us  e2e %.2f ms rows %d pairs %d' % ('$1', d['value'], d['ms_per_step'], 1e3*s['k_pairs'], 1e3*s['k_rows'], 1e3*s['grid'], 1e3*s['lists'], 1e3*s['total'], d['e2e']['ms_per_step'], d['config']['rows_per_gpu'], d['config']['pairs_per_gpu']))" || tail -3 $out/bench_$1.err
 }
 one default
+shopt -s nullglob
 for lib in build/variants/lib_*.so; do
 	name=$(basename $lib .so)
 	NWB_LIB=$PWD/$lib one ${name#lib_}
