@@ -67,7 +67,7 @@ struct nwb_ctx {
 	int64_t first = 0, count = -1;
 
 	// device scratch (grow-only)
-	DevBuf d_tables, d_prim, d_red, d_bands, d_cellcnt, d_cstart, d_entries, d_cub, d_pairs, d_paircount;
+	DevBuf d_tables, d_prim, d_red, d_bands, d_cellcnt, d_entries, d_cub, d_pairs, d_paircount;
 	DevBuf d_cnt[MAXC], d_segoff[MAXC], d_seg_s[MAXC], d_seg_sep[MAXC], d_Ls[MAXC], d_Lsep[MAXC], d_Ltrig[MAXC];
 	DevBuf d_rows, d_rowoff, d_matsz, d_matoff, d_mat, d_cols, d_cols2, d_keep, d_keeppos, d_misc;
 	DevBuf d_spill, d_status, d_spilloff[MAXC], d_spillseg[MAXC], d_cells;
@@ -473,7 +473,7 @@ void nwb_destroy(nwb_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	DevBuf *single[] = {&ctx->d_tables, &ctx->d_prim, &ctx->d_red, &ctx->d_bands, &ctx->d_cellcnt, &ctx->d_cstart,
+	DevBuf *single[] = {&ctx->d_tables, &ctx->d_prim, &ctx->d_red, &ctx->d_bands, &ctx->d_cellcnt,
 		&ctx->d_entries, &ctx->d_cub, &ctx->d_pairs, &ctx->d_paircount, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_matsz,
 		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc, &ctx->d_spill, &ctx->d_status, &ctx->d_cells,
 		&ctx->d_hrow, &ctx->d_hsrc, &ctx->d_hout};

@@ -1,8 +1,11 @@
 // Kernels of the nway match path (sm_100a, fp64 CUDA cores -- there is no dense contraction on this path).
 //
 // Pipeline (one shard of primaries per context):
-//   k_prim_prep     per primary: lon, sin/cos(lat), search box           -> P_* arrays           (K0)
-//   k_prim_cells    count / fill: primary -> every grid cell its box overlaps                    (K0)
+//   k_prim_prep     per primary: lon, sin/cos(lat), search box           -> P_* arrays; with a known grid
+//                   geometry also the count pass: cellcnt[cell] += 1 for every cell the box overlaps (K0)
+//   k_cell_headers  per cell: count, start of its overflow segment (block scan, no device-wide scan) (K0)
+//   k_prim_cells    count (grid geometry just chosen) / fill: the first three primaries of a cell go
+//                   straight into its 32-byte record, later ones into the overflow segment        (K0)
 //   k_pairs         stream a secondary catalogue once: cell -> box test -> per-warp candidate queue ->
 //                   dense exact separations -> (secondary, sep) straight into the primary's slot (K1)
 //   k_spill_*       the rare primaries with more matches than slots: overflow records -> segments (K1)
@@ -146,7 +149,9 @@ struct PrimArrays {
 // 32 bytes = one L2 sector per cell, fetched with one 256-bit load: how many primaries are registered here and the
 // first three of them inline, packed (PEntry); entries beyond the third become work items.  A secondary in a cell
 // with <= 3 primaries (90 % of the occupied cells at C3's densities) needs no second lookup.
-//     q[0] = cnt | list start << 32      q[1] = entry 0      q[2] = entry 1      q[3] = entry 2
+//     q[0] = cnt | (overflow segment start - 3) << 32      q[1] = entry 0      q[2] = entry 1      q[3] = entry 2
+// q[0] is written by k_cell_headers, q[1..3] by the fill pass (whichever three primaries asked first); entry k >= 3 of
+// the cell is entries[(q[0] >> 32) + k].  Slots beyond cnt are never read.
 struct CellRec {
 	unsigned long long q[4];
 };
