@@ -1,5 +1,9 @@
 """Device-time of the match path on BASELINE.json's other named configurations (bench.py measures configs[2]):
 
+  C1  configs[0]: COSMOS XMM x OPTICAL, r = 20 arcsec                      } the committed subset of the demo catalogues
+  C2  configs[1]: COSMOS XMM x OPTICAL x IRAC, r = 20 arcsec, automatic    } (tests/golden/cosmos_subset.npz: every source
+      OPT MAG + IRAC mag_ch1 priors                                         } within 30 arcsec of an XMM source -- the same
+      -> latency of the whole nway_match() call (these are 1797 groups: launch-latency bound)   rows as the full files)
   C4  configs[3]: synthetic 3-cat 1e6 x 1e7 x 1e7 all-sky, r = 10 arcsec, circular errors (one GPU's worth)
   C5  configs[4]: synthetic 4-cat all-sky 1e5 x 3 x 1e8 (--c5-scale of the secondaries), elliptical primary errors,
       one magnitude prior per secondary catalogue, command-line correction on
@@ -40,6 +44,27 @@ def build(name, c5_scale):
 	return tables, 10.0, dict(unrelated_mode='cli')
 
 
+def api_latency(name, steps):
+	"""wall time of the public call nway_b200.nway_match() (host arrays in, pandas DataFrame out) on the COSMOS cases"""
+	import nway_b200
+	from nway_b200 import _lib
+	from tests import cases
+	case = 'cosmos2' if name == 'c1' else 'cosmos3_magauto'
+	wall, rows, ms = [], 0, {}
+	for k in range(steps + 1):
+		tables = cases.build_case(case)
+		t0 = time.perf_counter()
+		res = nway_b200.nway_match(tables, 20.0, 0.9, logger=nway_b200.NullOutputLogger(), store_mag_hists=False)
+		dt = time.perf_counter() - t0
+		rows = len(res)
+		if k >= 1:
+			wall.append(dt)
+			ms = _lib.get_context().timings()
+	print(json.dumps(dict(config=name, case=case, sizes=[len(t['ra']) for t in tables], radius_arcsec=20.0, rows=rows,
+		api_wall_ms=1e3 * float(np.median(wall)), api_wall_ms_min=1e3 * float(min(wall)), device_stage_ms_last_pass=ms,
+		reference_cpu_s={'c1': 3.17, 'c2': 21.7}[name], note='reference time: SURVEY.md 8d, full demo catalogues, one core')))
+
+
 def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument('configs', nargs='*', default=['c4', 'c5'])
@@ -49,6 +74,9 @@ def main():
 	import nway_b200
 	from nway_b200 import _lib
 	for name in args.configs:
+		if name in ('c1', 'c2'):
+			api_latency(name, args.steps)
+			continue
 		t0 = time.time()
 		tables, radius, kw = build(name, args.c5_scale)
 		t_build = time.time() - t0
