@@ -152,6 +152,13 @@ def run_reference(args):
 	if rank != 0:
 		return
 	scale = args.ref_scale
+	if scale is None:
+		# bounded sample: size it so that the warm-up + K timed steps end within a minute or two on whatever host this is
+		# (the algorithm is linear in the area at fixed densities; one small probe step measures this host's speed)
+		probe = 0.004
+		_, t = cpu_port(probe)
+		per_unit = t[0] / probe
+		scale = max(0.002, min(0.05, 60.0 / (per_unit * (args.steps + min(args.warmup, 1)))))
 	rows, times = cpu_port(scale, steps=args.steps, warmup=min(args.warmup, 1))
 	sec = sum(times) / len(times)
 	value = rows / sec
@@ -467,7 +474,7 @@ def main():
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C3 area (same densities); 1.0 = the named workload')
 	ap.add_argument('--cpu-scale', type=float, default=0.4, help='sample of the workload the CPU baseline is timed on')
-	ap.add_argument('--ref-scale', type=float, default=0.05, help='sample per step of --impl reference')
+	ap.add_argument('--ref-scale', type=float, default=None, help='sample per step of --impl reference (fraction of the C3 area; default: sized from --steps so that the run ends within about two minutes)')
 	ap.add_argument('--no-cpu', action='store_true')
 	args = ap.parse_args()
 	if args.impl == 'reference':
