@@ -1,6 +1,7 @@
 """Generate tests/golden/* from the UNMODIFIED reference (run in the build container only).
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py                  everything
+    python oracle/make_golden.py allsky2 allsky3  only the reference outputs of the named cases
 
 Writes
   tests/golden/cosmos_subset.npz   inputs: the reference's demo catalogues (doc/COSMOS_*.fits) reduced to
@@ -53,9 +54,34 @@ def digest(res, names, stride):
 	return out
 
 
+def reference_outputs(only=None):
+	for name, spec in cases.GOLDEN_CASES.items():
+		if only and name not in only:
+			continue
+		tables = cases.build_case(name)
+		names = [t['name'] for t in tables]
+		res = refrun.run_reference(tables, spec['radius'], spec['completeness'], **spec.get('kwargs', {}))
+		# the oracle must agree with the real reference here and now, to the bit for the row set and
+		# to 1e-13 for the floats (it agrees to 0 ulp on this machine, but numpy SIMD paths may differ)
+		orc = O.nway_match(cases.build_case(name), spec['radius'], spec['completeness'], **spec.get('kwargs', {}))
+		for c in res.columns:
+			a, b = res[c].values, orc[c]
+			assert len(a) == len(b), (name, c)
+			if a.dtype.kind in 'iu':
+				assert (a == b).all(), (name, c)
+			else:
+				assert np.allclose(a, b, rtol=1e-13, atol=1e-300, equal_nan=True), (name, c)
+		d = digest(res, names, spec.get('stride', 37))
+		np.savez_compressed(os.path.join(GOLDEN, 'ref_%s.npz' % name), **d)
+		print('%-16s rows %8d  sum p_any %.12f' % (name, len(res), d['p_any'].sum()))
+
+
 def main():
 	os.makedirs(GOLDEN, exist_ok=True)
 	refrun.load_reference()
+	if len(sys.argv) > 1:
+		reference_outputs(only=set(sys.argv[1:]))
+		return
 
 	# ---- COSMOS subset fixture ------------------------------------------------------------
 	full = refrun.cosmos_tables(3, mags=True)
@@ -80,23 +106,7 @@ def main():
 	np.savez_compressed(os.path.join(GOLDEN, 'cosmos_subset.npz'), **fixture)
 
 	# ---- reference outputs ---------------------------------------------------------------------
-	for name, spec in cases.GOLDEN_CASES.items():
-		tables = cases.build_case(name)
-		names = [t['name'] for t in tables]
-		res = refrun.run_reference(tables, spec['radius'], spec['completeness'], **spec.get('kwargs', {}))
-		# the oracle must agree with the real reference here and now, to the bit for the row set and
-		# to 1e-13 for the floats (it agrees to 0 ulp on this machine, but numpy SIMD paths may differ)
-		orc = O.nway_match(cases.build_case(name), spec['radius'], spec['completeness'], **spec.get('kwargs', {}))
-		for c in res.columns:
-			a, b = res[c].values, orc[c]
-			assert len(a) == len(b), (name, c)
-			if a.dtype.kind in 'iu':
-				assert (a == b).all(), (name, c)
-			else:
-				assert np.allclose(a, b, rtol=1e-13, atol=1e-300, equal_nan=True), (name, c)
-		d = digest(res, names, spec.get('stride', 37))
-		np.savez_compressed(os.path.join(GOLDEN, 'ref_%s.npz' % name), **d)
-		print('%-16s rows %8d  sum p_any %.12f' % (name, len(res), d['p_any'].sum()))
+	reference_outputs()
 
 	# ---- known-answer vectors -------------------------------------------------------------------
 	nw = refrun.load_reference()

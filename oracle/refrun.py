@@ -8,8 +8,9 @@ import it.
 
 The reference cannot be imported as-is here because astropy, healpy and matplotlib
 are not installed.  We register inert stub modules for
-those three packages; the real nwaylib code then runs unchanged whenever
-fastskymatch.crossproduct takes its flat-sky branch (fastskymatch.py:94-98).
+those three packages; the real nwaylib code then runs unchanged: fastskymatch.crossproduct in its flat-sky branch
+(fastskymatch.py:94-98) needs nothing else, and for its HEALPix branch (:134-160) the three healpy functions it
+calls are provided by oracle/healpix_nest.py (a restatement of the published pixelisation).
 """
 import os
 import sys
@@ -63,12 +64,13 @@ def _install_stubs():
 	healpy = mod('healpy')
 	pixelfunc = mod('healpy.pixelfunc')
 	healpy.pixelfunc = pixelfunc
-	pixelfunc.nside2resol = lambda nside: numpy.sqrt(4 * numpy.pi / (12. * nside * nside))
-
-	def _nohealpy(*args, **kwargs):
-		raise NotImplementedError('healpy stub: the HEALPix branch cannot run here')
-	pixelfunc.ang2pix = _nohealpy
-	pixelfunc.get_all_neighbours = _nohealpy
+	# healpy is un-vendored and unpinned (pyproject.toml:53): its three calls on the path are restated in
+	# oracle/healpix_nest.py (published HEALPix algorithm, checked against healpy's docstring examples), so that the
+	# real crossproduct() can also take its HEALPix branch here (fastskymatch.py:134-160)
+	from oracle import healpix_nest
+	pixelfunc.nside2resol = healpix_nest.nside2resol
+	pixelfunc.ang2pix = healpix_nest.ang2pix
+	pixelfunc.get_all_neighbours = healpix_nest.get_all_neighbours
 
 	mpl = mod('matplotlib')
 	plt = mod('matplotlib.pyplot')

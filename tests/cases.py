@@ -53,6 +53,36 @@ def allsky(seed, counts, sigmas, names='ABCDEFGH'):
 	return out
 
 
+def allsky_hard(seed, counts, sigmas, radius_arcsec, ncluster=250):
+	"""all-sky catalogues with the difficult primaries put in by hand -- the two poles and their surroundings, both sides
+	of ra = 0 / 360, the corners where HEALPix base pixels meet -- and secondaries clustered around the primaries, so
+	that the match has real groups everywhere the sphere is awkward.  Takes the HEALPix branch of the reference's
+	crossproduct (fastskymatch.py:134-160)."""
+	rng = np.random.default_rng(seed)
+	tables = allsky(seed + 1, counts, sigmas)
+	p = tables[0]
+	hard_ra = [0.0, 359.99999, 0.00001, 123.0, 250.0, 180.0, 45.0, 135.0, 0.0, 90.0, 44.9999, 315.0, 90.0001]
+	hard_dec = [0.0, 10.0, -45.0, 89.9999, -89.99995, 90.0, 41.8103149, -41.8103149, 41.81, 0.0, 0.0001, 89.99, -90.0]
+	nh = len(hard_ra)
+	p['ra'][:nh] = hard_ra
+	p['dec'][:nh] = hard_dec
+	n0 = len(p['ra'])
+	for t in tables[1:]:
+		n = min(ncluster * 4, len(t['ra']))
+		k = np.concatenate((rng.integers(0, nh, n // 2), rng.integers(0, n0, n - n // 2)))
+		rad = np.radians(rng.uniform(0, 1.3 * radius_arcsec / 3600.0, n))
+		ang = rng.uniform(0, 2 * np.pi, n)
+		dec = p['dec'][k] + np.degrees(rad * np.cos(ang))
+		over, under = dec > 90, dec < -90
+		dec[over] = 180 - dec[over]
+		dec[under] = -180 - dec[under]
+		cosd = np.maximum(np.cos(np.radians(p['dec'][k])), 1e-6)
+		ra = (p['ra'][k] + np.degrees(rad * np.sin(ang)) / cosd + np.where(over | under, 180, 0)) % 360
+		t['ra'][:n] = ra
+		t['dec'][:n] = dec
+	return tables
+
+
 def config_c3(scale=1.0, seed=20260301):
 	"""BASELINE.json configs[2]: 1e5 x 1e7 uniform on 1 deg^2, sigma 1.0 / 0.2 arcsec, r = 5 arcsec,
 	completeness 0.9 (generator of SURVEY.md 8d).  scale < 1 shrinks the AREA at fixed surface density, so a
@@ -105,6 +135,9 @@ GOLDEN_CASES = {
 	'syn3_pcvec': dict(radius=8, completeness=np.array([1.0, 0.8, 0.6]), stride=151, kwargs=dict(prob_ratio_secondary=0.1)),
 	'syn4': dict(radius=6, completeness=0.95, stride=199),
 	'syn4_minprob': dict(radius=6, completeness=0.95, stride=23, kwargs=dict(min_prob=0.01)),
+	# whole sphere: the reference takes its HEALPix branch (healpy restated in oracle/healpix_nest.py)
+	'allsky2': dict(radius=120, completeness=0.9, stride=7),
+	'allsky3': dict(radius=300, completeness=0.8, stride=7),
 }
 
 
@@ -127,6 +160,10 @@ def build_case(name):
 		return uniform_patch(5, (500, 20000, 15000), (1.0, 0.3, 0.5), 0.1)
 	if name in ('syn4', 'syn4_minprob'):
 		return with_mags(uniform_patch(6, (200, 3000, 3000, 2500), (1.0, 0.4, 0.5, 0.8), 0.05), 3, cats=(2,), ncols=1)
+	if name == 'allsky2':
+		return allsky_hard(31, (600, 6000), (4.0, 2.0), 120.0)
+	if name == 'allsky3':
+		return allsky_hard(32, (400, 5000, 4000), (5.0, 3.0, 4.0), 300.0, ncluster=90)
 	raise KeyError(name)
 
 
