@@ -135,9 +135,13 @@ GOLDEN_CASES = {
 	'syn3_pcvec': dict(radius=8, completeness=np.array([1.0, 0.8, 0.6]), stride=151, kwargs=dict(prob_ratio_secondary=0.1)),
 	'syn4': dict(radius=6, completeness=0.95, stride=199),
 	'syn4_minprob': dict(radius=6, completeness=0.95, stride=23, kwargs=dict(min_prob=0.01)),
-	# whole sphere: the reference takes its HEALPix branch (healpy restated in oracle/healpix_nest.py)
-	'allsky2': dict(radius=120, completeness=0.9, stride=7),
-	'allsky3': dict(radius=300, completeness=0.8, stride=7),
+	# whole sphere: the reference takes its HEALPix branch (healpy restated in oracle/healpix_nest.py).  The oracle
+	# reproduces these to the bit; for the device the posterior-like columns are checked at 3e-9 = ln(10) x the 1e-9
+	# the parity metric allows on log BF: at |dec| ~ 90 the reference's separation formula (fastskymatch.py:44) cancels
+	# to an absolute 1e-16 rad, which a 1-ulp difference between CUDA's and glibc's sin / cos turns into a few 1e-11 of
+	# a 300-arcsec separation and, times separation / sigma^2, into up to ~1e-10 of the posteriors
+	'allsky2': dict(radius=120, completeness=0.9, stride=7, gpu_rtol=3e-9),
+	'allsky3': dict(radius=300, completeness=0.8, stride=7, gpu_rtol=3e-9),
 }
 
 

@@ -76,18 +76,18 @@ def load_golden(name):
 	return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
 
-def check_against_digest(name, got, names):
+def check_against_digest(name, got, names, rtol=None):
 	g = load_golden('ref_%s.npz' % name)
 	idx = np.stack([got[n] for n in names], axis=1).astype(np.int64)
 	assert len(idx) == int(g['nrows'])
 	sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(idx).tobytes()).digest(), dtype=np.uint8)
 	assert (sha == g['idx_sha256']).all(), 'row set / order differs from the reference'
 	starts = np.concatenate(([0], np.flatnonzero(np.diff(idx[:, 0]) != 0) + 1)) if len(idx) else np.zeros(0, dtype=np.int64)
-	ok, dabs, drel, worst = column_error('prob_has_match', g['p_any'], np.asarray(got['prob_has_match'])[starts])
+	ok, dabs, drel, worst = column_error('prob_has_match', g['p_any'], np.asarray(got['prob_has_match'])[starts], rtol)
 	assert ok, ('p_any', name, worst, dabs, drel)
 	sel = g['sample_rows']
 	ref = {str(c): g['col_' + str(c)] for c in g['columns']}
-	assert_tables_match(ref, {c: np.asarray(got[c])[sel] for c in ref}, context=name)
+	assert_tables_match(ref, {c: np.asarray(got[c])[sel] for c in ref}, context=name, rtol=rtol)
 	for c in ref:
 		v = np.asarray(got[c])
 		s = np.nansum(v[np.isfinite(v)]) if v.dtype.kind == 'f' else v.sum()

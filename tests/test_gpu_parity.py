@@ -33,9 +33,11 @@ def test_cuda_matches_oracle_and_reference(name):
 	ref = O.nway_match(tables, spec['radius'], spec['completeness'], **kw)
 	cols = [c for c in ref if not c.startswith('_')]
 	assert list(got.keys()) == cols, (list(got.keys()), cols)
-	lines = parity.assert_tables_match(ref, got, columns=cols, context=name)
+	# gpu_rtol: see tests/cases.py (the all-sky cases sit at high declinations, where the reference's own separation
+	# formula is ill-conditioned and 1-ulp differences of sin / cos show up at a few 1e-11 in the posteriors)
+	lines = parity.assert_tables_match(ref, got, columns=cols, context=name, rtol=spec.get('gpu_rtol'))
 	report(name, lines)
-	parity.check_against_digest(name, got, [t['name'] for t in tables])
+	parity.check_against_digest(name, got, [t['name'] for t in tables], rtol=spec.get('gpu_rtol'))
 
 
 @pytest.mark.parametrize('mode', ['cli'])
