@@ -6,7 +6,9 @@ command-line mode and by the host-side calibration code of the product (nway_b20
   doc/logs/match2-offset:30   24614 rows     doc/logs/match3-offset:32   220645 rows
   doc/logs/cutoff2            p_any cut-offs 0.82 / 0.77 / 0.74 / 0.67 with 9.35 / 22.43 / 30.05 / 47.86 % of the matches
   doc/logs/cutoff3            0.94 / 0.85 / 0.76 / 0.55 with 36.78 / 55.15 / 64.94 % (the last percentage is 78.13 in the log
-                              and 78.19 here: one of the 1797 sources sits on the 0.55 cut-off)
+                              and 78.19 here -- one of the 1797 sources sits on the 0.55 cut-off; the UNMODIFIED nway.py,
+                              run in this container through oracle/refcli.py on the same two command lines, also gives
+                              78.19: the published log predates the current code / numpy / scipy)
 """
 import io
 import os
