@@ -1,7 +1,11 @@
 // Device-side arithmetic of the nway match path.  fp64 throughout, compiled with --fmad=false so that the
 // operation order below IS the rounding order (the reference is unfused numpy).
 #pragma once
+#ifdef NWB_HOST_EMU
+#include "nwb_host_emu.h"   // tests/emu: the few CUDA names these headers use, for a plain host compiler
+#else
 #include <cuda_runtime.h>
+#endif
 #include <math.h>
 #include <stdint.h>
 
@@ -22,7 +26,11 @@ struct Sector32 { unsigned long long q[4]; };
 __device__ __forceinline__ Sector32 ldg_sector(const void *p /* 32-byte aligned */)
 {
 	Sector32 s;
+#ifdef NWB_HOST_EMU
+	s = *reinterpret_cast<const Sector32 *>(p);
+#else
 	asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s.q[0]), "=l"(s.q[1]), "=l"(s.q[2]), "=l"(s.q[3]) : "l"(p));
+#endif
 	return s;
 }
 
