@@ -1,0 +1,138 @@
+"""CPU: the device arithmetic, built for the host from the SAME source the CUDA library is compiled from
+(nway_b200/csrc/nwb_device.cuh through tests/emu/arith_emu.cpp), against numpy / the oracle on millions of arguments.
+What differs between this build and the device is only the math library underneath (glibc here, CUDA's there); what
+is checked is everything the source adds on top of it: the operation order of the reference, the division-free
+x/180 and x/pi, the polynomial shortcuts for small angles, the table-driven 10^x, the memo-free log Bayes factor."""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import nway_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = ctypes.c_void_p
+
+
+@pytest.fixture(scope='module')
+def emu(tmp_path_factory):
+	out = str(tmp_path_factory.mktemp('emu') / 'arith_emu.so')
+	res = subprocess.run(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared', '-w', '-I', os.path.join(ROOT, 'tests', 'emu'),
+		'-o', out, os.path.join(ROOT, 'tests', 'emu', 'arith_emu.cpp')], capture_output=True, text=True)
+	assert res.returncode == 0, res.stderr[-3000:]
+	return ctypes.CDLL(out)
+
+
+def ptr(a):
+	return a.ctypes.data
+
+
+def ulps(a, b):
+	with np.errstate(invalid='ignore', divide='ignore'):
+		return np.abs(a - b) / np.spacing(np.maximum(np.abs(a), np.abs(b)))
+
+
+def test_division_by_180_and_pi_is_the_ieee_quotient(emu):
+	rng = np.random.default_rng(0)
+	x = np.concatenate((rng.uniform(-400, 400, 3000000), rng.uniform(-1e-3, 1e-3, 1000000), 10 ** rng.uniform(-300, 300, 1000000),
+		np.array([0.0, -0.0, 180.0, 360.0, 90.0, np.pi, 1e-320, 5e-324])))
+	a, b = np.empty_like(x), np.empty_like(x)
+	emu.nwb_emu_div(ctypes.c_longlong(len(x)), P(ptr(x)), P(ptr(a)), P(ptr(b)))
+	assert (a == x / 180).all() and (b == x / np.pi).all()
+
+
+def test_separation_follows_the_reference_formula(emu):
+	rng = np.random.default_rng(1)
+	n = 2000000
+	ra1 = rng.uniform(0, 360, n)
+	dec1 = np.degrees(np.arcsin(rng.uniform(-1, 1, n)))
+	dec1[:1000] = np.where(rng.uniform(size=1000) < 0.5, 90.0, -90.0) - rng.uniform(-1e-6, 1e-6, 1000) ** 2 * np.sign(rng.uniform(-1, 1, 1000))
+	dec1 = np.clip(dec1, -90, 90)
+	step = 10 ** rng.uniform(-7, 1.0, n)                      # 0.4 milli-arcsec .. 10 degrees
+	ang = rng.uniform(0, 2 * np.pi, n)
+	dec2 = np.clip(dec1 + step * np.cos(ang), -90, 90)
+	ra2 = ra1 + step * np.sin(ang) / np.maximum(np.cos(np.radians(dec1)), 1e-3)
+	ra2[::7] = ra1[::7]
+	dec2[::11] = dec1[::11]
+	out = np.empty(n)
+	emu.nwb_emu_sep(ctypes.c_longlong(n), P(ptr(ra1)), P(ptr(dec1)), P(ptr(ra2)), P(ptr(dec2)), P(ptr(out)))
+	ref = O.dist((ra1, dec1), (ra2, dec2)) * 60 * 60
+	assert np.isfinite(out).all()
+	# the reference's formula loses ~1e-16 rad ABSOLUTE to cancellation (fastskymatch.py:44); the polynomial shortcuts
+	# must stay within that: a few 1e-11 arcsec, plus a few ulp of the value itself
+	err = np.abs(out - ref)
+	assert (err <= 6e-11 + 4 * np.spacing(ref)).all(), (err.max(), ref[np.argmax(err)], ra1[np.argmax(err)], dec1[np.argmax(err)])
+	same = ra2 == ra1
+	coincident = same & (dec2 == dec1)
+	assert (out[coincident] == 0).all()
+
+
+def test_exp10_table(emu):
+	rng = np.random.default_rng(2)
+	x = np.concatenate((rng.uniform(-330, 310, 3000000), rng.uniform(-1, 1, 1000000), np.array([0.0, -0.0, 1.0, -1.0, 308.25, -323.3, -400.0, 400.0, np.nan, np.inf, -np.inf])))
+	out = np.empty_like(x)
+	emu.nwb_emu_exp10(ctypes.c_longlong(len(x)), P(ptr(x)), P(ptr(out)))
+	with np.errstate(over='ignore', under='ignore'):
+		ref = np.power(10.0, x.astype(np.longdouble)).astype(np.float64)   # 80-bit power, rounded once
+	fin = np.isfinite(ref) & (ref > 1e-300)
+	assert ulps(out[fin], ref[fin]).max() <= 1.5
+	assert np.isnan(out[np.isnan(x)]).all() and (out[x == np.inf] == np.inf).all() and (out[x == -np.inf] == 0).all()
+	assert (out[x > 308.3] == np.inf).all() and (out[(x < -323.4)] == 0).all()
+	sub = np.isfinite(ref) & (ref <= 1e-300) & (ref > 0)
+	assert ulps(out[sub], ref[sub]).max() <= 2   # results near / below the normal range are scaled in two steps
+
+
+@pytest.mark.parametrize('ncat', [2, 3, 4])
+def test_log_bayes_factor(emu, ncat):
+	rng = np.random.default_rng(10 + ncat)
+	n = 300000
+	sig = rng.uniform(0.05, 5, (n, ncat))
+	npair = ncat * (ncat - 1) // 2
+	sep = rng.uniform(0, 30, (n, npair))
+	norm = np.array([(k - 1) * math.log(2) + 2 * (k - 1) * O.LOG_ARCSEC2RAD for k in range(ncat + 1)])
+	present = np.full(n, (1 << ncat) - 1, dtype=np.uint32)
+	out = np.empty(n)
+	emu.nwb_emu_log_bf(ctypes.c_longlong(n), ncat, P(ptr(norm)), ctypes.c_double(O.LOG10_E), P(ptr(present)), P(ptr(sig)), P(ptr(sep)), P(ptr(out)))
+	p = [[None] * ncat for _ in range(ncat)]
+	k = 0
+	for a in range(ncat):
+		for b in range(a + 1, ncat):
+			p[a][b] = sep[:, k]
+			k += 1
+	ref = O.log_bf(p, [sig[:, c] for c in range(ncat)])
+	# same operations in the same order, except w = sigma^-2: numpy's pow(sigma, -2.0) against 1 / (sigma * sigma) on the device
+	# (two roundings: up to 1 ulp apart), so the sums agree to a few ulp of their largest term
+	w = sig ** -2.
+	big = sum(w[:, a] * w[:, b] * p[a][b] ** 2 for a in range(ncat) for b in range(a + 1, ncat)) / 2 / w.sum(axis=1) * O.LOG10_E
+	tol = lambda r: 8 * np.spacing(np.maximum(np.maximum(np.abs(r), big), 64.0))   # the exponent term can dwarf the result
+	assert (np.abs(out - ref) <= tol(ref)).all(), np.abs(out - ref).max()
+	assert (out == ref).mean() > 0.5
+	# a sub-association (catalogue 1 absent) equals the Bayes factor of the remaining catalogues
+	if ncat >= 3:
+		present[:] = ((1 << ncat) - 1) & ~2
+		emu.nwb_emu_log_bf(ctypes.c_longlong(n), ncat, P(ptr(norm)), ctypes.c_double(O.LOG10_E), P(ptr(present)), P(ptr(sig)), P(ptr(sep)), P(ptr(out)))
+		keep = [c for c in range(ncat) if c != 1]
+		p2 = [[None] * len(keep) for _ in keep]
+		for i, a in enumerate(keep):
+			for j, b in enumerate(keep):
+				if i < j:
+					p2[i][j] = p[a][b]
+		ref2 = O.log_bf(p2, [sig[:, c] for c in keep])
+		assert (np.abs(out - ref2) <= tol(ref2)).all()
+
+
+def test_posterior(emu):
+	rng = np.random.default_rng(5)
+	n = 1000000
+	prior = 10 ** rng.uniform(-14, 0, n)
+	prior[:10] = 1.0
+	lbf = rng.uniform(-500, 40, n)
+	l10p = np.log10(prior)
+	out = np.empty(n)
+	emu.nwb_emu_posterior(ctypes.c_longlong(n), P(ptr(prior)), P(ptr(l10p)), P(ptr(lbf)), P(ptr(out)))
+	with np.errstate(invalid='ignore'):
+		ref = O.posterior(prior, lbf)   # prior = 1 with an overflowing exponential is 0 * inf = NaN in the reference too
+	assert np.allclose(out, ref, rtol=4e-16 * 3, atol=0, equal_nan=True)   # glibc's exp10 vs numpy's 10**x: a few ulp
