@@ -158,6 +158,46 @@ __device__ __forceinline__ double log_bf_ref(const ConstTables *__restrict__ T, 
 	return (T->norm[n] + slog + exponent) * T->log10e;
 }
 
+// ---- elliptical positional errors (CLI only in the reference): bayesdistance.py:164-240, fastskymatch.py:50-74 ----
+// Offsets (arcsec) of the target t in the tangent frame centred on the origin o: what astropy's
+// SkyOffsetFrame(origin=o) gives for t, with the sign of fastskymatch.py:65-66.
+__device__ __forceinline__ void offsets_ref(double ra_o, double dec_o, double ra_t, double dec_t, double &dra, double &ddec)
+{
+	const double D2R = 0.017453292519943295, R2D = 57.29577951308232;   // numpy.radians / numpy.degrees constants
+	double so, co, st, ct, sd, cd;
+	sincos(dec_o * D2R, &so, &co);
+	sincos(dec_t * D2R, &st, &ct);
+	sincos(ra_t * D2R - ra_o * D2R, &sd, &cd);
+	double lon = atan2(ct * sd, co * ct * cd + so * st);
+	double z = co * st - so * ct * cd;
+	double lat = asin(fmin(fmax(z, -1.0), 1.0));
+	dra = -(lon * R2D) * 60 * 60;
+	ddec = -(lat * R2D) * 60 * 60;
+}
+
+// v^T Sigma^-1 v for the unit vector v (bayesdistance.py:150-161,183-187)
+__device__ __forceinline__ double dir_precision(double vx, double vy, double sx, double sy, double rho)
+{
+	double f = 1.0 / (sx * sx * (sy * sy) * (1 - rho * rho));
+	double m11 = f * (sy * sy), m12 = f * -rho * sx * sy, m22 = f * (sx * sx);
+	double l1 = vx * m11 + vy * m12;
+	double l2 = vx * m12 + vy * m22;
+	return l1 * vx + l2 * vy;
+}
+
+// separation of one pair rescaled by the ratio of circular to directional error (bayesdistance.py:224-238)
+__device__ __forceinline__ double ell_rescaled_sep(double vx, double vy, double sxa, double sya, double rhoa,
+	double sxb, double syb, double rhob, double siga, double sigb)
+{
+	double d = sqrt(vx * vx + vy * vy);
+	double ux = d == 0 ? 0.7071067811865476 : vx / (d + 1e-300);
+	double uy = d == 0 ? 0.7071067811865476 : vy / (d + 1e-300);
+	double wa = dir_precision(ux, uy, sxa, sya, rhoa);
+	double wb = dir_precision(ux, uy, sxb, syb, rhob);
+	double ratio = (siga * siga + sigb * sigb) / (1 / wa + 1 / wb);
+	return d * (1.0 / sqrt(ratio));
+}
+
 // 10^x for the row kernels.  Same scheme as the CUDA library routine (k = rint(x log2 10), r = x - k log10 2 in two
 // pieces, degree-13 polynomial of 10^r, scale by 2^k) but with the coefficients in constant memory, so a call is
 // ~30 instructions instead of ~70 (the library materialises every 64-bit coefficient with two moves).  Checked

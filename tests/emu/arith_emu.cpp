@@ -55,4 +55,37 @@ void nwb_emu_posterior(long long n, const double *prior, const double *log10prio
 	for (long long i = 0; i < n; i++) out[i] = posterior_ref(prior[i], log10prior[i], lbf[i]);
 }
 
+// offsets (arcsec) of the target in the tangent frame of the origin: offsets_ref
+void nwb_emu_offsets(long long n, const double *ra_o, const double *dec_o, const double *ra_t, const double *dec_t, double *dra, double *ddec)
+{
+	for (long long i = 0; i < n; i++) offsets_ref(ra_o[i], dec_o[i], ra_t[i], dec_t[i], dra[i], ddec[i]);
+}
+
+// two catalogues with elliptical errors (sigma_x, sigma_y, rho): circularised errors, rescaled separation, log_bf_ref<2>
+// -- the per-row work of ell_prepare + the row kernels (nwb_kernels.cuh)
+void nwb_emu_log_bf_ell2(long long n, const double *norm, double log10e, const double *vx, const double *vy,
+	const double *ea /* n x 3 */, const double *eb /* n x 3 */, double *out)
+{
+	ConstTables T;
+	memset(&T, 0, sizeof(T));
+	for (int k = 0; k <= 2; k++) T.norm[k] = norm[k];
+	T.log10e = log10e;
+	for (long long i = 0; i < n; i++) {
+		const double *a = ea + 3 * i, *b = eb + 3 * i;
+		double sig[2] = {sqrt((a[0] * a[0] + a[1] * a[1]) / 2), sqrt((b[0] * b[0] + b[1] * b[1]) / 2)};
+		double sep[1] = {ell_rescaled_sep(vx[i], vy[i], a[0], a[1], a[2], b[0], b[1], b[2], sig[0], sig[1])};
+		out[i] = log_bf_ref<2>(&T, 2, 3u, sig, sep);
+	}
+}
+
+// zero-order-hold magnitude prior: mag_weight
+void nwb_emu_mag_weight(long long n, int nbins, const double *edges, const double *weight, const double *bias, const double *m, double *w, double *b)
+{
+	static MagTable M;
+	M.cat = 1; M.nbins = nbins; M.mag = nullptr;
+	for (int k = 0; k <= nbins; k++) M.edges[k] = edges[k];
+	for (int k = 0; k < nbins; k++) { M.weight[k] = weight[k]; M.bias[k] = bias[k]; }
+	for (long long i = 0; i < n; i++) w[i] = mag_weight(M, m[i], b[i]);
+}
+
 }  // extern "C"

@@ -136,3 +136,60 @@ def test_posterior(emu):
 	with np.errstate(invalid='ignore'):
 		ref = O.posterior(prior, lbf)   # prior = 1 with an overflowing exponential is 0 * inf = NaN in the reference too
 	assert np.allclose(out, ref, rtol=4e-16 * 3, atol=0, equal_nan=True)   # glibc's exp10 vs numpy's 10**x: a few ulp
+
+
+def test_tangent_plane_offsets(emu):
+	rng = np.random.default_rng(6)
+	n = 1000000
+	ra_o = rng.uniform(0, 360, n)
+	dec_o = np.degrees(np.arcsin(rng.uniform(-1, 1, n)))
+	step = 10 ** rng.uniform(-6, -0.5, n)
+	ang = rng.uniform(0, 2 * np.pi, n)
+	dec_t = np.clip(dec_o + step * np.cos(ang), -90, 90)
+	ra_t = (ra_o + step * np.sin(ang) / np.maximum(np.cos(np.radians(dec_o)), 1e-2)) % 360
+	dra, ddec = np.empty(n), np.empty(n)
+	emu.nwb_emu_offsets(ctypes.c_longlong(n), P(ptr(ra_o)), P(ptr(dec_o)), P(ptr(ra_t)), P(ptr(dec_t)), P(ptr(dra)), P(ptr(ddec)))
+	_, rdra, rddec = O.offsets((ra_o, dec_o), (ra_t, dec_t))
+	# the closed form cancels like the separation formula does: ~1e-16 rad absolute
+	assert (np.abs(dra - rdra * 3600) <= 8e-11 + 8 * np.spacing(np.abs(rdra * 3600))).all()
+	assert (np.abs(ddec - rddec * 3600) <= 8e-11 + 8 * np.spacing(np.abs(rddec * 3600))).all()
+
+
+def test_elliptical_bayes_factor(emu):
+	"""ell_rescaled_sep + log_bf_ref<2> against the oracle's log_bf_elliptical, itself pinned to the reference's
+	(tests/golden/kat.npz, test_kat_dist_logbf_posterior_elliptical)"""
+	rng = np.random.default_rng(7)
+	n = 500000
+	vx, vy = rng.normal(0, 3, n), rng.normal(0, 3, n)
+	vx[:100] = 0
+	vy[:100] = 0
+	ell = []
+	for _ in range(2):
+		a = rng.uniform(0.2, 4, n)
+		ell.append(O.convert_from_ellipse(a, a * rng.uniform(0.2, 1, n), rng.uniform(0, np.pi, n)))
+	ea = np.ascontiguousarray(np.stack(ell[0], axis=1))
+	eb = np.ascontiguousarray(np.stack(ell[1], axis=1))
+	norm = np.array([(k - 1) * math.log(2) + 2 * (k - 1) * O.LOG_ARCSEC2RAD for k in range(3)])
+	out = np.empty(n)
+	emu.nwb_emu_log_bf_ell2(ctypes.c_longlong(n), P(ptr(norm)), ctypes.c_double(O.LOG10_E), P(ptr(vx)), P(ptr(vy)), P(ptr(ea)), P(ptr(eb)), P(ptr(out)))
+	ref = O.log_bf_elliptical([[None, vx], [None, None]], [[None, vy], [None, None]], ell)
+	assert (np.abs(out - ref) <= 1e-12 * np.maximum(np.abs(ref), 100.0)).all(), np.abs(out - ref).max()
+
+
+def test_magnitude_prior_lookup(emu):
+	from nway_b200 import magnitudeweights
+	rng = np.random.default_rng(8)
+	nb = 16
+	edges = np.sort(rng.uniform(15, 28, nb + 1))
+	hs, ha = rng.uniform(0.01, 0.3, nb), rng.uniform(0.01, 0.3, nb)
+	ha[3] = 0.0    # ratio 100 (magnitudeweights.py:23)
+	hs[11] = 0.0   # ratio 0 -> weight -inf
+	e, weight, bias = magnitudeweights.step_tables(edges, hs, ha)
+	m = np.concatenate((rng.uniform(10, 32, 200000), edges, np.nextafter(edges, 40), np.nextafter(edges, 0), np.array([-99.0, np.nan, np.inf, -np.inf])))
+	w, b = np.empty_like(m), np.empty_like(m)
+	emu.nwb_emu_mag_weight(ctypes.c_longlong(len(m)), nb, P(ptr(e)), P(ptr(weight)), P(ptr(bias)), P(ptr(m)), P(ptr(w)), P(ptr(b)))
+	with np.errstate(divide='ignore', invalid='ignore'):
+		ref = np.log10(O.bias_lookup(edges, hs, ha, m))   # __init__.py:386: log10 of the interpolated ratio ...
+	ref[np.isnan(ref)] = 0                                    # ... NaN (outside the table, undefined magnitude) -> 0 (:388)
+	assert ((w == ref) | (np.isinf(w) & (w == ref))).all()
+	assert np.array_equal(b, 10 ** ref)
