@@ -231,6 +231,36 @@ __device__ __forceinline__ double nwb_exp10(double x)
 	return p * __hiloint2double((1023 + k1) << 20, 0) * __hiloint2double((1023 + k2) << 20, 0);
 }
 
+// Scalar pieces of the fused group normalisation of k_rows2 (__init__.py:423-457), with ONE exponential per row:
+//   t_k = 10^(v_k - m_rest) (k >= 1, m_rest = max of them),  s_rest = sum t_k,  p_i = t_k / s_rest.
+// p_any = 1 - 10^(v0 - bfsum), bfsum = log10(s_all) + m_all, s_all = sum 10^(v_k - m_all)   (__init__.py:428-439)
+//       = 1 - 10^(v0 - m_all) / s_all = [sum over k >= 1 of 10^(v_k - m_all)] / s_all
+// -- the same number without the logarithm, the second exponential and the cancellation of "1 -"; it differs from the
+// reference's rounding of that expression by the reference's own ~1e-14 (parity metric).  One of the two
+// exponents is zero: e0 = 10^(-|v0 - m_rest|).  rinv = 1 / s_rest (the largest t_k is exactly 1, so max p_i = rinv).
+__device__ __forceinline__ void group_p_any(int rows, double v0, double m_rest, double s_rest, double &p_any, double &rinv)
+{
+	p_any = 0.0;
+	rinv = 0.0;
+	if (rows > 1) {
+		const double m_all = fmax(v0, m_rest);
+		const double e0 = nwb_exp10(fmin(v0, m_rest) - m_all);
+		const double rest = v0 >= m_rest ? s_rest * e0 : s_rest;      // sum over k >= 1, scaled by 10^(-m_all)
+		const double s_all = v0 >= m_rest ? 1.0 + rest : rest + e0;
+		p_any = rest / s_all;
+		rinv = 1.0 / s_rest;
+	}
+}
+
+// dist_post = 1/(1 + (1 - prior) 10^(-v)) from the exponential the normalisation evaluated anyway: 10^(-v_k) =
+// 10^(-m_rest) / t_k, i.e. t_k / (t_k + oscale) with oscale = (1 - prior) 10^(-m_rest); the direct form where that
+// would leave the double range (|m_rest| > 250, t_k = 0)
+__device__ __forceinline__ double shared_post(bool direct, double t, double oscale, double omp, double lbf, double l10p1)
+{
+	if (direct || !(t > 1e-290)) return 1. / (1 + omp * nwb_exp10(-lbf - l10p1));
+	return t / (t + oscale);
+}
+
 // bayesdistance.py:26-32
 __device__ __forceinline__ double posterior_ref(double prior, double log10prior, double log_bf)
 {

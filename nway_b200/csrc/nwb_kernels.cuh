@@ -1333,7 +1333,6 @@ k_rows2(RowParams R)
 		__syncwarp();
 		const double v0 = M.v[0];
 		m_rest = warp_max(m_rest);
-		const double m_all = fmax(v0, m_rest);
 		double s_rest = 0.0;
 		for (int k = lane + (lane == 0 ? 32 : 0); k < rows; k += 32) {
 			double t = nwb_exp10(M.v[k] - m_rest);
@@ -1341,19 +1340,8 @@ k_rows2(RowParams R)
 			s_rest += t;
 		}
 		s_rest = warp_sum(s_rest);
-		double p_any = 0.0, rinv = 0.0;
-		if (rows > 1) {
-			// p_any = 1 - 10^(v0 - bfsum), bfsum = log10(s_all) + m_all, s_all = sum 10^(v_k - m_all)   (__init__.py:428-439)
-			//       = 1 - 10^(v0 - m_all) / s_all = [sum over k >= 1 of 10^(v_k - m_all)] / s_all
-			// -- the same number without the logarithm, the second exponential and the cancellation of "1 -"; it differs
-			// from the reference's rounding of that expression by the reference's own ~1e-14 (parity metric).
-			// One of the two exponents below is zero: e0 = 10^(-|v0 - m_rest|).
-			const double e0 = nwb_exp10(fmin(v0, m_rest) - m_all);
-			const double rest = v0 >= m_rest ? s_rest * e0 : s_rest;      // sum over k >= 1, scaled by 10^(-m_all)
-			const double s_all = v0 >= m_rest ? 1.0 + rest : rest + e0;
-			p_any = rest / s_all;
-			rinv = 1.0 / s_rest;
-		}
+		double p_any, rinv;
+		group_p_any(rows, v0, m_rest, s_rest, p_any, rinv);
 		// lone no-counterpart row: bfsum = v0 exactly, p_any = 1 - 10^0 = 0
 		__syncwarp();
 		const double best = rinv;   // the largest t_k is exactly 1, so max p_i = 1 * rinv (0 for a lone row)
@@ -1372,10 +1360,7 @@ k_rows2(RowParams R)
 			R.C.flag[row] = (pi == best) ? 1 : (pi > R.ratio_secondary * best ? 2 : 0);
 			if (SHARE) {
 				double post = 1.0;   // row 0: prior = 1, (1 - prior) * 10^0 = 0
-				if (k > 0) {
-					if (direct || !(t > 1e-290)) post = 1. / (1 + omp * nwb_exp10(-R.C.lbf[row] - l10p1));
-					else post = t / (t + oscale);
-				}
+				if (k > 0) post = shared_post(direct, t, oscale, omp, R.C.lbf[row], l10p1);
 				R.C.dist_post[row] = post;
 				R.C.p_single[row] = post;
 			}

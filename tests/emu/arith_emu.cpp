@@ -88,4 +88,45 @@ void nwb_emu_mag_weight(long long n, int nbins, const double *edges, const doubl
 	for (long long i = 0; i < n; i++) w[i] = mag_weight(M, m[i], b[i]);
 }
 
+// One group (one primary) through the fused normalisation of k_rows2<FUSE, SHARE> (nwb_kernels.cuh): rows 1.. are
+// distributed over 32 lanes (k = lane + 32 j), every lane sums its own exponentials, warp_sum adds the lanes in its
+// butterfly order; then group_p_any / shared_post (nwb_device.cuh) per row.  v = log-weights, lbf = log Bayes factors.
+void nwb_emu_group(int rows, const double *v, const double *lbf, double prior1, double l10p1, double ratio_secondary,
+	double *p_any_out, double *p_i, long long *flag, double *post)
+{
+	const double v0 = v[0];
+	double m_rest = -INFINITY;
+	for (int k = 1; k < rows; k++) m_rest = fmax(m_rest, v[k]);
+	double lane_sum[32];
+	double t[4096];
+	for (int lane = 0; lane < 32; lane++) {
+		double s = 0.0;
+		for (int k = lane + (lane == 0 ? 32 : 0); k < rows; k += 32) {
+			t[k] = nwb_exp10(v[k] - m_rest);
+			s += t[k];
+		}
+		lane_sum[lane] = s;
+	}
+	for (int o = 16; o > 0; o >>= 1) {   // warp_sum: v += shfl_xor(v, o)
+		double nxt[32];
+		for (int i = 0; i < 32; i++) nxt[i] = lane_sum[i] + lane_sum[i ^ o];
+		for (int i = 0; i < 32; i++) lane_sum[i] = nxt[i];
+	}
+	const double s_rest = lane_sum[0];
+	double p_any, rinv;
+	group_p_any(rows, v0, m_rest, s_rest, p_any, rinv);
+	const double best = rinv;
+	const bool direct = !(fabs(m_rest) <= 250.0);
+	const double oscale = (rows > 1 && !direct) ? (1 - prior1) * nwb_exp10(-m_rest) : 0.0;
+	const double omp = 1 - prior1;
+	for (int k = 0; k < rows; k++) {
+		const double tk = k == 0 ? v0 : t[k];
+		const double pi = k == 0 ? 0.0 : tk * rinv;
+		p_i[k] = pi;
+		flag[k] = (pi == best) ? 1 : (pi > ratio_secondary * best ? 2 : 0);
+		post[k] = k == 0 ? 1.0 : shared_post(direct, tk, oscale, omp, lbf[k], l10p1);
+	}
+	*p_any_out = p_any;
+}
+
 }  // extern "C"

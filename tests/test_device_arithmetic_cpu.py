@@ -193,3 +193,51 @@ def test_magnitude_prior_lookup(emu):
 	ref[np.isnan(ref)] = 0                                    # ... NaN (outside the table, undefined magnitude) -> 0 (:388)
 	assert ((w == ref) | (np.isinf(w) & (w == ref))).all()
 	assert np.array_equal(b, 10 ** ref)
+
+
+def test_fused_group_normalisation(emu):
+	"""the one-exponential-per-row normalisation of k_rows2 (p_any without the logarithm and the "1 -", p_i from the
+	shared exponentials, dist_post from the same exponentials) against the reference's formulas (__init__.py:423-457,
+	bayesdistance.py:26-32) on random groups: ordinary ones, groups dominated by the no-counterpart row or by one
+	counterpart, log-weights hundreds of decades apart, ties, lone rows"""
+	rng = np.random.default_rng(9)
+	prior1 = 3.7e-4
+	l10p1 = float(np.log10(prior1))
+	worst = dict(p_any=0.0, p_i=0.0, post=0.0)
+	ngroups = 30000
+	for g in range(ngroups):
+		rows = int(rng.integers(1, 129))
+		kind = g % 6
+		spread = [3, 30, 300, 3, 3, 1000][kind]
+		lbf = rng.normal(0, spread, rows)
+		if kind == 3:
+			lbf[1:] -= rng.uniform(0, 40)       # the no-counterpart row dominates
+		if kind == 4 and rows > 2:
+			lbf[2] = lbf[1]                         # a tie for the best counterpart
+		lbf[0] = 0.0
+		v = lbf + l10p1
+		v[0] = 0.0                                  # row 0: log10(prior = 1) + log BF 0
+		p_any = ctypes.c_double()
+		p_i, post = np.empty(rows), np.empty(rows)
+		flag = np.empty(rows, dtype=np.int64)
+		emu.nwb_emu_group(rows, P(ptr(v)), P(ptr(lbf)), ctypes.c_double(prior1), ctypes.c_double(l10p1), ctypes.c_double(0.5),
+			ctypes.byref(p_any), P(ptr(p_i)), P(ptr(flag)), P(ptr(post)))
+		with np.errstate(over='ignore', divide='ignore', invalid='ignore'):
+			rpa, rpi, rflag = O.group_statistics(v, [0], 0.5)
+			rpost = O.posterior(np.r_[1.0, np.full(rows - 1, prior1)], lbf)
+		if rows > 1 and not np.isfinite(rpi).all():
+			continue   # the reference itself overflows here (10**(v - bfsum1) with bfsum1 = -inf)
+		# the parity metric of tests/parity.py
+		assert abs(p_any.value - rpa[0]) <= 1e-10 * abs(rpa[0]) + 2e-13, (g, rows, p_any.value, rpa[0])
+		big = rpi >= 1e-30
+		assert (np.abs(p_i[big] - rpi[big]) <= 1e-10 * rpi[big]).all() and (np.abs(p_i[~big] - rpi[~big]) <= 1e-40).all(), (g, rows)
+		ok = np.abs(post - rpost) <= 1e-10 * np.abs(rpost) + 1e-300
+		assert ok.all(), (g, rows, post[~ok], rpost[~ok])
+		# flags: exact unless a p_i sits on the 0.5 x best threshold or ties with the best within rounding
+		sure = (np.abs(rpi - 0.5 * rpi.max()) > 1e-9 * rpi.max()) & ((rpi == rpi.max()) | (np.abs(rpi - rpi.max()) > 1e-9 * rpi.max()))
+		assert (flag[sure] == rflag[sure]).all(), (g, rows)
+		worst['p_any'] = max(worst['p_any'], abs(p_any.value - rpa[0]))
+		if big.any():
+			worst['p_i'] = max(worst['p_i'], float(np.max(np.abs(p_i[big] - rpi[big]) / rpi[big])))
+	print('worst differences from the reference formulas over %d groups: %s' % (ngroups, worst))
+	assert worst['p_i'] < 5e-12 and worst['p_any'] < 2e-13, worst
