@@ -43,6 +43,18 @@ __device__ __forceinline__ double div_const(double x, double b, double rb)
 	double r = fma(-q, b, x);
 	return fma(r, rb, q);
 }
+// a / b from a reciprocal y = RN(1 / b) that is already there (the row kernels memoise it per error value): the
+// correctly rounded quotient (Markstein: q0 = RN(a y), r = a - b q0 exactly by FMA, RN(q0 + r y) = RN(a / b)) as long as
+// nothing under- or overflows on the way -- anything else (a huge or tiny, b denormal-ish) takes the division.
+__device__ __forceinline__ double quotient_by_reciprocal(double a, double b, double y)
+{
+	if (fabs(a) < 1e280 && fabs(a) > 1e-280 && b > 1e-280 && b < 1e280) {
+		double q0 = a * y;
+		double rr = fma(-q0, b, a);
+		return fma(rr, y, q0);
+	}
+	return a / b;
+}
 #define NWB_INV180 (1.0 / 180.0)
 #define NWB_INVPI (1.0 / NWB_PI)
 

@@ -1202,18 +1202,8 @@ __device__ __forceinline__ void rows2_write(const RowParams &R, const ConstTable
 		double wsum = memo.wsum;
 		double slog = lw0 + memo.lw1 - memo.lwsum;
 		double q = w0 * w1 * (R.sep_f32 ? (double) __fmul_rn((float) sep, (float) sep) : sep * sep);
-		// -q / 2 / wsum: the halving is exact; the quotient is the correctly rounded one (Markstein: with y = RN(1/b),
-		// q0 = RN(a y), r = a - b q0 exactly by FMA, RN(q0 + r y) = RN(a / b)) as long as nothing under/overflows --
-		// anything else (q huge or wsum denormal-ish) takes the division
-		double hq = -q / 2;
-		double exponent;
-		if (fabs(hq) < 1e280 && fabs(hq) > 1e-280 && wsum > 1e-280 && wsum < 1e280) {
-			double q0 = hq * memo.rwsum;
-			double rr = fma(-q0, wsum, hq);
-			exponent = fma(rr, memo.rwsum, q0);
-		} else {
-			exponent = hq / wsum;
-		}
+		// -q / 2 / wsum: the halving is exact, the quotient comes from the memoised reciprocal (quotient_by_reciprocal)
+		const double exponent = quotient_by_reciprocal(-q / 2, wsum, memo.rwsum);
 		lbf = (T->norm[2] + slog + exponent) * T->log10e;
 	}
 	unsigned smask = present ? 1u : 0u;

@@ -27,6 +27,11 @@ void nwb_emu_div(long long n, const double *x, double *by180, double *bypi)
 	}
 }
 
+void nwb_emu_quotient(long long n, const double *a, const double *b, double *out)
+{
+	for (long long i = 0; i < n; i++) out[i] = quotient_by_reciprocal(a[i], b[i], 1.0 / b[i]);
+}
+
 void nwb_emu_exp10(long long n, const double *x, double *out)
 {
 	for (long long i = 0; i < n; i++) out[i] = nwb_exp10(x[i]);

@@ -44,6 +44,22 @@ def test_division_by_180_and_pi_is_the_ieee_quotient(emu):
 	assert (a == x / 180).all() and (b == x / np.pi).all()
 
 
+def test_quotient_from_memoised_reciprocal_is_the_ieee_quotient(emu):
+	"""-q / 2 / wsum of the 2-catalogue Bayes factor (bayesdistance.py:84) without a division per row"""
+	rng = np.random.default_rng(12)
+	n = 6000000
+	a = -(10 ** rng.uniform(-12, 12, n)) * rng.uniform(0.5, 1, n)
+	b = 10 ** rng.uniform(-6, 8, n) * rng.uniform(0.5, 1, n)
+	a[:1000] = -(10 ** rng.uniform(-300, 300, 1000))
+	b[1000:2000] = 10 ** rng.uniform(-300, 300, 1000)
+	a[2000:2010] = [0.0, -0.0, -1e-320, -5e-324, -1e308, -np.inf, np.nan, -1.0, -3.0, -1e-281]
+	out = np.empty(n)
+	emu.nwb_emu_quotient(ctypes.c_longlong(n), P(ptr(a)), P(ptr(b)), P(ptr(out)))
+	with np.errstate(over='ignore', under='ignore', invalid='ignore'):
+		ref = a / b
+	assert ((out == ref) | (np.isnan(out) & np.isnan(ref))).all()
+
+
 def test_separation_follows_the_reference_formula(emu):
 	rng = np.random.default_rng(1)
 	n = 2000000
