@@ -89,3 +89,33 @@ def test_cli_correction_reproduces_recorded_explain_log():
 	assert np.allclose(top, [0.71, 0.21, 0.04, 0.03, 0.01], atol=0.006)
 	api = O.nway_match(tables, 20, 1.0, unrelated_mode='api')
 	assert abs(api['prob_has_match'][g][0] - 0.9696) < 0.001
+
+
+def test_flat_hash_predicate_reproduces_the_reference_row_set():
+	"""the row-set switch planned for the device: the complete enumeration, restricted to the
+	tuples whose present members span at most one cell of `radius` degrees in int(ra / err) and in int(dec / err)
+	(fastskymatch.py:125-132), IS the reference's flat-sky row set -- also where that hash is incomplete (mid-latitudes)"""
+	from tests.test_gpu_fuzz import random_case
+	incomplete = 0
+	for seed in (1003, 1004, 1019, 1038, 1071, 2059, 2074):
+		tables, radius, pc, kw, kind = random_case(seed)
+		assert not kw
+		err = radius / 3600
+		assert O.flat_sky_applicable([(t['ra'], t['dec']) for t in tables], err)
+		full = O.nway_match([dict(t) for t in tables], radius, pc)
+		ref = O.nway_match([dict(t) for t in tables], radius, pc, enumerator='refhash')
+		names = [t['name'] for t in tables]
+		idx = np.stack([full[n] for n in names], axis=1)
+		big = np.iinfo(np.int64).max
+		lo = np.full((2, len(idx)), big)
+		hi = np.full((2, len(idx)), -big)
+		for c, t in enumerate(tables):
+			present = idx[:, c] >= 0
+			for k, coord in enumerate((t['ra'], t['dec'])):
+				cell = np.trunc(coord / err).astype(np.int64)[np.maximum(idx[:, c], 0)]   # python's int() truncates toward zero
+				lo[k] = np.where(present, np.minimum(lo[k], cell), lo[k])
+				hi[k] = np.where(present, np.maximum(hi[k], cell), hi[k])
+		keep = ((hi - lo) <= 1).all(axis=0)
+		assert set(map(tuple, idx[keep].tolist())) == set(map(tuple, np.stack([ref[n] for n in names], axis=1).tolist())), seed
+		incomplete += int(keep.sum() < len(idx))
+	assert incomplete >= 4
