@@ -27,3 +27,33 @@ def test_greatarc_interpolate():
 		ra, dec = calibrate.greatarc_interpolate(a, b, f)
 		d = O.dist(a, b)
 		assert abs(O.dist(a, (ra, dec)) - f * d) < 1e-12 and abs(O.dist((ra, dec), b) - (1 - f) * d) < 1e-12
+
+
+def test_helper_command_lines_without_a_gpu(tmp_path):
+	"""the root scripts are thin wrappers around nway_b200/calibrate_cli.py: argument handling, FITS I/O and the cut-off
+	table run on the host (the collision searches of the other two need the device and are covered by the GPU tests)"""
+	import os
+	import subprocess
+	import sys
+	from nway_b200 import fitsio
+	from tests import cases
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	paths = cases.write_cosmos_subset_fits(str(tmp_path))
+	# no shift given: the reference's error message, exit code 1, nothing written
+	res = subprocess.run([sys.executable, os.path.join(root, 'nway-create-shifted-catalogue.py'), '--radius', '40', paths['XMM'], str(tmp_path / 'out.fits')],
+		capture_output=True, text=True)
+	assert res.returncode == 1 and 'ERROR: You have to set either shift-ra or shift-dec to non-zero' in res.stdout, res.stderr[-500:]
+	assert not os.path.exists(str(tmp_path / 'out.fits'))
+	res = subprocess.run([sys.executable, os.path.join(root, 'nway-create-fake-catalogue.py'), '--help'], capture_output=True, text=True)
+	assert res.returncode == 0 and '--seed' in res.stdout and '--radius' in res.stdout
+	# cut-off table from two match tables on disk
+	rng = np.random.default_rng(3)
+	for name, a, b in (('real.fits', 5, 2), ('fake.fits', 1, 6)):
+		n = 2000
+		fitsio.write_table(str(tmp_path / name), [fitsio.Column('ncat', 'I', np.where(np.arange(n) % 3 == 0, 1, 2)),
+			fitsio.Column('p_any', 'E', rng.beta(a, b, n)), fitsio.Column('p_i', 'E', rng.uniform(size=n)), fitsio.Column('match_flag', 'I', np.ones(n))], 'NWAYMATCH')
+	res = subprocess.run([sys.executable, os.path.join(root, 'nway-calibrate-cutoff.py'), 'real.fits', 'fake.fits'], capture_output=True, text=True, cwd=str(tmp_path))
+	assert res.returncode == 0, res.stderr[-1000:]
+	assert 'For a false detection rate of <1%' in res.stdout and 'created table "real.fits_p_any_cutoffquality.txt"' in res.stdout
+	tab = np.loadtxt(str(tmp_path / 'real.fits_p_any_cutoffquality.txt'))
+	assert tab.shape == (101, 3) and tab[0, 0] == 0 and tab[-1, 0] == 1
