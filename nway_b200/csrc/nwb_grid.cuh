@@ -117,6 +117,15 @@ struct CellRec {
 	unsigned long long q[4];
 };
 
+// Half-width in ra (degrees) of the box that contains every point within rb degrees of a source at declination d
+// (the small circle's extreme longitudes: sin(dra) = sin(rb) / cos(d)), slightly inflated; 360 = "all of ra" near a pole.
+__device__ __forceinline__ double search_box_dra(double d, double rb)
+{
+	if (fabs(d) + rb >= 89.999) return 360.0;
+	double s = sin(rb / 180 * NWB_PI) / cos((fabs(d)) / 180 * NWB_PI);
+	return s >= 1.0 ? 360.0 : asin(s) * 180 / NWB_PI * (1 + 1e-9) + 1e-12;
+}
+
 // Register one primary in every grid cell its (slightly inflated) search box overlaps.
 // FILL = false: cellcnt[cell] += 1.
 // FILL = true : take a slot of the cell by counting cellcnt back down (no second memset).  Slots 0..2 live INSIDE the

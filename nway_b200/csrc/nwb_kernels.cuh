@@ -67,13 +67,7 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 		pr.lon = deg2rad_ref(r); pr.slat = sl; pr.clat = cl; pr.spare = 0.0;
 		P.rec[i] = pr;
 		double rn = wrap360(r);
-		double dra;
-		if (fabs(d) + rb >= 89.999) {
-			dra = 360.0;
-		} else {
-			double s = sin(rb / 180 * NWB_PI) / cos((fabs(d)) / 180 * NWB_PI);
-			dra = s >= 1.0 ? 360.0 : asin(s) * 180 / NWB_PI * (1 + 1e-9) + 1e-12;
-		}
+		const double dra = search_box_dra(d, rb);
 		P.ra_n[i] = rn;
 		P.dec[i] = d;
 		P.dra[i] = dra;

@@ -27,11 +27,7 @@ void bounding_box(int np, const double *ra, const double *dec, double rb, std::v
 	for (int i = 0; i < np; i++) {
 		double r = ra[i], d = dec[i];
 		rn[i] = wrap360(r);
-		if (fabs(d) + rb >= 89.999) dra[i] = 360.0;
-		else {
-			double s = sin(rb / 180 * NWB_PI) / cos((fabs(d)) / 180 * NWB_PI);
-			dra[i] = s >= 1.0 ? 360.0 : asin(s) * 180 / NWB_PI * (1 + 1e-9) + 1e-12;
-		}
+		dra[i] = search_box_dra(d, rb);
 		double rn_b = wrap360(rn[i] + 180.0);
 		v[0] = std::min(v[0], d); v[1] = std::max(v[1], d);
 		v[2] = std::min(v[2], rn[i] - dra[i]); v[3] = std::max(v[3], rn[i] + dra[i]);
