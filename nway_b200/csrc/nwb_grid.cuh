@@ -215,6 +215,26 @@ __device__ __forceinline__ void prim_register(const Grid &G, const int i, const 
 		}
 	}
 }
+// Where a secondary falls in the grid (first stage of k_pairs; the band record B is fetched in between): declination in
+// band heights from the lower edge (valid if 0 <= t < nbands), ra in degrees from the grid origin in [0, 360) (valid if
+// the grid spans the circle or x <= ra_span), the cell along ra (clamped like racell_of) and the position in cell widths.
+__device__ __forceinline__ double k1_band_coord(const Grid &G, double dec) { return (dec - G.dec_lo) * G.inv_h; }
+
+__device__ __forceinline__ double k1_ra_coord(const Grid &G, double ra)
+{
+	double x = wrap360(ra) - G.ra_org_n;
+	if (x < 0.0) x += 360.0;
+	return x;
+}
+
+__device__ __forceinline__ double k1_ra_cell(const BandRec &B, double x, int &ic)
+{
+	const double xcells = x * B.inv_w;
+	ic = __double2int_rd(xcells);
+	ic = ic >= B.nra ? B.nra - 1 : (ic < 0 ? 0 : ic);
+	return xcells;
+}
+
 // the fp32 flat pre-test (see struct Entry); (x, y) = the secondary relative to the grid origin
 __device__ __forceinline__ bool k1_pretest(const Grid &G, float x, float y, float ex, float ey, float eclat)
 {

@@ -329,11 +329,9 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 		unsigned long long e0 = 0, e1 = 0, e2 = 0;
 		float xr = 0.f, yr = 0.f, kx = 0.f;
 		if (i < n) {
-			double y = d - G.dec_lo;
-			double t = y * G.inv_h;
+			const double t = k1_band_coord(G, d);
 			if (t >= 0.0 && t < nbands_d) {
-				double x = wrap360(r) - G.ra_org_n;
-				if (x < 0.0) x += 360.0;
+				const double x = k1_ra_coord(G, r);
 				if (G.full_circle || x <= G.ra_span) {
 					const int b = __double2int_rd(t);
 					BandRec B;
@@ -345,9 +343,8 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 						B = load_band(G, b);
 						kx = __ldg(G.kx + b);
 					}
-					const double xcells = x * B.inv_w;
-					int ic = __double2int_rd(xcells);
-					ic = ic >= B.nra ? B.nra - 1 : (ic < 0 ? 0 : ic);
+					int ic;
+					const double xcells = k1_ra_cell(B, x, ic);
 					const int cell = B.base + ic;
 					if (DENSE || !G.bits || (__ldg(G.bits + (cell >> 5)) >> (cell & 31) & 1u)) {
 						const Sector32 cr = ldg_sector(cells + cell);   // one sector, one request

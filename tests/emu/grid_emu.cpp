@@ -1,7 +1,7 @@
 // Host emulation of what decides WHICH pairs reach the exact test on the device: the grid chosen from the primaries
 // (build_grid / pretest_constants, nwb_grid_host.h), the registration of every primary in the cells its search box
-// overlaps and the packed / fp32 cell entries (prim_register, nwb_grid.cuh), the cell a secondary falls into (the
-// arithmetic of k_pairs' first stage, restated below from nwb_kernels.cuh) and the two fp32 pre-tests.  The device
+// overlaps and the packed / fp32 cell entries (prim_register, nwb_grid.cuh), the cell a secondary falls into (k1_band_coord /
+// k1_ra_coord / k1_ra_cell: the functions k_pairs' first stage calls) and the two fp32 pre-tests.  The device
 // functions are compiled here from the SAME headers the library is built from (tests/emu/nwb_host_emu.h provides the
 // handful of CUDA names they use).
 //
@@ -102,17 +102,15 @@ long long nwb_emu_check(int np, const double *pra, const double *pdec, int ns, c
 		stats[0]++;
 		// first stage of k_pairs (nwb_kernels.cuh): the cell of the secondary and its position inside it
 		bool found = false;
-		const double t = (d - G.dec_lo) * G.inv_h;
+		const double t = k1_band_coord(G, d);
 		if (t >= 0.0 && t < nbands_d) {
-			double x = wrap360(r) - G.ra_org_n;
-			if (x < 0.0) x += 360.0;
+			const double x = k1_ra_coord(G, r);
 			if (G.full_circle || x <= G.ra_span) {
 				const int b = __double2int_rd(t);
 				const BandRec B = load_band(G, b);
 				const float kx = G.kx[b];
-				const double xcells = x * B.inv_w;
-				int ic = __double2int_rd(xcells);
-				ic = ic >= B.nra ? B.nra - 1 : (ic < 0 ? 0 : ic);
+				int ic;
+				const double xcells = k1_ra_cell(B, x, ic);
 				const int cell = B.base + ic;
 				const CellRec &cr = cells[cell];
 				const int ecnt = (int) (unsigned) cr.q[0], estart = (int) (cr.q[0] >> 32);
@@ -123,8 +121,7 @@ long long nwb_emu_check(int np, const double *pra, const double *pdec, int ns, c
 					} else {
 						// k1_items
 						const Entry &en = entries[estart + e];
-						double xx = wrap360(r) - G.ra_org_n;
-						if (xx < 0.0) xx += 360.0;
+						const double xx = k1_ra_coord(G, r);
 						if (en.p == p && k1_pretest(G, (float) xx, (float) (d - G.dec_lo), en.x, en.y, en.clat)) { found = true; stats[2]++; }
 					}
 				}
