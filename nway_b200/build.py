@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libnwayb200.so')
 SOURCES = ['nwb_api.cu']
-HEADERS = ['nwb_device.cuh', 'nwb_grid.cuh', 'nwb_grid_host.h', 'nwb_kernels.cuh', os.path.join('..', '..', 'include', 'nwayb200.h')]
+HEADERS = ['nwb_device.cuh', 'nwb_grid.cuh', 'nwb_grid_host.h', 'nwb_rows.cuh', 'nwb_kernels.cuh', os.path.join('..', '..', 'include', 'nwayb200.h')]
 
 NVCC_FLAGS = [
 	'-gencode', 'arch=compute_100a,code=sm_100a',

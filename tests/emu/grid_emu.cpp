@@ -9,34 +9,11 @@
 // arithmetic) is below the radius, the secondary's cell must hold an entry of that primary and the entry must pass its
 // pre-test -- otherwise the device would silently lose a row.  Returns the number of such misses.
 #define NWB_HOST_EMU 1
-#include "../../nway_b200/csrc/nwb_grid_host.h"
+#include "emu_k0.h"
 
-#include <cstdio>
 #include <cstdlib>
-#include <vector>
 
 using namespace nwb;
-
-namespace {
-
-// order-preserving bounding-box reduction of k_prim_prep (nwb_kernels.cuh), as plain min / max
-void bounding_box(int np, const double *ra, const double *dec, double rb, std::vector<double> &rn, std::vector<double> &dra, double red[6])
-{
-	double v[6] = {1e300, -1e300, 1e300, -1e300, 1e300, -1e300};
-	rn.resize(np); dra.resize(np);
-	for (int i = 0; i < np; i++) {
-		double r = ra[i], d = dec[i];
-		rn[i] = wrap360(r);
-		dra[i] = search_box_dra(d, rb);
-		double rn_b = wrap360(rn[i] + 180.0);
-		v[0] = std::min(v[0], d); v[1] = std::max(v[1], d);
-		v[2] = std::min(v[2], rn[i] - dra[i]); v[3] = std::max(v[3], rn[i] + dra[i]);
-		v[4] = std::min(v[4], rn_b - dra[i]); v[5] = std::max(v[5], rn_b + dra[i]);
-	}
-	for (int k = 0; k < 6; k++) red[k] = v[k];
-}
-
-}  // namespace
 
 extern "C" {
 
@@ -46,46 +23,13 @@ extern "C" {
 long long nwb_emu_check(int np, const double *pra, const double *pdec, int ns, const double *sra, const double *sdec,
 	double radius_arcsec, long long npairs, const int *pi, const int *si, long long max_cells_override, long long *stats, int *first_miss)
 {
-	const double r_deg = radius_arcsec / 3600.0;
-	const double rb = r_deg * (1 + 1e-9) + 1e-12;
-	const double rb_ins = rb + 1e-9, dra_eps = 1e-9;
-	std::vector<double> rn, dra;
-	double red[6];
-	bounding_box(np, pra, pdec, rb, rn, dra, red);
-	HostGrid HG;
-	long long max_cells = std::min<long long>(2ll << 20, std::max<long long>(1ll << 16, 16 * (long long) np));   // nwb_api.cu match_impl
-	if (max_cells_override > 0) max_cells = max_cells_override;
-	build_grid(red, rb_ins, rb_ins, max_cells, HG);
-	pretest_constants(HG, rb_ins);
-	Grid G = HG.g;
-	G.bands = HG.bands.data();
-	G.kx = HG.kx.data();
-	G.bits = nullptr;
-	const double entry_tau_max = (rb_ins * M_PI / 180 > 0.02) ? -1.0 : 0.02;
-	// K0: count, headers, fill (k_prim_prep<COUNT> / k_cell_headers / k_prim_cells<true>, one thread after the other)
-	std::vector<int> cellcnt(G.ncells + 1, 0);
-	std::vector<CellRec> cells(G.ncells);
-	std::vector<double> clat(np);
-	for (int i = 0; i < np; i++) {
-		const double cl = cos(deg2rad_ref(pdec[i]));
-		const double tau = (rb_ins / 180 * NWB_PI) * tan(fmin(fabs(pdec[i]), 89.9999) / 180 * NWB_PI);
-		clat[i] = (tau > entry_tau_max || dra[i] >= 180.0) ? 0.0 : (double) __double2float_rd(cl);
-		prim_register<false>(G, i, pdec[i], rn[i], dra[i], cl, rb_ins, dra_eps, 0, 1, cellcnt.data(), nullptr, nullptr);
-	}
-	long long total = 0, regs = 0;
-	for (long long c = 0; c < G.ncells; c++) {
-		const int cnt = cellcnt[c];
-		const int start = (int) total - 3;
-		total += cnt > 3 ? cnt - 3 : 0;
-		regs += cnt;
-		cells[c].q[0] = (unsigned long long) (unsigned) cnt | ((unsigned long long) (unsigned) start << 32);
-	}
-	std::vector<Entry> entries(total + 1);
-	for (int i = 0; i < np; i++)
-		for (int bslot = 0; bslot < 4; bslot++)   // the four threads of a primary in k_prim_cells
-			prim_register<true>(G, i, pdec[i], rn[i], dra[i], clat[i], rb_ins, dra_eps, bslot, 4, cellcnt.data(), cells.data(), entries.data());
-	for (long long c = 0; c < G.ncells; c++)
-		if (cellcnt[c] != 0) { fprintf(stderr, "grid_emu: count and fill disagree in cell %lld\n", c); return -1; }
+	emu::K0 K;
+	emu::build_k0(K, np, pra, pdec, radius_arcsec, max_cells_override);
+	if (!K.ok) return -1;
+	const Grid &G = K.G;
+	const std::vector<CellRec> &cells = K.cells;
+	const std::vector<Entry> &entries = K.entries;
+	const long long regs = K.registrations;
 	stats[0] = stats[1] = stats[2] = 0;
 	stats[3] = G.ncells; stats[4] = G.nbands; stats[5] = regs;
 	long long misses = 0;

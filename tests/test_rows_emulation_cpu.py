@@ -1,0 +1,72 @@
+"""CPU: a whole two-catalogue match computed on the host from the device's own per-element source
+(tests/emu/rows_emu.cpp: grid, registration, pre-tests, exact separation, rows2_write, the fused one-exponential group
+normalisation -- nwb_grid.cuh / nwb_rows.cuh / nwb_device.cuh built with g++), against the oracle with the parity
+metric of the GPU tests: identical row set and order, integer columns exact, floats within 1e-10.  The GPU tests do the
+same through the real kernels; this one runs where there is no GPU and covers everything but the kernels'
+orchestration (queues, slots, the in-group sort)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import nway_oracle as O
+from tests import cases, parity
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = ctypes.c_void_p
+
+
+@pytest.fixture(scope='module')
+def emu(tmp_path_factory):
+	out = str(tmp_path_factory.mktemp('emu') / 'rows_emu.so')
+	res = subprocess.run(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared', '-w', '-I', os.path.join(ROOT, 'tests', 'emu'),
+		'-o', out, os.path.join(ROOT, 'tests', 'emu', 'rows_emu.cpp')], capture_output=True, text=True)
+	assert res.returncode == 0, res.stderr[-3000:]
+	lib = ctypes.CDLL(out)
+	lib.nwb_emu_match2.restype = ctypes.c_longlong
+	return lib
+
+
+def host_match(emu, tables, radius, completeness):
+	import nway_b200
+	tab = nway_b200._scalar_tables(tables, completeness, nway_b200.NullOutputLogger())   # the host scalars the library gets too
+	a = [np.ascontiguousarray(tables[0][k], dtype=np.float64) for k in ('ra', 'dec', 'error')]
+	b = [np.ascontiguousarray(tables[1][k], dtype=np.float64) for k in ('ra', 'dec', 'error')]
+	cap = 64
+	while True:
+		cols = [np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64), np.zeros(cap), np.zeros(cap), np.zeros(cap, dtype=np.int64),
+			np.zeros(cap), np.zeros(cap), np.zeros(cap), np.zeros(cap), np.zeros(cap, dtype=np.int64), np.zeros(cap), np.zeros(cap)]
+		norm, prior, l10p = [np.ascontiguousarray(tab[k], dtype=np.float64) for k in ('norm', 'prior', 'log10prior')]
+		R = emu.nwb_emu_match2(len(a[0]), P(a[0].ctypes.data), P(a[1].ctypes.data), P(a[2].ctypes.data),
+			len(b[0]), P(b[0].ctypes.data), P(b[1].ctypes.data), P(b[2].ctypes.data), ctypes.c_double(radius),
+			P(norm.ctypes.data), ctypes.c_double(tab['log10e']), P(prior.ctypes.data), P(l10p.ctypes.data), ctypes.c_double(0.5),
+			ctypes.c_longlong(cap), *[P(c.ctypes.data) for c in cols])
+		if R >= 0:
+			break
+		cap = -R - 1 + 16
+	na, nb = tables[0]['name'], tables[1]['name']
+	names = [na, nb, 'Separation_%s_%s' % (na, nb), 'Separation_max', 'ncat', 'dist_bayesfactor_uncorrected', 'dist_bayesfactor',
+		'dist_post', 'p_single', 'match_flag', 'prob_has_match', 'prob_this_match']
+	return {n: c[:R] for n, c in zip(names, cols)}
+
+
+@pytest.mark.parametrize('name', ['syn2', 'syn2_sparse', 'cosmos2', 'allsky2'])
+def test_host_build_of_the_device_source_matches_the_oracle(emu, name):
+	spec = cases.GOLDEN_CASES[name]
+	got = host_match(emu, cases.build_case(name), spec['radius'], spec['completeness'])
+	ref = O.nway_match(cases.build_case(name), spec['radius'], spec['completeness'])
+	cols = [c for c in ref if not c.startswith('_')]
+	assert sorted(got.keys()) == sorted(cols)
+	parity.assert_tables_match(ref, got, columns=cols, context='host emulation / ' + name)
+	parity.check_against_digest(name, got, [t['name'] for t in cases.build_case(name)])   # and the reference's own output
+
+
+def test_bench_workload_sample(emu):
+	"""the C3 generator of bench.py at 1/50 of the area: the configuration the throughput is quoted on"""
+	tables = cases.config_c3(scale=0.02, seed=20260301)
+	got = host_match(emu, tables, 5.0, 0.9)
+	ref = O.nway_match(cases.config_c3(scale=0.02, seed=20260301), 5.0, 0.9)
+	parity.assert_tables_match(ref, got, columns=[c for c in ref if not c.startswith('_')], context='host emulation / C3 sample')
+	assert len(got['A']) > 100000
