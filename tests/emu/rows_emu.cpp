@@ -19,6 +19,8 @@ extern "C" {
 long long nwb_emu_match2(int np, const double *pra, const double *pdec, const double *perr,
 	int ns, const double *sra, const double *sdec, const double *serr, double radius_arcsec,
 	const double *norm /* [3] */, double log10e, const double *prior /* [2] */, const double *log10prior /* [2] */, double ratio_secondary,
+	int nmag, const double *const *mag /* [nmag] columns of catalogue 1 */, const int *nbins, const double *const *edges,
+	const double *const *weight, const double *const *biasval, double *const *bias_out /* [nmag] */,
 	long long max_rows, long long *idx0, long long *idx1, double *sep, double *sepmax, long long *ncat, double *lbf_u, double *lbf,
 	double *dist_post, double *p_single, long long *flag, double *p_any, double *p_i)
 {
@@ -86,7 +88,13 @@ long long nwb_emu_match2(int np, const double *pra, const double *pdec, const do
 	T.log10prior[0] = log10prior[0]; T.log10prior[1] = log10prior[1];
 	RowParams RP;
 	memset(&RP, 0, sizeof(RP));
-	RP.ncat = 2; RP.nmag = 0; RP.np = np; RP.first = 0;
+	for (int j = 0; j < nmag; j++) {   // magnitude priors of the secondary catalogue (nwb_set_maghist)
+		MagTable &MT = T.mag[j];
+		MT.cat = 1; MT.nbins = nbins[j]; MT.mag = mag[j];
+		for (int k = 0; k <= nbins[j]; k++) MT.edges[k] = edges[j][k];
+		for (int k = 0; k < nbins[j]; k++) { MT.weight[k] = weight[j][k]; MT.bias[k] = biasval[j][k]; }
+	}
+	RP.ncat = 2; RP.nmag = nmag; RP.np = np; RP.first = 0;
 	RP.radius = radius_arcsec; RP.ratio_secondary = ratio_secondary;
 	RP.err[0] = perr; RP.err[1] = serr;
 	RP.n[0] = np; RP.n[1] = ns;
@@ -95,6 +103,8 @@ long long nwb_emu_match2(int np, const double *pra, const double *pdec, const do
 	RP.C.idx[0] = idx0; RP.C.idx[1] = idx1; RP.C.sep[0] = sep; RP.C.sepmax = sepmax; RP.C.ncat = ncat;
 	RP.C.lbf_u = lbf_u; RP.C.lbf = lbf; RP.C.dist_post = dist_post; RP.C.p_single = p_single; RP.C.flag = flag;
 	RP.C.p_any = p_any; RP.C.p_i = p_i;
+	for (int j = 0; j < nmag; j++) RP.C.bias[j] = bias_out[j];
+	const bool share = nmag == 0;   // nwb_api.cu: k_rows2<true, true> without magnitude priors, <true, false> with
 	R2Memo memo;
 	double m_sig0 = -1.0, w0 = 0.0, lw0 = 0.0;
 	std::vector<double> v, tt;
@@ -110,7 +120,8 @@ long long nwb_emu_match2(int np, const double *pra, const double *pdec, const do
 		double m_rest = -INFINITY;
 		for (int k = 0; k < rows; k++) {
 			double vk = 0.0;
-			rows2_write<true, true>(RP, &T, rbase + k, (long long) p, k == 0 ? -1 : (long long) M[k - 1].s, k == 0 ? 0.0 : M[k - 1].sep, w0, lw0, memo, vk);
+			if (share) rows2_write<true, true>(RP, &T, rbase + k, (long long) p, k == 0 ? -1 : (long long) M[k - 1].s, k == 0 ? 0.0 : M[k - 1].sep, w0, lw0, memo, vk);
+			else rows2_write<true, false>(RP, &T, rbase + k, (long long) p, k == 0 ? -1 : (long long) M[k - 1].s, k == 0 ? 0.0 : M[k - 1].sep, w0, lw0, memo, vk);
 			v[k] = vk;
 			if (k > 0) m_rest = fmax(m_rest, vk);
 		}
@@ -133,7 +144,7 @@ long long nwb_emu_match2(int np, const double *pra, const double *pdec, const do
 		group_p_any(rows, v0, m_rest, lane_sum[0], pa, rinv);
 		const double best = rinv;
 		const bool direct = !(fabs(m_rest) <= 250.0);
-		const double oscale = (rows > 1 && !direct) ? (1 - T.prior[1]) * nwb_exp10(-m_rest) : 0.0;
+		const double oscale = (share && rows > 1 && !direct) ? (1 - T.prior[1]) * nwb_exp10(-m_rest) : 0.0;
 		const double omp = 1 - T.prior[1], l10p1 = T.log10prior[1];
 		for (int k = 0; k < rows; k++) {
 			const long long row = rbase + k;
@@ -142,9 +153,11 @@ long long nwb_emu_match2(int np, const double *pra, const double *pdec, const do
 			p_i[row] = pi;
 			p_any[row] = pa;
 			flag[row] = (pi == best) ? 1 : (pi > ratio_secondary * best ? 2 : 0);
-			const double post = k == 0 ? 1.0 : shared_post(direct, tk, oscale, omp, lbf[row], l10p1);
-			dist_post[row] = post;
-			p_single[row] = post;
+			if (share) {
+				const double post = k == 0 ? 1.0 : shared_post(direct, tk, oscale, omp, lbf[row], l10p1);
+				dist_post[row] = post;
+				p_single[row] = post;
+			}
 		}
 		rbase += rows;
 	}

@@ -34,25 +34,42 @@ def host_match(emu, tables, radius, completeness):
 	tab = nway_b200._scalar_tables(tables, completeness, nway_b200.NullOutputLogger())   # the host scalars the library gets too
 	a = [np.ascontiguousarray(tables[0][k], dtype=np.float64) for k in ('ra', 'dec', 'error')]
 	b = [np.ascontiguousarray(tables[1][k], dtype=np.float64) for k in ('ra', 'dec', 'error')]
+	from nway_b200 import magnitudeweights
+	mags = []
+	for magvals, maghist in zip(tables[1].get('mags', []), tables[1].get('maghists', [])):
+		m = np.array(magvals, dtype=np.float64)
+		m[m == -99] = np.nan                                       # nway_b200.nway_match does the same (__init__.py:318-319)
+		lo, hi, hs, ha = maghist
+		e, w, bv = magnitudeweights.step_tables(np.array(list(lo) + [hi[-1]]), hs, ha)
+		mags.append([np.ascontiguousarray(x, dtype=np.float64) for x in (m, e, w, bv)])
+	nmag = len(mags)
+	PP = P * max(nmag, 1)
+	nb = (ctypes.c_int * max(nmag, 1))(*[len(x[2]) for x in mags])
 	cap = 64
 	while True:
 		cols = [np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64), np.zeros(cap), np.zeros(cap), np.zeros(cap, dtype=np.int64),
 			np.zeros(cap), np.zeros(cap), np.zeros(cap), np.zeros(cap), np.zeros(cap, dtype=np.int64), np.zeros(cap), np.zeros(cap)]
+		bias_cols = [np.zeros(cap) for _ in range(nmag)]
 		norm, prior, l10p = [np.ascontiguousarray(tab[k], dtype=np.float64) for k in ('norm', 'prior', 'log10prior')]
 		R = emu.nwb_emu_match2(len(a[0]), P(a[0].ctypes.data), P(a[1].ctypes.data), P(a[2].ctypes.data),
 			len(b[0]), P(b[0].ctypes.data), P(b[1].ctypes.data), P(b[2].ctypes.data), ctypes.c_double(radius),
 			P(norm.ctypes.data), ctypes.c_double(tab['log10e']), P(prior.ctypes.data), P(l10p.ctypes.data), ctypes.c_double(0.5),
+			nmag, PP(*[x[0].ctypes.data for x in mags]), nb, PP(*[x[1].ctypes.data for x in mags]), PP(*[x[2].ctypes.data for x in mags]),
+			PP(*[x[3].ctypes.data for x in mags]), PP(*[c.ctypes.data for c in bias_cols]),
 			ctypes.c_longlong(cap), *[P(c.ctypes.data) for c in cols])
 		if R >= 0:
 			break
 		cap = -R - 1 + 16
-	na, nb = tables[0]['name'], tables[1]['name']
-	names = [na, nb, 'Separation_%s_%s' % (na, nb), 'Separation_max', 'ncat', 'dist_bayesfactor_uncorrected', 'dist_bayesfactor',
+	na, nb_name = tables[0]['name'], tables[1]['name']
+	names = [na, nb_name, 'Separation_%s_%s' % (na, nb_name), 'Separation_max', 'ncat', 'dist_bayesfactor_uncorrected', 'dist_bayesfactor',
 		'dist_post', 'p_single', 'match_flag', 'prob_has_match', 'prob_this_match']
-	return {n: c[:R] for n, c in zip(names, cols)}
+	out = {n: c[:R] for n, c in zip(names, cols)}
+	for magname, c in zip(tables[1].get('magnames', []), bias_cols):
+		out['bias_%s_%s' % (nb_name, magname)] = c[:R]
+	return out
 
 
-@pytest.mark.parametrize('name', ['syn2', 'syn2_sparse', 'cosmos2', 'allsky2'])
+@pytest.mark.parametrize('name', ['syn2', 'syn2_sparse', 'syn2_maghist', 'cosmos2', 'allsky2'])
 def test_host_build_of_the_device_source_matches_the_oracle(emu, name):
 	spec = cases.GOLDEN_CASES[name]
 	got = host_match(emu, cases.build_case(name), spec['radius'], spec['completeness'])
