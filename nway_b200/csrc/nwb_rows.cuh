@@ -1,7 +1,7 @@
 // What a row of the output table is made of, as plain per-row functions: the pair store k_pairs fills, the parameter
 // block of the row kernels, the magnitude-prior look-up of a row and the scoring of one row of a two-catalogue match
 // (rows2_write).  Kept apart from the kernels so that tests/emu/rows_emu.cpp can run exactly these functions on the
-// host and compare whole tables with the oracle.
+// host and compare whole tables with an independent CPU computation.
 #pragma once
 #include "nwb_device.cuh"
 
