@@ -84,10 +84,10 @@ def run(emu, radius, ra, dec, sra, sdec, max_cells):
 	return miss, stats, first
 
 
-@pytest.mark.parametrize('block', range(6))
+@pytest.mark.parametrize('block', range(5))
 def test_no_pair_within_the_radius_is_filtered_out(emu, block):
 	total = inline = overflow = 0
-	for seed in range(5000 + 20 * block, 5000 + 20 * (block + 1)):
+	for seed in range(5000 + 16 * block, 5000 + 16 * (block + 1)):
 		kind, radius, ra, dec, sra, sdec, max_cells = random_field(seed)
 		miss, stats, first = run(emu, radius, ra, dec, sra, sdec, max_cells)
 		assert miss == 0, 'seed %d (%s, r = %.4g arcsec, %d primaries, %d cells): %d of %d pairs lost, first: primary %d (%.8f, %.8f) secondary %d (%.8f, %.8f)' % (
