@@ -87,3 +87,88 @@ def test_bench_workload_sample(emu):
 	ref = O.nway_match(cases.config_c3(scale=0.02, seed=20260301), 5.0, 0.9)
 	parity.assert_tables_match(ref, got, columns=[c for c in ref if not c.startswith('_')], context='host emulation / C3 sample')
 	assert len(got['A']) > 100000
+
+
+# ---- three and four catalogues (tests/emu/rowsn_emu.cpp) ---------------------------------------------------
+
+@pytest.fixture(scope='module')
+def emun(tmp_path_factory):
+	out = str(tmp_path_factory.mktemp('emu') / 'rowsn_emu.so')
+	res = subprocess.run(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared', '-w', '-I', os.path.join(ROOT, 'tests', 'emu'),
+		'-o', out, os.path.join(ROOT, 'tests', 'emu', 'rowsn_emu.cpp')], capture_output=True, text=True)
+	assert res.returncode == 0, res.stderr[-3000:]
+	lib = ctypes.CDLL(out)
+	lib.nwb_emu_matchn.restype = ctypes.c_longlong
+	return lib
+
+
+def host_match_n(emun, tables, radius, completeness, ratio_secondary=0.5):
+	import nway_b200
+	from nway_b200 import magnitudeweights
+	nc = len(tables)
+	npair = nc * (nc - 1) // 2
+	tab = nway_b200._scalar_tables(tables, completeness, nway_b200.NullOutputLogger())
+	keep = []   # arrays that must stay alive during the call
+
+	def arr(x, dtype=np.float64):
+		a = np.ascontiguousarray(x, dtype=dtype)
+		keep.append(a)
+		return a
+
+	def pp(arrays):
+		return (P * max(len(arrays), 1))(*[a.ctypes.data for a in arrays])
+
+	ra, dec, err = [[arr(t[k]) for t in tables] for k in ('ra', 'dec', 'error')]
+	n = (ctypes.c_int * nc)(*[len(t['ra']) for t in tables])
+	mag_cat, mags, edges, weights, biases, names_bias = [], [], [], [], [], []
+	for c, t in enumerate(tables):
+		for magvals, maghist, magname in zip(t.get('mags', []), t.get('maghists', []), t.get('magnames', [])):
+			m = np.array(magvals, dtype=np.float64)
+			m[m == -99] = np.nan
+			lo, hi, hs, ha = maghist
+			e, w, bv = magnitudeweights.step_tables(np.array(list(lo) + [hi[-1]]), hs, ha)
+			mag_cat.append(c); mags.append(arr(m)); edges.append(arr(e)); weights.append(arr(w)); biases.append(arr(bv))
+			names_bias.append('bias_%s_%s' % (t['name'], magname))
+	nmag = len(mags)
+	cap = 1024
+	while True:
+		idx = [np.zeros(cap, dtype=np.int64) for _ in range(nc)]
+		seps = [np.zeros(cap) for _ in range(npair)]
+		bias_cols = [np.zeros(cap) for _ in range(nmag)]
+		sepmax, lbf_u, lbf, post, ps, pany, pi = [np.zeros(cap) for _ in range(7)]
+		ncat, flag = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64)
+		norm, prior, l10p = arr(tab['norm']), arr(tab['prior']), arr(tab['log10prior'])
+		R = emun.nwb_emu_matchn(nc, n, pp(ra), pp(dec), pp(err), ctypes.c_double(radius), P(norm.ctypes.data), ctypes.c_double(tab['log10e']),
+			P(prior.ctypes.data), P(l10p.ctypes.data), ctypes.c_double(ratio_secondary), nmag, (ctypes.c_int * max(nmag, 1))(*mag_cat), pp(mags),
+			(ctypes.c_int * max(nmag, 1))(*[len(w) for w in weights]), pp(edges), pp(weights), pp(biases), pp(bias_cols), ctypes.c_longlong(cap),
+			pp(idx), pp(seps), P(sepmax.ctypes.data), P(ncat.ctypes.data), P(lbf_u.ctypes.data), P(lbf.ctypes.data), P(post.ctypes.data),
+			P(ps.ctypes.data), P(flag.ctypes.data), P(pany.ctypes.data), P(pi.ctypes.data))
+		if R >= 0:
+			break
+		cap = -R - 1 + 16
+	names = [t['name'] for t in tables]
+	out = {}
+	for c in range(nc):
+		out[names[c]] = idx[c][:R]
+	k = 0
+	for a in range(nc):
+		for b in range(a + 1, nc):
+			out['Separation_%s_%s' % (names[a], names[b])] = seps[k][:R]
+			k += 1
+	out.update(Separation_max=sepmax[:R], ncat=ncat[:R], dist_bayesfactor_uncorrected=lbf_u[:R], dist_bayesfactor=lbf[:R], dist_post=post[:R])
+	for name, col in zip(names_bias, bias_cols):
+		out[name] = col[:R]
+	out.update(p_single=ps[:R], match_flag=flag[:R], prob_has_match=pany[:R], prob_this_match=pi[:R])
+	return out
+
+
+@pytest.mark.parametrize('name', ['syn2', 'syn3', 'syn3_pcvec', 'syn4', 'cosmos3', 'allsky3'])
+def test_host_build_of_the_device_source_matches_the_oracle_n_catalogues(emun, name):
+	spec = cases.GOLDEN_CASES[name]
+	kw = spec.get('kwargs', {})
+	got = host_match_n(emun, cases.build_case(name), spec['radius'], spec['completeness'], ratio_secondary=kw.get('prob_ratio_secondary', 0.5))
+	ref = O.nway_match(cases.build_case(name), spec['radius'], spec['completeness'], **kw)
+	cols = [c for c in ref if not c.startswith('_')]
+	assert sorted(got.keys()) == sorted(cols)
+	parity.assert_tables_match(ref, got, columns=cols, context='host emulation / ' + name)
+	parity.check_against_digest(name, got, [t['name'] for t in cases.build_case(name)])
