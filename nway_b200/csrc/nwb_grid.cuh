@@ -215,6 +215,22 @@ __device__ __forceinline__ void prim_register(const Grid &G, const int i, const 
 		}
 	}
 }
+// The reference's flat-sky hash (fastskymatch.py:125-132) puts a source into the buckets (i, j), (i+1, j), (i, j+1),
+// (i+1, j+1) with i = int(ra / err), j = int(dec / err) (python's int(): truncation toward zero; err = the search radius
+// in degrees), and forms tuples per bucket: a tuple exists iff the cells of its present members span at most one step
+// in i and in j.  Off the equator that loses pairs a complete search finds.  These two functions are the
+// predicate of the planned NWB_COMPAT_FLAT_HASH switch; no kernel calls them yet.
+__device__ __forceinline__ long long flat_hash_cell(double coord_deg, double err_deg)
+{
+	return (long long) (coord_deg / err_deg);   // IEEE division, conversion truncates toward zero
+}
+
+__device__ __forceinline__ bool flat_hash_same_bucket(long long ia, long long ja, long long ib, long long jb)
+{
+	const long long di = ia - ib, dj = ja - jb;
+	return di >= -1 && di <= 1 && dj >= -1 && dj <= 1;
+}
+
 // Where a secondary falls in the grid (first stage of k_pairs; the band record B is fetched in between): declination in
 // band heights from the lower edge (valid if 0 <= t < nbands), ra in degrees from the grid origin in [0, 360) (valid if
 // the grid spans the circle or x <= ra_span), the cell along ra (clamped like racell_of) and the position in cell widths.

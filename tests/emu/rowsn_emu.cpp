@@ -36,7 +36,7 @@ double lanes_sum(const std::vector<double> &x, long long first)   // sum over k 
 
 template <int NC>
 long long run(const int *n, const double *const *ra, const double *const *dec, const double *const *err, double radius,
-	const ConstTables &T, double ratio_secondary, int nmag, long long max_rows, long long *const *idx, double *const *sep_out, double *sepmax,
+	const ConstTables &T, double ratio_secondary, int nmag, int flat_hash, long long max_rows, long long *const *idx, double *const *sep_out, double *sepmax,
 	long long *ncat, double *lbf_u, double *lbf_c, double *dist_post, double *const *bias_out, double *p_single, long long *flag, double *p_any, double *p_i)
 {
 	const int np = n[0];
@@ -121,6 +121,15 @@ long long run(const int *n, const double *const *ra, const double *const *dec, c
 					}
 					sep[pair_index(a, b, NC)] = s;
 				}
+			if (ok && flat_hash) {
+				// NWB_COMPAT_FLAT_HASH as planned: every pair of present members in the same or adjacent hash cells
+				long long ci[NC], cj[NC];
+				for (int c = 0; c < NC; c++)
+					if (present >> c & 1u) { ci[c] = flat_hash_cell(ra[c][sidx[c]], radius / 3600.0); cj[c] = flat_hash_cell(dec[c][sidx[c]], radius / 3600.0); }
+				for (int a = 0; a < NC; a++)
+					for (int b = a + 1; b < NC; b++)
+						if ((present >> a & 1u) && (present >> b & 1u)) ok = ok && flat_hash_same_bucket(ci[a], cj[a], ci[b], cj[b]);
+			}
 			if (!ok) continue;
 			if (row >= max_rows) { row++; continue; }
 			double smax = 0.0;
@@ -173,7 +182,7 @@ extern "C" {
 long long nwb_emu_matchn(int ncat, const int *n, const double *const *ra, const double *const *dec, const double *const *err, double radius,
 	const double *norm, double log10e, const double *prior, const double *log10prior, double ratio_secondary,
 	int nmag, const int *mag_cat, const double *const *mag, const int *nbins, const double *const *edges, const double *const *weight,
-	const double *const *biasval, double *const *bias_out, long long max_rows, long long *const *idx, double *const *sep_out, double *sepmax,
+	const double *const *biasval, double *const *bias_out, int flat_hash, long long max_rows, long long *const *idx, double *const *sep_out, double *sepmax,
 	long long *ncat_out, double *lbf_u, double *lbf_c, double *dist_post, double *p_single, long long *flag, double *p_any, double *p_i)
 {
 	static ConstTables T;
@@ -187,7 +196,7 @@ long long nwb_emu_matchn(int ncat, const int *n, const double *const *ra, const 
 		for (int k = 0; k <= nbins[j]; k++) MT.edges[k] = edges[j][k];
 		for (int k = 0; k < nbins[j]; k++) { MT.weight[k] = weight[j][k]; MT.bias[k] = biasval[j][k]; }
 	}
-#define NWB_RUN(NC) run<NC>(n, ra, dec, err, radius, T, ratio_secondary, nmag, max_rows, idx, sep_out, sepmax, ncat_out, lbf_u, lbf_c, dist_post, bias_out, p_single, flag, p_any, p_i)
+#define NWB_RUN(NC) run<NC>(n, ra, dec, err, radius, T, ratio_secondary, nmag, flat_hash, max_rows, idx, sep_out, sepmax, ncat_out, lbf_u, lbf_c, dist_post, bias_out, p_single, flag, p_any, p_i)
 	switch (ncat) {
 		case 2: return NWB_RUN(2);
 		case 3: return NWB_RUN(3);

@@ -102,7 +102,7 @@ def emun(tmp_path_factory):
 	return lib
 
 
-def host_match_n(emun, tables, radius, completeness, ratio_secondary=0.5):
+def host_match_n(emun, tables, radius, completeness, ratio_secondary=0.5, flat_hash=False):
 	import nway_b200
 	from nway_b200 import magnitudeweights
 	nc = len(tables)
@@ -140,7 +140,7 @@ def host_match_n(emun, tables, radius, completeness, ratio_secondary=0.5):
 		norm, prior, l10p = arr(tab['norm']), arr(tab['prior']), arr(tab['log10prior'])
 		R = emun.nwb_emu_matchn(nc, n, pp(ra), pp(dec), pp(err), ctypes.c_double(radius), P(norm.ctypes.data), ctypes.c_double(tab['log10e']),
 			P(prior.ctypes.data), P(l10p.ctypes.data), ctypes.c_double(ratio_secondary), nmag, (ctypes.c_int * max(nmag, 1))(*mag_cat), pp(mags),
-			(ctypes.c_int * max(nmag, 1))(*[len(w) for w in weights]), pp(edges), pp(weights), pp(biases), pp(bias_cols), ctypes.c_longlong(cap),
+			(ctypes.c_int * max(nmag, 1))(*[len(w) for w in weights]), pp(edges), pp(weights), pp(biases), pp(bias_cols), int(flat_hash), ctypes.c_longlong(cap),
 			pp(idx), pp(seps), P(sepmax.ctypes.data), P(ncat.ctypes.data), P(lbf_u.ctypes.data), P(lbf.ctypes.data), P(post.ctypes.data),
 			P(ps.ctypes.data), P(flag.ctypes.data), P(pany.ctypes.data), P(pi.ctypes.data))
 		if R >= 0:
@@ -172,3 +172,19 @@ def test_host_build_of_the_device_source_matches_the_oracle_n_catalogues(emun, n
 	assert sorted(got.keys()) == sorted(cols)
 	parity.assert_tables_match(ref, got, columns=cols, context='host emulation / ' + name)
 	parity.check_against_digest(name, got, [t['name'] for t in cases.build_case(name)])
+
+
+@pytest.mark.parametrize('seed', [1003, 1019, 1071, 1038])
+def test_flat_hash_switch_reproduces_the_reference_rows(emun, seed):
+	"""the planned NWB_COMPAT_FLAT_HASH predicate (flat_hash_cell / flat_hash_same_bucket, nwb_grid.cuh) applied inside the
+	emulated row enumeration: the table equals the oracle's with the reference's own flat-sky hash -- fewer rows than
+	the complete search at mid-latitudes (1003, 1019, 1071), the same near the equator"""
+	from tests.test_gpu_fuzz import random_case
+	tables, radius, pc, kw, kind = random_case(seed)
+	assert not kw and O.flat_sky_applicable([(t['ra'], t['dec']) for t in tables], radius / 3600)
+	got = host_match_n(emun, [dict(t) for t in tables], radius, pc, flat_hash=True)
+	ref = O.nway_match([dict(t) for t in tables], radius, pc, enumerator='refhash')
+	cols = [c for c in ref if not c.startswith('_')]
+	parity.assert_tables_match(ref, got, columns=cols, context='flat-hash switch / seed %d' % seed, rtol=3e-9)
+	full = host_match_n(emun, [dict(t) for t in tables], radius, pc)
+	assert len(full[tables[0]['name']]) >= len(got[tables[0]['name']])
