@@ -86,13 +86,24 @@ int nwb_set_params(nwb_ctx *ctx, double match_radius_arcsec, const double *compl
  * behaviour is radius 0 here.  npairs = 0 clears the list.  Call after the catalogues are set. */
 int nwb_set_prefilter(nwb_ctx *ctx, int npairs, const int *cat_a, const int *cat_b, const double *radius_arcsec);
 
-/* Compatibility switches of the reference's command-line program (nway.py); default 0 = the fp64 API behaviour.
+/* Compatibility switches; default 0 = fp64 separations, complete enumeration on the whole sphere.
  * NWB_COMPAT_SEP_F32: nway.py stores every separation (and, for elliptical errors, every tangent-plane offset) in a
  * float32 FITS column and scores what it reads back (fastskymatch.py:328-331 -> nway.py:269,302-305):
  * round them to float32 after the (fp64) radius filter and before the Bayes factor.  The Separation columns then
- * hold float32-representable values. */
-enum { NWB_COMPAT_SEP_F32 = 1 };
+ * hold float32-representable values.
+ * NWB_COMPAT_FLAT_HASH: reproduce the ROW SET of the reference where its enumeration is incomplete.  When every
+ * catalogue has |dec| < 45, ra in (10 r, 360 - 10 r) and r < 1 deg, crossproduct() hashes on square cells of r degrees
+ * in (ra, dec) WITHOUT cos(dec) (fastskymatch.py:94-101,123-133): away from the equator pairs whose ra difference
+ * spans more than two cells are never formed although they are within the radius.  With this flag a
+ * pair / tuple is kept only if the reference's hash would have put all of its members into one bucket (cells
+ * int(ra / err), int(dec / err), err = match_radius / 60. / 60, spanning <= 1 step each); when the reference would
+ * take its HEALPix branch instead (fastskymatch.py:134-160, complete) nothing changes.  The catalogue bounds this
+ * depends on are reduced on the device once per nwb_set_catalogue.  nwb_flat_hash_applied tells which it was. */
+enum { NWB_COMPAT_SEP_F32 = 1, NWB_COMPAT_FLAT_HASH = 2 };
 int nwb_set_compat(nwb_ctx *ctx, int flags);
+/* after nwb_match: *applied = 1 if the last match applied the flat-sky bucket predicate (NWB_COMPAT_FLAT_HASH set and
+ * the reference's flat-sky condition fastskymatch.py:94-98 true for these catalogues), else 0 */
+int nwb_flat_hash_applied(nwb_ctx *ctx, int *applied);
 
 /* Optional: the scalar tables the kernels consume, computed by the caller with the reference's own numpy
  * expressions (so they are bit-identical to what nwaylib computes on that host).  If not called, the library

@@ -155,7 +155,7 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	store_mag_hists=True,
 	logger=default_logger,
 	unrelated_mode='api', device=None, primary_range=None, as_frame=True, keep_on_device=False, allow_empty=False,
-	cli_compat=False, pairwise_errs=()):
+	cli_compat=False, pairwise_errs=(), flat_hash_compat=True):
 	"""Same contract as nwaylib.nway_match (nwaylib/__init__.py:31-83); see there for the arguments.
 
 	match_tables: list of dicts with name, ra, dec (deg), error (arcsec), area (deg^2), mags, magnames, maghists
@@ -176,6 +176,12 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	                  intended -- associations containing sources of both a and b are formed only if those two are
 	                  closer than the radius (fastskymatch.py:184-208; the reference's code as written drops all of
 	                  them, SURVEY.md Q8, which is radius 0 here)
+	  flat_hash_compat  True (default): return exactly the reference's rows.  Where nwaylib takes its flat-sky hash (every
+	                  catalogue at |dec| < 45 deg, away from ra = 0, radius < 1 deg: fastskymatch.py:94-98) it bins ra
+	                  without cos(dec) and, away from the equator, never forms some pairs that ARE within the radius
+	                  (SURVEY.md Q3); those associations are left out here too, so that prob_has_match / prob_this_match /
+	                  match_flag of a group are the reference's.  False: the complete enumeration on the whole sphere
+	                  (a superset; identical near the equator and wherever the reference uses its HEALPix hash).
 	  cli_compat      the arithmetic quirks of the command-line program nway.py on top of unrelated_mode='cli':
 	                  separations (elliptical: offsets) pass through float32 before they are scored
 	                  and automatic histograms take the weights of the selected rows (nway.py:471)
@@ -216,7 +222,7 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	tab = _scalar_tables(match_tables, prior_completeness, logger)
 	mode = _lib.UNRELATED_CLI if (unrelated_mode == 'cli' and consider_unrelated_associations) else _lib.UNRELATED_API
 	ctx.set_params(match_radius, tab['pc'], prob_ratio_secondary, mode)
-	ctx.set_compat(_lib.COMPAT_SEP_F32 if cli_compat else 0)
+	ctx.set_compat((_lib.COMPAT_SEP_F32 if cli_compat else 0) | (_lib.COMPAT_FLAT_HASH if flat_hash_compat else 0))
 	ctx.set_prefilter(list(pairwise_errs))
 	ctx.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
 

@@ -17,6 +17,7 @@ COL_SEPMAX, COL_NCAT, COL_LOGBF_UNCORR, COL_LOGBF, COL_DIST_POST, COL_P_SINGLE, 
 ERR_CIRCULAR, ERR_ELLIPSE = 1, 3
 UNRELATED_API, UNRELATED_CLI = 0, 1
 COMPAT_SEP_F32 = 1
+COMPAT_FLAT_HASH = 2
 T_GRID, T_PAIRS, T_LISTS, T_ROWS, T_FINAL, T_TOTAL, T_KPAIRS, T_KROWS = range(8)
 STAGE_NAMES = ['grid', 'pairs', 'lists', 'rows', 'final', 'total', 'k_pairs', 'k_rows']
 NWB_ERR_EMPTY = -3
@@ -32,6 +33,7 @@ EXPORTS = {
 		ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int]),
 	'nwb_set_params': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_double_p, ctypes.c_double, ctypes.c_int]),
 	'nwb_set_compat': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+	'nwb_flat_hash_applied': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
 	'nwb_maghist_select': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
 		c_int64_p, c_int64_p, c_double_p]),
 	'nwb_maghist_sample': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p]),
@@ -181,6 +183,12 @@ class Context(object):
 
 	def set_compat(self, flags):
 		self.check(self.lib.nwb_set_compat(self.h, int(flags)))
+
+	def flat_hash_applied(self):
+		"""did the last match apply the reference's flat-sky bucket predicate (COMPAT_FLAT_HASH)?"""
+		v = ctypes.c_int(0)
+		self.check(self.lib.nwb_flat_hash_applied(self.h, ctypes.byref(v)))
+		return bool(v.value)
 
 	def set_tables(self, norm, log10e, prior, log10prior, sub_log10prior):
 		a, b, c, d = f64(norm), f64(prior), f64(log10prior), f64(sub_log10prior)

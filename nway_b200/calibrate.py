@@ -33,7 +33,8 @@ def pairs_within(ra1, dec1, ra2, dec2, radius_arcsec, device=None):
 		dict(name='A', ra=numpy.asarray(ra1, dtype=float), dec=numpy.asarray(dec1, dtype=float), error=numpy.ones(n1), area=area, mags=[], magnames=[], maghists=[]),
 		dict(name='B', ra=ra2, dec=dec2, error=numpy.ones(n2), area=area, mags=[], magnames=[], maghists=[]),
 	]
-	cols = nway_match(tables, radius_arcsec, 1.0, logger=NullOutputLogger(), store_mag_hists=False, as_frame=False, device=device)
+	cols = nway_match(tables, radius_arcsec, 1.0, logger=NullOutputLogger(), store_mag_hists=False, as_frame=False, device=device,
+		flat_hash_compat=False)   # a neighbour search: every pair within the radius, not the reference hash's subset
 	has = cols['B'] >= 0
 	return cols['A'][has], cols['B'][has], cols['Separation_A_B'][has]
 

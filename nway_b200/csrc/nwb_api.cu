@@ -39,6 +39,9 @@ struct CatSlot {
 	DevBuf own;   // one allocation holding ra|dec|err|mags when copied from the host
 	bool err_const = false;   // every source has the same (positive, circular) error
 	double err_value = 0;
+	bool bounds_known = false;   // NWB_COMPAT_FLAT_HASH: smallest / largest ra, largest |dec|, any NaN (k_radec_bounds)
+	double ra_min = 0, ra_max = 0, absdec_max = 0;
+	bool has_nan = false;
 };
 
 struct HostMagHist {
@@ -61,6 +64,7 @@ struct nwb_ctx {
 	double pc[MAXC];
 	int unrelated_mode = NWB_UNRELATED_API;
 	int compat = 0;
+	double flat_err = 0;             // > 0: this match applies the reference's flat-sky bucket predicate (NWB_COMPAT_FLAT_HASH)
 	bool any_big = true;             // some primary has more candidate tuples than k_rows_small handles
 	double prefilter[MAXP];          // per catalogue pair, arcsec; +inf = none
 	bool prefilter_on = false;
@@ -439,6 +443,7 @@ int nwb_set_catalogue(nwb_ctx *ctx, int c, int ncat, int64_t n, const double *ra
 		S.ra = d; S.dec = d + n; S.err = d + 2 * n; S.mags = m ? d + (2 + ecols) * n : nullptr;
 	}
 	S.set = true;
+	S.bounds_known = false;
 	ctx->tables_dirty = true;
 	ctx->matched = ctx->finalized = false;
 	ctx->pending = false;   // a match still in flight belongs to the old catalogue: abandoned
@@ -504,8 +509,15 @@ int nwb_set_prefilter(nwb_ctx *ctx, int npairs, const int *cat_a, const int *cat
 int nwb_set_compat(nwb_ctx *ctx, int flags)
 {
 	if (!ctx) return NWB_ERR_ARG;
-	if (flags & ~NWB_COMPAT_SEP_F32) return fail(ctx, NWB_ERR_ARG, "unknown compatibility flag");
+	if (flags & ~(NWB_COMPAT_SEP_F32 | NWB_COMPAT_FLAT_HASH)) return fail(ctx, NWB_ERR_ARG, "unknown compatibility flag");
 	ctx->compat = flags;
+	return NWB_OK;
+}
+
+int nwb_flat_hash_applied(nwb_ctx *ctx, int *applied)
+{
+	if (!ctx || !applied) return NWB_ERR_ARG;
+	*applied = ctx->flat_err > 0.0 ? 1 : 0;
 	return NWB_OK;
 }
 
@@ -585,12 +597,56 @@ static int fill_row_params(nwb_ctx *ctx, const PairStore *stores, int64_t first,
 	rp.ell = ell ? 1 : 0;
 	rp.sep_f32 = (ctx->compat & NWB_COMPAT_SEP_F32) ? 1 : 0;
 	rp.small_t = SMALL_T;
+	rp.flat_err = ctx->flat_err;
 	for (int k = 0; k < MAXP; k++) rp.pair_radius[k] = ctx->prefilter_on ? std::min(ctx->radius, ctx->prefilter[k]) : ctx->radius;
 	rp.T = (const ConstTables *) ctx->d_tables.p;
 	rp.S1 = stores[1];
 	rp.err1_const = ctx->cat[1].err_const ? 1 : 0;
 	rp.err1_value = ctx->cat[1].err_value;
 	rp.guard = nullptr;
+	return NWB_OK;
+}
+
+// NWB_COMPAT_FLAT_HASH: would the reference's crossproduct() take its flat-sky branch for these catalogues and this
+// radius (fastskymatch.py:94-98: err < 1 deg, every ra in (10 err, 360 - 10 err), every |dec| < 45)?  The bounds of a
+// catalogue are reduced on the device once per nwb_set_catalogue.  *flat_err = the bucket size in degrees, or 0.
+static int flat_hash_decision(nwb_ctx *ctx, double *flat_err)
+{
+	*flat_err = 0.0;
+	if (!(ctx->compat & NWB_COMPAT_FLAT_HASH)) return NWB_OK;
+	const double err = ctx->radius / 60. / 60;   // the reference's expression (__init__.py:128, nway.py:214)
+	if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocMapped));
+	ENSURE(ctx->d_status, 64 * sizeof(long long));
+	bool flat = err < 1;
+	for (int c = 0; c < ctx->ncat && flat; c++) {
+		CatSlot &S = ctx->cat[c];
+		if (!S.bounds_known) {
+			if (S.n > 0) {
+				unsigned long long init[4] = {~0ull, 0ull, 0ull, 0ull};
+				unsigned long long *d_b = (unsigned long long *) ctx->d_status.p + 48;
+				CU(cudaMemcpyAsync(d_b, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+				LAUNCH(ctx, k_radec_bounds, (int) std::min<int64_t>((S.n + 255) / 256, 148 * 8), 256, (long long) S.n, S.ra, S.dec, d_b);
+				LAUNCH(ctx, k_words_to_host, 1, 32, (const long long *) d_b, ctx->h_status + 56, 4);
+				CU(cudaStreamSynchronize(ctx->stream));
+				double v[3];
+				for (int k = 0; k < 3; k++) {
+					unsigned long long u = (unsigned long long) ctx->h_status[56 + k];
+					u ^= (u >> 63) ? 0x8000000000000000ull : ~0ull;
+					memcpy(&v[k], &u, 8);
+				}
+				S.ra_min = v[0]; S.ra_max = v[1]; S.absdec_max = v[2];
+				S.has_nan = ctx->h_status[59] != 0;
+			} else {
+				S.ra_min = INFINITY; S.ra_max = -INFINITY; S.absdec_max = 0; S.has_nan = false;   // all() of nothing is true
+			}
+			S.bounds_known = true;
+		}
+		flat = flat && !S.has_nan && S.ra_min > 10 * err && S.ra_max < 360 - 10 * err && S.absdec_max < 45;
+	}
+	if (!flat) return NWB_OK;
+	if (!(360.0 / err < 2147483000.0))
+		return fail(ctx, NWB_ERR_ARG, "NWB_COMPAT_FLAT_HASH: the radius is too small for 32-bit flat-sky cells");
+	*flat_err = err;
 	return NWB_OK;
 }
 
@@ -621,6 +677,9 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	{ int r = upload_tables(ctx); if (r) return r; }
 	const bool cli = ctx->unrelated_mode == NWB_UNRELATED_CLI && nc >= 3;
 	const bool fuse = fuse_final && !cli;
+	double flat_err = 0.0;
+	{ int r = flat_hash_decision(ctx, &flat_err); if (r) return r; }
+	ctx->flat_err = flat_err;
 	if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocMapped));
 	long long *hs = ctx->h_status;
 
@@ -643,7 +702,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	if (!use_cached) {
 		CU(cudaMemsetAsync(d_red, 0, 6 * sizeof(unsigned long long), st));
 		LAUNCH(ctx, (k_prim_prep<false>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
-			Grid(), rb_ins, dra_eps, (int *) nullptr, entry_tau_max);
+			Grid(), rb_ins, dra_eps, (int *) nullptr, entry_tau_max, flat_err);
 		// the grid geometry is chosen on the host from the bounding box: one sync.  It is kept for the next match
 		// on this context, which only has to verify (on the device) that the box is still the same.
 		unsigned long long *raw = (unsigned long long *) (hs + 32);
@@ -736,7 +795,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			// known geometry: the primaries are counted into their cells by the preparation kernel itself
 			LAUNCH(ctx, k_zero, (int) std::min<size_t>((zero_ints / 4 + 255) / 256, 148 * 8), 256, (int4 *) d_cellcnt, (long long) (zero_ints / 4), d_red, 6);
 			LAUNCH(ctx, (k_prim_prep<true>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
-				G, rb_ins, dra_eps, d_cellcnt, entry_tau_max);
+				G, rb_ins, dra_eps, d_cellcnt, entry_tau_max, flat_err);
 		} else {
 			CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
 			LAUNCH(ctx, (k_prim_cells<false>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (CellRec *) nullptr,
@@ -772,6 +831,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			ka.P = P; ka.radius = ctx->prefilter_on ? std::min(ctx->radius, ctx->prefilter[pair_index(0, c, nc)]) : ctx->radius; ka.base = d_base + base_off[c]; ka.C = Cs[c]; ka.cnt = d_cnt[c];
 			ka.spill = d_spill + (size_t) ctx->spill_cap * (c - 1); ka.spill_cap = (unsigned long long) ctx->spill_cap;
 			ka.spill_count = d_spillcount + c;
+			ka.flat_err = flat_err;
 			if (G.nbands <= K1_SBANDS && !G.bits)
 				LAUNCH(ctx, (k_pairs<true>), grid, K1_WARPS * 32, (int) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_etotal,
 					(const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
@@ -875,20 +935,21 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			ctx->stats[1] += (int64_t) npair;
 			ENSURE(ctx->d_Ls[c], std::max<size_t>(1, npair) * sizeof(int));
 			ENSURE(ctx->d_Lsep[c], std::max<size_t>(1, npair) * sizeof(double));
-			ENSURE(ctx->d_Ltrig[c], std::max<size_t>(1, npair) * 3 * sizeof(double));
+			ENSURE(ctx->d_Ltrig[c], std::max<size_t>(1, npair) * 4 * sizeof(double));   // lon | sin lat | cos lat | flat-sky cell
 			double *tr = (double *) ctx->d_Ltrig[c].p;
 			const long long *off = (const long long *) ctx->d_segoff[c].p;
 			if (npair) {
 				LAUNCH(ctx, k_sort_lists_small, pblocks, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
-					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair);
+					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair, (long long *) (tr + 3 * npair), flat_err);
 				if (h_maxcnt[c] > SMALL_N)
 					LAUNCH(ctx, k_sort_lists, wgrid, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
-						ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair, SMALL_N);
+						ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair, SMALL_N, (long long *) (tr + 3 * npair), flat_err);
 			}
 			L.off[c] = off;
 			L.s[c] = (const int *) ctx->d_Ls[c].p;
 			L.sep[c] = (const double *) ctx->d_Lsep[c].p;
 			L.lon[c] = tr; L.slat[c] = tr + npair; L.clat[c] = tr + 2 * npair;
+			L.ij[c] = (const long long *) (tr + 3 * npair);
 		}
 		rp.L = L;
 		CU(cudaEventRecord(ctx->ev[3], st));

@@ -8,6 +8,7 @@
 #endif
 #include <math.h>
 #include <stdint.h>
+#include "nwb_sincos_tab.h"
 
 #define NWB_FULL 0xffffffffu
 #define NWB_PI 3.141592653589793
@@ -58,29 +59,166 @@ __device__ __forceinline__ double quotient_by_reciprocal(double a, double b, dou
 #define NWB_INV180 (1.0 / 180.0)
 #define NWB_INVPI (1.0 / NWB_PI)
 
+// ---------------------------------------------------------------------------------------------------------
+// sin / cos with the bits of the reference's.  The reference evaluates fastskymatch.py:36-41 with numpy, whose
+// float64 sin / cos are glibc's (numpy 2.x ships no SIMD double-precision sin / cos).  The Vincenty numerator
+// (fastskymatch.py:44) cancels: a 1-ulp difference in sin(lat) or cos(dlon) is an ABSOLUTE ~1e-16 rad in the
+// separation, which the Bayes factor multiplies by separation / sigma^2 -- up to a few 1e-10 in the posteriors.  So
+// the path needs glibc's bits, not merely an accurate sine.  What follows restates the algorithm of glibc 2.39's
+// double-precision sin / cos (sysdeps/ieee754/dbl-64/s_sin.c as built for x86-64 with FMA -- the variant every
+// AVX2-class host selects): |x| < 0.126: odd polynomial; below 0.855469: table of sin / cos(k/128) in double-double
+// plus degree-5/6 corrections; below 2.426265: the same around pi/2 - |x|; below 105414350: Cody-Waite reduction by
+// pi/2 in four pieces.  Every rounding -- which products are fused into an FMA and which are not -- follows that build
+// (the TU is compiled --fmad=false, so fma() below is the only fusion).  tests/test_device_arithmetic_cpu.py builds
+// this header for the host and compares with libm on tens of millions of arguments: identical bits.
+// ---------------------------------------------------------------------------------------------------------
+#ifdef NWB_HOST_EMU
+static const double nwb_sincostab[4 * NWB_SINCOS_ROWS] = {NWB_SINCOS_TABLE};
+#else
+__device__ __align__(32) const double nwb_sincostab[4 * NWB_SINCOS_ROWS] = {NWB_SINCOS_TABLE};
+#endif
+
+struct SinCosRow { double sn, ssn, cs, ccs; };
+
+__device__ __forceinline__ SinCosRow sincos_row(int k)
+{
+	const Sector32 r = ldg_sector(nwb_sincostab + 4 * k);   // one 32-byte row, one request
+	SinCosRow t;
+	t.sn = __longlong_as_double((long long) r.q[0]); t.ssn = __longlong_as_double((long long) r.q[1]);
+	t.cs = __longlong_as_double((long long) r.q[2]); t.ccs = __longlong_as_double((long long) r.q[3]);
+	return t;
+}
+
+namespace gl {
+constexpr double big = 0x1.8p45, toint = 0x1.8p52;
+constexpr double sn3 = -0x1.5555555555515p-3, sn5 = 0x1.11110e829872fp-7;
+constexpr double cs2 = 0.5, cs4 = -0x1.5555555555535p-5, cs6 = 0x1.6c16bedd9e239p-10;
+constexpr double s1 = -0x1.5555555555555p-3, s2 = 0x1.1111111110ecep-7, s3 = -0x1.a01a019db08b8p-13,
+	s4 = 0x1.71de27b9a7ed9p-19, s5 = -0x1.addffc2fcdf59p-26;
+constexpr double hp0 = 0x1.921fb54442d18p+0, hp1 = 0x1.1a62633145c07p-54;
+constexpr double hpinv = 0x1.45f306dc9c883p-1, mp1 = 0x1.921fb58p+0, mp2 = -0x1.dde973cp-27, pp3 = -0x1.cb3b398p-55,
+	pp4 = -0x1.d747f23e32ed7p-83;
+
+// x + dx -> sin, |x| < 0.126
+__device__ __forceinline__ double taylor_sin(double x, double dx)
+{
+	const double xx = x * x;
+	const double poly = fma(fma(fma(fma(s5, xx, s4), xx, s3), xx, s2), xx, s1);
+	const double t = fma(xx, fma(poly, x, -(0.5 * dx)), dx);
+	return x + t;
+}
+
+// where |x| falls in the table: row k = rint(|x| * 128), remainder xr = |x| - k/128 (exact)
+__device__ __forceinline__ int table_split(double ax, double &xr)
+{
+	const double u = big + ax;
+	xr = ax - (u - big);
+	return __double2loint(u);
+}
+
+__device__ __forceinline__ double do_sin(double x, double dx)
+{
+	if (fabs(x) < 0.126) return taylor_sin(x, dx);
+	if (x <= 0) dx = -dx;
+	double xr;
+	const SinCosRow T = sincos_row(table_split(fabs(x), xr));
+	const double xx = xr * xr;
+	const double s = xr + fma(xr * xx, fma(xx, sn5, sn3), dx);
+	const double c = fma(xr, dx, xx * fma(xx, fma(xx, cs6, cs4), cs2));
+	const double cor = fma(s, T.cs, fma(-c, T.sn, fma(s, T.ccs, T.ssn)));
+	return copysign(T.sn + cor, x);
+}
+
+__device__ __forceinline__ double do_cos(double x, double dx)
+{
+	if (x < 0) dx = -dx;
+	double xr;
+	const SinCosRow T = sincos_row(table_split(fabs(x), xr));
+	xr = xr + dx;
+	const double xx = xr * xr;
+	const double s = fma(xr * xx, fma(xx, sn5, sn3), xr);
+	const double c = xx * fma(xx, fma(xx, cs6, cs4), cs2);
+	const double cor = fma(-s, T.sn, fma(-c, T.cs, fma(-s, T.ssn, T.ccs)));
+	return T.cs + cor;
+}
+
+// x = n pi/2 + (a + da), |a| <= pi/4 (+ rounding); 136 bits of pi/2
+__device__ __forceinline__ int reduce(double x, double &a, double &da)
+{
+	const double t = fma(x, hpinv, toint);
+	const double xn = t - toint;
+	const int n = __double2loint(t) & 3;
+	const double y = fma(-xn, mp2, fma(-xn, mp1, x));
+	const double t2 = fma(-xn, pp3, y);
+	const double d1 = fma(-pp3, xn, y - t2);
+	const double b = fma(-xn, pp4, t2);
+	const double d2 = fma(-xn, pp4, t2 - b);
+	a = b;
+	da = d1 + d2;
+	return n;
+}
+
+__device__ __forceinline__ double do_sincos(double a, double da, int n)
+{
+	const double r = (n & 1) ? do_cos(a, da) : do_sin(a, da);
+	return (n & 2) ? -r : r;
+}
+}  // namespace gl
+
+__device__ __forceinline__ double sin_ref(double x)
+{
+	const int k = __double2hiint(x) & 0x7fffffff;
+	if (k < 0x3e500000) return x;
+	if (k < 0x3feb6000) return gl::do_sin(x, 0.0);
+	if (k < 0x400368fd) return copysign(gl::do_cos(gl::hp0 - fabs(x), gl::hp1), x);
+	if (k < 0x419921fb) {
+		double a, da;
+		const int n = gl::reduce(x, a, da);
+		return gl::do_sincos(a, da, n);
+	}
+	return sin(x);   // |x| > 1e8 rad: not an angle this path produces
+}
+
+__device__ __forceinline__ double cos_ref(double x)
+{
+	const int k = __double2hiint(x) & 0x7fffffff;
+	if (k < 0x3e400000) return 1.0;
+	if (k < 0x3feb6000) return gl::do_cos(x, 0.0);
+	if (k < 0x400368fd) {
+		const double y = gl::hp0 - fabs(x);
+		const double a = y + gl::hp1;
+		const double da = (y - a) + gl::hp1;
+		return gl::do_sin(a, da);
+	}
+	if (k < 0x419921fb) {
+		double a, da;
+		const int n = gl::reduce(x, a, da);
+		return gl::do_sincos(a, da, n + 1);
+	}
+	return cos(x);
+}
+
+__device__ __forceinline__ void sincos_ref(double x, double *s, double *c)
+{
+	*s = sin_ref(x);
+	*c = cos_ref(x);
+}
+
 // reference: nwaylib/fastskymatch.py:31-34 -- divide by 180 first, then multiply by pi
 __device__ __forceinline__ double deg2rad_ref(double x) { return div_const(x, 180.0, NWB_INV180) * NWB_PI; }
 
 // Great-circle separation in ARCSEC between a (lower catalogue index) and b, from the precomputed
-// lon = ra/180*pi, sin/cos(dec/180*pi).  fastskymatch.py:36-47 then *60*60 (__init__.py:163).
-// The operation order is the reference's.  For the small angles this path lives on (|dlon| < 2^-7 rad and a
-// separation below 2^-7 rad) sin/cos/atan are evaluated by their Taylor polynomials, which are accurate to
-// well under 1 ulp there (truncation < 2^-70) and far cheaper than the general library routines; anything else
-// (near the poles, huge radii) takes the library route.
+// lon = ra/180*pi, sin/cos(dec/180*pi) (sincos_ref).  fastskymatch.py:36-47 then *60*60 (__init__.py:163).
+// The operation order is the reference's and sin / cos of the longitude difference carry the reference's bits
+// (sin_ref / cos_ref above): num2 and den are O(1) sums that cancel down to the separation, so those bits ARE the
+// result.  What follows the cancellation only has to be accurate in the relative sense: for separations below
+// 2^-7 rad hypot / atan2 are a square root and atan's Taylor polynomial (truncation < 2^-70); anything else (near
+// the poles, huge radii) takes the library routines.
 __device__ __forceinline__ double sep_arcsec_ref(double lon1, double slat1, double clat1,
 	double lon2, double slat2, double clat2)
 {
-	double dlon = lon2 - lon1;
-	double sdlon, cdlon;
-	if (fabs(dlon) < 0x1p-7) {
-		double x2 = dlon * dlon;
-		double ps = fma(x2, fma(x2, fma(x2, 1.0 / 362880, -1.0 / 5040), 1.0 / 120), -1.0 / 6);
-		sdlon = fma(dlon * x2, ps, dlon);
-		double pc = fma(x2, fma(x2, fma(x2, 1.0 / 40320, -1.0 / 720), 1.0 / 24), -0.5);
-		cdlon = fma(x2, pc, 1.0);
-	} else {
-		sincos(dlon, &sdlon, &cdlon);
-	}
+	const double dlon = lon2 - lon1;
+	const double sdlon = sin_ref(dlon), cdlon = cos_ref(dlon);
 	double num1 = clat2 * sdlon;
 	double num2 = clat1 * slat2 - slat1 * clat2 * cdlon;
 	double den = slat1 * slat2 + clat1 * clat2 * cdlon;
@@ -177,9 +315,9 @@ __device__ __forceinline__ void offsets_ref(double ra_o, double dec_o, double ra
 {
 	const double D2R = 0.017453292519943295, R2D = 57.29577951308232;   // numpy.radians / numpy.degrees constants
 	double so, co, st, ct, sd, cd;
-	sincos(dec_o * D2R, &so, &co);
-	sincos(dec_t * D2R, &st, &ct);
-	sincos(ra_t * D2R - ra_o * D2R, &sd, &cd);
+	sincos_ref(dec_o * D2R, &so, &co);
+	sincos_ref(dec_t * D2R, &st, &ct);
+	sincos_ref(ra_t * D2R - ra_o * D2R, &sd, &cd);
 	double lon = atan2(ct * sd, co * ct * cd + so * st);
 	double z = co * st - so * ct * cd;
 	double lat = asin(fmin(fmax(z, -1.0), 1.0));

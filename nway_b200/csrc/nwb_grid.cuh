@@ -98,7 +98,8 @@ __device__ __forceinline__ BandRec load_band(const Grid &G, int b)
 // K0: primaries
 // ---------------------------------------------------------------------------------------------------------
 struct PrimRec {   // 32 bytes = one L2 sector: what the exact formula needs of a primary
-	double lon, slat, clat, spare;
+	double lon, slat, clat;
+	long long ij;   // NWB_COMPAT_FLAT_HASH: the reference's flat-sky cell of the primary (flat_hash_pack), else 0
 };
 
 struct PrimArrays {
@@ -217,9 +218,11 @@ __device__ __forceinline__ void prim_register(const Grid &G, const int i, const 
 }
 // The reference's flat-sky hash (fastskymatch.py:125-132) puts a source into the buckets (i, j), (i+1, j), (i, j+1),
 // (i+1, j+1) with i = int(ra / err), j = int(dec / err) (python's int(): truncation toward zero; err = the search radius
-// in degrees), and forms tuples per bucket: a tuple exists iff the cells of its present members span at most one step
-// in i and in j.  Off the equator that loses pairs a complete search finds.  These two functions are the
-// predicate of the planned NWB_COMPAT_FLAT_HASH switch; no kernel calls them yet.
+// in degrees, match_radius / 60. / 60), and forms tuples per bucket: a tuple exists iff the cells of its present members
+// span at most one step in i and in j.  Off the equator that loses pairs a complete search finds.
+// NWB_COMPAT_FLAT_HASH applies exactly this predicate after the exact search -- to every (primary, secondary) pair in
+// k_pairs, to every tuple in k_count_rows / k_rows -- whenever the reference would take that branch
+// (fastskymatch.py:94-98, decided on the host from the catalogues' bounds).
 __device__ __forceinline__ long long flat_hash_cell(double coord_deg, double err_deg)
 {
 	return (long long) (coord_deg / err_deg);   // IEEE division, conversion truncates toward zero
@@ -230,6 +233,15 @@ __device__ __forceinline__ bool flat_hash_same_bucket(long long ia, long long ja
 	const long long di = ia - ib, dj = ja - jb;
 	return di >= -1 && di <= 1 && dj >= -1 && dj <= 1;
 }
+
+// (i, j) of a source in one 64-bit word (the host refuses radii so small that 360 / err leaves the int range)
+__device__ __forceinline__ long long flat_hash_pack(double ra_deg, double dec_deg, double err_deg)
+{
+	const int i = (int) flat_hash_cell(ra_deg, err_deg), j = (int) flat_hash_cell(dec_deg, err_deg);
+	return (long long) (((unsigned long long) (unsigned) i << 32) | (unsigned long long) (unsigned) j);
+}
+__device__ __forceinline__ int flat_hash_i(long long w) { return (int) (w >> 32); }
+__device__ __forceinline__ int flat_hash_j(long long w) { return (int) (unsigned) (unsigned long long) w; }
 
 // Where a secondary falls in the grid (first stage of k_pairs; the band record B is fetched in between): declination in
 // band heights from the lower edge (valid if 0 <= t < nbands), ra in degrees from the grid origin in [0, 360) (valid if

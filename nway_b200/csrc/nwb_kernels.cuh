@@ -29,7 +29,7 @@ namespace nwb {
 template <bool COUNT>
 __global__ void k_prim_prep(int np, long long first, const double *__restrict__ ra, const double *__restrict__ dec,
 	double rb, PrimArrays P, unsigned long long *__restrict__ red /* [6], zeroed */,
-	Grid G, double rb_ins, double dra_eps, int *__restrict__ cellcnt, double tau_max)
+	Grid G, double rb_ins, double dra_eps, int *__restrict__ cellcnt, double tau_max, double flat_err)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	double v[6] = {1e300, -1e300, 1e300, -1e300, 1e300, -1e300};   // dec min/max, A lo/hi, B lo/hi
@@ -37,9 +37,10 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 		double r = ra[first + i], d = dec[first + i];
 		double lat = deg2rad_ref(d);
 		double sl, cl;
-		sincos(lat, &sl, &cl);
+		sincos_ref(lat, &sl, &cl);
 		PrimRec pr;
-		pr.lon = deg2rad_ref(r); pr.slat = sl; pr.clat = cl; pr.spare = 0.0;
+		pr.lon = deg2rad_ref(r); pr.slat = sl; pr.clat = cl;
+		pr.ij = flat_err > 0.0 ? flat_hash_pack(r, d, flat_err) : 0ll;
 		P.rec[i] = pr;
 		double rn = wrap360(r);
 		const double dra = search_box_dra(d, rb);
@@ -177,6 +178,7 @@ struct K1Args {
 	SpillRec *spill;
 	unsigned long long spill_cap;
 	unsigned long long *spill_count;
+	double flat_err;   // > 0: NWB_COMPAT_FLAT_HASH is in force, = the reference's bucket size in degrees
 };
 
 // exact fp64 separation for `count` (<= 32) queued candidates, one per lane; a match takes the next slot of its
@@ -189,11 +191,16 @@ __device__ __forceinline__ void k1_flush(const K1Smem &M, int lo, int count, int
 		const int s = c.x, p = c.y;
 		const Sector32 pr = ldg_sector(A.P.rec + p);   // one sector, one request
 		double slat2, clat2;
-		sincos(deg2rad_ref(rd.y), &slat2, &clat2);
+		sincos_ref(deg2rad_ref(rd.y), &slat2, &clat2);
 		double lon2 = deg2rad_ref(rd.x);
 		double sep = sep_arcsec_ref(__longlong_as_double(pr.q[0]), __longlong_as_double(pr.q[1]), __longlong_as_double(pr.q[2]),
 			lon2, slat2, clat2);
-		if (sep < A.radius) {
+		bool keep = sep < A.radius;
+		if (keep && A.flat_err > 0.0) {   // the reference's hash never brought these two together (fastskymatch.py:125-132)
+			const long long ws = flat_hash_pack(rd.x, rd.y, A.flat_err), wp = (long long) pr.q[3];
+			keep = flat_hash_same_bucket(flat_hash_i(wp), flat_hash_j(wp), flat_hash_i(ws), flat_hash_j(ws));
+		}
+		if (keep) {
 			int slot = atomicAdd(&A.cnt[p], 1);
 			if (slot < A.C) {
 				int4 v;
@@ -452,7 +459,8 @@ __global__ void k_spill_scatter(long long n, const SpillRec *__restrict__ recs, 
 // secondary-secondary separations.
 __global__ void k_sort_lists(int np, PairStore S, const long long *__restrict__ seg_off, int *__restrict__ L_s,
 	double *__restrict__ L_sep, const double *__restrict__ ra, const double *__restrict__ dec,
-	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat, int small_n)
+	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat, int small_n,
+	long long *__restrict__ L_ij, double flat_err)
 {
 	int lane = threadIdx.x & 31;
 	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -468,10 +476,11 @@ __global__ void k_sort_lists(int np, PairStore S, const long long *__restrict__ 
 			L_s[lo + rank] = me.s;
 			L_sep[lo + rank] = me.sep;
 			double sl, cl;
-			sincos(deg2rad_ref(dec[me.s]), &sl, &cl);
+			sincos_ref(deg2rad_ref(dec[me.s]), &sl, &cl);
 			L_lon[lo + rank] = deg2rad_ref(ra[me.s]);
 			L_slat[lo + rank] = sl;
 			L_clat[lo + rank] = cl;
+			if (flat_err > 0.0) L_ij[lo + rank] = flat_hash_pack(ra[me.s], dec[me.s], flat_err);
 		}
 	}
 }
@@ -482,7 +491,8 @@ constexpr int SMALL_N = 4;
 
 __global__ void k_sort_lists_small(int np, PairStore S, const long long *__restrict__ seg_off, int *__restrict__ L_s,
 	double *__restrict__ L_sep, const double *__restrict__ ra, const double *__restrict__ dec,
-	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat)
+	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat,
+	long long *__restrict__ L_ij, double flat_err)
 {
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= np) return;
@@ -506,10 +516,11 @@ __global__ void k_sort_lists_small(int np, PairStore S, const long long *__restr
 		L_s[lo + e] = x[e].s;
 		L_sep[lo + e] = x[e].sep;
 		double sl, cl;
-		sincos(deg2rad_ref(dec[x[e].s]), &sl, &cl);
+		sincos_ref(deg2rad_ref(dec[x[e].s]), &sl, &cl);
 		L_lon[lo + e] = deg2rad_ref(ra[x[e].s]);
 		L_slat[lo + e] = sl;
 		L_clat[lo + e] = cl;
+		if (flat_err > 0.0) L_ij[lo + e] = flat_hash_pack(ra[x[e].s], dec[x[e].s], flat_err);
 	}
 }
 
@@ -580,6 +591,7 @@ __global__ void k_count_rows(RowParams R, long long *__restrict__ rows)
 			T *= nl[c] + 1;
 		}
 		if (T <= R.small_t) continue;   // k_count_rows_small's
+		const long long wp = R.flat_err > 0.0 ? flat_hash_pack(R.ra[0][R.first + p], R.dec[0][R.first + p], R.flat_err) : 0ll;
 		double *mat = R.mat + R.mat_off[p];
 		long long boff = 0;
 #pragma unroll
@@ -619,6 +631,7 @@ __global__ void k_count_rows(RowParams R, long long *__restrict__ rows)
 					bo += (long long) nl[a] * nl[b];
 				}
 			}
+			if (R.flat_err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
 			count += ok;
 		}
 		count = warp_sum_ll(count);
@@ -644,6 +657,7 @@ __global__ void k_count_rows_small(RowParams R, long long *__restrict__ rows)
 	}
 	if (T > R.small_t) return;
 	if (T == 1) { rows[p] = 1; return; }
+	const long long wp = R.flat_err > 0.0 ? flat_hash_pack(R.ra[0][R.first + p], R.dec[0][R.first + p], R.flat_err) : 0ll;
 	double *mat = R.mat + R.mat_off[p];
 	long long boff = 0;
 #pragma unroll
@@ -682,6 +696,7 @@ __global__ void k_count_rows_small(RowParams R, long long *__restrict__ rows)
 				bo += (long long) nl[a] * nl[b];
 			}
 		}
+		if (R.flat_err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
 		count += ok;
 	}
 	rows[p] = count;
@@ -786,6 +801,7 @@ k_rows(RowParams R)
 		const double *mat = NC > 2 ? R.mat + R.mat_off[p] : nullptr;
 		const long long gp = R.first + p;
 		const double sig0 = R.err[0][gp];
+		const long long wp = R.flat_err > 0.0 ? flat_hash_pack(R.ra[0][gp], R.dec[0][gp], R.flat_err) : 0ll;
 		long long written = 0;
 		for (long long t0 = 0; t0 < ntup; t0 += 32) {
 			long long t = t0 + lane;
@@ -832,6 +848,7 @@ k_rows(RowParams R)
 						}
 					}
 				}
+				if (R.flat_err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
 			}
 			unsigned m = __ballot_sync(NWB_FULL, ok);
 			if (ok) {
@@ -911,6 +928,7 @@ k_rows_small(RowParams R)
 	const long long rbase = R.row_off[p];
 	const double *mat = NC > 2 ? R.mat + R.mat_off[p] : nullptr;
 	const long long gp = R.first + p;
+	const long long wp = R.flat_err > 0.0 ? flat_hash_pack(R.ra[0][gp], R.dec[0][gp], R.flat_err) : 0ll;
 	double v[SMALL_T];
 	int nrow = 0;
 	for (int t = 0; t < ntup; t++) {
@@ -955,6 +973,7 @@ k_rows_small(RowParams R)
 				}
 			}
 		}
+		if (R.flat_err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
 		if (!ok) continue;
 		const long long row = rbase + nrow;
 		double smax = 0.0;
@@ -1321,6 +1340,36 @@ __global__ void k_minmax(long long n, const double *__restrict__ x, double *__re
 	}
 }
 
+// smallest / largest ra, largest |dec| and the number of NaNs of a catalogue: what the reference's choice between its
+// flat-sky and its HEALPix hash depends on (fastskymatch.py:94-98).  Order-preserving integer images as in k_prim_prep.
+__global__ void k_radec_bounds(long long n, const double *__restrict__ ra, const double *__restrict__ dec,
+	unsigned long long *__restrict__ out /* [0] min ra (pre-set ~0), [1] max ra, [2] max |dec|, [3] NaNs (pre-set 0) */)
+{
+	double lo = INFINITY, hi = -INFINITY, ad = 0.0;
+	unsigned long long nans = 0;
+	for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+		const double r = ra[i], d = dec[i];
+		if (r != r || d != d) nans++;
+		lo = fmin(lo, r); hi = fmax(hi, r); ad = fmax(ad, fabs(d));
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		lo = fmin(lo, __shfl_xor_sync(NWB_FULL, lo, o));
+		hi = fmax(hi, __shfl_xor_sync(NWB_FULL, hi, o));
+		ad = fmax(ad, __shfl_xor_sync(NWB_FULL, ad, o));
+		nans += __shfl_xor_sync(NWB_FULL, nans, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		auto key = [](double x) {
+			unsigned long long u = (unsigned long long) __double_as_longlong(x);
+			return u ^ ((u >> 63) ? ~0ull : 0x8000000000000000ull);
+		};
+		atomicMin(out + 0, key(lo));
+		atomicMax(out + 1, key(hi));
+		atomicMax(out + 2, key(ad));
+		if (nans) atomicAdd(out + 3, nans);
+	}
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // N1: automatic magnitude histograms (nwaylib/__init__.py:324-366, nway.py:455-503) -- the selection half on the device
 // ---------------------------------------------------------------------------------------------------------
@@ -1456,9 +1505,9 @@ __global__ void k_dist(long long n, const double *__restrict__ ra1, const double
 	long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	double s1, c1, s2, c2, sd, cd;
-	sincos(deg2rad_ref(dec1[i]), &s1, &c1);
-	sincos(deg2rad_ref(dec2[i]), &s2, &c2);
-	sincos(deg2rad_ref(ra2[i]) - deg2rad_ref(ra1[i]), &sd, &cd);
+	sincos_ref(deg2rad_ref(dec1[i]), &s1, &c1);
+	sincos_ref(deg2rad_ref(dec2[i]), &s2, &c2);
+	sincos_ref(deg2rad_ref(ra2[i]) - deg2rad_ref(ra1[i]), &sd, &cd);
 	double num1 = c2 * sd;
 	double num2 = c1 * s2 - s1 * c2 * cd;
 	double den = s1 * s2 + c1 * c2 * cd;

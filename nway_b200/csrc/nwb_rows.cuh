@@ -4,6 +4,7 @@
 // host and compare whole tables with an independent CPU computation.
 #pragma once
 #include "nwb_device.cuh"
+#include "nwb_grid.cuh"
 
 namespace nwb {
 
@@ -41,6 +42,7 @@ struct Lists {
 	const int *s[MAXC];
 	const double *sep[MAXC];
 	const double *lon[MAXC], *slat[MAXC], *clat[MAXC];
+	const long long *ij[MAXC];    // NWB_COMPAT_FLAT_HASH: the reference's flat-sky cell of every list entry (flat_hash_pack)
 };
 
 struct Columns {
@@ -63,6 +65,7 @@ struct RowParams {
 	const double *err[MAXC];         // sigma columns (circular); elliptical: sigma_x | sigma_y | rho, each n[c] long
 	int ell;                         // elliptical mode (nway.py:346-354): every catalogue carries a triple
 	int sep_f32;                     // nway.py compatibility: separations / offsets pass through float32
+	double flat_err;                 // > 0: NWB_COMPAT_FLAT_HASH in force; the reference's bucket size in degrees (radius / 60. / 60)
 	int small_t;                     // primaries with at most this many candidate tuples are handled by k_rows_small (0 = off)
 	long long n[MAXC];               // catalogue sizes (stride of the error triple)
 	const double *ra[MAXC], *dec[MAXC];
@@ -86,6 +89,24 @@ __device__ __forceinline__ bool guard_ok(const RowParams &R)
 {
 	if (!R.guard) return true;
 	return R.guard[9] == 0 && R.guard[1] == 0 && R.guard[8] <= R.max_rows && R.guard[0] <= R.entries_cap;
+}
+
+// NWB_COMPAT_FLAT_HASH: does the reference's flat-sky hash hold this tuple?  It does iff one bucket received all of its
+// present members, i.e. their cells span at most one step in i and in j (fastskymatch.py:125-132, 164-181).
+// wp = cell of the primary, dg[c] = 0 (absent) or 1 + position in catalogue c's list, lo[c] = start of that list.
+template <int NC>
+__device__ __forceinline__ bool tuple_in_one_bucket(const RowParams &R, long long wp, const int *dg, const long long *lo)
+{
+	int imin = flat_hash_i(wp), imax = imin, jmin = flat_hash_j(wp), jmax = jmin;
+#pragma unroll
+	for (int c = 1; c < NC; c++)
+		if (dg[c] > 0) {
+			const long long w = R.L.ij[c][lo[c] + dg[c] - 1];
+			const int i = flat_hash_i(w), j = flat_hash_j(w);
+			imin = min(imin, i); imax = max(imax, i);
+			jmin = min(jmin, j); jmax = max(jmax, j);
+		}
+	return imax - imin <= 1 && jmax - jmin <= 1;
 }
 
 // bias lookup for one row: returns sum of weights in the reference's order ((0 + w1) + w2 ...), writes bias cols

@@ -63,7 +63,8 @@ def reference_outputs(only=None):
 		res = refrun.run_reference(tables, spec['radius'], spec['completeness'], **spec.get('kwargs', {}))
 		# the oracle must agree with the real reference here and now, to the bit for the row set and
 		# to 1e-13 for the floats (it agrees to 0 ulp on this machine, but numpy SIMD paths may differ)
-		orc = O.nway_match(cases.build_case(name), spec['radius'], spec['completeness'], **spec.get('kwargs', {}))
+		orc = O.nway_match(cases.build_case(name), spec['radius'], spec['completeness'], enumerator=spec.get('enumerator', 'reference'),
+			**spec.get('kwargs', {}))
 		for c in res.columns:
 			a, b = res[c].values, orc[c]
 			assert len(a) == len(b), (name, c)

@@ -101,6 +101,25 @@ def crossproduct_refhash(radectables, err):
 	return np.array(sorted(tuples), dtype=np.int64)
 
 
+def flat_hash_keeps(radectables, err, idx):
+	"""Which index tuples does the reference's flat-sky hash form at all?  Those whose present members were all put
+	into one bucket: a source goes to the cells (i, j) .. (i+1, j+1) with i = int(ra / err), j = int(dec / err)
+	(fastskymatch.py:125-132), so the members share a bucket iff their i span at most one step and their j likewise.
+	Vectorised form of crossproduct_refhash (which restates the loops literally); equal to it on every row that
+	survives the radius filter -- tests/test_oracle_golden.py -- and pinned to the real reference by the off-equator
+	goldens (tests/golden/ref_offeq*.npz)."""
+	big = np.iinfo(np.int64).max
+	imin = np.full(len(idx), big); imax = np.full(len(idx), -big)
+	jmin = np.full(len(idx), big); jmax = np.full(len(idx), -big)
+	for c, (ras, decs) in enumerate(radectables):
+		present = idx[:, c] >= 0
+		ci = (ras / err).astype(np.int64)[idx[:, c]]
+		cj = (decs / err).astype(np.int64)[idx[:, c]]
+		imin = np.where(present, np.minimum(imin, ci), imin); imax = np.where(present, np.maximum(imax, ci), imax)
+		jmin = np.where(present, np.minimum(jmin, cj), jmin); jmax = np.where(present, np.maximum(jmax, cj), jmax)
+	return (imax - imin <= 1) & (jmax - jmin <= 1)
+
+
 def _unitvec(ra, dec):
 	lam, phi = np.radians(ra), np.radians(dec)
 	return np.stack([np.cos(phi) * np.cos(lam), np.cos(phi) * np.sin(lam), np.sin(phi)], axis=1)
@@ -174,7 +193,7 @@ def error_triples(tables):
 	return out
 
 
-def create_match_table(tables, match_radius, enumerator='complete', sep_f32=False, pairwise_errs=()):
+def create_match_table(tables, match_radius, enumerator='reference', sep_f32=False, pairwise_errs=()):
 	"""nwaylib/__init__.py:123-196.  Returns dict(idx (R,N) int64, sep {(a,b): (R,)}, sepmax, ncat,
 	errors [N x (R,)]); in elliptical mode also off {(a,b): (dra, ddec)} in arcsec, measured like the CLI does
 	(fastskymatch.py:299-331: offset frame centred on the source of the LATER catalogue b, the earlier one is the
@@ -187,6 +206,8 @@ def create_match_table(tables, match_radius, enumerator='complete', sep_f32=Fals
 		idx = crossproduct_refhash(radec, radius_deg)
 	else:
 		idx = crossproduct_complete(radec, radius_deg)
+		if enumerator == 'reference' and flat_sky_applicable(radec, radius_deg):
+			idx = idx[flat_hash_keeps(radec, radius_deg, idx)]
 	n = len(tables)
 	nrows = len(idx)
 	sep = {}
@@ -522,10 +543,14 @@ def group_statistics(v, starts, ratio_secondary):
 
 def nway_match(tables, match_radius, prior_completeness, mag_include_radius=None, mag_exclude_radius=None,
 		magauto_post_single_minvalue=0.9, prob_ratio_secondary=0.5, min_prob=0.,
-		unrelated_mode='api', enumerator='complete', cli_compat=False, pairwise_errs=()):
+		unrelated_mode='api', enumerator='reference', cli_compat=False, pairwise_errs=()):
 	"""nwaylib.nway_match (nwaylib/__init__.py:31-120) as a dict of numpy columns.
 	unrelated_mode 'api' reproduces the API (inert correction, Q1); 'cli' applies nway.py:366-421.
-	cli_compat: float32 separations / offsets (Q2) and the CLI's histogram weights (Q7), as nway.py computes."""
+	cli_compat: float32 separations / offsets (Q2) and the CLI's histogram weights (Q7), as nway.py computes.
+	enumerator: 'reference' (default) = the reference's row set: where nwaylib uses its flat-sky hash
+	(fastskymatch.py:94-98) the complete search filtered by that hash's bucket predicate (flat_hash_keeps, incomplete
+	away from the equator like the original), where it uses HEALPix the complete search; 'refhash' = the
+	flat-sky hash restated loop by loop (asserts that it applies); 'complete' = every association within the radius."""
 	if mag_exclude_radius is None:
 		mag_exclude_radius = mag_include_radius
 	n = len(tables)

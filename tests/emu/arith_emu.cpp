@@ -13,10 +13,16 @@ void nwb_emu_sep(long long n, const double *ra1, const double *dec1, const doubl
 {
 	for (long long i = 0; i < n; i++) {
 		double s1, c1, s2, c2;
-		sincos(deg2rad_ref(dec1[i]), &s1, &c1);
-		sincos(deg2rad_ref(dec2[i]), &s2, &c2);
+		sincos_ref(deg2rad_ref(dec1[i]), &s1, &c1);
+		sincos_ref(deg2rad_ref(dec2[i]), &s2, &c2);
 		out[i] = sep_arcsec_ref(deg2rad_ref(ra1[i]), s1, c1, deg2rad_ref(ra2[i]), s2, c2);
 	}
+}
+
+// sin_ref / cos_ref: glibc's double-precision sin / cos restated for the device
+void nwb_emu_sincos(long long n, const double *x, double *s, double *c)
+{
+	for (long long i = 0; i < n; i++) sincos_ref(x[i], &s[i], &c[i]);
 }
 
 void nwb_emu_div(long long n, const double *x, double *by180, double *bypi)

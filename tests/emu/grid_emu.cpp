@@ -39,8 +39,8 @@ long long nwb_emu_check(int np, const double *pra, const double *pdec, int ns, c
 		const double r = sra[s], d = sdec[s];
 		// the exact stage of k1_flush
 		double sl1, cl1, sl2, cl2;
-		sincos(deg2rad_ref(pdec[p]), &sl1, &cl1);
-		sincos(deg2rad_ref(d), &sl2, &cl2);
+		sincos_ref(deg2rad_ref(pdec[p]), &sl1, &cl1);
+		sincos_ref(deg2rad_ref(d), &sl2, &cl2);
 		const double sep = sep_arcsec_ref(deg2rad_ref(pra[p]), sl1, cl1, deg2rad_ref(r), sl2, cl2);
 		if (!(sep < radius_arcsec)) continue;
 		stats[0]++;

@@ -36,6 +36,8 @@ static inline double __hiloint2double(int hi, int lo)
 	memcpy(&d, &u, 8);
 	return d;
 }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
 static inline int __double2hiint(double d) { unsigned long long u; memcpy(&u, &d, 8); return (int) (u >> 32); }
 static inline int __double2loint(double d) { unsigned long long u; memcpy(&u, &d, 8); return (int) (u & 0xffffffffu); }
 static inline float __fmul_rn(float a, float b) { return a * b; }

@@ -32,8 +32,8 @@ long long nwb_emu_match2(int np, const double *pra, const double *pdec, const do
 	std::vector<PrimRec> prec(np);
 	for (int i = 0; i < np; i++) {
 		double sl, cl;
-		sincos(deg2rad_ref(pdec[i]), &sl, &cl);
-		prec[i].lon = deg2rad_ref(pra[i]); prec[i].slat = sl; prec[i].clat = cl; prec[i].spare = 0.0;
+		sincos_ref(deg2rad_ref(pdec[i]), &sl, &cl);
+		prec[i].lon = deg2rad_ref(pra[i]); prec[i].slat = sl; prec[i].clat = cl; prec[i].ij = 0;
 	}
 	// k_pairs: every secondary against the entries of its cell; survivors of the pre-test get the exact separation
 	std::vector<std::vector<Slot16>> match(np);
@@ -66,7 +66,7 @@ long long nwb_emu_match2(int np, const double *pra, const double *pdec, const do
 			if (!pass) continue;
 			// k1_flush
 			double slat2, clat2;
-			sincos(deg2rad_ref(d), &slat2, &clat2);
+			sincos_ref(deg2rad_ref(d), &slat2, &clat2);
 			const double lon2 = deg2rad_ref(r);
 			const double sp = sep_arcsec_ref(prec[p].lon, prec[p].slat, prec[p].clat, lon2, slat2, clat2);
 			if (sp < radius_arcsec) {

@@ -47,8 +47,8 @@ long long run(const int *n, const double *const *ra, const double *const *dec, c
 	std::vector<PrimRec> prec(np);
 	for (int i = 0; i < np; i++) {
 		double sl, cl;
-		sincos(deg2rad_ref(dec[0][i]), &sl, &cl);
-		prec[i].lon = deg2rad_ref(ra[0][i]); prec[i].slat = sl; prec[i].clat = cl; prec[i].spare = 0.0;
+		sincos_ref(deg2rad_ref(dec[0][i]), &sl, &cl);
+		prec[i].lon = deg2rad_ref(ra[0][i]); prec[i].slat = sl; prec[i].clat = cl; prec[i].ij = 0;
 	}
 	std::vector<std::vector<Item>> L[NC];
 	const double nbands_d = (double) G.nbands;
@@ -74,7 +74,7 @@ long long run(const int *n, const double *const *ra, const double *const *dec, c
 				else { const Entry &en = K.entries[estart + e]; p = en.p; pass = k1_pretest(G, (float) k1_ra_coord(G, r), (float) (d - G.dec_lo), en.x, en.y, en.clat); }
 				if (!pass) continue;
 				Item it;
-				sincos(deg2rad_ref(d), &it.slat, &it.clat);
+				sincos_ref(deg2rad_ref(d), &it.slat, &it.clat);
 				it.lon = deg2rad_ref(r);
 				it.sep = sep_arcsec_ref(prec[p].lon, prec[p].slat, prec[p].clat, it.lon, it.slat, it.clat);
 				it.s = s;

@@ -91,7 +91,7 @@ def random_case(seed):
 	return tables, radius, pc, kw, kind
 
 
-@pytest.mark.parametrize('seed', list(range(1000, 1060)))
+@pytest.mark.parametrize('seed', list(range(1000, 1080)))
 def test_random_configuration(seed):
 	import nway_b200
 	from oracle import nway_oracle as O
@@ -103,15 +103,22 @@ def test_random_configuration(seed):
 	copy = [dict(t) for t in tables]
 	got = nway_b200.nway_match(copy, radius, pc, logger=nway_b200.NullOutputLogger(), store_mag_hists=False, as_frame=False, **kw)
 	assert ref is not None
+	flat = O.flat_sky_applicable([(t['ra'], t['dec']) for t in tables], radius / 60. / 60)
+	assert nway_b200._lib.get_context().flat_hash_applied() == flat   # the device takes the reference's decision (fastskymatch.py:94-98)
+	if flat and seed % 2:
+		# ... and with the switch off it returns the complete enumeration (odd seeds: both are checked)
+		full = O.nway_match([dict(t) for t in tables], radius, pc, enumerator='complete', **kw)
+		got2 = nway_b200.nway_match([dict(t) for t in tables], radius, pc, logger=nway_b200.NullOutputLogger(), store_mag_hists=False, as_frame=False,
+			flat_hash_compat=False, **kw)
+		parity.assert_tables_match(full, got2, columns=[c for c in full if not c.startswith('_')], context='fuzz seed %d, complete' % seed,
+			rtol=5e-7 if kw.get('cli_compat') else None)
 	cols = [c for c in ref if not c.startswith('_')]
-	# Posterior-like columns: d p / p = ln(10) x d(log BF), and tests/parity.py accepts log BF at 1e-9 absolute -- the
-	# consistent bound on p is 2.3e-9 relative.  The golden configurations (separations of arcseconds, tests/
-	# test_gpu_parity.py) stay within the 1e-10 of the north star; the sub-arcsecond separations drawn here amplify the
-	# 1-ulp differences between CUDA's and glibc's sin / cos by 1 / separation (fastskymatch.py:44 cancels), so they are
-	# checked at the bound that follows from the log-BF tolerance.
-	rtol = 3e-9
-	if any(isinstance(t['error'], tuple) for t in tables):
-		rtol = 1e-8   # offsets near the poles: asin / atan2 of the device vs numpy, amplified by 1 / d
+	# The north star's tolerance (tests/parity.py: 1e-10 relative) everywhere the arithmetic is fp64: sin / cos carry the
+	# reference's bits (sin_ref / cos_ref), so the cancelling part of the separation formula (fastskymatch.py:44) is
+	# reproduced exactly, poles and sub-arcsecond separations included.
+	rtol = None
 	if kw.get('cli_compat'):
-		rtol = 5e-7   # separations are rounded to float32: a 1e-11 difference before the rounding can move it by one float32 ulp
+		# separations are rounded to float32 before they are scored: the few-ulp difference that hypot / atan2 leave in the
+		# fp64 value moves one float32 rounding in ~1e7, and that one then differs by a float32 ulp
+		rtol = 5e-7
 	parity.assert_tables_match(ref, got, columns=cols, context='fuzz seed %d (%s, r=%.3g, ncat=%d, %s)' % (seed, kind, radius, len(tables), sorted(kw)), rtol=rtol)

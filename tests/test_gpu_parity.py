@@ -30,14 +30,44 @@ def test_cuda_matches_oracle_and_reference(name):
 	kw = spec.get('kwargs', {})
 	got = run_cuda(cases.build_case(name), spec['radius'], spec['completeness'], **kw)
 	tables = cases.build_case(name)
-	ref = O.nway_match(tables, spec['radius'], spec['completeness'], **kw)
+	ref = O.nway_match(tables, spec['radius'], spec['completeness'], enumerator=spec.get('enumerator', 'reference'), **kw)
 	cols = [c for c in ref if not c.startswith('_')]
 	assert list(got.keys()) == cols, (list(got.keys()), cols)
-	# gpu_rtol: see tests/cases.py (the all-sky cases sit at high declinations, where the reference's own separation
-	# formula is ill-conditioned and 1-ulp differences of sin / cos show up at a few 1e-11 in the posteriors)
-	lines = parity.assert_tables_match(ref, got, columns=cols, context=name, rtol=spec.get('gpu_rtol'))
+	# every case at the north star's tolerance (tests/parity.py: 1e-10 relative), all-sky and off-equator included
+	lines = parity.assert_tables_match(ref, got, columns=cols, context=name)
 	report(name, lines)
-	parity.check_against_digest(name, got, [t['name'] for t in tables], rtol=spec.get('gpu_rtol'))
+	parity.check_against_digest(name, got, [t['name'] for t in tables])
+
+
+@pytest.mark.parametrize('name', ['offeq2', 'offeq3'])
+def test_flat_hash_switch(name):
+	"""NWB_COMPAT_FLAT_HASH on (default): the rows of the UNMODIFIED reference on a flat-sky field away from the equator
+	(committed golden, fastskymatch.py:94-101,123-133 leaves pairs out there); off: the complete enumeration, a strict
+	superset with identical per-row columns; and the switch is inert where the reference hashes with HEALPix."""
+	import nway_b200
+	from oracle import nway_oracle as O
+	spec = cases.GOLDEN_CASES[name]
+	names = [t['name'] for t in cases.build_case(name)]
+	on = run_cuda(cases.build_case(name), spec['radius'], spec['completeness'])
+	assert nway_b200._lib.get_context().flat_hash_applied()
+	parity.check_against_digest(name, on, names)
+	off = run_cuda(cases.build_case(name), spec['radius'], spec['completeness'], flat_hash_compat=False)
+	assert not nway_b200._lib.get_context().flat_hash_applied()
+	full = O.nway_match(cases.build_case(name), spec['radius'], spec['completeness'], enumerator='complete')
+	cols = [c for c in full if not c.startswith('_')]
+	report(name + '/complete', parity.assert_tables_match(full, off, columns=cols, context=name + '/complete'))
+	assert len(off[names[0]]) > len(on[names[0]])
+	rows_off = {tuple(r): k for k, r in enumerate(np.stack([off[n] for n in names], axis=1).tolist())}
+	pos = np.array([rows_off[tuple(r)] for r in np.stack([on[n] for n in names], axis=1).tolist()])   # KeyError = not a subset
+	for c in cols:
+		if c.startswith('Separation') or c.startswith('dist_') or c == 'ncat':
+			assert np.array_equal(np.asarray(on[c]), np.asarray(off[c])[pos], equal_nan=True), c   # per-row columns: same bits
+	# a whole-sky field: the reference uses its HEALPix hash, the switch changes nothing
+	a = run_cuda(cases.build_case('allsky2'), 120, 0.9)
+	assert not nway_b200._lib.get_context().flat_hash_applied()
+	b = run_cuda(cases.build_case('allsky2'), 120, 0.9, flat_hash_compat=False)
+	for c in a:
+		assert np.array_equal(np.asarray(a[c]), np.asarray(b[c]), equal_nan=True), c
 
 
 @pytest.mark.parametrize('mode', ['cli'])
@@ -193,11 +223,10 @@ def test_elliptical_errors(ncat, mode):
 		return tables
 	got = run_cuda(build(), 6.0, 0.9, unrelated_mode=mode)
 	ref = O.nway_match(build(), 6.0, 0.9, unrelated_mode=mode)
-	# tolerance 1e-8 here: the tangent-plane latitude asin(cos d1 sin d2 - sin d1 cos d2 cos dl) cancels ~4 digits at
-	# dec 35 deg (terms 0.47, result 3e-5), so 1-ulp differences of sin/cos give 1e-12 in the offsets and, through
-	# psi'^2 / sigma^2 (up to ~70 for rows with p_i >= 1e-30), a few 1e-10 in p_i; this piece is unpinned anyway
+	# at the north star's tolerance: the sines and cosines inside the tangent-plane offsets carry the reference's bits, so
+	# the cancelling latitude term cos d1 sin d2 - sin d1 cos d2 cos dl is reproduced exactly
 	report('elliptical%d/%s' % (ncat, mode), parity.assert_tables_match(ref, got, columns=[c for c in ref if not c.startswith('_')],
-		context='elliptical', rtol=1e-8))
+		context='elliptical'))
 	# and the reference's own consistency property (tests/bayesdistance_test.py:149-203): circular errors through
 	# the elliptical code give the circular answer to ~7 decimals
 	circ = cases.uniform_patch(19, (150, 4000, 3000)[:min(ncat, 3)], (1.0, 0.4, 0.6)[:min(ncat, 3)], 0.05)
