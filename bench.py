@@ -131,20 +131,39 @@ def hbm_peak():
 	return 6650.0, 'fallback'
 
 
-def cpu_port(scale, steps=1, warmup=0):
-	"""the reference's algorithm (oracle port, flat-sky hash + cartesian product + numpy scoring) on a bounded
-	sample of the workload: same surface densities, `scale` of the area.  Single-threaded, as the reference is."""
-	from oracle import nway_oracle as O
+WORKLOAD = 'C3 (BASELINE.json configs[2]): synthetic 2-cat, 100000 primaries per GPU x 10000000 secondaries uniform on 1 deg^2, r=5 arcsec, circular errors'
+
+
+def cpu_reference(scale, steps=1, warmup=0):
+	"""The reference's own CPU path on a bounded sample of the workload (same surface densities, `scale` of the area):
+	the UNMODIFIED nwaylib.nway_match from oracle/_ref (pip-installed copy of the reference, oracle/install_ref.py;
+	kind 'reference') -- or, where that copy is missing, the oracle's port of the same algorithm (flat-sky hash +
+	cartesian product + numpy scoring; kind 'port').  Single-threaded: the reference has no parallel path
+	(/root/reference/TODO:5-14; joblib is only its disk cache, bypassed here so that every step does the work)."""
 	tables, _ = make_workload(1, scale=scale)
+	from oracle import refrun
+	kind = 'reference' if refrun.package_root() is not None else 'port'
+	if kind == 'reference':
+		refrun.load_reference()
+		run = lambda: len(refrun.run_reference([dict(t) for t in tables], RADIUS, COMPLETENESS))
+	else:
+		from oracle import nway_oracle as O
+		run = lambda: len(O.nway_match(tables, RADIUS, COMPLETENESS, enumerator='refhash')['A'])
 	times, rows = [], 0
 	for k in range(warmup + steps):
 		t0 = time.perf_counter()
-		out = O.nway_match(tables, RADIUS, COMPLETENESS, enumerator='refhash')
+		rows = run()
 		dt = time.perf_counter() - t0
-		rows = len(out['A'])
 		if k >= warmup:
 			times.append(dt)
-	return rows, times
+	return rows, times, kind
+
+
+def cpu_sample_text(kind, scale, rows, sec):
+	what = ('the unmodified nwaylib.nway_match (nway 4.7.1, oracle/_ref), joblib cache bypassed' if kind == 'reference'
+		else 'oracle port of the reference algorithm (flat-sky hash + product + numpy scoring)')
+	return 'C3 at %.4g of the area (%d x %d sources, same densities): %d rows per step in %.2f s; %s; single-threaded like the reference' % (
+		scale, round(N_PRIMARY * scale), round(N_SECONDARY * scale), rows, sec, what)
 
 
 def run_reference(args):
@@ -153,24 +172,23 @@ def run_reference(args):
 		return
 	scale = args.ref_scale
 	if scale is None:
-		# bounded sample: size it so that the warm-up + K timed steps end within a minute or two on whatever host this is
-		# (the algorithm is linear in the area at fixed densities; one small probe step measures this host's speed)
+		# bounded sample: size it so that the warm-up + K timed steps end within about three minutes on whatever host this
+		# is (the algorithm is linear in the area at fixed densities; one small probe step measures this host's speed)
 		probe = 0.004
-		_, t = cpu_port(probe)
+		cpu_reference(probe)   # imports, first-call costs
+		_, t, _ = cpu_reference(probe)
 		per_unit = t[0] / probe
-		scale = max(0.002, min(0.05, 60.0 / (per_unit * (args.steps + min(args.warmup, 1)))))
-	rows, times = cpu_port(scale, steps=args.steps, warmup=min(args.warmup, 1))
+		scale = max(0.004, min(0.05, 150.0 / (per_unit * (args.steps + min(args.warmup, 1)))))
+	rows, times, kind = cpu_reference(scale, steps=args.steps, warmup=min(args.warmup, 1))
 	sec = sum(times) / len(times)
 	value = rows / sec
-	sample = 'C3 at %.4g of the area (%d x %d sources, same densities): %d rows per step in %.2f s' % (
-		scale, round(N_PRIMARY * scale), round(N_SECONDARY * scale), rows, sec)
 	line = {
 		'impl': 'reference', 'metric': 'candidate associations/sec', 'value': value, 'unit': 'associations/s',
 		'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
 		'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-		'config': {'workload': 'C3 synthetic 2-cat 1e5 x 1e7 on 1 deg^2, r=5 arcsec (bounded sample)', 'sample_scale': scale,
-			'radius_arcsec': RADIUS, 'prior_completeness': COMPLETENESS},
-		'cpu_baseline': {'value': value, 'unit': 'associations/s', 'cores': 1, 'kind': 'port', 'sample': sample},
+		'config': {'workload': WORKLOAD, 'radius_arcsec': RADIUS, 'prior_completeness': COMPLETENESS,
+			'sample': 'each step = the workload at %.4g of its area (same densities), see cpu_baseline.sample' % scale},
+		'cpu_baseline': {'value': value, 'unit': 'associations/s', 'cores': 1, 'kind': kind, 'sample': cpu_sample_text(kind, scale, rows, sec)},
 		'e2e': {'value': value, 'unit': 'associations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
 		'gpu_launches': 0,
 	}
@@ -437,16 +455,15 @@ def run_b200(args):
 
 	cpu = None
 	if world == 1 and not args.no_cpu:
-		crow, ctimes = cpu_port(args.cpu_scale)
-		cpu = {'value': crow / ctimes[0], 'unit': 'associations/s', 'cores': 1, 'kind': 'port',
-			'sample': 'C3 at %.4g of the area (%d x %d sources, same densities), %d rows in %.1f s; oracle port of the reference algorithm (flat-sky hash + product + numpy scoring), single-threaded like the reference' % (
-				args.cpu_scale, round(N_PRIMARY * args.cpu_scale), round(N_SECONDARY * args.cpu_scale), crow, ctimes[0])}
+		crow, ctimes, ckind = cpu_reference(args.cpu_scale)
+		cpu = {'value': crow / ctimes[0], 'unit': 'associations/s', 'cores': 1, 'kind': ckind,
+			'sample': cpu_sample_text(ckind, args.cpu_scale, crow, ctimes[0])}
 
 	line = {
 		'metric': 'candidate associations/sec', 'value': value, 'unit': 'associations/s', 'n_gpus': world,
 		'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step_max, 'higher_is_better': True,
 		'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-		'config': {'workload': 'C3 (BASELINE.json configs[2]): synthetic 2-cat, %d primaries per GPU x %d secondaries uniform on %.3g deg^2, r=5 arcsec, circular errors' % (n0, n1, args.scale),
+		'config': {'workload': WORKLOAD if args.scale == 1.0 else WORKLOAD + ' -- at %.3g of the area (%d x %d)' % (args.scale, n0, n1),
 			'rows_per_gpu': rows, 'pairs_per_gpu': pairs, 'radius_arcsec': RADIUS, 'prior_completeness': COMPLETENESS,
 			'parallelism': 'primary rows sharded, %d rank(s); secondaries replicated; exchange = NCCL all-gather of row counts (side stream, overlaps the next match)' % world,
 			'stepping': 'nwb_match_async back to back, nwb_match_wait every 32 steps and at the end', 'cpu_affinity': affinity,
@@ -473,7 +490,7 @@ def main():
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
 	ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C3 area (same densities); 1.0 = the named workload')
-	ap.add_argument('--cpu-scale', type=float, default=0.4, help='sample of the workload the CPU baseline is timed on')
+	ap.add_argument('--cpu-scale', type=float, default=0.05, help='sample of the workload the CPU baseline is timed on')
 	ap.add_argument('--ref-scale', type=float, default=None, help='sample per step of --impl reference (fraction of the C3 area; default: sized from --steps so that the run ends within about two minutes)')
 	ap.add_argument('--no-cpu', action='store_true')
 	args = ap.parse_args()

@@ -165,7 +165,9 @@ __device__ __forceinline__ double do_sincos(double a, double da, int n)
 }
 }  // namespace gl
 
-__device__ __forceinline__ double sin_ref(double x)
+// the complete functions, every branch.  Out of line: the hot paths below take the one or two branches their arguments
+// can reach inline and come here only for the rest.
+__device__ __noinline__ double sin_ref_any(double x)
 {
 	const int k = __double2hiint(x) & 0x7fffffff;
 	if (k < 0x3e500000) return x;
@@ -179,7 +181,7 @@ __device__ __forceinline__ double sin_ref(double x)
 	return sin(x);   // |x| > 1e8 rad: not an angle this path produces
 }
 
-__device__ __forceinline__ double cos_ref(double x)
+__device__ __noinline__ double cos_ref_any(double x)
 {
 	const int k = __double2hiint(x) & 0x7fffffff;
 	if (k < 0x3e400000) return 1.0;
@@ -198,11 +200,65 @@ __device__ __forceinline__ double cos_ref(double x)
 	return cos(x);
 }
 
+// sin and cos of a small angle (a longitude difference of a close pair): below 1/256 rad the sine is the odd
+// polynomial and the cosine sits on row 0 of the table (sin 0 = 0, cos 0 = 1: the corrections collapse to 1 - c) --
+// the same roundings as do_sin / do_cos, no table access
+__device__ __forceinline__ void sincos_ref_small(double x, double *s, double *c)
+{
+	const double ax = fabs(x);
+	if (ax <= 0x1p-8 && ax >= 0x1p-26) {
+		*s = gl::taylor_sin(x, 0.0);
+		const double xx = ax * ax;
+		*c = 1.0 - xx * fma(xx, fma(xx, gl::cs6, gl::cs4), gl::cs2);
+	} else {
+		*s = sin_ref_any(x);
+		*c = cos_ref_any(x);
+	}
+}
+
+// sin and cos of one angle in [-pi/2, pi/2] (a latitude): the table row, the remainder and the two polynomials are
+// shared between the sine and the cosine wherever glibc's two functions take the same branch
 __device__ __forceinline__ void sincos_ref(double x, double *s, double *c)
 {
-	*s = sin_ref(x);
-	*c = cos_ref(x);
+	const double ax = fabs(x);
+	const int hx = __double2hiint(ax);   // glibc branches on the high word
+	if (hx < 0x3feb6000 && hx >= 0x3e500000) {
+		double xr;
+		const int k = gl::table_split(ax, xr);
+		const double xx = xr * xr;
+		const double x3p = (xr * xx);
+		const double p = fma(xx, gl::sn5, gl::sn3);
+		const double cc = xx * fma(xx, fma(xx, gl::cs6, gl::cs4), gl::cs2);
+		if (k == 0) {   // |x| <= 1/256: row 0 is (0, 0, 1, 0)
+			*s = gl::taylor_sin(x, 0.0);
+			*c = 1.0 - cc;
+			return;
+		}
+		const SinCosRow T = sincos_row(k);
+		const double sc = fma(x3p, p, xr);                 // do_cos(x, 0): s
+		*c = T.cs + fma(-sc, T.sn, fma(-cc, T.cs, fma(-sc, T.ssn, T.ccs)));
+		if (ax < 0.126) {
+			*s = gl::taylor_sin(x, 0.0);
+		} else {
+			const double ss = xr + x3p * p;                  // do_sin(x, 0): s (dx = +-0 adds nothing), c = cc
+			*s = copysign(T.sn + fma(ss, T.cs, fma(-cc, T.sn, fma(ss, T.ccs, T.ssn))), x);
+		}
+		return;
+	}
+	if (hx >= 0x3feb6000 && hx < 0x400368fd) {   // around pi/2
+		const double y = gl::hp0 - ax;
+		*s = copysign(gl::do_cos(y, gl::hp1), x);
+		const double a = y + gl::hp1;
+		const double da = (y - a) + gl::hp1;
+		*c = gl::do_sin(a, da);
+		return;
+	}
+	*s = sin_ref_any(x);
+	*c = cos_ref_any(x);
 }
+
+__device__ __forceinline__ double sin_ref(double x) { return sin_ref_any(x); }
+__device__ __forceinline__ double cos_ref(double x) { return cos_ref_any(x); }
 
 // reference: nwaylib/fastskymatch.py:31-34 -- divide by 180 first, then multiply by pi
 __device__ __forceinline__ double deg2rad_ref(double x) { return div_const(x, 180.0, NWB_INV180) * NWB_PI; }
@@ -218,7 +274,8 @@ __device__ __forceinline__ double sep_arcsec_ref(double lon1, double slat1, doub
 	double lon2, double slat2, double clat2)
 {
 	const double dlon = lon2 - lon1;
-	const double sdlon = sin_ref(dlon), cdlon = cos_ref(dlon);
+	double sdlon, cdlon;
+	sincos_ref_small(dlon, &sdlon, &cdlon);
 	double num1 = clat2 * sdlon;
 	double num2 = clat1 * slat2 - slat1 * clat2 * cdlon;
 	double den = slat1 * slat2 + clat1 * clat2 * cdlon;

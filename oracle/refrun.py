@@ -1,10 +1,11 @@
-"""Run the UNMODIFIED reference (/root/reference, nway 4.7.1) in this container.
+"""Run the UNMODIFIED reference (nway 4.7.1): from /root/reference in the build container, or from the pip-installed
+copy oracle/_ref/ (oracle/install_ref.py; git-ignored, shipped to the GPU box with the snapshot).
 
-TEST INFRASTRUCTURE ONLY.  This module exists to (a) validate oracle/nway_oracle.py
-against the real reference and (b) generate the golden vectors committed under
-tests/golden/ (see oracle/make_golden.py).  It only works where /root/reference is
-mounted (the build container); nothing in the GPU tests, smoke() or bench.py may
-import it.
+TEST / BENCH INFRASTRUCTURE ONLY.  This module exists to (a) validate oracle/nway_oracle.py
+against the real reference, (b) generate the golden vectors committed under
+tests/golden/ (see oracle/make_golden.py) and (c) time the reference's own CPU path for
+bench.py --impl reference / cpu_baseline (from oracle/_ref only -- /root/reference does not
+exist on the GPU box).  The product never imports it.
 
 The reference cannot be imported as-is here because astropy, healpy and matplotlib
 are not installed.  We register inert stub modules for
@@ -18,11 +19,21 @@ import types
 
 import numpy
 
-REFERENCE_ROOT = '/root/reference'
+REFERENCE_ROOT = '/root/reference'                                     # the mounted source tree (build container only)
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')   # pip --target copy (oracle/install_ref.py)
 
 
 def reference_available():
+	"""the source tree with its demo catalogues and scripts (tests that need doc/ or nway.py check this)"""
 	return os.path.isdir(os.path.join(REFERENCE_ROOT, 'nwaylib'))
+
+
+def package_root():
+	"""where the unmodified nwaylib package can be imported from: the mounted tree, else the installed copy, else None"""
+	for root in (REFERENCE_ROOT, INSTALLED_ROOT):
+		if os.path.isfile(os.path.join(root, 'nwaylib', '__init__.py')):
+			return root
+	return None
 
 
 def _install_stubs():
@@ -86,12 +97,13 @@ def load_reference(scratch_dir='/tmp/nwb_refrun'):
 	global _nwaylib
 	if _nwaylib is not None:
 		return _nwaylib
-	assert reference_available(), 'reference not mounted at %s' % REFERENCE_ROOT
+	root = package_root()
+	assert root is not None, 'reference neither mounted at %s nor installed in %s' % (REFERENCE_ROOT, INSTALLED_ROOT)
 	_install_stubs()
 	os.makedirs(scratch_dir, exist_ok=True)
 	os.chdir(scratch_dir)
-	if REFERENCE_ROOT not in sys.path:
-		sys.path.insert(0, REFERENCE_ROOT)
+	if root not in sys.path:
+		sys.path.insert(0, root)
 	import nwaylib
 	import nwaylib.fastskymatch
 	import nwaylib.bayesdistance

@@ -25,6 +25,17 @@ void nwb_emu_sincos(long long n, const double *x, double *s, double *c)
 	for (long long i = 0; i < n; i++) sincos_ref(x[i], &s[i], &c[i]);
 }
 
+// the small-angle entry point (longitude differences) and the complete functions
+void nwb_emu_sincos_small(long long n, const double *x, double *s, double *c)
+{
+	for (long long i = 0; i < n; i++) sincos_ref_small(x[i], &s[i], &c[i]);
+}
+
+void nwb_emu_sincos_any(long long n, const double *x, double *s, double *c)
+{
+	for (long long i = 0; i < n; i++) { s[i] = sin_ref(x[i]); c[i] = cos_ref(x[i]); }
+}
+
 void nwb_emu_div(long long n, const double *x, double *by180, double *bypi)
 {
 	for (long long i = 0; i < n; i++) {

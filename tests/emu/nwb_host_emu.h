@@ -12,6 +12,7 @@
 #define __global__
 #define __constant__ static const
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 
 struct int2 { int x, y; };

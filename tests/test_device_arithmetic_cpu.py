@@ -72,10 +72,16 @@ def test_sin_cos_have_the_bits_of_the_reference(emu):
 		np.arange(-400, 400) / 128.0, (np.arange(-400, 400) + 0.5) / 128.0,     # the table's nodes and mid-points
 		np.concatenate([np.nextafter(s * v, [-np.inf, np.inf]) for v in edges for s in (1, -1)]), np.array(edges), -np.array(edges),
 		np.array([0.0, -0.0, 1e-300, 5e-324])))
+	x = np.concatenate((x, np.concatenate([np.nextafter(s * v, [-np.inf, np.inf]) for v in (2.0 ** -8, 2.0 ** -7, 1.5 / 128) for s in (1, -1)]),
+		np.array([2.0 ** -8, -2.0 ** -8]), rng.uniform(-2.0 ** -7, 2.0 ** -7, 2000000)))
 	s, c = np.empty_like(x), np.empty_like(x)
-	emu.nwb_emu_sincos(ctypes.c_longlong(len(x)), P(ptr(x)), P(ptr(s)), P(ptr(c)))
-	assert (s == np.sin(x)).all() and (c == np.cos(x)).all()
-	assert (np.signbit(s) == np.signbit(np.sin(x))).all()
+	# three entry points: latitudes (shared table row), small longitude differences (no table), every branch
+	for fn in (emu.nwb_emu_sincos, emu.nwb_emu_sincos_small, emu.nwb_emu_sincos_any):
+		s[:] = np.nan
+		c[:] = np.nan
+		fn(ctypes.c_longlong(len(x)), P(ptr(x)), P(ptr(s)), P(ptr(c)))
+		assert (s == np.sin(x)).all() and (c == np.cos(x)).all()
+		assert (np.signbit(s) == np.signbit(np.sin(x))).all()
 	# the scalar libm entry points the table was read from
 	for v in x[::200003]:
 		assert math.sin(v) == s[np.flatnonzero(x == v)[0]] and math.cos(v) == c[np.flatnonzero(x == v)[0]]
