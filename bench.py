@@ -214,7 +214,10 @@ def run_b200(args):
 
 	tables, n0 = make_workload(world, scale=args.scale)
 	ctx = _lib.Context(local)
-	stream = torch.cuda.current_stream()
+	# one explicit stream for the match kernels AND the collectives (torch's default stream has the handle 0, which the
+	# library reads as "use your own stream"): everything of a step is ordered on it
+	stream = torch.cuda.Stream(device=dev)
+	torch.cuda.set_stream(stream)
 	ctx.set_stream(stream.cuda_stream)
 
 	# ---- inputs resident in HBM ------------------------------------------------------------------------
@@ -228,6 +231,9 @@ def run_b200(args):
 	tab = nway_b200._scalar_tables(tables, COMPLETENESS, nway_b200.NullOutputLogger())
 	ctx.set_params(RADIUS, tab['pc'], 0.5, _lib.UNRELATED_API)
 	ctx.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
+	# the row set of the reference: on this flat-sky field nwaylib hashes on (ra, dec) cells (fastskymatch.py:94-101); the
+	# device applies the same bucket predicate to every match (at |dec| <= 0.5 deg it removes nothing, tests/test_gpu_fullsize.py)
+	ctx.set_compat(_lib.COMPAT_FLAT_HASH)
 	ctx.set_primary_range(rank * n0, n0)
 	# the one exchange of the sharded path: per-rank row counts (what is needed to place each shard in the global table),
 	# gathered by NCCL straight from device memory.  It runs on a side stream, double-buffered, so that the next
@@ -348,6 +354,7 @@ def run_b200(args):
 	# inputs from pinned host memory and all of its result columns back, in order, on its own stream.
 	ctx.set_stream(None)   # back to the context's own non-blocking stream
 	ctx_b = _lib.Context(local)
+	ctx_b.set_compat(_lib.COMPAT_FLAT_HASH)
 	lanes = [(ctx, host_out), (ctx_b, [torch.empty(rows + 1024, dtype=torch.float64).pin_memory() for _ in colsel])]
 
 	def e2e_begin(c, out):
@@ -383,7 +390,8 @@ def run_b200(args):
 	t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
 	if world > 1:
 		dist.all_reduce(t, op=dist.ReduceOp.MAX)
-	e2e_value = total_rows / (float(t.item()) * 1e-3)
+	e2e_ms_max = float(t.item())
+	e2e_value = total_rows / (e2e_ms_max * 1e-3)
 	for _, out in lanes:   # both lanes must have delivered the same table
 		for k in (1, 2, 10, 11):   # bit patterns (the index columns are int64 in these 8-byte buffers; -1 would read as NaN)
 			assert torch.equal(out[k][:rows].view(torch.int64), host_out[k][:rows].view(torch.int64)), 'lanes disagree in column %d' % k
@@ -392,31 +400,60 @@ def run_b200(args):
 	p_any = host_out[10][:rows].numpy()
 	assert np.isfinite(p_any).all() and (p_any >= -1e-12).all() and (p_any <= 1 + 1e-12).all()
 
-	# ---- (N > 1, informational) the padded NCCL all-gather of the whole table, outside the timed region -----------
-	allgather_ms = None
+	# ---- (N > 1) the same step WITH the reassembly of the output table: match, all-gather of the row counts, one
+	# unpadded all-gather-v of every rank's shard (12 columns) straight from the context's column allocation into
+	# its place in the gathered table (nway_b200.parallel.allgather_table: one NCCL group over NVLink) ----------------
+	table_gather = None
 	if world > 1:
 		from nway_b200 import parallel
-		ctx.set_primary_range(0, n0)   # the context still holds this rank's own block of primaries from the e2e loop
-		nr2 = ctx.match(fuse_final=True)
-		cols = {}
-		for k, sel in enumerate(colsel):
-			tns = torch.empty(nr2, dtype=torch.int64 if sel in (_lib.COL_IDX, _lib.COL_IDX + 1, _lib.COL_NCAT, _lib.COL_MATCH_FLAG) else torch.float64, device=dev)
-			ctx.fetch_device(sel, tns.data_ptr())
-			cols[k] = tns
-		ctx.sync()
-		cnts = parallel.exchange_counts(nr2, None, dev)
-		parallel.allgather_columns(cols, cnts)   # warm-up
+		torch.cuda.set_stream(stream)
+		ctx.set_stream(stream.cuda_stream)
+		for c, tb in enumerate(tables):   # back to the resident catalogues (the e2e loop left this rank's host copies in the context)
+			ra, dec, err = dev_arrays[c]
+			ctx.set_catalogue_device(c, len(tables), len(tb['ra']), ra.data_ptr(), dec.data_ptr(), err.data_ptr(), tb['area'])
+		ctx.set_params(RADIUS, tab['pc'], 0.5, _lib.UNRELATED_API)
+		ctx.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
+		ctx.set_primary_range(rank * n0, n0)
+		gtab = None
+
+		def gather_step():
+			nonlocal gtab
+			ctx.match_async(fuse_final=True)
+			nr = ctx.match_wait()
+			cnts = parallel.exchange_counts(nr, None, dev)
+			if gtab is None or gtab.shape[1] != sum(cnts):
+				gtab = torch.empty((len(colsel), sum(cnts)), dtype=torch.int64, device=dev)
+			parallel.allgather_table(ctx.table_view(), cnts, out=gtab)
+			return cnts
+
+		for _ in range(3):
+			cnts = gather_step()
 		barrier()
 		g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-		g0.record()
-		full = parallel.allgather_columns(cols, cnts)
-		g1.record()
+		gsteps = max(3, min(args.steps, 20))
+		g0.record(stream)
+		for _ in range(gsteps):
+			cnts = gather_step()
+		g1.record(stream)
 		barrier()
-		tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+		tg = torch.tensor([g0.elapsed_time(g1) / gsteps], dtype=torch.float64, device=dev)
 		dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-		allgather_ms = float(tg.item())
-		assert full[0].numel() == sum(cnts)
-		del full
+		gms = float(tg.item())
+		# the gathered table: every shard in rank order, primaries ascending, identical on all ranks
+		assert gtab.shape[1] == sum(cnts) == total_rows
+		prim = gtab[0]
+		assert bool((prim[1:] >= prim[:-1]).all()) and int(prim[0]) == 0 and int(prim[-1]) == world * n0 - 1
+		chk = torch.stack([gtab[0].sum(), gtab[4].sum()]).to(torch.float64)   # primary indices, ncat
+		mx, mn = chk.clone(), chk.clone()
+		dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+		dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+		assert bool((mx == mn).all()), 'the ranks hold different gathered tables'
+		recv_bytes = (total_rows - cnts[rank]) * 8 * len(colsel)
+		table_gather = {'value': total_rows / (gms * 1e-3), 'unit': 'associations/s', 'ms_per_step': gms, 'steps': gsteps,
+			'allgather_ms': gms - ms_step_max, 'received_bytes_per_gpu': recv_bytes,
+			'receive_GBs_per_gpu': recv_bytes / (max(gms - ms_step_max, 1e-6) * 1e-3) / 1e9,
+			'how': 'every step: match, NCCL all-gather of the row counts, then ONE grouped exchange (batch_isend_irecv = one ncclGroup) of every (column, peer) shard at its exact size from the context columns into the gathered table; all ranks end with the whole table in HBM'}
+		del gtab
 
 	if rank != 0:
 		if world > 1:
@@ -469,10 +506,11 @@ def run_b200(args):
 			'stepping': 'nwb_match_async back to back, nwb_match_wait every 32 steps and at the end', 'cpu_affinity': affinity,
 			'l2': 'inputs (%.0f MB) and outputs (%.0f MB) per step exceed the 126 MB L2; no explicit flush' % (h2d / 1e6, d2h / 1e6),
 			'stage_ms': {k: acc[k] / nsampled for k in acc}, 'grid': stats,
-			'allgather_full_table_ms': allgather_ms},
+			'compat': 'NWB_COMPAT_FLAT_HASH (the reference\'s flat-sky row set)'},
 		'roofline': roofline,
 		'cpu_baseline': cpu,
-		'e2e': {'value': e2e_value, 'unit': 'associations/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': float(t.item()),
+		'with_table_allgather': table_gather,
+		'e2e': {'value': e2e_value, 'unit': 'associations/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms_max,
 			'how': 'host pinned buffers through the C ABI, every step: H2D of all catalogue columns, match, D2H of all 12 result columns; two contexts in flight (the H2D + match of one step overlap the D2H of the previous one)',
 			'single_call_ms': single_call_ms},
 		'gpu_launches': launches,

@@ -188,10 +188,22 @@ int nwb_fetch(nwb_ctx *ctx, int column, void *dst_host);
 int nwb_fetch_device(nwb_ctx *ctx, int column, void *dst_device);
 /* device address of a column (valid until the next nwb_match on this context) */
 int nwb_column_ptr(nwb_ctx *ctx, int column, void **dev_ptr);
+/* The whole table at once: every column of the last match lives in ONE device allocation, column k (in the output order
+ * of the reference: indices, separations, Separation_max, ncat, dist_bayesfactor_uncorrected, dist_bayesfactor,
+ * dist_post, biases, p_single, match_flag, prob_has_match, prob_this_match) at base + k * stride_bytes, nrows 8-byte
+ * values each.  A multi-GPU caller sends its shard of every column straight from here (nway_b200.parallel) -- no
+ * per-column copy. */
+int nwb_table_layout(nwb_ctx *ctx, void **base, int64_t *stride_bytes, int *ncols, int64_t *nrows);
 /* device address of the int64 row count of the last match (lets a multi-GPU caller all-gather the per-rank row
  * counts with NCCL straight from device memory) */
 int nwb_nrows_device_ptr(nwb_ctx *ctx, void **dev_ptr);
 int nwb_sync(nwb_ctx *ctx);
+
+/* Measurement only: run the memory-system skeleton of the streaming kernel k_pairs for secondary catalogue c on the
+ * grid the last nwb_match left -- the same coalesced stream, cell-record gather, primary-record gather, slot atomicAdd
+ * and slot store, none of the arithmetic -- `reps` times and return the mean duration.  The floor
+ * the access pattern puts under k_pairs; bench.py reports it next to the kernel.  Invalidates the match result. */
+int nwb_bench_skeleton(nwb_ctx *ctx, int c, int reps, float *ms);
 
 /* per-stage device time of the last nwb_match (+ nwb_finalize), and how many kernels it launched */
 int nwb_timing(nwb_ctx *ctx, int stage, float *ms);

@@ -51,9 +51,11 @@ EXPORTS = {
 	'nwb_nrows_device_ptr': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
 	'nwb_fetch_device': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
 	'nwb_column_ptr': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+	'nwb_table_layout': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), c_int64_p, ctypes.POINTER(ctypes.c_int), c_int64_p]),
 	'nwb_sync': (ctypes.c_int, [ctypes.c_void_p]),
 	'nwb_timing': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
 	'nwb_launch_count': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
+	'nwb_bench_skeleton': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
 	'nwb_stats': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
 	'nwb_dist': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
 	'nwb_log_bf': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
@@ -183,6 +185,28 @@ class Context(object):
 
 	def set_compat(self, flags):
 		self.check(self.lib.nwb_set_compat(self.h, int(flags)))
+
+	def bench_skeleton(self, c=1, reps=5):
+		"""mean duration (ms) of the memory-system skeleton of k_pairs on the grid of the last match (invalidates its result)"""
+		v = ctypes.c_float(0)
+		self.check(self.lib.nwb_bench_skeleton(self.h, int(c), int(reps), ctypes.byref(v)))
+		return float(v.value)
+
+	def table_layout(self):
+		"""(base device pointer, column stride in bytes, number of columns, rows) of the last match's table"""
+		base, stride, ncols, nrows = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int(), ctypes.c_int64()
+		self.check(self.lib.nwb_table_layout(self.h, ctypes.byref(base), ctypes.byref(stride), ctypes.byref(ncols), ctypes.byref(nrows)))
+		return int(base.value or 0), int(stride.value), int(ncols.value), int(nrows.value)
+
+	def table_view(self):
+		"""the last match's table as a (ncols, nrows) int64 torch view of the context's own allocation (no copy; float
+		columns are read with .view(torch.float64)); valid until the next match on this context"""
+		import torch
+		base, stride, ncols, nrows = self.table_layout()
+		if nrows == 0 or base == 0:
+			return torch.empty((ncols, 0), dtype=torch.int64, device=torch.device('cuda', self.device))
+		flat = torch.as_tensor(DeviceView(base, ncols * (stride // 8)), device=torch.device('cuda', self.device))
+		return flat.view(ncols, stride // 8)[:, :nrows]
 
 	def flat_hash_applied(self):
 		"""did the last match apply the reference's flat-sky bucket predicate (COMPAT_FLAT_HASH)?"""

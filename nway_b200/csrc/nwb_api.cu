@@ -64,6 +64,10 @@ struct nwb_ctx {
 	double pc[MAXC];
 	int unrelated_mode = NWB_UNRELATED_API;
 	int compat = 0;
+	// what nwb_bench_skeleton needs of the last match: K1 arguments per secondary catalogue and the grid's buffers
+	K1Args last_k1[MAXC];
+	bool last_k1_dense = false;
+	const int *last_etotal = nullptr;
 	double flat_err = 0;             // > 0: this match applies the reference's flat-sky bucket predicate (NWB_COMPAT_FLAT_HASH)
 	bool any_big = true;             // some primary has more candidate tuples than k_rows_small handles
 	double prefilter[MAXP];          // per catalogue pair, arcsec; +inf = none
@@ -75,13 +79,13 @@ struct nwb_ctx {
 	DevBuf d_tables, d_prim, d_red, d_bands, d_cellcnt, d_entries, d_cub, d_pairs, d_paircount;
 	DevBuf d_cnt[MAXC], d_segoff[MAXC], d_seg_s[MAXC], d_seg_sep[MAXC], d_Ls[MAXC], d_Lsep[MAXC], d_Ltrig[MAXC];
 	DevBuf d_rows, d_rowoff, d_matsz, d_matoff, d_mat, d_cols, d_cols2, d_keep, d_keeppos, d_misc;
-	DevBuf d_spill, d_status, d_spilloff[MAXC], d_spillseg[MAXC], d_cells;
+	DevBuf d_spill, d_status, d_spilloff[MAXC], d_spillseg[MAXC], d_cells, d_worklist;
 	DevBuf d_hrow, d_hsrc, d_hout;   // automatic histograms: per-row / per-source scratch, compact sample
 	int hist_cat = -1, hist_k = -1;  // the (catalogue, magnitude) whose 'possible' marks d_hsrc holds
 	size_t entries_cap = 0;
 	unsigned long long spill_cap = 0;
 	long long *h_status = nullptr;   // pinned
-	int k1_blocks_per_sm = 0, num_sms = 0;
+	int k1_occ[8] = {0, 0, 0, 0, 0, 0, 0, 0}, num_sms = 0;   // resident blocks per SM of every k_pairs instantiation
 	// grid geometry of the previous match, re-used when the primaries' bounding box and the radius are unchanged
 	bool geom_valid = false;
 	double geom_rb = 0;
@@ -344,6 +348,39 @@ int launch_count(nwb_ctx *ctx, const RowParams &rp, long long *rows, int grid, b
 	return NWB_OK;
 }
 
+// k_pairs<DENSE, FLAT, SKEL>: band table in shared memory and no occupancy bitmap / the reference's flat-sky bucket
+// predicate on every match (NWB_COMPAT_FLAT_HASH) / the memory-system skeleton (nwb_bench_skeleton)
+int launch_pairs(nwb_ctx *ctx, bool dense, bool flat, bool skel, int n, const double *ra, const double *dec, const Grid &G,
+	const int *etotal, const CellRec *cells, const Entry *entries, long long entries_cap, const K1Args &ka)
+{
+	// persistent: exactly one wave of resident blocks of THIS instantiation (they differ in registers), each striding over
+	// the catalogue -- a grid sized for another variant's occupancy would leave SMs with an uneven number of blocks
+	const int which = (dense ? 1 : 0) | (flat ? 2 : 0) | (skel ? 4 : 0);
+	if (ctx->num_sms <= 0) {
+		int nsm = 0;
+		CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+		ctx->num_sms = std::max(nsm, 1);
+	}
+	if (ctx->k1_occ[which] <= 0) {
+		int nb = 0;
+#define NWB_OCC(D, F, S) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (k_pairs<D, F, S>), K1_WARPS * 32, 0))
+		if (skel) { if (dense) NWB_OCC(true, false, true); else NWB_OCC(false, false, true); }
+		else if (flat) { if (dense) NWB_OCC(true, true, false); else NWB_OCC(false, true, false); }
+		else { if (dense) NWB_OCC(true, false, false); else NWB_OCC(false, false, false); }
+#undef NWB_OCC
+		ctx->k1_occ[which] = std::max(nb, 1);
+	}
+	const int grid = (int) std::min<int64_t>(((int64_t) n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), (int64_t) ctx->num_sms * ctx->k1_occ[which]);
+	if ((int64_t) n + (int64_t) grid * K1_WARPS * 32 + 64 > 0x7fffffffll)
+		return fail(ctx, NWB_ERR_ARG, "catalogue too large: secondary indices are 32-bit");
+#define NWB_KP(D, F, S) LAUNCH(ctx, (k_pairs<D, F, S>), grid, K1_WARPS * 32, n, ra, dec, G, etotal, cells, entries, entries_cap, ka)
+	if (skel) { if (dense) NWB_KP(true, false, true); else NWB_KP(false, false, true); }
+	else if (flat) { if (dense) NWB_KP(true, true, false); else NWB_KP(false, true, false); }
+	else { if (dense) NWB_KP(true, false, false); else NWB_KP(false, false, false); }
+#undef NWB_KP
+	return NWB_OK;
+}
+
 }  // namespace
 
 // =========================================================================================================
@@ -384,7 +421,7 @@ void nwb_destroy(nwb_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *single[] = {&ctx->d_tables, &ctx->d_prim, &ctx->d_red, &ctx->d_bands, &ctx->d_cellcnt,
 		&ctx->d_entries, &ctx->d_cub, &ctx->d_pairs, &ctx->d_paircount, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_matsz,
-		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc, &ctx->d_spill, &ctx->d_status, &ctx->d_cells,
+		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc, &ctx->d_spill, &ctx->d_status, &ctx->d_cells, &ctx->d_worklist,
 		&ctx->d_hrow, &ctx->d_hsrc, &ctx->d_hout};
 	for (DevBuf *b : single) release(*b);
 	for (int c = 0; c < MAXC; c++) {
@@ -597,7 +634,7 @@ static int fill_row_params(nwb_ctx *ctx, const PairStore *stores, int64_t first,
 	rp.ell = ell ? 1 : 0;
 	rp.sep_f32 = (ctx->compat & NWB_COMPAT_SEP_F32) ? 1 : 0;
 	rp.small_t = SMALL_T;
-	rp.flat_err = ctx->flat_err;
+	rp.flat.err = ctx->flat_err; rp.flat.rerr = ctx->flat_err > 0.0 ? 1.0 / ctx->flat_err : 0.0;
 	for (int k = 0; k < MAXP; k++) rp.pair_radius[k] = ctx->prefilter_on ? std::min(ctx->radius, ctx->prefilter[k]) : ctx->radius;
 	rp.T = (const ConstTables *) ctx->d_tables.p;
 	rp.S1 = stores[1];
@@ -644,7 +681,7 @@ static int flat_hash_decision(nwb_ctx *ctx, double *flat_err)
 		flat = flat && !S.has_nan && S.ra_min > 10 * err && S.ra_max < 360 - 10 * err && S.absdec_max < 45;
 	}
 	if (!flat) return NWB_OK;
-	if (!(360.0 / err < 2147483000.0))
+	if (!(360.0 / err < 1073741000.0))
 		return fail(ctx, NWB_ERR_ARG, "NWB_COMPAT_FLAT_HASH: the radius is too small for 32-bit flat-sky cells");
 	*flat_err = err;
 	return NWB_OK;
@@ -680,6 +717,8 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	double flat_err = 0.0;
 	{ int r = flat_hash_decision(ctx, &flat_err); if (r) return r; }
 	ctx->flat_err = flat_err;
+	FlatHash flat;
+	flat.err = flat_err; flat.rerr = flat_err > 0.0 ? 1.0 / flat_err : 0.0;
 	if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocMapped));
 	long long *hs = ctx->h_status;
 
@@ -702,7 +741,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	if (!use_cached) {
 		CU(cudaMemsetAsync(d_red, 0, 6 * sizeof(unsigned long long), st));
 		LAUNCH(ctx, (k_prim_prep<false>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
-			Grid(), rb_ins, dra_eps, (int *) nullptr, entry_tau_max, flat_err);
+			Grid(), rb_ins, dra_eps, (int *) nullptr, entry_tau_max, flat, (CellRec *) nullptr, (OverflowItem *) nullptr, (int *) nullptr, (long long) 0);
 		// the grid geometry is chosen on the host from the bounding box: one sync.  It is kept for the next match
 		// on this context, which only has to verify (on the device) that the box is still the same.
 		unsigned long long *raw = (unsigned long long *) (hs + 32);
@@ -794,16 +833,21 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		if (attempt == 0 && use_cached) {
 			// known geometry: the primaries are counted into their cells by the preparation kernel itself
 			LAUNCH(ctx, k_zero, (int) std::min<size_t>((zero_ints / 4 + 255) / 256, 148 * 8), 256, (int4 *) d_cellcnt, (long long) (zero_ints / 4), d_red, 6);
+			// ... and placed: the first three of a cell inline, the rest noted in the work list (one pass over the primaries)
+			ENSURE(ctx->d_worklist, ctx->entries_cap * sizeof(OverflowItem));
 			LAUNCH(ctx, (k_prim_prep<true>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
-				G, rb_ins, dra_eps, d_cellcnt, entry_tau_max, flat_err);
+				G, rb_ins, dra_eps, d_cellcnt, entry_tau_max, flat, d_cells, (OverflowItem *) ctx->d_worklist.p, d_etotal + 2, (long long) ctx->entries_cap);
+			LAUNCH(ctx, k_cell_headers, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cellcnt, d_cells, (unsigned *) G.bits, d_etotal);
+			LAUNCH(ctx, k_fill_overflow, 148 * 2, 256, G, P, (const OverflowItem *) ctx->d_worklist.p, (const int *) (d_etotal + 2), (long long) ctx->entries_cap,
+				(const CellRec *) d_cells, d_entries, (const int *) d_etotal, (long long) ctx->entries_cap);
 		} else {
 			CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
 			LAUNCH(ctx, (k_prim_cells<false>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (CellRec *) nullptr,
 				(Entry *) nullptr, (const int *) nullptr, (long long) 0);
+			LAUNCH(ctx, k_cell_headers, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cellcnt, d_cells, (unsigned *) G.bits, d_etotal);
+			LAUNCH(ctx, (k_prim_cells<true>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, d_cells,
+				d_entries, (const int *) d_etotal, (long long) ctx->entries_cap);
 		}
-		LAUNCH(ctx, k_cell_headers, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cellcnt, d_cells, (unsigned *) G.bits, d_etotal);
-		LAUNCH(ctx, (k_prim_cells<true>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, d_cells,
-			d_entries, (const int *) d_etotal, (long long) ctx->entries_cap);
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[1], st));
 
 		// ---- K1: stream the secondaries ----------------------------------------------------------------
@@ -815,36 +859,29 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			stores[c].spill_off = nullptr;
 			stores[c].spill = nullptr;
 			if (n == 0) continue;
-			if (ctx->k1_blocks_per_sm <= 0) {
-				int nb = 0, nsm = 0;
-				CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pairs<false>, K1_WARPS * 32, 0));
-				CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-				ctx->k1_blocks_per_sm = std::max(nb, 1);
-				ctx->num_sms = std::max(nsm, 1);
-			}
-			// persistent: exactly one wave of resident blocks, each striding over the catalogue
-			int grid = (int) std::min<int64_t>((n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), (int64_t) ctx->num_sms * ctx->k1_blocks_per_sm);
-			if (n + (int64_t) grid * K1_WARPS * 32 + 64 > 0x7fffffffll)
-				return fail(ctx, NWB_ERR_ARG, "catalogue too large: secondary indices are 32-bit");
 			CU(cudaEventRecord(ctx->kev[2 * c], st));
 			K1Args ka;
 			ka.P = P; ka.radius = ctx->prefilter_on ? std::min(ctx->radius, ctx->prefilter[pair_index(0, c, nc)]) : ctx->radius; ka.base = d_base + base_off[c]; ka.C = Cs[c]; ka.cnt = d_cnt[c];
 			ka.spill = d_spill + (size_t) ctx->spill_cap * (c - 1); ka.spill_cap = (unsigned long long) ctx->spill_cap;
 			ka.spill_count = d_spillcount + c;
-			ka.flat_err = flat_err;
-			if (G.nbands <= K1_SBANDS && !G.bits)
-				LAUNCH(ctx, (k_pairs<true>), grid, K1_WARPS * 32, (int) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_etotal,
-					(const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
-			else
-				LAUNCH(ctx, (k_pairs<false>), grid, K1_WARPS * 32, (int) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_etotal,
-					(const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
+			ka.flat = flat;
+			ctx->last_k1[c] = ka; ctx->last_k1_dense = G.nbands <= K1_SBANDS && !G.bits;
+			ctx->last_etotal = d_etotal;
+			{ int r = launch_pairs(ctx, ctx->last_k1_dense, flat_err > 0.0, false, (int) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_etotal,
+				(const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka); if (r) return r; }
 			CU(cudaEventRecord(ctx->kev[2 * c + 1], st));
 		}
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[2], st));
-		if (!generic) { int r = scan_rows2(ctx, (const int *) d_cnt[1], d_rowoff, np); if (r) return r; }
-		LAUNCH(ctx, k_collect_status, 1, 32, nc, (const int *) d_etotal, (const unsigned long long *) d_spillcount,
-			!generic ? (const long long *) d_rowoff + np : (const long long *) nullptr, (const unsigned long long *) d_red,
-			ctx->geom_key, d_status, hs);
+		if (!generic && np <= (1 << 18)) {
+			// row offsets + status words in one single-block launch
+			LAUNCH(ctx, k_rowoff_status, 1, RO_THREADS, (int) np, (const int *) d_cnt[1], d_rowoff, nc, (const int *) d_etotal,
+				(const unsigned long long *) d_spillcount, (const unsigned long long *) d_red, ctx->geom_key, d_status, hs);
+		} else {
+			if (!generic) { int r = scan_rows2(ctx, (const int *) d_cnt[1], d_rowoff, np); if (r) return r; }
+			LAUNCH(ctx, k_collect_status, 1, 32, nc, (const int *) d_etotal, (const unsigned long long *) d_spillcount,
+				!generic ? (const long long *) d_rowoff + np : (const long long *) nullptr, (const unsigned long long *) d_red,
+				ctx->geom_key, d_status, hs);
+		}
 		// speculative K2: if the table of the previous match was big enough, launch the row kernel right away; it
 		// checks the status words on the device.  One host sync per match instead of three.
 		speculated = false;
@@ -940,10 +977,10 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			const long long *off = (const long long *) ctx->d_segoff[c].p;
 			if (npair) {
 				LAUNCH(ctx, k_sort_lists_small, pblocks, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
-					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair, (long long *) (tr + 3 * npair), flat_err);
+					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair, (long long *) (tr + 3 * npair), flat);
 				if (h_maxcnt[c] > SMALL_N)
 					LAUNCH(ctx, k_sort_lists, wgrid, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
-						ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair, SMALL_N, (long long *) (tr + 3 * npair), flat_err);
+						ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + npair, tr + 2 * npair, SMALL_N, (long long *) (tr + 3 * npair), flat);
 			}
 			L.off[c] = off;
 			L.s[c] = (const int *) ctx->d_Ls[c].p;
@@ -1164,6 +1201,17 @@ int nwb_column_ptr(nwb_ctx *ctx, int column, void **dev_ptr)
 	return column_lookup(ctx, column, dev_ptr);
 }
 
+int nwb_table_layout(nwb_ctx *ctx, void **base, int64_t *stride_bytes, int *ncols, int64_t *nrows)
+{
+	if (!ctx || !base || !stride_bytes || !ncols || !nrows) return NWB_ERR_ARG;
+	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	*base = ctx->d_cols.p;
+	*stride_bytes = (int64_t) (((size_t) std::max<int64_t>(ctx->cols_cap_rows, 1) * 8 + 255) / 256 * 256);
+	*ncols = ctx->ncols;
+	*nrows = ctx->nrows;
+	return NWB_OK;
+}
+
 int nwb_fetch(nwb_ctx *ctx, int column, void *dst_host)
 {
 	if (!ctx || !dst_host) return NWB_ERR_ARG;
@@ -1203,6 +1251,40 @@ int nwb_timing(nwb_ctx *ctx, int stage, float *ms)
 	if (!ctx || !ms || stage < 0 || stage >= NWB_T_COUNT) return NWB_ERR_ARG;
 	{ int r = refresh_timings(ctx); if (r) return r; }
 	*ms = ctx->ms[stage];
+	return NWB_OK;
+}
+
+int nwb_bench_skeleton(nwb_ctx *ctx, int c, int reps, float *ms)
+{
+	if (!ctx || !ms) return NWB_ERR_ARG;
+	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	if (c < 1 || c >= ctx->res_ncat || ctx->cat[c].n == 0 || reps < 1) return fail(ctx, NWB_ERR_ARG, "bad catalogue / repetitions");
+	CU(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const Grid G = ctx->geom_G;
+	K1Args ka = ctx->last_k1[c];
+	// the skeleton takes its slots from a counter array of its own; the slot area it scribbles over is the match's
+	ENSURE(ctx->d_misc, (size_t) (ctx->np + 1) * sizeof(int));
+	ka.cnt = (int *) ctx->d_misc.p;
+	ctx->matched = ctx->finalized = false;   // the pair store no longer holds the match
+	cudaEvent_t e0, e1;
+	CU(cudaEventCreate(&e0));
+	CU(cudaEventCreate(&e1));
+	float total = 0;
+	for (int k = 0; k < reps + 1; k++) {
+		CU(cudaMemsetAsync(ka.cnt, 0, (size_t) (ctx->np + 1) * sizeof(int), st));
+		CU(cudaEventRecord(e0, st));
+		{ int r = launch_pairs(ctx, ctx->last_k1_dense, false, true, (int) ctx->cat[c].n, ctx->cat[c].ra, ctx->cat[c].dec, G,
+			(const int *) ctx->last_etotal, (const CellRec *) ctx->d_cells.p, (const Entry *) ctx->d_entries.p, (long long) ctx->entries_cap, ka); if (r) return r; }
+		CU(cudaEventRecord(e1, st));
+		CU(cudaStreamSynchronize(st));
+		float t = 0;
+		CU(cudaEventElapsedTime(&t, e0, e1));
+		if (k > 0) total += t;   // the first repetition warms up
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	*ms = total / reps;
 	return NWB_OK;
 }
 

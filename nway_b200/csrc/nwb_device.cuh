@@ -167,7 +167,15 @@ __device__ __forceinline__ double do_sincos(double a, double da, int n)
 
 // the complete functions, every branch.  Out of line: the hot paths below take the one or two branches their arguments
 // can reach inline and come here only for the rest.
-__device__ __noinline__ double sin_ref_any(double x)
+#ifndef NWB_SINCOS_ANY_INLINE
+#define NWB_SINCOS_ANY_INLINE 0
+#endif
+#if NWB_SINCOS_ANY_INLINE
+#define NWB_ANY_ATTR __forceinline__
+#else
+#define NWB_ANY_ATTR __noinline__
+#endif
+__device__ NWB_ANY_ATTR double sin_ref_any(double x)
 {
 	const int k = __double2hiint(x) & 0x7fffffff;
 	if (k < 0x3e500000) return x;
@@ -181,7 +189,7 @@ __device__ __noinline__ double sin_ref_any(double x)
 	return sin(x);   // |x| > 1e8 rad: not an angle this path produces
 }
 
-__device__ __noinline__ double cos_ref_any(double x)
+__device__ NWB_ANY_ATTR double cos_ref_any(double x)
 {
 	const int k = __double2hiint(x) & 0x7fffffff;
 	if (k < 0x3e400000) return 1.0;
@@ -205,6 +213,10 @@ __device__ __noinline__ double cos_ref_any(double x)
 // the same roundings as do_sin / do_cos, no table access
 __device__ __forceinline__ void sincos_ref_small(double x, double *s, double *c)
 {
+#if defined(NWB_AB_LIBRARY_SINCOS) && !defined(NWB_HOST_EMU)   // A/B measurement only: what the reference's bits cost (round-1 arithmetic)
+	sincos(x, s, c);
+	return;
+#endif
 	const double ax = fabs(x);
 	if (ax <= 0x1p-8 && ax >= 0x1p-26) {
 		*s = gl::taylor_sin(x, 0.0);
@@ -220,6 +232,10 @@ __device__ __forceinline__ void sincos_ref_small(double x, double *s, double *c)
 // shared between the sine and the cosine wherever glibc's two functions take the same branch
 __device__ __forceinline__ void sincos_ref(double x, double *s, double *c)
 {
+#if defined(NWB_AB_LIBRARY_SINCOS) && !defined(NWB_HOST_EMU)
+	sincos(x, s, c);
+	return;
+#endif
 	const double ax = fabs(x);
 	const int hx = __double2hiint(ax);   // glibc branches on the high word
 	if (hx < 0x3feb6000 && hx >= 0x3e500000) {

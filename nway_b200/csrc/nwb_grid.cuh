@@ -128,15 +128,24 @@ __device__ __forceinline__ double search_box_dra(double d, double rb)
 }
 
 // Register one primary in every grid cell its (slightly inflated) search box overlaps.
-// FILL = false: cellcnt[cell] += 1.
-// FILL = true : take a slot of the cell by counting cellcnt back down (no second memset).  Slots 0..2 live INSIDE the
+// MODE = REG_COUNT: cellcnt[cell] += 1.
+// MODE = REG_FILL : take a slot of the cell by counting cellcnt back down (no second memset).  Slots 0..2 live INSIDE the
 // cell record (packed, see PEntry) and are written there directly; later slots go to the cell's overflow segment of
-// `entries`, whose start k_cell_headers put into the record.  Both passes enumerate the same (band, cell) pairs from the
-// same doubles, whichever thread layout (bslot, bstride) they use.
-template <bool FILL>
+// `entries`, whose start k_cell_headers put into the record.
+// MODE = REG_COUNT_INLINE (grid geometry known beforehand): count AND place in one pass -- the slot is the value the
+// counting atomicAdd returns; slots 0..2 are written into the cell record right away, the few later ones (5 % at the
+// benchmark's densities) are noted in a work list (primary, cell, slot) and stored by k_fill_overflow once
+// k_cell_headers has handed out the overflow segments.  No separate fill pass over all primaries.
+// All passes enumerate the same (band, cell) pairs from the same doubles, whichever thread layout (bslot, bstride).
+enum { REG_COUNT = 0, REG_FILL = 1, REG_COUNT_INLINE = 2 };
+
+struct OverflowItem { int p, cell, slot, pad; };   // 16 bytes
+
+template <int MODE>
 __device__ __forceinline__ void prim_register(const Grid &G, const int i, const double d, const double rn, const double dra,
 	const double clat_i, const double rb_ins, const double dra_eps, const int bslot, const int bstride,
-	int *__restrict__ cellcnt, CellRec *cells, Entry *__restrict__ entries)
+	int *__restrict__ cellcnt, CellRec *cells, Entry *__restrict__ entries,
+	OverflowItem *__restrict__ worklist = nullptr, int *__restrict__ worklist_n = nullptr, long long worklist_cap = 0)
 {
 	int b0 = band_of(G, d - rb_ins), b1 = band_of(G, d + rb_ins);
 	b0 = max(b0, 0);
@@ -168,7 +177,7 @@ __device__ __forceinline__ void prim_register(const Grid &G, const int i, const 
 			cnt = i1 - i0 + 1;
 		}
 		int cb = B.base;
-		if (!FILL) {
+		if (MODE == REG_COUNT) {
 			for (int k = 0; k < cnt; k++) atomicAdd(&cellcnt[cb + (i0 + k) % n], 1);
 			continue;
 		}
@@ -182,7 +191,7 @@ __device__ __forceinline__ void prim_register(const Grid &G, const int i, const 
 				cell[u] = 0;
 				if (k0 + u < cnt) {
 					cell[u] = cb + (i0 + k0 + u) % n;
-					sl[u] = atomicSub(&cellcnt[cell[u]], 1) - 1;
+					sl[u] = MODE == REG_FILL ? atomicSub(&cellcnt[cell[u]], 1) - 1 : atomicAdd(&cellcnt[cell[u]], 1);
 				}
 			}
 #pragma unroll
@@ -199,6 +208,13 @@ __device__ __forceinline__ void prim_register(const Grid &G, const int i, const 
 					}
 					const unsigned xy = pe_encode(xc - (double) m, yp - (double) b, always);
 					cells[cell[u]].q[1 + sl[u]] = (unsigned long long) xy | ((unsigned long long) (unsigned) i << 32);
+				} else if (MODE == REG_COUNT_INLINE) {
+					const int pos = atomicAdd(worklist_n, 1);
+					if ((long long) pos < worklist_cap) {
+						int4 v;
+						v.x = i; v.y = cell[u]; v.z = sl[u]; v.w = 0;
+						*reinterpret_cast<int4 *>(worklist + pos) = v;
+					}
 				} else {
 					if (!have_en) {   // the fp32 entry of the crowded cells' work items (rare: computed on demand)
 						double x = rn - G.ra_org_n;
@@ -234,10 +250,26 @@ __device__ __forceinline__ bool flat_hash_same_bucket(long long ia, long long ja
 	return di >= -1 && di <= 1 && dj >= -1 && dj <= 1;
 }
 
-// (i, j) of a source in one 64-bit word (the host refuses radii so small that 360 / err leaves the int range)
-__device__ __forceinline__ long long flat_hash_pack(double ra_deg, double dec_deg, double err_deg)
+// The bucket size and its reciprocal.  int(coord / err) needs the correctly rounded quotient (a cell boundary is
+// exactly where the rounding decides); q0 = RN(coord * rerr), the FMA residual and one FMA correction give it without
+// the division subroutine (Markstein, as div_const) -- coordinates are at most 360 and err is in (360 / 2^31, 1), so
+// nothing over- or underflows on the way.  Checked against coord / err in tests/test_device_arithmetic_cpu.py.
+struct FlatHash {
+	double err;    // 0 = NWB_COMPAT_FLAT_HASH not in force
+	double rerr;   // RN(1 / err)
+};
+
+__device__ __forceinline__ int flat_hash_cell_fast(double coord_deg, const FlatHash &F)
 {
-	const int i = (int) flat_hash_cell(ra_deg, err_deg), j = (int) flat_hash_cell(dec_deg, err_deg);
+	const double q0 = coord_deg * F.rerr;
+	const double r = fma(-q0, F.err, coord_deg);
+	return (int) fma(r, F.rerr, q0);
+}
+
+// (i, j) of a source in one 64-bit word (the host refuses radii so small that 360 / err leaves the int range)
+__device__ __forceinline__ long long flat_hash_pack(double ra_deg, double dec_deg, const FlatHash &F)
+{
+	const int i = flat_hash_cell_fast(ra_deg, F), j = flat_hash_cell_fast(dec_deg, F);
 	return (long long) (((unsigned long long) (unsigned) i << 32) | (unsigned long long) (unsigned) j);
 }
 __device__ __forceinline__ int flat_hash_i(long long w) { return (int) (w >> 32); }

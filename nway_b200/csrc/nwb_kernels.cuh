@@ -29,7 +29,8 @@ namespace nwb {
 template <bool COUNT>
 __global__ void k_prim_prep(int np, long long first, const double *__restrict__ ra, const double *__restrict__ dec,
 	double rb, PrimArrays P, unsigned long long *__restrict__ red /* [6], zeroed */,
-	Grid G, double rb_ins, double dra_eps, int *__restrict__ cellcnt, double tau_max, double flat_err)
+	Grid G, double rb_ins, double dra_eps, int *__restrict__ cellcnt, double tau_max, FlatHash flat,
+	CellRec *cells, OverflowItem *__restrict__ worklist, int *__restrict__ worklist_n, long long worklist_cap)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	double v[6] = {1e300, -1e300, 1e300, -1e300, 1e300, -1e300};   // dec min/max, A lo/hi, B lo/hi
@@ -40,7 +41,7 @@ __global__ void k_prim_prep(int np, long long first, const double *__restrict__ 
 		sincos_ref(lat, &sl, &cl);
 		PrimRec pr;
 		pr.lon = deg2rad_ref(r); pr.slat = sl; pr.clat = cl;
-		pr.ij = flat_err > 0.0 ? flat_hash_pack(r, d, flat_err) : 0ll;
+		pr.ij = flat.err > 0.0 ? flat_hash_pack(r, d, flat) : 0ll;
 		P.rec[i] = pr;
 		double rn = wrap360(r);
 		const double dra = search_box_dra(d, rb);
@@ -99,7 +100,30 @@ k_prim_cells(int np, Grid G, PrimArrays P, double rb_ins, double dra_eps,
 	const int i = t >> 2, bslot = t & 3;
 	if (i >= np) return;
 	if (FILL && (long long) etotal[0] > entries_cap) return;
-	prim_register<FILL>(G, i, P.dec[i], P.ra_n[i], P.dra[i], FILL ? P.clat[i] : 0.0, rb_ins, dra_eps, bslot, 4, cellcnt, cells, entries);
+	prim_register<FILL ? REG_FILL : REG_COUNT>(G, i, P.dec[i], P.ra_n[i], P.dra[i], FILL ? P.clat[i] : 0.0, rb_ins, dra_eps, bslot, 4, cellcnt, cells, entries);
+}
+
+// the entries beyond a cell's third, noted by k_prim_prep<COUNT> (prim_register<REG_COUNT_INLINE>): 16-byte fp32 entries
+// into the overflow segments k_cell_headers handed out
+__global__ void __launch_bounds__(256)
+k_fill_overflow(Grid G, PrimArrays P, const OverflowItem *__restrict__ worklist, const int *__restrict__ worklist_n, long long worklist_cap,
+	const CellRec *__restrict__ cells, Entry *__restrict__ entries, const int *__restrict__ etotal, long long entries_cap)
+{
+	if ((long long) etotal[0] > entries_cap) return;   // the host retries with a bigger buffer
+	const long long n = min((long long) worklist_n[0], worklist_cap);
+	for (long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long) gridDim.x * blockDim.x) {
+		const int4 it = __ldg(reinterpret_cast<const int4 *>(worklist + k));
+		const int i = it.x;
+		double x = P.ra_n[i] - G.ra_org_n;
+		if (x < 0.0) x += 360.0;
+		Entry en;
+		en.x = (float) x;
+		en.y = (float) (P.dec[i] - G.dec_lo);
+		en.clat = (float) P.clat[i];
+		en.p = i;
+		const int est = (int) (cells[it.y].q[0] >> 32);
+		*reinterpret_cast<int4 *>(entries + est + it.z) = *reinterpret_cast<const int4 *>(&en);
+	}
 }
 
 // One header per cell: q[0] = count | (start of the cell's overflow segment - 3) << 32, so that entry k >= 3 of the cell
@@ -152,13 +176,19 @@ k_cell_headers(long long ncells, const int *__restrict__ cellcnt, CellRec *__res
 // runs full warps instead of the 1-5 active lanes a per-thread loop would give.  A match takes the next slot of
 // its primary (atomicAdd on the per-primary counter) and is written there directly -- no append buffer, no
 // scatter pass.
-constexpr int K1_WARPS = 8;
+#ifndef NWB_K1_WARPS
+#define NWB_K1_WARPS 8
+#endif
+constexpr int K1_WARPS = NWB_K1_WARPS;
 constexpr int K1_ICAP = 64;                      // work items: 31 left over + 32 new (tested before the next 32)
 constexpr int K1_QCAP = 64;                      // candidates: 31 left over + 32 new (flushed before the next 32)
 constexpr int K1_SBANDS = 1024;                  // bands cached in shared memory (16 KB)
 
+// resident blocks per SM the register budget is set for: 3 (<= 80 registers; the kernel wants 76-80 with the reference's
+// sin / cos and the flat-hash predicate in the exact stage).  At 4 (64 registers) ptxas spills loop-carried values of the
+// streaming loop: measured 291-302 us against 228-236 us on the benchmark (profiles/r02_kpairs_variants.txt)
 #ifndef NWB_K1_MINBLOCKS
-#define NWB_K1_MINBLOCKS 4
+#define NWB_K1_MINBLOCKS 3
 #endif
 
 
@@ -178,27 +208,50 @@ struct K1Args {
 	SpillRec *spill;
 	unsigned long long spill_cap;
 	unsigned long long *spill_count;
-	double flat_err;   // > 0: NWB_COMPAT_FLAT_HASH is in force, = the reference's bucket size in degrees
+	FlatHash flat;     // NWB_COMPAT_FLAT_HASH (k_pairs<.., FLAT = true>): the reference's bucket size in degrees
 };
 
 // exact fp64 separation for `count` (<= 32) queued candidates, one per lane; a match takes the next slot of its
 // primary
-__device__ __forceinline__ void k1_flush(const K1Smem &M, int lo, int count, int lane, const K1Args &A)
+#ifndef NWB_FLUSH_NOINLINE
+#define NWB_FLUSH_NOINLINE 0
+#endif
+#if NWB_FLUSH_NOINLINE
+#define NWB_FLUSH_ATTR __noinline__
+#else
+#define NWB_FLUSH_ATTR __forceinline__
+#endif
+template <bool FLAT, bool SKEL>
+__device__ NWB_FLUSH_ATTR void k1_flush(const K1Smem &M, int lo, int count, int lane, const K1Args &A)
 {
 	if (lane < count) {
 		const int2 c = M.cand_sp[lo + lane];
 		const double2 rd = M.cand_rd[lo + lane];
 		const int s = c.x, p = c.y;
+		bool same = true;
+		if (FLAT) {
+			// NWB_COMPAT_FLAT_HASH: did the reference's hash bring these two together at all (fastskymatch.py:125-132)?  Decided
+			// first, from the primary's cell word alone -- one predicate lives through the arithmetic below
+			const unsigned long long wp = (unsigned long long) __ldg(&A.P.rec[p].ij);
+			const int di = flat_hash_cell_fast(rd.x, A.flat) - (int) (wp >> 32);
+			const int dj = flat_hash_cell_fast(rd.y, A.flat) - (int) (unsigned) wp;
+			same = (unsigned) (di + 1) <= 2u && (unsigned) (dj + 1) <= 2u;   // cells below 2^30: the differences cannot wrap
+		}
 		const Sector32 pr = ldg_sector(A.P.rec + p);   // one sector, one request
-		double slat2, clat2;
-		sincos_ref(deg2rad_ref(rd.y), &slat2, &clat2);
-		double lon2 = deg2rad_ref(rd.x);
-		double sep = sep_arcsec_ref(__longlong_as_double(pr.q[0]), __longlong_as_double(pr.q[1]), __longlong_as_double(pr.q[2]),
-			lon2, slat2, clat2);
-		bool keep = sep < A.radius;
-		if (keep && A.flat_err > 0.0) {   // the reference's hash never brought these two together (fastskymatch.py:125-132)
-			const long long ws = flat_hash_pack(rd.x, rd.y, A.flat_err), wp = (long long) pr.q[3];
-			keep = flat_hash_same_bucket(flat_hash_i(wp), flat_hash_j(wp), flat_hash_i(ws), flat_hash_j(ws));
+		double sep;
+		bool keep;
+		if (SKEL) {
+			// the memory-system skeleton (nwb_bench_skeleton): every access of the real kernel, none of its arithmetic;
+			// ~3 % of the candidates are dropped at random, the share the exact test rejects
+			sep = __longlong_as_double((long long) pr.q[0]) + rd.y;
+			keep = (((unsigned) s * 2654435761u) ^ (unsigned) p) % 32u != 0u;
+		} else {
+			double slat2, clat2;
+			sincos_ref(deg2rad_ref(rd.y), &slat2, &clat2);
+			double lon2 = deg2rad_ref(rd.x);
+			sep = sep_arcsec_ref(__longlong_as_double(pr.q[0]), __longlong_as_double(pr.q[1]), __longlong_as_double(pr.q[2]),
+				lon2, slat2, clat2);
+			keep = sep < A.radius && same;
 		}
 		if (keep) {
 			int slot = atomicAdd(&A.cnt[p], 1);
@@ -219,6 +272,7 @@ __device__ __forceinline__ void k1_flush(const K1Smem &M, int lo, int count, int
 }
 
 // queue the lanes with pass == true as candidates; run the exact stage when 32 are there
+template <bool FLAT, bool SKEL>
 __device__ __forceinline__ void k1_enqueue(K1Smem &M, bool pass, int s, int p, double r, double d, int lane, int &qn,
 	const K1Args &A)
 {
@@ -233,15 +287,16 @@ __device__ __forceinline__ void k1_enqueue(K1Smem &M, bool pass, int s, int p, d
 		__syncwarp();
 		if (qn >= 32) {
 			qn -= 32;
-			k1_flush(M, qn, 32, lane, A);
+			k1_flush<FLAT, SKEL>(M, qn, 32, lane, A);
 			__syncwarp();
 		}
 	}
 }
 
-// fp32 pre-test of `count` work items (entries beyond the first of a cell), one per lane
+// fp32 pre-test of `count` (<= 32) work items (entries beyond the third of a cell), one per lane; the survivors are
+// appended to the candidate queue, which must hold fewer than 32 on entry
 __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane, int &qn, const Grid &G,
-	const Entry *__restrict__ entries, const K1Args &A)
+	const Entry *__restrict__ entries)
 {
 	bool pass = false;
 	int s = 0, p = 0;
@@ -257,22 +312,30 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 		s = es.y;
 		p = ev.w;
 	}
-	k1_enqueue(M, pass, s, p, r, d, lane, qn, A);
+	const unsigned m = __ballot_sync(NWB_FULL, pass);
+	if (pass) {
+		const int q = qn + __popc(m & ((1u << lane) - 1));
+		M.cand_sp[q] = make_int2(s, p);
+		M.cand_rd[q] = make_double2(r, d);
+	}
+	qn += __popc(m);
 }
 
 // One thread per secondary source, coalesced loads of (ra, dec): 16 algorithmic bytes per source, the next batch
-// prefetched while the current one is processed.  The kernel is bound by L2 -> SM sector traffic (every lookup
-// is a random 32-byte sector), so the data is laid out to need few of them:
-//   1. per source ONE sector: the cell record = number of primaries registered in the cell, and the first of
-//      them inline; it is pre-tested (fp32, flat metric) on the spot.  Further primaries of the cell become work
+// prefetched while the current one is processed.  The kernel lives on L2 -> SM sector traffic (every lookup is a random
+// 32-byte sector), so the data is laid out to need few of them:
+//   1. per source ONE sector: the cell record = number of primaries registered in the cell, and the first three of
+//      them inline; they are pre-tested (fp32, flat metric) on the spot.  Further primaries of the cell become work
 //      items in a per-warp shared-memory list and are pre-tested 32 at a time (one 16-byte entry each).
 //   2. survivors (candidates) carry the source's (ra, dec) with them; whenever 32 are queued every lane
 //      evaluates one exact fp64 separation in the reference's arithmetic against ONE sector of primary data.
 //   3. a match takes the next slot of its primary (atomicAdd on the per-primary counter) and is written there
 //      directly -- no append buffer, no scatter pass.
+// The two dense stages (work items -> candidates, candidates -> matches) run at ONE place of the loop, after everything
+// of the batch has been queued: nothing of the batch is live across them, and the code of the exact stage exists once.
 // DENSE: the band table fits shared memory and there is no occupancy bitmap (the streaming configuration of the
-// benchmark) -- the same kernel with those two run-time branches resolved at compile time.
-template <bool DENSE>
+// benchmark).  FLAT: NWB_COMPAT_FLAT_HASH is in force.  SKEL: the memory-system skeleton (nwb_bench_skeleton).
+template <bool DENSE, bool FLAT, bool SKEL>
 __global__ void __launch_bounds__(K1_WARPS * 32, NWB_K1_MINBLOCKS)
 k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G,
 	const int *__restrict__ etotal, const CellRec *__restrict__ cells, const Entry *__restrict__ entries,
@@ -293,7 +356,7 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 	const int lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1;
 	K1Smem &M = smem[threadIdx.x >> 5];
-	int nit = 0, qn = 0;   // warp-uniform fill levels of the two lists
+	int nit = 0, qn = 0;   // warp-uniform fill levels of the two lists; both below 32 at the top of the loop
 	// 32-bit indices: the host guarantees n + (one wave of threads) < 2^31 (secondary indices are ints in the slots anyway)
 	const int stride = gridDim.x * blockDim.x;
 	const int nround = (n + 31) / 32 * 32;
@@ -302,6 +365,7 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 	double r_nxt = 0, d_nxt = 0;
 	if (i < n) { r_nxt = ra[i]; d_nxt = dec[i]; }
 	for (; i < nround; i += stride) {
+		const bool last = i + stride >= nround;   // this warp's final batch: the lists are drained completely
 		const double r = r_nxt, d = d_nxt;
 		{
 			const int j = i + stride;   // software prefetch of the next batch: hides the DRAM latency
@@ -341,8 +405,10 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 		}
 		// the inline entries: up to three fp32 pre-tests on the spot
 		const int ninl = min(ecnt, 3);
-		if (!__any_sync(NWB_FULL, ninl > 0)) continue;   // sparse primaries: most batches end here
-		{
+		const bool any = __any_sync(NWB_FULL, ninl > 0);
+		if (!any && !last) continue;   // sparse primaries: most batches end here
+		int maxc = 0;
+		if (any) {
 			// the three pre-tests first (independent: they overlap), then ONE update of the candidate queue
 			const bool p0 = ninl > 0 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e0);
 			const bool p1 = ninl > 1 && k1_pretest_packed(G, xr, yr, kx, (unsigned) e1);
@@ -350,50 +416,53 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 			const unsigned m0 = __ballot_sync(NWB_FULL, p0), m1 = __ballot_sync(NWB_FULL, p1), m2 = __ballot_sync(NWB_FULL, p2);
 			const int n0 = __popc(m0), n01 = n0 + __popc(m1), n012 = n01 + __popc(m2);
 			if (qn + n012 <= K1_QCAP) {
-				if (n012) {
-					if (p0) { const int q = qn + __popc(m0 & lt); M.cand_sp[q] = make_int2(i, (int) (e0 >> 32)); M.cand_rd[q] = make_double2(r, d); }
-					if (p1) { const int q = qn + n0 + __popc(m1 & lt); M.cand_sp[q] = make_int2(i, (int) (e1 >> 32)); M.cand_rd[q] = make_double2(r, d); }
-					if (p2) { const int q = qn + n01 + __popc(m2 & lt); M.cand_sp[q] = make_int2(i, (int) (e2 >> 32)); M.cand_rd[q] = make_double2(r, d); }
-					qn += n012;
-					__syncwarp();
-					while (qn >= 32) {
-						qn -= 32;
-						k1_flush(M, qn, 32, lane, A);
-						__syncwarp();
-					}
+				if (p0) { const int q = qn + __popc(m0 & lt); M.cand_sp[q] = make_int2(i, (int) (e0 >> 32)); M.cand_rd[q] = make_double2(r, d); }
+				if (p1) { const int q = qn + n0 + __popc(m1 & lt); M.cand_sp[q] = make_int2(i, (int) (e1 >> 32)); M.cand_rd[q] = make_double2(r, d); }
+				if (p2) { const int q = qn + n01 + __popc(m2 & lt); M.cand_sp[q] = make_int2(i, (int) (e2 >> 32)); M.cand_rd[q] = make_double2(r, d); }
+				qn += n012;
+			} else {   // more than the queue holds at once (rare): one entry rank at a time
+#pragma unroll 1
+				for (int k = 0; k < 3; k++) {
+					const bool pk = k == 0 ? p0 : (k == 1 ? p1 : p2);
+					const unsigned long long ek = k == 0 ? e0 : (k == 1 ? e1 : e2);
+					k1_enqueue<FLAT, SKEL>(M, pk, i, (int) (ek >> 32), r, d, lane, qn, A);
 				}
-			} else {   // more than the queue holds at once (rare): one entry at a time
-				k1_enqueue(M, p0, i, (int) (e0 >> 32), r, d, lane, qn, A);
-				k1_enqueue(M, p1, i, (int) (e1 >> 32), r, d, lane, qn, A);
-				k1_enqueue(M, p2, i, (int) (e2 >> 32), r, d, lane, qn, A);
 			}
+			maxc = __reduce_max_sync(NWB_FULL, ecnt);
 		}
-		// crowded cells (> 3 primaries): the entries beyond the third become work items, pre-tested 32 at a time
-		const int maxc = __reduce_max_sync(NWB_FULL, ecnt);
-		for (int k = 3; k < maxc; k++) {
-			const bool has = k < ecnt;
-			const unsigned m = __ballot_sync(NWB_FULL, has);
-			if (has) {
-				int q = nit + __popc(m & lt);
-				M.item_es[q] = make_int2(estart + k, i);
-				M.item_rd[q] = make_double2(r, d);
+		// crowded cells (> 3 primaries): the entries beyond the third become work items; then the two dense stages
+		int k = 3;
+		for (;;) {
+			while (k < maxc && nit < 32) {
+				const bool has = k < ecnt;
+				const unsigned m = __ballot_sync(NWB_FULL, has);
+				if (has) {
+					const int q = nit + __popc(m & lt);
+					M.item_es[q] = make_int2(estart + k, i);
+					M.item_rd[q] = make_double2(r, d);
+				}
+				nit += __popc(m);
+				k++;
 			}
-			nit += __popc(m);
-			if (nit >= 32) {
-				__syncwarp();
-				nit -= 32;
-				k1_items(M, nit, 32, lane, qn, G, entries, A);
-				__syncwarp();
+			const bool done = k >= maxc, fin = last && done;
+			__syncwarp();
+			for (;;) {
+				if (qn >= 32 || (fin && nit == 0 && qn > 0)) {   // candidates -> matches, 32 at a time (fewer only when draining)
+					const int take = min(qn, 32);
+					qn -= take;
+					k1_flush<FLAT, SKEL>(M, qn, take, lane, A);
+					__syncwarp();
+				} else if (nit >= 32 || (fin && nit > 0)) {      // work items -> candidates (fewer than 32 are queued here)
+					const int take = min(nit, 32);
+					nit -= take;
+					k1_items(M, nit, take, lane, qn, G, entries);
+					__syncwarp();
+				} else {
+					break;
+				}
 			}
+			if (done) break;
 		}
-	}
-	__syncwarp();
-	if (nit > 0) k1_items(M, 0, nit, lane, qn, G, entries, A);
-	__syncwarp();
-	while (qn > 0) {
-		int take = min(qn, 32);
-		qn -= take;
-		k1_flush(M, qn, take, lane, A);
 	}
 }
 
@@ -413,6 +482,74 @@ __global__ void k_collect_status(int ncat, const int *__restrict__ entries_total
 	if (t == 10) { v = entries_total[1]; mine = true; }    // registrations (primary, cell)
 	if (t >= 1 && t < ncat) { v = (long long) spill_count[t]; mine = true; }
 	if (t == 8) { v = total_rows ? *total_rows : 0; mine = true; }
+	if (t == 9) {   // [9] != 0: the primaries' bounding box is not the one the (re-used) grid geometry was built for
+		for (int k = 0; k < 6; k++) v |= (long long) (bounds[k] != expected.k[k]);
+		mine = true;
+	}
+	if (mine) { out[t] = v; host[t] = v; }
+}
+
+// Two catalogues, up to a few hundred thousand primaries: row offsets AND the status words in ONE single-block launch.
+// row_off[p] = sum over q < p of (cnt[q] + 1) -- a primary's matches plus its no-counterpart row -- row_off[np] = R;
+// then the words of k_collect_status.  Replaces cub's two scan kernels + k_collect_status (three dependent launches,
+// ~22 us of launch latency for 400 KB of data) where a device-wide scan is not worth its set-up.
+constexpr int RO_THREADS = 1024;
+
+__global__ void __launch_bounds__(RO_THREADS)
+k_rowoff_status(int np, const int *__restrict__ cnt, long long *__restrict__ row_off,
+	int ncat, const int *__restrict__ entries_total, const unsigned long long *__restrict__ spill_count,
+	const unsigned long long *__restrict__ bounds, BoundsKey expected, long long *__restrict__ out, long long *__restrict__ host)
+{
+	__shared__ long long wsum[32];
+	__shared__ long long carry_s;
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	if (t == 0) carry_s = 0;
+	__syncthreads();
+	for (int base = 0; base < np; base += RO_THREADS * 4) {
+		const int i = base + 4 * t;
+		int4 c = make_int4(0, 0, 0, 0);
+		if (i + 3 < np) c = __ldg(reinterpret_cast<const int4 *>(cnt + i));   // cnt is 16-byte aligned (a multiple of 4 ints into its block)
+		else {
+			if (i < np) c.x = cnt[i];
+			if (i + 1 < np) c.y = cnt[i + 1];
+			if (i + 2 < np) c.z = cnt[i + 2];
+		}
+		const int v0 = i < np ? c.x + 1 : 0, v1 = i + 1 < np ? c.y + 1 : 0, v2 = i + 2 < np ? c.z + 1 : 0, v3 = i + 3 < np ? c.w + 1 : 0;
+		const long long tot = (long long) v0 + v1 + v2 + v3;
+		long long incl = tot;
+		for (int o = 1; o < 32; o <<= 1) {
+			const long long y = __shfl_up_sync(NWB_FULL, incl, o);
+			if (lane >= o) incl += y;
+		}
+		if (lane == 31) wsum[w] = incl;
+		__syncthreads();
+		if (w == 0) {
+			long long x = wsum[lane];
+			for (int o = 1; o < 32; o <<= 1) {
+				const long long y = __shfl_up_sync(NWB_FULL, x, o);
+				if (lane >= o) x += y;
+			}
+			wsum[lane] = x;   // inclusive over warps
+		}
+		__syncthreads();
+		const long long carry = carry_s;
+		const long long excl = carry + (w > 0 ? wsum[w - 1] : 0) + incl - tot;
+		if (i < np) row_off[i] = excl;
+		if (i + 1 < np) row_off[i + 1] = excl + v0;
+		if (i + 2 < np) row_off[i + 2] = excl + v0 + v1;
+		if (i + 3 < np) row_off[i + 3] = excl + v0 + v1 + v2;
+		__syncthreads();
+		if (t == 0) carry_s = carry + wsum[31];
+		__syncthreads();
+	}
+	const long long total = carry_s;
+	if (t == 0) row_off[np] = total;
+	long long v = 0;
+	bool mine = false;
+	if (t == 0) { v = entries_total[0]; mine = true; }     // overflow entries of the cell lists
+	if (t == 10) { v = entries_total[1]; mine = true; }    // registrations (primary, cell)
+	if (t >= 1 && t < ncat) { v = (long long) spill_count[t]; mine = true; }
+	if (t == 8) { v = total; mine = true; }
 	if (t == 9) {   // [9] != 0: the primaries' bounding box is not the one the (re-used) grid geometry was built for
 		for (int k = 0; k < 6; k++) v |= (long long) (bounds[k] != expected.k[k]);
 		mine = true;
@@ -460,7 +597,7 @@ __global__ void k_spill_scatter(long long n, const SpillRec *__restrict__ recs, 
 __global__ void k_sort_lists(int np, PairStore S, const long long *__restrict__ seg_off, int *__restrict__ L_s,
 	double *__restrict__ L_sep, const double *__restrict__ ra, const double *__restrict__ dec,
 	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat, int small_n,
-	long long *__restrict__ L_ij, double flat_err)
+	long long *__restrict__ L_ij, FlatHash flat)
 {
 	int lane = threadIdx.x & 31;
 	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -480,7 +617,7 @@ __global__ void k_sort_lists(int np, PairStore S, const long long *__restrict__ 
 			L_lon[lo + rank] = deg2rad_ref(ra[me.s]);
 			L_slat[lo + rank] = sl;
 			L_clat[lo + rank] = cl;
-			if (flat_err > 0.0) L_ij[lo + rank] = flat_hash_pack(ra[me.s], dec[me.s], flat_err);
+			if (flat.err > 0.0) L_ij[lo + rank] = flat_hash_pack(ra[me.s], dec[me.s], flat);
 		}
 	}
 }
@@ -492,7 +629,7 @@ constexpr int SMALL_N = 4;
 __global__ void k_sort_lists_small(int np, PairStore S, const long long *__restrict__ seg_off, int *__restrict__ L_s,
 	double *__restrict__ L_sep, const double *__restrict__ ra, const double *__restrict__ dec,
 	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat,
-	long long *__restrict__ L_ij, double flat_err)
+	long long *__restrict__ L_ij, FlatHash flat)
 {
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= np) return;
@@ -520,7 +657,7 @@ __global__ void k_sort_lists_small(int np, PairStore S, const long long *__restr
 		L_lon[lo + e] = deg2rad_ref(ra[x[e].s]);
 		L_slat[lo + e] = sl;
 		L_clat[lo + e] = cl;
-		if (flat_err > 0.0) L_ij[lo + e] = flat_hash_pack(ra[x[e].s], dec[x[e].s], flat_err);
+		if (flat.err > 0.0) L_ij[lo + e] = flat_hash_pack(ra[x[e].s], dec[x[e].s], flat);
 	}
 }
 
@@ -591,7 +728,7 @@ __global__ void k_count_rows(RowParams R, long long *__restrict__ rows)
 			T *= nl[c] + 1;
 		}
 		if (T <= R.small_t) continue;   // k_count_rows_small's
-		const long long wp = R.flat_err > 0.0 ? flat_hash_pack(R.ra[0][R.first + p], R.dec[0][R.first + p], R.flat_err) : 0ll;
+		const long long wp = R.flat.err > 0.0 ? flat_hash_pack(R.ra[0][R.first + p], R.dec[0][R.first + p], R.flat) : 0ll;
 		double *mat = R.mat + R.mat_off[p];
 		long long boff = 0;
 #pragma unroll
@@ -631,7 +768,7 @@ __global__ void k_count_rows(RowParams R, long long *__restrict__ rows)
 					bo += (long long) nl[a] * nl[b];
 				}
 			}
-			if (R.flat_err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
+			if (R.flat.err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
 			count += ok;
 		}
 		count = warp_sum_ll(count);
@@ -657,7 +794,7 @@ __global__ void k_count_rows_small(RowParams R, long long *__restrict__ rows)
 	}
 	if (T > R.small_t) return;
 	if (T == 1) { rows[p] = 1; return; }
-	const long long wp = R.flat_err > 0.0 ? flat_hash_pack(R.ra[0][R.first + p], R.dec[0][R.first + p], R.flat_err) : 0ll;
+	const long long wp = R.flat.err > 0.0 ? flat_hash_pack(R.ra[0][R.first + p], R.dec[0][R.first + p], R.flat) : 0ll;
 	double *mat = R.mat + R.mat_off[p];
 	long long boff = 0;
 #pragma unroll
@@ -696,7 +833,7 @@ __global__ void k_count_rows_small(RowParams R, long long *__restrict__ rows)
 				bo += (long long) nl[a] * nl[b];
 			}
 		}
-		if (R.flat_err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
+		if (R.flat.err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
 		count += ok;
 	}
 	rows[p] = count;
@@ -801,7 +938,7 @@ k_rows(RowParams R)
 		const double *mat = NC > 2 ? R.mat + R.mat_off[p] : nullptr;
 		const long long gp = R.first + p;
 		const double sig0 = R.err[0][gp];
-		const long long wp = R.flat_err > 0.0 ? flat_hash_pack(R.ra[0][gp], R.dec[0][gp], R.flat_err) : 0ll;
+		const long long wp = R.flat.err > 0.0 ? flat_hash_pack(R.ra[0][gp], R.dec[0][gp], R.flat) : 0ll;
 		long long written = 0;
 		for (long long t0 = 0; t0 < ntup; t0 += 32) {
 			long long t = t0 + lane;
@@ -848,7 +985,7 @@ k_rows(RowParams R)
 						}
 					}
 				}
-				if (R.flat_err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
+				if (R.flat.err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
 			}
 			unsigned m = __ballot_sync(NWB_FULL, ok);
 			if (ok) {
@@ -928,7 +1065,7 @@ k_rows_small(RowParams R)
 	const long long rbase = R.row_off[p];
 	const double *mat = NC > 2 ? R.mat + R.mat_off[p] : nullptr;
 	const long long gp = R.first + p;
-	const long long wp = R.flat_err > 0.0 ? flat_hash_pack(R.ra[0][gp], R.dec[0][gp], R.flat_err) : 0ll;
+	const long long wp = R.flat.err > 0.0 ? flat_hash_pack(R.ra[0][gp], R.dec[0][gp], R.flat) : 0ll;
 	double v[SMALL_T];
 	int nrow = 0;
 	for (int t = 0; t < ntup; t++) {
@@ -973,7 +1110,7 @@ k_rows_small(RowParams R)
 				}
 			}
 		}
-		if (R.flat_err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
+		if (R.flat.err > 0.0) ok = ok && tuple_in_one_bucket<NC>(R, wp, dg, lo);
 		if (!ok) continue;
 		const long long row = rbase + nrow;
 		double smax = 0.0;

@@ -65,7 +65,7 @@ struct RowParams {
 	const double *err[MAXC];         // sigma columns (circular); elliptical: sigma_x | sigma_y | rho, each n[c] long
 	int ell;                         // elliptical mode (nway.py:346-354): every catalogue carries a triple
 	int sep_f32;                     // nway.py compatibility: separations / offsets pass through float32
-	double flat_err;                 // > 0: NWB_COMPAT_FLAT_HASH in force; the reference's bucket size in degrees (radius / 60. / 60)
+	FlatHash flat;                   // .err > 0: NWB_COMPAT_FLAT_HASH in force; the reference's bucket size in degrees (radius / 60. / 60)
 	int small_t;                     // primaries with at most this many candidate tuples are handled by k_rows_small (0 = off)
 	long long n[MAXC];               // catalogue sizes (stride of the error triple)
 	const double *ra[MAXC], *dec[MAXC];

@@ -4,8 +4,9 @@ Every output row belongs to exactly one primary source and every reduction of th
 match_flag, the CLI correction) stays inside one primary's rows, so the shards are independent: each rank
 matches its contiguous block of primaries against the full secondary catalogues.  The only exchange is the
 re-assembly of the table: an all-gather of the per-rank row counts (which fixes where each shard sits in the
-global table) and, if the caller wants the whole table on every rank, one padded all-gather per column --
-NCCL over NVLink for device tensors, gloo for the CPU tests.
+global table) and, if the caller wants the whole table on every rank, ONE variable-length all-gather of the shards:
+every (column, peer) message at its exact size, sent from the context's own column allocation into its final place
+in the gathered table, all in one NCCL group over NVLink (gloo for the CPU tests).
 """
 from collections import OrderedDict
 
@@ -34,28 +35,75 @@ def row_offsets(counts):
 	return [int(x) for x in numpy.concatenate(([0], numpy.cumsum(counts)[:-1]))]
 
 
-def allgather_columns(cols, counts, group=None):
-	"""cols: mapping name -> 1-D torch tensor (all of this rank's row count, 8-byte dtypes, same device).
-	Returns name -> tensor of sum(counts) rows, shards in rank order, identical on every rank.  NCCL needs equal
-	message sizes, so each column is padded to the longest shard and trimmed after the collective."""
+def _exchange(send, recv, group=None):
+	"""ONE grouped exchange: send = [(tensor, peer)], recv = [(tensor, peer)], every message at its exact size.  With NCCL
+	the whole list is a single ncclGroup (torch.distributed.batch_isend_irecv) -- no padding, no staging copies, no
+	concatenation afterwards: the receives land in their final place."""
+	import torch.distributed as dist
+	ops = [dist.P2POp(dist.irecv, t, p, group) for t, p in recv] + [dist.P2POp(dist.isend, t, p, group) for t, p in send]
+	if ops:
+		for w in dist.batch_isend_irecv(ops):
+			w.wait()
+
+
+def allgather_table(local, counts, group=None, gather='all', out=None):
+	"""The reassembly of the sharded output table (SURVEY.md 8e "Collective") as one variable-length all-gather.
+
+	local: (ncols, counts[rank]) tensor of 8-byte values whose rows are contiguous (e.g. Context.table_view(): the
+	context's own column allocation, sent from where the row kernels wrote it).  counts: rows of every rank's shard, in
+	rank order (exchange_counts).  Returns the (ncols, sum(counts)) table, shards in rank order, on every rank
+	(gather='all') or on rank 0 only (gather='rank0': a real gather, the other ranks only send and return None).
+	Per peer and column one message of exactly that shard's size, all of them in one NCCL group; the own shard is
+	placed with one strided device copy."""
 	import torch
 	import torch.distributed as dist
-	world = dist.get_world_size(group)
+	rank, world = dist.get_rank(group), dist.get_world_size(group)
+	assert len(counts) == world and local.shape[1] == counts[rank]
+	ncols = local.shape[0]
+	offs = row_offsets(counts)
+	want = gather == 'all' or rank == 0
+	if want:
+		if out is None:
+			out = torch.empty((ncols, sum(counts)), dtype=local.dtype, device=local.device)
+		if counts[rank]:
+			out[:, offs[rank]:offs[rank] + counts[rank]].copy_(local)
+	send, recv = [], []
+	for peer in range(world):
+		if peer == rank:
+			continue
+		if counts[rank] and (gather == 'all' or peer == 0):
+			send += [(local[k], peer) for k in range(ncols)]
+		if want and counts[peer]:
+			recv += [(out[k, offs[peer]:offs[peer] + counts[peer]], peer) for k in range(ncols)]
+	_exchange(send, recv, group)
+	return out if want else None
+
+
+def allgather_columns(cols, counts, group=None):
+	"""cols: mapping name -> 1-D tensor (this rank's rows; same device, any dtypes).  Returns name -> tensor of
+	sum(counts) rows, shards in rank order, identical on every rank: the same single grouped exchange as
+	allgather_table, for callers that hold separate columns."""
+	import torch
+	import torch.distributed as dist
+	rank, world = dist.get_rank(group), dist.get_world_size(group)
 	assert len(counts) == world
-	longest = max(max(counts), 1)
-	out = OrderedDict()
+	offs = row_offsets(counts)
+	total = sum(counts)
+	out = OrderedDict((name, torch.empty(total, dtype=col.dtype, device=col.device)) for name, col in cols.items())
+	send, recv = [], []
 	for name, col in cols.items():
-		n = col.shape[0]
-		send = col
-		if n != longest:
-			send = torch.zeros(longest, dtype=col.dtype, device=col.device)
-			send[:n] = col
-		recv = torch.empty(world * longest, dtype=col.dtype, device=col.device)
-		dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
-		if all(c == longest for c in counts):
-			out[name] = recv
-		else:
-			out[name] = torch.cat([recv[r * longest:r * longest + counts[r]] for r in range(world)])
+		assert col.shape[0] == counts[rank]
+		if counts[rank]:
+			out[name][offs[rank]:offs[rank] + counts[rank]].copy_(col)
+	for peer in range(world):
+		if peer == rank:
+			continue
+		for name, col in cols.items():
+			if counts[rank]:
+				send.append((col.contiguous(), peer))
+			if counts[peer]:
+				recv.append((out[name][offs[peer]:offs[peer] + counts[peer]], peer))
+	_exchange(send, recv, group)
 	return out
 
 
@@ -63,7 +111,7 @@ def nway_match_sharded(match_tables, match_radius, prior_completeness, gather='a
 	"""nway_match() across the ranks of a torch.distributed process group (one rank per GPU).
 
 	Every rank passes the same catalogues; rank r matches primaries shard_range(N0, r, world).  gather:
-	  'all'   every rank returns the complete table (padded NCCL all-gather of every column),
+	  'all'   every rank returns the complete table (one unpadded all-gather-v straight from the context's columns),
 	  'rank0' ranks send their shard to rank 0 (returns the table there, None elsewhere),
 	  'none'  every rank returns only its own shard plus (counts, offsets) to place it.
 	Automatic magnitude histograms (maghists=None) need the global first pass and are not supported here:
@@ -89,16 +137,15 @@ def nway_match_sharded(match_tables, match_radius, prior_completeness, gather='a
 	ctx = _lib.get_context(device)
 	names, seps, biases = _column_names(match_tables)
 	int_cols = set(names) | {'ncat', 'match_flag'}
-	cols = OrderedDict()
-	for name, sel in local['selectors'].items():
-		tns = torch.empty(nrows, dtype=torch.int64 if name in int_cols else torch.float64, device=dev)
-		if nrows:
-			ctx.fetch_device(sel, tns.data_ptr())
-		cols[name] = tns
-	ctx.sync()
+	colnames = list(local['selectors'].keys())
+	shard = ctx.table_view() if nrows else torch.empty((len(colnames), 0), dtype=torch.int64, device=dev)
+
+	def to_host(table):
+		host = table.cpu().numpy()
+		return OrderedDict((name, host[k] if name in int_cols else host[k].view(numpy.float64)) for k, name in enumerate(colnames))
+
 	if gather == 'none':
-		return OrderedDict((k, v.cpu().numpy()) for k, v in cols.items()), counts, offsets
-	full = allgather_columns(cols, counts, group)
-	if gather == 'rank0' and rank != 0:
-		return None
-	return OrderedDict((k, v.cpu().numpy()) for k, v in full.items())
+		return to_host(shard), counts, offsets
+	torch.cuda.current_stream(dev).synchronize()   # the context works on its own stream; it has been synchronised by nway_match
+	full = allgather_table(shard, counts, group, gather=gather)
+	return None if full is None else to_host(full)

@@ -40,7 +40,7 @@ struct K0 {
 };
 
 // max_cells_override > 0 replaces the library's own choice of the cell budget (coarser grids: crowded cells)
-inline void build_k0(K0 &K, int np, const double *pra, const double *pdec, double radius_arcsec, long long max_cells_override)
+inline void build_k0(K0 &K, int np, const double *pra, const double *pdec, double radius_arcsec, long long max_cells_override, bool one_pass = true)
 {
 	std::vector<double> &rn = K.rn, &dra = K.dra;
 	HostGrid &HG = K.HG;
@@ -61,15 +61,24 @@ inline void build_k0(K0 &K, int np, const double *pra, const double *pdec, doubl
 	G.kx = HG.kx.data();
 	G.bits = nullptr;
 	const double entry_tau_max = (rb_ins * M_PI / 180 > 0.02) ? -1.0 : 0.02;
-	// K0: count, headers, fill (k_prim_prep<COUNT> / k_cell_headers / k_prim_cells<true>, one thread after the other)
+	// K0, one thread after the other.  one_pass (the steady state: grid geometry known from the previous match):
+	// k_prim_prep<COUNT> counts AND places (prim_register<REG_COUNT_INLINE>: first three of a cell inline, the rest into a
+	// work list), k_cell_headers, k_fill_overflow.  Otherwise (first match of a context): k_prim_cells<false> counts,
+	// k_cell_headers, k_prim_cells<true> fills by counting back down.
 	std::vector<int> cellcnt(G.ncells + 1, 0);
 	cells.assign(G.ncells, CellRec());
 	std::vector<double> clat(np);
+	std::vector<OverflowItem> worklist((size_t) np * 64 + 64);
+	int worklist_n = 0;
 	for (int i = 0; i < np; i++) {
 		const double cl = cos(deg2rad_ref(pdec[i]));
 		const double tau = (rb_ins / 180 * NWB_PI) * tan(fmin(fabs(pdec[i]), 89.9999) / 180 * NWB_PI);
 		clat[i] = (tau > entry_tau_max || dra[i] >= 180.0) ? 0.0 : (double) __double2float_rd(cl);
-		prim_register<false>(G, i, pdec[i], rn[i], dra[i], cl, rb_ins, dra_eps, 0, 1, cellcnt.data(), nullptr, nullptr);
+		if (one_pass)
+			prim_register<REG_COUNT_INLINE>(G, i, pdec[i], rn[i], dra[i], cl, rb_ins, dra_eps, 0, 1, cellcnt.data(), cells.data(), nullptr,
+				worklist.data(), &worklist_n, (long long) worklist.size());
+		else
+			prim_register<REG_COUNT>(G, i, pdec[i], rn[i], dra[i], cl, rb_ins, dra_eps, 0, 1, cellcnt.data(), nullptr, nullptr);
 	}
 	long long total = 0, regs = 0;
 	for (long long c = 0; c < G.ncells; c++) {
@@ -77,14 +86,26 @@ inline void build_k0(K0 &K, int np, const double *pra, const double *pdec, doubl
 		const int start = (int) total - 3;
 		total += cnt > 3 ? cnt - 3 : 0;
 		regs += cnt;
-		cells[c].q[0] = (unsigned long long) (unsigned) cnt | ((unsigned long long) (unsigned) start << 32);
+		cells[c].q[0] = (unsigned long long) (unsigned) cnt | ((unsigned long long) (unsigned) start << 32);   // q[1..3] stay as placed
 	}
 	entries.assign(total + 1, Entry());
-	for (int i = 0; i < np; i++)
-		for (int bslot = 0; bslot < 4; bslot++)   // the four threads of a primary in k_prim_cells
-			prim_register<true>(G, i, pdec[i], rn[i], dra[i], clat[i], rb_ins, dra_eps, bslot, 4, cellcnt.data(), cells.data(), entries.data());
-	for (long long c = 0; c < G.ncells; c++)
-		if (cellcnt[c] != 0) { fprintf(stderr, "emu: count and fill disagree in cell %lld\n", c); K.ok = false; return; }
+	if (one_pass) {
+		if ((long long) worklist_n != total || worklist_n > (long long) worklist.size()) { fprintf(stderr, "emu: work list %d, overflow entries %lld\n", worklist_n, total); K.ok = false; return; }
+		for (int k = 0; k < worklist_n; k++) {   // k_fill_overflow
+			const OverflowItem it = worklist[k];
+			double x = rn[it.p] - G.ra_org_n;
+			if (x < 0.0) x += 360.0;
+			Entry en;
+			en.x = (float) x; en.y = (float) (pdec[it.p] - G.dec_lo); en.clat = (float) clat[it.p]; en.p = it.p;
+			entries[(int) (cells[it.cell].q[0] >> 32) + it.slot] = en;
+		}
+	} else {
+		for (int i = 0; i < np; i++)
+			for (int bslot = 0; bslot < 4; bslot++)   // the four threads of a primary in k_prim_cells
+				prim_register<REG_FILL>(G, i, pdec[i], rn[i], dra[i], clat[i], rb_ins, dra_eps, bslot, 4, cellcnt.data(), cells.data(), entries.data());
+		for (long long c = 0; c < G.ncells; c++)
+			if (cellcnt[c] != 0) { fprintf(stderr, "emu: count and fill disagree in cell %lld\n", c); K.ok = false; return; }
+	}
 	K.registrations = regs;
 }
 

@@ -15,7 +15,12 @@
 
 using namespace nwb;
 
+static int g_one_pass = 1;
+
 extern "C" {
+
+// which K0 path build_k0 emulates: 1 = count + place in one pass (the steady state), 0 = count, headers, fill (first match)
+void nwb_emu_set_one_pass(int v) { g_one_pass = v; }
 
 // Returns the number of pairs (pi[k], si[k]) with exact separation < radius that the grid + pre-tests would not hand to
 // the exact stage; stats[0] = pairs within the radius, [1] = of those found through an inline (packed) entry, [2] =
@@ -24,7 +29,7 @@ long long nwb_emu_check(int np, const double *pra, const double *pdec, int ns, c
 	double radius_arcsec, long long npairs, const int *pi, const int *si, long long max_cells_override, long long *stats, int *first_miss)
 {
 	emu::K0 K;
-	emu::build_k0(K, np, pra, pdec, radius_arcsec, max_cells_override);
+	emu::build_k0(K, np, pra, pdec, radius_arcsec, max_cells_override, g_one_pass != 0);
 	if (!K.ok) return -1;
 	const Grid &G = K.G;
 	const std::vector<CellRec> &cells = K.cells;

@@ -1,5 +1,5 @@
-"""CPU, world_size 2, gloo: the host-side logic of the sharded path (shard bounds, count exchange, padded
-all-gather of ragged shards, re-assembly order).  The per-shard tables come from the oracle, so this runs without
+"""CPU, world_size 2, gloo: the host-side logic of the sharded path (shard bounds, count exchange, the unpadded
+all-gather-v of ragged shards as one grouped exchange, gather to rank 0, re-assembly order).  The per-shard tables come from the oracle, so this runs without
 a GPU; the same code path runs over NCCL on device tensors in tests/test_gpu_parity.py / bench.py."""
 import os
 import socket
@@ -42,6 +42,22 @@ def worker(rank, world, port, ret):
 			a, b = v.numpy(), full[k]
 			assert a.shape == b.shape, k
 			assert np.array_equal(a, b, equal_nan=True), k
+		# the table form: (ncols, rows) of 8-byte words sent from a strided view (what Context.table_view() is), to
+		# every rank and to rank 0 only
+		names = list(cols)
+		stride = int(mine.sum()) + 37
+		store = torch.zeros((len(names), stride), dtype=torch.int64)
+		for k, name in enumerate(names):
+			store[k, :int(mine.sum())] = cols[name].view(torch.int64)
+		local = store[:, :int(mine.sum())]
+		for mode in ('all', 'rank0'):
+			tab = parallel.allgather_table(local, counts, gather=mode)
+			if mode == 'rank0' and rank != 0:
+				assert tab is None
+				continue
+			assert tab.shape == (len(names), len(full['A']))
+			for k, name in enumerate(names):
+				assert np.array_equal(tab[k].numpy().view(full[name].dtype), full[name], equal_nan=True), (mode, name)
 		ret[rank] = 'ok'
 	except Exception as e:   # surface the failure in the parent
 		ret[rank] = repr(e)
