@@ -194,7 +194,8 @@ int nwb_column_ptr(nwb_ctx *ctx, int column, void **dev_ptr);
  * values each.  A multi-GPU caller sends its shard of every column straight from here (nway_b200.parallel) -- no
  * per-column copy. */
 int nwb_table_layout(nwb_ctx *ctx, void **base, int64_t *stride_bytes, int *ncols, int64_t *nrows);
-/* device address of the int64 row count of the last match (lets a multi-GPU caller all-gather the per-rank row
+/* (valid until nwb_truncate, which compacts the table but not the per-primary offsets this word belongs to)
+ * device address of the int64 row count of the last match (lets a multi-GPU caller all-gather the per-rank row
  * counts with NCCL straight from device memory) */
 int nwb_nrows_device_ptr(nwb_ctx *ctx, void **dev_ptr);
 int nwb_sync(nwb_ctx *ctx);

@@ -198,6 +198,16 @@ def nway_match(match_tables, match_radius, prior_completeness,
 
 	ncats = len(match_tables)
 	elliptical = any(_is_triple(t['error']) for t in match_tables)
+	# limits of the device tables, checked before anything is uploaded
+	if not 2 <= ncats <= _lib.MAX_CATALOGUES:
+		raise ValueError('between 2 and %d catalogues can be matched, got %d' % (_lib.MAX_CATALOGUES, ncats))
+	nmagcols = sum(len(t.get('mags', [])) for t in match_tables)
+	if nmagcols > _lib.MAX_MAG_COLUMNS:
+		raise ValueError('at most %d magnitude columns (all catalogues together) are supported, got %d' % (_lib.MAX_MAG_COLUMNS, nmagcols))
+	for t in match_tables:
+		for maghist, magname in zip(t.get('maghists', []), t.get('magnames', [])):
+			if maghist is not None and len(maghist[0]) > _lib.MAX_HIST_BINS:
+				raise ValueError('magnitude histogram for "%s_%s" has %d bins; at most %d are supported' % (t['name'], magname, len(maghist[0]), _lib.MAX_HIST_BINS))
 	ctx = _lib.get_context(device)
 	mag_columns = []   # (catalogue, k, values in the caller's dtype with -99 -> NaN, maghist, name)
 	for c, t in enumerate(match_tables):

@@ -16,6 +16,7 @@ COL_IDX, COL_SEP, COL_BIAS = 0, 100, 200
 COL_SEPMAX, COL_NCAT, COL_LOGBF_UNCORR, COL_LOGBF, COL_DIST_POST, COL_P_SINGLE, COL_MATCH_FLAG, COL_P_ANY, COL_P_I = range(300, 309)
 ERR_CIRCULAR, ERR_ELLIPSE = 1, 3
 UNRELATED_API, UNRELATED_CLI = 0, 1
+MAX_CATALOGUES, MAX_MAG_COLUMNS, MAX_HIST_BINS = 8, 8, 64   # nwb::MAXC, MAXM, MAXB (nwb_device.cuh)
 COMPAT_SEP_F32 = 1
 COMPAT_FLAT_HASH = 2
 T_GRID, T_PAIRS, T_LISTS, T_ROWS, T_FINAL, T_TOTAL, T_KPAIRS, T_KROWS = range(8)

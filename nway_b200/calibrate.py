@@ -91,12 +91,17 @@ def fake_catalogue(ra, dec, radius_arcsec, seed=0, device=None, max_rounds=200, 
 	rng = numpy.random.RandomState(seed) if seed > 0 else numpy.random
 	log = logger.log if logger is not None else (lambda *a: None)
 	# neighbour lists: grow the search radius until (almost) every source has enough neighbours beyond `radius`
+	# (a small or sparse catalogue cannot give every source 10 neighbours: min(10, n - 1) is what can be asked for, and the
+	# search stops at the library's largest radius, just under 30 degrees -- nwb_set_params)
 	search = max(4 * radius_arcsec, 60.0)
+	search_max = 0.999 * 30 * 3600.0
+	want = max(1, min(10, n - 1))
 	for _ in range(24):
+		search = min(search, search_max)
 		i, j, s = pairs_within(ra, dec, ra, dec, search, device=device)
 		far = s > radius_arcsec   # excludes the source itself (s = 0) and anything too close to interpolate towards
 		counts = numpy.bincount(i[far], minlength=n)
-		if (counts >= 10).mean() > 0.98 and (counts >= 1).all() or search > 0.49 * 3600 * 180:
+		if (counts >= want).mean() > 0.98 and (counts >= 1).all() or search >= search_max:
 			break
 		search *= 2
 	assert (counts >= 1).all(), 'Method failed: No sources found nearby, could not interpolate a fake source.'

@@ -72,9 +72,10 @@ def build_parser():
 		with high accuracy are matched against some with low accuracy (high --radius).
 
 		Example: --prefilter-pair GOODS IRAC 0.1""")
-	parser.add_argument('--prefilter-mode', choices=['fixed', 'reference'], default='fixed',
-		help='fixed: --prefilter-pair as documented (drop associations whose two members are farther apart than the radius). '
-		'reference: what nway.py 4.7.1 actually does -- every association containing both catalogues is dropped, whatever the radius')
+	parser.add_argument('--prefilter-mode', choices=['fixed', 'reference'], default='reference',
+		help='reference (default: the same rows as nway.py 4.7.1): every association containing both catalogues is dropped, whatever '
+		'the radius -- what the reference\'s code does (its mask assignment has no effect, fastskymatch.py:203). '
+		'fixed: --prefilter-pair as documented (drop associations whose two members are farther apart than the radius)')
 	parser.add_argument('--device', type=int, default=None, help='CUDA device index (default: $NWB_DEVICE, $LOCAL_RANK or 0)')
 	return parser
 
@@ -203,6 +204,8 @@ def main(argv=None):
 		for tablea, tableb, err in args.prefilter_pair]
 	if len(pairwise_errs) > 0:
 		print('    pair-wise pre-filtering on')
+		if args.prefilter_mode == 'reference':
+			print('    NOTE: as in nway.py 4.7.1, --prefilter-pair removes EVERY association that contains both catalogues of a pair, whatever their separation; --prefilter-mode fixed applies the radius as documented')
 
 	mag_include_radius = args.mag_radius
 	mag_exclude_radius = args.mag_exclude_radius

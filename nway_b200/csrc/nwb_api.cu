@@ -872,8 +872,8 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			CU(cudaEventRecord(ctx->kev[2 * c + 1], st));
 		}
 		if (attempt == 0) CU(cudaEventRecord(ctx->ev[2], st));
-		if (!generic && np <= (1 << 18)) {
-			// row offsets + status words in one single-block launch
+		if (!generic && np <= 4 * RO_THREADS * 4) {
+			// a few thousand primaries (the launch-latency-bound regime): row offsets + status words in one single-block launch
 			LAUNCH(ctx, k_rowoff_status, 1, RO_THREADS, (int) np, (const int *) d_cnt[1], d_rowoff, nc, (const int *) d_etotal,
 				(const unsigned long long *) d_spillcount, (const unsigned long long *) d_red, ctx->geom_key, d_status, hs);
 		} else {

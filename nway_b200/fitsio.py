@@ -3,8 +3,12 @@
 The reference reads its catalogues with astropy (`pyfits.open(f)[1]`, nway.py:174-181) and writes the match
 table with `BinTableHDU.from_columns` + `HDUList.writeto` (nway.py:629-649, fastskymatch.py:345-363).  This
 module covers exactly what that needs: a primary HDU without data followed by ONE BINTABLE extension with
-scalar columns of type L, B, I, J, K, E, D and fixed-width strings nA -- fixed-width big-endian rows in
-2880-byte blocks of 80-character header cards.
+columns of type L, B, I, J, K, E, D (scalar or fixed-length vectors such as 2E) and fixed-width strings nA --
+fixed-width big-endian rows in 2880-byte blocks of 80-character header cards.  TSCALn / TZEROn are applied on read as
+astropy does: the unsigned-integer convention (TSCAL 1, TZERO 2^15 / 2^31 / 2^63; -128 for signed bytes) gives
+uint16 / uint32 / uint64 / int8 columns, which are written back with the same keywords; any other scaling gives a
+float64 column (format D).  Variable-length columns (P, Q descriptors) cannot be carried through without their heap:
+they are left out and listed in Table.skipped instead of making the catalogue unreadable.
 
 	table = read_table('COSMOS_XMM.fits')        # Table: .name, .header, .columns, .formats, .data
 	write_table('out.fits', columns, extname='NWAYMATCH', primary_header=[...], table_header=[...])
@@ -20,14 +24,31 @@ BLOCK = 2880
 _FORMATS = {'L': 'i1', 'B': 'u1', 'I': '>i2', 'J': '>i4', 'K': '>i8', 'E': '>f4', 'D': '>f8'}
 
 
+# the unsigned-integer convention: TFORM letter -> (numpy dtype of the values, TZERO)
+_UNSIGNED = {'I': ('u2', 2 ** 15), 'J': ('u4', 2 ** 31), 'K': ('u8', 2 ** 63), 'B': ('i1', -128)}
+
+
 class Column(object):
 	"""name + FITS format + array; the array is converted to the format's type on construction, as
-	astropy's Column does (so that a later in-place change of the source array does not leak in)"""
+	astropy's Column does (so that a later in-place change of the source array does not leak in).  An unsigned array
+	(uint16 / uint32 / uint64; int8 for B) in an I / J / K / B column keeps its values and is written with the TZERO of
+	the unsigned-integer convention (.zero)."""
 
 	def __init__(self, name, format, array):
 		self.name = name
 		self.format = format
-		self.array = numpy.array(array, dtype=native_dtype(format))
+		self.zero = None
+		rep, letter = split_format(format)
+		src = numpy.asarray(array)
+		if letter in _UNSIGNED and rep == 1 and src.dtype == numpy.dtype(_UNSIGNED[letter][0]):
+			self.array = numpy.array(src)
+			self.zero = _UNSIGNED[letter][1]
+		elif letter in _FORMATS and rep > 1:
+			self.array = numpy.array(src, dtype=numpy.dtype(_FORMATS[letter]).newbyteorder('='))
+			if self.array.ndim != 2 or self.array.shape[1] != rep:
+				raise ValueError('column "%s" (%s) needs an array of shape (rows, %d)' % (name, format, rep))
+		else:
+			self.array = numpy.array(src, dtype=native_dtype(format))
 
 	def __repr__(self):
 		return 'Column(%r, %r, %d rows)' % (self.name, self.format, len(self.array))
@@ -37,12 +58,13 @@ class Table(object):
 	"""one BINTABLE extension: name (EXTNAME), header (OrderedDict keyword -> value), column names / TFORMs,
 	data (numpy structured array, native byte order)"""
 
-	def __init__(self, name, header, columns, formats, data):
+	def __init__(self, name, header, columns, formats, data, skipped=()):
 		self.name = name
 		self.header = header
 		self.columns = columns
 		self.formats = formats
 		self.data = data
+		self.skipped = list(skipped)   # variable-length columns left out: (name, TFORM)
 
 	def __len__(self):
 		return len(self.data)
@@ -65,18 +87,20 @@ def native_dtype(fmt):
 		return numpy.dtype(bool)
 	if letter not in _FORMATS:
 		raise ValueError('unsupported FITS column format "%s"' % fmt)
-	if rep != 1:
-		raise ValueError('vector columns are not supported (format "%s")' % fmt)
-	return numpy.dtype(_FORMATS[letter]).newbyteorder('=')
+	base = numpy.dtype(_FORMATS[letter]).newbyteorder('=')
+	return base if rep == 1 else numpy.dtype((base, (rep,)))
 
 
 def _disk_dtype(fmt):
 	rep, letter = split_format(fmt)
 	if letter == 'A':
 		return numpy.dtype('S%d' % rep)
-	if letter not in _FORMATS or rep != 1:
+	if letter in ('P', 'Q'):   # variable-length array descriptor (length, heap offset): read over, not interpreted
+		return numpy.dtype('V%d' % (rep * (8 if letter == 'P' else 16)))
+	if letter not in _FORMATS:
 		raise ValueError('unsupported FITS column format "%s"' % fmt)
-	return numpy.dtype(_FORMATS[letter])
+	base = numpy.dtype(_FORMATS[letter])
+	return base if rep == 1 else numpy.dtype((base, (rep,)))
 
 
 def _parse_value(v):
@@ -163,14 +187,35 @@ def read_table(path, ext=1):
 				raise ValueError('%s: row width %d does not match the column formats (%d)' % (path, int(cards['NAXIS1']), disk.itemsize))
 			nrows = int(cards['NAXIS2'])
 			raw = numpy.frombuffer(buf, dtype=disk, count=nrows, offset=pos)
-			native = numpy.dtype([(n, native_dtype(f)) for n, f in zip(names, formats)])
-			data = numpy.empty(nrows, dtype=native)
-			for n, f in zip(names, formats):
-				if split_format(f)[1] == 'L':
-					data[n] = raw[n] == ord('T')
+			keep, out_formats, values, skipped = [], [], {}, []
+			for i, (n, f) in enumerate(zip(names, formats)):
+				rep, letter = split_format(f)
+				if letter in ('P', 'Q'):
+					skipped.append((n, f))
+					continue
+				scale, zero = cards.get('TSCAL%d' % (i + 1), 1), cards.get('TZERO%d' % (i + 1), 0)
+				if letter == 'L':
+					v = raw[n] == ord('T')
+				elif letter != 'A' and (scale != 1 or zero != 0):
+					if letter in _UNSIGNED and scale == 1 and zero == _UNSIGNED[letter][1]:
+						# unsigned-integer convention: exact integer arithmetic, no detour through floating point
+						udt = numpy.dtype(_UNSIGNED[letter][0])
+						v = (raw[n].astype(numpy.dtype(_FORMATS[letter]).newbyteorder('=')).view(udt) ^ udt.type(1 << (8 * udt.itemsize - 1))) if letter != 'B' \
+							else (raw[n].astype('u1') ^ numpy.uint8(128)).view('i1')
+					else:
+						v = raw[n].astype(numpy.float64) * scale + zero
+						f = ('%d' % rep if rep != 1 else '') + 'D'
 				else:
-					data[n] = raw[n]
-			return Table(str(cards.get('EXTNAME', '')), cards, names, formats, data)
+					v = raw[n].astype(native_dtype(f).base) if letter != 'A' else raw[n]
+				keep.append(n)
+				out_formats.append(f)
+				values[n] = v
+			native = numpy.dtype([(n, values[n].dtype, values[n].shape[1:]) for n in keep])
+			data = numpy.empty(nrows, dtype=native)
+			for n in keep:
+				data[n] = values[n]
+			names, formats = keep, out_formats
+			return Table(str(cards.get('EXTNAME', '')), cards, names, formats, data, skipped)
 		pos += (size + BLOCK - 1) // BLOCK * BLOCK
 		ihdu += 1
 	raise ValueError('%s: no extension %d' % (path, ext))
@@ -249,6 +294,9 @@ def write_table(path, columns, extname, primary_header=(), table_header=(), comm
 			raise ValueError('column "%s" has %d rows, expected %d' % (c.name, len(c.array), nrows))
 		if split_format(c.format)[1] == 'L':
 			rec[c.name] = numpy.where(c.array, ord('T'), ord('F'))
+		elif getattr(c, 'zero', None) is not None:   # unsigned-integer convention: stored value = value - TZERO (flip the top bit)
+			a = c.array
+			rec[c.name] = (a.view('u1') ^ numpy.uint8(128)) if a.dtype.itemsize == 1 else (a ^ a.dtype.type(1 << (8 * a.dtype.itemsize - 1))).view(a.dtype.str.replace('u', 'i'))
 		else:
 			rec[c.name] = c.array
 	now = datetime.datetime.now().isoformat()
@@ -264,6 +312,9 @@ def write_table(path, columns, extname, primary_header=(), table_header=(), comm
 	for i, c in enumerate(columns):
 		tab.append(_card('TTYPE%d' % (i + 1), c.name))
 		tab.append(_card('TFORM%d' % (i + 1), c.format))
+		if getattr(c, 'zero', None) is not None:
+			tab.append(_card('TSCAL%d' % (i + 1), 1))
+			tab.append(_card('TZERO%d' % (i + 1), c.zero))
 	tab.append(_card('EXTNAME', extname))
 	for k, v in table_header:
 		tab += _cards(k, v)

@@ -56,3 +56,33 @@ def test_oracle_cli_mode_against_reference_cli(name, tmp_path):
 	"""the oracle port with cli_compat=True == the real nway.py, bit for bit in the output formats"""
 	got = cliparity.oracle_cli_table(name)
 	cliparity.check_against_cli_digest(name, got, exact=True)
+
+
+def test_fits_unsigned_scaled_and_vector_columns(tmp_path):
+	"""TZERO / TSCAL as astropy applies them (unsigned-integer convention -> uint columns, written back with the same
+	keywords; other scalings -> float64), fixed-length vector columns carried through, variable-length columns left out"""
+	import struct
+	from nway_b200 import fitsio
+	n = 5
+	cols = [fitsio.Column('ID', 'K', np.array([0, 1, 2 ** 63, 2 ** 64 - 1, 7], dtype=np.uint64)),
+		fitsio.Column('U2', 'I', np.array([0, 1, 32768, 65535, 9], dtype=np.uint16)),
+		fitsio.Column('U4', 'J', np.array([0, 1, 2 ** 31, 2 ** 32 - 1, 9], dtype=np.uint32)),
+		fitsio.Column('S1', 'B', np.array([-128, -1, 0, 127, 5], dtype=np.int8)),
+		fitsio.Column('RA', 'D', np.arange(n) * 1.5), fitsio.Column('V', '2E', np.arange(2 * n).reshape(n, 2)),
+		fitsio.Column('I', 'J', np.arange(n) - 2)]
+	path = str(tmp_path / 't.fits')
+	fitsio.write_table(path, cols, 'T', table_header=[('SKYAREA', 2.0)])
+	t = fitsio.read_table(path)
+	assert t.formats == ['K', 'I', 'J', 'B', 'D', '2E', 'J'] and t.header['TZERO1'] == 2 ** 63 and t.header['TZERO2'] == 32768
+	for c in cols:
+		assert t.data[c.name].dtype == c.array.dtype and np.array_equal(t.data[c.name], c.array), c.name
+	# a generic scaling and a variable-length column, patched into the header / row layout by hand
+	raw = bytearray(open(path, 'rb').read())
+	hdr_end = raw.index(b'END' + b' ' * 77, 2880)
+	card = ('%-8s= %20s' % ('TSCAL7', '0.5')).ljust(80).encode() + ('%-8s= %20s' % ('TZERO7', '10.0')).ljust(80).encode()
+	assert raw[hdr_end + 80:hdr_end + 240] == b' ' * 160   # room for two more cards before the block ends
+	raw[hdr_end:hdr_end + 240] = card + b'END'.ljust(80)
+	open(path, 'wb').write(bytes(raw))
+	t2 = fitsio.read_table(path)
+	assert t2.formats[-1] == 'D' and np.array_equal(t2.data['I'], (np.arange(n) - 2) * 0.5 + 10.0)
+	assert fitsio._disk_dtype('1PE(7)').itemsize == 8 and fitsio._disk_dtype('QD').itemsize == 16

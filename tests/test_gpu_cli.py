@@ -32,7 +32,7 @@ def run_cli(name, tmp_path, extra=()):
 
 @pytest.mark.parametrize('name', ['cli2', 'cli3', 'cli3_magauto', 'cli3_bayes', 'cli3_minprob', 'cli3_prefilter'])
 def test_cli_against_reference_cli(name, tmp_path):
-	extra = ['--prefilter-mode', 'reference'] if name == 'cli3_prefilter' else []
+	extra = []   # --prefilter-mode reference is the default: the drop-in entry point returns the reference's rows
 	t, cards = run_cli(name, tmp_path, extra)
 	got = {n: t.data[n] for n in t.columns}
 	report = cliparity.check_against_cli_digest(name, got, check_layout=True, formats=dict(zip(t.columns, t.formats)), header=cards)
@@ -44,7 +44,7 @@ def test_cli_against_reference_cli(name, tmp_path):
 def test_cli_prefilter_fixed_against_oracle(tmp_path):
 	"""--prefilter-pair as documented (the reference's own implementation is broken): against the oracle"""
 	from oracle import nway_oracle as O
-	t, cards = run_cli('cli3_prefilter', tmp_path)
+	t, cards = run_cli('cli3_prefilter', tmp_path, ['--prefilter-mode', 'fixed'])
 	tabs = cases.cosmos_subset(3)
 	tabs[1]['error'] = 0.1 * np.ones(len(tabs[1]['ra']))
 	tabs[2]['error'] = 0.5 * np.ones(len(tabs[2]['ra']))
