@@ -121,6 +121,18 @@ def bind_near_gpu(local):
 		return None
 
 
+def kernel_source_hash():
+	"""sha256 over the CUDA sources of the library: ties profiles/traffic.json to the code it was captured from"""
+	import hashlib
+	h = hashlib.sha256()
+	d = os.path.join(ROOT, 'nway_b200', 'csrc')
+	for name in sorted(os.listdir(d)):
+		if name.endswith(('.cu', '.cuh', '.h')):
+			h.update(name.encode())
+			h.update(open(os.path.join(d, name), 'rb').read())
+	return h.hexdigest()
+
+
 def hbm_peak():
 	path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
 	if os.path.exists(path):
@@ -482,13 +494,28 @@ def run_b200(args):
 		'pipeline': {'B_alg_bytes': b_alg, 'GBs': b_alg / (ms_step_max * 1e-3) / 1e9, 'frac': b_alg / (ms_step_max * 1e-3) / 1e9 / peak}}
 	ncu_traffic = os.path.join(ROOT, 'profiles', 'traffic.json')
 	if os.path.exists(ncu_traffic) and args.scale == 1.0:
-		try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel, from the committed ncu capture
-			prof = json.load(open(ncu_traffic))['kernels'][kname.split('<')[0]]
-			roofline['traffic'] = prof['dram_bytes_per_launch']
-			if 'limiter' in prof:   # what the ncu capture says actually bounds the kernel (it is not HBM): informational
-				roofline['limiter'] = prof['limiter']
+		try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel, from the committed ncu capture --
+			# only if that capture was taken from the kernel sources this library was built from
+			cap = json.load(open(ncu_traffic))
+			prof = cap['kernels'][kname.split('<')[0]]
+			if cap.get('kernel_source_sha256') == kernel_source_hash():
+				roofline['traffic'] = prof['dram_bytes_per_launch']
+				if 'limiter' in prof:   # what the ncu capture says actually bounds the kernel (it is not HBM): informational
+					roofline['limiter'] = prof['limiter']
+			else:
+				roofline['traffic_note'] = 'profiles/traffic.json was captured from other kernel sources (%s...): not reported' % str(cap.get('kernel_source_sha256'))[:12]
 		except Exception:
 			pass
+	if world == 1 and args.scale == 1.0:
+		try:
+			# the memory-system skeleton of k_pairs on the same grid and catalogue: every global-memory access of the kernel,
+			# none of its arithmetic (nwb_bench_skeleton) -- what the access pattern alone costs
+			ctx.set_compat(_lib.COMPAT_FLAT_HASH)
+			ctx.match(fuse_final=True)
+			sk = ctx.bench_skeleton(1, 5)
+			roofline['k_pairs_memory_skeleton'] = {'ms': sk, 'GBs': bytes_pairs / (sk * 1e-3) / 1e9, 'k_pairs_over_skeleton': k_pairs_ms / sk}
+		except Exception as e:
+			roofline['k_pairs_memory_skeleton'] = {'error': str(e)[:200]}
 
 	cpu = None
 	if world == 1 and not args.no_cpu:

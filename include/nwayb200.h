@@ -124,6 +124,30 @@ int nwb_set_maghist(nwb_ctx *ctx, int c, int k, int nbins, const double *edges, 
  * output stay global.  Default: all. */
 int nwb_set_primary_range(nwb_ctx *ctx, int64_t first, int64_t count);
 
+/* ---- multi-GPU, strong scaling: the streaming of the secondaries split between the ranks --------------------------
+ * The shards of nwb_set_primary_range are independent but every one of them streams every secondary, so their time
+ * does not shrink with the number of GPUs once the stream dominates (BASELINE.json configs[3], configs[4]: 1e5 .. 1e6
+ * primaries against 1e7 .. 3e8 secondaries).  Shard mode divides the STREAM instead: every rank holds all catalogues in
+ * HBM (the row stages gather errors, magnitudes and coordinates by global index) and builds the grid over ALL primaries,
+ * but streams only its slice [n r / W, n (r + 1) / W) of every secondary catalogue; a match is written straight into the
+ * pair store of the rank that OWNS the primary (contiguous blocks of ceil(n0 / W) primaries) -- one system-scope
+ * atomicAdd and one 16-byte store into that rank's exchange buffer over NVLink peer memory (cudaIpc) from inside the
+ * streaming kernel, no staging, no collective on the data path.  Each rank then produces the rows of its own primaries;
+ * the table is reassembled as in the other mode (nway_b200.parallel.allgather_table).
+ *   nwb_shard_setup    (after the catalogues and nwb_set_params) allocates this rank's exchange buffer and returns its
+ *                      64-byte cudaIpcMemHandle; spill_capacity = matches beyond a primary's slots the buffer can hold
+ *   nwb_shard_connect  takes all ranks' handles (world x 64 bytes, rank order; the caller all-gathers them) and opens them
+ *   nwb_shard_match    one match in three phases with a barrier BETWEEN THE RANKS after phase 0 and after phase 1 (the
+ *                      caller's: any stream-ordered collective on the context's stream): 0 = zero the own counters,
+ *                      1 = grid + streaming (matches arrive from all ranks), 2 = rows of the own primaries.  Returns 1
+ *                      from phase 2 when a buffer turned out too small: every rank has to repeat the match from phase 0
+ *                      (the caller all-reduces the return codes).  world = 1 degenerates to an ordinary match.
+ *   nwb_shard_close    leaves shard mode. */
+int nwb_shard_setup(nwb_ctx *ctx, int rank, int world, int64_t spill_capacity, void *ipc_handle_out, int64_t *exchange_bytes);
+int nwb_shard_connect(nwb_ctx *ctx, const void *ipc_handles);
+int nwb_shard_match(nwb_ctx *ctx, int phase, int fuse_final, int64_t *nrows);
+int nwb_shard_close(nwb_ctx *ctx);
+
 /* ---- the path ------------------------------------------------------------------------------------------ */
 
 /* H1+H2+H3: bin, enumerate, separations, radius filter, log Bayes factor, prior, dist_post
@@ -217,7 +241,17 @@ int nwb_stats(nwb_ctx *ctx, int64_t *out4);
 int nwb_dist(nwb_ctx *ctx, int64_t n, const double *ra1, const double *dec1, const double *ra2,
 	const double *dec2, double *out_deg);                        /* fastskymatch.py:26-47 */
 int nwb_log_bf(nwb_ctx *ctx, int64_t n, int ncat, const double *sep /* ncat*ncat blocks of n, only i<j read */,
-	const double *err /* ncat blocks of n */, double *out);     /* bayesdistance.py:64-86 */
+	const double *err /* ncat blocks of n */, double *out);     /* Score a caller-supplied candidate list with the catalogues, parameters and tables now set on the context: idx = nrows x
+ * ncat row indices (row-major, host; -1 = the catalogue takes no part), as fastskymatch.crossproduct returns them
+ * (fastskymatch.py:92-218).  Per row, UNFILTERED (the reference filters Separation_max < match_radius afterwards,
+ * __init__.py:180): sep = the separations of every catalogue pair in arcsec, pair after pair in the order of the
+ * Separation columns, NaN where a member is absent (may be NULL); sepmax (__init__.py:166); ncat (:177); log_bf = the log10
+ * Bayes factor of the present catalogues (__init__.py:220-259, bayesdistance.py:64-86); dist_post = posterior(prior, log_bf)
+ * (bayesdistance.py:26-32).  Lets a caller tell an arithmetic mismatch from an enumeration mismatch. */
+int nwb_score_rows(nwb_ctx *ctx, int64_t nrows, const int64_t *idx, double *sep, double *sepmax, int64_t *ncat,
+	double *log_bf, double *dist_post);
+
+/* bayesdistance.py:64-86 */
 int nwb_posterior(nwb_ctx *ctx, int64_t n, const double *prior, const double *log_bf, double *out); /* :26-32 */
 int nwb_log_bf_elliptical(nwb_ctx *ctx, int64_t n, int ncat, const double *sep_ra, const double *sep_dec /* like sep */,
 	const double *err /* ncat blocks of (sigma_x | sigma_y | rho), each n */, double *out);   /* bayesdistance.py:207-240 */

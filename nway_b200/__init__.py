@@ -155,7 +155,7 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	store_mag_hists=True,
 	logger=default_logger,
 	unrelated_mode='api', device=None, primary_range=None, as_frame=True, keep_on_device=False, allow_empty=False,
-	cli_compat=False, pairwise_errs=(), flat_hash_compat=True):
+	cli_compat=False, pairwise_errs=(), flat_hash_compat=True, matcher=None):
 	"""Same contract as nwaylib.nway_match (nwaylib/__init__.py:31-83); see there for the arguments.
 
 	match_tables: list of dicts with name, ra, dec (deg), error (arcsec), area (deg^2), mags, magnames, maghists
@@ -182,6 +182,8 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	                  (SURVEY.md Q3); those associations are left out here too, so that prob_has_match / prob_this_match /
 	                  match_flag of a group are the reference's.  False: the complete enumeration on the whole sphere
 	                  (a superset; identical near the equator and wherever the reference uses its HEALPix hash).
+	  matcher         callable(ctx, fuse_final) -> rows that runs the match in place of ctx.match (nway_b200.parallel: the
+	                  multi-GPU mode in which the ranks share the streaming of the secondaries)
 	  cli_compat      the arithmetic quirks of the command-line program nway.py on top of unrelated_mode='cli':
 	                  separations (elliptical: offsets) pass through float32 before they are scored
 	                  and automatic histograms take the weights of the selected rows (nway.py:471)
@@ -247,7 +249,7 @@ def nway_match(match_tables, match_radius, prior_completeness,
 			install_hist(c, k, numpy.array(list(bins_lo) + [bins_hi[-1]]), hist_sel, hist_all)
 
 	logger.log('Computing distance-based probabilities ...')
-	nrows = ctx.match(fuse_final=not auto)
+	nrows = ctx.match(fuse_final=not auto) if matcher is None else matcher(ctx, not auto)
 	logger.log('matching: %6d matches after filtering by search radius' % nrows)
 	if not nrows > 0:
 		if allow_empty:

@@ -43,6 +43,10 @@ EXPORTS = {
 	'nwb_set_tables': (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_double, c_double_p, c_double_p, c_double_p]),
 	'nwb_set_maghist': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
 	'nwb_set_primary_range': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]),
+	'nwb_shard_setup': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, c_int64_p]),
+	'nwb_shard_connect': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+	'nwb_shard_match': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_int64_p]),
+	'nwb_shard_close': (ctypes.c_int, [ctypes.c_void_p]),
 	'nwb_match': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_int64_p]),
 	'nwb_match_async': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
 	'nwb_match_wait': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
@@ -60,6 +64,7 @@ EXPORTS = {
 	'nwb_stats': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
 	'nwb_dist': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
 	'nwb_log_bf': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
+	'nwb_score_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_int64_p, c_double_p, c_double_p, c_int64_p, c_double_p, c_double_p]),
 	'nwb_posterior': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p]),
 	'nwb_log_bf_elliptical': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
 	'nwb_row_offsets': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p]),
@@ -234,6 +239,43 @@ class Context(object):
 			return 0
 		self.check(rc)
 		return n.value
+
+	def shard_setup(self, rank, world, spill_capacity=65536):
+		"""enter shard mode (nwb_shard_setup); returns this rank's 64-byte IPC handle and the size of its exchange buffer"""
+		h = ctypes.create_string_buffer(64)
+		nbytes = ctypes.c_int64(0)
+		self.check(self.lib.nwb_shard_setup(self.h, int(rank), int(world), int(spill_capacity), h, ctypes.byref(nbytes)))
+		return h.raw, nbytes.value
+
+	def shard_connect(self, handles):
+		"""handles: the ranks' IPC handles in rank order (bytes, 64 each)"""
+		blob = ctypes.create_string_buffer(b''.join(handles), 64 * len(handles))
+		self.check(self.lib.nwb_shard_connect(self.h, blob))
+
+	def shard_match(self, phase, fuse_final=True):
+		"""one phase of a shard-mode match; phase 2 returns (rows, retry)"""
+		n = ctypes.c_int64(0)
+		rc = self.lib.nwb_shard_match(self.h, int(phase), 1 if fuse_final else 0, ctypes.byref(n))
+		if rc == 1:
+			return 0, True
+		if rc == NWB_ERR_EMPTY:
+			return 0, False
+		self.check(rc)
+		return n.value, False
+
+	def shard_close(self):
+		self.check(self.lib.nwb_shard_close(self.h))
+
+	def score_rows(self, idx):
+		"""nwb_score_rows: idx (R, ncat) int64 -> dict(sep (npairs, R), sepmax, ncat, log_bf, dist_post)"""
+		idx = numpy.ascontiguousarray(idx, dtype=numpy.int64)
+		R, nc = idx.shape
+		npairs = nc * (nc - 1) // 2
+		sep = numpy.empty((npairs, R))
+		sepmax, lbf, post = numpy.empty(R), numpy.empty(R), numpy.empty(R)
+		ncat = numpy.empty(R, dtype=numpy.int64)
+		self.check(self.lib.nwb_score_rows(self.h, R, idx.ctypes.data_as(c_int64_p), dptr(sep), dptr(sepmax), ncat.ctypes.data_as(c_int64_p), dptr(lbf), dptr(post)))
+		return dict(sep=sep, sepmax=sepmax, ncat=ncat, log_bf=lbf, dist_post=post)
 
 	def match_async(self, fuse_final=True):
 		"""enqueue a match on the context's stream without waiting for it (nwb_match_async); collect it with match_wait()"""

@@ -64,6 +64,18 @@ struct nwb_ctx {
 	double pc[MAXC];
 	int unrelated_mode = NWB_UNRELATED_API;
 	int compat = 0;
+	// shard mode (nwb_shard_*): streaming split by secondary rows, matches scattered into the owners' exchange buffers
+	struct Shard {
+		bool on = false, connected = false;
+		int rank = 0, world = 1;
+		int64_t block = 0;              // primaries per rank (the last rank may own fewer)
+		DevBuf xch, d_peers;            // this rank's exchange buffer; device array of every rank's buffer base
+		void *peer[16] = {nullptr};     // host copy; [rank] = xch.p, the others opened through cudaIpc
+		size_t off_cnt[MAXC] = {0}, off_slot[MAXC] = {0}, off_spill[MAXC] = {0}, off_spillcnt[MAXC] = {0};
+		size_t zero_bytes = 0, bytes = 0;   // counters + match counts come first: zeroed before every match
+		int C[MAXC] = {0};
+		unsigned long long spill_cap = 0;
+	} shard;
 	// what nwb_bench_skeleton needs of the last match: K1 arguments per secondary catalogue and the grid's buffers
 	K1Args last_k1[MAXC];
 	bool last_k1_dense = false;
@@ -85,7 +97,7 @@ struct nwb_ctx {
 	size_t entries_cap = 0;
 	unsigned long long spill_cap = 0;
 	long long *h_status = nullptr;   // pinned
-	int k1_occ[8] = {0, 0, 0, 0, 0, 0, 0, 0}, num_sms = 0;   // resident blocks per SM of every k_pairs instantiation
+	int k1_occ[16] = {0}, num_sms = 0;   // resident blocks per SM of every k_pairs instantiation
 	// grid geometry of the previous match, re-used when the primaries' bounding box and the radius are unchanged
 	bool geom_valid = false;
 	double geom_rb = 0;
@@ -94,7 +106,7 @@ struct nwb_ctx {
 	Grid geom_G;
 	int64_t cols_cap_rows = 0;
 	int cols_cap_ncols = 0;
-	bool timing_dirty = false, tables_dirty = true;
+	bool timing_dirty = false, tables_dirty = true, shard_events_valid = false;
 	int timing_ncat = 0;
 
 	// result
@@ -350,38 +362,54 @@ int launch_count(nwb_ctx *ctx, const RowParams &rp, long long *rows, int grid, b
 
 // k_pairs<DENSE, FLAT, SKEL>: band table in shared memory and no occupancy bitmap / the reference's flat-sky bucket
 // predicate on every match (NWB_COMPAT_FLAT_HASH) / the memory-system skeleton (nwb_bench_skeleton)
-int launch_pairs(nwb_ctx *ctx, bool dense, bool flat, bool skel, int n, const double *ra, const double *dec, const Grid &G,
+int launch_pairs(nwb_ctx *ctx, bool dense, bool flat, bool skel, bool scat, int n, const double *ra, const double *dec, const Grid &G,
 	const int *etotal, const CellRec *cells, const Entry *entries, long long entries_cap, const K1Args &ka)
 {
 	// persistent: exactly one wave of resident blocks of THIS instantiation (they differ in registers), each striding over
 	// the catalogue -- a grid sized for another variant's occupancy would leave SMs with an uneven number of blocks
-	const int which = (dense ? 1 : 0) | (flat ? 2 : 0) | (skel ? 4 : 0);
+	const int which = (dense ? 1 : 0) | (flat ? 2 : 0) | (skel ? 4 : 0) | (scat ? 8 : 0);
 	if (ctx->num_sms <= 0) {
 		int nsm = 0;
 		CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
 		ctx->num_sms = std::max(nsm, 1);
 	}
+	// the instantiations that exist: (dense, flat) x { plain, scatter } + (dense) x skeleton
+#define NWB_KP_DISPATCH(DO) \
+	if (skel) { if (dense) DO(true, false, true, false); else DO(false, false, true, false); } \
+	else if (scat) { if (flat) { if (dense) DO(true, true, false, true); else DO(false, true, false, true); } \
+		else { if (dense) DO(true, false, false, true); else DO(false, false, false, true); } } \
+	else if (flat) { if (dense) DO(true, true, false, false); else DO(false, true, false, false); } \
+	else { if (dense) DO(true, false, false, false); else DO(false, false, false, false); }
 	if (ctx->k1_occ[which] <= 0) {
 		int nb = 0;
-#define NWB_OCC(D, F, S) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (k_pairs<D, F, S>), K1_WARPS * 32, 0))
-		if (skel) { if (dense) NWB_OCC(true, false, true); else NWB_OCC(false, false, true); }
-		else if (flat) { if (dense) NWB_OCC(true, true, false); else NWB_OCC(false, true, false); }
-		else { if (dense) NWB_OCC(true, false, false); else NWB_OCC(false, false, false); }
+#define NWB_OCC(D, F, S, X) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (k_pairs<D, F, S, X>), K1_WARPS * 32, 0))
+		NWB_KP_DISPATCH(NWB_OCC)
 #undef NWB_OCC
 		ctx->k1_occ[which] = std::max(nb, 1);
 	}
-	const int grid = (int) std::min<int64_t>(((int64_t) n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), (int64_t) ctx->num_sms * ctx->k1_occ[which]);
-	if ((int64_t) n + (int64_t) grid * K1_WARPS * 32 + 64 > 0x7fffffffll)
+	const int grid = (int) std::max<int64_t>(1, std::min<int64_t>(((int64_t) n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), (int64_t) ctx->num_sms * ctx->k1_occ[which]));
+	if ((int64_t) n + (int64_t) ka.s_base + (int64_t) grid * K1_WARPS * 32 + 64 > 0x7fffffffll)
 		return fail(ctx, NWB_ERR_ARG, "catalogue too large: secondary indices are 32-bit");
-#define NWB_KP(D, F, S) LAUNCH(ctx, (k_pairs<D, F, S>), grid, K1_WARPS * 32, n, ra, dec, G, etotal, cells, entries, entries_cap, ka)
-	if (skel) { if (dense) NWB_KP(true, false, true); else NWB_KP(false, false, true); }
-	else if (flat) { if (dense) NWB_KP(true, true, false); else NWB_KP(false, true, false); }
-	else { if (dense) NWB_KP(true, false, false); else NWB_KP(false, false, false); }
+#define NWB_KP(D, F, S, X) LAUNCH(ctx, (k_pairs<D, F, S, X>), grid, K1_WARPS * 32, n, ra, dec, G, etotal, cells, entries, entries_cap, ka)
+	NWB_KP_DISPATCH(NWB_KP)
 #undef NWB_KP
+#undef NWB_KP_DISPATCH
 	return NWB_OK;
 }
 
 }  // namespace
+
+// shard mode: close the peers' exchange buffers, free the own one
+static void shard_release(nwb_ctx *ctx)
+{
+	nwb_ctx::Shard &S = ctx->shard;
+	for (int r = 0; r < S.world && r < 16; r++)
+		if (r != S.rank && S.peer[r]) cudaIpcCloseMemHandle(S.peer[r]);
+	for (auto &p : S.peer) p = nullptr;
+	release(S.xch);
+	release(S.d_peers);
+	S.on = S.connected = false;
+}
 
 // =========================================================================================================
 extern "C" {
@@ -429,6 +457,7 @@ void nwb_destroy(nwb_ctx *ctx)
 		release(ctx->d_Ls[c]); release(ctx->d_Lsep[c]); release(ctx->d_Ltrig[c]); release(ctx->cat[c].own);
 		release(ctx->d_spilloff[c]); release(ctx->d_spillseg[c]);
 	}
+	shard_release(ctx);
 	if (ctx->h_status) cudaFreeHost(ctx->h_status);
 	for (auto &ev : ctx->ev) cudaEventDestroy(ev);
 	for (auto &ev : ctx->kev) cudaEventDestroy(ev);
@@ -644,6 +673,21 @@ static int fill_row_params(nwb_ctx *ctx, const PairStore *stores, int64_t first,
 	return NWB_OK;
 }
 
+// slots per primary for the matches of catalogue c: expected number + 6 sigma (a uniform field almost never spills),
+// capped so that the pair store of np primaries stays below ~6 GB
+static int slots_per_primary(const nwb_ctx *ctx, int c, int64_t np)
+{
+	const int nc = ctx->ncat;
+	const double r_deg = ctx->radius / 3600.0;
+	const double mu = (double) ctx->cat[c].n * (M_PI * r_deg * r_deg) / ctx->cat[c].area;
+	const double want = std::ceil(mu + 6 * std::sqrt(mu) + 2);
+	const double cap_mem = std::floor(6e9 / 16.0 / (double) std::max<int64_t>(np, 1) / (nc - 1));
+	int C = (int) std::max(2.0, std::min(std::min(want, cap_mem), 1e6));
+	C = (C + 1) / 2 * 2;
+	if (ctx->cat[c].n == 0) C = 2;
+	return C;
+}
+
 // NWB_COMPAT_FLAT_HASH: would the reference's crossproduct() take its flat-sky branch for these catalogues and this
 // radius (fastskymatch.py:94-98: err < 1 deg, every ra in (10 err, 360 - 10 err), every |dec| < 45)?  The bounds of a
 // catalogue are reduced on the device once per nwb_set_catalogue.  *flat_err = the bucket size in degrees, or 0.
@@ -687,8 +731,14 @@ static int flat_hash_decision(nwb_ctx *ctx, double *flat_err)
 	return NWB_OK;
 }
 
-static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_cached, bool defer)
+// phase: 0 = the whole match.  Shard mode (nwb_shard_match) runs it in two halves with a barrier between the ranks in
+// between: 1 = grid over ALL primaries + this rank's slice of every secondary catalogue streamed, matches scattered to
+// the owners of the primaries; 2 = lists / rows / normalisation of the primaries this rank owns.
+static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_cached, bool defer, int phase = 0)
 {
+	const bool shard = ctx->shard.on;
+	if ((phase != 0) != shard) return fail(ctx, NWB_ERR_STATE, shard ? "shard mode: use nwb_shard_match" : "nwb_shard_setup first");
+	if (shard && !ctx->shard.connected) return fail(ctx, NWB_ERR_STATE, "nwb_shard_connect first");
 	const int nc = ctx->ncat;
 	if (nc < 2) return fail(ctx, NWB_ERR_ARG, "no catalogues");
 	for (int c = 0; c < nc; c++) {
@@ -706,10 +756,17 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	ctx->matched = ctx->finalized = false;
 	ctx->pending = false;
 	ctx->launches = 0;
+	// two views of the primary catalogue: the rows this context produces (first, np) and the primaries its grid indexes
+	// (gfirst, gnp) -- the same unless the streaming is sharded, where every rank's grid holds ALL primaries
 	int64_t first = ctx->first, np = ctx->count < 0 ? ctx->cat[0].n - ctx->first : ctx->count;
+	if (shard) {
+		first = std::min<int64_t>(ctx->shard.rank * ctx->shard.block, ctx->cat[0].n);
+		np = std::min<int64_t>(ctx->shard.block, ctx->cat[0].n - first);
+	}
 	if (first + np > ctx->cat[0].n || np < 0) return fail(ctx, NWB_ERR_ARG, "primary range exceeds the catalogue");
+	const int64_t gfirst = shard ? 0 : first, gnp = shard ? ctx->cat[0].n : np;
 	ctx->np = np;
-	if (np == 0) { if (nrows) *nrows = 0; return fail(ctx, NWB_ERR_EMPTY, "No matches."); }
+	if (gnp == 0 || (np == 0 && phase != 1)) { if (nrows) *nrows = 0; ctx->nrows = 0; return fail(ctx, NWB_ERR_EMPTY, "No matches."); }
 	if (!ctx->tables_set && ctx->tables_dirty) default_tables(ctx);
 	{ int r = upload_tables(ctx); if (r) return r; }
 	const bool cli = ctx->unrelated_mode == NWB_UNRELATED_CLI && nc >= 3;
@@ -722,25 +779,26 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocMapped));
 	long long *hs = ctx->h_status;
 
-	CU(cudaEventRecord(ctx->ev[0], st));
+	if (phase != 2) CU(cudaEventRecord(ctx->ev[0], st));
 	// ---- K0: primaries -> bounding box (the one unavoidable early sync: the grid geometry is chosen on the host)
 	const double r_deg = ctx->radius / 3600.0;
 	const double rb = r_deg * (1 + 1e-9) + 1e-12;
 	const double rb_ins = rb + 1e-9, dra_eps = 1e-9;
 	const double entry_tau_max = (rb_ins * M_PI / 180 > 0.02) ? -1.0 : 0.02;   // the pole rule of pretest_constants (Grid::tau_max)
-	ENSURE(ctx->d_prim, (size_t) np * 8 * sizeof(double));
+	ENSURE(ctx->d_prim, (size_t) gnp * 8 * sizeof(double));
 	PrimArrays P;
 	{
 		double *b = (double *) ctx->d_prim.p;
-		P.rec = (PrimRec *) b; P.clat = b + 4 * np; P.ra_n = b + 5 * np; P.dec = b + 6 * np; P.dra = b + 7 * np;
+		P.rec = (PrimRec *) b; P.clat = b + 4 * gnp; P.ra_n = b + 5 * gnp; P.dec = b + 6 * gnp; P.dra = b + 7 * gnp;
 	}
-	int pblocks = grid_for(np, 256);
+	const int gblocks = grid_for(gnp, 256);   // one thread per primary of the grid
+	int pblocks = grid_for(std::max<int64_t>(np, 1), 256);   // ... per primary whose rows this context writes
 	ENSURE(ctx->d_red, 8 * sizeof(double));
 	unsigned long long *d_red = (unsigned long long *) ctx->d_red.p;
-	const bool use_cached = allow_cached && ctx->geom_valid && ctx->geom_rb == rb && ctx->geom_np == np && ctx->geom_first == first;
-	if (!use_cached) {
+	const bool use_cached = allow_cached && ctx->geom_valid && ctx->geom_rb == rb && ctx->geom_np == gnp && ctx->geom_first == gfirst;
+	if (!use_cached && phase != 2) {
 		CU(cudaMemsetAsync(d_red, 0, 6 * sizeof(unsigned long long), st));
-		LAUNCH(ctx, (k_prim_prep<false>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
+		LAUNCH(ctx, (k_prim_prep<false>), gblocks, 256, (int) gnp, (long long) gfirst, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
 			Grid(), rb_ins, dra_eps, (int *) nullptr, entry_tau_max, flat, (CellRec *) nullptr, (OverflowItem *) nullptr, (int *) nullptr, (long long) 0);
 		// the grid geometry is chosen on the host from the bounding box: one sync.  It is kept for the next match
 		// on this context, which only has to verify (on the device) that the box is still the same.
@@ -758,7 +816,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		HostGrid HG;
 		// cells: ~16 per primary is plenty (each primary occupies 1-9 of them), and the 32-byte records of at most 2 M
 		// cells (64 MB) stay in the 126 MB L2 next to the streamed catalogue
-		long long max_cells = std::min<long long>(2ll << 20, std::max<long long>(1ll << 16, 16 * (long long) np));
+		long long max_cells = std::min<long long>(2ll << 20, std::max<long long>(1ll << 16, 16 * (long long) gnp));
 		build_grid(red, rb_ins, rb_ins * NWB_CELL_FACTOR, max_cells, HG);
 		pretest_constants(HG, rb_ins);
 		size_t nb = (size_t) HG.g.nbands;
@@ -769,7 +827,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		HG.g.bands = (const BandRec *) ctx->d_bands.p;
 		HG.g.kx = (const float *) ((const char *) ctx->d_bands.p + nb * sizeof(BandRec));
 		ctx->geom_G = HG.g;
-		ctx->geom_rb = rb; ctx->geom_np = np; ctx->geom_first = first;
+		ctx->geom_rb = rb; ctx->geom_np = gnp; ctx->geom_first = gfirst;
 		ctx->geom_valid = true;
 	}
 	{
@@ -780,7 +838,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		ENSURE(ctx->d_cells, rec_bytes + bit_bytes);
 		const double s_deg = 1.0 / g.inv_h;
 		const double reach = 1.0 + 2.0 * rb_ins / s_deg;   // cells a primary's box spans along one axis, on average
-		const bool sparse = (double) np * reach * reach < 0.5 * (double) g.ncells;
+		const bool sparse = (double) gnp * reach * reach < 0.5 * (double) g.ncells;
 		g.bits = sparse ? (const unsigned *) ((const char *) ctx->d_cells.p + rec_bytes) : nullptr;
 	}
 	const Grid G = ctx->geom_G;
@@ -794,25 +852,24 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	for (int c = 1; c < nc; c++) d_cnt[c] = d_cellcnt + (ncell1 + 3) / 4 * 4 + cnt_stride * (c - 1);
 	unsigned long long *d_spillcount = (unsigned long long *) (d_cellcnt + (ncell1 + 3) / 4 * 4 + cnt_stride * (nc - 1));
 	int *d_etotal = (int *) (d_spillcount + 12);   // [0] overflow entries of the cell lists, [1] registrations
+	char *xch = (char *) ctx->shard.xch.p;
+	if (shard) {   // match counters and spill counters of the own primaries live in the exchange buffer, where the peers write
+		for (int c = 1; c < nc; c++) d_cnt[c] = (int *) (xch + ctx->shard.off_cnt[c]);
+		d_spillcount = (unsigned long long *) (xch + ctx->shard.off_spillcnt[0]);
+	}
 
-	// slots per primary and catalogue: expected matches + 6 sigma (a uniform field almost never spills)
+	// slots per primary and catalogue (slots_per_primary); shard mode: the exchange buffer's, fixed by nwb_shard_setup
 	int Cs[MAXC] = {0};
 	size_t base_off[MAXC + 1] = {0};
-	const double disc_deg2 = M_PI * r_deg * r_deg;
 	for (int c = 1; c < nc; c++) {
-		double mu = (double) ctx->cat[c].n * disc_deg2 / ctx->cat[c].area;
-		double want = std::ceil(mu + 6 * std::sqrt(mu) + 2);
-		double cap_mem = std::floor(6e9 / 16.0 / (double) np / (nc - 1));
-		int C = (int) std::max(2.0, std::min(std::min(want, cap_mem), 1e6));
-		C = (C + 1) / 2 * 2;
-		if (ctx->cat[c].n == 0) C = 2;
-		Cs[c] = C;
-		base_off[c + 1] = base_off[c] + (size_t) np * C;
+		Cs[c] = shard ? ctx->shard.C[c] : slots_per_primary(ctx, c, np);
+		base_off[c + 1] = base_off[c] + (shard ? 0 : (size_t) np * Cs[c]);
 	}
 	ENSURE(ctx->d_pairs, std::max<size_t>(1, base_off[nc]) * sizeof(Slot16));
 	Slot16 *d_base = (Slot16 *) ctx->d_pairs.p;
 	if (ctx->spill_cap < 65536) ctx->spill_cap = 65536;
-	if (ctx->entries_cap < (size_t) np * 12 + 4096) ctx->entries_cap = (size_t) np * 12 + 4096;
+	if (shard) ctx->spill_cap = ctx->shard.spill_cap;
+	if (ctx->entries_cap < (size_t) gnp * 12 + 4096) ctx->entries_cap = (size_t) gnp * 12 + 4096;
 	ENSURE(ctx->d_rows, (size_t) (np + 1) * sizeof(long long));
 	ENSURE(ctx->d_rowoff, (size_t) (np + 1) * sizeof(long long));
 	long long *d_rows = (long long *) ctx->d_rows.p, *d_rowoff = (long long *) ctx->d_rowoff.p;
@@ -826,52 +883,73 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	bool done = false, speculated = false;
 	for (int attempt = 0; !done && attempt < 4; attempt++) {
 		ENSURE(ctx->d_entries, ctx->entries_cap * sizeof(Entry));
-		ENSURE(ctx->d_spill, (size_t) ctx->spill_cap * (nc - 1) * sizeof(SpillRec));
+		if (!shard) ENSURE(ctx->d_spill, (size_t) ctx->spill_cap * (nc - 1) * sizeof(SpillRec));
 		Entry *d_entries = (Entry *) ctx->d_entries.p;
 		SpillRec *d_spill = (SpillRec *) ctx->d_spill.p;
 		CellRec *d_cells = (CellRec *) ctx->d_cells.p;
-		if (attempt == 0 && use_cached) {
+		if (phase == 2) {
+			// shard mode, second half: the grid and the streaming were phase 1
+		} else if (attempt == 0 && use_cached) {
 			// known geometry: the primaries are counted into their cells by the preparation kernel itself
 			LAUNCH(ctx, k_zero, (int) std::min<size_t>((zero_ints / 4 + 255) / 256, 148 * 8), 256, (int4 *) d_cellcnt, (long long) (zero_ints / 4), d_red, 6);
 			// ... and placed: the first three of a cell inline, the rest noted in the work list (one pass over the primaries)
 			ENSURE(ctx->d_worklist, ctx->entries_cap * sizeof(OverflowItem));
-			LAUNCH(ctx, (k_prim_prep<true>), pblocks, 256, (int) np, (long long) first, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
+			LAUNCH(ctx, (k_prim_prep<true>), gblocks, 256, (int) gnp, (long long) gfirst, ctx->cat[0].ra, ctx->cat[0].dec, rb, P, d_red,
 				G, rb_ins, dra_eps, d_cellcnt, entry_tau_max, flat, d_cells, (OverflowItem *) ctx->d_worklist.p, d_etotal + 2, (long long) ctx->entries_cap);
 			LAUNCH(ctx, k_cell_headers, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cellcnt, d_cells, (unsigned *) G.bits, d_etotal);
 			LAUNCH(ctx, k_fill_overflow, 148 * 2, 256, G, P, (const OverflowItem *) ctx->d_worklist.p, (const int *) (d_etotal + 2), (long long) ctx->entries_cap,
 				(const CellRec *) d_cells, d_entries, (const int *) d_etotal, (long long) ctx->entries_cap);
 		} else {
 			CU(cudaMemsetAsync(d_cellcnt, 0, zero_ints * sizeof(int), st));
-			LAUNCH(ctx, (k_prim_cells<false>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, (CellRec *) nullptr,
+			LAUNCH(ctx, (k_prim_cells<false>), grid_for(gnp * 4, 256), 256, (int) gnp, G, P, rb_ins, dra_eps, d_cellcnt, (CellRec *) nullptr,
 				(Entry *) nullptr, (const int *) nullptr, (long long) 0);
 			LAUNCH(ctx, k_cell_headers, grid_for(G.ncells, 256), 256, (long long) G.ncells, (const int *) d_cellcnt, d_cells, (unsigned *) G.bits, d_etotal);
-			LAUNCH(ctx, (k_prim_cells<true>), grid_for(np * 4, 256), 256, (int) np, G, P, rb_ins, dra_eps, d_cellcnt, d_cells,
+			LAUNCH(ctx, (k_prim_cells<true>), grid_for(gnp * 4, 256), 256, (int) gnp, G, P, rb_ins, dra_eps, d_cellcnt, d_cells,
 				d_entries, (const int *) d_etotal, (long long) ctx->entries_cap);
 		}
-		if (attempt == 0) CU(cudaEventRecord(ctx->ev[1], st));
+		if (attempt == 0 && phase != 2) CU(cudaEventRecord(ctx->ev[1], st));
 
 		// ---- K1: stream the secondaries ----------------------------------------------------------------
 		for (int c = 1; c < nc; c++) {
 			int64_t n = ctx->cat[c].n;
-			stores[c].base = d_base + base_off[c];
+			stores[c].base = shard ? (const Slot16 *) (xch + ctx->shard.off_slot[c]) : d_base + base_off[c];
 			stores[c].C = Cs[c];
 			stores[c].cnt = d_cnt[c];
 			stores[c].spill_off = nullptr;
 			stores[c].spill = nullptr;
-			if (n == 0) continue;
+			if (n == 0 || phase == 2) continue;
 			CU(cudaEventRecord(ctx->kev[2 * c], st));
 			K1Args ka;
+			memset(&ka, 0, sizeof(ka));
 			ka.P = P; ka.radius = ctx->prefilter_on ? std::min(ctx->radius, ctx->prefilter[pair_index(0, c, nc)]) : ctx->radius; ka.base = d_base + base_off[c]; ka.C = Cs[c]; ka.cnt = d_cnt[c];
 			ka.spill = d_spill + (size_t) ctx->spill_cap * (c - 1); ka.spill_cap = (unsigned long long) ctx->spill_cap;
 			ka.spill_count = d_spillcount + c;
 			ka.flat = flat;
+			// shard mode: this rank streams its slice [s_first, s_first + s_count) of the catalogue; the matches go to the owners
+			int64_t s_first = 0, s_count = n;
+			if (shard) {
+				s_first = n * ctx->shard.rank / ctx->shard.world;
+				s_count = n * (ctx->shard.rank + 1) / ctx->shard.world - s_first;
+				ka.s_base = (int) s_first;
+				ka.x_block = (int) ctx->shard.block;
+				ka.x_peers = (char *const *) ctx->shard.d_peers.p;
+				ka.x_cnt_off = (long long) ctx->shard.off_cnt[c]; ka.x_slot_off = (long long) ctx->shard.off_slot[c];
+				ka.x_spill_off = (long long) ctx->shard.off_spill[c]; ka.x_spillcnt_off = (long long) ctx->shard.off_spillcnt[c];
+			}
 			ctx->last_k1[c] = ka; ctx->last_k1_dense = G.nbands <= K1_SBANDS && !G.bits;
 			ctx->last_etotal = d_etotal;
-			{ int r = launch_pairs(ctx, ctx->last_k1_dense, flat_err > 0.0, false, (int) n, ctx->cat[c].ra, ctx->cat[c].dec, G, (const int *) d_etotal,
-				(const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka); if (r) return r; }
+			if (s_count > 0) {
+				int r = launch_pairs(ctx, ctx->last_k1_dense, flat_err > 0.0, false, shard, (int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
+					(const int *) d_etotal, (const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
+				if (r) return r;
+			}
 			CU(cudaEventRecord(ctx->kev[2 * c + 1], st));
 		}
-		if (attempt == 0) CU(cudaEventRecord(ctx->ev[2], st));
+		if (attempt == 0 && phase != 2) CU(cudaEventRecord(ctx->ev[2], st));
+		if (phase == 1) {   // the caller puts a barrier between the ranks here: every rank's matches must have arrived
+			ctx->shard_events_valid = true;
+			return NWB_OK;
+		}
 		if (!generic && np <= 4 * RO_THREADS * 4) {
 			// a few thousand primaries (the launch-latency-bound regime): row offsets + status words in one single-block launch
 			LAUNCH(ctx, k_rowoff_status, 1, RO_THREADS, (int) np, (const int *) d_cnt[1], d_rowoff, nc, (const int *) d_etotal,
@@ -885,7 +963,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		// speculative K2: if the table of the previous match was big enough, launch the row kernel right away; it
 		// checks the status words on the device.  One host sync per match instead of three.
 		speculated = false;
-		if (!generic && ctx->cols_cap_rows > 0 && ctx->cols_cap_ncols == 2 + 1 + 9 + ctx->res_nmag) {
+		if (!generic && !shard && ctx->cols_cap_rows > 0 && ctx->cols_cap_ncols == 2 + 1 + 9 + ctx->res_nmag) {
 			int r = fill_row_params(ctx, stores, first, np, ell);
 			if (r) return r;
 			ctx->rp.row_off = d_rowoff;
@@ -918,12 +996,20 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			return 1;       // caller retries without the cache
 		}
 		done = true;
+		if (shard && hs[9] != 0) { ctx->geom_valid = false; return 1; }
 		if ((size_t) hs[0] > ctx->entries_cap) { ctx->entries_cap = (size_t) hs[0] + 1024; done = false; }
 		for (int c = 1; c < nc; c++)
 			if ((unsigned long long) hs[c] > ctx->spill_cap) { ctx->spill_cap = (unsigned long long) hs[c] + 1024; done = false; }
 		R = hs[8];
 		ctx->stats[3] = hs[10];
 		if (speculated && !(done && hs[1] == 0 && R <= ctx->cols_cap_rows)) speculated = false;   // the kernel declined
+		if (shard && !done) {
+			// the streaming is shared between the ranks: a bigger buffer takes effect when ALL of them redo the match
+			for (int c = 1; c < nc; c++)
+				if ((unsigned long long) hs[c] > ctx->shard.spill_cap)
+					return fail(ctx, NWB_ERR_NOMEM, "shard mode: more overflowing matches than the exchange buffer holds (a very clustered catalogue): nwb_shard_setup with a larger spill capacity");
+			return 1;
+		}
 	}
 	if (!done) return fail(ctx, NWB_ERR_NOMEM, "grid / spill buffers kept overflowing");
 	ctx->stats[2] = G.ncells;
@@ -939,7 +1025,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		CU(cudaMemsetAsync(sizes, 0, (size_t) (np + 1) * sizeof(int), st));
 		LAUNCH(ctx, k_spill_sizes, pblocks, 256, (int) np, (const int *) d_cnt[c], Cs[c], sizes);
 		{ int r = scan_int_to_ll(ctx, sizes, (long long *) ctx->d_spilloff[c].p, np + 1); if (r) return r; }
-		LAUNCH(ctx, k_spill_scatter, grid_for(nsp, 256), 256, nsp, (const SpillRec *) ctx->d_spill.p + (size_t) ctx->spill_cap * (c - 1),
+		LAUNCH(ctx, k_spill_scatter, grid_for(nsp, 256), 256, nsp, shard ? (const SpillRec *) (xch + ctx->shard.off_spill[c]) : (const SpillRec *) ctx->d_spill.p + (size_t) ctx->spill_cap * (c - 1),
 			Cs[c], (const long long *) ctx->d_spilloff[c].p, (Slot16 *) ctx->d_spillseg[c].p);
 		stores[c].spill_off = (const long long *) ctx->d_spilloff[c].p;
 		stores[c].spill = (const Slot16 *) ctx->d_spillseg[c].p;
@@ -1074,6 +1160,112 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	if (nrows) *nrows = R;
 	if (R == 0) return fail(ctx, NWB_ERR_EMPTY, "No matches.");
 	return NWB_OK;
+}
+
+// ---- shard mode: streaming split by secondary rows, matches scattered to the owners over peer memory --------------
+int nwb_shard_setup(nwb_ctx *ctx, int rank, int world, int64_t spill_capacity, void *ipc_handle_out, int64_t *exchange_bytes)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(ctx, NWB_ERR_ARG, "bad rank / world (at most 16 ranks)");
+	if (world > 1 && !ipc_handle_out) return fail(ctx, NWB_ERR_ARG, "ipc_handle_out is NULL");
+	const int nc = ctx->ncat;
+	if (nc < 2 || !ctx->params_set) return fail(ctx, NWB_ERR_STATE, "set the catalogues and nwb_set_params first");
+	for (int c = 0; c < nc; c++)
+		if (!ctx->cat[c].set) return fail(ctx, NWB_ERR_STATE, "catalogue " + std::to_string(c) + " not set");
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	shard_release(ctx);
+	nwb_ctx::Shard &S = ctx->shard;
+	S.rank = rank; S.world = world;
+	const int64_t n0 = ctx->cat[0].n;
+	S.block = std::max<int64_t>(1, (n0 + world - 1) / world);
+	S.spill_cap = (unsigned long long) std::max<int64_t>(spill_capacity, 4096);
+	// layout, identical on every rank: spill counters | match counters per catalogue | slots per catalogue | spill records
+	size_t off = 0;
+	auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+	const size_t sc = take(MAXC * sizeof(unsigned long long));
+	for (int c = 0; c < MAXC; c++) S.off_spillcnt[c] = sc + (size_t) c * sizeof(unsigned long long);
+	for (int c = 1; c < nc; c++) S.off_cnt[c] = take((size_t) (S.block + 4) * sizeof(int));
+	S.zero_bytes = off;
+	for (int c = 1; c < nc; c++) {
+		S.C[c] = slots_per_primary(ctx, c, S.block);
+		S.off_slot[c] = take((size_t) S.block * S.C[c] * sizeof(Slot16));
+	}
+	for (int c = 1; c < nc; c++) S.off_spill[c] = take((size_t) S.spill_cap * sizeof(SpillRec));
+	S.bytes = off;
+	// a plain cudaMalloc of its own: IPC handles cover whole allocations
+	{ int r = ensure(ctx, S.xch, S.bytes); if (r) return r; }
+	CU(cudaMemsetAsync(S.xch.p, 0, S.zero_bytes, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (ipc_handle_out) {
+		cudaIpcMemHandle_t h;
+		memset(&h, 0, sizeof(h));
+		if (world > 1) CU(cudaIpcGetMemHandle(&h, S.xch.p));
+		memcpy(ipc_handle_out, &h, sizeof(h));
+	}
+	if (exchange_bytes) *exchange_bytes = (int64_t) S.bytes;
+	S.on = true;
+	S.connected = false;
+	ctx->geom_valid = false;
+	ctx->matched = ctx->finalized = false;
+	return NWB_OK;
+}
+
+int nwb_shard_connect(nwb_ctx *ctx, const void *ipc_handles)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	nwb_ctx::Shard &S = ctx->shard;
+	if (!S.on) return fail(ctx, NWB_ERR_STATE, "nwb_shard_setup first");
+	if (S.world > 1 && !ipc_handles) return fail(ctx, NWB_ERR_ARG, "ipc_handles is NULL");
+	CU(cudaSetDevice(ctx->device));
+	for (int r = 0; r < S.world; r++) {
+		if (r == S.rank) { S.peer[r] = S.xch.p; continue; }
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const char *) ipc_handles + (size_t) r * sizeof(h), sizeof(h));
+		void *p = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			return fail(ctx, NWB_ERR_CUDA, "cudaIpcOpenMemHandle for rank " + std::to_string(r) + ": " + cudaGetErrorString(e) +
+				" (shard mode needs peer access between the GPUs of one node)");
+		}
+		S.peer[r] = p;
+	}
+	{ int r = ensure(ctx, S.d_peers, 16 * sizeof(void *)); if (r) return r; }
+	CU(cudaMemcpyAsync(S.d_peers.p, S.peer, 16 * sizeof(void *), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	S.connected = true;
+	return NWB_OK;
+}
+
+int nwb_shard_close(nwb_ctx *ctx)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	shard_release(ctx);
+	ctx->geom_valid = false;
+	return NWB_OK;
+}
+
+int nwb_shard_match(nwb_ctx *ctx, int phase, int fuse_final, int64_t *nrows)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	nwb_ctx::Shard &S = ctx->shard;
+	if (!S.on || !S.connected) return fail(ctx, NWB_ERR_STATE, "nwb_shard_setup / nwb_shard_connect first");
+	CU(cudaSetDevice(ctx->device));
+	if (phase == 0) {
+		// the own primaries' counters back to zero -- BEFORE any rank streams (the caller's barrier follows)
+		LAUNCH(ctx, k_zero, (int) std::min<size_t>((S.zero_bytes / 16 + 255) / 256, 148 * 4), 256, (int4 *) S.xch.p, (long long) (S.zero_bytes / 16),
+			(unsigned long long *) S.xch.p, 0);
+		ctx->matched = ctx->finalized = false;
+		return NWB_OK;
+	}
+	if (phase == 1) {
+		return match_impl(ctx, fuse_final, nullptr, true, false, 1);
+	}
+	if (phase == 2) return match_impl(ctx, fuse_final, nrows, true, false, 2);   // 1 = every rank has to redo the match from phase 0
+	return fail(ctx, NWB_ERR_ARG, "phase must be 0, 1 or 2");
 }
 
 int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)
@@ -1274,7 +1466,7 @@ int nwb_bench_skeleton(nwb_ctx *ctx, int c, int reps, float *ms)
 	for (int k = 0; k < reps + 1; k++) {
 		CU(cudaMemsetAsync(ka.cnt, 0, (size_t) (ctx->np + 1) * sizeof(int), st));
 		CU(cudaEventRecord(e0, st));
-		{ int r = launch_pairs(ctx, ctx->last_k1_dense, false, true, (int) ctx->cat[c].n, ctx->cat[c].ra, ctx->cat[c].dec, G,
+		{ int r = launch_pairs(ctx, ctx->last_k1_dense, false, true, false, (int) ctx->cat[c].n, ctx->cat[c].ra, ctx->cat[c].dec, G,
 			(const int *) ctx->last_etotal, (const CellRec *) ctx->d_cells.p, (const Entry *) ctx->d_entries.p, (long long) ctx->entries_cap, ka); if (r) return r; }
 		CU(cudaEventRecord(e1, st));
 		CU(cudaStreamSynchronize(st));
@@ -1504,6 +1696,48 @@ int nwb_row_offsets(nwb_ctx *ctx, int a, int b, double *dra_host, double *ddec_h
 	CU(cudaMemcpyAsync(dra_host, d, R * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaMemcpyAsync(ddec_host, d + R, R * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	return NWB_OK;
+}
+
+int nwb_score_rows(nwb_ctx *ctx, int64_t nrows, const int64_t *idx, double *sep, double *sepmax, int64_t *ncat_out, double *log_bf, double *dist_post)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (nrows < 0 || (nrows > 0 && (!idx || !sepmax || !ncat_out || !log_bf || !dist_post))) return fail(ctx, NWB_ERR_ARG, "NULL argument");
+	const int nc = ctx->ncat;
+	if (nc < 2 || !ctx->params_set) return fail(ctx, NWB_ERR_STATE, "set the catalogues and nwb_set_params first");
+	bool ell = false;
+	for (int c = 0; c < nc; c++) {
+		if (!ctx->cat[c].set) return fail(ctx, NWB_ERR_STATE, "catalogue " + std::to_string(c) + " not set");
+		ell = ell || ctx->cat[c].err_kind == NWB_ERR_ELLIPSE;
+	}
+	if (ell)
+		for (int c = 0; c < nc; c++)
+			if (ctx->cat[c].err_kind != NWB_ERR_ELLIPSE) return fail(ctx, NWB_ERR_ARG, "elliptical mode: every catalogue must carry (sigma_x, sigma_y, rho)");
+	if (nrows == 0) return NWB_OK;
+	CU(cudaSetDevice(ctx->device));
+	if (!ctx->tables_set && ctx->tables_dirty) default_tables(ctx);
+	{ int r = upload_tables(ctx); if (r) return r; }
+	PairStore none[MAXC];
+	memset(none, 0, sizeof(none));
+	RowParams saved = ctx->rp;
+	{ int r = fill_row_params(ctx, none, 0, 0, ell); if (r) return r; }
+	const RowParams rp = ctx->rp;
+	ctx->rp = saved;   // the parameter block of the last match stays what nwb_finalize expects
+	const int npairs = nc * (nc - 1) / 2;
+	const size_t R = (size_t) nrows;
+	ENSURE(ctx->d_misc, R * (size_t) (nc + npairs + 4) * 8 + 64);
+	long long *d_idx = (long long *) ctx->d_misc.p;
+	double *d_sep = (double *) (d_idx + R * nc), *d_max = d_sep + R * npairs, *d_lbf = d_max + R, *d_post = d_lbf + R;
+	long long *d_ncat = (long long *) (d_post + R);
+	cudaStream_t st = ctx->stream;
+	CU(cudaMemcpyAsync(d_idx, idx, R * nc * 8, cudaMemcpyHostToDevice, st));
+	LAUNCH(ctx, k_score_rows, grid_for(nrows, 128), 128, rp, (long long) nrows, (const long long *) d_idx, d_sep, d_max, d_ncat, d_lbf, d_post);
+	if (sep) CU(cudaMemcpyAsync(sep, d_sep, R * npairs * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(sepmax, d_max, R * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(ncat_out, d_ncat, R * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(log_bf, d_lbf, R * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(dist_post, d_post, R * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
 	return NWB_OK;
 }
 

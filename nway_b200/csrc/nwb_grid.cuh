@@ -177,13 +177,11 @@ __device__ __forceinline__ void prim_register(const Grid &G, const int i, const 
 			cnt = i1 - i0 + 1;
 		}
 		int cb = B.base;
-		if (MODE == REG_COUNT) {
+		if (MODE == REG_COUNT)
 			for (int k = 0; k < cnt; k++) atomicAdd(&cellcnt[cb + (i0 + k) % n], 1);
-			continue;
-		}
 		// four cells at a time: the slot requests (atomics with return) are independent, issued together so that their
 		// latencies overlap; then the stores
-		for (int k0 = 0; k0 < cnt; k0 += 4) {
+		for (int k0 = 0; MODE != REG_COUNT && k0 < cnt; k0 += 4) {
 			int sl[4], cell[4];
 #pragma unroll
 			for (int u = 0; u < 4; u++) {

@@ -209,6 +209,12 @@ struct K1Args {
 	unsigned long long spill_cap;
 	unsigned long long *spill_count;
 	FlatHash flat;     // NWB_COMPAT_FLAT_HASH (k_pairs<.., FLAT = true>): the reference's bucket size in degrees
+	// shard mode (k_pairs<.., SCAT = true>, nwb_shard_*): this rank streams a slice of the catalogue against ALL primaries
+	// and writes every match straight into the pair store of the rank that owns the primary -- peer memory over NVLink
+	int s_base;                    // catalogue index of the first streamed source
+	int x_block;                   // primaries per rank: owner = p / x_block, index there = p % x_block
+	char *const *x_peers;          // [world] base of every rank's exchange buffer (device array; own rank: local)
+	long long x_cnt_off, x_slot_off, x_spill_off, x_spillcnt_off;   // byte offsets of this catalogue's areas in the exchange buffer
 };
 
 // exact fp64 separation for `count` (<= 32) queued candidates, one per lane; a match takes the next slot of its
@@ -221,7 +227,7 @@ struct K1Args {
 #else
 #define NWB_FLUSH_ATTR __forceinline__
 #endif
-template <bool FLAT, bool SKEL>
+template <bool FLAT, bool SKEL, bool SCAT>
 __device__ NWB_FLUSH_ATTR void k1_flush(const K1Smem &M, int lo, int count, int lane, const K1Args &A)
 {
 	if (lane < count) {
@@ -254,17 +260,37 @@ __device__ NWB_FLUSH_ATTR void k1_flush(const K1Smem &M, int lo, int count, int 
 			keep = sep < A.radius && same;
 		}
 		if (keep) {
-			int slot = atomicAdd(&A.cnt[p], 1);
-			if (slot < A.C) {
-				int4 v;
-				v.x = s; v.y = 0; v.z = __double2loint(sep); v.w = __double2hiint(sep);
-				*reinterpret_cast<int4 *>(A.base + (size_t) p * A.C + slot) = v;
+			if (SCAT) {
+				// the pair store of the primary's owner, in that rank's exchange buffer: one system-scope atomic and one
+				// 16-byte store over NVLink (the own rank's share stays local)
+				const int r = p / A.x_block, pl = p - r * A.x_block;
+				char *pb = reinterpret_cast<char *>(__ldg(reinterpret_cast<const unsigned long long *>(A.x_peers + r)));
+				const int slot = atomicAdd_system(reinterpret_cast<int *>(pb + A.x_cnt_off) + pl, 1);
+				if (slot < A.C) {
+					int4 v;
+					v.x = s + A.s_base; v.y = 0; v.z = __double2loint(sep); v.w = __double2hiint(sep);
+					*reinterpret_cast<int4 *>(reinterpret_cast<Slot16 *>(pb + A.x_slot_off) + (size_t) pl * A.C + slot) = v;
+				} else {
+					const unsigned long long pos = atomicAdd_system(reinterpret_cast<unsigned long long *>(pb + A.x_spillcnt_off), 1ull);
+					if (pos < A.spill_cap) {
+						SpillRec rec;
+						rec.p = pl; rec.slot = slot; rec.s = s + A.s_base; rec.pad = 0; rec.sep = sep;
+						reinterpret_cast<SpillRec *>(pb + A.x_spill_off)[pos] = rec;
+					}
+				}
 			} else {
-				unsigned long long pos = atomicAdd(A.spill_count, 1ull);
-				if (pos < A.spill_cap) {
-					SpillRec rec;
-					rec.p = p; rec.slot = slot; rec.s = s; rec.pad = 0; rec.sep = sep;
-					A.spill[pos] = rec;
+				int slot = atomicAdd(&A.cnt[p], 1);
+				if (slot < A.C) {
+					int4 v;
+					v.x = s; v.y = 0; v.z = __double2loint(sep); v.w = __double2hiint(sep);
+					*reinterpret_cast<int4 *>(A.base + (size_t) p * A.C + slot) = v;
+				} else {
+					unsigned long long pos = atomicAdd(A.spill_count, 1ull);
+					if (pos < A.spill_cap) {
+						SpillRec rec;
+						rec.p = p; rec.slot = slot; rec.s = s; rec.pad = 0; rec.sep = sep;
+						A.spill[pos] = rec;
+					}
 				}
 			}
 		}
@@ -272,7 +298,7 @@ __device__ NWB_FLUSH_ATTR void k1_flush(const K1Smem &M, int lo, int count, int 
 }
 
 // queue the lanes with pass == true as candidates; run the exact stage when 32 are there
-template <bool FLAT, bool SKEL>
+template <bool FLAT, bool SKEL, bool SCAT>
 __device__ __forceinline__ void k1_enqueue(K1Smem &M, bool pass, int s, int p, double r, double d, int lane, int &qn,
 	const K1Args &A)
 {
@@ -287,7 +313,7 @@ __device__ __forceinline__ void k1_enqueue(K1Smem &M, bool pass, int s, int p, d
 		__syncwarp();
 		if (qn >= 32) {
 			qn -= 32;
-			k1_flush<FLAT, SKEL>(M, qn, 32, lane, A);
+			k1_flush<FLAT, SKEL, SCAT>(M, qn, 32, lane, A);
 			__syncwarp();
 		}
 	}
@@ -335,7 +361,8 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 // of the batch has been queued: nothing of the batch is live across them, and the code of the exact stage exists once.
 // DENSE: the band table fits shared memory and there is no occupancy bitmap (the streaming configuration of the
 // benchmark).  FLAT: NWB_COMPAT_FLAT_HASH is in force.  SKEL: the memory-system skeleton (nwb_bench_skeleton).
-template <bool DENSE, bool FLAT, bool SKEL>
+// SCAT: shard mode -- matches go to the owner of the primary over peer memory (K1Args::x_*).
+template <bool DENSE, bool FLAT, bool SKEL, bool SCAT>
 __global__ void __launch_bounds__(K1_WARPS * 32, NWB_K1_MINBLOCKS)
 k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G,
 	const int *__restrict__ etotal, const CellRec *__restrict__ cells, const Entry *__restrict__ entries,
@@ -425,7 +452,7 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 				for (int k = 0; k < 3; k++) {
 					const bool pk = k == 0 ? p0 : (k == 1 ? p1 : p2);
 					const unsigned long long ek = k == 0 ? e0 : (k == 1 ? e1 : e2);
-					k1_enqueue<FLAT, SKEL>(M, pk, i, (int) (ek >> 32), r, d, lane, qn, A);
+					k1_enqueue<FLAT, SKEL, SCAT>(M, pk, i, (int) (ek >> 32), r, d, lane, qn, A);
 				}
 			}
 			maxc = __reduce_max_sync(NWB_FULL, ecnt);
@@ -450,7 +477,7 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 				if (qn >= 32 || (fin && nit == 0 && qn > 0)) {   // candidates -> matches, 32 at a time (fewer only when draining)
 					const int take = min(qn, 32);
 					qn -= take;
-					k1_flush<FLAT, SKEL>(M, qn, take, lane, A);
+					k1_flush<FLAT, SKEL, SCAT>(M, qn, take, lane, A);
 					__syncwarp();
 				} else if (nit >= 32 || (fin && nit > 0)) {      // work items -> candidates (fewer than 32 are queued here)
 					const int take = min(nit, 32);
@@ -1702,6 +1729,59 @@ __global__ void k_row_offsets(long long nrows, const long long *__restrict__ ia,
 	if (sa >= 0 && sb >= 0) offsets_ref(ra_b[sb], dec_b[sb], ra_a[sa], dec_a[sa], x, y);
 	dra[i] = x;
 	ddec[i] = y;
+}
+
+// Score a caller-supplied candidate list (nwb_score_rows): one thread per row of `idx` (R x ncat row indices, -1 = the
+// catalogue takes no part) -- what the reference computes for every tuple crossproduct() hands it, BEFORE the radius
+// filter: the separations of every pair (fastskymatch.py:26-47 via __init__.py:143-168), Separation_max (:166), ncat
+// (:177), the log Bayes factor of the present catalogues and its prior (__init__.py:220-259, bayesdistance.py:64-86),
+// dist_post (bayesdistance.py:26-32).  Separates an arithmetic mismatch from an enumeration mismatch.
+__global__ void k_score_rows(RowParams R, long long nrows, const long long *__restrict__ idx, double *__restrict__ sep_out /* npairs x nrows or null */,
+	double *__restrict__ sepmax, long long *__restrict__ ncat_out, double *__restrict__ lbf_out, double *__restrict__ post_out)
+{
+	const long long row = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= nrows) return;
+	const int nc = R.ncat;
+	long long sidx[MAXC];
+	double lon[MAXC], sl[MAXC], cl[MAXC], sig[MAXC], sep[MAXP];
+	unsigned present = 0;
+	for (int c = 0; c < nc; c++) {
+		const long long i = idx[row * nc + c];
+		sidx[c] = i;
+		if (i >= 0 && i < R.n[c]) {
+			present |= 1u << c;
+			lon[c] = deg2rad_ref(R.ra[c][i]);
+			sincos_ref(deg2rad_ref(R.dec[c][i]), &sl[c], &cl[c]);
+			if (!R.ell) sig[c] = R.err[c][i];
+		} else {
+			sidx[c] = -1;
+		}
+	}
+	double smax = 0.0;
+	for (int a = 0; a < nc; a++)
+		for (int b = a + 1; b < nc; b++) {
+			double v = nan("");
+			if ((present >> a & 1u) && (present >> b & 1u)) {
+				v = sep_arcsec_ref(lon[a], sl[a], cl[a], lon[b], sl[b], cl[b]);
+				if (R.sep_f32) v = (double) (float) v;
+				if (v > smax) smax = v;
+			}
+			sep[pair_index(a, b, nc)] = v;
+			if (sep_out) sep_out[(long long) pair_index(a, b, nc) * nrows + row] = v;
+		}
+	sepmax[row] = smax;
+	ncat_out[row] = __popc(present);
+	double lbf;
+	if (R.ell) {
+		double esig[MAXC], esep[MAXP];
+		ell_prepare(R, present, sidx, esig, esep);
+		lbf = log_bf_ref<0>(R.T, nc, present, esig, esep);
+	} else {
+		lbf = log_bf_ref<0>(R.T, nc, present, sig, sep, R.sep_f32 != 0);
+	}
+	lbf_out[row] = lbf;
+	const unsigned smask = present >> 1;
+	post_out[row] = posterior_ref(R.T->prior[smask], R.T->log10prior[smask], lbf);
 }
 
 __global__ void k_posterior(long long n, const double *__restrict__ prior, const double *__restrict__ lbf,

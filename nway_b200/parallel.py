@@ -149,3 +149,108 @@ def nway_match_sharded(match_tables, match_radius, prior_completeness, gather='a
 	torch.cuda.current_stream(dev).synchronize()   # the context works on its own stream; it has been synchronised by nway_match
 	full = allgather_table(shard, counts, group, gather=gather)
 	return None if full is None else to_host(full)
+
+
+class ScatterMatcher(object):
+	"""The match of nway_b200.nway_match() in shard mode (include/nwayb200.h, nwb_shard_*): every rank holds all
+	catalogues but STREAMS only its slice of every secondary catalogue against all primaries; a match is written by the
+	streaming kernel straight into the pair store of the rank that owns the primary (blocks of ceil(n0 / world)
+	primaries) over NVLink peer memory; each rank then produces the rows of its own primaries.  The time of the stream --
+	the dominant cost when secondaries outnumber primaries by orders of magnitude -- divides by the number of GPUs.
+
+	One instance per (process group, context); __call__(ctx, fuse_final) runs one match: phase 0 (zero the own
+	counters) | barrier | phase 1 (grid + streaming, matches arrive from all ranks) | barrier | phase 2 (rows), then one
+	all-reduce of the "buffer too small, everybody again" flags.  The barriers are NCCL all-reduces of one word on the
+	context's stream: stream-ordered, no host synchronisation."""
+
+	def __init__(self, group=None, device=None, spill_capacity=65536):
+		import torch
+		import torch.distributed as dist
+		self.group = group
+		self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+		self.device = torch.cuda.current_device() if device is None else device
+		self.dev = torch.device('cuda', self.device)
+		self.stream = torch.cuda.Stream(device=self.dev)
+		self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
+		self.flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+		self.spill_capacity = spill_capacity
+		self.ready_for = None
+
+	def setup(self, ctx):
+		"""exchange buffers + peer mapping for the catalogues / radius now set on the context (collective)"""
+		import torch.distributed as dist
+		handle, nbytes = ctx.shard_setup(self.rank, self.world, self.spill_capacity)
+		handles = [None] * self.world
+		dist.all_gather_object(handles, handle, group=self.group)
+		ctx.shard_connect(handles)
+		ctx.set_stream(self.stream.cuda_stream)
+		self.ready_for = ctx
+		return nbytes
+
+	def barrier(self):
+		import torch.distributed as dist
+		dist.all_reduce(self.token, group=self.group)
+
+	def __call__(self, ctx, fuse_final=True):
+		import torch
+		import torch.distributed as dist
+		if self.ready_for is not ctx:
+			self.setup(ctx)
+		with torch.cuda.stream(self.stream):
+			for attempt in range(4):
+				ctx.shard_match(0)
+				self.barrier()
+				ctx.shard_match(1)
+				self.barrier()
+				nrows, retry = ctx.shard_match(2, fuse_final)
+				self.flag.fill_(1 if retry else 0)
+				dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
+				if int(self.flag.item()) == 0:
+					return nrows
+		raise RuntimeError('shard mode: the grid buffers kept overflowing')
+
+	def close(self, ctx):
+		ctx.set_stream(None)
+		ctx.shard_close()
+		self.ready_for = None
+
+
+def nway_match_scatter(match_tables, match_radius, prior_completeness, gather='all', group=None, device=None, **kwargs):
+	"""nway_match() with the streaming of the secondaries shared between the ranks (strong scaling; see ScatterMatcher).
+	Every rank passes the same catalogues.  gather as in nway_match_sharded: 'all' / 'rank0' / 'none'.  Automatic
+	magnitude histograms are not available in this mode (supply maghists)."""
+	import torch
+	import torch.distributed as dist
+	from . import nway_match, _lib, _column_names
+	for t in match_tables:
+		if any(h is None for h in t.get('maghists', [])):
+			raise NotImplementedError('automatic magnitude histograms are a global step; supply maghists in sharded mode')
+	rank, world = dist.get_rank(group), dist.get_world_size(group)
+	if device is None:
+		device = torch.cuda.current_device()
+	dev = torch.device('cuda', device)
+	ctx = _lib.get_context(device)
+	matcher = ScatterMatcher(group, device)
+	kwargs['as_frame'] = False
+	kwargs['keep_on_device'] = True
+	try:
+		local = nway_match(match_tables, match_radius, prior_completeness, device=device, allow_empty=True, matcher=matcher, **kwargs)
+		nrows = local['nrows']
+		with torch.cuda.stream(matcher.stream):
+			counts = exchange_counts(nrows, group, dev)
+			offsets = row_offsets(counts)
+			names, seps, biases = _column_names(match_tables)
+			int_cols = set(names) | {'ncat', 'match_flag'}
+			colnames = list(local['selectors'].keys())
+			shard = ctx.table_view() if nrows else torch.empty((len(colnames), 0), dtype=torch.int64, device=dev)
+
+			def to_host(table):
+				host = table.cpu().numpy()
+				return OrderedDict((name, host[k] if name in int_cols else host[k].view(numpy.float64)) for k, name in enumerate(colnames))
+
+			if gather == 'none':
+				return to_host(shard), counts, offsets
+			full = allgather_table(shard, counts, group, gather=gather)
+			return None if full is None else to_host(full)
+	finally:
+		matcher.close(ctx)

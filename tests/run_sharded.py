@@ -29,6 +29,20 @@ def main():
 	lo = offsets[rank]
 	for k in full:
 		assert np.array_equal(shard[k], full[k][lo:lo + counts[rank]], equal_nan=True), k
+	# the other multi-GPU mode: the ranks share the streaming of the secondaries, matches travel to the owner of the
+	# primary over peer memory (nwb_shard_*); same table, bit for bit
+	got2 = parallel.nway_match_scatter(tables, 7.0, 0.9, gather='all', device=local, logger=nway_b200.NullOutputLogger())
+	assert list(got2.keys()) == list(full.keys())
+	for k in full:
+		assert got2[k].shape == full[k].shape, ('scatter', k, got2[k].shape, full[k].shape)
+		assert np.array_equal(got2[k], full[k], equal_nan=True), ('scatter', k)
+	# ... also for two catalogues (the specialised row kernel) and on an off-equator flat field (NWB_COMPAT_FLAT_HASH)
+	for name in ('syn2', 'offeq3'):
+		spec = cases.GOLDEN_CASES[name]
+		one = nway_b200.nway_match(cases.build_case(name), spec['radius'], spec['completeness'], logger=nway_b200.NullOutputLogger(), as_frame=False, device=local)
+		two = parallel.nway_match_scatter(cases.build_case(name), spec['radius'], spec['completeness'], gather='all', device=local, logger=nway_b200.NullOutputLogger())
+		for k in one:
+			assert np.array_equal(two[k], one[k], equal_nan=True), ('scatter', name, k)
 	dist.barrier()
 	if rank == 0:
 		print('SHARDED_OK world=%d rows=%d' % (dist.get_world_size(), len(full['A'])))

@@ -327,3 +327,43 @@ def test_async_match_equals_sync_match_and_recovers_from_failed_speculation():
 		assert ref_ctx.match() == n
 		for x, y in zip(_all_columns(ctx, n), _all_columns(ref_ctx, n)):
 			assert (x == y).all()
+
+
+def test_score_rows_of_a_supplied_candidate_list():
+	"""nwb_score_rows: the caller's index tuples (here the oracle's complete enumeration plus tuples the radius filter
+	would drop) scored on the device -- separations, Separation_max, ncat, log Bayes factor, dist_post -- against the
+	oracle's arithmetic on the same tuples (nwaylib/__init__.py:123-196, 220-259)"""
+	import nway_b200
+	from nway_b200 import _lib
+	from oracle import nway_oracle as O
+	tables = cases.uniform_patch(31, (300, 6000, 5000), (1.0, 0.3, 0.5), 0.06, dec0=20.0)
+	radius, pc = 7.0, 0.9
+	run_cuda([dict(t) for t in tables], radius, pc)   # leaves catalogues, parameters and tables set on the context
+	radec = [(t['ra'], t['dec']) for t in tables]
+	idx = O.crossproduct_complete(radec, 2.5 * radius / 3600)   # a wider net: most of these fail the radius filter
+	assert len(idx) > 5000
+	got = _lib.get_context().score_rows(idx)
+	n = len(tables)
+	sepmax = np.zeros(len(idx))
+	k = 0
+	seps = {}
+	for a in range(n):
+		for b in range(a + 1, n):
+			ia, ib = idx[:, a], idx[:, b]
+			col = O.dist((radec[a][0][ia], radec[a][1][ia]), (radec[b][0][ib], radec[b][1][ib])) * 60 * 60
+			col[(ia == -1) | (ib == -1)] = np.nan
+			seps[(a, b)] = col
+			with np.errstate(invalid='ignore'):
+				sepmax = np.where(np.isnan(col), sepmax, np.maximum(col, sepmax))
+			assert parity.column_error('Separation', col, got['sep'][k])[0]
+			k += 1
+	assert parity.column_error('Separation_max', sepmax, got['sepmax'])[0]
+	assert np.array_equal(got['ncat'], (idx > -1).sum(axis=1))
+	mt = dict(idx=idx, sep=seps, sepmax=sepmax, ncat=(idx > -1).sum(axis=1), errors=[np.asarray(t['error'], dtype=float)[idx[:, c]] for c, t in enumerate(tables)])
+	nu, nu_plus = O.source_densities(tables)
+	prior, lbf = O.single_log_bf(mt, nu, nu_plus, O.completeness_vector(pc, n))
+	ok, dabs, drel, worst = parity.column_error('dist_bayesfactor', lbf, got['log_bf'])
+	assert ok, (dabs, drel, worst)
+	big = lbf > -300   # dist_post underflows to 0 below; relative comparison where it is a number
+	ok, dabs, drel, worst = parity.column_error('dist_post', O.posterior(prior, lbf)[big], got['dist_post'][big])
+	assert ok, (dabs, drel, worst)

@@ -20,3 +20,13 @@ try:
 except Exception as e:
     print('bench parse failed', e); print(open('$out/bench_n$n.err').read()[-3000:])
 PY
+if [ -n "$STRONG" ]; then
+	timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29643 tools/bench_strong.py $STRONG > $out/strong_n$n.jsonl 2> $out/strong_n$n.err; echo "strong exit $?"
+	python - <<PY
+import json
+for l in open('$out/strong_n$n.jsonl'):
+    if l.startswith('{'):
+        d=json.loads(l); print('%s N=%d %-15s %.3f ms rows %d  %.3e rows/s' % (d['config'], d['n_gpus'], d['mode'], d['device_ms'], d['rows'], d['associations_per_s']))
+PY
+	grep -v "^\[W\|^W1\|^$\|OMP_NUM\|\*\*\*\*" $out/strong_n$n.err | tail -15
+fi

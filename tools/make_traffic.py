@@ -30,7 +30,9 @@ def main(path, label):
 		out[key]['limiter'] = {'l1tex_data_pipe_lsu_wavefronts_pct': g('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed'),
 			'issue_active_pct': g('smsp__issue_active.avg.pct_of_peak_sustained_active'),
 			'dram_throughput_pct': g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')}
-	json.dump({'source': label, 'kernels': out}, open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w'), indent=1)
+	sys.path.insert(0, ROOT)
+	import bench
+	json.dump({'source': label, 'kernel_source_sha256': bench.kernel_source_hash(), 'kernels': out}, open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w'), indent=1)
 	print(json.dumps(out))
 
 
