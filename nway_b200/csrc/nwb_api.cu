@@ -76,6 +76,15 @@ struct nwb_ctx {
 		int C[MAXC] = {0};
 		unsigned long long spill_cap = 0;
 	} shard;
+	// N >= 3 / elliptical: what the previous match of this shape left behind -- buffer capacities and launch decisions -- so
+	// that the next one can enqueue its whole pipeline behind device-side gates (k_spec_gate) without host round trips
+	struct GenCaps {
+		bool valid = false;
+		int nc = 0, ell = 0;
+		int64_t np = -1;
+		long long cap_list[MAXC] = {0}, cap_mat = 0;
+		int big_sort[MAXC] = {0}, any_big = 0;
+	} gen;
 	// what nwb_bench_skeleton needs of the last match: K1 arguments per secondary catalogue and the grid's buffers
 	K1Args last_k1[MAXC];
 	bool last_k1_dense = false;
@@ -1036,6 +1045,122 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	int wgrid = std::max(1, (int) std::min<int64_t>((np * 32 + 255) / 256, 148 * 64));
 	ctx->stats[1] = 0;
 
+	// ---- N >= 3 / elliptical, speculative: lists, separation scratch, row count, rows and normalisation enqueued back to
+	// back behind device-side gates, ONE synchronisation at the end; taken when the previous match of this context had
+	// the same shape (its buffers and launch decisions are reused) and nothing spilled.  If a gate stays shut -- more
+	// matches than the lists hold, more rows than the table, a primary that needs the warp-per-primary kernels where
+	// none were launched -- the stage-by-stage path below redoes the work.
+	bool generic_done = false;
+	{
+		bool can = generic && ctx->gen.valid && ctx->gen.nc == nc && ctx->gen.ell == (int) ell && ctx->gen.np == np &&
+			ctx->cols_cap_rows > 0 && ctx->cols_cap_ncols == nc + nc * (nc - 1) / 2 + 9 + ctx->res_nmag;
+		for (int c = 1; c < nc; c++) can = can && hs[c] == 0;
+		if (can) {
+			const nwb_ctx::GenCaps &Gc = ctx->gen;
+			int *d_gates = (int *) (d_status + 52);
+			Lists L;
+			memset(&L, 0, sizeof(L));
+			GateArgs ga;
+			memset(&ga, 0, sizeof(ga));
+			ga.ncat = nc; ga.gates = d_gates; ga.host = hs; ga.maxcnt = (const int *) (d_status + 40);
+			CU(cudaMemsetAsync(d_status + 40, 0, 4 * sizeof(long long), st));
+			for (int c = 1; c < nc; c++) {
+				ENSURE(ctx->d_segoff[c], (size_t) (np + 1) * sizeof(long long));
+				long long *off = (long long *) ctx->d_segoff[c].p;
+				{ int r = scan_int_to_ll(ctx, (const int *) d_cnt[c], off, np + 1); if (r) return r; }
+				LAUNCH(ctx, k_max_int, (int) std::min<int64_t>((np + 255) / 256, 148 * 8), 256, (long long) np, (const int *) d_cnt[c], (int *) (d_status + 40) + c);
+				ga.seg_total[c] = off + np; ga.cap_list[c] = Gc.cap_list[c]; ga.big_sort[c] = Gc.big_sort[c];
+			}
+			ga.level = 1;
+			LAUNCH(ctx, k_spec_gate, 1, 32, ga, SMALL_N, SMALL_T);
+			for (int c = 1; c < nc; c++) {
+				const size_t cap = (size_t) Gc.cap_list[c];
+				double *tr = (double *) ctx->d_Ltrig[c].p;
+				const long long *off = (const long long *) ctx->d_segoff[c].p;
+				LAUNCH(ctx, k_sort_lists_small, pblocks, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
+					ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + cap, tr + 2 * cap, (long long *) (tr + 3 * cap), flat, (const int *) (d_gates + 1));
+				if (Gc.big_sort[c])
+					LAUNCH(ctx, k_sort_lists, wgrid, 256, (int) np, stores[c], off, (int *) ctx->d_Ls[c].p, (double *) ctx->d_Lsep[c].p,
+						ctx->cat[c].ra, ctx->cat[c].dec, tr, tr + cap, tr + 2 * cap, SMALL_N, (long long *) (tr + 3 * cap), flat, (const int *) (d_gates + 1));
+				L.off[c] = off;
+				L.s[c] = (const int *) ctx->d_Ls[c].p;
+				L.sep[c] = (const double *) ctx->d_Lsep[c].p;
+				L.lon[c] = tr; L.slat[c] = tr + cap; L.clat[c] = tr + 2 * cap;
+				L.ij[c] = (const long long *) (tr + 3 * cap);
+			}
+			rp.L = L;
+			CU(cudaEventRecord(ctx->ev[3], st));
+			ENSURE(ctx->d_matsz, (size_t) (np + 1) * sizeof(long long));
+			ENSURE(ctx->d_matoff, (size_t) (np + 1) * sizeof(long long));
+			long long *d_matsz = (long long *) ctx->d_matsz.p, *d_matoff = (long long *) ctx->d_matoff.p;
+			CU(cudaMemsetAsync(d_matsz, 0, (size_t) (np + 1) * sizeof(long long), st));
+			unsigned long long *d_maxtup = (unsigned long long *) (d_status + 44);
+			CU(cudaMemsetAsync(d_maxtup, 0, sizeof(unsigned long long), st));
+			LAUNCH(ctx, k_mat_sizes, pblocks, 256, (int) np, nc, L, d_matsz, d_maxtup, (const int *) (d_gates + 1));
+			{ int r = scan_ll(ctx, d_matsz, d_matoff, np + 1); if (r) return r; }
+			ga.level = 2; ga.mat_total = d_matoff + np; ga.cap_mat = Gc.cap_mat; ga.max_tuples = d_maxtup; ga.any_big = Gc.any_big;
+			LAUNCH(ctx, k_spec_gate, 1, 32, ga, SMALL_N, SMALL_T);
+			rp.mat_off = d_matoff;
+			rp.mat = (double *) ctx->d_mat.p;
+			CU(cudaMemsetAsync(d_rows, 0, (size_t) (np + 1) * sizeof(long long), st));
+			rp.gate = d_gates + 2;
+			const bool big = Gc.any_big != 0;
+			int r = 0;
+			switch (nc) {
+				case 2: r = launch_count<2>(ctx, rp, d_rows, wgrid, big); break;
+				case 3: r = launch_count<3>(ctx, rp, d_rows, wgrid, big); break;
+				case 4: r = launch_count<4>(ctx, rp, d_rows, wgrid, big); break;
+				case 5: r = launch_count<5>(ctx, rp, d_rows, wgrid, big); break;
+				case 6: r = launch_count<6>(ctx, rp, d_rows, wgrid, big); break;
+				case 7: r = launch_count<7>(ctx, rp, d_rows, wgrid, big); break;
+				default: r = launch_count<8>(ctx, rp, d_rows, wgrid, big); break;
+			}
+			if (r) return r;
+			{ int r2 = scan_ll(ctx, d_rows, d_rowoff, np + 1); if (r2) return r2; }
+			ga.level = 3; ga.rows_total = d_rowoff + np; ga.cap_rows = ctx->cols_cap_rows;
+			LAUNCH(ctx, k_spec_gate, 1, 32, ga, SMALL_N, SMALL_T);
+			rp.row_off = d_rowoff;
+			{ int r2 = layout_columns(ctx, ctx->d_cols, ctx->cols_cap_rows, nc, ctx->res_nmag, ctx->cols, ctx->ncols); if (r2) return r2; }
+			rp.C = ctx->cols;
+			rp.gate = d_gates + 3;
+			CU(cudaEventRecord(ctx->kev[0], st));
+			switch (nc) {
+				case 2: r = launch_rows<2>(ctx, rp, fuse, wgrid, big); break;
+				case 3: r = launch_rows<3>(ctx, rp, fuse, wgrid, big); break;
+				case 4: r = launch_rows<4>(ctx, rp, fuse, wgrid, big); break;
+				case 5: r = launch_rows<5>(ctx, rp, fuse, wgrid, big); break;
+				case 6: r = launch_rows<6>(ctx, rp, fuse, wgrid, big); break;
+				case 7: r = launch_rows<7>(ctx, rp, fuse, wgrid, big); break;
+				default: r = launch_rows<8>(ctx, rp, fuse, wgrid, big); break;
+			}
+			if (r) return r;
+			CU(cudaEventRecord(ctx->kev[1], st));
+			if (cli) LAUNCH(ctx, k_correct_cli, wgrid, 256, rp);
+			CU(cudaEventRecord(ctx->ev[4], st));
+			if (fuse_final && !fuse) { int r2 = run_final(ctx); if (r2) return r2; }
+			CU(cudaEventRecord(ctx->ev[5], st));
+			CU(cudaStreamSynchronize(st));
+			rp.gate = nullptr;
+			if (hs[63] == 1) {
+				generic_done = true;
+				R = hs[25];
+				ctx->any_big = big;
+				for (int c = 1; c < nc; c++) ctx->stats[1] += (int64_t) hs[16 + c];
+			}
+		}
+	}
+	if (generic_done) {
+		ctx->res_ncat = nc;
+		ctx->timing_dirty = true;
+		ctx->timing_ncat = nc;
+		ctx->nrows = R;
+		ctx->matched = true;
+		ctx->finalized = fuse_final != 0;
+		if (nrows) *nrows = R;
+		if (R == 0) return fail(ctx, NWB_ERR_EMPTY, "No matches.");
+		return NWB_OK;
+	}
+
 	if (generic) {
 		// ---- lists: N >= 3 (and the elliptical mode) need the matches sorted and compact -----------------------------------------
 		Lists L;
@@ -1109,6 +1234,14 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		CU(cudaMemcpyAsync(hs + 25, d_rowoff + np, sizeof(long long), cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
 		R = hs[25];
+		// what the next match of this shape may assume (speculative pipeline above)
+		ctx->gen.valid = true; ctx->gen.nc = nc; ctx->gen.ell = (int) ell; ctx->gen.np = np;
+		ctx->gen.cap_mat = (long long) (ctx->d_mat.cap / sizeof(double));
+		ctx->gen.any_big = any_big ? 1 : 0;
+		for (int c = 1; c < nc; c++) {
+			ctx->gen.cap_list[c] = (long long) std::min(std::min(ctx->d_Ls[c].cap / sizeof(int), ctx->d_Lsep[c].cap / sizeof(double)), ctx->d_Ltrig[c].cap / (4 * sizeof(double)));
+			ctx->gen.big_sort[c] = h_maxcnt[c] > SMALL_N ? 1 : 0;
+		}
 	} else {
 		ctx->stats[1] = R - np;
 		if (!speculated) CU(cudaEventRecord(ctx->ev[3], st));

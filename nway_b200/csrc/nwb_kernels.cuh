@@ -190,6 +190,12 @@ constexpr int K1_SBANDS = 1024;                  // bands cached in shared memor
 #ifndef NWB_K1_MINBLOCKS
 #define NWB_K1_MINBLOCKS 3
 #endif
+// the other instantiation (occupancy bitmap: sparse primaries, e.g. an all-sky match) is a pure stream -- nearly every
+// source ends at its bitmap bit -- and lives on resident warps, not on the exact stage: 4 blocks per SM (C5: 2.5 ms
+// against 3.6 ms at 3 blocks, profiles/r02_strong_scaling.txt)
+#ifndef NWB_K1_MINBLOCKS_SPARSE
+#define NWB_K1_MINBLOCKS_SPARSE 4
+#endif
 
 
 struct K1Smem {   // per warp
@@ -363,7 +369,7 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 // benchmark).  FLAT: NWB_COMPAT_FLAT_HASH is in force.  SKEL: the memory-system skeleton (nwb_bench_skeleton).
 // SCAT: shard mode -- matches go to the owner of the primary over peer memory (K1Args::x_*).
 template <bool DENSE, bool FLAT, bool SKEL, bool SCAT>
-__global__ void __launch_bounds__(K1_WARPS * 32, NWB_K1_MINBLOCKS)
+__global__ void __launch_bounds__(K1_WARPS * 32, DENSE ? NWB_K1_MINBLOCKS : NWB_K1_MINBLOCKS_SPARSE)
 k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G,
 	const int *__restrict__ etotal, const CellRec *__restrict__ cells, const Entry *__restrict__ entries,
 	long long entries_cap, K1Args A)
@@ -586,6 +592,54 @@ k_rowoff_status(int np, const int *__restrict__ cnt, long long *__restrict__ row
 	if (mine) { out[t] = v; host[t] = v; }
 }
 
+// N >= 3 / elliptical, speculative pipeline (no host round trip between the stages): after each prefix sum one thread
+// checks that what the sum says fits the buffers the previous match left -- list entries per catalogue, the secondary-
+// secondary separation scratch, the output table -- and that the launch decisions taken from the previous match still
+// cover this one (warp-per-primary kernels present where some primary needs them); the next stage's kernels read the
+// word and do nothing if it is 0.  The totals also go to mapped host memory: the host reads them after its single
+// synchronisation at the end and, if a gate stayed shut, redoes the match stage by stage.
+struct GateArgs {
+	int level, ncat;
+	const long long *seg_total[MAXC];   // level 1: list entries of catalogue c (segment offsets [np])
+	long long cap_list[MAXC];
+	const int *maxcnt;                  // [MAXC]: largest match count of a primary
+	int big_sort[MAXC];                 // the warp-per-primary sort is launched for catalogue c
+	const long long *mat_total;         // level 2
+	long long cap_mat;
+	const unsigned long long *max_tuples;
+	int any_big;                        // the warp-per-primary count / row kernels are launched
+	const long long *rows_total;        // level 3
+	long long cap_rows;
+	int *gates;                         // [4]
+	long long *host;                    // mapped: [16 + c] list entries, [40 ..] maxcnt words, [24] mat, [26] tuples, [25] rows, [60 + level] gate
+};
+
+__global__ void k_spec_gate(GateArgs A, int small_n, int small_t)
+{
+	if (threadIdx.x != 0) return;
+	bool ok = true;
+	if (A.level == 1) {
+		for (int c = 1; c < A.ncat; c++) {
+			const long long n = *A.seg_total[c];
+			A.host[16 + c] = n;
+			ok = ok && n <= A.cap_list[c] && (A.maxcnt[c] <= small_n || A.big_sort[c]);
+		}
+		for (int k = 0; k < 4; k++) A.host[40 + k] = reinterpret_cast<const long long *>(A.maxcnt)[k];
+	} else if (A.level == 2) {
+		const long long m = *A.mat_total;
+		const unsigned long long t = *A.max_tuples;
+		A.host[24] = m;
+		A.host[26] = (long long) t;
+		ok = A.gates[1] != 0 && m <= A.cap_mat && (t <= (unsigned long long) small_t || A.any_big);
+	} else {
+		const long long r = *A.rows_total;
+		A.host[25] = r;
+		ok = A.gates[2] != 0 && r <= A.cap_rows;
+	}
+	A.gates[A.level] = ok ? 1 : 0;
+	A.host[60 + A.level] = ok ? 1 : 0;
+}
+
 // a few 8-byte words from device memory into mapped pinned host memory.  Small read-backs go this way rather than through
 // cudaMemcpyAsync: a copy would queue on the device-to-host copy engine behind whatever bulk transfer another context
 // has in flight there (two contexts overlapping their H2D / D2H), a store from a kernel does not.
@@ -626,8 +680,9 @@ __global__ void k_spill_scatter(long long n, const SpillRec *__restrict__ recs, 
 __global__ void k_sort_lists(int np, PairStore S, const long long *__restrict__ seg_off, int *__restrict__ L_s,
 	double *__restrict__ L_sep, const double *__restrict__ ra, const double *__restrict__ dec,
 	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat, int small_n,
-	long long *__restrict__ L_ij, FlatHash flat)
+	long long *__restrict__ L_ij, FlatHash flat, const int *gate = nullptr)
 {
+	if (!gate_open(gate)) return;
 	int lane = threadIdx.x & 31;
 	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -658,8 +713,9 @@ constexpr int SMALL_N = 4;
 __global__ void k_sort_lists_small(int np, PairStore S, const long long *__restrict__ seg_off, int *__restrict__ L_s,
 	double *__restrict__ L_sep, const double *__restrict__ ra, const double *__restrict__ dec,
 	double *__restrict__ L_lon, double *__restrict__ L_slat, double *__restrict__ L_clat,
-	long long *__restrict__ L_ij, FlatHash flat)
+	long long *__restrict__ L_ij, FlatHash flat, const int *gate = nullptr)
 {
+	if (!gate_open(gate)) return;
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= np) return;
 	int n = S.cnt[p];
@@ -706,8 +762,10 @@ __device__ __forceinline__ long long mat_block_offset(const int *nl, int c, int 
 // sizes of the secondary-secondary separation scratch per primary
 // (+ the largest number of candidate tuples of any primary, so that the host can skip the warp-per-primary kernels
 // when every primary is handled by the one-thread-per-primary ones)
-__global__ void k_mat_sizes(int np, int ncat, Lists L, long long *__restrict__ sizes, unsigned long long *__restrict__ max_tuples)
+__global__ void k_mat_sizes(int np, int ncat, Lists L, long long *__restrict__ sizes, unsigned long long *__restrict__ max_tuples,
+	const int *gate = nullptr)
 {
+	if (!gate_open(gate)) return;
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned long long ntup = 0;
 	if (p < np) {
@@ -742,6 +800,7 @@ __global__ void k_max_int(long long n, const int *__restrict__ x, int *__restric
 template <int NC>
 __global__ void k_count_rows(RowParams R, long long *__restrict__ rows)
 {
+	if (!gate_open(R.gate)) return;
 	int lane = threadIdx.x & 31;
 	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -809,6 +868,7 @@ __global__ void k_count_rows(RowParams R, long long *__restrict__ rows)
 template <int NC>
 __global__ void k_count_rows_small(RowParams R, long long *__restrict__ rows)
 {
+	if (!gate_open(R.gate)) return;
 	const int p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= R.np) return;
 	int nl[NC];
@@ -947,6 +1007,7 @@ template <int NC, bool FUSE>
 __global__ void __launch_bounds__(256)
 k_rows(RowParams R)
 {
+	if (!gate_open(R.gate)) return;
 	const int lane = threadIdx.x & 31;
 	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1077,6 +1138,7 @@ template <int NC, bool FUSE>
 __global__ void __launch_bounds__(128)
 k_rows_small(RowParams R)
 {
+	if (!gate_open(R.gate)) return;
 	const int p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= R.np) return;
 	const ConstTables *__restrict__ T = R.T;
@@ -1391,6 +1453,7 @@ k_rows2(RowParams R)
 __global__ void __launch_bounds__(256)
 k_final(RowParams R)
 {
+	if (!gate_open(R.gate)) return;
 	const int lane = threadIdx.x & 31;
 	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1421,6 +1484,7 @@ k_final(RowParams R)
 // intersection has >= 2 members; every row whose ABSENT set is exactly M gets best(M) added.
 __global__ void k_correct_cli(RowParams R)
 {
+	if (!gate_open(R.gate)) return;
 	const int lane = threadIdx.x & 31;
 	int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	int nwarps = (gridDim.x * blockDim.x) >> 5;

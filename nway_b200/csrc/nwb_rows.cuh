@@ -83,7 +83,12 @@ struct RowParams {
 	// its single sync and re-runs the non-speculative path otherwise
 	const long long *guard;
 	long long max_rows, entries_cap;
+	// N >= 3 / elliptical, speculative launch: the stage runs only if the word the gate kernel (k_spec_gate) wrote for it
+	// says that everything it depends on fits the buffers of the previous match
+	const int *gate;
 };
+
+__device__ __forceinline__ bool gate_open(const int *gate) { return !gate || *reinterpret_cast<const volatile int *>(gate) != 0; }
 
 __device__ __forceinline__ bool guard_ok(const RowParams &R)
 {

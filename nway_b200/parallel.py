@@ -35,6 +35,9 @@ def row_offsets(counts):
 	return [int(x) for x in numpy.concatenate(([0], numpy.cumsum(counts)[:-1]))]
 
 
+PACK_BELOW_BYTES = 1 << 20   # per (column, peer) message: below this the exchange is latency-bound and shards travel packed
+
+
 def _exchange(send, recv, group=None):
 	"""ONE grouped exchange: send = [(tensor, peer)], recv = [(tensor, peer)], every message at its exact size.  With NCCL
 	the whole list is a single ncclGroup (torch.distributed.batch_isend_irecv) -- no padding, no staging copies, no
@@ -54,7 +57,8 @@ def allgather_table(local, counts, group=None, gather='all', out=None):
 	rank order (exchange_counts).  Returns the (ncols, sum(counts)) table, shards in rank order, on every rank
 	(gather='all') or on rank 0 only (gather='rank0': a real gather, the other ranks only send and return None).
 	Per peer and column one message of exactly that shard's size, all of them in one NCCL group; the own shard is
-	placed with one strided device copy."""
+	placed with one strided device copy.  Small shards (column pieces below PACK_BELOW_BYTES) travel as one packed
+	message per peer instead: there the number of messages, not their bytes, is the cost."""
 	import torch
 	import torch.distributed as dist
 	rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -68,14 +72,33 @@ def allgather_table(local, counts, group=None, gather='all', out=None):
 		if counts[rank]:
 			out[:, offs[rank]:offs[rank] + counts[rank]].copy_(local)
 	send, recv = [], []
+	if max(counts) * local.element_size() >= PACK_BELOW_BYTES:
+		# bandwidth regime: every (column, peer) message goes from the context's column to its final place, no staging
+		for peer in range(world):
+			if peer == rank:
+				continue
+			if counts[rank] and (gather == 'all' or peer == 0):
+				send += [(local[k], peer) for k in range(ncols)]
+			if want and counts[peer]:
+				recv += [(out[k, offs[peer]:offs[peer] + counts[peer]], peer) for k in range(ncols)]
+		_exchange(send, recv, group)
+		return out if want else None
+	# latency regime (shards of a few MB: a sparse all-sky match): ONE message per peer -- the shard packed into a
+	# contiguous (ncols, rows) block, unpacked into the table's columns on arrival; 2 (world - 1) messages instead of
+	# 2 ncols (world - 1)
+	packed = local.contiguous() if counts[rank] else None
+	staging = {}
 	for peer in range(world):
 		if peer == rank:
 			continue
 		if counts[rank] and (gather == 'all' or peer == 0):
-			send += [(local[k], peer) for k in range(ncols)]
+			send.append((packed.view(-1), peer))
 		if want and counts[peer]:
-			recv += [(out[k, offs[peer]:offs[peer] + counts[peer]], peer) for k in range(ncols)]
+			staging[peer] = torch.empty(ncols * counts[peer], dtype=local.dtype, device=local.device)
+			recv.append((staging[peer], peer))
 	_exchange(send, recv, group)
+	for peer, buf in staging.items():
+		out[:, offs[peer]:offs[peer] + counts[peer]].copy_(buf.view(ncols, counts[peer]))
 	return out if want else None
 
 

@@ -329,6 +329,51 @@ def test_async_match_equals_sync_match_and_recovers_from_failed_speculation():
 			assert (x == y).all()
 
 
+def _table_columns(ctx, nrows, ncat):
+	from nway_b200 import _lib
+	npairs = ncat * (ncat - 1) // 2
+	sels = [_lib.COL_IDX + c for c in range(ncat)] + [_lib.COL_SEP + k for k in range(npairs)] + [_lib.COL_SEPMAX, _lib.COL_NCAT,
+		_lib.COL_LOGBF_UNCORR, _lib.COL_LOGBF, _lib.COL_DIST_POST, _lib.COL_P_SINGLE, _lib.COL_MATCH_FLAG, _lib.COL_P_ANY, _lib.COL_P_I]
+	out = [ctx.fetch(sel, nrows, dtype=np.int64) for sel in sels]
+	ctx.sync()
+	return out
+
+
+@pytest.mark.parametrize('ncat,mode', [(3, 'api'), (4, 'cli')])
+def test_speculative_pipeline_for_three_and_more_catalogues(ncat, mode):
+	"""N >= 3: the second match of a context enqueues lists, separation scratch, row count, rows and normalisation behind
+	device-side gates with one synchronisation at the end (nwb_api.cu, k_spec_gate).  Same table bit for bit as the
+	stage-by-stage path of a fresh context -- also when a gate stays shut: catalogues replaced by denser ones (more list
+	entries and rows than the buffers of the previous match hold), by clustered ones (primaries that need the
+	warp-per-primary kernels where only the thread-per-primary ones were launched), and back."""
+	from nway_b200 import _lib
+	sizes = (400, 9000, 7000, 6000)[:ncat]
+	sig = (1.0, 0.3, 0.5, 0.4)[:ncat]
+	a = cases.uniform_patch(61, sizes, sig, 0.3)                                   # sparse: at most a few matches per primary
+	b = cases.uniform_patch(62, (400,) + tuple(6 * n for n in sizes[1:]), sig, 0.3)   # six times denser: buffers outgrown
+	c = cases.uniform_patch(63, sizes, sig, 0.02)                                  # crowded: big groups
+	unrelated = _lib.UNRELATED_CLI if mode == 'cli' else _lib.UNRELATED_API
+
+	def load(ctx, tables):
+		_load_tables(ctx, tables, 6.0, 0.9)
+		import nway_b200
+		tab = nway_b200._scalar_tables(tables, 0.9, nway_b200.NullOutputLogger())
+		ctx.set_params(6.0, tab['pc'], 0.5, unrelated)
+		ctx.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
+
+	ctx = _lib.Context(0)
+	for tables in (a, a, a, b, b, c, a, c, c):
+		load(ctx, tables)
+		n = ctx.match()
+		ref_ctx = _lib.Context(0)
+		load(ref_ctx, tables)
+		assert ref_ctx.match() == n
+		for x, y in zip(_table_columns(ctx, n, ncat), _table_columns(ref_ctx, n, ncat)):
+			assert (x == y).all()
+		ref_ctx.close()
+	ctx.close()
+
+
 def test_score_rows_of_a_supplied_candidate_list():
 	"""nwb_score_rows: the caller's index tuples (here the oracle's complete enumeration plus tuples the radius filter
 	would drop) scored on the device -- separations, Separation_max, ncat, log Bayes factor, dist_post -- against the
