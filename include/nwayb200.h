@@ -187,6 +187,13 @@ int nwb_finalize(nwb_ctx *ctx);
  *   closed on the right; the caller turns them into a density exactly as numpy does. */
 int nwb_maghist_select(nwb_ctx *ctx, int c, int k, int by_radius, double thr_select, double thr_possible, int weights_cli,
 	int64_t *nselected, int64_t *counts3, double *minmax2);
+/* The same selection over caller-supplied device columns of nrows rows (index column of catalogue c, Separation_max,
+ * dist_post): the rows of ALL shards of a multi-GPU match gathered in global row order -- the first occurrence of a source
+ * and the reference's weight indexing are properties of the whole table, not of a shard.  Every rank runs it
+ * on the same gathered columns and obtains the same histogram (nway_b200.parallel.nway_match_sharded). */
+int nwb_maghist_select_rows(nwb_ctx *ctx, int c, int k, int64_t nrows, const int64_t *res_dev, const double *sepmax_dev,
+	const double *dist_post_dev, int by_radius, double thr_select, double thr_possible, int weights_cli,
+	int64_t *nselected, int64_t *counts3, double *minmax2);
 int nwb_maghist_sample(nwb_ctx *ctx, int64_t nselected, double *mag_host, double *weight_host);
 int nwb_maghist_count(nwb_ctx *ctx, int c, int k, int nbins, const double *edges, int64_t *counts);
 

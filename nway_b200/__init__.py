@@ -155,7 +155,7 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	store_mag_hists=True,
 	logger=default_logger,
 	unrelated_mode='api', device=None, primary_range=None, as_frame=True, keep_on_device=False, allow_empty=False,
-	cli_compat=False, pairwise_errs=(), flat_hash_compat=True, matcher=None):
+	cli_compat=False, pairwise_errs=(), flat_hash_compat=True, matcher=None, hist_rows=None):
 	"""Same contract as nwaylib.nway_match (nwaylib/__init__.py:31-83); see there for the arguments.
 
 	match_tables: list of dicts with name, ra, dec (deg), error (arcsec), area (deg^2), mags, magnames, maghists
@@ -182,6 +182,9 @@ def nway_match(match_tables, match_radius, prior_completeness,
 	                  (SURVEY.md Q3); those associations are left out here too, so that prob_has_match / prob_this_match /
 	                  match_flag of a group are the reference's.  False: the complete enumeration on the whole sphere
 	                  (a superset; identical near the equator and wherever the reference uses its HEALPix hash).
+	  hist_rows       callable(ctx, c) -> (nrows, res_ptr, sepmax_ptr, dist_post_ptr): the device columns the automatic
+	                  histograms of catalogue c are selected from instead of this context's own rows (nway_b200.parallel:
+	                  the rows of all shards, gathered)
 	  matcher         callable(ctx, fuse_final) -> rows that runs the match in place of ctx.match (nway_b200.parallel: the
 	                  multi-GPU mode in which the ranks share the streaming of the secondaries)
 	  cli_compat      the arithmetic quirks of the command-line program nway.py on top of unrelated_mode='cli':
@@ -266,7 +269,8 @@ def nway_match(match_tables, match_radius, prior_completeness,
 			mag = '%s:%s' % (table_name, magname)
 			logger.log('Incorporating bias "%s" ...' % mag)
 			bins, hist_sel, hist_all, nsel, npossible, nothers = magnitudeweights.auto_histogram_device(ctx, c, k, magvals.dtype,
-				mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue, cli=cli_compat)
+				mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue, cli=cli_compat,
+				rows=None if hist_rows is None else hist_rows(ctx, c))
 			logger.log('magnitude histogram of column "%s": %d secure matches, %d insecure matches and %d secure non-matches of %d total entries (%d valid)' % (
 				col, nsel, npossible, nothers, len(magvals), numpy.isfinite(magvals).sum()))
 			if store_mag_hists:

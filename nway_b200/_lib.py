@@ -37,6 +37,8 @@ EXPORTS = {
 	'nwb_flat_hash_applied': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
 	'nwb_maghist_select': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
 		c_int64_p, c_int64_p, c_double_p]),
+	'nwb_maghist_select_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+		ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, c_int64_p, c_int64_p, c_double_p]),
 	'nwb_maghist_sample': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p]),
 	'nwb_maghist_count': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_int64_p]),
 	'nwb_set_prefilter': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), c_double_p]),
@@ -170,14 +172,20 @@ class Context(object):
 		r = (ctypes.c_double * max(n, 1))(*[float(x[2]) for x in pairwise_errs])
 		self.check(self.lib.nwb_set_prefilter(self.h, n, a, b, r))
 
-	def maghist_select(self, c, k, by_radius, thr_select, thr_possible, weights_cli):
+	def maghist_select(self, c, k, by_radius, thr_select, thr_possible, weights_cli, rows=None):
 		"""device half of the automatic histogram: returns (magnitudes, weights) of the unique selected sources in
-		ascending source order, (n_possible, n_others, n_valid), (min, max) magnitude of the field sources"""
+		ascending source order, (n_possible, n_others, n_valid), (min, max) magnitude of the field sources.
+		rows: (nrows, res_ptr, sepmax_ptr, dist_post_ptr) device columns to select from instead of the context's own table
+		(the gathered rows of all shards, nwb_maghist_select_rows)"""
 		nsel = ctypes.c_int64()
 		counts = (ctypes.c_int64 * 3)()
 		mm = (ctypes.c_double * 2)()
-		self.check(self.lib.nwb_maghist_select(self.h, int(c), int(k), int(bool(by_radius)), float(thr_select), float(thr_possible),
-			int(bool(weights_cli)), ctypes.byref(nsel), counts, mm))
+		if rows is None:
+			self.check(self.lib.nwb_maghist_select(self.h, int(c), int(k), int(bool(by_radius)), float(thr_select), float(thr_possible),
+				int(bool(weights_cli)), ctypes.byref(nsel), counts, mm))
+		else:
+			self.check(self.lib.nwb_maghist_select_rows(self.h, int(c), int(k), int(rows[0]), rows[1], rows[2], rows[3], int(bool(by_radius)),
+				float(thr_select), float(thr_possible), int(bool(weights_cli)), ctypes.byref(nsel), counts, mm))
 		mag, w = numpy.empty(nsel.value), numpy.empty(nsel.value)
 		if nsel.value:
 			self.check(self.lib.nwb_maghist_sample(self.h, nsel.value, dptr(mag), dptr(w)))

@@ -100,19 +100,20 @@ struct nwb_ctx {
 	DevBuf d_tables, d_prim, d_red, d_bands, d_cellcnt, d_entries, d_cub, d_pairs, d_paircount;
 	DevBuf d_cnt[MAXC], d_segoff[MAXC], d_seg_s[MAXC], d_seg_sep[MAXC], d_Ls[MAXC], d_Lsep[MAXC], d_Ltrig[MAXC];
 	DevBuf d_rows, d_rowoff, d_matsz, d_matoff, d_mat, d_cols, d_cols2, d_keep, d_keeppos, d_misc;
-	DevBuf d_spill, d_status, d_spilloff[MAXC], d_spillseg[MAXC], d_cells, d_worklist;
+	DevBuf d_spill, d_status, d_spilloff[MAXC], d_spillseg[MAXC], d_cells, d_worklist, d_surv;
 	DevBuf d_hrow, d_hsrc, d_hout;   // automatic histograms: per-row / per-source scratch, compact sample
 	int hist_cat = -1, hist_k = -1;  // the (catalogue, magnitude) whose 'possible' marks d_hsrc holds
 	size_t entries_cap = 0;
 	unsigned long long spill_cap = 0;
 	long long *h_status = nullptr;   // pinned
-	int k1_occ[16] = {0}, num_sms = 0;   // resident blocks per SM of every k_pairs instantiation
+	int k1_occ[16] = {0}, num_sms = 0, filter_occ = 0;   // resident blocks per SM of every k_pairs instantiation
 	// grid geometry of the previous match, re-used when the primaries' bounding box and the radius are unchanged
 	bool geom_valid = false;
 	double geom_rb = 0;
 	int64_t geom_np = -1, geom_first = -1;
 	BoundsKey geom_key;
 	Grid geom_G;
+	double geom_occ = 1.0;
 	int64_t cols_cap_rows = 0;
 	int cols_cap_ncols = 0;
 	bool timing_dirty = false, tables_dirty = true, shard_events_valid = false;
@@ -458,7 +459,7 @@ void nwb_destroy(nwb_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *single[] = {&ctx->d_tables, &ctx->d_prim, &ctx->d_red, &ctx->d_bands, &ctx->d_cellcnt,
 		&ctx->d_entries, &ctx->d_cub, &ctx->d_pairs, &ctx->d_paircount, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_matsz,
-		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc, &ctx->d_spill, &ctx->d_status, &ctx->d_cells, &ctx->d_worklist,
+		&ctx->d_matoff, &ctx->d_mat, &ctx->d_cols, &ctx->d_cols2, &ctx->d_keep, &ctx->d_keeppos, &ctx->d_misc, &ctx->d_spill, &ctx->d_status, &ctx->d_cells, &ctx->d_worklist, &ctx->d_surv,
 		&ctx->d_hrow, &ctx->d_hsrc, &ctx->d_hout};
 	for (DevBuf *b : single) release(*b);
 	for (int c = 0; c < MAXC; c++) {
@@ -849,18 +850,20 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		const double reach = 1.0 + 2.0 * rb_ins / s_deg;   // cells a primary's box spans along one axis, on average
 		const bool sparse = (double) gnp * reach * reach < 0.5 * (double) g.ncells;
 		g.bits = sparse ? (const unsigned *) ((const char *) ctx->d_cells.p + rec_bytes) : nullptr;
+		ctx->geom_occ = (double) gnp * reach * reach / (double) g.ncells;   // expected share of occupied cells (an upper estimate)
 	}
 	const Grid G = ctx->geom_G;
 	// one zero-initialised block: cell counters | per-catalogue match counters | scalar counters
 	const size_t ncell1 = (size_t) G.ncells + 1;
 	const size_t cnt_stride = ((size_t) np + 1 + 3) / 4 * 4;
-	const size_t zero_ints = (ncell1 + 3) / 4 * 4 + cnt_stride * (nc - 1) + 4 * MAXC;
+	const size_t zero_ints = (ncell1 + 3) / 4 * 4 + cnt_stride * (nc - 1) + 8 * MAXC;
 	ENSURE(ctx->d_cellcnt, zero_ints * sizeof(int));
 	int *d_cellcnt = (int *) ctx->d_cellcnt.p;
 	int *d_cnt[MAXC] = {nullptr};
 	for (int c = 1; c < nc; c++) d_cnt[c] = d_cellcnt + (ncell1 + 3) / 4 * 4 + cnt_stride * (c - 1);
 	unsigned long long *d_spillcount = (unsigned long long *) (d_cellcnt + (ncell1 + 3) / 4 * 4 + cnt_stride * (nc - 1));
-	int *d_etotal = (int *) (d_spillcount + 12);   // [0] overflow entries of the cell lists, [1] registrations
+	int *d_etotal = (int *) (d_spillcount + 12);   // [0] overflow entries of the cell lists, [1] registrations, [2] K0 work list
+	unsigned long long *d_survn = (unsigned long long *) (d_etotal + 8);   // [c]: survivors of k_filter for catalogue c
 	char *xch = (char *) ctx->shard.xch.p;
 	if (shard) {   // match counters and spill counters of the own primaries live in the exchange buffer, where the peers write
 		for (int c = 1; c < nc; c++) d_cnt[c] = (int *) (xch + ctx->shard.off_cnt[c]);
@@ -947,7 +950,32 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			}
 			ctx->last_k1[c] = ka; ctx->last_k1_dense = G.nbands <= K1_SBANDS && !G.bits;
 			ctx->last_etotal = d_etotal;
-			if (s_count > 0) {
+			// sparse primaries and a long catalogue: the stream as two kernels -- k_filter (coordinates -> bitmap bit, survivors
+			// appended to a list) at full occupancy, then k_pairs over the few per cent that survive.  Should the list overflow
+			// (denser than estimated) the second k_pairs launch streams the catalogue directly; otherwise it does nothing.
+			const bool two_kernels = G.bits && s_count >= (1 << 20) && ctx->geom_occ < 0.2;
+			if (two_kernels && s_count > 0) {
+				const long long cap = (long long) std::min<double>((double) s_count, (double) s_count * (3.0 * ctx->geom_occ + 0.02) + 4096.0);
+				ENSURE(ctx->d_surv, (size_t) cap * sizeof(int));
+				if (ctx->filter_occ <= 0) {
+					int nb = 0, nsm = 0;
+					CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_filter, 256, 0));
+					CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+					ctx->filter_occ = std::max(nb, 1);
+					ctx->num_sms = std::max(nsm, 1);
+				}
+				LAUNCH(ctx, k_filter, ctx->num_sms * ctx->filter_occ, 256, (int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
+					(int *) ctx->d_surv.p, d_survn + c, cap);
+				ka.surv = (const int *) ctx->d_surv.p; ka.surv_n = d_survn + c; ka.surv_cap = cap;
+				for (int mode = 1; mode <= 2; mode++) {
+					ka.surv_mode = mode;
+					int r = launch_pairs(ctx, false, flat_err > 0.0, false, shard, (int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
+						(const int *) d_etotal, (const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
+					if (r) return r;
+				}
+				ka.surv_mode = 0;
+				ctx->last_k1[c] = ka;
+			} else if (s_count > 0) {
 				int r = launch_pairs(ctx, ctx->last_k1_dense, flat_err > 0.0, false, shard, (int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
 					(const int *) d_etotal, (const CellRec *) d_cells, (const Entry *) d_entries, (long long) ctx->entries_cap, ka);
 				if (r) return r;
@@ -1628,16 +1656,16 @@ int nwb_stats(nwb_ctx *ctx, int64_t *out4)
 }
 
 // ---- N1: automatic magnitude histograms ---------------------------------------------------------------------
-int nwb_maghist_select(nwb_ctx *ctx, int c, int k, int by_radius, double thr_select, double thr_possible, int weights_cli,
-	int64_t *nselected, int64_t *counts3, double *minmax2)
+// the selection over the rows (res = index column of catalogue c, sepmax, dist_post: device columns of R rows) -- the
+// context's own table, or the rows of ALL shards gathered by the caller (nwb_maghist_select_rows)
+static int maghist_select_impl(nwb_ctx *ctx, int c, int k, int64_t R, const long long *res_col, const double *sepmax_col, const double *post_col,
+	int by_radius, double thr_select, double thr_possible, int weights_cli, int64_t *nselected, int64_t *counts3, double *minmax2)
 {
-	if (!ctx) return NWB_ERR_ARG;
-	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
-	if (c < 1 || c >= ctx->res_ncat) return fail(ctx, NWB_ERR_ARG, "catalogue index out of range");
+	if (c < 1 || c >= ctx->ncat) return fail(ctx, NWB_ERR_ARG, "catalogue index out of range");
 	if (k < 0 || k >= ctx->cat[c].m) return fail(ctx, NWB_ERR_ARG, "magnitude column out of range");
 	CU(cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
-	const int64_t R = ctx->nrows, n = ctx->cat[c].n;
+	const int64_t n = ctx->cat[c].n;
 	if (R >= 0x7f7f7f7fll) return fail(ctx, NWB_ERR_ARG, "table too long for the histogram selection");
 	const double *mag = ctx->cat[c].mags + (size_t) k * n;
 	// per-row scratch: flag bytes | isel | idef | selpos | defpos | W
@@ -1657,13 +1685,12 @@ int nwb_maghist_select(nwb_ctx *ctx, int c, int k, int by_radius, double thr_sel
 	CU(cudaMemsetAsync(selflag, 0, (np_ + 64) * sizeof(int), st));
 	unsigned long long init[5] = {0, 0, 0, ~0ull, 0};
 	CU(cudaMemcpyAsync(stats, init, sizeof(init), cudaMemcpyHostToDevice, st));
-	const double *sw = by_radius ? nullptr : (const double *) ctx->cols.dist_post;
+	const double *sw = by_radius ? nullptr : post_col;
 	if (R > 0) {
-		LAUNCH(ctx, k_hist_flags, grid_for(R, 256), 256, (long long) R, (const long long *) ctx->cols.idx[c],
-			(const double *) ctx->cols.sepmax, (const double *) ctx->cols.dist_post, by_radius, thr_select, thr_possible, flag, isel, idef);
+		LAUNCH(ctx, k_hist_flags, grid_for(R, 256), 256, (long long) R, res_col, sepmax_col, post_col, by_radius, thr_select, thr_possible, flag, isel, idef);
 		{ int r = scan_int(ctx, isel, selpos, R); if (r) return r; }
 		{ int r = scan_int(ctx, idef, defpos, R); if (r) return r; }
-		LAUNCH(ctx, k_hist_mark, grid_for(R, 256), 256, (long long) R, (const long long *) ctx->cols.idx[c], (const unsigned char *) flag,
+		LAUNCH(ctx, k_hist_mark, grid_for(R, 256), 256, (long long) R, res_col, (const unsigned char *) flag,
 			(const int *) selpos, (const int *) defpos, sw, weights_cli, first, possible, W);
 	}
 	if (n > 0) {
@@ -1695,6 +1722,25 @@ int nwb_maghist_select(nwb_ctx *ctx, int c, int k, int by_radius, double thr_sel
 		if (hs[49] == 0) minmax2[0] = minmax2[1] = NAN;
 	}
 	return NWB_OK;
+}
+
+int nwb_maghist_select(nwb_ctx *ctx, int c, int k, int by_radius, double thr_select, double thr_possible, int weights_cli,
+	int64_t *nselected, int64_t *counts3, double *minmax2)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	if (c < 1 || c >= ctx->res_ncat) return fail(ctx, NWB_ERR_ARG, "catalogue index out of range");
+	return maghist_select_impl(ctx, c, k, ctx->nrows, (const long long *) ctx->cols.idx[c], (const double *) ctx->cols.sepmax,
+		(const double *) ctx->cols.dist_post, by_radius, thr_select, thr_possible, weights_cli, nselected, counts3, minmax2);
+}
+
+int nwb_maghist_select_rows(nwb_ctx *ctx, int c, int k, int64_t nrows, const int64_t *res_dev, const double *sepmax_dev, const double *dist_post_dev,
+	int by_radius, double thr_select, double thr_possible, int weights_cli, int64_t *nselected, int64_t *counts3, double *minmax2)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (nrows < 0 || (nrows > 0 && (!res_dev || !sepmax_dev || !dist_post_dev))) return fail(ctx, NWB_ERR_ARG, "NULL column");
+	return maghist_select_impl(ctx, c, k, nrows, (const long long *) res_dev, sepmax_dev, dist_post_dev, by_radius, thr_select, thr_possible,
+		weights_cli, nselected, counts3, minmax2);
 }
 
 int nwb_maghist_sample(nwb_ctx *ctx, int64_t nselected, double *mag_host, double *weight_host)

@@ -190,11 +190,13 @@ constexpr int K1_SBANDS = 1024;                  // bands cached in shared memor
 #ifndef NWB_K1_MINBLOCKS
 #define NWB_K1_MINBLOCKS 3
 #endif
-// the other instantiation (occupancy bitmap: sparse primaries, e.g. an all-sky match) is a pure stream -- nearly every
-// source ends at its bitmap bit -- and lives on resident warps, not on the exact stage: 4 blocks per SM (C5: 2.5 ms
-// against 3.6 ms at 3 blocks, profiles/r02_strong_scaling.txt)
+// the other instantiation (occupancy bitmap: sparse primaries, e.g. an all-sky match): measured on C5 (3e8 sources, 97 %
+// of which end at their bitmap bit) 3.55 ms at 3 blocks per SM, 6.1 ms at 4 (64 registers: the streaming loop's values
+// spill) -- and 2.5 ms in round 1, whose exact stage needed fewer registers.  Long sparse streams therefore run as two
+// kernels (k_filter + k_pairs over the survivors, nwb_api.cu); this instantiation handles the survivors and the
+// short catalogues.
 #ifndef NWB_K1_MINBLOCKS_SPARSE
-#define NWB_K1_MINBLOCKS_SPARSE 4
+#define NWB_K1_MINBLOCKS_SPARSE 3
 #endif
 
 
@@ -221,6 +223,12 @@ struct K1Args {
 	int x_block;                   // primaries per rank: owner = p / x_block, index there = p % x_block
 	char *const *x_peers;          // [world] base of every rank's exchange buffer (device array; own rank: local)
 	long long x_cnt_off, x_slot_off, x_spill_off, x_spillcnt_off;   // byte offsets of this catalogue's areas in the exchange buffer
+	// sparse primaries, two-kernel stream (k_filter + k_pairs over the survivors): surv_mode 1 = take the sources from the
+	// survivor list (do nothing if it overflowed), 2 = the direct stream as the fallback (do nothing unless it overflowed)
+	int surv_mode;
+	const int *surv;
+	const unsigned long long *surv_n;
+	long long surv_cap;
 };
 
 // exact fp64 separation for `count` (<= 32) queued candidates, one per lane; a match takes the next slot of its
@@ -353,6 +361,69 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 	qn += __popc(m);
 }
 
+// Sparse primaries (an all-sky match: a few per cent of the grid cells hold a primary), first of two kernels: the pure
+// stream.  One thread per source: coordinates -> cell -> one bit of the occupancy bitmap; the sources whose cell is
+// occupied are appended to a survivor list (warp-aggregated: one atomicAdd per warp and batch), which k_pairs then
+// works through.  No queues, no exact stage, ~32 registers: every SM runs full of warps and the kernel streams the
+// catalogue at HBM speed -- where the one-kernel stream carries the register budget of the exact stage through all of
+// it (BASELINE.json configs[4]: 3e8 sources, 97 % of which end at their bitmap bit).
+constexpr int KF_SBANDS = 2560;   // bands cached in shared memory (40 KB + 10 KB)
+
+__global__ void __launch_bounds__(256)
+k_filter(int n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G, int *__restrict__ surv,
+	unsigned long long *__restrict__ surv_n, long long surv_cap)
+{
+	__shared__ int4 sbands[KF_SBANDS];
+	const bool bands_in_smem = G.nbands <= KF_SBANDS;
+	if (bands_in_smem) {
+		for (int b = threadIdx.x; b < G.nbands; b += blockDim.x) sbands[b] = __ldg(reinterpret_cast<const int4 *>(G.bands + b));
+		__syncthreads();
+	}
+	const int lane = threadIdx.x & 31;
+	const int stride = gridDim.x * blockDim.x;
+	const int nround = (n + 31) / 32 * 32;
+	const double nbands_d = (double) G.nbands;
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	double r_nxt = 0, d_nxt = 0;
+	if (i < n) { r_nxt = ra[i]; d_nxt = dec[i]; }
+	for (; i < nround; i += stride) {
+		const double r = r_nxt, d = d_nxt;
+		{
+			const int j = i + stride;
+			if (j < n) { r_nxt = ra[j]; d_nxt = dec[j]; }
+		}
+		bool keep = false;
+		if (i < n) {
+			const double t = k1_band_coord(G, d);
+			if (t >= 0.0 && t < nbands_d) {
+				const double x = k1_ra_coord(G, r);
+				if (G.full_circle || x <= G.ra_span) {
+					const int b = __double2int_rd(t);
+					BandRec B;
+					if (bands_in_smem) {
+						const int4 v = sbands[b];
+						B.base = v.x; B.nra = v.y; B.inv_w = __hiloint2double(v.w, v.z);
+					} else {
+						B = load_band(G, b);
+					}
+					int ic;
+					k1_ra_cell(B, x, ic);
+					const int cell = B.base + ic;
+					keep = (__ldg(G.bits + (cell >> 5)) >> (cell & 31) & 1u) != 0u;
+				}
+			}
+		}
+		const unsigned m = __ballot_sync(NWB_FULL, keep);
+		if (m) {
+			unsigned long long base = 0;
+			if (lane == 0) base = atomicAdd(surv_n, (unsigned long long) __popc(m));
+			base = __shfl_sync(NWB_FULL, base, 0);
+			const unsigned long long pos = base + __popc(m & ((1u << lane) - 1));
+			if (keep && pos < (unsigned long long) surv_cap) surv[pos] = i;
+		}
+	}
+}
+
 // One thread per secondary source, coalesced loads of (ra, dec): 16 algorithmic bytes per source, the next batch
 // prefetched while the current one is processed.  The kernel lives on L2 -> SM sector traffic (every lookup is a random
 // 32-byte sector), so the data is laid out to need few of them:
@@ -392,22 +463,38 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 	int nit = 0, qn = 0;   // warp-uniform fill levels of the two lists; both below 32 at the top of the loop
 	// 32-bit indices: the host guarantees n + (one wave of threads) < 2^31 (secondary indices are ints in the slots anyway)
 	const int stride = gridDim.x * blockDim.x;
+	// sparse primaries: the sources may come from the survivor list of k_filter (the ~3 % whose grid cell holds a primary)
+	const bool indirect = !DENSE && A.surv_mode == 1;
+	if (!DENSE && A.surv_mode != 0) {
+		const unsigned long long ns = *A.surv_n;
+		if (indirect ? ns > (unsigned long long) A.surv_cap : ns <= (unsigned long long) A.surv_cap) return;
+		if (indirect) n = (int) ns;
+	}
 	const int nround = (n + 31) / 32 * 32;
 	const double nbands_d = (double) G.nbands;
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	int j0 = blockIdx.x * blockDim.x + threadIdx.x;   // position in the stream (or in the survivor list)
+	int i_nxt = j0;
 	double r_nxt = 0, d_nxt = 0;
-	if (i < n) { r_nxt = ra[i]; d_nxt = dec[i]; }
-	for (; i < nround; i += stride) {
-		const bool last = i + stride >= nround;   // this warp's final batch: the lists are drained completely
+	if (j0 < n) {
+		if (indirect) i_nxt = __ldg(A.surv + j0);
+		r_nxt = ra[i_nxt]; d_nxt = dec[i_nxt];
+	}
+	for (; j0 < nround; j0 += stride) {
+		const bool last = j0 + stride >= nround;   // this warp's final batch: the lists are drained completely
 		const double r = r_nxt, d = d_nxt;
+		const int i = indirect ? i_nxt : j0;        // the source's index in its catalogue
+		const bool live = j0 < n;
 		{
-			const int j = i + stride;   // software prefetch of the next batch: hides the DRAM latency
-			if (j < n) { r_nxt = ra[j]; d_nxt = dec[j]; }
+			const int j = j0 + stride;   // software prefetch of the next batch: hides the DRAM latency
+			if (j < n) {
+				i_nxt = indirect ? __ldg(A.surv + j) : j;
+				r_nxt = ra[i_nxt]; d_nxt = dec[i_nxt];
+			}
 		}
 		int ecnt = 0, estart = 0;
 		unsigned long long e0 = 0, e1 = 0, e2 = 0;
 		float xr = 0.f, yr = 0.f, kx = 0.f;
-		if (i < n) {
+		if (live) {
 			const double t = k1_band_coord(G, d);
 			if (t >= 0.0 && t < nbands_d) {
 				const double x = k1_ra_coord(G, r);

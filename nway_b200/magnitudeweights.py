@@ -32,17 +32,18 @@ def fitfunc_histogram(bin_mag, hist_sel, hist_all):
 	return scipy.interpolate.interp1d(bin_mag, list(y) + [y[-1]], bounds_error=False, kind='zero')
 
 
-def auto_histogram_device(ctx, c, k, magdtype, mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue, cli=False):
+def auto_histogram_device(ctx, c, k, magdtype, mag_include_radius, mag_exclude_radius, magauto_post_single_minvalue, cli=False, rows=None):
 	"""The automatic histogram of one magnitude column (nwaylib/__init__.py:324-366, magnitudeweights.py:90-118) with the
 	row / catalogue-sized work on the device: the selection of secure counterparts, first-occurrence unique, the
 	reference's weight indexing and the field-source histogram run in nwb_maghist_select /
 	nwb_maghist_count; the host only sees the compact sample of selected sources and builds the <= 17 quantile bins from
 	it.  magdtype: dtype of the caller's magnitude column (the reference bins in that dtype: float32 quantile edges
-	differ from float64 ones).  Returns bins, hist_sel, hist_all, n_secure, n_possible, n_others."""
+	differ from float64 ones).  rows: select from these device columns (all shards' rows, see Context.maghist_select)
+	instead of the context's own table.  Returns bins, hist_sel, hist_all, n_secure, n_possible, n_others."""
 	if mag_include_radius is not None:
-		mag_sel, w, (npossible, nothers, nvalid), (lo, hi) = ctx.maghist_select(c, k, True, mag_include_radius, mag_exclude_radius, cli)
+		mag_sel, w, (npossible, nothers, nvalid), (lo, hi) = ctx.maghist_select(c, k, True, mag_include_radius, mag_exclude_radius, cli, rows)
 	else:
-		mag_sel, w, (npossible, nothers, nvalid), (lo, hi) = ctx.maghist_select(c, k, False, magauto_post_single_minvalue, 0.01, cli)
+		mag_sel, w, (npossible, nothers, nvalid), (lo, hi) = ctx.maghist_select(c, k, False, magauto_post_single_minvalue, 0.01, cli, rows)
 	assert len(mag_sel) > 0, 'No magnitude values within radius.'
 	magdtype = numpy.dtype(magdtype)
 	if magdtype.kind != 'f':

@@ -137,22 +137,42 @@ def nway_match_sharded(match_tables, match_radius, prior_completeness, gather='a
 	  'all'   every rank returns the complete table (one unpadded all-gather-v straight from the context's columns),
 	  'rank0' ranks send their shard to rank 0 (returns the table there, None elsewhere),
 	  'none'  every rank returns only its own shard plus (counts, offsets) to place it.
-	Automatic magnitude histograms (maghists=None) need the global first pass and are not supported here:
-	supply the histograms."""
+	Automatic magnitude histograms (maghists=None) are selected from the rows of ALL shards: between the two passes
+	every rank gathers three columns of the whole table (hist_rows below) and derives the same histogram from them, as
+	the single-device match does from its own rows (nwaylib/__init__.py:324-375)."""
 	import torch
 	import torch.distributed as dist
 	from . import nway_match, _lib, _column_names
-	for t in match_tables:
-		if any(h is None for h in t.get('maghists', [])):
-			raise NotImplementedError('automatic magnitude histograms are a global step; supply maghists in sharded mode')
 	rank, world = dist.get_rank(group), dist.get_world_size(group)
 	if device is None:
 		device = torch.cuda.current_device()
 	first, count = shard_range(len(match_tables[0]['ra']), rank, world)
 	kwargs['as_frame'] = False
 	kwargs['keep_on_device'] = True
+	ncat = len(match_tables)
+	held = []
+
+	def hist_rows(ctx, c):
+		"""the columns the automatic histogram of catalogue c is selected from: index of c, Separation_max and dist_post
+		of ALL shards in global row order (one small all-gather-v) -- the selection is a property of the whole table:
+		first occurrence of a source over all rows, the reference's weight indexing (nwaylib/__init__.py:324-366)"""
+		base, stride, ncols, nrows = ctx.table_layout()
+		dev = torch.device('cuda', device)
+		counts = exchange_counts(nrows, group, dev)
+		npairs = ncat * (ncat - 1) // 2
+		pick = [c, ncat + npairs, ncat + npairs + 4]   # <name_c>, Separation_max, dist_post in the table's column order
+		view = ctx.table_view()
+		local3 = torch.stack([view[k] for k in pick]) if nrows else torch.empty((3, 0), dtype=torch.int64, device=dev)
+		torch.cuda.current_stream(dev).synchronize()
+		ctx.sync()
+		full = allgather_table(local3, counts, group)
+		torch.cuda.current_stream(dev).synchronize()
+		held.append(full)   # stays alive while the library reads it
+		return (full.shape[1], full[0].data_ptr(), full[1].data_ptr(), full[2].data_ptr())
+
+	auto = any(h is None for t in match_tables for h in t.get('maghists', []))
 	local = nway_match(match_tables, match_radius, prior_completeness, primary_range=(first, count), device=device,
-		allow_empty=True, **kwargs)
+		allow_empty=True, hist_rows=hist_rows if auto else None, **kwargs)
 	nrows = local['nrows']
 	dev = torch.device('cuda', device)
 	counts = exchange_counts(nrows, group, dev)

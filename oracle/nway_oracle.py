@@ -47,10 +47,43 @@ def dist(apos, bpos):
 	return np.arctan2(np.hypot(y1, y2), x) * 180 / np.pi
 
 
+def offsets_skyoffsetframe(apos, bpos):
+	"""(dra, ddec) in degrees as fastskymatch.dist3d forms them (fastskymatch.py:50-74), following astropy's OWN algorithm
+	step by step -- astropy (un-vendored, unpinned: pyproject.toml) is absent here, so this restates its published code
+	path: SkyOffsetFrame(origin=a) turns ICRS into the offset frame with the matrix
+	    R_x(-rotation = 0) @ R_y(-lat_a) @ R_z(lon_a)
+	(astropy/coordinates/builtin_frames/skyoffset.py, reference_to_skyoffset; rotation_matrix(angle, axis) of
+	astropy/coordinates/matrix_utilities.py: R_z = [[c, s, 0], [-s, c, 0], [0, 0, 1]], R_y = [[c, 0, -s], [0, 1, 0],
+	[s, 0, c]]) applied to the unit vector (cos d cos a, cos d sin a, sin d); back to angles with
+	UnitSphericalRepresentation.from_cartesian: lon = atan2(y, x), lat = atan2(z, hypot(x, y)); the frame's longitude wraps
+	at 180 degrees.  dist3d then takes dra = na.lon - nb.lon, ddec = na.lat - nb.lat with na = the origin in its own frame
+	(0 up to rounding -- kept, as the reference keeps it).  tests/test_oracle_golden.py holds offsets() -- the closed
+	form the device evaluates -- against this to 1e-10 arcsec everywhere on the sphere."""
+	def to_frame(lon0, lat0, lon, lat):
+		c0, s0 = np.cos(lon0), np.sin(lon0)
+		cl, sl = np.cos(-lat0), np.sin(-lat0)
+		rz = np.array([[c0, s0, 0 * c0], [-s0, c0, 0 * c0], [0 * c0, 0 * c0, 1 + 0 * c0]])
+		ry = np.array([[cl, 0 * cl, -sl], [0 * cl, 1 + 0 * cl, 0 * cl], [sl, 0 * cl, cl]])
+		m = np.einsum('ij...,jk...->ik...', ry, rz)
+		v = np.array([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)])
+		x, y, z = np.einsum('ij...,j...->i...', m, v)
+		lon_f = np.degrees(np.arctan2(y, x))
+		lon_f = np.where(lon_f >= 180, lon_f - 360, lon_f)
+		return lon_f, np.degrees(np.arctan2(z, np.hypot(x, y)))
+	ra1, dec1 = np.radians(apos[0]), np.radians(apos[1])
+	ra2, dec2 = np.radians(bpos[0]), np.radians(bpos[1])
+	ra1, dec1, ra2, dec2 = np.broadcast_arrays(ra1, dec1, ra2, dec2)
+	na_lon, na_lat = to_frame(ra1, dec1, ra1, dec1)
+	nb_lon, nb_lat = to_frame(ra1, dec1, ra2, dec2)
+	return na_lon - nb_lon, na_lat - nb_lat
+
+
 def offsets(apos, bpos):
 	"""(separation, dra, ddec) in degrees: what astropy's SkyOffsetFrame(origin=a) gives
-	for b (fastskymatch.py:50-74 -> un-vendored astropy; closed form of SURVEY Appendix A.6).
-	PARITY UNPINNED for this function: astropy is absent here and no reference test pins it."""
+	for b (fastskymatch.py:50-74 -> un-vendored astropy; closed form of SURVEY Appendix A.6: the product of the two
+	rotations of offsets_skyoffsetframe() written out).  Pinned to that restatement of astropy's algorithm, not to
+	astropy's output: astropy is absent here and no reference test pins dist3d (the command-line program rounds these
+	offsets to float32 before use, 6e-8 relative; the two forms differ by ~1e-11 arcsec)."""
 	ra1, dec1 = np.radians(apos[0]), np.radians(apos[1])
 	ra2, dec2 = np.radians(bpos[0]), np.radians(bpos[1])
 	dl = ra2 - ra1

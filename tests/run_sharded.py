@@ -29,6 +29,16 @@ def main():
 	lo = offsets[rank]
 	for k in full:
 		assert np.array_equal(shard[k], full[k][lo:lo + counts[rank]], equal_nan=True), k
+	# automatic magnitude histograms in sharded mode: selected from the gathered rows of all shards -- the same table as
+	# on one device, by radius and by posterior (the reference's two modes, nwaylib/__init__.py:324-375)
+	synthetic = lambda: cases.with_mags(cases.uniform_patch(14, (900, 30000, 20000), (1.0, 0.4, 0.6), 0.12), 5, cats=(1, 2), hist=False)
+	cosmos = lambda: cases.cosmos_subset(3, mags=True)   # BASELINE.json configs[1]: both priors automatic, selected by posterior
+	for auto, radius, kw in ((synthetic, 7.0, dict(mag_include_radius=3.0)), (cosmos, 20.0, dict()), (cosmos, 20.0, dict(mag_include_radius=4.0))):
+		one = nway_b200.nway_match(auto(), radius, 0.9, logger=nway_b200.NullOutputLogger(), as_frame=False, device=local, store_mag_hists=False, **kw)
+		two = parallel.nway_match_sharded(auto(), radius, 0.9, gather='all', device=local, logger=nway_b200.NullOutputLogger(), store_mag_hists=False, **kw)
+		assert list(one.keys()) == list(two.keys())
+		for k in one:
+			assert np.array_equal(two[k], one[k], equal_nan=True), ('auto histograms', sorted(kw), k)
 	# the other multi-GPU mode: the ranks share the streaming of the secondaries, matches travel to the owner of the
 	# primary over peer memory (nwb_shard_*); same table, bit for bit
 	got2 = parallel.nway_match_scatter(tables, 7.0, 0.9, gather='all', device=local, logger=nway_b200.NullOutputLogger())
