@@ -233,9 +233,11 @@ int nwb_sync(nwb_ctx *ctx);
 
 /* Measurement only: run the memory-system skeleton of the streaming kernel k_pairs for secondary catalogue c on the
  * grid the last nwb_match left -- the same coalesced stream, cell-record gather, primary-record gather, slot atomicAdd
- * and slot store, none of the arithmetic -- `reps` times and return the mean duration.  The floor
- * the access pattern puts under k_pairs; bench.py reports it next to the kernel.  Invalidates the match result. */
-int nwb_bench_skeleton(nwb_ctx *ctx, int c, int reps, float *ms);
+ * and slot store, none of the arithmetic -- `reps` times and return the mean duration.  blocks_per_sm:
+ * resident blocks per SM to run it at (0 = as many as the match kernel of the last nwb_match had: the skeleton needs fewer
+ * registers, and more resident warps make this access pattern slower, not faster).  bench.py reports it next to the kernel.
+ * Invalidates the match result. */
+int nwb_bench_skeleton(nwb_ctx *ctx, int c, int reps, int blocks_per_sm, float *ms);
 
 /* per-stage device time of the last nwb_match (+ nwb_finalize), and how many kernels it launched */
 int nwb_timing(nwb_ctx *ctx, int stage, float *ms);

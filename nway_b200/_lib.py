@@ -62,7 +62,7 @@ EXPORTS = {
 	'nwb_sync': (ctypes.c_int, [ctypes.c_void_p]),
 	'nwb_timing': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
 	'nwb_launch_count': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
-	'nwb_bench_skeleton': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
+	'nwb_bench_skeleton': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
 	'nwb_stats': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
 	'nwb_dist': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
 	'nwb_log_bf': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
@@ -200,10 +200,11 @@ class Context(object):
 	def set_compat(self, flags):
 		self.check(self.lib.nwb_set_compat(self.h, int(flags)))
 
-	def bench_skeleton(self, c=1, reps=5):
-		"""mean duration (ms) of the memory-system skeleton of k_pairs on the grid of the last match (invalidates its result)"""
+	def bench_skeleton(self, c=1, reps=5, blocks_per_sm=0):
+		"""mean duration (ms) of the memory-system skeleton of k_pairs on the grid of the last match (invalidates its result);
+		blocks_per_sm = 0: at the residency of the match kernel"""
 		v = ctypes.c_float(0)
-		self.check(self.lib.nwb_bench_skeleton(self.h, int(c), int(reps), ctypes.byref(v)))
+		self.check(self.lib.nwb_bench_skeleton(self.h, int(c), int(reps), int(blocks_per_sm), ctypes.byref(v)))
 		return float(v.value)
 
 	def table_layout(self):

@@ -106,7 +106,7 @@ struct nwb_ctx {
 	size_t entries_cap = 0;
 	unsigned long long spill_cap = 0;
 	long long *h_status = nullptr;   // pinned
-	int k1_occ[16] = {0}, num_sms = 0, filter_occ = 0;   // resident blocks per SM of every k_pairs instantiation
+	int k1_occ[16] = {0}, num_sms = 0, filter_occ = 0, skel_blocks = 0;   // resident blocks per SM of every k_pairs instantiation
 	// grid geometry of the previous match, re-used when the primaries' bounding box and the radius are unchanged
 	bool geom_valid = false;
 	double geom_rb = 0;
@@ -397,10 +397,28 @@ int launch_pairs(nwb_ctx *ctx, bool dense, bool flat, bool skel, bool scat, int 
 #undef NWB_OCC
 		ctx->k1_occ[which] = std::max(nb, 1);
 	}
-	const int grid = (int) std::max<int64_t>(1, std::min<int64_t>(((int64_t) n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), (int64_t) ctx->num_sms * ctx->k1_occ[which]));
+	int occ = ctx->k1_occ[which];
+	size_t dyn = 0;
+	if (skel && ctx->skel_blocks > 0 && ctx->skel_blocks < occ) {
+		// the skeleton at the residency of the kernel it is compared with: it needs fewer registers, and MORE resident warps
+		// make this access pattern slower, not faster (profiles/r02_kpairs_variants.txt) -- dynamic shared memory it never
+		// touches caps the blocks per SM
+		occ = ctx->skel_blocks;
+		cudaFuncAttributes fa;
+		if (dense) CU(cudaFuncGetAttributes(&fa, k_pairs<true, false, true, false>)); else CU(cudaFuncGetAttributes(&fa, k_pairs<false, false, true, false>));
+		const size_t per_block = (size_t) 227 * 1024 / (size_t) occ;
+		if (per_block > fa.sharedSizeBytes + 2048) dyn = per_block - fa.sharedSizeBytes - 1024;
+		if (dense) CU(cudaFuncSetAttribute(k_pairs<true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
+		else CU(cudaFuncSetAttribute(k_pairs<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
+	}
+	const int grid = (int) std::max<int64_t>(1, std::min<int64_t>(((int64_t) n + K1_WARPS * 32 - 1) / (K1_WARPS * 32), (int64_t) ctx->num_sms * occ));
 	if ((int64_t) n + (int64_t) ka.s_base + (int64_t) grid * K1_WARPS * 32 + 64 > 0x7fffffffll)
 		return fail(ctx, NWB_ERR_ARG, "catalogue too large: secondary indices are 32-bit");
-#define NWB_KP(D, F, S, X) LAUNCH(ctx, (k_pairs<D, F, S, X>), grid, K1_WARPS * 32, n, ra, dec, G, etotal, cells, entries, entries_cap, ka)
+#define NWB_KP(D, F, S, X) do { \
+	k_pairs<D, F, S, X><<<grid, K1_WARPS * 32, dyn, ctx->stream>>>(n, ra, dec, G, etotal, cells, entries, entries_cap, ka); \
+	ctx->launches++; \
+	cudaError_t e_ = cudaGetLastError(); \
+	if (e_ != cudaSuccess) return fail(ctx, NWB_ERR_CUDA, std::string("k_pairs: ") + cudaGetErrorString(e_)); } while (0)
 	NWB_KP_DISPATCH(NWB_KP)
 #undef NWB_KP
 #undef NWB_KP_DISPATCH
@@ -655,6 +673,8 @@ static int run_final(nwb_ctx *ctx)
 {
 	int grid = (int) std::min<int64_t>((ctx->np * 32 + 255) / 256, 148 * 64);
 	grid = std::max(grid, 1);
+	// groups of a few rows (sparse primaries): one thread each; the warp-per-primary kernel takes the rest
+	if (ctx->rp.small_t > 0) LAUNCH(ctx, k_final_small, (int) ((ctx->np + 127) / 128), 128, ctx->rp);
 	LAUNCH(ctx, k_final, grid, 256, ctx->rp);
 	return NWB_OK;
 }
@@ -956,7 +976,9 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			const bool two_kernels = G.bits && s_count >= (1 << 20) && ctx->geom_occ < 0.2;
 			if (two_kernels && s_count > 0) {
 				const long long cap = (long long) std::min<double>((double) s_count, (double) s_count * (3.0 * ctx->geom_occ + 0.02) + 4096.0);
-				ENSURE(ctx->d_surv, (size_t) cap * sizeof(int));
+				ENSURE(ctx->d_surv, (size_t) cap * (sizeof(int) + sizeof(double2)) + 256);
+				double2 *d_surv_rd = (double2 *) ctx->d_surv.p;   // coordinates first (16-byte aligned), indices behind
+				int *d_surv_idx = (int *) (d_surv_rd + cap);
 				if (ctx->filter_occ <= 0) {
 					int nb = 0, nsm = 0;
 					CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_filter, 256, 0));
@@ -965,8 +987,8 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 					ctx->num_sms = std::max(nsm, 1);
 				}
 				LAUNCH(ctx, k_filter, ctx->num_sms * ctx->filter_occ, 256, (int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
-					(int *) ctx->d_surv.p, d_survn + c, cap);
-				ka.surv = (const int *) ctx->d_surv.p; ka.surv_n = d_survn + c; ka.surv_cap = cap;
+					d_surv_idx, d_surv_rd, d_survn + c, cap);
+				ka.surv = d_surv_idx; ka.surv_rd = d_surv_rd; ka.surv_n = d_survn + c; ka.surv_cap = cap;
 				for (int mode = 1; mode <= 2; mode++) {
 					ka.surv_mode = mode;
 					int r = launch_pairs(ctx, false, flat_err > 0.0, false, shard, (int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
@@ -1607,7 +1629,7 @@ int nwb_timing(nwb_ctx *ctx, int stage, float *ms)
 	return NWB_OK;
 }
 
-int nwb_bench_skeleton(nwb_ctx *ctx, int c, int reps, float *ms)
+int nwb_bench_skeleton(nwb_ctx *ctx, int c, int reps, int blocks_per_sm, float *ms)
 {
 	if (!ctx || !ms) return NWB_ERR_ARG;
 	if (!ctx->matched) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
@@ -1616,6 +1638,11 @@ int nwb_bench_skeleton(nwb_ctx *ctx, int c, int reps, float *ms)
 	cudaStream_t st = ctx->stream;
 	const Grid G = ctx->geom_G;
 	K1Args ka = ctx->last_k1[c];
+	{
+		// residency of the match kernel the skeleton is compared with (the instantiation the last match used)
+		const int which = (ctx->last_k1_dense ? 1 : 0) | (ctx->flat_err > 0.0 ? 2 : 0);
+		ctx->skel_blocks = blocks_per_sm > 0 ? blocks_per_sm : ctx->k1_occ[which];
+	}
 	// the skeleton takes its slots from a counter array of its own; the slot area it scribbles over is the match's
 	ENSURE(ctx->d_misc, (size_t) (ctx->np + 1) * sizeof(int));
 	ka.cnt = (int *) ctx->d_misc.p;

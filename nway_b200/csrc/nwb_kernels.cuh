@@ -226,7 +226,8 @@ struct K1Args {
 	// sparse primaries, two-kernel stream (k_filter + k_pairs over the survivors): surv_mode 1 = take the sources from the
 	// survivor list (do nothing if it overflowed), 2 = the direct stream as the fallback (do nothing unless it overflowed)
 	int surv_mode;
-	const int *surv;
+	const int *surv;               // survivors: catalogue indices ...
+	const double2 *surv_rd;        // ... and their (ra, dec), compact: k_pairs reads them coalesced
 	const unsigned long long *surv_n;
 	long long surv_cap;
 };
@@ -367,59 +368,90 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 // works through.  No queues, no exact stage, ~32 registers: every SM runs full of warps and the kernel streams the
 // catalogue at HBM speed -- where the one-kernel stream carries the register budget of the exact stage through all of
 // it (BASELINE.json configs[4]: 3e8 sources, 97 % of which end at their bitmap bit).
-constexpr int KF_SBANDS = 2560;   // bands cached in shared memory (40 KB + 10 KB)
+// The band table and the bitmap are read through L1 (__ldg): with only a small survivor buffer in shared memory the SM
+// keeps most of its 228 KB as L1, which then holds both (a few tens of KB of band records, ncells / 8 bytes of bitmap)
+// -- the bitmap look-up, the one dependent access of the stream, becomes an L1 hit instead of an L2 round trip.  Two
+// sources per thread and iteration, the next iteration's four loads issued before the current one is processed: ~64 KB
+// of coordinates in flight per SM, enough for the HBM latency-bandwidth product.
+constexpr int KF_BUF = 1024;      // survivors (index + coordinates: 20 KB) a block collects in shared memory before it appends them to the global list
+constexpr int KF_U = 2;           // sources per thread and iteration
+
+__device__ __forceinline__ bool kf_occupied(const Grid &G, double r, double d, double nbands_d)
+{
+	const double t = k1_band_coord(G, d);
+	if (!(t >= 0.0 && t < nbands_d)) return false;
+	const double x = k1_ra_coord(G, r);
+	if (!(G.full_circle || x <= G.ra_span)) return false;
+	const BandRec B = load_band(G, __double2int_rd(t));
+	int ic;
+	k1_ra_cell(B, x, ic);
+	const int cell = B.base + ic;
+	return (__ldg(G.bits + (cell >> 5)) >> (cell & 31) & 1u) != 0u;
+}
 
 __global__ void __launch_bounds__(256)
 k_filter(int n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G, int *__restrict__ surv,
-	unsigned long long *__restrict__ surv_n, long long surv_cap)
+	double2 *__restrict__ surv_rd, unsigned long long *__restrict__ surv_n, long long surv_cap)
 {
-	__shared__ int4 sbands[KF_SBANDS];
-	const bool bands_in_smem = G.nbands <= KF_SBANDS;
-	if (bands_in_smem) {
-		for (int b = threadIdx.x; b < G.nbands; b += blockDim.x) sbands[b] = __ldg(reinterpret_cast<const int4 *>(G.bands + b));
-		__syncthreads();
-	}
+	__shared__ int buf[KF_BUF];
+	__shared__ double2 buf_rd[KF_BUF];
+	__shared__ int nbuf;
+	__shared__ unsigned long long gbase;
+	if (threadIdx.x == 0) nbuf = 0;
+	__syncthreads();
 	const int lane = threadIdx.x & 31;
-	const int stride = gridDim.x * blockDim.x;
-	const int nround = (n + 31) / 32 * 32;
+	const int chunk = (int) blockDim.x * KF_U;                 // sources per block and iteration
+	const long long stride = (long long) gridDim.x * chunk;
+	const long long nround = ((long long) n + chunk - 1) / chunk * chunk;   // whole chunks: every thread reaches the barriers
 	const double nbands_d = (double) G.nbands;
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	double r_nxt = 0, d_nxt = 0;
-	if (i < n) { r_nxt = ra[i]; d_nxt = dec[i]; }
-	for (; i < nround; i += stride) {
-		const double r = r_nxt, d = d_nxt;
-		{
-			const int j = i + stride;
-			if (j < n) { r_nxt = ra[j]; d_nxt = dec[j]; }
+	long long base = (long long) blockIdx.x * chunk;
+	double r_nxt[KF_U], d_nxt[KF_U];
+#pragma unroll
+	for (int u = 0; u < KF_U; u++) {
+		const long long i = base + u * (int) blockDim.x + threadIdx.x;
+		r_nxt[u] = 0; d_nxt[u] = 0;
+		if (i < n) { r_nxt[u] = ra[i]; d_nxt[u] = dec[i]; }
+	}
+	for (; base < nround; base += stride) {
+		double r[KF_U], d[KF_U];
+#pragma unroll
+		for (int u = 0; u < KF_U; u++) { r[u] = r_nxt[u]; d[u] = d_nxt[u]; }
+#pragma unroll
+		for (int u = 0; u < KF_U; u++) {
+			const long long j = base + stride + u * (int) blockDim.x + threadIdx.x;
+			if (j < n) { r_nxt[u] = ra[j]; d_nxt[u] = dec[j]; }
 		}
-		bool keep = false;
-		if (i < n) {
-			const double t = k1_band_coord(G, d);
-			if (t >= 0.0 && t < nbands_d) {
-				const double x = k1_ra_coord(G, r);
-				if (G.full_circle || x <= G.ra_span) {
-					const int b = __double2int_rd(t);
-					BandRec B;
-					if (bands_in_smem) {
-						const int4 v = sbands[b];
-						B.base = v.x; B.nra = v.y; B.inv_w = __hiloint2double(v.w, v.z);
-					} else {
-						B = load_band(G, b);
-					}
-					int ic;
-					k1_ra_cell(B, x, ic);
-					const int cell = B.base + ic;
-					keep = (__ldg(G.bits + (cell >> 5)) >> (cell & 31) & 1u) != 0u;
+#pragma unroll
+		for (int u = 0; u < KF_U; u++) {
+			const long long i = base + u * (int) blockDim.x + threadIdx.x;
+			const bool keep = i < n && kf_occupied(G, r[u], d[u], nbands_d);
+			// into the block's buffer: one shared-memory atomicAdd per warp that has survivors
+			const unsigned m = __ballot_sync(NWB_FULL, keep);
+			if (m) {
+				int pos = 0;
+				if (lane == 0) pos = atomicAdd(&nbuf, __popc(m));
+				pos = __shfl_sync(NWB_FULL, pos, 0);
+				if (keep) {
+					const int q = pos + __popc(m & ((1u << lane) - 1));
+					buf[q] = (int) i;
+					buf_rd[q] = make_double2(r[u], d[u]);
 				}
 			}
 		}
-		const unsigned m = __ballot_sync(NWB_FULL, keep);
-		if (m) {
-			unsigned long long base = 0;
-			if (lane == 0) base = atomicAdd(surv_n, (unsigned long long) __popc(m));
-			base = __shfl_sync(NWB_FULL, base, 0);
-			const unsigned long long pos = base + __popc(m & ((1u << lane) - 1));
-			if (keep && pos < (unsigned long long) surv_cap) surv[pos] = i;
+		__syncthreads();
+		const int have = nbuf;
+		__syncthreads();   // nobody adds to nbuf again before everybody has read it: `have` is block-uniform
+		const bool last = base + stride >= nround;   // block-uniform
+		if (have > KF_BUF - chunk || (last && have > 0)) {
+			// append the buffer to the global list: ONE global atomicAdd per several hundred survivors, coalesced stores
+			if (threadIdx.x == 0) gbase = atomicAdd(surv_n, (unsigned long long) have);
+			__syncthreads();
+			const unsigned long long g = gbase;
+			for (int k = threadIdx.x; k < have; k += blockDim.x)
+				if (g + k < (unsigned long long) surv_cap) { surv[g + k] = buf[k]; surv_rd[g + k] = buf_rd[k]; }
+			__syncthreads();
+			if (threadIdx.x == 0) nbuf = 0;
+			__syncthreads();
 		}
 	}
 }
@@ -476,8 +508,13 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 	int i_nxt = j0;
 	double r_nxt = 0, d_nxt = 0;
 	if (j0 < n) {
-		if (indirect) i_nxt = __ldg(A.surv + j0);
-		r_nxt = ra[i_nxt]; d_nxt = dec[i_nxt];
+		if (indirect) {
+			i_nxt = __ldg(A.surv + j0);
+			const double2 rd = __ldg(A.surv_rd + j0);
+			r_nxt = rd.x; d_nxt = rd.y;
+		} else {
+			r_nxt = ra[j0]; d_nxt = dec[j0];
+		}
 	}
 	for (; j0 < nround; j0 += stride) {
 		const bool last = j0 + stride >= nround;   // this warp's final batch: the lists are drained completely
@@ -487,8 +524,13 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 		{
 			const int j = j0 + stride;   // software prefetch of the next batch: hides the DRAM latency
 			if (j < n) {
-				i_nxt = indirect ? __ldg(A.surv + j) : j;
-				r_nxt = ra[i_nxt]; d_nxt = dec[i_nxt];
+				if (indirect) {
+					i_nxt = __ldg(A.surv + j);
+					const double2 rd = __ldg(A.surv_rd + j);
+					r_nxt = rd.x; d_nxt = rd.y;
+				} else {
+					r_nxt = ra[j]; d_nxt = dec[j];
+				}
 			}
 		}
 		int ecnt = 0, estart = 0;
@@ -1547,6 +1589,7 @@ k_final(RowParams R)
 	const ConstTables *__restrict__ T = R.T;
 	for (int p = warp; p < R.np; p += nwarps) {
 		long long r0 = R.row_off[p], n = R.row_off[p + 1] - r0;
+		if (n <= R.small_t) continue;   // k_final_small's
 		for (long long k = lane; k < n; k += 32) {
 			long long row = r0 + k;
 			long long sidx[MAXC];
@@ -1565,6 +1608,59 @@ k_final(RowParams R)
 	}
 }
 
+// K3 for sparse primaries: ONE THREAD per primary with at most R.small_t rows (see k_rows_small): an all-sky match leaves
+// ~99 % of the groups with nothing but their no-counterpart row, for which a warp per primary is 31 idle lanes behind a
+// chain of dependent loads.  Same formulas (__init__.py:423-457), scalar.
+__global__ void __launch_bounds__(128)
+k_final_small(RowParams R)
+{
+	if (!gate_open(R.gate)) return;
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= R.np) return;
+	const ConstTables *__restrict__ T = R.T;
+	const long long r0 = R.row_off[p];
+	const int n = (int) min((long long) (SMALL_T + 1), R.row_off[p + 1] - r0);
+	if (n > R.small_t || n <= 0) return;
+	double v[SMALL_T];
+	for (int k = 0; k < n; k++) {
+		const long long row = r0 + k;
+		long long sidx[MAXC];
+		unsigned smask = 0;
+		for (int c = 0; c < R.ncat; c++) {
+			sidx[c] = R.C.idx[c][row];
+			if (c > 0 && sidx[c] >= 0) smask |= 1u << (c - 1);
+		}
+		const double total = R.C.lbf[row] + row_bias(R, row, sidx);
+		const double prior = T->prior[smask], l10p = T->log10prior[smask];
+		R.C.p_single[row] = posterior_ref(prior, l10p, total);
+		v[k] = total + l10p;
+	}
+	double m_all = -INFINITY, m_rest = -INFINITY;
+	for (int k = 0; k < n; k++) {
+		m_all = fmax(m_all, v[k]);
+		if (k > 0) m_rest = fmax(m_rest, v[k]);
+	}
+	double s_all = 0.0, s_rest = 0.0;
+	for (int k = 0; k < n; k++) {
+		s_all += exp10(v[k] - m_all);
+		if (k > 0) s_rest += exp10(v[k] - m_rest);
+	}
+	const double bfsum = log10(s_all) + m_all;
+	const double bfsum1 = n > 1 ? log10(s_rest) + m_rest : 0.0;
+	const double p_any = 1 - exp10(v[0] - bfsum);
+	double best = 0.0;
+	for (int k = 1; k < n; k++) {
+		v[k] = exp10(v[k] - bfsum1);
+		best = fmax(best, v[k]);
+	}
+	v[0] = 0.0;
+	for (int k = 0; k < n; k++) {
+		R.C.p_i[r0 + k] = v[k];
+		R.C.p_any[r0 + k] = p_any;
+		R.C.flag[r0 + k] = (v[k] == best) ? 1 : (v[k] > R.ratio_secondary * best ? 2 : 0);
+	}
+}
+
 // K2b: the CLI's unrelated-association correction (nway.py:366-421), one warp per primary.
 // For every set M of >= 2 secondary catalogues: best(M) = max(0, max over rows j with ncat_j > 2 of
 // log_bf(sub-association M & present_j of row j) + log10(nu[A0]/prod nu_plus[A])), taken when the
@@ -1580,6 +1676,7 @@ __global__ void k_correct_cli(RowParams R)
 	const unsigned all = (1u << (nc - 1)) - 1;   // over secondaries, bit c-1
 	for (int p = warp; p < R.np; p += nwarps) {
 		long long r0 = R.row_off[p], n = R.row_off[p + 1] - r0;
+		if (n < 3) continue;   // a correction needs a row with two more secondaries than another (nway.py:380-400): none in a group of 1 or 2
 		for (unsigned M = 3; M <= all; M++) {
 			if (__popc(M) < 2) continue;
 			// does any row of the group miss exactly M?

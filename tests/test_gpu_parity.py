@@ -351,7 +351,7 @@ def test_speculative_pipeline_for_three_and_more_catalogues(ncat, mode):
 	sig = (1.0, 0.3, 0.5, 0.4)[:ncat]
 	a = cases.uniform_patch(61, sizes, sig, 0.3)                                   # sparse: at most a few matches per primary
 	b = cases.uniform_patch(62, (400,) + tuple(6 * n for n in sizes[1:]), sig, 0.3)   # six times denser: buffers outgrown
-	c = cases.uniform_patch(63, sizes, sig, 0.02)                                  # crowded: big groups
+	c = cases.uniform_patch(63, sizes, sig, 0.06 if ncat == 4 else 0.03)           # crowded: big groups
 	unrelated = _lib.UNRELATED_CLI if mode == 'cli' else _lib.UNRELATED_API
 
 	def load(ctx, tables):

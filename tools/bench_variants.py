@@ -75,11 +75,15 @@ def main():
 		stage = ctx.timings()
 		ctx.match(fuse_final=True)
 		skel = ctx.bench_skeleton(1, 10)
+		skel_by_blocks = {}
+		for b in (2, 3, 4, 5):
+			ctx.match(fuse_final=True)
+			skel_by_blocks[b] = ctx.bench_skeleton(1, 5, b)
 		n1 = len(sec['ra'])
 		pairs = rows - n0
 		kb = n1 * 16 + pairs * 16
 		print(json.dumps(dict(variant=name, flat=args.flat, rows=rows, step_ms=step_ms, rows_per_s=rows / (step_ms * 1e-3), stage_ms=stage,
-			k_pairs_ms=stage['k_pairs'], k_pairs_skeleton_ms=skel, k_pairs_vs_skeleton=stage['k_pairs'] / skel if skel else None,
+			k_pairs_ms=stage['k_pairs'], k_pairs_skeleton_ms=skel, skeleton_ms_by_blocks_per_sm=skel_by_blocks, k_pairs_vs_skeleton=stage['k_pairs'] / skel if skel else None,
 			k_pairs_GBs=kb / (stage['k_pairs'] * 1e-3) / 1e9, skeleton_GBs=kb / (skel * 1e-3) / 1e9)))
 		ctx.close()
 		del keep
