@@ -137,11 +137,13 @@ int nwb_set_primary_range(nwb_ctx *ctx, int64_t first, int64_t count);
  *   nwb_shard_setup    (after the catalogues and nwb_set_params) allocates this rank's exchange buffer and returns its
  *                      64-byte cudaIpcMemHandle; spill_capacity = matches beyond a primary's slots the buffer can hold
  *   nwb_shard_connect  takes all ranks' handles (world x 64 bytes, rank order; the caller all-gathers them) and opens them
- *   nwb_shard_match    one match in three phases with a barrier BETWEEN THE RANKS after phase 0 and after phase 1 (the
- *                      caller's: any stream-ordered collective on the context's stream): 0 = zero the own counters,
- *                      1 = grid + streaming (matches arrive from all ranks), 2 = rows of the own primaries.  Returns 1
- *                      from phase 2 when a buffer turned out too small: every rank has to repeat the match from phase 0
- *                      (the caller all-reduces the return codes).  world = 1 degenerates to an ordinary match.
+ *   nwb_shard_match    one match in two phases with ONE barrier between the ranks in between (the caller's: any stream-ordered
+ *                      collective on the context's stream): 1 = grid + streaming -- matches arrive from all ranks -- , 2 = rows
+ *                      of the own primaries.  The exchange buffer holds two sets of counters and slots: match e uses set
+ *                      e % 2 and zeroes the other one for its successor, which is what makes a single barrier enough.
+ *                      Phase 2 returns 1 when a grid buffer turned out too small: every rank sees the same (the primaries
+ *                      are replicated) and repeats phases 1 and 2.  Phase 0 resets both sets (after an aborted match; a
+ *                      barrier must follow).  world = 1 degenerates to an ordinary match.
  *   nwb_shard_close    leaves shard mode. */
 int nwb_shard_setup(nwb_ctx *ctx, int rank, int world, int64_t spill_capacity, void *ipc_handle_out, int64_t *exchange_bytes);
 int nwb_shard_connect(nwb_ctx *ctx, const void *ipc_handles);

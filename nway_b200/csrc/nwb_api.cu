@@ -73,6 +73,8 @@ struct nwb_ctx {
 		void *peer[16] = {nullptr};     // host copy; [rank] = xch.p, the others opened through cudaIpc
 		size_t off_cnt[MAXC] = {0}, off_slot[MAXC] = {0}, off_spill[MAXC] = {0}, off_spillcnt[MAXC] = {0};
 		size_t zero_bytes = 0, bytes = 0;   // counters + match counts come first: zeroed before every match
+		size_t set_bytes = 0;               // TWO such sets: match e uses set e % 2 while set (e + 1) % 2 is zeroed for the next one
+		long long epoch = 0;
 		int C[MAXC] = {0};
 		unsigned long long spill_cap = 0;
 	} shard;
@@ -884,7 +886,8 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 	unsigned long long *d_spillcount = (unsigned long long *) (d_cellcnt + (ncell1 + 3) / 4 * 4 + cnt_stride * (nc - 1));
 	int *d_etotal = (int *) (d_spillcount + 12);   // [0] overflow entries of the cell lists, [1] registrations, [2] K0 work list
 	unsigned long long *d_survn = (unsigned long long *) (d_etotal + 8);   // [c]: survivors of k_filter for catalogue c
-	char *xch = (char *) ctx->shard.xch.p;
+	const size_t xset = shard ? (size_t) (ctx->shard.epoch & 1) * ctx->shard.set_bytes : 0;   // this match's set of the exchange buffer
+	char *xch = (char *) ctx->shard.xch.p + xset;
 	if (shard) {   // match counters and spill counters of the own primaries live in the exchange buffer, where the peers write
 		for (int c = 1; c < nc; c++) d_cnt[c] = (int *) (xch + ctx->shard.off_cnt[c]);
 		d_spillcount = (unsigned long long *) (xch + ctx->shard.off_spillcnt[0]);
@@ -965,8 +968,8 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 				ka.s_base = (int) s_first;
 				ka.x_block = (int) ctx->shard.block;
 				ka.x_peers = (char *const *) ctx->shard.d_peers.p;
-				ka.x_cnt_off = (long long) ctx->shard.off_cnt[c]; ka.x_slot_off = (long long) ctx->shard.off_slot[c];
-				ka.x_spill_off = (long long) ctx->shard.off_spill[c]; ka.x_spillcnt_off = (long long) ctx->shard.off_spillcnt[c];
+				ka.x_cnt_off = (long long) (xset + ctx->shard.off_cnt[c]); ka.x_slot_off = (long long) (xset + ctx->shard.off_slot[c]);
+				ka.x_spill_off = (long long) (xset + ctx->shard.off_spill[c]); ka.x_spillcnt_off = (long long) (xset + ctx->shard.off_spillcnt[c]);
 			}
 			ctx->last_k1[c] = ka; ctx->last_k1_dense = G.nbands <= K1_SBANDS && !G.bits;
 			ctx->last_etotal = d_etotal;
@@ -975,10 +978,6 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			// (denser than estimated) the second k_pairs launch streams the catalogue directly; otherwise it does nothing.
 			const bool two_kernels = G.bits && s_count >= (1 << 20) && ctx->geom_occ < 0.2;
 			if (two_kernels && s_count > 0) {
-				const long long cap = (long long) std::min<double>((double) s_count, (double) s_count * (3.0 * ctx->geom_occ + 0.02) + 4096.0);
-				ENSURE(ctx->d_surv, (size_t) cap * (sizeof(int) + sizeof(double2)) + 256);
-				double2 *d_surv_rd = (double2 *) ctx->d_surv.p;   // coordinates first (16-byte aligned), indices behind
-				int *d_surv_idx = (int *) (d_surv_rd + cap);
 				if (ctx->filter_occ <= 0) {
 					int nb = 0, nsm = 0;
 					CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_filter, 256, 0));
@@ -986,9 +985,19 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 					ctx->filter_occ = std::max(nb, 1);
 					ctx->num_sms = std::max(nsm, 1);
 				}
-				LAUNCH(ctx, k_filter, ctx->num_sms * ctx->filter_occ, 256, (int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
-					d_surv_idx, d_surv_rd, d_survn + c, cap);
-				ka.surv = d_surv_idx; ka.surv_rd = d_surv_rd; ka.surv_n = d_survn + c; ka.surv_cap = cap;
+				// one segment of survivor records per block: expected survivors x 3 + a margin (the blocks stride evenly over the
+				// catalogue, so a uniform sky fills them alike; a patch far denser than the average overflows a segment)
+				const int nseg = ctx->num_sms * ctx->filter_occ;
+				const int segcap = (int) std::min<double>(2e9 / nseg, ((double) s_count / nseg) * (3.0 * ctx->geom_occ + 0.02) + 512.0);
+				const size_t cap = (size_t) nseg * segcap;
+				ENSURE(ctx->d_surv, cap * (sizeof(int) + sizeof(double2)) + ((size_t) nseg + 1) * sizeof(int) + 512);
+				double2 *d_surv_rd = (double2 *) ctx->d_surv.p;   // coordinates first (16-byte aligned), indices behind, then the counts
+				int *d_surv_idx = (int *) (d_surv_rd + cap);
+				int *d_surv_cnt = d_surv_idx + cap;
+				CU(cudaMemsetAsync(d_surv_cnt + nseg, 0, sizeof(int), st));
+				LAUNCH(ctx, k_filter, nseg, 256, (int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
+					d_surv_idx, d_surv_rd, d_surv_cnt, segcap);
+				ka.surv = d_surv_idx; ka.surv_rd = d_surv_rd; ka.surv_cnt = d_surv_cnt; ka.surv_nseg = nseg; ka.surv_segcap = segcap;
 				for (int mode = 1; mode <= 2; mode++) {
 					ka.surv_mode = mode;
 					int r = launch_pairs(ctx, false, flat_err > 0.0, false, shard, (int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
@@ -1375,10 +1384,13 @@ int nwb_shard_setup(nwb_ctx *ctx, int rank, int world, int64_t spill_capacity, v
 		S.off_slot[c] = take((size_t) S.block * S.C[c] * sizeof(Slot16));
 	}
 	for (int c = 1; c < nc; c++) S.off_spill[c] = take((size_t) S.spill_cap * sizeof(SpillRec));
-	S.bytes = off;
+	S.set_bytes = off;
+	S.bytes = 2 * off;
+	S.epoch = 0;
 	// a plain cudaMalloc of its own: IPC handles cover whole allocations
 	{ int r = ensure(ctx, S.xch, S.bytes); if (r) return r; }
 	CU(cudaMemsetAsync(S.xch.p, 0, S.zero_bytes, ctx->stream));
+	CU(cudaMemsetAsync((char *) S.xch.p + S.set_bytes, 0, S.zero_bytes, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	if (ipc_handle_out) {
 		cudaIpcMemHandle_t h;
@@ -1438,16 +1450,28 @@ int nwb_shard_match(nwb_ctx *ctx, int phase, int fuse_final, int64_t *nrows)
 	if (!S.on || !S.connected) return fail(ctx, NWB_ERR_STATE, "nwb_shard_setup / nwb_shard_connect first");
 	CU(cudaSetDevice(ctx->device));
 	if (phase == 0) {
-		// the own primaries' counters back to zero -- BEFORE any rank streams (the caller's barrier follows)
+		// both sets of counters back to zero (after an aborted match; a barrier between the ranks must follow).  Not part
+		// of the steady state: every match zeroes the OTHER set for its successor
 		LAUNCH(ctx, k_zero, (int) std::min<size_t>((S.zero_bytes / 16 + 255) / 256, 148 * 4), 256, (int4 *) S.xch.p, (long long) (S.zero_bytes / 16),
+			(unsigned long long *) S.xch.p, 0);
+		LAUNCH(ctx, k_zero, (int) std::min<size_t>((S.zero_bytes / 16 + 255) / 256, 148 * 4), 256, (int4 *) ((char *) S.xch.p + S.set_bytes), (long long) (S.zero_bytes / 16),
 			(unsigned long long *) S.xch.p, 0);
 		ctx->matched = ctx->finalized = false;
 		return NWB_OK;
 	}
 	if (phase == 1) {
+		// the set the NEXT match will use: nobody reads it any more (this rank's rows of the previous match are stream-ordered
+		// before this launch) and no peer writes it before the barrier that follows this phase
+		char *next = (char *) S.xch.p + (size_t) ((S.epoch + 1) & 1) * S.set_bytes;
+		LAUNCH(ctx, k_zero, (int) std::min<size_t>((S.zero_bytes / 16 + 255) / 256, 148 * 4), 256, (int4 *) next, (long long) (S.zero_bytes / 16),
+			(unsigned long long *) next, 0);
 		return match_impl(ctx, fuse_final, nullptr, true, false, 1);
 	}
-	if (phase == 2) return match_impl(ctx, fuse_final, nrows, true, false, 2);   // 1 = every rank has to redo the match from phase 0
+	if (phase == 2) {
+		const int r = match_impl(ctx, fuse_final, nrows, true, false, 2);   // 1 = every rank has to repeat the match (phases 1, 2)
+		S.epoch++;   // the next match (or the repetition) uses the other set
+		return r;
+	}
 	return fail(ctx, NWB_ERR_ARG, "phase must be 0, 1 or 2");
 }
 

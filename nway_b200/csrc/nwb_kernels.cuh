@@ -227,9 +227,9 @@ struct K1Args {
 	// survivor list (do nothing if it overflowed), 2 = the direct stream as the fallback (do nothing unless it overflowed)
 	int surv_mode;
 	const int *surv;               // survivors: catalogue indices ...
-	const double2 *surv_rd;        // ... and their (ra, dec), compact: k_pairs reads them coalesced
-	const unsigned long long *surv_n;
-	long long surv_cap;
+	const double2 *surv_rd;        // ... and their (ra, dec): one segment of surv_segcap records per block of k_filter
+	const int *surv_cnt;           // [surv_nseg] records in every segment, [surv_nseg] = 1 if a segment overflowed
+	int surv_nseg, surv_segcap;
 };
 
 // exact fp64 separation for `count` (<= 32) queued candidates, one per lane; a match takes the next slot of its
@@ -368,12 +368,15 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 // works through.  No queues, no exact stage, ~32 registers: every SM runs full of warps and the kernel streams the
 // catalogue at HBM speed -- where the one-kernel stream carries the register budget of the exact stage through all of
 // it (BASELINE.json configs[4]: 3e8 sources, 97 % of which end at their bitmap bit).
-// The band table and the bitmap are read through L1 (__ldg): with only a small survivor buffer in shared memory the SM
-// keeps most of its 228 KB as L1, which then holds both (a few tens of KB of band records, ncells / 8 bytes of bitmap)
-// -- the bitmap look-up, the one dependent access of the stream, becomes an L1 hit instead of an L2 round trip.  Two
-// sources per thread and iteration, the next iteration's four loads issued before the current one is processed: ~64 KB
-// of coordinates in flight per SM, enough for the HBM latency-bandwidth product.
-constexpr int KF_BUF = 1024;      // survivors (index + coordinates: 20 KB) a block collects in shared memory before it appends them to the global list
+// The band table and the bitmap are read through L1 (__ldg): the kernel uses no shared memory to speak of, so the SM keeps
+// its 228 KB as L1, which then holds most of both (a few tens of KB of band records, ncells / 8 bytes of bitmap) -- the
+// bitmap look-up, the one dependent access of the stream, is an L1 hit more often than an L2 round trip.  Two sources
+// per thread and iteration, the next iteration's four loads issued before the current one is processed: ~64 KB of
+// coordinates in flight per SM, enough for the HBM latency-bandwidth product.  Every block appends its survivors
+// (index, ra, dec) to a SEGMENT OF ITS OWN in global memory: the position comes from a shared-memory counter (one
+// atomicAdd per warp and batch), so there is no global atomic, no staging buffer and no barrier in the loop; k_pairs
+// walks all segments and skips their unused tails.  A segment that overflows (a far denser patch of sky than the
+// average) raises a flag and the direct stream takes over.
 constexpr int KF_U = 2;           // sources per thread and iteration
 
 __device__ __forceinline__ bool kf_occupied(const Grid &G, double r, double d, double nbands_d)
@@ -391,19 +394,16 @@ __device__ __forceinline__ bool kf_occupied(const Grid &G, double r, double d, d
 
 __global__ void __launch_bounds__(256)
 k_filter(int n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G, int *__restrict__ surv,
-	double2 *__restrict__ surv_rd, unsigned long long *__restrict__ surv_n, long long surv_cap)
+	double2 *__restrict__ surv_rd, int *__restrict__ surv_cnt /* [gridDim.x + 1] */, int segcap)
 {
-	__shared__ int buf[KF_BUF];
-	__shared__ double2 buf_rd[KF_BUF];
-	__shared__ int nbuf;
-	__shared__ unsigned long long gbase;
-	if (threadIdx.x == 0) nbuf = 0;
+	__shared__ int nblk;
+	if (threadIdx.x == 0) nblk = 0;
 	__syncthreads();
 	const int lane = threadIdx.x & 31;
 	const int chunk = (int) blockDim.x * KF_U;                 // sources per block and iteration
 	const long long stride = (long long) gridDim.x * chunk;
-	const long long nround = ((long long) n + chunk - 1) / chunk * chunk;   // whole chunks: every thread reaches the barriers
 	const double nbands_d = (double) G.nbands;
+	const long long seg0 = (long long) blockIdx.x * segcap;
 	long long base = (long long) blockIdx.x * chunk;
 	double r_nxt[KF_U], d_nxt[KF_U];
 #pragma unroll
@@ -412,7 +412,7 @@ k_filter(int n, const double *__restrict__ ra, const double *__restrict__ dec, G
 		r_nxt[u] = 0; d_nxt[u] = 0;
 		if (i < n) { r_nxt[u] = ra[i]; d_nxt[u] = dec[i]; }
 	}
-	for (; base < nround; base += stride) {
+	for (; base < n; base += stride) {
 		double r[KF_U], d[KF_U];
 #pragma unroll
 		for (int u = 0; u < KF_U; u++) { r[u] = r_nxt[u]; d[u] = d_nxt[u]; }
@@ -425,34 +425,22 @@ k_filter(int n, const double *__restrict__ ra, const double *__restrict__ dec, G
 		for (int u = 0; u < KF_U; u++) {
 			const long long i = base + u * (int) blockDim.x + threadIdx.x;
 			const bool keep = i < n && kf_occupied(G, r[u], d[u], nbands_d);
-			// into the block's buffer: one shared-memory atomicAdd per warp that has survivors
 			const unsigned m = __ballot_sync(NWB_FULL, keep);
 			if (m) {
 				int pos = 0;
-				if (lane == 0) pos = atomicAdd(&nbuf, __popc(m));
-				pos = __shfl_sync(NWB_FULL, pos, 0);
-				if (keep) {
-					const int q = pos + __popc(m & ((1u << lane) - 1));
-					buf[q] = (int) i;
-					buf_rd[q] = make_double2(r[u], d[u]);
+				if (lane == 0) pos = atomicAdd(&nblk, __popc(m));
+				pos = __shfl_sync(NWB_FULL, pos, 0) + __popc(m & ((1u << lane) - 1));
+				if (keep && pos < segcap) {
+					surv[seg0 + pos] = (int) i;
+					surv_rd[seg0 + pos] = make_double2(r[u], d[u]);
 				}
 			}
 		}
-		__syncthreads();
-		const int have = nbuf;
-		__syncthreads();   // nobody adds to nbuf again before everybody has read it: `have` is block-uniform
-		const bool last = base + stride >= nround;   // block-uniform
-		if (have > KF_BUF - chunk || (last && have > 0)) {
-			// append the buffer to the global list: ONE global atomicAdd per several hundred survivors, coalesced stores
-			if (threadIdx.x == 0) gbase = atomicAdd(surv_n, (unsigned long long) have);
-			__syncthreads();
-			const unsigned long long g = gbase;
-			for (int k = threadIdx.x; k < have; k += blockDim.x)
-				if (g + k < (unsigned long long) surv_cap) { surv[g + k] = buf[k]; surv_rd[g + k] = buf_rd[k]; }
-			__syncthreads();
-			if (threadIdx.x == 0) nbuf = 0;
-			__syncthreads();
-		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		surv_cnt[blockIdx.x] = min(nblk, segcap);
+		if (nblk > segcap) surv_cnt[gridDim.x] = 1;
 	}
 }
 
@@ -498,20 +486,25 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 	// sparse primaries: the sources may come from the survivor list of k_filter (the ~3 % whose grid cell holds a primary)
 	const bool indirect = !DENSE && A.surv_mode == 1;
 	if (!DENSE && A.surv_mode != 0) {
-		const unsigned long long ns = *A.surv_n;
-		if (indirect ? ns > (unsigned long long) A.surv_cap : ns <= (unsigned long long) A.surv_cap) return;
-		if (indirect) n = (int) ns;
+		const bool overflowed = A.surv_cnt[A.surv_nseg] != 0;
+		if (indirect ? overflowed : !overflowed) return;
+		if (indirect) n = A.surv_nseg * A.surv_segcap;   // every slot of every segment; the unused ones are skipped below
 	}
 	const int nround = (n + 31) / 32 * 32;
 	const double nbands_d = (double) G.nbands;
 	int j0 = blockIdx.x * blockDim.x + threadIdx.x;   // position in the stream (or in the survivor list)
 	int i_nxt = j0;
 	double r_nxt = 0, d_nxt = 0;
+	bool live_nxt = j0 < n;
 	if (j0 < n) {
 		if (indirect) {
-			i_nxt = __ldg(A.surv + j0);
-			const double2 rd = __ldg(A.surv_rd + j0);
-			r_nxt = rd.x; d_nxt = rd.y;
+			const int seg = j0 / A.surv_segcap;
+			live_nxt = j0 - seg * A.surv_segcap < __ldg(A.surv_cnt + seg);
+			if (live_nxt) {
+				i_nxt = __ldg(A.surv + j0);
+				const double2 rd = __ldg(A.surv_rd + j0);
+				r_nxt = rd.x; d_nxt = rd.y;
+			}
 		} else {
 			r_nxt = ra[j0]; d_nxt = dec[j0];
 		}
@@ -520,14 +513,19 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 		const bool last = j0 + stride >= nround;   // this warp's final batch: the lists are drained completely
 		const double r = r_nxt, d = d_nxt;
 		const int i = indirect ? i_nxt : j0;        // the source's index in its catalogue
-		const bool live = j0 < n;
+		const bool live = live_nxt;
 		{
 			const int j = j0 + stride;   // software prefetch of the next batch: hides the DRAM latency
+			live_nxt = j < n;
 			if (j < n) {
 				if (indirect) {
-					i_nxt = __ldg(A.surv + j);
-					const double2 rd = __ldg(A.surv_rd + j);
-					r_nxt = rd.x; d_nxt = rd.y;
+					const int seg = j / A.surv_segcap;
+					live_nxt = j - seg * A.surv_segcap < __ldg(A.surv_cnt + seg);
+					if (live_nxt) {
+						i_nxt = __ldg(A.surv + j);
+						const double2 rd = __ldg(A.surv_rd + j);
+						r_nxt = rd.x; d_nxt = rd.y;
+					}
 				} else {
 					r_nxt = ra[j]; d_nxt = dec[j];
 				}

@@ -201,10 +201,10 @@ class ScatterMatcher(object):
 	primaries) over NVLink peer memory; each rank then produces the rows of its own primaries.  The time of the stream --
 	the dominant cost when secondaries outnumber primaries by orders of magnitude -- divides by the number of GPUs.
 
-	One instance per (process group, context); __call__(ctx, fuse_final) runs one match: phase 0 (zero the own
-	counters) | barrier | phase 1 (grid + streaming, matches arrive from all ranks) | barrier | phase 2 (rows), then one
-	all-reduce of the "buffer too small, everybody again" flags.  The barriers are NCCL all-reduces of one word on the
-	context's stream: stream-ordered, no host synchronisation."""
+	One instance per (process group, context); __call__(ctx, fuse_final) runs one match: phase 1 (grid + streaming,
+	matches arrive from all ranks) | barrier | phase 2 (rows).  The barrier is an NCCL all-reduce of one word on the
+	context's stream: stream-ordered, no host synchronisation; one is enough because the exchange buffers are double-
+	buffered (include/nwayb200.h)."""
 
 	def __init__(self, group=None, device=None, spill_capacity=65536):
 		import torch
@@ -241,14 +241,12 @@ class ScatterMatcher(object):
 			self.setup(ctx)
 		with torch.cuda.stream(self.stream):
 			for attempt in range(4):
-				ctx.shard_match(0)
-				self.barrier()
 				ctx.shard_match(1)
 				self.barrier()
 				nrows, retry = ctx.shard_match(2, fuse_final)
-				self.flag.fill_(1 if retry else 0)
-				dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
-				if int(self.flag.item()) == 0:
+				# "a grid buffer was too small": a property of the (replicated) primaries, so every rank takes the same
+				# decision without asking the others
+				if not retry:
 					return nrows
 		raise RuntimeError('shard mode: the grid buffers kept overflowing')
 
