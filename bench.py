@@ -443,46 +443,75 @@ def run_b200(args):
 		ctx.set_params(RADIUS, tab['pc'], 0.5, _lib.UNRELATED_API)
 		ctx.set_tables(tab['norm'], tab['log10e'], tab['prior'], tab['log10prior'], tab['sub_log10prior'])
 		ctx.set_primary_range(rank * n0, n0)
-		gtab = None
+		recv_bytes = (total_rows - rows) * 8 * len(colsel)
 
-		def gather_step():
-			nonlocal gtab
+		def check_gathered(gtab, cnts):
+			# the gathered table: every shard in rank order, primaries ascending, identical on all ranks
+			assert gtab.shape[1] == sum(cnts) == total_rows
+			prim = gtab[0]
+			assert bool((prim[1:] >= prim[:-1]).all()) and int(prim[0]) == 0 and int(prim[-1]) == world * n0 - 1
+			chk = torch.stack([gtab[k].sum() for k in range(gtab.shape[0])]).to(torch.float64)   # bit patterns of all columns
+			mx, mn = chk.clone(), chk.clone()
+			dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+			dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+			assert bool((mx == mn).all()), 'the ranks hold different gathered tables'
+			return chk
+
+		def time_gather(step):
+			for _ in range(3):
+				step()
+			barrier()
+			g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+			gsteps = max(3, min(args.steps, 20))
+			g0.record(stream)
+			for _ in range(gsteps):
+				gtab, cnts = step()
+			g1.record(stream)
+			barrier()
+			tg = torch.tensor([g0.elapsed_time(g1) / gsteps], dtype=torch.float64, device=dev)
+			dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+			gms = float(tg.item())
+			return gms, gsteps, check_gathered(gtab, cnts)
+
+		def line_of(gms, gsteps, how):
+			return {'value': total_rows / (gms * 1e-3), 'unit': 'associations/s', 'ms_per_step': gms, 'steps': gsteps,
+				'allgather_ms': gms - ms_step_max, 'received_bytes_per_gpu': recv_bytes,
+				'receive_GBs_per_gpu': recv_bytes / (max(gms - ms_step_max, 1e-6) * 1e-3) / 1e9, 'how': how}
+
+		# (a) the product path: the library's peer-memory gather (nwb_gather_*: every GPU stores its shard into every rank's
+		# table over NVLink), SM stores and, for comparison, the copy engines
+		variants = {}
+		sums = {}
+		for name, engine in (('peer_memory_sm', 0), ('peer_memory_copy_engines', 1)):
+			tg_ = parallel.TableGather(None, local, stream=stream, engine=engine)
+			tg_.setup(ctx, total_rows + 4096, len(colsel))
+
+			def peer_step():
+				ctx.match_async(fuse_final=True)
+				nr = ctx.match_wait()
+				return tg_(ctx)
+
+			gms, gsteps, sums[name] = time_gather(peer_step)
+			variants[name] = line_of(gms, gsteps, 'every step: match, NCCL all-gather of the row counts, nwb_gather_push (%s: each GPU writes its 12 columns into their final place in all %d tables over NVLink peer memory), one NCCL barrier; all ranks end with the whole table in HBM'
+				% ('one kernel of 16-byte stores' if engine == 0 else 'cudaMemcpyAsync on one stream per destination', world))
+			tg_.close(ctx)
+		# (b) the same through torch.distributed / NCCL (parallel.allgather_table: one packed message per peer + unpacking)
+		gt = torch.empty((len(colsel), total_rows), dtype=torch.int64, device=dev)
+
+		def nccl_step():
 			ctx.match_async(fuse_final=True)
 			nr = ctx.match_wait()
 			cnts = parallel.exchange_counts(nr, None, dev)
-			if gtab is None or gtab.shape[1] != sum(cnts):
-				gtab = torch.empty((len(colsel), sum(cnts)), dtype=torch.int64, device=dev)
-			parallel.allgather_table(ctx.table_view(), cnts, out=gtab)
-			return cnts
+			parallel.allgather_table(ctx.table_view(), cnts, out=gt)
+			return gt, cnts
 
-		for _ in range(3):
-			cnts = gather_step()
-		barrier()
-		g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-		gsteps = max(3, min(args.steps, 20))
-		g0.record(stream)
-		for _ in range(gsteps):
-			cnts = gather_step()
-		g1.record(stream)
-		barrier()
-		tg = torch.tensor([g0.elapsed_time(g1) / gsteps], dtype=torch.float64, device=dev)
-		dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-		gms = float(tg.item())
-		# the gathered table: every shard in rank order, primaries ascending, identical on all ranks
-		assert gtab.shape[1] == sum(cnts) == total_rows
-		prim = gtab[0]
-		assert bool((prim[1:] >= prim[:-1]).all()) and int(prim[0]) == 0 and int(prim[-1]) == world * n0 - 1
-		chk = torch.stack([gtab[0].sum(), gtab[4].sum()]).to(torch.float64)   # primary indices, ncat
-		mx, mn = chk.clone(), chk.clone()
-		dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-		dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-		assert bool((mx == mn).all()), 'the ranks hold different gathered tables'
-		recv_bytes = (total_rows - cnts[rank]) * 8 * len(colsel)
-		table_gather = {'value': total_rows / (gms * 1e-3), 'unit': 'associations/s', 'ms_per_step': gms, 'steps': gsteps,
-			'allgather_ms': gms - ms_step_max, 'received_bytes_per_gpu': recv_bytes,
-			'receive_GBs_per_gpu': recv_bytes / (max(gms - ms_step_max, 1e-6) * 1e-3) / 1e9,
-			'how': 'every step: match, NCCL all-gather of the row counts, then ONE grouped exchange (batch_isend_irecv = one ncclGroup) of every (column, peer) shard at its exact size from the context columns into the gathered table; all ranks end with the whole table in HBM'}
-		del gtab
+		gms, gsteps, sums['nccl'] = time_gather(nccl_step)
+		variants['nccl_packed'] = line_of(gms, gsteps, 'every step: match, NCCL all-gather of the row counts, one exact-size message per peer in one ncclGroup, unpacked into the columns on arrival')
+		del gt
+		for name in sums:
+			assert torch.equal(sums[name], sums['nccl']), 'the gather variants disagree: ' + name
+		table_gather = dict(variants['peer_memory_sm'])
+		table_gather['variants'] = {k: {'ms_per_step': v['ms_per_step'], 'allgather_ms': v['allgather_ms'], 'receive_GBs_per_gpu': v['receive_GBs_per_gpu']} for k, v in variants.items()}
 
 	if rank != 0:
 		if world > 1:

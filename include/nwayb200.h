@@ -150,6 +150,32 @@ int nwb_shard_connect(nwb_ctx *ctx, const void *ipc_handles);
 int nwb_shard_match(nwb_ctx *ctx, int phase, int fuse_final, int64_t *nrows);
 int nwb_shard_close(nwb_ctx *ctx);
 
+/* ---- multi-GPU: the reassembly of the sharded table over peer memory ------------------------------------------------
+ * Either mode above leaves every rank with the rows of its own primaries; the reference's caller holds ONE table
+ * (nwaylib/__init__.py:272-275 builds it in one process).  nwb_gather_* reassemble it on every rank without a
+ * collective library on the data path: each rank's GPU stores its shard -- column by column, from where the row kernels
+ * wrote it -- straight into its final position in the gathered table of every rank over NVLink peer memory (cudaIpc).
+ * No padding to the largest shard, no staging buffer, no unpacking copy: the bytes cross the link once and land in place.
+ *   nwb_gather_setup    allocates this rank's gathered-table buffer -- TWO sets of ncols columns of capacity_rows 8-byte
+ *                       values, alternating between pushes, so that a rank may still read table e while its peers already
+ *                       push e + 1 -- and returns its 64-byte cudaIpcMemHandle
+ *   nwb_gather_connect  takes all ranks' handles (world x 64 bytes, rank order; the caller all-gathers them)
+ *   nwb_gather_push     counts[world] = rows of every rank's shard, on the host (counts_on_device = 0) or in device memory
+ *                       (1: e.g. the result of an all-gather of the ranks' nwb_nrows_device_ptr words enqueued on the same
+ *                       stream -- no host round trip between the match and the push).
+ *                       Enqueues the push of the own shard on the context's stream (engine 0: one kernel of 16-byte
+ *                       stores from the SMs; 1: the copy engines, one stream per destination, host counts only) and
+ *                       returns the device address of this rank's gathered table for this push: column k at
+ *                       table + k * stride_bytes, sum(counts) rows, shards in rank order.  The table is complete once
+ *                       every rank's push has finished: the caller places ONE stream-ordered barrier between the ranks
+ *                       behind it (any collective on the context's stream).  A table beyond capacity_rows is an error
+ *                       (host counts) or is not written at all (device counts: check sum(counts) afterwards).
+ *   nwb_gather_close    closes the peer mappings and frees the buffer. */
+int nwb_gather_setup(nwb_ctx *ctx, int rank, int world, int64_t capacity_rows, int ncols, void *ipc_handle_out);
+int nwb_gather_connect(nwb_ctx *ctx, const void *ipc_handles);
+int nwb_gather_push(nwb_ctx *ctx, const int64_t *counts, int counts_on_device, int engine, void **table, int64_t *stride_bytes);
+int nwb_gather_close(nwb_ctx *ctx);
+
 /* ---- the path ------------------------------------------------------------------------------------------ */
 
 /* H1+H2+H3: bin, enumerate, separations, radius filter, log Bayes factor, prior, dist_post

@@ -49,6 +49,10 @@ EXPORTS = {
 	'nwb_shard_connect': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
 	'nwb_shard_match': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_int64_p]),
 	'nwb_shard_close': (ctypes.c_int, [ctypes.c_void_p]),
+	'nwb_gather_setup': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
+	'nwb_gather_connect': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+	'nwb_gather_push': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_int64_p]),
+	'nwb_gather_close': (ctypes.c_int, [ctypes.c_void_p]),
 	'nwb_match': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_int64_p]),
 	'nwb_match_async': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
 	'nwb_match_wait': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
@@ -274,6 +278,37 @@ class Context(object):
 
 	def shard_close(self):
 		self.check(self.lib.nwb_shard_close(self.h))
+
+	def gather_setup(self, rank, world, capacity_rows, ncols):
+		"""nwb_gather_setup: this rank's gathered-table buffer (two sets of ncols x capacity_rows); returns its 64-byte IPC handle"""
+		h = ctypes.create_string_buffer(64)
+		self.check(self.lib.nwb_gather_setup(self.h, int(rank), int(world), int(capacity_rows), int(ncols), h))
+		return h.raw
+
+	def gather_connect(self, handles):
+		blob = ctypes.create_string_buffer(b''.join(handles), 64 * len(handles))
+		self.check(self.lib.nwb_gather_connect(self.h, blob))
+
+	def gather_push(self, counts, engine=0):
+		"""nwb_gather_push: enqueue the push of the last match's table into every rank's gathered table.  counts: the
+		shards' row counts, a list (host) or a device pointer to world int64 (int: no host round trip).  Returns this
+		rank's gathered table as a (ncols, capacity_rows) int64 torch view -- the first sum(counts) rows of every column
+		are the table, complete after the caller's barrier"""
+		import torch
+		table = ctypes.c_void_p(0)
+		stride = ctypes.c_int64(0)
+		if isinstance(counts, int):
+			rc = self.lib.nwb_gather_push(self.h, ctypes.c_void_p(counts), 1, int(engine), ctypes.byref(table), ctypes.byref(stride))
+		else:
+			c = (ctypes.c_int64 * len(counts))(*[int(x) for x in counts])
+			rc = self.lib.nwb_gather_push(self.h, ctypes.cast(c, ctypes.c_void_p), 0, int(engine), ctypes.byref(table), ctypes.byref(stride))
+		self.check(rc)
+		ncols = self.table_layout()[2]
+		dev = torch.device('cuda', self.device)
+		return torch.as_tensor(DeviceView(table.value, ncols * (stride.value // 8)), device=dev).view(ncols, stride.value // 8)
+
+	def gather_close(self):
+		self.check(self.lib.nwb_gather_close(self.h))
 
 	def score_rows(self, idx):
 		"""nwb_score_rows: idx (R, ncat) int64 -> dict(sep (npairs, R), sepmax, ncat, log_bf, dist_post)"""

@@ -78,6 +78,19 @@ struct nwb_ctx {
 		int C[MAXC] = {0};
 		unsigned long long spill_cap = 0;
 	} shard;
+	// table all-gather over peer memory (nwb_gather_*)
+	struct Gather {
+		bool on = false, connected = false;
+		int rank = 0, world = 1;
+		DevBuf buf;                     // TWO sets of set_bytes: push e goes to set e % 2 of every rank
+		void *peer[16] = {nullptr};     // [rank] = buf.p, the others opened through cudaIpc
+		size_t set_bytes = 0, stride = 0;   // bytes per set / between the columns of a gathered table
+		int64_t cap_rows = 0;
+		int ncols = 0;
+		long long epoch = 0;
+		cudaStream_t lane[16] = {nullptr};   // copy-engine variant: one stream per destination
+		cudaEvent_t fork = nullptr, join[16] = {nullptr};
+	} gather;
 	// N >= 3 / elliptical: what the previous match of this shape left behind -- buffer capacities and launch decisions -- so
 	// that the next one can enqueue its whole pipeline behind device-side gates (k_spec_gate) without host round trips
 	struct GenCaps {
@@ -441,6 +454,20 @@ static void shard_release(nwb_ctx *ctx)
 	S.on = S.connected = false;
 }
 
+// table all-gather: close the peers' buffers, free the own one
+static void gather_release(nwb_ctx *ctx)
+{
+	nwb_ctx::Gather &T = ctx->gather;
+	for (int r = 0; r < T.world && r < 16; r++)
+		if (r != T.rank && T.peer[r]) cudaIpcCloseMemHandle(T.peer[r]);
+	for (auto &p : T.peer) p = nullptr;
+	for (auto &l : T.lane) if (l) { cudaStreamDestroy(l); l = nullptr; }
+	for (auto &e : T.join) if (e) { cudaEventDestroy(e); e = nullptr; }
+	if (T.fork) { cudaEventDestroy(T.fork); T.fork = nullptr; }
+	release(T.buf);
+	T.on = T.connected = false;
+}
+
 // =========================================================================================================
 extern "C" {
 
@@ -488,6 +515,7 @@ void nwb_destroy(nwb_ctx *ctx)
 		release(ctx->d_spilloff[c]); release(ctx->d_spillseg[c]);
 	}
 	shard_release(ctx);
+	gather_release(ctx);
 	if (ctx->h_status) cudaFreeHost(ctx->h_status);
 	for (auto &ev : ctx->ev) cudaEventDestroy(ev);
 	for (auto &ev : ctx->kev) cudaEventDestroy(ev);
@@ -858,6 +886,14 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		CU(cudaStreamSynchronize(st));   // HG.bands / HG.kx are temporaries
 		HG.g.bands = (const BandRec *) ctx->d_bands.p;
 		HG.g.kx = (const float *) ((const char *) ctx->d_bands.p + nb * sizeof(BandRec));
+		{
+			// the regular bitmap of the pure stream (k_filter): as many ra cells per band as the widest band of the grid has
+			int widest = 1;
+			for (const BandRec &B : HG.bands) widest = std::max(widest, B.nra);
+			HG.g.nr2 = (widest + 31) / 32 * 32;
+			HG.g.inv_w2 = (double) HG.g.nr2 / HG.g.ra_span;
+			HG.g.bits2 = nullptr;
+		}
 		ctx->geom_G = HG.g;
 		ctx->geom_rb = rb; ctx->geom_np = gnp; ctx->geom_first = gfirst;
 		ctx->geom_valid = true;
@@ -866,12 +902,14 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		// cell records, then (sparse primaries only) the occupancy bitmap behind them
 		Grid &g = ctx->geom_G;
 		const size_t rec_bytes = ((size_t) g.ncells * sizeof(CellRec) + 255) / 256 * 256;
-		const size_t bit_bytes = ((size_t) g.ncells / 32 + 2) * sizeof(unsigned);
-		ENSURE(ctx->d_cells, rec_bytes + bit_bytes);
+		const size_t bit_bytes = (((size_t) g.ncells / 32 + 2) * sizeof(unsigned) + 255) / 256 * 256;
+		const size_t bit2_bytes = ((size_t) g.nbands * g.nr2 / 32 + 2) * sizeof(unsigned);
+		ENSURE(ctx->d_cells, rec_bytes + bit_bytes + bit2_bytes);
 		const double s_deg = 1.0 / g.inv_h;
 		const double reach = 1.0 + 2.0 * rb_ins / s_deg;   // cells a primary's box spans along one axis, on average
 		const bool sparse = (double) gnp * reach * reach < 0.5 * (double) g.ncells;
 		g.bits = sparse ? (const unsigned *) ((const char *) ctx->d_cells.p + rec_bytes) : nullptr;
+		g.bits2 = sparse ? (const unsigned *) ((const char *) ctx->d_cells.p + rec_bytes + bit_bytes) : nullptr;
 		ctx->geom_occ = (double) gnp * reach * reach / (double) g.ncells;   // expected share of occupied cells (an upper estimate)
 	}
 	const Grid G = ctx->geom_G;
@@ -944,6 +982,19 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		}
 		if (attempt == 0 && phase != 2) CU(cudaEventRecord(ctx->ev[1], st));
 
+		// the regular bitmap of the pure stream, when some catalogue will take the two-kernel route (see below)
+		if (phase != 2 && G.bits2 && ctx->geom_occ < 0.2) {
+			bool any_long = false;
+			for (int c = 1; c < nc; c++) {
+				const int64_t n = ctx->cat[c].n;
+				const int64_t cnt = shard ? n * (ctx->shard.rank + 1) / ctx->shard.world - n * ctx->shard.rank / ctx->shard.world : n;
+				any_long = any_long || cnt >= (1 << 20);
+			}
+			if (any_long) {
+				CU(cudaMemsetAsync((void *) G.bits2, 0, ((size_t) G.nbands * G.nr2 / 32 + 2) * sizeof(unsigned), st));
+				LAUNCH(ctx, k_prim_bits2, gblocks, 256, (int) gnp, G, P, rb_ins, dra_eps, (unsigned *) G.bits2);
+			}
+		}
 		// ---- K1: stream the secondaries ----------------------------------------------------------------
 		for (int c = 1; c < nc; c++) {
 			int64_t n = ctx->cat[c].n;
@@ -976,7 +1027,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			// sparse primaries and a long catalogue: the stream as two kernels -- k_filter (coordinates -> bitmap bit, survivors
 			// appended to a list) at full occupancy, then k_pairs over the few per cent that survive.  Should the list overflow
 			// (denser than estimated) the second k_pairs launch streams the catalogue directly; otherwise it does nothing.
-			const bool two_kernels = G.bits && s_count >= (1 << 20) && ctx->geom_occ < 0.2;
+			const bool two_kernels = G.bits && G.bits2 && s_count >= (1 << 20) && ctx->geom_occ < 0.2;
 			if (two_kernels && s_count > 0) {
 				if (ctx->filter_occ <= 0) {
 					int nb = 0, nsm = 0;
@@ -1473,6 +1524,141 @@ int nwb_shard_match(nwb_ctx *ctx, int phase, int fuse_final, int64_t *nrows)
 		return r;
 	}
 	return fail(ctx, NWB_ERR_ARG, "phase must be 0, 1 or 2");
+}
+
+// ---- table all-gather over peer memory ---------------------------------------------------------------------------
+int nwb_gather_setup(nwb_ctx *ctx, int rank, int world, int64_t capacity_rows, int ncols, void *ipc_handle_out)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(ctx, NWB_ERR_ARG, "bad rank / world (at most 16 ranks)");
+	if (capacity_rows < 0 || ncols < 1) return fail(ctx, NWB_ERR_ARG, "capacity_rows < 0 or ncols < 1");
+	if (world > 1 && !ipc_handle_out) return fail(ctx, NWB_ERR_ARG, "ipc_handle_out is NULL");
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	gather_release(ctx);
+	nwb_ctx::Gather &T = ctx->gather;
+	T.rank = rank; T.world = world;
+	T.ncols = ncols;
+	T.cap_rows = std::max<int64_t>(capacity_rows, 32);
+	T.stride = ((size_t) T.cap_rows * 8 + 255) / 256 * 256;
+	T.set_bytes = T.stride * ncols;
+	T.epoch = 0;
+	{ int r = ensure(ctx, T.buf, 2 * T.set_bytes); if (r) return r; }   // a cudaMalloc of its own: IPC handles cover whole allocations
+	if (ipc_handle_out) {
+		cudaIpcMemHandle_t h;
+		memset(&h, 0, sizeof(h));
+		if (world > 1) CU(cudaIpcGetMemHandle(&h, T.buf.p));
+		memcpy(ipc_handle_out, &h, sizeof(h));
+	}
+	T.on = true;
+	T.connected = false;
+	return NWB_OK;
+}
+
+int nwb_gather_connect(nwb_ctx *ctx, const void *ipc_handles)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	nwb_ctx::Gather &T = ctx->gather;
+	if (!T.on) return fail(ctx, NWB_ERR_STATE, "nwb_gather_setup first");
+	if (T.world > 1 && !ipc_handles) return fail(ctx, NWB_ERR_ARG, "ipc_handles is NULL");
+	CU(cudaSetDevice(ctx->device));
+	for (int r = 0; r < T.world; r++) {
+		if (r == T.rank) { T.peer[r] = T.buf.p; continue; }
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const char *) ipc_handles + (size_t) r * sizeof(h), sizeof(h));
+		void *p = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			return fail(ctx, NWB_ERR_CUDA, "cudaIpcOpenMemHandle for rank " + std::to_string(r) + ": " + cudaGetErrorString(e) +
+				" (the peer-memory all-gather needs peer access between the GPUs of one node)");
+		}
+		T.peer[r] = p;
+	}
+	T.connected = true;
+	return NWB_OK;
+}
+
+int nwb_gather_close(nwb_ctx *ctx)
+{
+	if (!ctx) return NWB_ERR_ARG;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	gather_release(ctx);
+	return NWB_OK;
+}
+
+int nwb_gather_push(nwb_ctx *ctx, const int64_t *counts, int counts_on_device, int engine, void **table, int64_t *stride_bytes)
+{
+	if (!ctx || !counts) return NWB_ERR_ARG;
+	nwb_ctx::Gather &T = ctx->gather;
+	if (!T.on || !T.connected) return fail(ctx, NWB_ERR_STATE, "nwb_gather_setup / nwb_gather_connect first");
+	if (!ctx->matched && !ctx->pending) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
+	if (ctx->ncols != T.ncols) return fail(ctx, NWB_ERR_ARG, "the table has " + std::to_string(ctx->ncols) + " columns, nwb_gather_setup was told " + std::to_string(T.ncols));
+	if (counts_on_device && engine != 0) return fail(ctx, NWB_ERR_ARG, "the copy engines need the counts on the host");
+	int64_t total = 0, off = 0;
+	if (!counts_on_device) {
+		for (int r = 0; r < T.world; r++) {
+			if (counts[r] < 0) return fail(ctx, NWB_ERR_ARG, "negative row count");
+			if (r < T.rank) off += counts[r];
+			total += counts[r];
+		}
+		if (!ctx->pending && counts[T.rank] != ctx->nrows) return fail(ctx, NWB_ERR_ARG, "counts[rank] is not the row count of the last match");
+		if (total > T.cap_rows)
+			return fail(ctx, NWB_ERR_NOMEM, "the gathered table (" + std::to_string(total) + " rows) exceeds the capacity given to nwb_gather_setup");
+	}
+	CU(cudaSetDevice(ctx->device));
+	const size_t set = (size_t) (T.epoch & 1) * T.set_bytes;
+	T.epoch++;
+	if (table) *table = (char *) T.buf.p + set;
+	if (stride_bytes) *stride_bytes = (int64_t) T.stride;
+	const int ncols = T.ncols;
+	const long long src_stride = (long long) (((size_t) std::max<int64_t>(ctx->cols_cap_rows, 1) * 8 + 255) / 256 * 256);
+	if (engine == 0) {
+		PushArgs A;
+		A.src = (const char *) ctx->d_cols.p; A.src_stride = src_stride;
+		A.counts = counts_on_device ? (const long long *) counts : nullptr;
+		for (int r = 0; r < 16; r++) A.counts_val[r] = (!counts_on_device && r < T.world) ? counts[r] : 0;
+		A.cap_rows = T.cap_rows;
+		const char *envc = getenv("NWB_PUSH_CHUNK");   // measurement knob
+		A.chunk = envc && atoll(envc) >= 512 ? atoll(envc) / 16 * 16 : 0;
+		A.ncols = ncols; A.world = T.world; A.rank = T.rank;
+		for (int r = 0; r < 16; r++) A.dst[r] = r < T.world ? (char *) T.peer[r] + set : nullptr;
+		A.dst_stride = (long long) T.stride;
+		if (ctx->num_sms <= 0) { int nsm = 0; CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device)); ctx->num_sms = std::max(nsm, 1); }
+		// enough blocks for every link to stay busy, few enough to leave after a small table at once
+		const char *env = getenv("NWB_PUSH_BLOCKS_PER_SM");   // measurement knob (tools/bench_push.py)
+		const int per_sm = env && atoi(env) > 0 && atoi(env) <= 4 ? atoi(env) : 4;
+		long long grid = (long long) ctx->num_sms * per_sm;
+		if (!counts_on_device) grid = std::max<long long>(1, std::min<long long>(grid, (counts[T.rank] + 2047) / 2048 * ncols * T.world));
+		const char *envs = getenv("NWB_PUSH_STORE");
+		const int flavour = envs ? atoi(envs) : 1;
+		if (flavour == 1) LAUNCH(ctx, k_table_push<1>, (int) grid, PUSH_THREADS, A);
+		else if (flavour == 2) LAUNCH(ctx, k_table_push<2>, (int) grid, PUSH_THREADS, A);
+		else LAUNCH(ctx, k_table_push<0>, (int) grid, PUSH_THREADS, A);
+		return NWB_OK;
+	}
+	const int64_t rows = counts[T.rank];
+	if (rows == 0) return NWB_OK;
+	// copy engines: one stream per destination, ncols copies each, joined back into the context's stream
+	if (!T.fork) {
+		CU(cudaEventCreateWithFlags(&T.fork, cudaEventDisableTiming));
+		for (int r = 0; r < T.world; r++) {
+			CU(cudaStreamCreateWithFlags(&T.lane[r], cudaStreamNonBlocking));
+			CU(cudaEventCreateWithFlags(&T.join[r], cudaEventDisableTiming));
+		}
+	}
+	CU(cudaEventRecord(T.fork, ctx->stream));
+	for (int i = 0; i < T.world; i++) {
+		const int r = (T.rank + 1 + i) % T.world;
+		CU(cudaStreamWaitEvent(T.lane[r], T.fork, 0));
+		for (int k = 0; k < ncols; k++)
+			CU(cudaMemcpyAsync((char *) T.peer[r] + set + (size_t) k * T.stride + (size_t) off * 8,
+				(const char *) ctx->d_cols.p + (size_t) k * src_stride, (size_t) rows * 8, cudaMemcpyDeviceToDevice, T.lane[r]));
+		CU(cudaEventRecord(T.join[r], T.lane[r]));
+		CU(cudaStreamWaitEvent(ctx->stream, T.join[r], 0));
+	}
+	return NWB_OK;
 }
 
 int nwb_match(nwb_ctx *ctx, int fuse_final, int64_t *nrows)

@@ -379,17 +379,53 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 // average) raises a flag and the direct stream takes over.
 constexpr int KF_U = 2;           // sources per thread and iteration
 
+__device__ __forceinline__ int kf_racell2(const Grid &G, double x)
+{
+	const int i = __double2int_rd(x * G.inv_w2);
+	return i >= G.nr2 ? G.nr2 - 1 : (i < 0 ? 0 : i);
+}
+
+// one look-up per source: the regular bitmap (Grid::bits2)
 __device__ __forceinline__ bool kf_occupied(const Grid &G, double r, double d, double nbands_d)
 {
 	const double t = k1_band_coord(G, d);
 	if (!(t >= 0.0 && t < nbands_d)) return false;
 	const double x = k1_ra_coord(G, r);
 	if (!(G.full_circle || x <= G.ra_span)) return false;
-	const BandRec B = load_band(G, __double2int_rd(t));
-	int ic;
-	k1_ra_cell(B, x, ic);
-	const int cell = B.base + ic;
-	return (__ldg(G.bits + (cell >> 5)) >> (cell & 31) & 1u) != 0u;
+	const long long cell = (long long) __double2int_rd(t) * G.nr2 + kf_racell2(G, x);
+	return (__ldg(G.bits2 + (cell >> 5)) >> (cell & 31) & 1u) != 0u;
+}
+
+// Registration of the primaries in the regular bitmap: every cell the (slightly inflated) search box overlaps, band by
+// band -- the same box, margins and wrap rules as prim_register, on the regular cells.
+__global__ void k_prim_bits2(int np, Grid G, PrimArrays P, double rb_ins, double dra_eps, unsigned *__restrict__ bits2)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= np) return;
+	const double d = P.dec[i], rn = P.ra_n[i], di = P.dra[i] + dra_eps;
+	int b0 = band_of(G, d - rb_ins), b1 = band_of(G, d + rb_ins);
+	b0 = max(b0, 0);
+	b1 = min(b1, G.nbands - 1);
+	const int n = G.nr2;
+	int i0, cnt;
+	if (G.full_circle) {
+		const double cellw = G.ra_span / n;
+		if (2 * di + 2 * cellw >= 360.0) { i0 = 0; cnt = n; }
+		else {
+			i0 = kf_racell2(G, wrap360(rn - di - G.ra_org));
+			const int i1 = kf_racell2(G, wrap360(rn + di - G.ra_org));
+			cnt = (i1 - i0 + n) % n + 1;
+		}
+	} else {
+		const double x0 = wrap360(rn - G.ra_org) - di, x1 = wrap360(rn - G.ra_org) + di;
+		i0 = kf_racell2(G, fmax(x0, 0.0));
+		cnt = kf_racell2(G, fmin(x1, G.ra_span)) - i0 + 1;
+	}
+	for (int b = b0; b <= b1; b++)
+		for (int k = 0; k < cnt; k++) {
+			const long long cell = (long long) b * n + (i0 + k) % n;
+			atomicOr(bits2 + (cell >> 5), 1u << (cell & 31));
+		}
 }
 
 __global__ void __launch_bounds__(256)
@@ -2039,3 +2075,83 @@ __global__ void k_posterior(long long n, const double *__restrict__ prior, const
 }
 
 }  // namespace nwb
+
+// ---- table all-gather over peer memory (nwb_gather_*) -------------------------------------------------------------
+// Every rank places its own shard of the output table -- ncols columns of `rows` 8-byte values, where the row kernels
+// wrote them -- straight into its final position in the gathered table of EVERY rank (dst[r]: the ranks' gather
+// buffers, the peers' mapped through cudaIpc; the own one is an ordinary copy): stores over NVLink from the SMs, no
+// staging, no unpacking afterwards.  Work item = (chunk of a column, peer), peers fastest so that all links are busy
+// at any time.  The destination row offset is only 8-byte aligned: up to 15 scalar head elements per chunk bring it to a
+// 128-byte line, from there on every warp store is four whole lines (8 GPUs, 8 x 590 MB: 6.49 ms; 7.42 ms with stores
+// that were only 16-byte aligned -- partial lines cost NVLink packets).
+struct PushArgs {
+	const char *src;             // the shard: column k at src + k * src_stride
+	long long src_stride;        // bytes
+	const long long *counts;     // device: rows of every rank's shard (e.g. an all-gather of the contexts' row counts) ...
+	long long counts_val[16];    // ... or, if counts is null, the same by value
+	long long cap_rows;          // rows the gathered table holds
+	long long chunk;             // elements per work item (a multiple of 16); 0 = sized by the kernel
+	int ncols, world, rank;
+	char *dst[16];               // the ranks' gathered tables (this set)
+	long long dst_stride;        // bytes between the gathered table's columns
+};
+
+constexpr int PUSH_THREADS = 512;
+
+template <int ST>
+__device__ __forceinline__ void push_store(double2 *p, double2 v)
+{
+	if (ST == 1) __stcs(p, v);
+	else if (ST == 2) __stwt(p, v);
+	else *p = v;
+}
+
+// ST: flavour of the 16-byte store (0 plain, 1 streaming, 2 write-through; 8 GPUs: 6.49 / 6.37 / 6.38 ms, tools/bench_push.py)
+template <int ST>
+__global__ void __launch_bounds__(PUSH_THREADS) k_table_push(PushArgs A)
+{
+	long long rows = 0, off = 0, total = 0;
+	for (int r = 0; r < A.world; r++) {
+		const long long c = A.counts ? __ldg(A.counts + r) : A.counts_val[r];
+		if (r < A.rank) off += c;
+		if (r == A.rank) rows = c;
+		total += c;
+	}
+	if (total > A.cap_rows) return;   // the host sees the same counts and reports it
+	const long long dst_off = off * 8;
+	// work items of up to 512 KB (long runs per link: 6.28 ms instead of 6.49 ms for 8 x 590 MB), smaller for a small table so
+	// that every block still gets a few
+	long long chunk = A.chunk;
+	if (chunk == 0) chunk = max(2048LL, min(65536LL, (rows * A.ncols * A.world / (4LL * gridDim.x) + 15) / 16 * 16));
+	const long long per_col = (rows + chunk - 1) / chunk;
+	const long long items = per_col * A.ncols * A.world;
+	for (long long id = blockIdx.x; id < items; id += gridDim.x) {
+		const int peer = (int) ((id + A.rank) % A.world);
+		const long long t = id / A.world;
+		const int col = (int) (t % A.ncols);
+		const long long first = (t / A.ncols) * chunk;
+		const long long n = min(chunk, rows - first);
+		const double *__restrict__ s = (const double *) (A.src + (long long) col * A.src_stride) + first;
+		double *__restrict__ d = (double *) (A.dst[peer] + (long long) col * A.dst_stride + dst_off) + first;
+		// up to 15 leading elements bring the destination to a 128-byte line: from there every warp store is four whole lines
+		const int head = (int) min(n, (long long) ((16 - (int) (((unsigned long long) d >> 3) & 15)) & 15));
+		if ((int) threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
+		const long long body = (n - head) >> 1;
+		const double *sb = s + head;
+		double2 *db = (double2 *) (d + head);
+		if ((((unsigned long long) sb) & 15) == 0) {   // source and destination equally aligned: 16-byte loads
+			const double2 *sb2 = (const double2 *) sb;
+#pragma unroll 4
+			for (long long i = threadIdx.x; i < body; i += PUSH_THREADS) push_store<ST>(db + i, __ldcs(sb2 + i));
+		} else {
+#pragma unroll 4
+			for (long long i = threadIdx.x; i < body; i += PUSH_THREADS) {
+				double2 v;
+				v.x = __ldcs(sb + 2 * i);
+				v.y = __ldcs(sb + 2 * i + 1);
+				push_store<ST>(db + i, v);
+			}
+		}
+		if (threadIdx.x == 32 && ((n - head) & 1)) d[n - 1] = s[n - 1];
+	}
+}

@@ -4,9 +4,11 @@ Every output row belongs to exactly one primary source and every reduction of th
 match_flag, the CLI correction) stays inside one primary's rows, so the shards are independent: each rank
 matches its contiguous block of primaries against the full secondary catalogues.  The only exchange is the
 re-assembly of the table: an all-gather of the per-rank row counts (which fixes where each shard sits in the
-global table) and, if the caller wants the whole table on every rank, ONE variable-length all-gather of the shards:
-every (column, peer) message at its exact size, sent from the context's own column allocation into its final place
-in the gathered table, all in one NCCL group over NVLink (gloo for the CPU tests).
+global table) and, if the caller wants the whole table on every rank, ONE variable-length all-gather of the shards.
+Two implementations: TableGather -- every GPU stores its shard straight into its final place in every rank's table
+over NVLink peer memory (the library's nwb_gather_*: no padding, no staging, no unpacking; for the repeated matches of
+a resident service) -- and allgather_table, the same exchange through torch.distributed (one exact-size message per
+peer in one NCCL group, unpacked on arrival; gloo for the CPU tests; what the one-shot calls use).
 """
 from collections import OrderedDict
 
@@ -35,13 +37,9 @@ def row_offsets(counts):
 	return [int(x) for x in numpy.concatenate(([0], numpy.cumsum(counts)[:-1]))]
 
 
-PACK_BELOW_BYTES = 1 << 20   # per (column, peer) message: below this the exchange is latency-bound and shards travel packed
-
-
 def _exchange(send, recv, group=None):
 	"""ONE grouped exchange: send = [(tensor, peer)], recv = [(tensor, peer)], every message at its exact size.  With NCCL
-	the whole list is a single ncclGroup (torch.distributed.batch_isend_irecv) -- no padding, no staging copies, no
-	concatenation afterwards: the receives land in their final place."""
+	the whole list is a single ncclGroup (torch.distributed.batch_isend_irecv) -- no padding to the largest shard."""
 	import torch.distributed as dist
 	ops = [dist.P2POp(dist.irecv, t, p, group) for t, p in recv] + [dist.P2POp(dist.isend, t, p, group) for t, p in send]
 	if ops:
@@ -52,13 +50,16 @@ def _exchange(send, recv, group=None):
 def allgather_table(local, counts, group=None, gather='all', out=None):
 	"""The reassembly of the sharded output table (SURVEY.md 8e "Collective") as one variable-length all-gather.
 
-	local: (ncols, counts[rank]) tensor of 8-byte values whose rows are contiguous (e.g. Context.table_view(): the
-	context's own column allocation, sent from where the row kernels wrote it).  counts: rows of every rank's shard, in
-	rank order (exchange_counts).  Returns the (ncols, sum(counts)) table, shards in rank order, on every rank
-	(gather='all') or on rank 0 only (gather='rank0': a real gather, the other ranks only send and return None).
-	Per peer and column one message of exactly that shard's size, all of them in one NCCL group; the own shard is
-	placed with one strided device copy.  Small shards (column pieces below PACK_BELOW_BYTES) travel as one packed
-	message per peer instead: there the number of messages, not their bytes, is the cost."""
+	local: (ncols, counts[rank]) tensor of 8-byte values (e.g. Context.table_view(): the context's own column
+	allocation).  counts: rows of every rank's shard, in rank order (exchange_counts).  Returns the (ncols, sum(counts))
+	table, shards in rank order, on every rank (gather='all') or on rank 0 only (gather='rank0': a real gather, the
+	other ranks only send and return None).  ONE message per peer of exactly that shard's size -- the shard packed into
+	a contiguous (ncols, rows) block -- all of them in one NCCL group, unpacked into the table's columns on arrival.
+	Measured on 8 B200 (tools/bench_allgather.py, 8 x 590 MB): 9.1 ms, against 17.2 ms for one message per (column,
+	peer) straight into place (168 messages per rank: NCCL serialises them over its point-to-point channels), 19.4 ms
+	for torch's uneven all_gather per column, 8.6 ms for one ncclAllGather padded to the largest shard plus the same
+	unpacking (6.4 ms of it the collective) -- and 2 (world - 1) messages instead of 2 ncols (world - 1) is what a
+	small table needs anyway (15 x 1.3e5 rows: 0.36 ms against 2.2 ms)."""
 	import torch
 	import torch.distributed as dist
 	rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -72,20 +73,6 @@ def allgather_table(local, counts, group=None, gather='all', out=None):
 		if counts[rank]:
 			out[:, offs[rank]:offs[rank] + counts[rank]].copy_(local)
 	send, recv = [], []
-	if max(counts) * local.element_size() >= PACK_BELOW_BYTES:
-		# bandwidth regime: every (column, peer) message goes from the context's column to its final place, no staging
-		for peer in range(world):
-			if peer == rank:
-				continue
-			if counts[rank] and (gather == 'all' or peer == 0):
-				send += [(local[k], peer) for k in range(ncols)]
-			if want and counts[peer]:
-				recv += [(out[k, offs[peer]:offs[peer] + counts[peer]], peer) for k in range(ncols)]
-		_exchange(send, recv, group)
-		return out if want else None
-	# latency regime (shards of a few MB: a sparse all-sky match): ONE message per peer -- the shard packed into a
-	# contiguous (ncols, rows) block, unpacked into the table's columns on arrival; 2 (world - 1) messages instead of
-	# 2 ncols (world - 1)
 	packed = local.contiguous() if counts[rank] else None
 	staging = {}
 	for peer in range(world):
@@ -100,6 +87,74 @@ def allgather_table(local, counts, group=None, gather='all', out=None):
 	for peer, buf in staging.items():
 		out[:, offs[peer]:offs[peer] + counts[peer]].copy_(buf.view(ncols, counts[peer]))
 	return out if want else None
+
+
+class TableGather(object):
+	"""The same reassembly over NVLink peer memory (include/nwayb200.h, nwb_gather_*): every rank's GPU stores its shard
+	of the table, column by column from where the row kernels wrote it, straight into its final position in the
+	gathered table of every rank.  No collective library on the data path, no padding, no staging, no unpacking: the
+	bytes cross the link once and land in place.  What remains of torch.distributed is the exchange of the row counts
+	(which fixes the positions) and ONE stream-ordered barrier behind the push.
+
+	One instance per (process group, context).  setup() is collective and allocates two sets of ncols x capacity_rows
+	on every rank (consecutive gathers alternate, so a rank may still read table e while its peers push e + 1); __call__
+	returns this rank's complete (ncols, total) table as a torch view, valid until the next-but-one call.  The context
+	works on `stream` (a torch stream; default: one of its own), and so do the count exchange and the barrier.  The row
+	counts are all-gathered on the device straight into the push kernel's argument, so nothing between the match and
+	the complete table waits for the host."""
+
+	def __init__(self, group=None, device=None, stream=None, engine=0):
+		import torch
+		import torch.distributed as dist
+		self.group = group
+		self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+		self.device = torch.cuda.current_device() if device is None else device
+		self.dev = torch.device('cuda', self.device)
+		self.stream = stream
+		self.engine = engine
+		self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
+		self.counts = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+		self.ready_for = None
+		self.capacity_rows = 0
+
+	def setup(self, ctx, capacity_rows, ncols):
+		import torch
+		import torch.distributed as dist
+		if self.stream is None:
+			self.stream = torch.cuda.Stream(device=self.dev)
+			ctx.set_stream(self.stream.cuda_stream)
+		handle = ctx.gather_setup(self.rank, self.world, capacity_rows, ncols)
+		handles = [None] * self.world
+		dist.all_gather_object(handles, handle, group=self.group)
+		ctx.gather_connect(handles)
+		self.ready_for, self.capacity_rows = ctx, int(capacity_rows)
+
+	def __call__(self, ctx, counts=None):
+		"""one gather of the context's last table; returns (table view, counts).  counts: the shards' row counts if the
+		caller has them on the host already (the copy engines need them there)."""
+		import torch
+		import torch.distributed as dist
+		assert self.ready_for is ctx, 'TableGather.setup first'
+		with torch.cuda.stream(self.stream):
+			if counts is None and self.engine == 1:
+				counts = exchange_counts(ctx.table_layout()[3], self.group, self.dev)
+			if counts is None:
+				mine = torch.tensor([ctx.table_layout()[3]], dtype=torch.int64, device=self.dev)
+				dist.all_gather_into_tensor(self.counts, mine, group=self.group)
+				wide = ctx.gather_push(self.counts.data_ptr(), 0)
+			else:
+				wide = ctx.gather_push([int(c) for c in counts], self.engine)
+			dist.all_reduce(self.token, group=self.group)   # every rank's push has landed once this has run
+			if counts is None:
+				counts = [int(c) for c in self.counts.cpu().tolist()]   # the one wait for the host: the table is complete behind it
+		total = sum(counts)
+		if total > self.capacity_rows:
+			raise RuntimeError('the gathered table has %d rows, TableGather.setup reserved %d' % (total, self.capacity_rows))
+		return wide[:, :total], counts
+
+	def close(self, ctx):
+		ctx.gather_close()
+		self.ready_for = None
 
 
 def allgather_columns(cols, counts, group=None):

@@ -29,6 +29,28 @@ def main():
 	lo = offsets[rank]
 	for k in full:
 		assert np.array_equal(shard[k], full[k][lo:lo + counts[rank]], equal_nan=True), k
+	# the reassembly over NVLink peer memory (nwb_gather_*, parallel.TableGather): SM stores and copy engines, two gathers
+	# each (both buffer sets), against the single-device table
+	from nway_b200 import _lib
+	n0 = len(tables[0]['ra'])
+	first, count = parallel.shard_range(n0, rank, dist.get_world_size())
+	mine = nway_b200.nway_match(tables, 7.0, 0.9, logger=nway_b200.NullOutputLogger(), as_frame=False, device=local,
+		primary_range=(first, count), allow_empty=True, keep_on_device=True)
+	ctx = _lib.get_context(local)
+	names = list(mine['selectors'].keys())
+	assert names == list(full.keys())
+	for engine in (0, 1):
+		tg = parallel.TableGather(None, local, engine=engine)
+		tg.setup(ctx, len(full['A']) + 8, len(names))
+		for again in range(3):
+			table, cnts = tg(ctx, None if again else parallel.exchange_counts(mine['nrows'], None, torch.device('cuda', local)))
+			tg.stream.synchronize()
+			host = table.cpu().numpy()
+			assert host.shape == (len(names), len(full['A'])), (host.shape, len(full['A']))
+			for k, name in enumerate(names):
+				assert np.array_equal(host[k].view(full[name].dtype), full[name], equal_nan=True), ('peer gather', engine, again, name)
+		tg.close(ctx)
+		ctx.set_stream(None)
 	# automatic magnitude histograms in sharded mode: selected from the gathered rows of all shards -- the same table as
 	# on one device, by radius and by posterior (the reference's two modes, nwaylib/__init__.py:324-375)
 	synthetic = lambda: cases.with_mags(cases.uniform_patch(14, (900, 30000, 20000), (1.0, 0.4, 0.6), 0.12), 5, cats=(1, 2), hist=False)

@@ -50,8 +50,7 @@ def worker(rank, world, port, ret):
 		for k, name in enumerate(names):
 			store[k, :int(mine.sum())] = cols[name].view(torch.int64)
 		local = store[:, :int(mine.sum())]
-		for mode, pack in (('all', 1 << 20), ('rank0', 1 << 20), ('all', 0), ('rank0', 0)):   # packed (latency regime) and per-column messages
-			parallel.PACK_BELOW_BYTES = pack
+		for mode in ('all', 'rank0'):
 			tab = parallel.allgather_table(local, counts, gather=mode)
 			if mode == 'rank0' and rank != 0:
 				assert tab is None

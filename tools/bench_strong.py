@@ -15,7 +15,8 @@ of columns for C5 would otherwise have to come through every rank's host).  Devi
 on the matching stream, maximum over the ranks; rank 0 prints one JSON line per configuration and mode:
   "plain"    (N = 1 only) nwb_match on one GPU
   "scatter"  shard mode, table left sharded by primary blocks
-  "scatter+gather"  ... plus the all-gather-v of the table to every rank
+  "scatter+gather"  ... plus the all-gather-v of the table to every rank (torch.distributed / NCCL, parallel.allgather_table)
+  "scatter+peer gather"  ... the same reassembly over peer memory (parallel.TableGather / nwb_gather_*)
 """
 import argparse
 import json
@@ -150,6 +151,20 @@ def main():
 			timed(with_gather, 'scatter+gather', args.steps)
 			prim = gtab['t'][0]
 			assert bool((prim[1:] >= prim[:-1]).all()), 'the gathered table is not in primary order'
+			# ... and the reassembly over peer memory (nwb_gather_*): each GPU stores its rows into every rank's table
+			tot = torch.tensor([matcher(ctx, True)], dtype=torch.int64, device=dev)
+			dist.all_reduce(tot)
+			tg = parallel.TableGather(None, local, stream=matcher.stream)
+			tg.setup(ctx, int(tot.item()) + 4096, ctx.table_layout()[2])
+			last = {}
+
+			def with_peer_gather():
+				nr = matcher(ctx, True)
+				last['t'], last['c'] = tg(ctx)
+				return nr
+			timed(with_peer_gather, 'scatter+peer gather', args.steps)
+			assert last['t'].shape == gtab['t'].shape and torch.equal(last['t'], gtab['t']), 'the two reassemblies disagree'
+			tg.close(ctx)
 		matcher.close(ctx)
 		if rank == 0:
 			base = None
