@@ -890,8 +890,14 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			// the regular bitmap of the pure stream (k_filter): as many ra cells per band as the widest band of the grid has
 			int widest = 1;
 			for (const BandRec &B : HG.bands) widest = std::max(widest, B.nra);
-			HG.g.nr2 = (widest + 31) / 32 * 32;
-			HG.g.inv_w2 = (double) HG.g.nr2 / HG.g.ra_span;
+			// ... scaled down, both ways alike, until it fits the shared memory of one block (KF_SMEM_WORDS)
+			const double kf_bits = 32.0 * KF_SMEM_WORDS;
+			const double f = std::sqrt(std::min(1.0, kf_bits / ((double) HG.g.nbands * (double) ((widest + 31) / 32 * 32))));
+			HG.g.nr2 = std::max(32, (int) ((double) ((widest + 31) / 32 * 32) * f) / 32 * 32);
+			HG.g.nb2 = (int) std::max<long long>(1, std::min<long long>(HG.g.nbands, (long long) kf_bits / HG.g.nr2));
+			// a hair low, so that coordinates inside the grid need no clamping (kf_occupied)
+			HG.g.inv_w2 = (double) HG.g.nr2 / HG.g.ra_span * (1.0 - 1e-12);
+			HG.g.band2_scale = (double) HG.g.nb2 / (double) HG.g.nbands * (1.0 - 1e-12);
 			HG.g.bits2 = nullptr;
 		}
 		ctx->geom_G = HG.g;
@@ -903,7 +909,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 		Grid &g = ctx->geom_G;
 		const size_t rec_bytes = ((size_t) g.ncells * sizeof(CellRec) + 255) / 256 * 256;
 		const size_t bit_bytes = (((size_t) g.ncells / 32 + 2) * sizeof(unsigned) + 255) / 256 * 256;
-		const size_t bit2_bytes = ((size_t) g.nbands * g.nr2 / 32 + 2) * sizeof(unsigned);
+		const size_t bit2_bytes = ((size_t) g.nb2 * g.nr2 / 32 + 8) * sizeof(unsigned);
 		ENSURE(ctx->d_cells, rec_bytes + bit_bytes + bit2_bytes);
 		const double s_deg = 1.0 / g.inv_h;
 		const double reach = 1.0 + 2.0 * rb_ins / s_deg;   // cells a primary's box spans along one axis, on average
@@ -991,7 +997,7 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 				any_long = any_long || cnt >= (1 << 20);
 			}
 			if (any_long) {
-				CU(cudaMemsetAsync((void *) G.bits2, 0, ((size_t) G.nbands * G.nr2 / 32 + 2) * sizeof(unsigned), st));
+				CU(cudaMemsetAsync((void *) G.bits2, 0, ((size_t) G.nb2 * G.nr2 / 32 + 8) * sizeof(unsigned), st));
 				LAUNCH(ctx, k_prim_bits2, gblocks, 256, (int) gnp, G, P, rb_ins, dra_eps, (unsigned *) G.bits2);
 			}
 		}
@@ -1030,24 +1036,32 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			const bool two_kernels = G.bits && G.bits2 && s_count >= (1 << 20) && ctx->geom_occ < 0.2;
 			if (two_kernels && s_count > 0) {
 				if (ctx->filter_occ <= 0) {
-					int nb = 0, nsm = 0;
-					CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_filter, 256, 0));
+					int nsm = 0;
+					CU(cudaFuncSetAttribute(k_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, KF_SMEM_WORDS * (int) sizeof(unsigned)));
 					CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-					ctx->filter_occ = std::max(nb, 1);
+					ctx->filter_occ = 1;   // one block of KF_THREADS per SM: the bitmap takes its shared memory
 					ctx->num_sms = std::max(nsm, 1);
 				}
 				// one segment of survivor records per block: expected survivors x 3 + a margin (the blocks stride evenly over the
 				// catalogue, so a uniform sky fills them alike; a patch far denser than the average overflows a segment)
 				const int nseg = ctx->num_sms * ctx->filter_occ;
-				const int segcap = (int) std::min<double>(2e9 / nseg, ((double) s_count / nseg) * (3.0 * ctx->geom_occ + 0.02) + 512.0);
+				// expected share of occupied cells of the coarse bitmap (an upper estimate, as geom_occ is for the grid)
+				const double occ2 = std::min(1.0, ctx->geom_occ * (double) G.ncells / ((double) G.nb2 * (double) G.nr2) * 2.0);
+				const int segcap = (int) std::min<double>(2e9 / nseg, ((double) s_count / nseg) * (3.0 * occ2 + 0.02) + 512.0);
 				const size_t cap = (size_t) nseg * segcap;
 				ENSURE(ctx->d_surv, cap * (sizeof(int) + sizeof(double2)) + ((size_t) nseg + 1) * sizeof(int) + 512);
 				double2 *d_surv_rd = (double2 *) ctx->d_surv.p;   // coordinates first (16-byte aligned), indices behind, then the counts
 				int *d_surv_idx = (int *) (d_surv_rd + cap);
 				int *d_surv_cnt = d_surv_idx + cap;
 				CU(cudaMemsetAsync(d_surv_cnt + nseg, 0, sizeof(int), st));
-				LAUNCH(ctx, k_filter, nseg, 256, (int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
-					d_surv_idx, d_surv_rd, d_surv_cnt, segcap);
+				{
+					const size_t smem = ((size_t) G.nb2 * (G.nr2 / 32) + 3) / 4 * 4 * sizeof(unsigned);
+					k_filter<<<nseg, KF_THREADS, smem, st>>>((int) s_count, ctx->cat[c].ra + s_first, ctx->cat[c].dec + s_first, G,
+						d_surv_idx, d_surv_rd, d_surv_cnt, segcap);
+					ctx->launches++;
+					cudaError_t e_ = cudaGetLastError();
+					if (e_ != cudaSuccess) return fail(ctx, NWB_ERR_CUDA, std::string("k_filter: ") + cudaGetErrorString(e_));
+				}
 				ka.surv = d_surv_idx; ka.surv_rd = d_surv_rd; ka.surv_cnt = d_surv_cnt; ka.surv_nseg = nseg; ka.surv_segcap = segcap;
 				for (int mode = 1; mode <= 2; mode++) {
 					ka.surv_mode = mode;

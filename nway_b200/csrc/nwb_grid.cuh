@@ -29,12 +29,13 @@ struct Grid {
 	const float *kx;        // [nbands] packed pre-test: degrees of true angle per cell width, rounded down; 0 = dec only
 	float hdeg;             // band height in degrees
 	float rr2p;             // squared radius of the packed pre-test (rr2's margins + the quantisation of the entries)
-	const unsigned *bits2;  // sparse primaries, the pure stream (k_filter): a second, REGULAR occupancy bitmap -- the same bands, but
-	                        // nr2 cells of equal ra width in every band -- so that a source finds its bit with ONE look-up and no band
-	                        // record: cell = band * nr2 + floor(x * inv_w2).  A superset of `bits` (a primary's search box is registered
-	                        // cell by cell, k_prim_bits2); toward the poles its cells are narrower than needed, never wider
-	int nr2;                // multiple of 32
+	const unsigned *bits2;  // sparse primaries, the pure stream (k_filter): a second, REGULAR and COARSE occupancy bitmap, small enough
+	                        // for every block to keep a copy in shared memory -- nb2 declination strips of equal height times nr2
+	                        // cells of equal ra width: cell = floor(t * band2_scale) * nr2 + floor(x * inv_w2).  A superset of `bits`
+	                        // (a primary's search box is registered cell by cell, k_prim_bits2)
+	int nr2, nb2;           // nr2: multiple of 32; nb2 * nr2 <= 32 * KF_SMEM_WORDS
 	double inv_w2;          // regular cells per degree of ra
+	double band2_scale;     // nb2 / nbands
 	const unsigned *bits;   // one bit per cell: any primary registered?  nullptr when most cells are occupied anyway.  A sparse
 	                        // primary catalogue leaves ~97 % of the cells empty; the bitmap (ncells / 8 bytes: L1 / L2 resident)
 	                        // answers those without touching the 32-byte cell records

@@ -363,49 +363,61 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 }
 
 // Sparse primaries (an all-sky match: a few per cent of the grid cells hold a primary), first of two kernels: the pure
-// stream.  One thread per source: coordinates -> cell -> one bit of the occupancy bitmap; the sources whose cell is
-// occupied are appended to a survivor list (warp-aggregated: one atomicAdd per warp and batch), which k_pairs then
-// works through.  No queues, no exact stage, ~32 registers: every SM runs full of warps and the kernel streams the
-// catalogue at HBM speed -- where the one-kernel stream carries the register budget of the exact stage through all of
-// it (BASELINE.json configs[4]: 3e8 sources, 97 % of which end at their bitmap bit).
-// The band table and the bitmap are read through L1 (__ldg): the kernel uses no shared memory to speak of, so the SM keeps
-// its 228 KB as L1, which then holds most of both (a few tens of KB of band records, ncells / 8 bytes of bitmap) -- the
-// bitmap look-up, the one dependent access of the stream, is an L1 hit more often than an L2 round trip.  Two sources
-// per thread and iteration, the next iteration's four loads issued before the current one is processed: ~64 KB of
-// coordinates in flight per SM, enough for the HBM latency-bandwidth product.  Every block appends its survivors
-// (index, ra, dec) to a SEGMENT OF ITS OWN in global memory: the position comes from a shared-memory counter (one
-// atomicAdd per warp and batch), so there is no global atomic, no staging buffer and no barrier in the loop; k_pairs
-// walks all segments and skips their unused tails.  A segment that overflows (a far denser patch of sky than the
-// average) raises a flag and the direct stream takes over.
-constexpr int KF_U = 2;           // sources per thread and iteration
+// stream.  One thread per source: coordinates -> cell of a COARSE REGULAR bitmap -> one bit; the sources whose bit is set
+// are appended to a survivor list, which k_pairs then works through (starting with the bitmap of the grid proper).  No queues, no exact stage: the kernel streams the catalogue
+// (BASELINE.json configs[4]: 3e8 sources, 97 % of which end at their bit).
+// The bit is what the stream pays for.  A gather from global memory costs one L1 wavefront per distinct sector -- 32
+// per warp and look-up for sources in random order, at one wavefront per cycle and SM that alone is 1.07 ms for 3e8
+// sources, an L1 hit or not.  So the bitmap lives in SHARED memory: one block of 1024 threads per SM holds a copy of all
+// of it (<= 224 KB: 1.8 M cells -- for the all-sky case 9 arcmin wide, 6 % of them occupied by 1e5 primaries), and the
+// look-up is a shared-memory load whose 32 random banks collide three or four deep.  Four sources per thread and
+// iteration, the next iteration's eight loads issued before the current one is processed: 64 KB of coordinates in
+// flight per SM, enough for the HBM latency-bandwidth product.  Every block appends its survivors (index, ra, dec) to
+// a SEGMENT OF ITS OWN in global memory: the position comes from a shared-memory counter (one atomicAdd per warp and
+// batch), so there is no global atomic, no staging buffer and no barrier in the loop; k_pairs walks all segments and
+// skips their unused tails.  A segment that overflows (a far denser patch of sky than the average) raises a flag and
+// the direct stream takes over.
+constexpr int KF_U = 4;           // sources per thread and iteration
+constexpr int KF_THREADS = 1024;
+constexpr int KF_SMEM_WORDS = 56 * 1024;   // 224 KB of bitmap
 
+// Cell functions of the regular bitmap.  inv_w2 and band2_scale are a hair below nr2 / ra_span and nb2 / nbands, so a
+// coordinate inside the grid (0 <= x <= ra_span, 0 <= t < nbands) lands inside without clamping; the registration clamps.
 __device__ __forceinline__ int kf_racell2(const Grid &G, double x)
 {
 	const int i = __double2int_rd(x * G.inv_w2);
 	return i >= G.nr2 ? G.nr2 - 1 : (i < 0 ? 0 : i);
 }
 
-// one look-up per source: the regular bitmap (Grid::bits2)
-__device__ __forceinline__ bool kf_occupied(const Grid &G, double r, double d, double nbands_d)
+__device__ __forceinline__ int kf_band2(const Grid &G, double t /* k1_band_coord */)
 {
-	const double t = k1_band_coord(G, d);
-	if (!(t >= 0.0 && t < nbands_d)) return false;
-	const double x = k1_ra_coord(G, r);
-	if (!(G.full_circle || x <= G.ra_span)) return false;
-	const long long cell = (long long) __double2int_rd(t) * G.nr2 + kf_racell2(G, x);
-	return (__ldg(G.bits2 + (cell >> 5)) >> (cell & 31) & 1u) != 0u;
+	const int b = __double2int_rd(t * G.band2_scale);
+	return b >= G.nb2 ? G.nb2 - 1 : (b < 0 ? 0 : b);
 }
 
-// Registration of the primaries in the regular bitmap: every cell the (slightly inflated) search box overlaps, band by
-// band -- the same box, margins and wrap rules as prim_register, on the regular cells.
+// The look-up in the block's copy of the regular bitmap.  (Following it with the grid's own bitmap for the few that pass --
+// two dependent gathers that some lane of nearly every warp then waits for -- cost more than it saved: 2.49 ms instead of
+// 1.89 ms for the stream of configs[4]; k_pairs makes that test anyway, with full warps of survivors.)
+__device__ __forceinline__ bool kf_occupied(const Grid &G, const unsigned *__restrict__ sbits, double r, double d, double nbands_d)
+{
+	const double t = (d - G.dec_lo) * G.inv_h;
+	double x = r - G.ra_org_n;   // ra in [0, 360), as nearly always: one subtraction; anything else takes the general route
+	if (x < 0.0) x += 360.0;
+	if (!(r >= 0.0 && r < 360.0)) x = k1_ra_coord(G, r);
+	const bool inside = t >= 0.0 && t < nbands_d && (G.full_circle || x <= G.ra_span);
+	const int cell2 = __double2int_rd(t * G.band2_scale) * G.nr2 + __double2int_rd(x * G.inv_w2);
+	return inside && (sbits[cell2 >> 5] >> (cell2 & 31) & 1u) != 0u;
+}
+
+// Registration of the primaries in the regular bitmap: every cell the (slightly inflated) search box overlaps, strip by
+// strip -- the same box, margins and wrap rules as prim_register, on the regular cells; strips and cells come from the
+// same monotone functions the look-up uses, so a source inside the box finds a set bit.
 __global__ void k_prim_bits2(int np, Grid G, PrimArrays P, double rb_ins, double dra_eps, unsigned *__restrict__ bits2)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= np) return;
 	const double d = P.dec[i], rn = P.ra_n[i], di = P.dra[i] + dra_eps;
-	int b0 = band_of(G, d - rb_ins), b1 = band_of(G, d + rb_ins);
-	b0 = max(b0, 0);
-	b1 = min(b1, G.nbands - 1);
+	const int b0 = kf_band2(G, k1_band_coord(G, d - rb_ins)), b1 = kf_band2(G, k1_band_coord(G, d + rb_ins));
 	const int n = G.nr2;
 	int i0, cnt;
 	if (G.full_circle) {
@@ -423,28 +435,56 @@ __global__ void k_prim_bits2(int np, Grid G, PrimArrays P, double rb_ins, double
 	}
 	for (int b = b0; b <= b1; b++)
 		for (int k = 0; k < cnt; k++) {
-			const long long cell = (long long) b * n + (i0 + k) % n;
+			const int cell = b * n + (i0 + k) % n;
 			atomicOr(bits2 + (cell >> 5), 1u << (cell & 31));
 		}
 }
 
-__global__ void __launch_bounds__(256)
+// one batch of the stream: KF_U sources per thread; FULL = every index of the batch is inside the catalogue
+template <bool FULL>
+__device__ __forceinline__ void kf_batch(const Grid &G, const unsigned *__restrict__ sbits, int n, int base, const double *r, const double *d,
+	double nbands_d, int *nblk, int *__restrict__ surv, double2 *__restrict__ surv_rd, int segcap)
+{
+#pragma unroll
+	for (int u = 0; u < KF_U; u++) {
+		const int i = base + u * KF_THREADS + (int) threadIdx.x;
+		if ((FULL || i < n) && kf_occupied(G, sbits, r[u], d[u], nbands_d)) {
+			// a few per cent of the sources get here: one shared-memory atomic each (the warp-aggregated form -- ballot, leader,
+			// shuffle -- executed its forty instructions for nearly every warp, since some lane of 32 nearly always passes)
+			const int pos = atomicAdd(nblk, 1);
+			if (pos < segcap) {
+				surv[pos] = i;
+				surv_rd[pos] = make_double2(r[u], d[u]);
+			}
+		}
+	}
+}
+
+// n + one wave of sources < 2^31 (the host's guarantee for every stream kernel): 32-bit indices throughout
+__global__ void __launch_bounds__(KF_THREADS, 1)
 k_filter(int n, const double *__restrict__ ra, const double *__restrict__ dec, Grid G, int *__restrict__ surv,
 	double2 *__restrict__ surv_rd, int *__restrict__ surv_cnt /* [gridDim.x + 1] */, int segcap)
 {
+	extern __shared__ unsigned kf_sbits[];   // nb2 * nr2 / 32 words
 	__shared__ int nblk;
+	{
+		const int words = G.nb2 * (G.nr2 >> 5);
+		const uint4 *src = reinterpret_cast<const uint4 *>(G.bits2);   // 16-byte aligned, padded to a multiple of four words
+		uint4 *dst = reinterpret_cast<uint4 *>(kf_sbits);
+		for (int w = threadIdx.x; w < (words + 3) / 4; w += KF_THREADS) dst[w] = __ldg(src + w);
+	}
 	if (threadIdx.x == 0) nblk = 0;
 	__syncthreads();
-	const int lane = threadIdx.x & 31;
-	const int chunk = (int) blockDim.x * KF_U;                 // sources per block and iteration
-	const long long stride = (long long) gridDim.x * chunk;
+	constexpr int chunk = KF_THREADS * KF_U;                   // sources per block and iteration
+	const int stride = (int) gridDim.x * chunk;
 	const double nbands_d = (double) G.nbands;
-	const long long seg0 = (long long) blockIdx.x * segcap;
-	long long base = (long long) blockIdx.x * chunk;
+	surv += (long long) blockIdx.x * segcap;
+	surv_rd += (long long) blockIdx.x * segcap;
+	int base = (int) blockIdx.x * chunk;
 	double r_nxt[KF_U], d_nxt[KF_U];
 #pragma unroll
 	for (int u = 0; u < KF_U; u++) {
-		const long long i = base + u * (int) blockDim.x + threadIdx.x;
+		const int i = base + u * KF_THREADS + (int) threadIdx.x;
 		r_nxt[u] = 0; d_nxt[u] = 0;
 		if (i < n) { r_nxt[u] = ra[i]; d_nxt[u] = dec[i]; }
 	}
@@ -452,25 +492,21 @@ k_filter(int n, const double *__restrict__ ra, const double *__restrict__ dec, G
 		double r[KF_U], d[KF_U];
 #pragma unroll
 		for (int u = 0; u < KF_U; u++) { r[u] = r_nxt[u]; d[u] = d_nxt[u]; }
+		const int nb = base + stride;
+		if (nb + chunk <= n) {   // the next batch lies inside the catalogue, and so does this one
 #pragma unroll
-		for (int u = 0; u < KF_U; u++) {
-			const long long j = base + stride + u * (int) blockDim.x + threadIdx.x;
-			if (j < n) { r_nxt[u] = ra[j]; d_nxt[u] = dec[j]; }
-		}
-#pragma unroll
-		for (int u = 0; u < KF_U; u++) {
-			const long long i = base + u * (int) blockDim.x + threadIdx.x;
-			const bool keep = i < n && kf_occupied(G, r[u], d[u], nbands_d);
-			const unsigned m = __ballot_sync(NWB_FULL, keep);
-			if (m) {
-				int pos = 0;
-				if (lane == 0) pos = atomicAdd(&nblk, __popc(m));
-				pos = __shfl_sync(NWB_FULL, pos, 0) + __popc(m & ((1u << lane) - 1));
-				if (keep && pos < segcap) {
-					surv[seg0 + pos] = (int) i;
-					surv_rd[seg0 + pos] = make_double2(r[u], d[u]);
-				}
+			for (int u = 0; u < KF_U; u++) {
+				const int j = nb + u * KF_THREADS + (int) threadIdx.x;
+				r_nxt[u] = ra[j]; d_nxt[u] = dec[j];
 			}
+			kf_batch<true>(G, kf_sbits, n, base, r, d, nbands_d, &nblk, surv, surv_rd, segcap);
+		} else {
+#pragma unroll
+			for (int u = 0; u < KF_U; u++) {
+				const int j = nb + u * KF_THREADS + (int) threadIdx.x;
+				if (j < n) { r_nxt[u] = ra[j]; d_nxt[u] = dec[j]; }
+			}
+			kf_batch<false>(G, kf_sbits, n, base, r, d, nbands_d, &nblk, surv, surv_rd, segcap);
 		}
 	}
 	__syncthreads();
@@ -518,29 +554,37 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 	K1Smem &M = smem[threadIdx.x >> 5];
 	int nit = 0, qn = 0;   // warp-uniform fill levels of the two lists; both below 32 at the top of the loop
 	// 32-bit indices: the host guarantees n + (one wave of threads) < 2^31 (secondary indices are ints in the slots anyway)
-	const int stride = gridDim.x * blockDim.x;
 	// sparse primaries: the sources may come from the survivor list of k_filter (the ~3 % whose grid cell holds a primary)
 	const bool indirect = !DENSE && A.surv_mode == 1;
 	if (!DENSE && A.surv_mode != 0) {
 		const bool overflowed = A.surv_cnt[A.surv_nseg] != 0;
 		if (indirect ? overflowed : !overflowed) return;
-		if (indirect) n = A.surv_nseg * A.surv_segcap;   // every slot of every segment; the unused ones are skipped below
+	}
+	// Survivor list: the warps are dealt out to the segments (warp w -> segment w % nseg, every (w / nseg)-th batch of it)
+	// and walk only the filled part of theirs -- from here on n, stride and j0 are this WARP's: its segment's fill level, the
+	// step between its batches, its position in the segment
+	int stride = gridDim.x * blockDim.x;
+	int j0 = blockIdx.x * blockDim.x + threadIdx.x;   // position in the stream (or in the warp's segment of the survivor list)
+	long long slot0 = 0;
+	if (indirect) {
+		const int gw = j0 >> 5, nw = stride >> 5;
+		const int seg = gw % A.surv_nseg, sub = gw / A.surv_nseg;
+		const int nsub = max(nw / A.surv_nseg, 1);   // the host launches at least one warp per segment
+		n = sub < nsub ? __ldg(A.surv_cnt + seg) : 0;
+		slot0 = (long long) seg * A.surv_segcap;
+		j0 = sub * 32 + lane;
+		stride = nsub * 32;
 	}
 	const int nround = (n + 31) / 32 * 32;
 	const double nbands_d = (double) G.nbands;
-	int j0 = blockIdx.x * blockDim.x + threadIdx.x;   // position in the stream (or in the survivor list)
 	int i_nxt = j0;
 	double r_nxt = 0, d_nxt = 0;
 	bool live_nxt = j0 < n;
 	if (j0 < n) {
 		if (indirect) {
-			const int seg = j0 / A.surv_segcap;
-			live_nxt = j0 - seg * A.surv_segcap < __ldg(A.surv_cnt + seg);
-			if (live_nxt) {
-				i_nxt = __ldg(A.surv + j0);
-				const double2 rd = __ldg(A.surv_rd + j0);
-				r_nxt = rd.x; d_nxt = rd.y;
-			}
+			i_nxt = __ldg(A.surv + slot0 + j0);
+			const double2 rd = __ldg(A.surv_rd + slot0 + j0);
+			r_nxt = rd.x; d_nxt = rd.y;
 		} else {
 			r_nxt = ra[j0]; d_nxt = dec[j0];
 		}
@@ -555,13 +599,9 @@ k_pairs(int n, const double *__restrict__ ra, const double *__restrict__ dec, Gr
 			live_nxt = j < n;
 			if (j < n) {
 				if (indirect) {
-					const int seg = j / A.surv_segcap;
-					live_nxt = j - seg * A.surv_segcap < __ldg(A.surv_cnt + seg);
-					if (live_nxt) {
-						i_nxt = __ldg(A.surv + j);
-						const double2 rd = __ldg(A.surv_rd + j);
-						r_nxt = rd.x; d_nxt = rd.y;
-					}
+					i_nxt = __ldg(A.surv + slot0 + j);
+					const double2 rd = __ldg(A.surv_rd + slot0 + j);
+					r_nxt = rd.x; d_nxt = rd.y;
 				} else {
 					r_nxt = ra[j]; d_nxt = dec[j];
 				}
