@@ -895,9 +895,10 @@ static int match_impl(nwb_ctx *ctx, int fuse_final, int64_t *nrows, bool allow_c
 			const double f = std::sqrt(std::min(1.0, kf_bits / ((double) HG.g.nbands * (double) ((widest + 31) / 32 * 32))));
 			HG.g.nr2 = std::max(32, (int) ((double) ((widest + 31) / 32 * 32) * f) / 32 * 32);
 			HG.g.nb2 = (int) std::max<long long>(1, std::min<long long>(HG.g.nbands, (long long) kf_bits / HG.g.nr2));
-			// a hair low, so that coordinates inside the grid need no clamping (kf_occupied)
-			HG.g.inv_w2 = (double) HG.g.nr2 / HG.g.ra_span * (1.0 - 1e-12);
-			HG.g.band2_scale = (double) HG.g.nb2 / (double) HG.g.nbands * (1.0 - 1e-12);
+			// the cell functions ROUND (kf_round): scales for nr2 - 1 and nb2 - 1 intervals, a hair low, so that coordinates inside
+			// the grid need no clamping (kf_occupied)
+			HG.g.inv_w2 = (double) (HG.g.nr2 - 1) / HG.g.ra_span * (1.0 - 1e-12);
+			HG.g.band2_scale = (double) (HG.g.nb2 - 1) / (double) HG.g.nbands * (1.0 - 1e-12);
 			HG.g.bits2 = nullptr;
 		}
 		ctx->geom_G = HG.g;

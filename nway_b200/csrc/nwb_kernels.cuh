@@ -371,27 +371,31 @@ __device__ __forceinline__ void k1_items(K1Smem &M, int lo, int count, int lane,
 // sources, an L1 hit or not.  So the bitmap lives in SHARED memory: one block of 1024 threads per SM holds a copy of all
 // of it (<= 224 KB: 1.8 M cells -- for the all-sky case 9 arcmin wide, 6 % of them occupied by 1e5 primaries), and the
 // look-up is a shared-memory load whose 32 random banks collide three or four deep.  Four sources per thread and
-// iteration, the next iteration's eight loads issued before the current one is processed: 64 KB of coordinates in
+// iteration, each one's successor loaded into its registers while it is processed: 64 KB of coordinates in
 // flight per SM, enough for the HBM latency-bandwidth product.  Every block appends its survivors (index, ra, dec) to
 // a SEGMENT OF ITS OWN in global memory: the position comes from a shared-memory counter (one atomicAdd per warp and
 // batch), so there is no global atomic, no staging buffer and no barrier in the loop; k_pairs walks all segments and
 // skips their unused tails.  A segment that overflows (a far denser patch of sky than the average) raises a flag and
 // the direct stream takes over.
-constexpr int KF_U = 4;           // sources per thread and iteration
+constexpr int KF_U = 4;           // sources per thread and iteration (eight: spills at the 64 registers 1024 threads leave)
 constexpr int KF_THREADS = 1024;
 constexpr int KF_SMEM_WORDS = 56 * 1024;   // 224 KB of bitmap
 
-// Cell functions of the regular bitmap.  inv_w2 and band2_scale are a hair below nr2 / ra_span and nb2 / nbands, so a
+// Cell functions of the regular bitmap: ROUND(coordinate * scale), by adding 1.5 * 2^52 and reading the low word -- one
+// fixed-latency DADD where floor() is a conversion through the slow pipe; any monotone function serves, as long as the
+// registration and the look-up share it.  inv_w2 and band2_scale are (nr2 - 1) / ra_span and (nb2 - 1) / nbands, so a
 // coordinate inside the grid (0 <= x <= ra_span, 0 <= t < nbands) lands inside without clamping; the registration clamps.
+__device__ __forceinline__ int kf_round(double v) { return __double2loint(v + 6755399441055744.0); }
+
 __device__ __forceinline__ int kf_racell2(const Grid &G, double x)
 {
-	const int i = __double2int_rd(x * G.inv_w2);
+	const int i = kf_round(fmin(fmax(x, 0.0), 360.0) * G.inv_w2);
 	return i >= G.nr2 ? G.nr2 - 1 : (i < 0 ? 0 : i);
 }
 
 __device__ __forceinline__ int kf_band2(const Grid &G, double t /* k1_band_coord */)
 {
-	const int b = __double2int_rd(t * G.band2_scale);
+	const int b = kf_round(fmin(fmax(t, 0.0), (double) G.nbands) * G.band2_scale);
 	return b >= G.nb2 ? G.nb2 - 1 : (b < 0 ? 0 : b);
 }
 
@@ -405,7 +409,7 @@ __device__ __forceinline__ bool kf_occupied(const Grid &G, const unsigned *__res
 	if (x < 0.0) x += 360.0;
 	if (!(r >= 0.0 && r < 360.0)) x = k1_ra_coord(G, r);
 	const bool inside = t >= 0.0 && t < nbands_d && (G.full_circle || x <= G.ra_span);
-	const int cell2 = __double2int_rd(t * G.band2_scale) * G.nr2 + __double2int_rd(x * G.inv_w2);
+	const int cell2 = kf_round(t * G.band2_scale) * G.nr2 + kf_round(x * G.inv_w2);
 	return inside && (sbits[cell2 >> 5] >> (cell2 & 31) & 1u) != 0u;
 }
 
@@ -440,21 +444,25 @@ __global__ void k_prim_bits2(int np, Grid G, PrimArrays P, double rb_ins, double
 		}
 }
 
-// one batch of the stream: KF_U sources per thread; FULL = every index of the batch is inside the catalogue
+// one batch of the stream: KF_U sources per thread, each replaced in its registers by the source of the next batch as soon
+// as it has been read; FULL = every index of this batch and the next is inside the catalogue
 template <bool FULL>
-__device__ __forceinline__ void kf_batch(const Grid &G, const unsigned *__restrict__ sbits, int n, int base, const double *r, const double *d,
+__device__ __forceinline__ void kf_batch(const Grid &G, const unsigned *__restrict__ sbits, int n, int base, int next,
+	const double *__restrict__ ra, const double *__restrict__ dec, double *rr, double *dd,
 	double nbands_d, int *nblk, int *__restrict__ surv, double2 *__restrict__ surv_rd, int segcap)
 {
 #pragma unroll
 	for (int u = 0; u < KF_U; u++) {
 		const int i = base + u * KF_THREADS + (int) threadIdx.x;
-		if ((FULL || i < n) && kf_occupied(G, sbits, r[u], d[u], nbands_d)) {
-			// a few per cent of the sources get here: one shared-memory atomic each (the warp-aggregated form -- ballot, leader,
-			// shuffle -- executed its forty instructions for nearly every warp, since some lane of 32 nearly always passes)
+		const int j = next + u * KF_THREADS + (int) threadIdx.x;
+		const double r = rr[u], d = dd[u];
+		if (FULL || j < n) { rr[u] = ra[j]; dd[u] = dec[j]; }
+		if ((FULL || i < n) && kf_occupied(G, sbits, r, d, nbands_d)) {
+			// a few per cent of the sources get here: one shared-memory atomic each (the compiler aggregates it per warp)
 			const int pos = atomicAdd(nblk, 1);
 			if (pos < segcap) {
 				surv[pos] = i;
-				surv_rd[pos] = make_double2(r[u], d[u]);
+				surv_rd[pos] = make_double2(r, d);
 			}
 		}
 	}
@@ -481,33 +489,17 @@ k_filter(int n, const double *__restrict__ ra, const double *__restrict__ dec, G
 	surv += (long long) blockIdx.x * segcap;
 	surv_rd += (long long) blockIdx.x * segcap;
 	int base = (int) blockIdx.x * chunk;
-	double r_nxt[KF_U], d_nxt[KF_U];
+	double rr[KF_U], dd[KF_U];
 #pragma unroll
 	for (int u = 0; u < KF_U; u++) {
 		const int i = base + u * KF_THREADS + (int) threadIdx.x;
-		r_nxt[u] = 0; d_nxt[u] = 0;
-		if (i < n) { r_nxt[u] = ra[i]; d_nxt[u] = dec[i]; }
+		rr[u] = 0; dd[u] = 0;
+		if (i < n) { rr[u] = ra[i]; dd[u] = dec[i]; }
 	}
 	for (; base < n; base += stride) {
-		double r[KF_U], d[KF_U];
-#pragma unroll
-		for (int u = 0; u < KF_U; u++) { r[u] = r_nxt[u]; d[u] = d_nxt[u]; }
-		const int nb = base + stride;
-		if (nb + chunk <= n) {   // the next batch lies inside the catalogue, and so does this one
-#pragma unroll
-			for (int u = 0; u < KF_U; u++) {
-				const int j = nb + u * KF_THREADS + (int) threadIdx.x;
-				r_nxt[u] = ra[j]; d_nxt[u] = dec[j];
-			}
-			kf_batch<true>(G, kf_sbits, n, base, r, d, nbands_d, &nblk, surv, surv_rd, segcap);
-		} else {
-#pragma unroll
-			for (int u = 0; u < KF_U; u++) {
-				const int j = nb + u * KF_THREADS + (int) threadIdx.x;
-				if (j < n) { r_nxt[u] = ra[j]; d_nxt[u] = dec[j]; }
-			}
-			kf_batch<false>(G, kf_sbits, n, base, r, d, nbands_d, &nblk, surv, surv_rd, segcap);
-		}
+		const int next = base + stride;
+		if (next + chunk <= n) kf_batch<true>(G, kf_sbits, n, base, next, ra, dec, rr, dd, nbands_d, &nblk, surv, surv_rd, segcap);
+		else kf_batch<false>(G, kf_sbits, n, base, next, ra, dec, rr, dd, nbands_d, &nblk, surv, surv_rd, segcap);
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
