@@ -558,8 +558,13 @@ def run_b200(args):
 			# none of its arithmetic (nwb_bench_skeleton) -- what the access pattern alone costs
 			ctx.set_compat(_lib.COMPAT_FLAT_HASH)
 			ctx.match(fuse_final=True)
-			sk = ctx.bench_skeleton(1, 5)
-			roofline['k_pairs_memory_skeleton'] = {'ms': sk, 'GBs': bytes_pairs / (sk * 1e-3) / 1e9, 'k_pairs_over_skeleton': k_pairs_ms / sk}
+			by_blocks = {}
+			for b in (2, 3, 4, 5):   # resident blocks per SM: the access stream is fastest when fewer warps than fit are in flight
+				ctx.match(fuse_final=True)
+				by_blocks[b] = ctx.bench_skeleton(1, 5, b)
+			sk = min(by_blocks.values())
+			roofline['k_pairs_memory_skeleton'] = {'ms': sk, 'GBs': bytes_pairs / (sk * 1e-3) / 1e9, 'k_pairs_over_skeleton': k_pairs_ms / sk,
+				'ms_by_resident_blocks_per_sm': by_blocks, 'what': 'the same global-memory accesses, queues and atomics as k_pairs without its arithmetic; best of 2..5 resident blocks per SM'}
 		except Exception as e:
 			roofline['k_pairs_memory_skeleton'] = {'error': str(e)[:200]}
 
