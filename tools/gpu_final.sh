@@ -19,7 +19,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_p
 ncu -i $out/hot.ncu-rep --page raw --csv > $out/hot_raw.csv 2>/dev/null
 python tools/ncu_summary.py $out/hot_raw.csv > $out/hot_summary.txt 2>&1
 cat $out/hot_summary.txt
-timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k 'regex:k_pairs<[^0-9>]*1[^0-9>]*1[^0-9>]*1[^0-9>]*0[^0-9>]*>' -c 1 -f -o $out/skeleton \
+timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k 'regex:.*k_pairs<[^0-9>]*1[^0-9>]*[01][^0-9>]*1[^0-9>]*0[^0-9>]*>.*' -c 1 -f -o $out/skeleton \
 	python bench.py --steps 2 --warmup 3 --no-cpu > $out/ncu_skel.log 2>&1
 ncu -i $out/skeleton.ncu-rep --page raw --csv > $out/skeleton_raw.csv 2>/dev/null
 python tools/ncu_summary.py $out/skeleton_raw.csv > $out/skeleton_summary.txt 2>&1
