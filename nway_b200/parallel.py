@@ -123,10 +123,26 @@ class TableGather(object):
 		if self.stream is None:
 			self.stream = torch.cuda.Stream(device=self.dev)
 			ctx.set_stream(self.stream.cuda_stream)
-		handle = ctx.gather_setup(self.rank, self.world, capacity_rows, ncols)
+		# a failure on one rank (no peer access, out of memory) must not leave the others waiting in a collective: every
+		# step's outcome is exchanged, and all ranks raise together
+		try:
+			handle, err = ctx.gather_setup(self.rank, self.world, capacity_rows, ncols), None
+		except Exception as e:
+			handle, err = None, repr(e)
 		handles = [None] * self.world
-		dist.all_gather_object(handles, handle, group=self.group)
-		ctx.gather_connect(handles)
+		dist.all_gather_object(handles, (handle, err), group=self.group)
+		if any(h is None for h, _ in handles):
+			raise RuntimeError('TableGather.setup failed: ' + '; '.join('rank %d: %s' % (r, e) for r, (h, e) in enumerate(handles) if h is None))
+		try:
+			ctx.gather_connect([h for h, _ in handles])
+			err = None
+		except Exception as e:
+			err = repr(e)
+		errs = [None] * self.world
+		dist.all_gather_object(errs, err, group=self.group)
+		if any(e is not None for e in errs):
+			ctx.gather_close()
+			raise RuntimeError('TableGather.setup failed: ' + '; '.join('rank %d: %s' % (r, e) for r, e in enumerate(errs) if e is not None))
 		self.ready_for, self.capacity_rows = ctx, int(capacity_rows)
 
 	def __call__(self, ctx, counts=None):
