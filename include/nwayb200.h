@@ -144,6 +144,9 @@ int nwb_set_primary_range(nwb_ctx *ctx, int64_t first, int64_t count);
  *                      Phase 2 returns 1 when a grid buffer turned out too small: every rank sees the same (the primaries
  *                      are replicated) and repeats phases 1 and 2.  Phase 0 resets both sets (after an aborted match; a
  *                      barrier must follow).  world = 1 degenerates to an ordinary match.
+ *                      Phase 3 = phases 1 and 2 in one call with the barrier as flags in peer memory: every rank stores a
+ *                      growing tag into every rank's exchange buffer behind its streaming kernel and waits, on the device,
+ *                      for the others' (gives up after 10 s: NWB_ERR_STATE) -- no collective library on the path at all.
  *   nwb_shard_close    leaves shard mode. */
 int nwb_shard_setup(nwb_ctx *ctx, int rank, int world, int64_t spill_capacity, void *ipc_handle_out, int64_t *exchange_bytes);
 int nwb_shard_connect(nwb_ctx *ctx, const void *ipc_handles);
@@ -164,7 +167,10 @@ int nwb_shard_close(nwb_ctx *ctx);
  *                       (1: e.g. the result of an all-gather of the ranks' nwb_nrows_device_ptr words enqueued on the same
  *                       stream -- no host round trip between the match and the push).
  *                       Enqueues the push of the own shard on the context's stream (engine 0: one kernel of 16-byte
- *                       stores from the SMs; 1: the copy engines, one stream per destination, host counts only) and
+ *                       stores from the SMs; 1: the copy engines, one stream per destination, host counts only; 2: as 0,
+ *                       but self-contained -- counts may be NULL: the ranks' row counts travel as flag words through the
+ *                       buffers' headers before the push, and a second exchange of flags behind it IS the barrier, so
+ *                       the table is complete when the stream gets there; nwb_gather_counts then returns the counts) and
  *                       returns the device address of this rank's gathered table for this push: column k at
  *                       table + k * stride_bytes, sum(counts) rows, shards in rank order.  The table is complete once
  *                       every rank's push has finished: the caller places ONE stream-ordered barrier between the ranks
@@ -174,6 +180,7 @@ int nwb_shard_close(nwb_ctx *ctx);
 int nwb_gather_setup(nwb_ctx *ctx, int rank, int world, int64_t capacity_rows, int ncols, void *ipc_handle_out);
 int nwb_gather_connect(nwb_ctx *ctx, const void *ipc_handles);
 int nwb_gather_push(nwb_ctx *ctx, const int64_t *counts, int counts_on_device, int engine, void **table, int64_t *stride_bytes);
+int nwb_gather_counts(nwb_ctx *ctx, int64_t *counts /* [world] */);   /* engine 2: waits for the stream; error if a rank never arrived */
 int nwb_gather_close(nwb_ctx *ctx);
 
 /* ---- the path ------------------------------------------------------------------------------------------ */

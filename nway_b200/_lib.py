@@ -52,6 +52,7 @@ EXPORTS = {
 	'nwb_gather_setup': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
 	'nwb_gather_connect': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
 	'nwb_gather_push': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_int64_p]),
+	'nwb_gather_counts': (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
 	'nwb_gather_close': (ctypes.c_int, [ctypes.c_void_p]),
 	'nwb_match': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_int64_p]),
 	'nwb_match_async': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -297,7 +298,9 @@ class Context(object):
 		import torch
 		table = ctypes.c_void_p(0)
 		stride = ctypes.c_int64(0)
-		if isinstance(counts, int):
+		if counts is None:   # engine 2: the library exchanges the counts itself
+			rc = self.lib.nwb_gather_push(self.h, None, 0, int(engine), ctypes.byref(table), ctypes.byref(stride))
+		elif isinstance(counts, int):
 			rc = self.lib.nwb_gather_push(self.h, ctypes.c_void_p(counts), 1, int(engine), ctypes.byref(table), ctypes.byref(stride))
 		else:
 			c = (ctypes.c_int64 * len(counts))(*[int(x) for x in counts])
@@ -306,6 +309,12 @@ class Context(object):
 		ncols = self.table_layout()[2]
 		dev = torch.device('cuda', self.device)
 		return torch.as_tensor(DeviceView(table.value, ncols * (stride.value // 8)), device=dev).view(ncols, stride.value // 8)
+
+	def gather_counts(self, world):
+		"""nwb_gather_counts: the ranks' row counts of the last engine-2 push (waits for the context's stream)"""
+		c = (ctypes.c_int64 * world)()
+		self.check(self.lib.nwb_gather_counts(self.h, c))
+		return [int(x) for x in c]
 
 	def gather_close(self):
 		self.check(self.lib.nwb_gather_close(self.h))

@@ -1,6 +1,7 @@
 // C ABI of the B200-native nway match path: context, buffers, stage orchestration.  See include/nwayb200.h.
 #include "../../include/nwayb200.h"
 #include "nwb_kernels.cuh"
+#include "nwb_peer.cuh"
 #include "nwb_grid_host.h"
 
 #include <cub/cub.cuh>
@@ -77,6 +78,8 @@ struct nwb_ctx {
 		long long epoch = 0;
 		int C[MAXC] = {0};
 		unsigned long long spill_cap = 0;
+		size_t off_bar = 0;                 // behind the two sets: 16 barrier words (k_peer_sync), tags only grow
+		unsigned long long bar_tag = 0;
 	} shard;
 	// table all-gather over peer memory (nwb_gather_*)
 	struct Gather {
@@ -90,6 +93,10 @@ struct nwb_ctx {
 		long long epoch = 0;
 		cudaStream_t lane[16] = {nullptr};   // copy-engine variant: one stream per destination
 		cudaEvent_t fork = nullptr, join[16] = {nullptr};
+		// engine 2 (no collective library at all): the buffer starts with a header of flag words -- row counts, their tags,
+		// completion tags (k_peer_sync) -- the sets follow at GATHER_HEADER
+		DevBuf d_counts;                // [17]: the ranks' row counts as collected by k_peer_sync, [16] = abort
+		long long *h_words = nullptr;   // pinned, mapped: the same for the host ([16] = error)
 	} gather;
 	// N >= 3 / elliptical: what the previous match of this shape left behind -- buffer capacities and launch decisions -- so
 	// that the next one can enqueue its whole pipeline behind device-side gates (k_spec_gate) without host round trips
@@ -442,6 +449,10 @@ int launch_pairs(nwb_ctx *ctx, bool dense, bool flat, bool skel, bool scat, int 
 
 }  // namespace
 
+constexpr size_t GATHER_HEADER = 4096;           // flag words of the gather buffer: payload 0, count tags 256, completion tags 512
+constexpr size_t GATHER_OFF_COUNT = 0, GATHER_OFF_COUNT_TAG = 256, GATHER_OFF_DONE_TAG = 512;
+constexpr unsigned long long PEER_TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;   // a rank that never arrives: give up after 10 s
+
 // shard mode: close the peers' exchange buffers, free the own one
 static void shard_release(nwb_ctx *ctx)
 {
@@ -464,6 +475,8 @@ static void gather_release(nwb_ctx *ctx)
 	for (auto &l : T.lane) if (l) { cudaStreamDestroy(l); l = nullptr; }
 	for (auto &e : T.join) if (e) { cudaEventDestroy(e); e = nullptr; }
 	if (T.fork) { cudaEventDestroy(T.fork); T.fork = nullptr; }
+	if (T.h_words) { cudaFreeHost(T.h_words); T.h_words = nullptr; }
+	release(T.d_counts);
 	release(T.buf);
 	T.on = T.connected = false;
 }
@@ -1451,12 +1464,15 @@ int nwb_shard_setup(nwb_ctx *ctx, int rank, int world, int64_t spill_capacity, v
 	}
 	for (int c = 1; c < nc; c++) S.off_spill[c] = take((size_t) S.spill_cap * sizeof(SpillRec));
 	S.set_bytes = off;
-	S.bytes = 2 * off;
+	S.off_bar = 2 * off;
+	S.bytes = 2 * off + 256;
 	S.epoch = 0;
+	S.bar_tag = 0;
 	// a plain cudaMalloc of its own: IPC handles cover whole allocations
 	{ int r = ensure(ctx, S.xch, S.bytes); if (r) return r; }
 	CU(cudaMemsetAsync(S.xch.p, 0, S.zero_bytes, ctx->stream));
 	CU(cudaMemsetAsync((char *) S.xch.p + S.set_bytes, 0, S.zero_bytes, ctx->stream));
+	CU(cudaMemsetAsync((char *) S.xch.p + S.off_bar, 0, 256, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	if (ipc_handle_out) {
 		cudaIpcMemHandle_t h;
@@ -1538,7 +1554,24 @@ int nwb_shard_match(nwb_ctx *ctx, int phase, int fuse_final, int64_t *nrows)
 		S.epoch++;   // the next match (or the repetition) uses the other set
 		return r;
 	}
-	return fail(ctx, NWB_ERR_ARG, "phase must be 0, 1 or 2");
+	if (phase == 3) {
+		// both halves with the barrier between them as flags in peer memory (k_peer_sync): no collective library, no
+		// return to the caller in between
+		int r = nwb_shard_match(ctx, 1, fuse_final, nullptr);
+		if (r) return r;
+		if (!ctx->h_status) CU(cudaHostAlloc((void **) &ctx->h_status, 64 * sizeof(long long), cudaHostAllocMapped));
+		ctx->h_status[45] = 0;
+		PeerSync B;
+		for (int k = 0; k < 16; k++) B.peers[k] = k < S.world ? (char *) S.peer[k] : nullptr;
+		B.tag_off = (long long) S.off_bar; B.payload_off = -1; B.tag = ++S.bar_tag; B.payload = 0;
+		B.collect_dev = nullptr; B.collect_host = ctx->h_status + 45 - 16;   // the error word lands in h_status[45]
+		B.timeout_ns = PEER_TIMEOUT_NS; B.world = S.world; B.rank = S.rank;
+		LAUNCH(ctx, k_peer_sync, 1, 32, B);
+		r = nwb_shard_match(ctx, 2, fuse_final, nrows);
+		if (ctx->h_status[45] != 0) return fail(ctx, NWB_ERR_STATE, "shard mode: a rank did not reach the barrier within 10 s");
+		return r;
+	}
+	return fail(ctx, NWB_ERR_ARG, "phase must be 0, 1, 2 or 3");
 }
 
 // ---- table all-gather over peer memory ---------------------------------------------------------------------------
@@ -1558,7 +1591,13 @@ int nwb_gather_setup(nwb_ctx *ctx, int rank, int world, int64_t capacity_rows, i
 	T.stride = ((size_t) T.cap_rows * 8 + 255) / 256 * 256;
 	T.set_bytes = T.stride * ncols;
 	T.epoch = 0;
-	{ int r = ensure(ctx, T.buf, 2 * T.set_bytes); if (r) return r; }   // a cudaMalloc of its own: IPC handles cover whole allocations
+	{ int r = ensure(ctx, T.buf, GATHER_HEADER + 2 * T.set_bytes); if (r) return r; }   // a cudaMalloc of its own: IPC handles cover whole allocations
+	{ int r = ensure(ctx, T.d_counts, 17 * sizeof(long long)); if (r) return r; }
+	CU(cudaMemsetAsync(T.buf.p, 0, GATHER_HEADER, ctx->stream));
+	CU(cudaMemsetAsync(T.d_counts.p, 0, 17 * sizeof(long long), ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (!T.h_words) CU(cudaHostAlloc((void **) &T.h_words, 32 * sizeof(long long), cudaHostAllocMapped));
+	memset(T.h_words, 0, 32 * sizeof(long long));
 	if (ipc_handle_out) {
 		cudaIpcMemHandle_t h;
 		memset(&h, 0, sizeof(h));
@@ -1605,14 +1644,18 @@ int nwb_gather_close(nwb_ctx *ctx)
 
 int nwb_gather_push(nwb_ctx *ctx, const int64_t *counts, int counts_on_device, int engine, void **table, int64_t *stride_bytes)
 {
-	if (!ctx || !counts) return NWB_ERR_ARG;
+	if (!ctx || (!counts && engine != 2)) return NWB_ERR_ARG;
 	nwb_ctx::Gather &T = ctx->gather;
 	if (!T.on || !T.connected) return fail(ctx, NWB_ERR_STATE, "nwb_gather_setup / nwb_gather_connect first");
 	if (!ctx->matched && !ctx->pending) return fail(ctx, NWB_ERR_STATE, "nwb_match has not run");
 	if (ctx->ncols != T.ncols) return fail(ctx, NWB_ERR_ARG, "the table has " + std::to_string(ctx->ncols) + " columns, nwb_gather_setup was told " + std::to_string(T.ncols));
 	if (counts_on_device && engine != 0) return fail(ctx, NWB_ERR_ARG, "the copy engines need the counts on the host");
+	if (engine == 2 && ctx->pending) return fail(ctx, NWB_ERR_STATE, "engine 2 publishes the row count of a finished match: nwb_match_wait first");
 	int64_t total = 0, off = 0;
-	if (!counts_on_device) {
+	if (engine == 2) {
+		counts = (const int64_t *) T.d_counts.p;   // filled by the count exchange below
+		counts_on_device = 1;
+	} else if (!counts_on_device) {
 		for (int r = 0; r < T.world; r++) {
 			if (counts[r] < 0) return fail(ctx, NWB_ERR_ARG, "negative row count");
 			if (r < T.rank) off += counts[r];
@@ -1623,13 +1666,23 @@ int nwb_gather_push(nwb_ctx *ctx, const int64_t *counts, int counts_on_device, i
 			return fail(ctx, NWB_ERR_NOMEM, "the gathered table (" + std::to_string(total) + " rows) exceeds the capacity given to nwb_gather_setup");
 	}
 	CU(cudaSetDevice(ctx->device));
-	const size_t set = (size_t) (T.epoch & 1) * T.set_bytes;
+	const size_t set = GATHER_HEADER + (size_t) (T.epoch & 1) * T.set_bytes;
 	T.epoch++;
 	if (table) *table = (char *) T.buf.p + set;
 	if (stride_bytes) *stride_bytes = (int64_t) T.stride;
 	const int ncols = T.ncols;
 	const long long src_stride = (long long) (((size_t) std::max<int64_t>(ctx->cols_cap_rows, 1) * 8 + 255) / 256 * 256);
-	if (engine == 0) {
+	PeerSync Y;
+	if (engine == 2) {
+		// the row counts travel as flag words: every rank writes its count into every rank's header and waits for the others'
+		for (int k = 0; k < 16; k++) Y.peers[k] = k < T.world ? (char *) T.peer[k] : nullptr;
+		Y.tag_off = (long long) GATHER_OFF_COUNT_TAG; Y.payload_off = (long long) GATHER_OFF_COUNT;
+		Y.tag = (unsigned long long) T.epoch; Y.payload = ctx->nrows;   // T.epoch was incremented above: tags start at 1
+		Y.collect_dev = (long long *) T.d_counts.p; Y.collect_host = T.h_words;
+		Y.timeout_ns = PEER_TIMEOUT_NS; Y.world = T.world; Y.rank = T.rank;
+		LAUNCH(ctx, k_peer_sync, 1, 32, Y);
+	}
+	if (engine == 0 || engine == 2) {
 		PushArgs A;
 		A.src = (const char *) ctx->d_cols.p; A.src_stride = src_stride;
 		A.counts = counts_on_device ? (const long long *) counts : nullptr;
@@ -1640,6 +1693,7 @@ int nwb_gather_push(nwb_ctx *ctx, const int64_t *counts, int counts_on_device, i
 		A.ncols = ncols; A.world = T.world; A.rank = T.rank;
 		for (int r = 0; r < 16; r++) A.dst[r] = r < T.world ? (char *) T.peer[r] + set : nullptr;
 		A.dst_stride = (long long) T.stride;
+		A.abort = engine == 2 ? (const long long *) T.d_counts.p + 16 : nullptr;
 		if (ctx->num_sms <= 0) { int nsm = 0; CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device)); ctx->num_sms = std::max(nsm, 1); }
 		// enough blocks for every link to stay busy, few enough to leave after a small table at once
 		const char *env = getenv("NWB_PUSH_BLOCKS_PER_SM");   // measurement knob (tools/bench_push.py)
@@ -1651,6 +1705,12 @@ int nwb_gather_push(nwb_ctx *ctx, const int64_t *counts, int counts_on_device, i
 		if (flavour == 1) LAUNCH(ctx, k_table_push<1>, (int) grid, PUSH_THREADS, A);
 		else if (flavour == 2) LAUNCH(ctx, k_table_push<2>, (int) grid, PUSH_THREADS, A);
 		else LAUNCH(ctx, k_table_push<0>, (int) grid, PUSH_THREADS, A);
+		if (engine == 2) {
+			// ... and so does "my push has landed": the table is complete when this kernel has seen every rank's tag
+			Y.tag_off = (long long) GATHER_OFF_DONE_TAG; Y.payload_off = -1;
+			Y.collect_dev = (long long *) T.d_counts.p;   // only its abort word is touched
+			LAUNCH(ctx, k_peer_sync, 1, 32, Y);
+		}
 		return NWB_OK;
 	}
 	const int64_t rows = counts[T.rank];
@@ -1673,6 +1733,21 @@ int nwb_gather_push(nwb_ctx *ctx, const int64_t *counts, int counts_on_device, i
 		CU(cudaEventRecord(T.join[r], T.lane[r]));
 		CU(cudaStreamWaitEvent(ctx->stream, T.join[r], 0));
 	}
+	return NWB_OK;
+}
+
+int nwb_gather_counts(nwb_ctx *ctx, int64_t *counts)
+{
+	if (!ctx || !counts) return NWB_ERR_ARG;
+	nwb_ctx::Gather &T = ctx->gather;
+	if (!T.on || !T.connected || !T.h_words) return fail(ctx, NWB_ERR_STATE, "nwb_gather_setup / nwb_gather_connect first");
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (T.h_words[16] != 0) return fail(ctx, NWB_ERR_STATE, "table gather: a rank did not arrive within 10 s");
+	int64_t total = 0;
+	for (int r = 0; r < T.world; r++) { counts[r] = T.h_words[r]; total += counts[r]; }
+	if (total > T.cap_rows)
+		return fail(ctx, NWB_ERR_NOMEM, "the gathered table (" + std::to_string(total) + " rows) exceeds the capacity given to nwb_gather_setup");
 	return NWB_OK;
 }
 

@@ -2126,6 +2126,7 @@ struct PushArgs {
 	int ncols, world, rank;
 	char *dst[16];               // the ranks' gathered tables (this set)
 	long long dst_stride;        // bytes between the gathered table's columns
+	const long long *abort;      // device word, non-zero = the count exchange before this kernel failed (k_peer_sync); may be null
 };
 
 constexpr int PUSH_THREADS = 512;
@@ -2149,7 +2150,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_table_push(PushArgs A)
 		if (r == A.rank) rows = c;
 		total += c;
 	}
-	if (total > A.cap_rows) return;   // the host sees the same counts and reports it
+	if (total > A.cap_rows || (A.abort && __ldg(A.abort) != 0)) return;   // the host sees the same counts / flag and reports it
 	const long long dst_off = off * 8;
 	// work items of up to 512 KB (long runs per link: 6.28 ms instead of 6.49 ms for 8 x 590 MB), smaller for a small table so
 	// that every block still gets a few

@@ -101,7 +101,8 @@ class TableGather(object):
 	returns this rank's complete (ncols, total) table as a torch view, valid until the next-but-one call.  The context
 	works on `stream` (a torch stream; default: one of its own), and so do the count exchange and the barrier.  The row
 	counts are all-gathered on the device straight into the push kernel's argument, so nothing between the match and
-	the complete table waits for the host."""
+	the complete table waits for the host.  engine: 0 = SM stores, counts and barrier through NCCL; 1 = copy engines; 2 = SM
+	stores with the counts and the barrier as flag words in peer memory -- nothing of torch.distributed per gather."""
 
 	def __init__(self, group=None, device=None, stream=None, engine=0):
 		import torch
@@ -151,6 +152,11 @@ class TableGather(object):
 		import torch
 		import torch.distributed as dist
 		assert self.ready_for is ctx, 'TableGather.setup first'
+		if self.engine == 2:
+			# no collective library at all: counts and completion travel as flag words in peer memory (k_peer_sync)
+			wide = ctx.gather_push(None, 2)
+			counts = ctx.gather_counts(self.world)   # waits for the stream: the table is complete
+			return wide[:, :sum(counts)], counts
 		with torch.cuda.stream(self.stream):
 			if counts is None and self.engine == 1:
 				counts = exchange_counts(ctx.table_layout()[3], self.group, self.dev)
@@ -277,10 +283,11 @@ class ScatterMatcher(object):
 	context's stream: stream-ordered, no host synchronisation; one is enough because the exchange buffers are double-
 	buffered (include/nwayb200.h)."""
 
-	def __init__(self, group=None, device=None, spill_capacity=65536):
+	def __init__(self, group=None, device=None, spill_capacity=65536, peer_barrier=True):
 		import torch
 		import torch.distributed as dist
 		self.group = group
+		self.peer_barrier = peer_barrier   # the barrier as flags in peer memory (nwb_shard_match phase 3) instead of an NCCL all-reduce
 		self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
 		self.device = torch.cuda.current_device() if device is None else device
 		self.dev = torch.device('cuda', self.device)
@@ -312,9 +319,12 @@ class ScatterMatcher(object):
 			self.setup(ctx)
 		with torch.cuda.stream(self.stream):
 			for attempt in range(4):
-				ctx.shard_match(1)
-				self.barrier()
-				nrows, retry = ctx.shard_match(2, fuse_final)
+				if self.peer_barrier:
+					nrows, retry = ctx.shard_match(3, fuse_final)
+				else:
+					ctx.shard_match(1)
+					self.barrier()
+					nrows, retry = ctx.shard_match(2, fuse_final)
 				# "a grid buffer was too small": a property of the (replicated) primaries, so every rank takes the same
 				# decision without asking the others
 				if not retry:
@@ -327,7 +337,7 @@ class ScatterMatcher(object):
 		self.ready_for = None
 
 
-def nway_match_scatter(match_tables, match_radius, prior_completeness, gather='all', group=None, device=None, **kwargs):
+def nway_match_scatter(match_tables, match_radius, prior_completeness, gather='all', group=None, device=None, peer_barrier=True, **kwargs):
 	"""nway_match() with the streaming of the secondaries shared between the ranks (strong scaling; see ScatterMatcher).
 	Every rank passes the same catalogues.  gather as in nway_match_sharded: 'all' / 'rank0' / 'none'.  Automatic
 	magnitude histograms are not available in this mode (supply maghists)."""
@@ -342,7 +352,7 @@ def nway_match_scatter(match_tables, match_radius, prior_completeness, gather='a
 		device = torch.cuda.current_device()
 	dev = torch.device('cuda', device)
 	ctx = _lib.get_context(device)
-	matcher = ScatterMatcher(group, device)
+	matcher = ScatterMatcher(group, device, peer_barrier=peer_barrier)
 	kwargs['as_frame'] = False
 	kwargs['keep_on_device'] = True
 	try:

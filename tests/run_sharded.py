@@ -39,7 +39,7 @@ def main():
 	ctx = _lib.get_context(local)
 	names = list(mine['selectors'].keys())
 	assert names == list(full.keys())
-	for engine in (0, 1):
+	for engine in (0, 1, 2):   # 2: counts and barrier as flag words in peer memory, nothing of NCCL per gather
 		tg = parallel.TableGather(None, local, engine=engine)
 		tg.setup(ctx, len(full['A']) + 8, len(names))
 		for again in range(3):
@@ -68,6 +68,10 @@ def main():
 	for k in full:
 		assert got2[k].shape == full[k].shape, ('scatter', k, got2[k].shape, full[k].shape)
 		assert np.array_equal(got2[k], full[k], equal_nan=True), ('scatter', k)
+	# ... with the NCCL all-reduce as the barrier instead of the flags in peer memory
+	got3 = parallel.nway_match_scatter(tables, 7.0, 0.9, gather='all', device=local, logger=nway_b200.NullOutputLogger(), peer_barrier=False)
+	for k in full:
+		assert np.array_equal(got3[k], full[k], equal_nan=True), ('scatter, NCCL barrier', k)
 	# ... also for two catalogues (the specialised row kernel) and on an off-equator flat field (NWB_COMPAT_FLAT_HASH)
 	for name in ('syn2', 'offeq3'):
 		spec = cases.GOLDEN_CASES[name]

@@ -16,7 +16,9 @@ on the matching stream, maximum over the ranks; rank 0 prints one JSON line per 
   "plain"    (N = 1 only) nwb_match on one GPU
   "scatter"  shard mode, table left sharded by primary blocks
   "scatter+gather"  ... plus the all-gather-v of the table to every rank (torch.distributed / NCCL, parallel.allgather_table)
-  "scatter+peer gather"  ... the same reassembly over peer memory (parallel.TableGather / nwb_gather_*)
+  "scatter+peer gather"  ... the same reassembly over peer memory (parallel.TableGather / nwb_gather_*), row counts and
+                         barrier as flag words in peer memory too ("..., NCCL counts": those two through NCCL)
+  "scatter, NCCL barrier"  shard mode with an NCCL all-reduce between its halves instead of the flags in peer memory
 """
 import argparse
 import json
@@ -133,6 +135,12 @@ def main():
 			ctx.set_stream(None)
 		else:
 			stage_plain = None
+		if world > 1:   # for comparison: the barrier between the two halves as an NCCL all-reduce
+			m0 = parallel.ScatterMatcher(None, local, peer_barrier=False)
+			m0.setup(ctx)
+			with torch.cuda.stream(m0.stream):
+				timed(lambda: m0(ctx, True), 'scatter, NCCL barrier', args.steps)
+			m0.close(ctx)
 		matcher = parallel.ScatterMatcher(None, local)
 		xbytes = matcher.setup(ctx)
 		with torch.cuda.stream(matcher.stream):
@@ -154,22 +162,23 @@ def main():
 			# ... and the reassembly over peer memory (nwb_gather_*): each GPU stores its rows into every rank's table
 			tot = torch.tensor([matcher(ctx, True)], dtype=torch.int64, device=dev)
 			dist.all_reduce(tot)
-			tg = parallel.TableGather(None, local, stream=matcher.stream)
-			tg.setup(ctx, int(tot.item()) + 4096, ctx.table_layout()[2])
-			last = {}
+			for label, engine in (('scatter+peer gather, NCCL counts', 0), ('scatter+peer gather', 2)):
+				tg = parallel.TableGather(None, local, stream=matcher.stream, engine=engine)
+				tg.setup(ctx, int(tot.item()) + 4096, ctx.table_layout()[2])
+				last = {}
 
-			def with_peer_gather():
-				nr = matcher(ctx, True)
-				last['t'], last['c'] = tg(ctx)
-				return nr
-			timed(with_peer_gather, 'scatter+peer gather', args.steps)
-			assert last['t'].shape == gtab['t'].shape and torch.equal(last['t'], gtab['t']), 'the two reassemblies disagree'
-			tg.close(ctx)
+				def with_peer_gather():
+					nr = matcher(ctx, True)
+					last['t'], last['c'] = tg(ctx)
+					return nr
+				timed(with_peer_gather, label, args.steps)
+				assert last['t'].shape == gtab['t'].shape and torch.equal(last['t'], gtab['t']), 'the two reassemblies disagree'
+				tg.close(ctx)
 		matcher.close(ctx)
 		if rank == 0:
 			base = None
 			for label, ms, rows in results:
-				if label in ('plain', 'scatter') and base is None:
+				if base is None:
 					base = rows
 				assert rows == base, (label, rows, base)   # every mode produces the same number of rows
 				print(json.dumps(dict(config=name, n_gpus=world, mode=label, sizes=list(sizes), radius_arcsec=radius, rows=rows, device_ms=ms,
