@@ -110,3 +110,23 @@ def test_c5_like_four_catalogues_elliptical_and_magnitude_priors():
 	part = {k: np.asarray(v)[rows] for k, v in got.items() if not k.startswith('_')}
 	ref['A'] = pick[ref['A']]
 	parity.assert_tables_match(ref, part, columns=[c for c in ref if not c.startswith('_')], context='C5-like subset')
+
+
+@pytest.mark.parametrize('ra0,dec0', [(100.0, 35.0), (352.0, -20.0), (40.0, 80.0)])
+def test_sparse_patch_streams_through_the_filter(ra0, dec0):
+	"""few primaries, a long secondary catalogue, NOT the whole sky: the two-kernel stream (k_filter with the shared-memory
+	bitmap on a grid that does not span the circle, across ra = 0, near a pole) against the oracle's whole table"""
+	import nway_b200
+	from nway_b200 import _lib
+	from oracle import nway_oracle as O
+	tables = cases.uniform_patch(int(ra0) + 7, (2500, 2300000), (1.0, 0.4), 16.0, ra0=ra0, dec0=dec0)
+	for t in tables:   # positions beyond 360 deg / 90 deg folded back onto the sphere
+		t['ra'] = np.mod(t['ra'], 360.0)
+		over = t['dec'] > 90.0
+		t['dec'] = np.where(over, 180.0 - t['dec'], t['dec'])
+		t['ra'] = np.where(over, np.mod(t['ra'] + 180.0, 360.0), t['ra'])
+	got = nway_b200.nway_match(tables, 6.0, 0.9, logger=nway_b200.NullOutputLogger(), as_frame=False)
+	check_properties(got, ['A', 'B'], 2500, 6.0)
+	ref = O.nway_match(tables, 6.0, 0.9)
+	parity.assert_tables_match(ref, got, columns=[c for c in ref if not c.startswith('_')], context='sparse patch at (%g, %g)' % (ra0, dec0))
+
