@@ -129,4 +129,15 @@ def test_sparse_patch_streams_through_the_filter(ra0, dec0):
 	check_properties(got, ['A', 'B'], 2500, 6.0)
 	ref = O.nway_match(tables, 6.0, 0.9)
 	parity.assert_tables_match(ref, got, columns=[c for c in ref if not c.startswith('_')], context='sparse patch at (%g, %g)' % (ra0, dec0))
+	# ... and it did take that route: the long catalogue costs launches (bitmap, k_filter, the fallback k_pairs) that the
+	# same field with a short catalogue -- streamed by k_pairs alone -- does not
+	ctx = _lib.get_context()
+	def launches_of(tabs):
+		nway_b200.nway_match(tabs, 6.0, 0.9, logger=nway_b200.NullOutputLogger(), as_frame=False)   # sizes the buffers
+		nway_b200.nway_match(tabs, 6.0, 0.9, logger=nway_b200.NullOutputLogger(), as_frame=False)
+		return ctx.launch_count()   # kernels of the last match
+	short = [dict(tables[0]), dict(tables[1])]
+	for k in ('ra', 'dec', 'error'):
+		short[1][k] = tables[1][k][:200000]
+	assert launches_of(tables) >= launches_of(short) + 2
 
