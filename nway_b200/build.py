@@ -6,8 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libnwayb200.so')
-SOURCES = ['nwb_api.cu']
-HEADERS = ['nwb_device.cuh', 'nwb_grid.cuh', 'nwb_grid_host.h', 'nwb_rows.cuh', 'nwb_kernels.cuh', os.path.join('..', '..', 'include', 'nwayb200.h')]
+SOURCES = ['nwb_api.cu']   # one translation unit; it includes every header of csrc/ and include/nwayb200.h
 
 NVCC_FLAGS = [
 	'-gencode', 'arch=compute_100a,code=sm_100a',
@@ -18,12 +17,36 @@ NVCC_FLAGS = [
 ]
 
 
+STAMP = LIB + '.srchash'   # what the library was built from (travels with it; file times do not always survive a copy)
+
+
+def dependencies():
+	"""every file the library is compiled from: all of csrc/ and the public header"""
+	deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cu', '.cuh', '.h'))]
+	return deps + [os.path.join(HERE, '..', 'include', 'nwayb200.h')]
+
+
+def source_hash():
+	"""sha256 over the compiler flags and the contents of dependencies()"""
+	import hashlib
+	h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+	for d in dependencies():
+		h.update(os.path.basename(d).encode())
+		with open(d, 'rb') as f:
+			h.update(f.read())
+	return h.hexdigest()
+
+
 def needs_build():
+	"""stale = built from other sources or flags.  Decided by content where the stamp written by build() is there, by
+	file times otherwise (a library built by hand)."""
 	if not os.path.exists(LIB):
 		return True
+	if os.path.exists(STAMP):
+		with open(STAMP) as f:
+			return f.read().strip() != source_hash()
 	t = os.path.getmtime(LIB)
-	deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-	return any(os.path.getmtime(d) > t for d in deps)
+	return any(os.path.getmtime(d) > t for d in dependencies() + [os.path.abspath(__file__)])
 
 
 def build_variant(out, defines):
@@ -42,6 +65,9 @@ def build(force=False, verbose=False):
 		return LIB
 	nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 	cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB, '-lcudart']
+	stamp = source_hash()
+	if os.path.exists(STAMP):
+		os.remove(STAMP)
 	res = subprocess.run(cmd, capture_output=True, text=True)
 	if res.returncode != 0 or (verbose and os.environ.get("NWB_BUILD_VERBOSE")):
 		sys.stderr.write(res.stdout + res.stderr)
@@ -49,6 +75,8 @@ def build(force=False, verbose=False):
 		raise RuntimeError('nvcc failed building libnwayb200.so')
 	with open(os.path.join(HERE, 'build.log'), 'w') as f:
 		f.write(' '.join(cmd) + '\n' + res.stdout + res.stderr)
+	with open(STAMP, 'w') as f:
+		f.write(stamp + '\n')
 	return LIB
 
 

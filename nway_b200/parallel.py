@@ -279,9 +279,10 @@ class ScatterMatcher(object):
 	the dominant cost when secondaries outnumber primaries by orders of magnitude -- divides by the number of GPUs.
 
 	One instance per (process group, context); __call__(ctx, fuse_final) runs one match: phase 1 (grid + streaming,
-	matches arrive from all ranks) | barrier | phase 2 (rows).  The barrier is an NCCL all-reduce of one word on the
-	context's stream: stream-ordered, no host synchronisation; one is enough because the exchange buffers are double-
-	buffered (include/nwayb200.h)."""
+	matches arrive from all ranks) | barrier | phase 2 (rows).  The barrier is stream-ordered, no host synchronisation,
+	and one is enough because the exchange buffers are double-buffered (include/nwayb200.h): by default flag words in
+	peer memory (peer_barrier=True: nwb_shard_match phase 3 enqueues phase 1, the flag exchange and phase 2 itself --
+	nothing of torch.distributed per match), else an NCCL all-reduce of one word on the context's stream."""
 
 	def __init__(self, group=None, device=None, spill_capacity=65536, peer_barrier=True):
 		import torch
@@ -300,10 +301,26 @@ class ScatterMatcher(object):
 	def setup(self, ctx):
 		"""exchange buffers + peer mapping for the catalogues / radius now set on the context (collective)"""
 		import torch.distributed as dist
-		handle, nbytes = ctx.shard_setup(self.rank, self.world, self.spill_capacity)
+		# as in TableGather.setup: a failure on one rank (no peer access, out of memory) is exchanged, and all ranks
+		# raise together instead of leaving the others waiting in a collective
+		try:
+			(handle, nbytes), err = ctx.shard_setup(self.rank, self.world, self.spill_capacity), None
+		except Exception as e:
+			(handle, nbytes), err = (None, 0), repr(e)
 		handles = [None] * self.world
-		dist.all_gather_object(handles, handle, group=self.group)
-		ctx.shard_connect(handles)
+		dist.all_gather_object(handles, (handle, err), group=self.group)
+		if any(h is None for h, _ in handles):
+			raise RuntimeError('ScatterMatcher.setup failed: ' + '; '.join('rank %d: %s' % (r, e) for r, (h, e) in enumerate(handles) if h is None))
+		try:
+			ctx.shard_connect([h for h, _ in handles])
+			err = None
+		except Exception as e:
+			err = repr(e)
+		errs = [None] * self.world
+		dist.all_gather_object(errs, err, group=self.group)
+		if any(e is not None for e in errs):
+			ctx.shard_close()
+			raise RuntimeError('ScatterMatcher.setup failed: ' + '; '.join('rank %d: %s' % (r, e) for r, e in enumerate(errs) if e is not None))
 		ctx.set_stream(self.stream.cuda_stream)
 		self.ready_for = ctx
 		return nbytes

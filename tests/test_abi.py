@@ -32,6 +32,23 @@ def test_library_exports_every_declared_symbol():
 	assert _lib.load().nwb_version() >= 100
 
 
+def test_build_is_stale_by_content_not_by_file_time(monkeypatch):
+	"""build() stamps the library with the hash of its sources and flags: a copy of the tree whose file times changed
+	(the push to the GPU box) is not rebuilt, a changed source is"""
+	from nway_b200 import build
+	build.build()
+	assert os.path.exists(build.STAMP) and not build.needs_build()
+	assert len(build.dependencies()) >= 8 and all(os.path.exists(d) for d in build.dependencies())
+	old = os.stat(build.LIB)
+	os.utime(build.LIB, (old.st_atime, old.st_mtime - 10 * 365 * 86400))   # the library looks ten years older than its sources
+	try:
+		assert not build.needs_build()
+	finally:
+		os.utime(build.LIB, (old.st_atime, old.st_mtime))
+	monkeypatch.setattr(build, 'NVCC_FLAGS', build.NVCC_FLAGS + ['-DSOMETHING_ELSE'])
+	assert build.needs_build()
+
+
 def test_no_cpu_fallback_without_device():
 	"""the product path must fail loudly, not fall back, when no CUDA device is present"""
 	import torch

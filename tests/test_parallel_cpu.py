@@ -65,6 +65,83 @@ def worker(rank, world, port, ret):
 		dist.destroy_process_group()
 
 
+class FakeContext(object):
+	"""stands in for _lib.Context in the collective set-up handshakes: fails where it is told to"""
+
+	def __init__(self, rank, fail_setup_on=None, fail_connect_on=None):
+		self.rank, self.fail_setup_on, self.fail_connect_on = rank, fail_setup_on, fail_connect_on
+		self.closed = 0
+		self.stream = 'unset'
+
+	def shard_setup(self, rank, world, spill_capacity):
+		if rank == self.fail_setup_on:
+			raise RuntimeError('no memory on rank %d' % rank)
+		return bytes([rank]) * 64, 4096
+
+	def gather_setup(self, rank, world, capacity_rows, ncols):
+		return self.shard_setup(rank, world, 0)[0]
+
+	def shard_connect(self, handles):
+		assert [h[0] for h in handles] == list(range(len(handles))) and all(len(h) == 64 for h in handles)
+		if self.rank == self.fail_connect_on:
+			raise RuntimeError('no peer access on rank %d' % self.rank)
+
+	gather_connect = shard_connect
+
+	def shard_close(self):
+		self.closed += 1
+
+	gather_close = shard_close
+
+	def set_stream(self, s):
+		self.stream = s
+
+
+class FakeStream(object):
+	cuda_stream = 1234
+
+
+def handshake_worker(rank, world, port, ret):
+	os.environ['MASTER_ADDR'] = '127.0.0.1'
+	os.environ['MASTER_PORT'] = str(port)
+	dist.init_process_group('gloo', rank=rank, world_size=world)
+	try:
+		def bare(cls):
+			m = object.__new__(cls)   # the constructors allocate on a CUDA device
+			m.group, m.rank, m.world, m.stream, m.ready_for = None, rank, world, FakeStream(), None
+			m.spill_capacity = 65536
+			return m
+		for cls, setup in ((parallel.ScatterMatcher, lambda m, c: m.setup(c)), (parallel.TableGather, lambda m, c: m.setup(c, 1000, 12))):
+			# a failure on ONE rank, in either step: EVERY rank raises and names it; nobody is left in a collective
+			for kw, culprit, word in ((dict(fail_setup_on=1), 1, 'no memory'), (dict(fail_connect_on=0), 0, 'no peer access')):
+				m, ctx = bare(cls), FakeContext(rank, **kw)
+				with pytest.raises(RuntimeError) as info:
+					setup(m, ctx)
+				assert 'rank %d' % culprit in str(info.value) and word in str(info.value), str(info.value)
+				assert m.ready_for is None
+				assert ctx.closed == (1 if 'fail_connect_on' in kw else 0)
+			m, ctx = bare(cls), FakeContext(rank)
+			setup(m, ctx)
+			assert m.ready_for is ctx and ctx.closed == 0
+			if cls is parallel.ScatterMatcher:
+				assert ctx.stream == FakeStream.cuda_stream
+		ret[rank] = 'ok'
+	except BaseException as e:
+		ret[rank] = repr(e)
+	finally:
+		dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world2_setup_failure_on_one_rank_raises_on_every_rank():
+	world = 2
+	port = free_port()
+	with mp.Manager() as mgr:
+		ret = mgr.dict()
+		mp.spawn(handshake_worker, args=(world, port, ret), nprocs=world, join=True)
+		assert dict(ret) == {0: 'ok', 1: 'ok'}, dict(ret)
+
+
 def test_shard_ranges_cover_the_primaries():
 	for n in (0, 1, 7, 100000, 1000003):
 		for world in (1, 2, 3, 8):
