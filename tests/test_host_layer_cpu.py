@@ -1,0 +1,177 @@
+"""CPU: the host layers above the C ABI, end to end, with the oracle standing in for the library's numeric stages
+(tests/oraclectx.py installs a stand-in for nway_b200._lib.Context -- TEST INFRASTRUCTURE, never the product path).
+
+What this covers that the other CPU tests do not: the orchestration of nway_b200.nway_match (scalar tables, installation of
+user histograms, the host half of the automatic histograms, the order of the stages, truncation, the logger, exceptions,
+the DataFrame), and nway_b200/cli.py from argv to the FITS table -- compared with the oracle AND with the committed
+outputs of the unmodified reference (tests/golden/ref_*.npz, ref_cli_*.npz), the same files the GPU tests use.
+The CUDA kernels are not involved here; their parity is tests/test_gpu_*.py."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import cases, cliparity, oraclectx, parity
+
+
+@pytest.fixture
+def hostctx(monkeypatch):
+	import nway_b200
+	ctx = oraclectx.OracleContext()
+	monkeypatch.setattr(nway_b200._lib, 'get_context', lambda device=None: ctx)
+	return ctx
+
+
+class Recorder(object):
+	def __init__(self):
+		self.lines, self.warnings = [], []
+
+	def log(self, *msg):
+		self.lines.append(' '.join(str(m) for m in msg))
+
+	def warn(self, msg):
+		self.warnings.append(msg)
+
+
+def run_host(tables, radius, completeness, **kw):
+	import nway_b200
+	kw.setdefault('logger', nway_b200.NullOutputLogger())
+	kw.setdefault('store_mag_hists', False)
+	kw.setdefault('as_frame', False)
+	return nway_b200.nway_match(tables, radius, completeness, **kw)
+
+
+@pytest.mark.parametrize('name', ['cosmos2_magradius', 'cosmos3_magauto', 'syn2_maghist', 'syn3_pcvec', 'syn4_minprob', 'offeq3_south'])
+def test_nway_match_host_logic_against_oracle_and_reference(name, hostctx):
+	"""automatic histograms by radius and by posterior (two columns), user histograms, completeness vector, truncation,
+	a flat field off the equator: the product's host code around the stand-in == the oracle's own nway_match == the
+	unmodified reference's committed output"""
+	from oracle import nway_oracle as O
+	spec = cases.GOLDEN_CASES[name]
+	kw = spec.get('kwargs', {})
+	tables = cases.build_case(name)
+	kept = [[np.array(m) for m in t['mags']] for t in tables]
+	got = run_host(tables, spec['radius'], spec['completeness'], **kw)
+	for t, mags in zip(tables, kept):   # unlike the reference (__init__.py:318-319) the caller's magnitudes are left alone
+		assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(t['mags'], mags))
+	ref = O.nway_match(cases.build_case(name), spec['radius'], spec['completeness'], **kw)
+	cols = [c for c in ref if not c.startswith('_')]
+	assert list(got.keys()) == cols
+	for c in cols:
+		assert got[c].dtype == (np.int64 if ref[c].dtype.kind in 'iu' else np.float64), c
+	parity.assert_tables_match(ref, got, columns=cols, context=name)
+	parity.check_against_digest(name, got, [t['name'] for t in tables])
+	auto = any(h is None for t in tables for h in t['maghists'])
+	want = ['match(fuse_final=0)', 'finalize'] if auto else ['match(fuse_final=1)']
+	assert hostctx.calls == want + (['truncate'] if kw.get('min_prob', 0) > 0 else [])
+
+
+def test_log_lines_files_and_frame(hostctx, tmp_path, monkeypatch):
+	"""the messages of nwaylib.nway_match in its order (__init__.py:86,188,207,221,312,363,368,400-401,468), the
+	*_fit.txt tables (:369-373) and the returned frame"""
+	import pandas
+	monkeypatch.chdir(tmp_path)
+	log = Recorder()
+	tables = cases.cosmos_subset(3, mags=True)
+	frame = run_host(tables, 20, 0.9, mag_include_radius=25.0, min_prob=0.001, logger=log, store_mag_hists=True, as_frame=True)
+	assert isinstance(frame, pandas.DataFrame)
+	assert list(frame.columns[:3]) == ['XMM', 'OPT', 'IRAC'] and list(frame.columns[-3:]) == ['match_flag', 'prob_has_match', 'prob_this_match']
+	assert frame['XMM'].dtype == np.int64 and frame['match_flag'].dtype == np.int64 and frame['ncat'].dtype == np.int64
+	assert frame['Separation_XMM_OPT'].dtype == np.float64 and not (frame['prob_this_match'] < 0.001).any()
+	assert log.warnings == ['WARNING: magnitude radius is very large (>= matching radius). Consider using a smaller value.']
+	want = ['Primary catalogue "XMM" (1797), density gives 3.71e+07 objects on entire sky',
+		'Computing distance-based probabilities ...',
+		'matching: 387601 matches after filtering by search radius',
+		'Incorporating bias "OPT:MAG" ...',
+		'magnitude histogram stored to "OPT_MAG_fit.txt".',
+		'Incorporating bias "IRAC:mag_ch1" ...',
+		'magnitude histogram stored to "IRAC_mag_ch1_fit.txt".',
+		'',
+		'Computing final probabilities ...']
+	found = [l for l in log.lines if l in want]
+	assert found == want, log.lines
+	counts = [l for l in log.lines if l.startswith('magnitude histogram of column')]
+	assert len(counts) == 2 and counts[0].startswith('magnitude histogram of column "OPT_MAG": ') and ' secure matches, ' in counts[0]
+	assert log.lines[-1].startswith('    cutting away ') and log.lines[-1].endswith(' (below p_i minimum)')
+	for col in ('OPT_MAG', 'IRAC_mag_ch1'):
+		text = open('%s_fit.txt' % col).read().splitlines()
+		assert text[0] == '# lo hi selected others'
+		rows = np.loadtxt('%s_fit.txt' % col)
+		assert 2 <= len(rows) <= 17 and rows.shape[1] == 4 and (rows[1:, 0] == rows[:-1, 1]).all()
+		assert all(len(l) == 43 for l in text[1:])   # four '%10.5f' fields
+
+
+def test_errors_before_and_after_the_match(hostctx):
+	import nway_b200
+	far = cases.uniform_patch(1, (20, 200), (1.0, 0.5), 0.01)
+	far[1]['ra'] += 5.0
+	alone = run_host(far, 5.0, 0.9)   # no secondary in reach: every primary keeps its no-counterpart row (fastskymatch.py:178-181)
+	assert np.array_equal(alone['A'], np.arange(20)) and (alone['B'] == -1).all() and (alone['prob_has_match'] == 0).all()
+	with pytest.raises(nway_b200.EmptyResultException):   # only a table without primaries is empty (__init__.py:92-93)
+		run_host(far, 5.0, 0.9, primary_range=(5, 0))
+	empty = run_host(far, 5.0, 0.9, primary_range=(5, 0), allow_empty=True)
+	assert list(empty.keys())[:2] == ['A', 'B'] and all(len(v) == 0 for v in empty.values())
+	few = cases.with_mags(cases.uniform_patch(2, (50, 1500), (1.0, 0.3), 0.02), 4, cats=(1,), hist=False)
+	with pytest.raises(nway_b200.UndersampledException) as info:
+		run_host(few, 5.0, 0.9, mag_include_radius=1.0)
+	assert 'too few secure matches' in str(info.value)
+	ok = cases.uniform_patch(3, (30, 300, 300), (1.0, 0.5, 0.5), 0.01)
+	with pytest.raises(Exception) as info:
+		run_host(ok, 5.0, [1.0, 0.9])
+	assert 'Prior completeness needs one value per catalog' in str(info.value)
+	with pytest.raises(ValueError):
+		run_host(ok, 5.0, 0.9, unrelated_mode='both')
+	with pytest.raises(ValueError):
+		run_host(ok[:1], 5.0, 0.9)
+	many = cases.with_mags(cases.uniform_patch(3, (30, 300, 300), (1.0, 0.5, 0.5), 0.01), 5, cats=(1, 2), ncols=5)
+	with pytest.raises(ValueError) as info:
+		run_host(many, 5.0, 0.9)
+	assert 'magnitude columns' in str(info.value)
+	wide = cases.with_mags(cases.uniform_patch(3, (30, 300), (1.0, 0.5), 0.01), 5, cats=(1,))
+	wide[1]['maghists'] = [cases.fixed_hist(1, nbins=65)]
+	with pytest.raises(ValueError) as info:
+		run_host(wide, 5.0, 0.9)
+	assert '65 bins' in str(info.value)
+
+
+def test_primary_ranges_concatenate_to_the_whole_table(hostctx):
+	"""what nway_b200.parallel relies on: the rows of a block of primaries are the same rows the whole match holds"""
+	spec = cases.GOLDEN_CASES['syn3']
+	whole = run_host(cases.build_case('syn3'), spec['radius'], spec['completeness'])
+	n0 = len(cases.build_case('syn3')[0]['ra'])
+	parts = [run_host(cases.build_case('syn3'), spec['radius'], spec['completeness'], primary_range=r, allow_empty=True)
+		for r in ((0, 170), (170, 1), (171, n0 - 171))]
+	for c in whole:
+		assert np.array_equal(np.concatenate([p[c] for p in parts]), whole[c], equal_nan=True), c
+	assert hostctx.primary_range == (171, n0 - 171)
+	run_host(cases.build_case('syn3'), spec['radius'], spec['completeness'])
+	assert hostctx.primary_range == (0, -1)   # a plain call clears the range of the previous one
+
+
+def run_cli_host(name, tmp_path, extra=()):
+	from nway_b200 import cli, fitsio
+	paths = cases.write_cosmos_subset_fits(str(tmp_path))
+	out = str(tmp_path / (name + '.fits'))
+	cwd = os.getcwd()
+	os.chdir(str(tmp_path))
+	try:
+		rc = cli.main(cases.cli_args(name, paths, out) + list(extra))
+	finally:
+		os.chdir(cwd)
+	assert rc == 0
+	t = fitsio.read_table(out)
+	cards, _ = fitsio._read_header(open(out, 'rb').read(), 0)
+	return t, cards
+
+
+@pytest.mark.parametrize('name', ['cli2', 'cli3_magauto', 'cli3_bayes', 'cli3_minprob', 'cli3_prefilter'])
+def test_cli_from_argv_to_fits_against_reference_cli(name, tmp_path, hostctx, capsys):
+	"""nway.py's layer (arguments, error columns, the merged input columns, column order and FITS formats, header keys,
+	the FITS writer and reader) around the stand-in: bit for bit the table of the unmodified reference script"""
+	t, cards = run_cli_host(name, tmp_path)
+	got = {n: t.data[n] for n in t.columns}
+	cliparity.check_against_cli_digest(name, got, exact=True, check_layout=True, formats=dict(zip(t.columns, t.formats)), header=cards)
+	assert t.name == 'NWAYMATCH' and cards['METHOD'] == 'NWAY multi-way matching'
+	assert cards['NWAYCMD'].startswith('nway.py --radius')
+	out = capsys.readouterr().out
+	assert 'writing "%s" (%d rows, %d columns) ...' % (str(tmp_path / (name + '.fits')), len(t), len(t.columns)) in out
