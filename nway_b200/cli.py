@@ -81,7 +81,7 @@ def build_parser():
 
 
 class PrintLogger(object):
-	"""logger duck type of nwaylib.logger printing to stdout like nway.py does"""
+	"""logger duck type of nwaylib.logger printing to stdout (the helper programs report this way)"""
 
 	def log(self, *msg):
 		print(' '.join(str(m) for m in msg))
@@ -90,8 +90,67 @@ class PrintLogger(object):
 		print(msg)
 
 	def progress(self, *args, **kwargs):
-		from .logger import _PassThroughBar
-		return _PassThroughBar()
+		from .logger import _Identity
+		return _Identity()
+
+
+class TranscriptLogger(object):
+	"""logger duck type of nwaylib.logger for the match of the command-line program.  nway.py computes everything in its own
+	script body and prints to stdout as it goes; here the same work is one nway_match() call that reports through its
+	logger with the API's wording.  This logger keeps what belongs to the script's transcript -- per magnitude column the
+	histogram lines (nway.py:495-497), the truncation line (:583) -- for main() to print in nway.py's order and wording,
+	and passes the rest to stderr, where the reference's matching stage (fastskymatch.py:243-252,335 through
+	logger.NormalLogger) writes too."""
+
+	def __init__(self):
+		self.column = None
+		self.histogram_lines = OrderedDict()   # 'TABLE:column' -> lines
+		self.truncation_line = None
+
+	def log(self, *msg):
+		msg = ' '.join(str(m) for m in msg)
+		if msg.startswith('Incorporating bias "') and msg.endswith('" ...'):
+			self.column = msg[len('Incorporating bias "'):-len('" ...')]
+			self.histogram_lines[self.column] = []
+		elif msg.startswith('magnitude histogram of column ') or msg.startswith('magnitude histogram stored to '):
+			self.histogram_lines[self.column].append('    ' + msg)
+		elif msg.lstrip().startswith('cutting away '):
+			self.truncation_line = msg
+		elif msg.startswith('matching: '):
+			sys.stderr.write(msg + '\n')
+		# anything else (densities, stage headings, user-supplied histograms) is printed by main() itself, as nway.py does
+
+	def warn(self, msg):
+		pass   # the one warning of the path (magnitude radius >= match radius) is printed per column by main(), nway.py:458-459
+
+	def progress(self, *args, **kwargs):
+		from .logger import _Identity
+		return _Identity()
+
+
+def offset_run_command(argv, first_catalogue, shiftfile, shiftoutfile):
+	"""this run's command line turned into the one for the offset catalogue of the calibration recipe (nway.py:597-622):
+	the primary catalogue replaced by the offset one, every `--mag T:col auto` by the histogram file this run has written,
+	the output by its own file"""
+	out = []
+	k = 0
+	while k < len(argv):
+		word = argv[k]
+		if word == first_catalogue:
+			out.append(shiftfile)
+		elif word == '--mag' and k + 2 < len(argv):
+			column, histogram = argv[k + 1], argv[k + 2]
+			out += [word, column, column.replace(':', '_') + '_fit.txt' if histogram == 'auto' else histogram]
+			k += 2
+		elif word == '--out' and k + 1 < len(argv):
+			out += [word, shiftoutfile]
+			k += 1
+		elif word.startswith('--out='):
+			out.append('--out=' + shiftoutfile)
+		else:
+			out.append(word)
+		k += 1
+	return ' '.join(out)
 
 
 def get_tablekeys(names, name, tablename=''):
@@ -165,7 +224,8 @@ def main(argv=None):
 
 	parser = build_parser()
 	args = parser.parse_args(argv)
-	cmdline = ' '.join(sys.argv if argv is None else ['nway.py'] + list(argv))
+	words = list(sys.argv) if argv is None else ['nway.py'] + list(argv)
+	cmdline = ' '.join(words)
 
 	print('NWAY arguments:')
 	diff_secondary = args.acceptable_prob
@@ -205,7 +265,7 @@ def main(argv=None):
 	if len(pairwise_errs) > 0:
 		print('    pair-wise pre-filtering on')
 		if args.prefilter_mode == 'reference':
-			print('    NOTE: as in nway.py 4.7.1, --prefilter-pair removes EVERY association that contains both catalogues of a pair, whatever their separation; --prefilter-mode fixed applies the radius as documented')
+			sys.stderr.write('NOTE: as in nway.py 4.7.1, --prefilter-pair removes EVERY association that contains both catalogues of a pair, whatever their separation; --prefilter-mode fixed applies the radius as documented\n')
 
 	mag_include_radius = args.mag_radius
 	mag_exclude_radius = args.mag_exclude_radius
@@ -233,9 +293,9 @@ def main(argv=None):
 
 	print('  finding position columns ...')
 	ra_keys = [get_tablekeys(t.columns, 'RA', tablename=n) for t, n in zip(tables, table_names)]
-	print('    using RA  columns: %s' % ', '.join(ra_keys))
+	sys.stderr.write('    using RA  columns: %s\n' % ', '.join(ra_keys))   # fastskymatch.py:249,251 (the matching stage's logger)
 	dec_keys = [get_tablekeys(t.columns, 'DEC', tablename=n) for t, n in zip(tables, table_names)]
-	print('    using DEC columns: %s' % ', '.join(dec_keys))
+	sys.stderr.write('    using DEC columns: %s\n' % ', '.join(dec_keys))
 	print('  building primary_id index ...')
 	primary_id_key = get_tablekeys(tables[0].columns, 'ID', tablename=table_names[0])
 	assert len(numpy.unique(tables[0].data[primary_id_key])) == len(tables[0].data[primary_id_key]), "ERROR: ID column '%s' in primary catalog contains duplicates." % primary_id_key
@@ -255,11 +315,38 @@ def main(argv=None):
 		if magfile == 'auto':
 			d['maghists'].append(None)
 		else:
-			print('    magnitude histogramming: using histogram from "%s" for column "%s_%s"' % (magfile, table_name, col_name))
 			d['maghists'].append(tuple(numpy.loadtxt(magfile).transpose()))
 
 	print('  computing probabilities ...')
-	logger = PrintLogger()
+	logger = TranscriptLogger()
+
+	def transcript(failed=False):
+		"""what nway.py prints between its Bayes-factor loop and the output table (nway.py:364-583), in its order"""
+		if args.consider_unrelated_associations:
+			# the correction runs when some row lacks two or more catalogues (nway.py:366-368): with three or more
+			# catalogues every primary's no-counterpart row does
+			print('    correcting for unrelated associations ...' if len(tables) >= 3 else '      correcting for unrelated associations ... not necessary')
+		if magnitude_columns:
+			print()
+			print('Incorporating magnitude biases ...')
+		for mag, magfile in magnitude_columns:
+			if magfile == 'auto' and mag not in logger.histogram_lines:
+				break   # the run ended at an earlier column
+			print('    magnitude bias "%s" ...' % mag)
+			if magfile == 'auto':
+				if mag_include_radius is not None and mag_include_radius >= match_radius:
+					print('WARNING: magnitude radius is very large (>= matching radius). Consider using a smaller value.')
+				print('\n'.join(logger.histogram_lines[mag]))
+			else:
+				print('    magnitude histogramming: using histogram from "%s" for column "%s"' % (magfile, mag.replace(':', '_')))
+		if failed:
+			return
+		print()
+		print('Computing final probabilities ...')
+		print('    grouping by column "%s" and flagging ...' % (primary_id_key))
+		if logger.truncation_line is not None:
+			print(logger.truncation_line)
+
 	try:
 		cols = nway_b200.nway_match(match_tables, match_radius, prior_completeness,
 			mag_include_radius=mag_include_radius, mag_exclude_radius=mag_exclude_radius,
@@ -269,9 +356,11 @@ def main(argv=None):
 			device=args.device, pairwise_errs=pairwise_errs)
 	except nway_b200.EmptyResultException:
 		raise AssertionError('No matches.')
-	except nway_b200.UndersampledException as e:
-		print(str(e))
+	except nway_b200.UndersampledException:
+		transcript(failed=True)
+		print('ERROR: too few secure matches to make a good histogram. If you are sure you want to use this poorly sampled histogram, replace "auto" with the filename. You can also decrease the mag-auto-minprob parameter.')
 		return 1
+	transcript()
 	nrows = len(cols[table_names[0]])
 	ncats = len(tables)
 
@@ -294,8 +383,6 @@ def main(argv=None):
 		# catalogues every primary's no-counterpart row does
 		if ncats >= 3:
 			columns.append(fitsio.Column('dist_bayesfactor_corrected', 'E', cols['dist_bayesfactor']))
-		else:
-			print('      correcting for unrelated associations ... not necessary')
 	columns.append(fitsio.Column('dist_post', 'E', cols['dist_post']))
 	biases = []
 	for mag, magfile in magnitude_columns:
@@ -316,7 +403,7 @@ def main(argv=None):
 		shiftoutfile = outfile + '-fake.fits'
 		print('      nway-create-fake-catalogue.py --radius %d %s %s' % (args.radius * 2, filenames[0], shiftfile))
 		print('   2) Match the offset catalogue in the same way as this run:')
-		print('      (this command line with %s as the first catalogue, auto replaced by the *_fit.txt files, --out %s)' % (shiftfile, shiftoutfile))
+		print('      ' + offset_run_command(words, filenames[0], shiftfile, shiftoutfile))
 		print('   3) determining the p_any cutoff that corresponds to a false-detection rate')
 		print('      nway-calibrate-cutoff.py %s %s' % (outfile, shiftoutfile))
 		print()

@@ -1,6 +1,6 @@
 """Generate tests/golden/ref_cli_*.npz from the UNMODIFIED reference command-line program (build container only).
 
-    python oracle/make_golden_cli.py
+    python oracle/make_golden_cli.py [--stdout-only]
 
 For every case of tests/cases.CLI_CASES the real /root/reference/nway.py is executed (oracle/refcli.py) on FITS
 files of the COSMOS subset; the digest holds the column names and FITS formats of its output table, the row count,
@@ -108,6 +108,19 @@ def oracle_table(name, paths):
 	return m
 
 
+def transcripts():
+	"""tests/golden/ref_cli_stdout_<case>.txt: what the unmodified nway.py prints to stdout for every case (its progress
+	bars and the matching stage's log go to stderr), with the scratch directory cut out of the file names"""
+	from oracle import refcli, refrun
+	work = tempfile.mkdtemp(prefix='nwb_refcli_')
+	paths = cases.write_cosmos_subset_fits(work)
+	for name in cases.CLI_CASES:
+		tab, log = refcli.run_cli(cases.cli_args(name, paths, name + '.fits'), work)
+		with open(os.path.join(GOLDEN, 'ref_cli_stdout_%s.txt' % name), 'w') as f:
+			f.write(log.replace(work + os.sep, '').replace(os.path.join(refrun.REFERENCE_ROOT, 'nway.py'), 'nway.py'))
+		print('%-16s %d lines of stdout' % (name, len(log.splitlines())))
+
+
 def main():
 	from oracle import refcli, refrun   # the real reference: build container only
 	os.makedirs(GOLDEN, exist_ok=True)
@@ -140,4 +153,8 @@ def main():
 
 
 if __name__ == '__main__':
-	main()
+	if '--stdout-only' in sys.argv:
+		transcripts()
+	else:
+		main()
+		transcripts()

@@ -20,6 +20,16 @@ def load_cli_golden(name):
 	return np.load(os.path.join(parity.GOLDEN, 'ref_cli_%s.npz' % name), allow_pickle=False)
 
 
+def load_cli_transcript(name):
+	"""stdout of the unmodified reference nway.py for the case, as lines (file names without their directory, the program
+	called nway.py)"""
+	return open(os.path.join(parity.GOLDEN, 'ref_cli_stdout_%s.txt' % name)).read().splitlines()
+
+
+def normalise_transcript(text, directory):
+	return text.replace(directory.rstrip(os.sep) + os.sep, '').splitlines()
+
+
 def check_against_cli_digest(name, got, exact=False, check_layout=False, formats=None, header=None):
 	"""got: mapping column -> array (the computed columns and the *_ID columns at least)"""
 	g = load_cli_golden(name)

@@ -31,9 +31,13 @@ def run_cli(name, tmp_path, extra=()):
 
 
 @pytest.mark.parametrize('name', ['cli2', 'cli3', 'cli3_magauto', 'cli3_bayes', 'cli3_minprob', 'cli3_prefilter'])
-def test_cli_against_reference_cli(name, tmp_path):
+def test_cli_against_reference_cli(name, tmp_path, capsys):
 	extra = []   # --prefilter-mode reference is the default: the drop-in entry point returns the reference's rows
 	t, cards = run_cli(name, tmp_path, extra)
+	# stdout, line for line what the unmodified script prints (tests/golden/ref_cli_stdout_*.txt) -- the histogram
+	# populations in it ("... secure matches, ... insecure matches and ... secure non-matches") are counted on the device
+	printed = capsys.readouterr().out
+	assert cliparity.normalise_transcript(printed, str(tmp_path)) == cliparity.load_cli_transcript(name)
 	got = {n: t.data[n] for n in t.columns}
 	report = cliparity.check_against_cli_digest(name, got, check_layout=True, formats=dict(zip(t.columns, t.formats)), header=cards)
 	print('\n'.join(report))

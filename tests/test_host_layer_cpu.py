@@ -167,11 +167,13 @@ def run_cli_host(name, tmp_path, extra=()):
 @pytest.mark.parametrize('name', ['cli2', 'cli3_magauto', 'cli3_bayes', 'cli3_minprob', 'cli3_prefilter'])
 def test_cli_from_argv_to_fits_against_reference_cli(name, tmp_path, hostctx, capsys):
 	"""nway.py's layer (arguments, error columns, the merged input columns, column order and FITS formats, header keys,
-	the FITS writer and reader) around the stand-in: bit for bit the table of the unmodified reference script"""
+	the FITS writer and reader) around the stand-in: bit for bit the table of the unmodified reference script -- and
+	line for line what that script prints to stdout (tests/golden/ref_cli_stdout_*.txt, oracle/make_golden_cli.py)"""
 	t, cards = run_cli_host(name, tmp_path)
+	printed = capsys.readouterr().out
+	assert cliparity.normalise_transcript(printed, str(tmp_path)) == cliparity.load_cli_transcript(name)
 	got = {n: t.data[n] for n in t.columns}
 	cliparity.check_against_cli_digest(name, got, exact=True, check_layout=True, formats=dict(zip(t.columns, t.formats)), header=cards)
 	assert t.name == 'NWAYMATCH' and cards['METHOD'] == 'NWAY multi-way matching'
 	assert cards['NWAYCMD'].startswith('nway.py --radius')
-	out = capsys.readouterr().out
-	assert 'writing "%s" (%d rows, %d columns) ...' % (str(tmp_path / (name + '.fits')), len(t), len(t.columns)) in out
+	assert '    writing "%s" (%d rows, %d columns) ...' % (str(tmp_path / (name + '.fits')), len(t), len(t.columns)) in printed.splitlines()
