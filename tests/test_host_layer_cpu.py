@@ -177,3 +177,33 @@ def test_cli_from_argv_to_fits_against_reference_cli(name, tmp_path, hostctx, ca
 	assert t.name == 'NWAYMATCH' and cards['METHOD'] == 'NWAY multi-way matching'
 	assert cards['NWAYCMD'].startswith('nway.py --radius')
 	assert '    writing "%s" (%d rows, %d columns) ...' % (str(tmp_path / (name + '.fits')), len(t), len(t.columns)) in printed.splitlines()
+
+
+def test_calibration_helpers_from_argv_to_fits(tmp_path, hostctx, capsys):
+	"""nway-create-shifted-catalogue.py / nway-create-fake-catalogue.py (nway_b200/calibrate_cli.py, calibrate.py): the
+	reference's published numbers for the shift (doc/logs/XMM-shift: 561 removed, 1236 left) and the guarantees of the fake
+	catalogue -- same size and columns, every new position at least the radius away from every original and every other new
+	one, inside the footprint"""
+	from nway_b200 import calibrate_cli, fitsio
+	from oracle import nway_oracle as O
+	paths = cases.write_cosmos_subset_fits(str(tmp_path))   # the XMM catalogue is complete in the subset
+	out = str(tmp_path / 'XMM-shift.fits')
+	assert calibrate_cli.shifted_main(['--radius', '40', '--shift-ra', '60', paths['XMM'], out]) == 0
+	printed = capsys.readouterr().out.splitlines()
+	assert printed == ['opening ' + paths['XMM'], '    using RA  column: RA', '    using DEC column: DEC',
+		'removed 561 sources which collide with original positions', 'writing "%s" (1236 rows)' % out]
+	t0, t1 = fitsio.read_table(paths['XMM']), fitsio.read_table(out)
+	assert len(t1) == 1236 and t1.columns == t0.columns and t1.formats == t0.formats and t1.header['SKYAREA'] == 2.0
+	assert np.isin(t1.data['ID'], t0.data['ID']).all() and (t1.data['RA'] > t0.data['RA'].min()).all()
+
+	out = str(tmp_path / 'XMM-fake.fits')
+	assert calibrate_cli.fake_main(['--radius', '40', '--seed', '7', paths['XMM'], out]) == 0
+	t1 = fitsio.read_table(out)
+	assert len(t1) == len(t0) and (t1.data['ID'] == t0.data['ID']).all() and (t1.data['pos_err'] == t0.data['pos_err']).all()
+	ra, dec, fra, fdec = t0.data['RA'], t0.data['DEC'], t1.data['RA'], t1.data['DEC']
+	assert (O.dist((fra[:, None], fdec[:, None]), (ra[None, :], dec[None, :])) * 3600).min() >= 40.0
+	d_self = O.dist((fra[:, None], fdec[:, None]), (fra[None, :], fdec[None, :])) * 3600
+	np.fill_diagonal(d_self, 1e9)
+	assert d_self.min() >= 40.0
+	assert fra.min() >= ra.min() and fra.max() <= ra.max() and fdec.min() >= dec.min() and fdec.max() <= dec.max()
+	assert (np.abs(fra - ra) + np.abs(fdec - dec) > 0).all()
