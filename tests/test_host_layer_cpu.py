@@ -207,3 +207,40 @@ def test_calibration_helpers_from_argv_to_fits(tmp_path, hostctx, capsys):
 	assert d_self.min() >= 40.0
 	assert fra.min() >= ra.min() and fra.max() <= ra.max() and fdec.min() >= dec.min() and fdec.max() <= dec.max()
 	assert (np.abs(fra - ra) + np.abs(fdec - dec) > 0).all()
+
+
+@pytest.mark.parametrize('nfiles', [2, 4])
+def test_match_multiple_and_crossproduct_mirrors(nfiles, tmp_path, hostctx):
+	"""the reference's own test of match_multiple (tests/fastskymatch_test.py:31-72,109-119: seeded uniform float32
+	catalogues on [0, 1] deg, err = 0.03 deg, through FITS files) on nway_b200.fastskymatch's mirror: the merged table's
+	layout and, beyond the reference's `len > 20`, the oracle's row set; crossproduct() returns the same rows"""
+	from nway_b200 import fitsio
+	from nway_b200.fastskymatch import match_multiple, crossproduct, healpix_nside_for, get_healpix_resolution_degrees
+	from nway_b200.logger import NullOutputLogger
+	from oracle import nway_oracle as O
+	np.random.seed(0)
+	files = []
+	for i in range(nfiles):
+		ra, dec = np.random.uniform(size=40), np.random.uniform(size=40)
+		files.append(str(tmp_path / ('test_input_%d.fits' % i)))
+		fitsio.write_table(files[-1], [fitsio.Column('ra', 'E', ra), fitsio.Column('dec', 'E', dec)], 'test_input_%d' % i)
+	tabs = [fitsio.read_table(f) for f in files]
+	names = [t.name for t in tabs]
+	err = 0.03
+	results, columns, header = match_multiple([t.data for t in tabs], names, err, [t.formats for t in tabs], logger=NullOutputLogger())
+	assert [c.name for c in columns][:2 * nfiles] == ['%s_%s' % (n, k) for n in names for k in ('ra', 'dec')]
+	assert [c.name for c in columns][-2:] == ['Separation_max', 'ncat'] and [c.format for c in columns][-2:] == ['E', 'I']
+	assert 'Separation_%s_%s' % (names[1], names[0]) in [c.name for c in columns]   # later catalogue first (fastskymatch.py:298)
+	assert header == dict(COLS_RA=' '.join('%s_ra' % n for n in names), COLS_DEC=' '.join('%s_dec' % n for n in names))
+	radec = [(x.data['ra'].astype(float), x.data['dec'].astype(float)) for x in tabs]
+	mt = O.create_match_table([dict(ra=r, dec=d, error=np.ones(len(r))) for r, d in radec], err * 3600)
+	assert len(results) == len(mt['idx']) > 20
+	for c, name in enumerate(names):
+		assert (results[name] == mt['idx'][:, c]).all()
+	merged = {c.name: c.array for c in columns}
+	absent = mt['idx'][:, 1] == -1
+	assert absent.any() and (merged['%s_ra' % names[1]][absent] == -99).all()   # fastskymatch.py:271-279
+	assert (merged['%s_ra' % names[1]][~absent] == tabs[1].data['ra'][mt['idx'][~absent, 1]]).all()
+	assert (crossproduct(radec, err) == mt['idx']).all()
+	assert healpix_nside_for(15. / 3600) == 8192 and healpix_nside_for(20. / 3600) == 4096   # doc/matching.rst:196
+	assert get_healpix_resolution_degrees(8192) >= 15. / 3600 > get_healpix_resolution_degrees(16384)
