@@ -244,3 +244,52 @@ def test_match_multiple_and_crossproduct_mirrors(nfiles, tmp_path, hostctx):
 	assert (crossproduct(radec, err) == mt['idx']).all()
 	assert healpix_nside_for(15. / 3600) == 8192 and healpix_nside_for(20. / 3600) == 4096   # doc/matching.rst:196
 	assert get_healpix_resolution_degrees(8192) >= 15. / 3600 > get_healpix_resolution_degrees(16384)
+
+
+def test_cli_error_specifications(tmp_path, hostctx, capsys):
+	"""`:major:minor:angle`, `:ra_err:dec_err` and a fixed number as position errors (nway.py:25-98): the error triples the
+	command-line layer builds from the FITS columns, the `_ra` / `_dec` offset columns it adds to the table
+	(fastskymatch.py:299-331) and the lines it prints about them"""
+	from nway_b200 import cli, fitsio
+	from oracle import nway_oracle as O
+	rng = np.random.default_rng(11)
+	tabs = cases.uniform_patch(3, (400, 6000, 5000), (1.0, 0.3, 0.5), 0.05)
+	n0, n1 = len(tabs[0]['ra']), len(tabs[1]['ra'])
+	maj = rng.uniform(0.5, 3, n0); mnr = rng.uniform(0.2, 1, n0) * maj; ang = rng.uniform(0, 180, n0)
+	era = rng.uniform(0.2, 0.6, n1); edec = rng.uniform(0.2, 0.6, n1)
+	files = []
+	for t, extra in zip(tabs, ([('emaj', 'D', maj), ('emin', 'D', mnr), ('eang', 'D', ang)], [('era', 'D', era), ('edec', 'D', edec)], [])):
+		n = len(t['ra'])
+		cols = [fitsio.Column('ID', 'K', np.arange(n) + 100), fitsio.Column('RA', 'D', t['ra']), fitsio.Column('DEC', 'D', t['dec'])]
+		cols += [fitsio.Column(*e) for e in extra]
+		files.append(str(tmp_path / ('%s.fits' % t['name'])))
+		fitsio.write_table(files[-1], cols, t['name'], table_header=[('SKYAREA', t['area'])])
+	out = str(tmp_path / 'ell.fits')
+	assert cli.main(['--radius', '6', '--prior-completeness', '0.9', files[0], ':emaj:emin:eang', files[1], ':era:edec', files[2], '0.5', '--out', out]) == 0
+	printed = capsys.readouterr().out
+	assert '    Position error for "A": found column emaj (for ra_error): Values are [%f..%f]' % (maj.min(), maj.max()) in printed
+	assert '    Position error for "A": found column eang (for ell_angle): Values are [%f..%f]' % (ang.min(), ang.max()) in printed
+	assert '    Position error for "B": found column edec (for dec_error): Values are [%f..%f]' % (edec.min(), edec.max()) in printed
+	assert '    Position error for "C": using fixed value 0.500000' in printed
+	t = fitsio.read_table(out)
+	names = [x['name'] for x in tabs]
+	tabs[0]['error'] = tuple(O.ellipse_from_cli(maj, mnr, ang))
+	tabs[1]['error'] = (era, edec, np.zeros(n1))
+	tabs[2]['error'] = 0.5 * np.ones(len(tabs[2]['ra']))
+	ref = O.nway_match(tabs, 6., 0.9, unrelated_mode='cli', cli_compat=True)
+	assert len(t) == len(ref[names[0]])
+	for nm in names:
+		assert (np.where(ref[nm] >= 0, ref[nm] + 100, -99) == t.data[nm + '_ID']).all()
+	for mine, theirs in (('p_any', 'prob_has_match'), ('p_i', 'prob_this_match'), ('dist_bayesfactor', 'dist_bayesfactor_uncorrected'),
+			('dist_bayesfactor_corrected', 'dist_bayesfactor'), ('Separation_B_A', 'Separation_A_B')):
+		assert np.array_equal(t.data[mine], ref[theirs].astype(np.float32), equal_nan=True), mine
+	cards, _ = fitsio._read_header(open(out, 'rb').read(), 0)
+	assert cards['COLS_ERR'] == 'A_:emaj:emin:eang B_:era:edec C_0.5'   # nway.py:541
+	for b, a in ((1, 0), (2, 0), (2, 1)):
+		k = 'Separation_%s_%s' % (names[b], names[a])
+		i = t.columns.index(k)
+		assert t.columns[i + 1:i + 3] == [k + '_ra', k + '_dec'] and t.formats[i:i + 3] == ['E', 'E', 'E']
+		both = (ref[names[a]] >= 0) & (ref[names[b]] >= 0)
+		sep = np.hypot(t.data[k + '_ra'][both].astype(float), t.data[k + '_dec'][both].astype(float))
+		assert np.allclose(sep, t.data[k][both], rtol=1e-5, atol=1e-5)   # the offsets are the separation's two components
+		assert np.isnan(t.data[k + '_ra'][~both]).all()
