@@ -70,7 +70,10 @@ int nwb_set_stream(nwb_ctx *ctx, void *cuda_stream);
  * (__init__.py:38-48).  mags: m columns of n values, column after column; NaN or -99 = undefined
  * (__init__.py:319,384).  on_device != 0: the pointers are device pointers on the context's device and are
  * used in place (they must stay valid until the next nwb_set_catalogue for c or nwb_destroy); otherwise
- * they are host pointers and are copied (pinned host memory makes the copy asynchronous DMA). */
+ * they are host pointers and are copied (pinned host memory makes the copy asynchronous DMA).
+ * Limits: at most NWB_MAX_CATS catalogues and NWB_MAX_MAGS magnitude columns in total; source indices travel as 32-bit
+ * words inside the match (slots, lists), so a catalogue may hold just under 2^31 sources (2.1e9; 48 GB of coordinates and
+ * errors) -- nwb_match returns NWB_ERR_ARG ("catalogue too large") beyond that; row counts and offsets are 64-bit. */
 int nwb_set_catalogue(nwb_ctx *ctx, int c, int ncat, int64_t n, const double *ra, const double *dec,
 	const double *err, int err_kind, const double *mags, int m, double area, int on_device);
 
