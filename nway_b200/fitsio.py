@@ -3,7 +3,8 @@
 The reference reads its catalogues with astropy (`pyfits.open(f)[1]`, nway.py:174-181) and writes the match
 table with `BinTableHDU.from_columns` + `HDUList.writeto` (nway.py:629-649, fastskymatch.py:345-363).  This
 module covers exactly what that needs: a primary HDU without data followed by ONE BINTABLE extension with
-columns of type L, B, I, J, K, E, D (scalar or fixed-length vectors such as 2E) and fixed-width strings nA --
+columns of type L, B, I, J, K, E, D, C, M (scalar or fixed-length vectors such as 2E), bit arrays nX (carried as their
+bytes) and fixed-width strings nA --
 fixed-width big-endian rows in 2880-byte blocks of 80-character header cards.  TSCALn / TZEROn are applied on read as
 astropy does: the unsigned-integer convention (TSCAL 1, TZERO 2^15 / 2^31 / 2^63; -128 for signed bytes) gives
 uint16 / uint32 / uint64 / int8 columns, which are written back with the same keywords; any other scaling gives a
@@ -21,7 +22,12 @@ import numpy
 BLOCK = 2880
 
 # TFORM letter -> numpy big-endian dtype
-_FORMATS = {'L': 'i1', 'B': 'u1', 'I': '>i2', 'J': '>i4', 'K': '>i8', 'E': '>f4', 'D': '>f8'}
+_FORMATS = {'L': 'i1', 'B': 'u1', 'I': '>i2', 'J': '>i4', 'K': '>i8', 'E': '>f4', 'D': '>f8', 'C': '>c8', 'M': '>c16', 'X': 'u1'}
+
+
+def _elements(rep, letter):
+	"""array elements per row of a column: the repeat count, except for bit arrays (nX: n bits in (n + 7) // 8 bytes)"""
+	return (rep + 7) // 8 if letter == 'X' else rep
 
 
 # the unsigned-integer convention: TFORM letter -> (numpy dtype of the values, TZERO)
@@ -43,10 +49,10 @@ class Column(object):
 		if letter in _UNSIGNED and rep == 1 and src.dtype == numpy.dtype(_UNSIGNED[letter][0]):
 			self.array = numpy.array(src)
 			self.zero = _UNSIGNED[letter][1]
-		elif letter in _FORMATS and rep > 1:
+		elif letter in _FORMATS and _elements(rep, letter) > 1:
 			self.array = numpy.array(src, dtype=numpy.dtype(_FORMATS[letter]).newbyteorder('='))
-			if self.array.ndim != 2 or self.array.shape[1] != rep:
-				raise ValueError('column "%s" (%s) needs an array of shape (rows, %d)' % (name, format, rep))
+			if self.array.ndim != 2 or self.array.shape[1] != _elements(rep, letter):
+				raise ValueError('column "%s" (%s) needs an array of shape (rows, %d)' % (name, format, _elements(rep, letter)))
 		else:
 			self.array = numpy.array(src, dtype=native_dtype(format))
 
@@ -88,7 +94,8 @@ def native_dtype(fmt):
 	if letter not in _FORMATS:
 		raise ValueError('unsupported FITS column format "%s"' % fmt)
 	base = numpy.dtype(_FORMATS[letter]).newbyteorder('=')
-	return base if rep == 1 else numpy.dtype((base, (rep,)))
+	n = _elements(rep, letter)
+	return base if n == 1 else numpy.dtype((base, (n,)))
 
 
 def _disk_dtype(fmt):
@@ -100,7 +107,8 @@ def _disk_dtype(fmt):
 	if letter not in _FORMATS:
 		raise ValueError('unsupported FITS column format "%s"' % fmt)
 	base = numpy.dtype(_FORMATS[letter])
-	return base if rep == 1 else numpy.dtype((base, (rep,)))
+	n = _elements(rep, letter)
+	return base if n == 1 else numpy.dtype((base, (n,)))
 
 
 def _parse_value(v):

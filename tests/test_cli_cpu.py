@@ -86,3 +86,25 @@ def test_fits_unsigned_scaled_and_vector_columns(tmp_path):
 	t2 = fitsio.read_table(path)
 	assert t2.formats[-1] == 'D' and np.array_equal(t2.data['I'], (np.arange(n) - 2) * 0.5 + 10.0)
 	assert fitsio._disk_dtype('1PE(7)').itemsize == 8 and fitsio._disk_dtype('QD').itemsize == 16
+
+
+def test_fits_bit_and_complex_columns(tmp_path):
+	"""columns the match never looks at must not make a catalogue unreadable: bit arrays (nX, carried as their bytes) and
+	complex numbers (C, M) go through the reader, the -99 fill of the merged table and the writer"""
+	from nway_b200 import cli, fitsio
+	n = 6
+	rng = np.random.default_rng(2)
+	cols = [fitsio.Column('ID', 'J', np.arange(n)), fitsio.Column('RA', 'D', rng.uniform(size=n)),
+		fitsio.Column('FLAGS', '12X', rng.integers(0, 255, (n, 2))), fitsio.Column('ONEBIT', '3X', rng.integers(0, 255, n)),
+		fitsio.Column('Z', 'C', rng.normal(size=n) + 1j * rng.normal(size=n)), fitsio.Column('W', '2M', rng.normal(size=(n, 2)) * (1 + 2j))]
+	path = str(tmp_path / 'x.fits')
+	fitsio.write_table(path, cols, 'T')
+	t = fitsio.read_table(path)
+	assert t.formats == ['J', 'D', '12X', '3X', 'C', '2M'] and t.header['NAXIS1'] == 4 + 8 + 2 + 1 + 8 + 32
+	for c in cols:
+		assert t.data[c.name].dtype == c.array.dtype and np.array_equal(t.data[c.name], c.array), c.name
+	idx = {'T': np.array([2, -1, 0])}
+	merged = {c.name: c.array for c in cli.merged_input_columns([t], ['T'], idx)}
+	assert np.array_equal(merged['T_FLAGS'][0], cols[2].array[2]) and merged['T_Z'][1] == -99 and merged['T_RA'][2] == cols[1].array[0]
+	with pytest.raises(ValueError):
+		fitsio.Column('bad', '12X', np.zeros((n, 3)))
