@@ -40,3 +40,33 @@ def test_cuda_arm_refuses_without_a_device():
 		pytest.skip('a device is visible here')
 	res = run('--gpus', '1', '--steps', '1', '--warmup', '0', '--no-cpu')
 	assert res.returncode != 0 and 'no CPU fallback' in (res.stderr + res.stdout)
+
+
+def test_committed_gpu_bench_line_is_consistent():
+	"""the bench line measured on B200 for the committed tree (profiles/r02_last_bench.json): every key of the driver's
+	contract, and the derived numbers follow from the measured ones (value from ms_per_step, roofline.achieved from the
+	algorithmic bytes and the kernel's time, frac from the measured peak); roofline.traffic is there because the ncu capture
+	it comes from was taken from exactly the kernel sources in this tree"""
+	import bench
+	line = json.load(open(os.path.join(ROOT, 'profiles', 'r02_last_bench.json')))
+	for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype',
+			'data', 'config', 'roofline', 'cpu_baseline', 'e2e', 'gpu_launches', 'clocks'):
+		assert k in line, k
+	base = json.load(open(os.path.join(ROOT, 'BASELINE.json')))
+	assert base['metric'].startswith(line['metric']) and line['dtype'] == 'f64' and line['warmup'] >= 3 and line['vs_baseline'] is None
+	rows = line['config']['rows_per_gpu'] * line['n_gpus']
+	assert abs(line['value'] - rows / (line['ms_per_step'] * 1e-3)) <= 1e-6 * line['value']
+	r = line['roofline']
+	assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and r['peak_kind'] == 'measured'
+	assert r['algorithmic_bytes'] == 16 * 10**7 + 16 * line['config']['pairs_per_gpu']   # DESIGN.md section 5: k_pairs
+	assert abs(r['achieved'] - r['algorithmic_bytes'] / (r['kernel_ms'] * 1e-3) / 1e9) <= 1e-6 * r['achieved']
+	assert abs(r['frac'] - r['achieved'] / r['peak']) <= 1e-9
+	assert r['algorithmic_bytes'] <= r['traffic'] <= 1.2 * r['algorithmic_bytes']   # no wasted re-reads
+	traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+	assert traffic['kernel_source_sha256'] == bench.kernel_source_hash()
+	assert r['traffic'] == traffic['kernels']['k_pairs']['dram_bytes_per_launch']
+	e = line['e2e']
+	assert e['h2d_bytes_per_step'] == 8 * 3 * (10**5 + 10**7) and e['d2h_bytes_per_step'] == 96 * line['config']['rows_per_gpu']
+	assert e['value'] < line['value'] and abs(e['value'] - rows / (e['ms_per_step'] * 1e-3)) <= 1e-6 * e['value']
+	assert line['cpu_baseline']['kind'] == 'reference' and line['cpu_baseline']['cores'] == 1
+	assert line['gpu_launches'] > 0 and not set(line['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
