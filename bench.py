@@ -2,15 +2,18 @@
 """bench.py -- candidate associations / second of the nway match-probability path on B200.
 
   python bench.py --gpus N --steps K --warmup W                 this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K --warmup W   the reference's CPU algorithm (oracle port)
+  python bench.py --impl reference --gpus N --steps K --warmup W   the reference's own CPU path: the unmodified
+                                                                nwaylib.nway_match from oracle/_ref (the oracle's port
+                                                                only where that copy is missing), on a bounded sample
 
 A "step" is one full pass of the hot path (grid -> stream secondaries -> lists -> rows + group normalisation)
 over the workload.  N = 1 workload: BASELINE.json configs[2] ("C3": 1e5 x 1e7 uniform on 1 deg^2, r = 5 arcsec,
 circular errors, fp64) -- the configuration BASELINE.md quotes the 1e9 associations/s target on; configs[1]
 (COSMOS 3-catalogue) needs the reference's FITS files, has 1797 primaries and is launch-latency bound, so it is
 a parity-test case (tests/golden), not a bench line.  N > 1: weak scaling -- every rank matches its own block
-of 1e5 primaries against the (replicated) 1e7 secondaries; the only exchange is an all-gather of the per-rank
-row counts (what is needed to place each shard in the global table).
+of 1e5 primaries against the (replicated) 1e7 secondaries; the only exchange of `value` is an all-gather of the per-rank
+row counts (what is needed to place each shard in the global table); `with_table_allgather` is the same step with the
+whole table reassembled on every rank inside the timed region (peer-memory stores, nway_b200.parallel.TableGather).
 
 Prints ONE JSON line (rank 0).
 """
