@@ -1,7 +1,8 @@
-"""Command lines of the calibration helpers, with the reference's arguments and printed lines
-(nway-create-shifted-catalogue.py, nway-create-fake-catalogue.py, nway-calibrate-cutoff.py of the reference); the work
-is in nway_b200/calibrate.py (every collision search is one pass of the GPU match path).  The same-named scripts at
-the repository root call these."""
+"""Command lines of the helper programs around a match, with the reference's arguments and printed lines: the
+calibration loop (nway-create-shifted-catalogue.py, nway-create-fake-catalogue.py, nway-calibrate-cutoff.py; the work is in
+nway_b200/calibrate.py, every collision search is one pass of the GPU match path) and the two pure FITS helpers a run
+starts and ends with (nway-write-header.py: name and sky area of a catalogue; nway-explain.py: the associations of one
+source, as text).  The same-named scripts at the repository root call these."""
 import argparse
 
 SHIFTED_MAIN_DOC = """Create a shifted catalogue for testing the false association rate (arguments of the reference's
@@ -96,4 +97,107 @@ def cutoff_main(argv=None):
 		header='p_any_cutoff selection_efficiency false_selection_rate', fmt='%.6f')
 	print('created table "%s_p_any_cutoffquality.txt"' % args.realfile)
 	print('\n'.join(lines))
+	return 0
+
+
+def write_header_main(argv=None):
+	"""nway-write-header.py <catalogue.fits> <tablename> <skyarea>: the two keywords nway.py needs in a catalogue
+	(nway.py:176-191: the extension's name, SKYAREA in square degrees), set in place -- nothing else of the file changes"""
+	import sys
+	from nway_b200 import fitsio
+	argv = sys.argv[1:] if argv is None else list(argv)
+	if len(argv) != 3:
+		sys.stderr.write("""SYNOPSIS: nway-write-header.py <catalogue.fits> <tablename> <skyarea>
+
+tablename: name of the catalogue
+skyarea: catalogue area in square degrees
+""")
+		return 1
+	path, name, area = argv
+	assert '_' not in name, 'Table name must not contain underscore "_".'
+	t = fitsio.read_table(path)
+	print('current', t.name, 'SKYAREA:', t.header.get('SKYAREA', None))
+	fitsio.set_table_keywords(path, [('EXTNAME', name), ('SKYAREA', float(area))])
+	t = fitsio.read_table(path)
+	print('new    ', t.name, 'SKYAREA:', t.header.get('SKYAREA', None))
+	return 0
+
+
+EXPLAIN_MAIN_DOC = """Explain the associations of one primary source in a match table written by nway.py: whether it has a
+counterpart, and every candidate association with its probability, the catalogues involved and the priors that moved it
+(arguments and printed text of the reference's nway-explain.py; its two plots are not drawn).
+
+Example: nway-explain.py example3.fits 422
+"""
+
+
+def explain_main(argv=None):
+	import numpy
+	from nway_b200 import fitsio
+	parser = argparse.ArgumentParser(description=EXPLAIN_MAIN_DOC, formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+	parser.add_argument('matchcatalogue', type=str, help='nway output catalogue')
+	parser.add_argument('id', type=str, help='ID to explain (from primary catalogue)')
+	args = parser.parse_args(argv)
+	t = fitsio.read_table(args.matchcatalogue)
+	with open(args.matchcatalogue, 'rb') as f:
+		header, _ = fitsio._read_header(f.read(), 0)
+	data = t.data
+	key = header['COL_PRIM']
+	kind = data.dtype[key].kind
+	wanted = int(args.id) if kind in 'iu' else float(args.id) if kind == 'f' else args.id.encode() if kind == 'S' else args.id
+	rows = numpy.flatnonzero(data[key] == wanted)
+	if len(rows) == 0:
+		print('ERROR: ID not found. Was searching for %s == %s' % (key, args.id))
+		return 1
+	group = data[rows]
+	p_any = group['p_any'][0]
+	print('NWAY results for Source %s:' % args.id)
+	print()
+	if p_any > 0.8:
+		print('This source probably has a counterpart (p_any=%.2f)' % p_any)
+	elif p_any < 0.1:
+		print('This source probably does not a counterpart (p_any=%.2f)' % p_any)
+	else:
+		print('It is uncertain if this source has a counterpart (p_any=%.2f)' % p_any)
+	print()
+	print("Assuming it has a counterpart, we have the following possible associations:")
+	print()
+	order = numpy.argsort(group['p_i'])[::-1]
+	# per catalogue, the distinct positions among the group's rows in that order; "absent" (-99) comes first.  The script names
+	# a catalogue in an association only when the row holds the FIRST of them (nway-explain.py:200-205), an empty name when
+	# the catalogue is absent, nothing at all otherwise
+	position_lists = []
+	for col_ra, col_dec in zip(header['COLS_RA'].split(' '), header['COLS_DEC'].split(' ')):
+		seen = [(-99, -99)]
+		for i in order:
+			here = (group[col_ra][i], group[col_dec][i])
+			if here not in seen:
+				seen.append(here)
+		position_lists.append((col_ra, col_dec, seen))
+	priors = [c for c in str(header.get('BIASING', '')).split(', ') if c.strip() != '']
+	for number, i in enumerate(order, 1):
+		parts = []
+		for (col_ra, col_dec, seen), tablename in zip(position_lists, header['TABLES'].split(', ')):
+			k = seen.index((group[col_ra][i], group[col_dec][i]))
+			if k == 0:
+				parts.append('')
+			elif k == 1:
+				parts.append(tablename)
+		flag = group['match_flag'][i]
+		if flag == 0:
+			print('Association %d: probability p_i=%.2f ' % (number, group['p_i'][i]))
+		else:
+			stars = '' if p_any < 0.1 else '**' if flag == 1 else '*' if flag == 2 else ''
+			print('Association %d%s[match_flag==%d]: probability p_i=%.2f ' % (number, stars, flag, group['p_i'][i]))
+		print('     Involved catalogues:  %s ' % '-'.join(parts))
+		for col in priors:
+			bias = group['bias_' + col][i]
+			if bias >= 2:
+				print('     prior %-15s increased the probability (bias_%s=%.2f)' % (col, col, bias))
+			elif bias <= 0.5:
+				print('     prior %-15s decreased the probability (bias_%s=%.2f)' % (col, col, bias))
+		print()
+	print()
+	print("Disclaimer: These results assume that the input (sky densities, positional errors, and priors) are correct.")
+	print()
 	return 0

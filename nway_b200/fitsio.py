@@ -333,3 +333,47 @@ def write_table(path, columns, extname, primary_header=(), table_header=(), comm
 		f.write(_finish(tab))
 		f.write(payload)
 		f.write(b'\0' * pad)
+
+
+def set_table_keywords(path, keywords, ext=1):
+	"""Set header keywords of the table in extension `ext` IN PLACE, leaving every other card and the data bytes as they are
+	(what `f[1].name = ...; f[1].header[...] = ...; f.writeto(path, overwrite=True)` amounts to for nway-write-header.py:19-31).
+	keywords: sequence of (keyword, value).  Returns the previous values (None where the keyword was absent)."""
+	with open(path, 'rb') as f:
+		buf = f.read()
+	pos, ihdu = 0, 0
+	while pos < len(buf):
+		start = pos
+		cards, pos = _read_header(buf, pos)
+		if ihdu == ext:
+			break
+		pos += (_data_size(cards) + BLOCK - 1) // BLOCK * BLOCK
+		ihdu += 1
+	else:
+		raise ValueError('%s: no extension %d' % (path, ext))
+	lines = [buf[k:k + 80].decode('ascii', 'replace') for k in range(start, pos, 80)]
+	end = [k for k, c in enumerate(lines) if c[:8].strip() == 'END'][0]
+	lines = lines[:end]
+	previous = []
+	for key, value in keywords:
+		key = key[:8].upper()
+		previous.append(cards.get(key))
+		if key in cards and cards[key] == value:
+			continue   # says so already: the card stays as it is
+		new = _cards(key, value)
+		at = [k for k, c in enumerate(lines) if c[:8].strip() == key and c[8:10] == '= ']
+		if at:
+			k = at[0]
+			if len(new) == 1 and not isinstance(value, str) and ' / ' in lines[k][10:]:
+				new = [_card(key, value, lines[k][10:].split(' / ', 1)[1].rstrip())]   # a changed number keeps the card's comment
+			stop = k + 1
+			while stop < len(lines) and lines[stop][:8].strip() == 'CONTINUE':   # a long string spans several cards
+				stop += 1
+			lines[k:stop] = new
+		else:
+			lines += new
+	with open(path, 'wb') as f:
+		f.write(buf[:start])
+		f.write(_finish(lines))
+		f.write(buf[pos:])
+	return previous

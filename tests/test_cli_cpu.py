@@ -108,3 +108,35 @@ def test_fits_bit_and_complex_columns(tmp_path):
 	assert np.array_equal(merged['T_FLAGS'][0], cols[2].array[2]) and merged['T_Z'][1] == -99 and merged['T_RA'][2] == cols[1].array[0]
 	with pytest.raises(ValueError):
 		fitsio.Column('bad', '12X', np.zeros((n, 3)))
+
+
+def test_write_header_sets_keywords_in_place(tmp_path, capsys):
+	"""nway-write-header.py: EXTNAME and SKYAREA of a catalogue set in place -- every other card (comments included) and the
+	data bytes stay; a header that outgrows its 2880-byte block moves the data; an unchanged value changes nothing"""
+	from nway_b200 import calibrate_cli, fitsio
+	n = 7
+	path = str(tmp_path / 'cat.fits')
+	fitsio.write_table(path, [fitsio.Column('ID', 'J', np.arange(n)), fitsio.Column('RA', 'D', np.arange(n) * 0.5)], 'OLDNAME',
+		table_header=[('OBSERVER', "it's me"), ('EXPTIME', 12.5)])
+	raw = open(path, 'rb').read()
+	assert calibrate_cli.write_header_main([path, 'XMM', '2']) == 0
+	assert capsys.readouterr().out.splitlines() == ['current OLDNAME SKYAREA: None', 'new     XMM SKYAREA: 2.0']
+	t = fitsio.read_table(path)
+	assert t.name == 'XMM' and t.header['SKYAREA'] == 2.0 and t.header['OBSERVER'] == "it's me" and t.header['EXPTIME'] == 12.5
+	assert np.array_equal(t.data['RA'], np.arange(n) * 0.5) and len(open(path, 'rb').read()) == len(raw)
+	once = open(path, 'rb').read()
+	assert calibrate_cli.write_header_main([path, 'XMM', '2.0']) == 0 and open(path, 'rb').read() == once
+	# a changed number keeps its comment; a long string takes CONTINUE cards; enough new cards push the data into the next block
+	fitsio.set_table_keywords(path, [('XTENSION', 'BINTABLE')])   # unchanged: stays, with its comment
+	assert b"XTENSION= 'BINTABLE' / binary table extension" in open(path, 'rb').read()
+	long_text = 'a long description ' * 8
+	old = fitsio.set_table_keywords(path, [('SKYAREA', 3.5), ('NAXIS2', n), ('NOTE', long_text)] + [('KEY%d' % k, k) for k in range(40)])
+	assert old[:3] == [2.0, n, None]
+	t = fitsio.read_table(path)
+	assert t.header['SKYAREA'] == 3.5 and t.header['NOTE'] == long_text.rstrip() and t.header['KEY39'] == 39
+	assert np.array_equal(t.data['ID'], np.arange(n)) and len(open(path, 'rb').read()) == len(raw) + 2880
+	fitsio.set_table_keywords(path, [('NOTE', 'short')])
+	assert fitsio.read_table(path).header['NOTE'] == 'short' and b'CONTINUE' not in open(path, 'rb').read()
+	assert calibrate_cli.write_header_main([path]) == 1
+	with pytest.raises(AssertionError):
+		calibrate_cli.write_header_main([path, 'X_Y', '1'])

@@ -2,7 +2,7 @@
 the workflow the reference documents (doc/Makefile:41-73) run with THIS repository's command-line programs on the full
 COSMOS catalogues, and every line they print to stdout compared with the logs the reference publishes for the same
 commands (doc/logs/XMM-shift, match2, match2-offset, cutoff2, match2-mag-auto, match2-mag-file, match3-mag-auto, match3,
-match3-offset, match3-mag-file, cutoff3):
+match3-offset, match3-mag-file, cutoff3, prep-XMM, explain):
 argument echo, densities, error columns, the unrelated-association line, histogram populations ("2540 secure matches,
 2541 insecure matches and 557679 secure non-matches ..."), the calibration recipe with its rewritten command line, row and
 column counts of the output table.  The oracle stands in for the library's numeric stages (tests/oraclectx.py), so this
@@ -41,6 +41,13 @@ def test_documented_workflow_prints_the_published_logs(tmp_path, monkeypatch, ca
 		want = published(log)[skip[1]:]
 		assert printed == want, '\n'.join(['%s:' % log] + ['%r\n%r' % (a, b) for a, b in zip(printed, want) if a != b][:6])
 
+	# doc/Makefile:36-38: name and area of a catalogue, written in place (on a copy: the demo files are read-only)
+	import shutil
+	shutil.copy(os.path.join(DOC, 'COSMOS_XMM.fits'), 'prep.fits')
+	before = open('prep.fits', 'rb').read()
+	run(calibrate_cli.write_header_main, ['prep.fits', 'XMM', '2'], 'prep-XMM')
+	assert open('prep.fits', 'rb').read() == before   # the file already said so: not a byte has changed
+
 	two = ['COSMOS_XMM.fits', ':pos_err', 'COSMOS_OPTICAL.fits', '0.1']
 	shifted = ['COSMOS_XMM-shift.fits'] + two[1:]
 	run(calibrate_cli.shifted_main, ['--radius', '40', '--shift-ra', '60', 'COSMOS_XMM.fits', 'COSMOS_XMM-shift.fits'], 'XMM-shift')
@@ -56,6 +63,9 @@ def test_documented_workflow_prints_the_published_logs(tmp_path, monkeypatch, ca
 	assert os.path.exists('IRAC_mag_ch1_fit.txt')
 	three, shifted3 = two + ['COSMOS_IRAC.fits', '0.5'], shifted + ['COSMOS_IRAC.fits', '0.5']
 	run(cli.main, three + ['--out=example3.fits', '--radius', '20'], 'match3')
+	# doc/Makefile:67-68: the associations of source 422 as text (the reference also announces its two plots)
+	assert calibrate_cli.explain_main(['example3.fits', '422']) == 0
+	assert capsys.readouterr().out.splitlines() == [l for l in published('explain') if not l.startswith('plotting to ')]
 	run(cli.main, shifted3 + ['--out=example3-offset.fits', '--radius', '20'], 'match3-offset')
 	run(cli.main, shifted3 + ['--out=example3-mag-offset.fits', '--radius', '20', '--mag', 'OPT:MAG', 'OPT_MAG_fit.txt',
 		'--mag', 'IRAC:mag_ch1', 'IRAC_mag_ch1_fit.txt'], 'match3-mag-file')

@@ -293,3 +293,31 @@ def test_cli_error_specifications(tmp_path, hostctx, capsys):
 		sep = np.hypot(t.data[k + '_ra'][both].astype(float), t.data[k + '_dec'][both].astype(float))
 		assert np.allclose(sep, t.data[k][both], rtol=1e-5, atol=1e-5)   # the offsets are the separation's two components
 		assert np.isnan(t.data[k + '_ra'][~both]).all()
+
+
+def test_explain_reproduces_the_published_known_answer(tmp_path, hostctx, capsys):
+	"""nway-explain.py on the 3-catalogue COSMOS match: the reference publishes the result for XMM source 422
+	(doc/logs/explain:1-19: p_any 0.41; p_i 0.71 / 0.21 / 0.04 / 0.03 / 0.01 with the catalogues involved).  The subset holds
+	every source that can appear in that group (row 368 of the XMM catalogue: ID 369 in the subset's files); its SKYAREA is
+	rescaled so that the source densities are those of the full catalogues (nway-write-header's keyword, set in place)"""
+	from nway_b200 import calibrate_cli, cli, fitsio
+	paths = cases.write_cosmos_subset_fits(str(tmp_path))
+	z = np.load(os.path.join(cases.GOLDEN_DIR, 'cosmos_subset.npz'))
+	for name, path in paths.items():
+		fitsio.set_table_keywords(path, [('SKYAREA', 2.0 * len(z[name + '_ra']) / int(z[name + '_nfull']))])
+	out = str(tmp_path / 'example3.fits')
+	assert cli.main(cases.cli_args('cli3', paths, out)) == 0
+	t = fitsio.read_table(out)
+	capsys.readouterr()
+	assert calibrate_cli.explain_main([out, '369']) == 0
+	lines = capsys.readouterr().out.splitlines()
+	assert lines[:6] == ['NWAY results for Source 369:', '', 'It is uncertain if this source has a counterpart (p_any=0.41)', '',
+		'Assuming it has a counterpart, we have the following possible associations:', '']
+	want = [('Association 1**[match_flag==1]: probability p_i=0.71 ', 'XMM-OPT-IRAC'), ('Association 2: probability p_i=0.21 ', 'XMM'),
+		('Association 3: probability p_i=0.04 ', 'XMM--IRAC'), ('Association 4: probability p_i=0.03 ', 'XMM-OPT-'), ('Association 5: probability p_i=0.01 ', 'XMM-')]
+	for k, (head, names) in enumerate(want):
+		assert lines[6 + 3 * k:9 + 3 * k] == [head, '     Involved catalogues:  %s ' % names, '']
+	assert sum(l.startswith('Association ') for l in lines) == 221 == int((t.data['XMM_ID'] == 369).sum())
+	assert lines[-2] == 'Disclaimer: These results assume that the input (sky densities, positional errors, and priors) are correct.'
+	assert calibrate_cli.explain_main([out, '99999']) == 1
+	assert capsys.readouterr().out.strip() == 'ERROR: ID not found. Was searching for XMM_ID == 99999'
