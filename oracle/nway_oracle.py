@@ -417,47 +417,64 @@ def log_bf_elliptical(sep_ra, sep_dec, pos_errors):
 # --------------------------------------------------------------------------------------
 
 def correct_unrelated_cli(mt, lbf, nu, nu_plus, group_start):
-	"""nway.py:366-421 (circular errors).  For each row missing >= 2 catalogues, add the best
-	positive log-posterior of a sub-association, made only of catalogues the row lacks, found in
-	any row of the same primary with ncat > 2.  The API's version (__init__.py:262-301) is inert
-	 and therefore not restated: API mode == no correction."""
+	"""nway.py:366-421.  For each row missing >= 2 catalogues, add the best positive log-posterior of a
+	sub-association, made only of catalogues the row lacks, found in any row of the same primary with ncat > 2.
+	The API's version (__init__.py:262-301) is inert and therefore not restated: API mode == no correction.
+
+	The script walks rows i and j in two nested Python loops and scores one sub-association at a time; the same numbers
+	are obtained here array-wise: the sub-association of row j depends only on (catalogues row i lacks) x (catalogues row
+	j holds), i.e. on a pair of presence patterns, so for every such pair the log-posteriors of all rows j are one
+	vectorised log_bf call, and "best of the group" is a segmented maximum."""
 	idx = mt['idx']
 	n = idx.shape[1]
 	out = lbf.copy()
+	nrows = len(idx)
+	if nrows == 0 or n < 3:
+		return out
 	ncat = mt['ncat']
-	starts = list(group_start) + [len(idx)]
-	for g in range(len(starts) - 1):
-		lo, hi = starts[g], starts[g + 1]
-		rich = [j for j in range(lo, hi) if ncat[j] > 2]
-		if not rich:
+	present = idx[:, 1:] != -1
+	pattern = (present * (1 << np.arange(n - 1))).sum(axis=1)   # bit k-1 set: catalogue k present
+	starts = np.asarray(group_start, dtype=np.int64)
+	group = np.repeat(np.arange(len(starts)), np.diff(np.concatenate((starts, [nrows]))))
+	rich = ncat > 2
+	full = (1 << (n - 1)) - 1
+	score = {}   # (aug tuple) -> log-posterior of that sub-association for every row holding all of aug (NaN elsewhere)
+
+	def sub_posterior(aug):
+		if aug not in score:
+			rows = np.flatnonzero(rich & present[:, [k - 1 for k in aug]].all(axis=1))
+			val = np.full(nrows, np.nan)
+			if len(rows):
+				pr = nu[aug[0]] / np.prod(nu_plus[list(aug)])
+				if 'off' in mt:   # nway.py:404-411
+					sra = [[mt['off'][(a, b)][0][rows] if a < b else None for b in aug] for a in aug]
+					sde = [[mt['off'][(a, b)][1][rows] if a < b else None for b in aug] for a in aug]
+					errs = [tuple(x[rows] for x in mt['errors'][k]) for k in aug]
+					v = log_bf_elliptical(sra, sde, errs)
+				else:
+					# nway.py:389-392 builds one numpy.array from float32 separations and float64 NaNs: float64
+					p = [[mt['sep'][(a, b)][rows].astype(float) if a < b else None for b in aug] for a in aug]
+					s = [mt['errors'][k][rows] for k in aug]
+					v = log_bf(p, s)
+				val[rows] = v + np.log10(pr)
+			score[aug] = val
+		return score[aug]
+
+	for lacking in range(1, full + 1):   # the catalogues row i lacks, as a bit set
+		missing = [k for k in range(1, n) if (lacking >> (k - 1)) & 1]
+		if len(missing) < 2:
 			continue
-		cache = {}
-		for i in range(lo, hi):
-			if ncat[i] > n - 2:
+		needy = np.flatnonzero((pattern == (full & ~lacking)) & (ncat <= n - 2))
+		if len(needy) == 0:
+			continue
+		best = np.zeros(len(starts))   # per primary: max(0, best sub-association posterior)
+		for holds in np.unique(pattern[rich]):
+			aug = tuple(k for k in missing if (holds >> (k - 1)) & 1)
+			if len(aug) < 2:
 				continue
-			missing = [k for k in range(1, n) if idx[i, k] == -1]
-			best = 0.0
-			for j in rich:
-				aug = tuple(k for k in missing if idx[j, k] != -1)
-				if len(aug) < 2:
-					continue
-				key = (j, aug)
-				if key not in cache:
-					pr = nu[aug[0]] / np.prod(nu_plus[list(aug)])
-					if 'off' in mt:   # nway.py:404-411
-						sra = [[np.array([mt['off'][(a, b)][0][j]]) if a < b else None for b in aug] for a in aug]
-						sde = [[np.array([mt['off'][(a, b)][1][j]]) if a < b else None for b in aug] for a in aug]
-						errs = [tuple(np.array([x[j]]) for x in mt['errors'][k]) for k in aug]
-						val = log_bf_elliptical(sra, sde, errs)[0]
-					else:
-						# nway.py:389-392 builds one numpy.array from float32 separations and float64 NaNs: float64
-						p = [[[float(mt['sep'][(a, b)][j])] if a < b else None for b in aug] for a in aug]
-						s = [[mt['errors'][k][j]] for k in aug]
-						val = log_bf(p, s)[0]
-					cache[key] = float(val + np.log10(pr))
-				best = max(best, cache[key])
-			if best > 0:
-				out[i] += best
+			rows = np.flatnonzero(rich & (pattern == holds))
+			np.maximum.at(best, group[rows], sub_posterior(aug)[rows])
+		out[needy] += best[group[needy]]
 	return out
 
 

@@ -164,7 +164,7 @@ def run_cli_host(name, tmp_path, extra=()):
 	return t, cards
 
 
-@pytest.mark.parametrize('name', ['cli2', 'cli3_magauto', 'cli3_bayes', 'cli3_minprob', 'cli3_prefilter'])
+@pytest.mark.parametrize('name', ['cli2', 'cli3', 'cli3_magauto', 'cli3_bayes', 'cli3_minprob', 'cli3_prefilter'])
 def test_cli_from_argv_to_fits_against_reference_cli(name, tmp_path, hostctx, capsys):
 	"""nway.py's layer (arguments, error columns, the merged input columns, column order and FITS formats, header keys,
 	the FITS writer and reader) around the stand-in: bit for bit the table of the unmodified reference script -- and
