@@ -22,7 +22,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np

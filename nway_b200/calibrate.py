@@ -11,7 +11,6 @@ question is one pass of the GPU match path (k_pairs): the positions to test are 
 positions to avoid the secondary one.  The bookkeeping around it (random draws, great-arc interpolation of O(N)
 points, the 101-point cut-off table) is host numpy, as in the reference.
 """
-from collections import OrderedDict
 
 import numpy
 from numpy import arccos, arctan2, cos, pi, sin, sqrt

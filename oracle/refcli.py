@@ -20,7 +20,6 @@ import io
 import os
 import runpy
 import sys
-import types
 from collections import OrderedDict
 
 import numpy

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-from tests import cases, parity
+from tests import parity
 
 ULP32 = float(np.finfo(np.float32).eps)
 

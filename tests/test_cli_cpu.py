@@ -61,7 +61,6 @@ def test_oracle_cli_mode_against_reference_cli(name, tmp_path):
 def test_fits_unsigned_scaled_and_vector_columns(tmp_path):
 	"""TZERO / TSCAL as astropy applies them (unsigned-integer convention -> uint columns, written back with the same
 	keywords; other scalings -> float64), fixed-length vector columns carried through, variable-length columns left out"""
-	import struct
 	from nway_b200 import fitsio
 	n = 5
 	cols = [fitsio.Column('ID', 'K', np.array([0, 1, 2 ** 63, 2 ** 64 - 1, 7], dtype=np.uint64)),

@@ -1,6 +1,4 @@
 """CPU: the oracle (oracle/nway_oracle.py) against the committed outputs of the REAL reference."""
-import hashlib
-import os
 
 import numpy as np
 import pytest

@@ -4,7 +4,6 @@ Run under torch.distributed.run; rank 0 prints one JSON line per method."""
 import json
 import os
 import sys
-import time
 
 import torch
 import torch.distributed as dist

@@ -3,7 +3,6 @@ alone and concurrently -- what bounds bench.py's end-to-end number at N GPUs (ev
 step).  Run under torch.distributed.run with one rank per GPU; rank 0 prints one JSON line."""
 import json
 import os
-import sys
 import time
 
 import torch
