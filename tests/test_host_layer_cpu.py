@@ -321,3 +321,52 @@ def test_explain_reproduces_the_published_known_answer(tmp_path, hostctx, capsys
 	assert lines[-2] == 'Disclaimer: These results assume that the input (sky densities, positional errors, and priors) are correct.'
 	assert calibrate_cli.explain_main([out, '99999']) == 1
 	assert capsys.readouterr().out.strip() == 'ERROR: ID not found. Was searching for XMM_ID == 99999'
+
+
+def test_reference_api_test_script(tmp_path, hostctx, monkeypatch):
+	"""the reference's API test (nway-apitest.py:17-127) call for call: catalogues read from FITS files (float32 error and
+	magnitude columns handed over as they are), two and three catalogues, automatic histograms by radius and by posterior,
+	then the histogram files the previous call has written -- its assertions (37836 / 387601 rows, the columns a caller
+	relies on) hold for the frames nway_b200.nway_match returns.  The committed subset of the demo catalogues keeps every
+	source that can appear in these matches."""
+	import nway_b200
+	from nway_b200 import fitsio
+	paths = cases.write_cosmos_subset_fits(str(tmp_path))
+	monkeypatch.chdir(tmp_path)
+
+	def table_from_fits(fitsname, poserr_value=None, area=None, magnitude_columns=[]):
+		t = fitsio.read_table(fitsname)
+		ra, dec = t.data['RA'], t.data['DEC']
+		poserr = t.data['pos_err'] if 'pos_err' in t.columns else poserr_value * np.ones(len(ra))
+		mags, maghists, magnames = [], [], []
+		for col_name, magfile in magnitude_columns:
+			mag_all = t.data[col_name].copy()
+			mag_all[mag_all == -99] = np.nan
+			mags.append(mag_all)
+			magnames.append(col_name)
+			maghists.append(None if magfile == 'auto' else tuple(np.loadtxt(magfile).transpose()))
+		return dict(name=t.name, ra=ra, dec=dec, error=poserr, area=t.header['SKYAREA'] * 1.0 if area is None else area, mags=mags, maghists=maghists, magnames=magnames)
+
+	minimum = ['Separation_max', 'ncat', 'dist_bayesfactor', 'dist_post', 'p_single', 'prob_has_match', 'prob_this_match']
+	xmm = lambda: table_from_fits(paths['XMM'], area=2.0)
+	opt = lambda mag=(): table_from_fits(paths['OPT'], poserr_value=0.1, area=2.0, magnitude_columns=[('MAG', m) for m in mag])
+	irac = lambda mag=(): table_from_fits(paths['IRAC'], poserr_value=0.5, area=2.0, magnitude_columns=[('mag_ch1', m) for m in mag])
+	quiet = nway_b200.NullOutputLogger()
+
+	result = nway_b200.nway_match([xmm(), opt()], match_radius=20, prior_completeness=0.9, logger=quiet)
+	assert len(result) == 37836 and all(c in result.columns for c in minimum + ['Separation_XMM_OPT'])
+	result = nway_b200.nway_match([xmm(), opt(['auto'])], match_radius=20, prior_completeness=0.9, store_mag_hists=False, mag_include_radius=4.0, logger=quiet)
+	assert len(result) == 37836 and all(c in result.columns for c in minimum + ['Separation_XMM_OPT', 'bias_OPT_MAG'])
+	assert not os.path.exists('OPT_MAG_fit.txt')
+	result = nway_b200.nway_match([xmm(), opt(['auto'])], match_radius=20, prior_completeness=0.9, mag_include_radius=4.0, logger=quiet)
+	assert len(result) == 37836 and os.path.exists('OPT_MAG_fit.txt')
+	extra = ['Separation_XMM_OPT', 'Separation_OPT_IRAC', 'Separation_XMM_IRAC', 'bias_OPT_MAG', 'bias_IRAC_mag_ch1']
+	auto = nway_b200.nway_match([xmm(), opt(['auto']), irac(['auto'])], match_radius=20, prior_completeness=0.9, logger=quiet)
+	assert len(auto) == 387601 and all(c in auto.columns for c in minimum + extra)
+	assert os.path.exists('IRAC_mag_ch1_fit.txt')
+	filed = nway_b200.nway_match([xmm(), opt(['OPT_MAG_fit.txt']), irac(['IRAC_mag_ch1_fit.txt'])], match_radius=20, prior_completeness=0.9, logger=quiet)
+	assert len(filed) == 387601 and all(c in filed.columns for c in minimum + extra)
+	# beyond the script: the same rows; the histograms read back from their five-decimal files are the ones of the run that
+	# made them up to that rounding (a sparsely filled bin can move a single source's probability by several per cent)
+	diff = np.abs(filed['prob_has_match'] - auto['prob_has_match'])
+	assert (filed['XMM'] == auto['XMM']).all() and (filed['OPT'] == auto['OPT']).all() and np.median(diff) < 1e-4 and diff.max() < 0.2
