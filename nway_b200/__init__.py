@@ -65,8 +65,10 @@ def _scalar_tables(match_tables, prior_completeness, logger):
 	assert numpy.isfinite(prior).all(), (source_densities, prior_completeness, source_densities_plus)
 	log_arcsec2rad = numpy.log(3600 * 180 / pi)
 	norm = numpy.array([(n - 1) * numpy.log(2) + 2 * (n - 1) * log_arcsec2rad for n in range(ncats + 1)])
+	with numpy.errstate(divide='ignore'):   # an empty secondary catalogue has density 0: its sub-association prior is 0, log10 -inf
+		sub_log10prior = log10(sub)
 	return dict(pc=prior_completeness, norm=norm, log10e=float(log10(numpy.e)), prior=prior, log10prior=log10(prior),
-		sub_log10prior=log10(sub))
+		sub_log10prior=sub_log10prior)
 
 
 def _is_triple(error):
