@@ -207,6 +207,19 @@ def allgather_columns(cols, counts, group=None):
 	return out
 
 
+def _table_device(ctx, device):
+	"""the torch device a context's table lives on: CUDA device `device`, unless the context names its own (the CPU tests
+	run this module's host logic over gloo with a context whose tables are host tensors)"""
+	import torch
+	return torch.device(getattr(ctx, 'torch_device', None) or 'cuda:%d' % device)
+
+
+def _wait_for_current_stream(dev):
+	import torch
+	if dev.type == 'cuda':
+		torch.cuda.current_stream(dev).synchronize()
+
+
 def nway_match_sharded(match_tables, match_radius, prior_completeness, gather='all', group=None, device=None, **kwargs):
 	"""nway_match() across the ranks of a torch.distributed process group (one rank per GPU).
 
@@ -234,16 +247,16 @@ def nway_match_sharded(match_tables, match_radius, prior_completeness, gather='a
 		of ALL shards in global row order (one small all-gather-v) -- the selection is a property of the whole table:
 		first occurrence of a source over all rows, the reference's weight indexing (nwaylib/__init__.py:324-366)"""
 		base, stride, ncols, nrows = ctx.table_layout()
-		dev = torch.device('cuda', device)
+		dev = _table_device(ctx, device)
 		counts = exchange_counts(nrows, group, dev)
 		npairs = ncat * (ncat - 1) // 2
 		pick = [c, ncat + npairs, ncat + npairs + 4]   # <name_c>, Separation_max, dist_post in the table's column order
 		view = ctx.table_view()
 		local3 = torch.stack([view[k] for k in pick]) if nrows else torch.empty((3, 0), dtype=torch.int64, device=dev)
-		torch.cuda.current_stream(dev).synchronize()
+		_wait_for_current_stream(dev)
 		ctx.sync()
 		full = allgather_table(local3, counts, group)
-		torch.cuda.current_stream(dev).synchronize()
+		_wait_for_current_stream(dev)
 		held.append(full)   # stays alive while the library reads it
 		return (full.shape[1], full[0].data_ptr(), full[1].data_ptr(), full[2].data_ptr())
 
@@ -251,10 +264,10 @@ def nway_match_sharded(match_tables, match_radius, prior_completeness, gather='a
 	local = nway_match(match_tables, match_radius, prior_completeness, primary_range=(first, count), device=device,
 		allow_empty=True, hist_rows=hist_rows if auto else None, **kwargs)
 	nrows = local['nrows']
-	dev = torch.device('cuda', device)
+	ctx = _lib.get_context(device)
+	dev = _table_device(ctx, device)
 	counts = exchange_counts(nrows, group, dev)
 	offsets = row_offsets(counts)
-	ctx = _lib.get_context(device)
 	names, seps, biases = _column_names(match_tables)
 	int_cols = set(names) | {'ncat', 'match_flag'}
 	colnames = list(local['selectors'].keys())
@@ -266,7 +279,7 @@ def nway_match_sharded(match_tables, match_radius, prior_completeness, gather='a
 
 	if gather == 'none':
 		return to_host(shard), counts, offsets
-	torch.cuda.current_stream(dev).synchronize()   # the context works on its own stream; it has been synchronised by nway_match
+	_wait_for_current_stream(dev)   # the context works on its own stream; it has been synchronised by nway_match
 	full = allgather_table(shard, counts, group, gather=gather)
 	return None if full is None else to_host(full)
 

@@ -8,6 +8,8 @@ Nothing here is measured or shipped, and the product never sees it: a test insta
 
 The stage boundaries are the library's (include/nwayb200.h): set_catalogue / set_params / set_compat / set_prefilter /
 set_maghist -> match(fuse_final) -> [maghist_select / maghist_count -> set_maghist -> finalize] -> truncate -> fetch."""
+import ctypes
+
 import numpy as np
 
 from nway_b200 import _lib as L
@@ -145,10 +147,16 @@ class OracleContext(object):
 
 	# ---- automatic histograms: the device half of nwaylib/__init__.py:324-366 (nwb_maghist_select / _count) ---------------
 	def maghist_select(self, c, k, by_radius, thr_select, thr_possible, weights_cli, rows=None):
-		assert rows is None, 'the gathered rows of several shards need the library'
-		res = self.mt['idx'][:, c]
 		magvals = self.tables[c]['mags'][k]
-		quantity = self.cols[L.COL_SEPMAX] if by_radius else self.cols[L.COL_DIST_POST]
+		if rows is None:
+			res = self.mt['idx'][:, c]
+			quantity = self.cols[L.COL_SEPMAX] if by_radius else self.cols[L.COL_DIST_POST]
+		else:
+			# nwb_maghist_select_rows: three columns of ALL shards' rows, handed over as addresses (nway_b200.parallel.hist_rows)
+			n, res_ptr, sepmax_ptr, post_ptr = rows
+			read = lambda ptr, ctype: np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), (n,)).copy()
+			res = read(res_ptr, ctypes.c_int64)
+			quantity = read(sepmax_ptr if by_radius else post_ptr, ctypes.c_double)
 		defined = res != -1
 		selection = ((quantity < thr_select) if by_radius else (quantity > thr_select)) & defined
 		possible = ((quantity < thr_possible) if by_radius else (quantity > thr_possible)) & defined
@@ -173,6 +181,32 @@ class OracleContext(object):
 		col = self.cols[int(column)]
 		assert len(col) == nrows
 		return np.ascontiguousarray(col, dtype=dtype)
+
+	# ---- the table as nway_b200.parallel reads it: one (ncols, rows) block of 8-byte words in the output column order --------
+	torch_device = 'cpu'
+
+	def _selectors_in_order(self):
+		n = len(self.tables)
+		nbias = sum(len(t['mags']) for t in self.tables)
+		return ([L.COL_IDX + c for c in range(n)] + [L.COL_SEP + k for k in range(n * (n - 1) // 2)] +
+			[L.COL_SEPMAX, L.COL_NCAT, L.COL_LOGBF_UNCORR, L.COL_LOGBF, L.COL_DIST_POST] + [L.COL_BIAS + k for k in range(nbias)] +
+			[L.COL_P_SINGLE, L.COL_MATCH_FLAG, L.COL_P_ANY, L.COL_P_I])
+
+	def table_view(self):
+		import torch
+		sel = self._selectors_in_order()
+		nrows = 0 if self.cols is None else len(self.cols[L.COL_IDX])
+		block = np.zeros((len(sel), nrows), dtype=np.int64)
+		for k, s in enumerate(sel):
+			if self.cols is not None and s in self.cols:   # the columns of the final stage exist after finalize only
+				col = self.cols[s]
+				block[k] = col if col.dtype.kind in 'iu' else np.ascontiguousarray(col, dtype=np.float64).view(np.int64)
+		self._block = torch.from_numpy(block)   # stays alive until the next view, like the library's allocation until the next match
+		return self._block
+
+	def table_layout(self):
+		view = self.table_view()
+		return view.data_ptr(), 8 * view.shape[1], view.shape[0], view.shape[1]
 
 	def row_offsets(self, a, b, nrows):
 		"""(dra, ddec) in arcsec between the members a < b of every row (nwb_row_offsets), NaN where one is absent"""

@@ -142,6 +142,61 @@ def test_world2_setup_failure_on_one_rank_raises_on_every_rank():
 		assert dict(ret) == {0: 'ok', 1: 'ok'}, dict(ret)
 
 
+def sharded_worker(rank, world, port, ret):
+	os.environ['MASTER_ADDR'] = '127.0.0.1'
+	os.environ['MASTER_PORT'] = str(port)
+	dist.init_process_group('gloo', rank=rank, world_size=world)
+	try:
+		import nway_b200
+		from tests import oraclectx, parity
+		ctx = oraclectx.OracleContext()
+		nway_b200._lib.get_context = lambda device=None: ctx   # this process only: the numeric stages on the CPU
+		quiet = dict(logger=nway_b200.NullOutputLogger(), store_mag_hists=False, device=0)
+		# automatic histograms (by posterior, two magnitude columns) are a property of the WHOLE table: every rank selects from
+		# three gathered columns of all shards and must end with the table of the single-device match -- the reference's
+		for name in ('cosmos3_magauto', 'cosmos2_magradius'):
+			spec = cases.GOLDEN_CASES[name]
+			got = parallel.nway_match_sharded(cases.build_case(name), spec['radius'], spec['completeness'], gather='all', **dict(quiet, **spec.get('kwargs', {})))
+			parity.check_against_digest(name, got, [t['name'] for t in cases.build_case(name)])
+			assert ctx.primary_range == parallel.shard_range(len(cases.build_case(name)[0]['ra']), rank, world)
+		# the three ways to hand the table back, a completeness vector, truncation: against the whole match of one context
+		spec = cases.GOLDEN_CASES['syn4_minprob']
+		args = (spec['radius'], spec['completeness'])
+		kw = dict(quiet, **spec['kwargs'])
+		whole = parity.load_golden('ref_syn4_minprob.npz')
+		everywhere = parallel.nway_match_sharded(cases.build_case('syn4_minprob'), *args, gather='all', **kw)
+		parity.check_against_digest('syn4_minprob', everywhere, [t['name'] for t in cases.build_case('syn4_minprob')])
+		at_root = parallel.nway_match_sharded(cases.build_case('syn4_minprob'), *args, gather='rank0', **kw)
+		assert (at_root is None) == (rank != 0)
+		if rank == 0:
+			for c in everywhere:
+				assert np.array_equal(at_root[c], everywhere[c], equal_nan=True), c
+		mine, counts, offsets = parallel.nway_match_sharded(cases.build_case('syn4_minprob'), *args, gather='none', **kw)
+		assert sum(counts) == int(whole['nrows']) == len(everywhere['A']) and offsets[0] == 0 and offsets[1] == counts[0]
+		for c in everywhere:
+			assert np.array_equal(mine[c], everywhere[c][offsets[rank]:offsets[rank] + counts[rank]], equal_nan=True), c
+		ret[rank] = 'ok'
+	except BaseException as e:
+		import traceback
+		ret[rank] = traceback.format_exc()[-1500:]
+	finally:
+		dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_world2_sharded_match_with_automatic_histograms_equals_the_reference():
+	"""nway_b200.parallel.nway_match_sharded itself over gloo, two ranks, the oracle standing in for the library's numeric
+	stages in each (tests/oraclectx.py): shard ranges, the count exchange, the gathered columns the automatic histograms
+	are selected from, the all-gather-v / gather / no gather of the table -- equal to the committed outputs of the
+	unmodified reference.  The same function runs over NCCL on B200 in tests/run_sharded.py."""
+	world = 2
+	port = free_port()
+	with mp.Manager() as mgr:
+		ret = mgr.dict()
+		mp.spawn(sharded_worker, args=(world, port, ret), nprocs=world, join=True)
+		assert dict(ret) == {0: 'ok', 1: 'ok'}, '\n'.join('rank %d: %s' % kv for kv in dict(ret).items())
+
+
 def test_shard_ranges_cover_the_primaries():
 	for n in (0, 1, 7, 100000, 1000003):
 		for world in (1, 2, 3, 8):
