@@ -175,10 +175,18 @@ def _data_size(cards):
 	return size + int(cards.get('PCOUNT', 0))
 
 
-def read_table(path, ext=1):
-	"""the BINTABLE in extension `ext` of a FITS file"""
+def _file_bytes(path):
 	with open(path, 'rb') as f:
 		buf = f.read()
+	if buf[:2] == b'\x1f\x8b':   # gzip, whatever the file is called
+		import gzip
+		buf = gzip.decompress(buf)
+	return buf
+
+
+def read_table(path, ext=1):
+	"""the BINTABLE in extension `ext` of a FITS file (gzip-compressed files are read as astropy reads them: transparently)"""
+	buf = _file_bytes(path)
 	pos = 0
 	ihdu = 0
 	while pos < len(buf):

@@ -32,6 +32,18 @@ def test_fits_roundtrip(tmp_path):
 		F.read_table(path, ext=2)
 
 
+def test_fits_gzip(tmp_path):
+	"""a gzip-compressed catalogue (COSMOS.fits.gz) reads like the plain file"""
+	import gzip
+	from nway_b200 import fitsio as F
+	plain, packed = str(tmp_path / 'c.fits'), str(tmp_path / 'c.fits.gz')
+	F.write_table(plain, [F.Column('ID', 'J', np.arange(9)), F.Column('RA', 'D', np.arange(9) / 7.)], 'CAT', table_header=[('SKYAREA', 0.5)])
+	with open(plain, 'rb') as f, gzip.open(packed, 'wb') as g:
+		g.write(f.read())
+	a, b = F.read_table(plain), F.read_table(packed)
+	assert b.name == 'CAT' and b.header['SKYAREA'] == 0.5 and b.columns == a.columns and (b.data == a.data).all()
+
+
 def test_fits_empty_and_bad_format(tmp_path):
 	from nway_b200 import fitsio as F
 	path = str(tmp_path / 'e.fits')
