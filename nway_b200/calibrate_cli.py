@@ -139,8 +139,7 @@ def explain_main(argv=None):
 	parser.add_argument('id', type=str, help='ID to explain (from primary catalogue)')
 	args = parser.parse_args(argv)
 	t = fitsio.read_table(args.matchcatalogue)
-	with open(args.matchcatalogue, 'rb') as f:
-		header, _ = fitsio._read_header(f.read(), 0)
+	header, _ = fitsio._read_header(fitsio._file_bytes(args.matchcatalogue), 0)
 	data = t.data
 	key = header['COL_PRIM']
 	kind = data.dtype[key].kind
